@@ -1,0 +1,45 @@
+"""ctypes loader for libbppp.so (the CUDA engine + C ABI of include/bppp.h).
+
+There is deliberately no CPU fallback: if the shared library is missing, or no CUDA device is
+present when a context is created, the call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libbppp.so")
+
+EXPORTS = [
+    "bppp_ctx_create", "bppp_ctx_destroy", "bppp_last_error", "bppp_ctx_info", "bppp_u64_commit_batch",
+    "bppp_u64_verify_batch", "bppp_u64_verify_batch_dev", "bppp_u64_prove_batch", "bppp_u64_prove_batch_dev",
+    "bppp_launch_count", "bppp_microbench",
+]
+
+_lib = None
+
+
+class BpppError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise BpppError(f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(SO_PATH)
+        L.bppp_last_error.restype = C.c_char_p
+        L.bppp_launch_count.restype = C.c_uint64
+        L.bppp_launch_count.argtypes = [C.c_void_p]
+        L.bppp_ctx_destroy.argtypes = [C.c_void_p]
+        L.bppp_ctx_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise BpppError(f"{what} failed with {rc}: {lib().bppp_last_error().decode()}")

@@ -1,0 +1,187 @@
+"""Python mirror of the reference's u64 range-proof interface over the C ABI (include/bppp.h)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Sequence, Tuple
+
+from ._lib import BpppError, check, lib
+
+# src/range_proof/u64_proof.rs:12-14
+G_VEC_FULL_SZ = 16
+H_VEC_CIRCUIT_SZ = 26
+H_VEC_FULL_SZ = 32
+
+FMT_COMPRESSED = 0
+FMT_AFFINE64 = 1
+U64_PROOF_BYTES = 525
+U64_PROOF_BYTES_AFFINE = 928
+U64_RNG_BYTES = 52 * 64
+
+ST_FALSE, ST_TRUE = 0, 1
+ST_PANIC_INVERT_ZERO, ST_PANIC_CHALLENGE_RANGE, ST_BAD_POINT, ST_BAD_SCALAR = -1, -2, -3, -4
+
+
+def _in(b: bytes):
+    return (C.c_uint8 * max(len(b), 1)).from_buffer_copy(b if len(b) else b"\0")
+
+
+class Context:
+    """Owns the device-side state of one U64RangeProofProtocol on one GPU (tables + workspace)."""
+
+    def __init__(self, gens64: bytes, device: int = 0, window_bits: int = 0, max_batch: int = 65536):
+        if len(gens64) != 64 * 49:
+            raise ValueError("gens64 must be 49 x 64 bytes: g || g_vec[16] || h_vec[32]")
+        self._h = C.c_void_p()
+        check(lib().bppp_ctx_create(C.byref(self._h), C.c_int(device), _in(gens64), C.c_int(window_bits),
+                                    C.c_size_t(max_batch)), "bppp_ctx_create")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().bppp_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self) -> dict:
+        tb, wb, ms, wbits = C.c_size_t(), C.c_size_t(), C.c_double(), C.c_int()
+        check(lib().bppp_ctx_info(self._h, C.byref(tb), C.byref(wb), C.byref(ms), C.byref(wbits)), "bppp_ctx_info")
+        return {"table_bytes": tb.value, "workspace_bytes": wb.value, "table_build_ms": ms.value,
+                "window_bits": wbits.value}
+
+    def launch_count(self) -> int:
+        return int(lib().bppp_launch_count(self._h))
+
+    # ---- host-buffer entry points ----
+    def commit_batch(self, xs: Sequence[int], blinds32: bytes, fmt: int = FMT_COMPRESSED) -> bytes:
+        n = len(xs)
+        if len(blinds32) != 32 * n:
+            raise ValueError("blinds32 must be n x 32 bytes")
+        osz = 33 if fmt == FMT_COMPRESSED else 64
+        out = (C.c_uint8 * max(osz * n, 1))()
+        xa = (C.c_uint64 * max(n, 1))(*xs)
+        check(lib().bppp_u64_commit_batch(self._h, C.c_size_t(n), xa, _in(blinds32), C.c_int(fmt), out),
+              "bppp_u64_commit_batch")
+        return bytes(out)[:osz * n]
+
+    def verify_batch(self, commits: bytes, proofs: bytes, label: bytes, fmt: int = FMT_COMPRESSED) -> List[int]:
+        csz = 33 if fmt == FMT_COMPRESSED else 64
+        psz = U64_PROOF_BYTES if fmt == FMT_COMPRESSED else U64_PROOF_BYTES_AFFINE
+        n = len(commits) // csz
+        if len(commits) != csz * n or len(proofs) != psz * n:
+            raise ValueError("commits/proofs length mismatch")
+        status = (C.c_int32 * max(n, 1))()
+        check(lib().bppp_u64_verify_batch(self._h, C.c_size_t(n), _in(commits), _in(proofs), C.c_int(fmt), _in(label),
+                                          C.c_size_t(len(label)), status), "bppp_u64_verify_batch")
+        return list(status)[:n]
+
+    def prove_batch(self, xs: Sequence[int], blinds32: bytes, rng: bytes, label: bytes) -> Tuple[bytes, List[int]]:
+        n = len(xs)
+        if len(blinds32) != 32 * n or len(rng) != U64_RNG_BYTES * n:
+            raise ValueError("blinds32 must be n x 32 bytes and rng n x 3328 bytes")
+        xa = (C.c_uint64 * max(n, 1))(*xs)
+        out = (C.c_uint8 * max(U64_PROOF_BYTES * n, 1))()
+        status = (C.c_int32 * max(n, 1))()
+        check(lib().bppp_u64_prove_batch(self._h, C.c_size_t(n), xa, _in(blinds32), _in(rng), _in(label),
+                                         C.c_size_t(len(label)), out, status), "bppp_u64_prove_batch")
+        return bytes(out)[:U64_PROOF_BYTES * n], list(status)[:n]
+
+    # ---- raw-pointer entry points (host numpy/pinned buffers or device pointers) ----
+    def verify_batch_ptr(self, n: int, commits_ptr: int, proofs_ptr: int, label: bytes, status_ptr: int,
+                         fmt: int = FMT_COMPRESSED):
+        check(lib().bppp_u64_verify_batch(self._h, C.c_size_t(n), C.c_void_p(commits_ptr), C.c_void_p(proofs_ptr),
+                                          C.c_int(fmt), _in(label), C.c_size_t(len(label)), C.c_void_p(status_ptr)),
+              "bppp_u64_verify_batch")
+
+    def prove_batch_ptr(self, n: int, xs_ptr: int, blinds_ptr: int, rng_ptr: int, label: bytes, proofs_ptr: int,
+                        status_ptr: int):
+        check(lib().bppp_u64_prove_batch(self._h, C.c_size_t(n), C.c_void_p(xs_ptr), C.c_void_p(blinds_ptr),
+                                         C.c_void_p(rng_ptr), _in(label), C.c_size_t(len(label)),
+                                         C.c_void_p(proofs_ptr), C.c_void_p(status_ptr)), "bppp_u64_prove_batch")
+
+    def verify_batch_dev(self, n: int, d_commits: int, d_proofs: int, label: bytes, d_status: int,
+                         fmt: int = FMT_COMPRESSED, stream: int = 0):
+        check(lib().bppp_u64_verify_batch_dev(self._h, C.c_size_t(n), C.c_void_p(d_commits), C.c_void_p(d_proofs),
+                                              C.c_int(fmt), _in(label), C.c_size_t(len(label)), C.c_void_p(d_status),
+                                              C.c_void_p(stream)), "bppp_u64_verify_batch_dev")
+
+    def prove_batch_dev(self, n: int, d_x: int, d_blinds: int, d_rng: int, label: bytes, d_proofs: int, d_status: int,
+                        stream: int = 0):
+        check(lib().bppp_u64_prove_batch_dev(self._h, C.c_size_t(n), C.c_void_p(d_x), C.c_void_p(d_blinds),
+                                             C.c_void_p(d_rng), _in(label), C.c_size_t(len(label)),
+                                             C.c_void_p(d_proofs), C.c_void_p(d_status), C.c_void_p(stream)),
+              "bppp_u64_prove_batch_dev")
+
+
+class U64RangeProofProtocol:
+    """Mirror of `bp_pp::range_proof::u64_proof::U64RangeProofProtocol` (u64_proof.rs:19-102).
+
+    Points are 64-byte affine `x || y` (what a shim holding k256 points passes), scalars 32-byte
+    big-endian.  `prove` takes the RNG as the byte string the reference's `RngCore` would have produced
+    (52 x 64 bytes).  A panic in the reference surfaces as `BpppError` here.
+    """
+    DIM_ND = 16
+    DIM_NP = 16
+
+    def __init__(self, g: bytes, g_vec: Iterable[bytes], h_vec: Iterable[bytes], device: int = 0, window_bits: int = 0,
+                 max_batch: int = 65536):
+        g_vec, h_vec = list(g_vec), list(h_vec)
+        if len(g_vec) != G_VEC_FULL_SZ or len(h_vec) != H_VEC_FULL_SZ:
+            raise ValueError("g_vec must hold 16 points and h_vec 32")   # the reference indexes out of bounds (panic)
+        self.g, self.g_vec, self.h_vec = g, g_vec, h_vec
+        self.ctx = Context(g + b"".join(g_vec) + b"".join(h_vec), device, window_bits, max_batch)
+
+    # u64_proof.rs:37-39
+    def commit_value(self, x: int, s: bytes) -> bytes:
+        return self.ctx.commit_batch([x], s)
+
+    def commit_batch(self, xs: Sequence[int], blinds32: bytes, fmt: int = FMT_COMPRESSED) -> bytes:
+        return self.ctx.commit_batch(xs, blinds32, fmt)
+
+    # u64_proof.rs:57-82
+    def prove(self, x: int, s: bytes, transcript_label: bytes, rng_bytes: bytes) -> bytes:
+        proofs, status = self.ctx.prove_batch([x], s, rng_bytes, transcript_label)
+        if status[0] != ST_TRUE:
+            raise BpppError(f"prove: the reference would panic here (status {status[0]})")
+        return proofs
+
+    def prove_batch(self, xs: Sequence[int], blinds32: bytes, rng: bytes, transcript_label: bytes):
+        return self.ctx.prove_batch(xs, blinds32, rng, transcript_label)
+
+    # u64_proof.rs:42-54
+    def verify(self, v: bytes, proof: bytes, transcript_label: bytes) -> bool:
+        status = self.ctx.verify_batch(v, proof, transcript_label, FMT_COMPRESSED if len(v) == 33 else FMT_AFFINE64)
+        if status[0] < 0:
+            raise BpppError(f"verify: malformed input or reference panic (status {status[0]})")
+        return status[0] == ST_TRUE
+
+    def verify_batch(self, commits: bytes, proofs: bytes, transcript_label: bytes, fmt: int = FMT_COMPRESSED):
+        return self.ctx.verify_batch(commits, proofs, transcript_label, fmt)
+
+    # u64_proof.rs:84-102
+    @staticmethod
+    def u64_to_hex(x: int) -> List[int]:
+        return [(x >> (4 * i)) & 15 for i in range(16)]
+
+    @staticmethod
+    def u64_to_hex_mapped(x: int) -> List[int]:
+        out = [0] * 16
+        for i in range(16):
+            out[(x >> (4 * i)) & 15] += 1
+        return out
+
+
+def microbench(device: int = 0) -> dict:
+    out = (C.c_double * 8)()
+    check(lib().bppp_microbench(C.c_int(device), out, C.c_int(8)), "bppp_microbench")
+    keys = ["imad_wide_per_s", "fe_mul_per_s", "fe_sqr_per_s", "sc_mul_per_s", "pt_add_mixed_per_s",
+            "pt_double_per_s", "pt_add_per_s", "sm_clock_mhz"]
+    return dict(zip(keys, list(out)))

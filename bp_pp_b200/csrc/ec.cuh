@@ -1,0 +1,229 @@
+// secp256k1 group law for sm_100a: homogeneous projective (X:Y:Z), complete formulas for
+// y^2 = x^3 + 7 (a = 0, b3 = 21; Renes-Costello-Batina 2016) -- branch-free on every input,
+// including P+P, P+(-P) and the identity (0:1:0), which tampered proofs do drive the verifier into.
+//
+// Replaces k256::ProjectivePoint::{add, sub, double, mul, eq, to_affine, to_bytes} as used at
+// reference src/util.rs:40,56,66,75,84, src/wnla.rs:66-72,100-102, src/transcript.rs:6-8.
+// The (X:Y:Z) representative is unobservable; results are compared/serialised in affine form.
+#pragma once
+#include "fe.cuh"
+#include "sc.cuh"
+
+namespace bppp {
+
+struct Pt {   // projective; identity = (0 : 1 : 0)
+    Fe x, y, z;
+};
+struct PtA {  // affine; (0, 0) is the sentinel for the identity (not on the curve)
+    Fe x, y;
+};
+
+BPPP_HD Pt pt_identity() { Pt r; r.x = fe_zero(); r.y = fe_one(); r.z = fe_zero(); return r; }
+BPPP_HD Pt pt_from_affine(const PtA &a, bool is_identity) {
+    Pt r; r.x = a.x; r.y = a.y; r.z = fe_one();
+    if (is_identity) r = pt_identity();
+    return r;
+}
+BPPP_HD Pt pt_neg(const Pt &p) {  // p.y magnitude <= 1
+    Pt r = p; r.y = fe_normalize_weak(fe_negate(p.y, 1)); return r;
+}
+BPPP_HD Pt pt_cmov(const Pt &a, const Pt &b, bool take_b) {
+    Pt r; r.x = fe_cmov(a.x, b.x, take_b); r.y = fe_cmov(a.y, b.y, take_b); r.z = fe_cmov(a.z, b.z, take_b); return r;
+}
+
+// All point routines take coordinates of magnitude 1 and return magnitude 1.
+
+// P + Q, both projective.  12 M + 2 mul-by-21.
+BPPP_HD Pt pt_add(const Pt &p, const Pt &q) {
+    Fe t0 = fe_mul(p.x, q.x);                                  // X1X2
+    Fe t1 = fe_mul(p.y, q.y);                                  // Y1Y2
+    Fe t2 = fe_mul(p.z, q.z);                                  // Z1Z2
+    Fe t3 = fe_mul(fe_add(p.x, p.y), fe_add(q.x, q.y));        // (X1+Y1)(X2+Y2)
+    Fe t4 = fe_mul(fe_add(p.y, p.z), fe_add(q.y, q.z));        // (Y1+Z1)(Y2+Z2)
+    Fe t5 = fe_mul(fe_add(p.x, p.z), fe_add(q.x, q.z));        // (X1+Z1)(X2+Z2)
+    Fe xy = fe_sub(t3, fe_add(t0, t1), 2);                     // X1Y2+X2Y1        mag 4
+    Fe yz = fe_sub(t4, fe_add(t1, t2), 2);                     // Y1Z2+Y2Z1        mag 4
+    Fe xz = fe_sub(t5, fe_add(t0, t2), 2);                     // X1Z2+X2Z1        mag 4
+    Fe x3 = fe_mul_int(t0, 3);                                 // 3 X1X2           mag 3
+    Fe bz = fe_normalize_weak(fe_mul_int(t2, 21));             // b3 Z1Z2          mag 1
+    Fe zp = fe_add(t1, bz);                                    // Y1Y2 + b3Z1Z2    mag 2
+    Fe zm = fe_sub(t1, bz, 1);                                 // Y1Y2 - b3Z1Z2    mag 3
+    Fe bxz = fe_normalize_weak(fe_mul_int(fe_normalize_weak(xz), 21));  // b3 (X1Z2+X2Z1)  mag 1
+    Pt r;
+    r.x = fe_normalize_weak(fe_sub(fe_mul(xy, zm), fe_mul(yz, bxz), 1));       // mag 3 -> 1
+    r.y = fe_normalize_weak(fe_add(fe_mul(zm, zp), fe_mul(x3, bxz)));          // mag 2 -> 1
+    r.z = fe_normalize_weak(fe_add(fe_mul(yz, zp), fe_mul(x3, xy)));           // mag 2 -> 1
+    return r;
+}
+
+// P + Q with Q affine (Z2 = 1, Q != identity).  11 M.
+BPPP_HD Pt pt_add_mixed(const Pt &p, const PtA &q) {
+    Fe t0 = fe_mul(p.x, q.x);                                  // X1X2
+    Fe t1 = fe_mul(p.y, q.y);                                  // Y1Y2
+    Fe t3 = fe_mul(fe_add(p.x, p.y), fe_add(q.x, q.y));
+    Fe xy = fe_sub(t3, fe_add(t0, t1), 2);                     // X1Y2+X2Y1        mag 4
+    Fe yz = fe_add(fe_mul(q.y, p.z), p.y);                     // Y2Z1+Y1          mag 2
+    Fe xz = fe_add(fe_mul(q.x, p.z), p.x);                     // X2Z1+X1          mag 2
+    Fe x3 = fe_mul_int(t0, 3);                                 // mag 3
+    Fe bz = fe_normalize_weak(fe_mul_int(p.z, 21));            // b3 Z1            mag 1
+    Fe zp = fe_add(t1, bz);                                    // mag 2
+    Fe zm = fe_sub(t1, bz, 1);                                 // mag 3
+    Fe bxz = fe_normalize_weak(fe_mul_int(fe_normalize_weak(xz), 21));
+    Pt r;
+    r.x = fe_normalize_weak(fe_sub(fe_mul(xy, zm), fe_mul(yz, bxz), 1));
+    r.y = fe_normalize_weak(fe_add(fe_mul(zm, zp), fe_mul(x3, bxz)));
+    r.z = fe_normalize_weak(fe_add(fe_mul(yz, zp), fe_mul(x3, xy)));
+    return r;
+}
+
+// 2P.  6 M + 2 S.
+BPPP_HD Pt pt_double(const Pt &p) {
+    Fe yy = fe_sqr(p.y);                                       // Y^2
+    Fe zz = fe_sqr(p.z);                                       // Z^2
+    Fe yz = fe_mul(p.y, p.z);
+    Fe xy = fe_mul(p.x, p.y);
+    Fe bzz = fe_normalize_weak(fe_mul_int(zz, 21));            // b3 Z^2           mag 1
+    Fe y8 = fe_mul_int(yy, 8);                                 // 8 Y^2            mag 8
+    Fe t0 = fe_sub(yy, fe_mul_int(bzz, 3), 3);                 // Y^2 - 9b Z^2     mag 5
+    Fe yp = fe_add(yy, bzz);                                   // Y^2 + 3b Z^2     mag 2
+    Pt r;
+    r.x = fe_normalize_weak(fe_mul_int(fe_mul(t0, xy), 2));                    // 2 XY (Y^2 - 9bZ^2)
+    r.y = fe_normalize_weak(fe_add(fe_mul(t0, yp), fe_mul(bzz, y8)));          // + 24 b Y^2 Z^2 = b3Z^2 * 8Y^2
+    r.z = fe_mul(yz, y8);                                                      // 8 Y^3 Z
+    return r;
+}
+
+BPPP_HD bool pt_is_identity(const Pt &p) { return fe_is_zero(p.z); }
+
+// ProjectivePoint::eq -- X1 Z2 == X2 Z1 and Y1 Z2 == Y2 Z1
+BPPP_HD bool pt_equal(const Pt &p, const Pt &q) {
+    Fe a = fe_normalize(fe_sub(fe_mul(p.x, q.z), fe_mul(q.x, p.z), 1));
+    Fe b = fe_normalize(fe_sub(fe_mul(p.y, q.z), fe_mul(q.y, p.z), 1));
+    return fe_is_zero_canonical(a) && fe_is_zero_canonical(b);
+}
+
+// to_affine given zinv = 1/Z (0 for the identity).  Returns canonical coordinates.
+BPPP_HD PtA pt_to_affine_with_zinv(const Pt &p, const Fe &zinv) {
+    PtA r;
+    r.x = fe_normalize(fe_mul(p.x, zinv));
+    r.y = fe_normalize(fe_mul(p.y, zinv));
+    return r;
+}
+// SEC1 compressed bytes (33): identity -> 33 zero bytes [recalled k256 convention]
+BPPP_HD void pta_compress(uint8_t out[33], const PtA &a_canonical, bool is_identity) {
+    uint32_t w[8];
+    fe_to_words(w, a_canonical.x);
+    out[0] = is_identity ? 0 : (uint8_t)(2u + (a_canonical.y.n[0] & 1u));
+    words_to_be32(out + 1, w);
+    if (is_identity) {
+#pragma unroll
+        for (int i = 1; i < 33; i++) out[i] = 0;
+    }
+}
+// on-curve test for canonical affine coordinates
+BPPP_HD bool pta_on_curve(const PtA &a) {
+    Fe lhs = fe_sqr(a.y);
+    Fe rhs = fe_add(fe_mul(fe_sqr(a.x), a.x), fe_from_u32(7));
+    return fe_is_zero(fe_sub(lhs, rhs, 2));
+}
+// SEC1 compressed decode.  Returns 0 ok, 1 identity (all-zero), -1 malformed.
+BPPP_HD int pta_decompress(PtA &r, const uint8_t in[33]) {
+    uint32_t any = 0;
+#pragma unroll
+    for (int i = 0; i < 33; i++) any |= in[i];
+    if (any == 0) { r.x = fe_zero(); r.y = fe_zero(); BPPP_SET_MAG(r.x, 1); BPPP_SET_MAG(r.y, 1); return 1; }
+    if (in[0] != 2 && in[0] != 3) return -1;
+    uint32_t w[8];
+    be32_to_words(w, in + 1);
+    if (words_ge_p(w)) return -1;
+    Fe x = fe_from_words(w);
+    Fe y2 = fe_add(fe_mul(fe_sqr(x), x), fe_from_u32(7));
+    Fe y = fe_sqrt_candidate(y2);
+    if (!fe_is_zero(fe_sub(fe_sqr(y), y2, 2))) return -1;
+    y = fe_normalize(y);
+    if ((y.n[0] & 1u) != (uint32_t)(in[0] & 1u)) y = fe_normalize(fe_negate(y, 1));
+    r.x = x; r.y = y;
+    return 0;
+}
+// 64-byte affine x||y big-endian.  Returns 0 ok, 1 identity (all-zero), -1 malformed / off-curve.
+BPPP_HD int pta_from_xy64(PtA &r, const uint8_t in[64]) {
+    uint32_t wx[8], wy[8];
+    be32_to_words(wx, in); be32_to_words(wy, in + 32);
+    uint32_t any = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) any |= wx[i] | wy[i];
+    r.x = fe_from_words(wx); r.y = fe_from_words(wy);
+    if (any == 0) return 1;
+    if (words_ge_p(wx) || words_ge_p(wy)) return -1;
+    if (!pta_on_curve(r)) return -1;
+    return 0;
+}
+BPPP_HD void pta_to_xy64(uint8_t out[64], const PtA &a_canonical, bool is_identity) {
+    uint32_t w[8];
+    fe_to_words(w, a_canonical.x); words_to_be32(out, w);
+    fe_to_words(w, a_canonical.y); words_to_be32(out + 32, w);
+    if (is_identity) {
+#pragma unroll
+        for (int i = 0; i < 64; i++) out[i] = 0;
+    }
+}
+
+// ---- variable-base scalar multiplication, signed 4-bit fixed windows ----
+// k + C with C = sum_{i<64} 8*16^i gives unsigned nibbles d'_i; the signed digit is d'_i - 8 in [-8, 7]
+// for i < 64, plus an unsigned top digit d'_64 in {0, 1}.  No data-dependent recoding.
+struct Digits4 {
+    uint32_t w[9];   // 65 nibbles of k + C
+};
+BPPP_HD Digits4 sc_signed_digits4(const Sc &k) {
+    Digits4 d;
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (uint64_t)k.v[i] + 0x88888888u; d.w[i] = (uint32_t)c; c >>= 32; }
+    d.w[8] = (uint32_t)c;
+    return d;
+}
+BPPP_HD int digits4_get(const Digits4 &d, int i) {   // i in 0..64 -> signed digit
+    uint32_t nib = (d.w[i >> 3] >> (4 * (i & 7))) & 15u;
+    return i < 64 ? (int)nib - 8 : (int)nib;
+}
+
+// table of 1P..8P for a projective P
+struct PtTable8 {
+    Pt m[8];
+};
+BPPP_HD void pt_table8_build(PtTable8 &t, const Pt &p) {
+    t.m[0] = p;
+    t.m[1] = pt_double(p);
+    t.m[2] = pt_add(t.m[1], p);
+    t.m[3] = pt_double(t.m[1]);
+    t.m[4] = pt_add(t.m[3], p);
+    t.m[5] = pt_double(t.m[2]);
+    t.m[6] = pt_add(t.m[5], p);
+    t.m[7] = pt_double(t.m[3]);
+}
+// signed digit lookup: returns d*P for d in [-8, 8], identity for 0
+BPPP_HD Pt pt_table8_get(const PtTable8 &t, int d) {
+    int a = d < 0 ? -d : d;
+    Pt r = pt_identity();
+    if (a != 0) {
+        r = t.m[a - 1];
+        if (d < 0) r = pt_neg(r);
+    }
+    return r;
+}
+
+// k*P (single point), used by the generic paths and tests
+BPPP_HD Pt pt_mul(const Pt &p, const Sc &k) {
+    PtTable8 tab;
+    pt_table8_build(tab, p);
+    Digits4 dg = sc_signed_digits4(k);
+    Pt acc = pt_table8_get(tab, digits4_get(dg, 64));
+#pragma unroll 1
+    for (int i = 63; i >= 0; i--) {
+        acc = pt_double(acc); acc = pt_double(acc); acc = pt_double(acc); acc = pt_double(acc);
+        acc = pt_add(acc, pt_table8_get(tab, digits4_get(dg, i)));
+    }
+    return acc;
+}
+
+}  // namespace bppp

@@ -1,0 +1,310 @@
+// U64RangeProofProtocol::verify (reference src/range_proof/u64_proof.rs:42-54) for a batch of
+// independent proofs run in lockstep: the per-proof logic of every phase between two multi-scalar
+// multiplications, as host+device functions over the word-major workspace.  The call chain being
+// restated is reciprocal.rs:98-107 -> circuit.rs:154-256 -> wnla.rs:75-121, with the reciprocal
+// circuit's coefficient vectors in closed form (derivation in DESIGN.md):
+//   c_nL[j] = -16^j mu^-(j+1)        c_nR[j] = (S - lambda^(j+1)) mu^-(j+1) + e     c_nO = 0
+//   c_lL[j] = -S / (e + j) (j < 16)  c_lR = c_lO = 0    c_l0[j] = lambda^(j+1)       S = sum_{i=1..16} lambda^i
+// Exact arithmetic => bit-identical to the dense-matrix evaluation of circuit.rs:584-653.
+#pragma once
+#include "ws.cuh"
+
+namespace bppp {
+
+// generator indices in the context: 0 = g, 1..16 = g_vec, 17..48 = h_vec (u64_proof.rs:19-28)
+static constexpr int GEN_G = 0, GEN_GVEC = 1, GEN_HVEC = 17, NUM_GENS = 49;
+
+// input point slots
+enum { VP_V = 0, VP_CL = 1, VP_CR = 2, VP_CO = 3, VP_CS = 4, VP_R = 5 /*r[0..3]*/, VP_X = 9 /*x[0..3]*/, VP_RR = 13, VP_COUNT = 14 };
+
+// word offsets of the per-proof verify record
+struct VL {
+    static constexpr int STATUS = 0;
+    static constexpr int IDMASK = 1;                    // bit k: input point k is the identity; bit 14: V' is
+    static constexpr int PT = 2;                        // 14 affine inputs x 16 words
+    static constexpr int VPA = PT + 16 * VP_COUNT;      // V' = V + r, affine (16)
+    static constexpr int L = VPA + 16;                  // l[2]
+    static constexpr int N = L + 16;                    // n[1]
+    static constexpr int MERLIN = N + 8;                // 51 words (+1 pad)
+    static constexpr int VP = MERLIN + 52;              // V' projective (30)
+    static constexpr int ZINV = VP + 30;                // 10
+    static constexpr int COM = ZINV + 10;               // running WNLA commitment, projective (30)
+    static constexpr int ACC = COM + 30;                // fixed-base MSM result (30)
+    static constexpr int C = ACC + 30;                  // c vector, 32 scalars
+    static constexpr int RHO = C + 256;
+    static constexpr int MU = RHO + 8;
+    static constexpr int Y = MU + 8;                    // y_0..y_3
+    static constexpr int FS = Y + 32;                   // fixed-base scalars (<= 49)
+    static constexpr int VS = FS + 8 * NUM_GENS;        // variable-base scalars (<= 5)
+    static constexpr int WORDS = VS + 40;
+};
+
+enum { FMT_COMPRESSED = 0, FMT_AFFINE64 = 1 };
+static constexpr int U64_PROOF_BYTES_COMPRESSED = 525;          // 13*33 + 3*32 (README.md:30-34)
+static constexpr int U64_PROOF_BYTES_AFFINE = 13 * 64 + 96;     // 928
+
+BPPP_HD void set_status(const WS &w, size_t i, int32_t st) {
+    // sticky: the first error wins
+    int32_t cur = (int32_t)ws_ld(w, i, VL::STATUS);
+    if (cur >= 0) ws_st(w, i, VL::STATUS, (uint32_t)st);
+}
+
+// Phase 0: decode one proof + commitment into the workspace; V' = V + r (projective).
+// Record order (reciprocal::SerializableProof, reciprocal.rs:37-41 / circuit.rs:37-46):
+//   c_l c_r c_o c_s | r[0..3] | x[0..3] | l[0..1] | n[0] | r
+BPPP_HD void u64v_load_one(const WS &w, size_t i, const uint8_t *commit, const uint8_t *proof, int fmt) {
+    const int psz = fmt == FMT_COMPRESSED ? 33 : 64;
+    int32_t status = ST_TRUE;
+    uint32_t idmask = 0;
+    PtA vpt, rpt;
+    bool vid = false, rid = false;
+#pragma unroll 1
+    for (int k = 0; k < VP_COUNT; k++) {
+        const uint8_t *src;
+        if (k == VP_V) src = commit;
+        else if (k == VP_RR) src = proof + 12 * psz + 96;
+        else src = proof + (k - 1) * psz;       // slots 1..12 are the first 12 record points in order
+        PtA a;
+        int s = fmt == FMT_COMPRESSED ? pta_decompress(a, src) : pta_from_xy64(a, src);
+        if (s < 0) { status = ST_BAD_POINT; a.x = fe_zero(); a.y = fe_zero(); BPPP_SET_MAG(a.x, 1); BPPP_SET_MAG(a.y, 1); s = 1; }
+        if (s == 1) idmask |= 1u << k;
+        a.x = fe_normalize(a.x); a.y = fe_normalize(a.y);
+        ws_st_pta(w, i, VL::PT + 16 * k, a);
+        if (k == VP_V) { vpt = a; vid = s == 1; }
+        if (k == VP_RR) { rpt = a; rid = s == 1; }
+    }
+    const uint8_t *sc_src = proof + 12 * psz;
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {
+        Sc s;
+        if (!sc_from_be32(s, sc_src + 32 * k)) { if (status >= 0) status = ST_BAD_SCALAR; s = sc_zero(); }
+        ws_st_sc(w, i, VL::L + 8 * k, s);
+    }
+    Pt vp = pt_add(pt_from_affine(vpt, vid), pt_from_affine(rpt, rid));   // reciprocal.rs:104
+    ws_st_pt(w, i, VL::VP, vp);
+    ws_st(w, i, VL::STATUS, (uint32_t)status);
+    ws_st(w, i, VL::IDMASK, idmask);
+}
+
+// to_affine of a stored projective point with its batch-inverted Z
+BPPP_HD PtA ws_affine(const WS &w, size_t i, int pt_off, int zinv_off, bool &is_identity) {
+    Pt p = ws_ld_pt(w, i, pt_off);
+    Fe zi = ws_ld_fe(w, i, zinv_off);
+    is_identity = fe_is_zero(zi);
+    return pt_to_affine_with_zinv(p, zi);
+}
+
+// Phase 1: transcript up to tau, all challenge-derived scalars for the circuit part.
+// reciprocal.rs:99-100; circuit.rs:155-239 (closed forms, see header).
+BPPP_HD void u64v_phase1_one(const WS &w, size_t i, const Merlin &init) {
+    Merlin m = init;
+    uint32_t idmask = ws_ld(w, i, VL::IDMASK);
+    bool bad = false, zero_inv = false;
+    // reciprocal.rs:99-100
+    PtA V = ws_ld_pta(w, i, VL::PT + 16 * VP_V);
+    merlin_append_point(m, BPPP_LBL("reciprocal_commitment"), V, idmask & (1u << VP_V));
+    Sc e; bad |= !merlin_challenge_scalar(m, BPPP_LBL("reciprocal_challenge"), e);
+    // circuit.rs:155-164
+    bool vp_id;
+    PtA vpa = ws_affine(w, i, VL::VP, VL::ZINV, vp_id);
+    ws_st_pta(w, i, VL::VPA, vpa);
+    if (vp_id) idmask |= 1u << 14;
+    ws_st(w, i, VL::IDMASK, idmask);
+    merlin_append_point(m, BPPP_LBL("commitment_cl"), ws_ld_pta(w, i, VL::PT + 16 * VP_CL), idmask & (1u << VP_CL));
+    merlin_append_point(m, BPPP_LBL("commitment_cr"), ws_ld_pta(w, i, VL::PT + 16 * VP_CR), idmask & (1u << VP_CR));
+    merlin_append_point(m, BPPP_LBL("commitment_co"), ws_ld_pta(w, i, VL::PT + 16 * VP_CO), idmask & (1u << VP_CO));
+    merlin_append_point(m, BPPP_LBL("commitment_v"), vpa, vp_id);
+    Sc rho, lambda, beta, delta, tau;
+    bad |= !merlin_challenge_scalar(m, BPPP_LBL("circuit_rho"), rho);
+    bad |= !merlin_challenge_scalar(m, BPPP_LBL("circuit_lambda"), lambda);
+    bad |= !merlin_challenge_scalar(m, BPPP_LBL("circuit_beta"), beta);
+    bad |= !merlin_challenge_scalar(m, BPPP_LBL("circuit_delta"), delta);
+    // circuit.rs:189-191
+    merlin_append_point(m, BPPP_LBL("commitment_cs"), ws_ld_pta(w, i, VL::PT + 16 * VP_CS), idmask & (1u << VP_CS));
+    bad |= !merlin_challenge_scalar(m, BPPP_LBL("circuit_tau"), tau);
+    ws_st_merlin(w, i, VL::MERLIN, m);
+
+    Sc mu = sc_sqr(rho);
+    // One inversion for {mu, tau, e+0 .. e+15} (Montgomery's trick); delta only has to be non-zero
+    // (circuit.rs:196 unwraps its inverse; c_nO = c_lO = 0 so the value is never used).
+    Sc inv[18], pre[18];
+    inv[0] = mu; inv[1] = tau;
+#pragma unroll 1
+    for (int j = 0; j < 16; j++) inv[2 + j] = sc_add(e, sc_from_u64((uint64_t)j));
+    zero_inv |= sc_is_zero(delta);
+    Sc run = sc_one();
+#pragma unroll 1
+    for (int k = 0; k < 18; k++) {
+        if (sc_is_zero(inv[k])) { zero_inv = true; inv[k] = sc_one(); }
+        pre[k] = run; run = sc_mul(run, inv[k]);
+    }
+    Sc rinv = sc_inv(run);
+#pragma unroll 1
+    for (int k = 17; k >= 0; k--) { Sc t = sc_mul(rinv, pre[k]); rinv = sc_mul(rinv, inv[k]); inv[k] = t; }
+    Sc mu_inv = inv[0], tau_inv = inv[1];
+    Sc tau2 = sc_sqr(tau), tau3 = sc_mul(tau2, tau);
+
+    // S = sum_{k=1..16} lambda^k, lambda powers kept for c_nR and c_l0
+    Sc lp[16];
+    Sc S = sc_zero(), cur = sc_one();
+#pragma unroll 1
+    for (int k = 0; k < 16; k++) { cur = sc_mul(cur, lambda); lp[k] = cur; S = sc_add(S, cur); }
+
+    // pn_tau, ps_tau (circuit.rs:198-204)
+    Sc ps = sc_zero(), musum = sc_zero();
+    Sc mip = sc_one(), mp = sc_one();       // mu^-(j+1), mu^(j+1)
+    Sc p16 = sc_one(), sixteen = sc_from_u64(16);
+#pragma unroll 1
+    for (int j = 0; j < 16; j++) {
+        mip = sc_mul(mip, mu_inv); mp = sc_mul(mp, mu);
+        Sc t1 = sc_mul(sc_mul(p16, mip), tau2);                       // -c_nL[j] tau^2
+        Sc t2 = sc_mul(sc_add(sc_mul(sc_sub(S, lp[j]), mip), e), tau);  // c_nR[j] tau
+        Sc pn = sc_add(t1, t2);
+        ws_st_sc(w, i, VL::FS + 8 * (1 + j), pn);
+        ps = sc_add(ps, sc_mul(sc_sqr(pn), mp));
+        musum = sc_add(musum, mp);
+        p16 = sc_mul(p16, sixteen);
+    }
+    ps = sc_sub(ps, sc_dbl(sc_mul(tau3, musum)));      // a_l = 0, a_m = 1 (reciprocal.rs:159,164)
+    ws_st_sc(w, i, VL::FS, ps);
+
+    // c = cr_tau || cl_tau || 0  (circuit.rs:208-239)
+    Sc bt = sc_mul(beta, tau);
+    ws_st_sc(w, i, VL::C + 0, sc_one());
+    ws_st_sc(w, i, VL::C + 8, sc_mul(tau_inv, beta));
+#pragma unroll 1
+    for (int k = 2; k < 9; k++) { ws_st_sc(w, i, VL::C + 8 * k, bt); bt = sc_mul(bt, tau); }
+    Sc s2 = sc_dbl(sc_mul(tau2, S));
+#pragma unroll 1
+    for (int j = 0; j < 16; j++) ws_st_sc(w, i, VL::C + 8 * (9 + j), sc_sub(sc_mul(s2, inv[2 + j]), lp[j]));
+#pragma unroll 1
+    for (int k = 25; k < 32; k++) ws_st_sc(w, i, VL::C + 8 * k, sc_zero());
+
+    // commitment = pt + tau^-1 c_s - delta c_o + tau c_l - tau^2 c_r + tau^3 (2 V')   (circuit.rs:182-187,230-235)
+    ws_st_sc(w, i, VL::VS + 0, tau_inv);
+    ws_st_sc(w, i, VL::VS + 8, sc_neg(delta));
+    ws_st_sc(w, i, VL::VS + 16, tau);
+    ws_st_sc(w, i, VL::VS + 24, sc_neg(tau2));
+    ws_st_sc(w, i, VL::VS + 32, sc_dbl(tau3));
+    ws_st_sc(w, i, VL::RHO, rho);
+    ws_st_sc(w, i, VL::MU, mu);
+    if (bad) set_status(w, i, ST_PANIC_CHALLENGE_RANGE);
+    if (zero_inv) set_status(w, i, ST_PANIC_INVERT_ZERO);
+}
+
+// joint variable-base sum_k ks[k] * pts[k] + init, signed 4-bit windows, shared doublings
+template <int NP>
+BPPP_HD Pt straus_var(const PtA *pts, const bool *ident, const Sc *ks, const Pt &init) {
+    PtTable8 tab[NP];
+    Digits4 dg[NP];
+#pragma unroll 1
+    for (int k = 0; k < NP; k++) { pt_table8_build(tab[k], pt_from_affine(pts[k], ident[k])); dg[k] = sc_signed_digits4(ks[k]); }
+    Pt acc = pt_identity();   // init is added last (it must not be doubled)
+#pragma unroll 1
+    for (int k = 0; k < NP; k++) acc = pt_add(acc, pt_table8_get(tab[k], digits4_get(dg[k], 64)));
+#pragma unroll 1
+    for (int d = 63; d >= 0; d--) {
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) acc = pt_double(acc);
+#pragma unroll 1
+        for (int k = 0; k < NP; k++) acc = pt_add(acc, pt_table8_get(tab[k], digits4_get(dg[k], d)));
+    }
+    return pt_add(acc, init);
+}
+
+// Phase 2b: com_0 = ACC (fixed part) + tau^-1 c_s - delta c_o + tau c_l - tau^2 c_r + 2 tau^3 V'
+BPPP_HD void u64v_var5_one(const WS &w, size_t i) {
+    uint32_t idmask = ws_ld(w, i, VL::IDMASK);
+    PtA pts[5]; bool ident[5]; Sc ks[5];
+    const int slots[4] = {VP_CS, VP_CO, VP_CL, VP_CR};
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) { pts[k] = ws_ld_pta(w, i, VL::PT + 16 * slots[k]); ident[k] = idmask & (1u << slots[k]); }
+    pts[4] = ws_ld_pta(w, i, VL::VPA); ident[4] = idmask & (1u << 14);
+#pragma unroll 1
+    for (int k = 0; k < 5; k++) ks[k] = ws_ld_sc(w, i, VL::VS + 8 * k);
+    Pt com = straus_var<5>(pts, ident, ks, ws_ld_pt(w, i, VL::ACC));
+    ws_st_pt(w, i, VL::COM, com);
+}
+
+// WNLA round j = 0..3 (wnla.rs:84-102): transcript -> y_j, fold c, scalars for com' = com + y X + (y^2-1) R
+BPPP_HD void u64v_round_one(const WS &w, size_t i, int j) {
+    Merlin m; ws_ld_merlin(m, w, i, VL::MERLIN);
+    uint32_t idmask = ws_ld(w, i, VL::IDMASK);
+    bool com_id;
+    PtA com = ws_affine(w, i, VL::COM, VL::ZINV, com_id);
+    const int xs = VP_X + (3 - j), rs = VP_R + (3 - j);     // proof.x.last(), proof.r.last() (wnla.rs:89-90)
+    merlin_append_point(m, BPPP_LBL("wnla_com"), com, com_id);
+    merlin_append_point(m, BPPP_LBL("wnla_x"), ws_ld_pta(w, i, VL::PT + 16 * xs), idmask & (1u << xs));
+    merlin_append_point(m, BPPP_LBL("wnla_r"), ws_ld_pta(w, i, VL::PT + 16 * rs), idmask & (1u << rs));
+    merlin_append_u64(m, BPPP_LBL("l.sz"), (uint64_t)(32 >> j));    // |h_vec| (wnla.rs:91)
+    merlin_append_u64(m, BPPP_LBL("n.sz"), (uint64_t)(16 >> j));    // |g_vec| (wnla.rs:92)
+    Sc y;
+    if (!merlin_challenge_scalar(m, BPPP_LBL("wnla_challenge"), y)) set_status(w, i, ST_PANIC_CHALLENGE_RANGE);
+    ws_st_merlin(w, i, VL::MERLIN, m);
+    ws_st_sc(w, i, VL::Y + 8 * j, y);
+    const int half = (32 >> j) / 2;
+#pragma unroll 1
+    for (int k = 0; k < half; k++) {     // c' = c0 + y c1 (wnla.rs:98)
+        Sc c0 = ws_ld_sc(w, i, VL::C + 8 * (2 * k)), c1 = ws_ld_sc(w, i, VL::C + 8 * (2 * k + 1));
+        ws_st_sc(w, i, VL::C + 8 * k, sc_add(c0, sc_mul(y, c1)));
+    }
+    ws_st_sc(w, i, VL::VS + 0, y);
+    ws_st_sc(w, i, VL::VS + 8, sc_sub(sc_sqr(y), sc_one()));
+}
+
+// com' = com + y X + (y^2 - 1) R  (wnla.rs:100-102)
+BPPP_HD void u64v_var2_one(const WS &w, size_t i, int j) {
+    uint32_t idmask = ws_ld(w, i, VL::IDMASK);
+    const int xs = VP_X + (3 - j), rs = VP_R + (3 - j);
+    PtA pts[2] = {ws_ld_pta(w, i, VL::PT + 16 * xs), ws_ld_pta(w, i, VL::PT + 16 * rs)};
+    bool ident[2] = {(bool)(idmask & (1u << xs)), (bool)(idmask & (1u << rs))};
+    Sc ks[2] = {ws_ld_sc(w, i, VL::VS), ws_ld_sc(w, i, VL::VS + 8)};
+    Pt com = straus_var<2>(pts, ident, ks, ws_ld_pt(w, i, VL::COM));
+    ws_st_pt(w, i, VL::COM, com);
+}
+
+// Base case (wnla.rs:80-82): scalars of commit(l, n) over the ORIGINAL generators.  After 4 folds
+//   h^(4)_s = sum_t (prod_k y_k^bit_k(t)) h_{16 s + t},  g^(4)_0 = sum_t (prod_k (bit_k(t) ? y_k : rho_k)) g_t
+// with rho_0 = rho, rho_{k+1} = mu_k, mu_{k+1} = mu_k^2 (wnla.rs:96-97,108-109).
+BPPP_HD void u64v_final_scalars_one(const WS &w, size_t i) {
+    Sc y[4], rk[4];
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) y[k] = ws_ld_sc(w, i, VL::Y + 8 * k);
+    Sc mu = ws_ld_sc(w, i, VL::MU);
+    rk[0] = ws_ld_sc(w, i, VL::RHO);
+#pragma unroll 1
+    for (int k = 1; k < 4; k++) { rk[k] = mu; mu = sc_sqr(mu); }
+    mu = sc_sqr(mu);   // mu_4
+    Sc l0 = ws_ld_sc(w, i, VL::L), l1 = ws_ld_sc(w, i, VL::L + 8), n0 = ws_ld_sc(w, i, VL::N);
+    Sc c0 = ws_ld_sc(w, i, VL::C), c1 = ws_ld_sc(w, i, VL::C + 8);
+    // v = <c, l> + |n|^2_mu (wnla.rs:67)
+    Sc v = sc_add(sc_add(sc_mul(c0, l0), sc_mul(c1, l1)), sc_mul(sc_sqr(n0), mu));
+    ws_st_sc(w, i, VL::FS, v);
+    Sc yp[16], gp[16];
+    yp[0] = sc_one(); gp[0] = sc_one();
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        int span = 1 << k;
+#pragma unroll 1
+        for (int t = 0; t < span; t++) {
+            yp[t + span] = sc_mul(yp[t], y[k]);
+            gp[t + span] = sc_mul(gp[t], y[k]);
+            gp[t] = sc_mul(gp[t], rk[k]);
+        }
+    }
+#pragma unroll 1
+    for (int t = 0; t < 16; t++) {
+        ws_st_sc(w, i, VL::FS + 8 * (GEN_GVEC + t), sc_mul(n0, gp[t]));
+        ws_st_sc(w, i, VL::FS + 8 * (GEN_HVEC + t), sc_mul(l0, yp[t]));
+        ws_st_sc(w, i, VL::FS + 8 * (GEN_HVEC + 16 + t), sc_mul(l1, yp[t]));
+    }
+}
+
+// verdict: commitment == commit(l, n)  (wnla.rs:81)
+BPPP_HD void u64v_verdict_one(const WS &w, size_t i) {
+    Pt com = ws_ld_pt(w, i, VL::COM), f = ws_ld_pt(w, i, VL::ACC);
+    int32_t st = (int32_t)ws_ld(w, i, VL::STATUS);
+    if (st >= 0) ws_st(w, i, VL::STATUS, pt_equal(com, f) ? ST_TRUE : ST_FALSE);
+}
+
+}  // namespace bppp

@@ -1,0 +1,155 @@
+// Batch workspace in HBM: word-major structure-of-arrays.  Word w of proof i lives at
+// p[w * n + i], so a warp of 32 consecutive proofs reads/writes 128 contiguous bytes per word
+// (coalesced) no matter which field of the per-proof record it touches.
+#pragma once
+#include "ec.cuh"
+#include "merlin.cuh"
+
+#if !defined(__CUDACC__)
+struct uint4 { uint32_t x, y, z, w; };
+#endif
+
+namespace bppp {
+
+struct WS {
+    uint32_t *p;
+    size_t n;   // proofs in this batch (row stride)
+};
+
+BPPP_HD uint32_t ws_ld(const WS &w, size_t i, int word) { return w.p[(size_t)word * w.n + i]; }
+BPPP_HD void ws_st(const WS &w, size_t i, int word, uint32_t v) { w.p[(size_t)word * w.n + i] = v; }
+
+BPPP_HD Sc ws_ld_sc(const WS &w, size_t i, int off) { Sc r;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.v[k] = ws_ld(w, i, off + k); return r; }
+BPPP_HD void ws_st_sc(const WS &w, size_t i, int off, const Sc &a) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) ws_st(w, i, off + k, a.v[k]); }
+BPPP_HD Fe ws_ld_fe(const WS &w, size_t i, int off) { Fe r;
+#pragma unroll
+    for (int k = 0; k < 10; k++) r.n[k] = ws_ld(w, i, off + k);
+    BPPP_SET_MAG(r, 1); return r; }
+BPPP_HD void ws_st_fe(const WS &w, size_t i, int off, const Fe &a) {
+#pragma unroll
+    for (int k = 0; k < 10; k++) ws_st(w, i, off + k, a.n[k]); }
+BPPP_HD Pt ws_ld_pt(const WS &w, size_t i, int off) { Pt r; r.x = ws_ld_fe(w, i, off); r.y = ws_ld_fe(w, i, off + 10); r.z = ws_ld_fe(w, i, off + 20); return r; }
+BPPP_HD void ws_st_pt(const WS &w, size_t i, int off, const Pt &a) { ws_st_fe(w, i, off, a.x); ws_st_fe(w, i, off + 10, a.y); ws_st_fe(w, i, off + 20, a.z); }
+// affine point stored as 16 canonical words (x[8], y[8]); (0,0) = identity sentinel
+BPPP_HD PtA ws_ld_pta(const WS &w, size_t i, int off) {
+    uint32_t x[8], y[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { x[k] = ws_ld(w, i, off + k); y[k] = ws_ld(w, i, off + 8 + k); }
+    PtA r; r.x = fe_from_words(x); r.y = fe_from_words(y); return r;
+}
+BPPP_HD void ws_st_pta(const WS &w, size_t i, int off, const PtA &a_canonical) {
+    uint32_t x[8], y[8];
+    fe_to_words(x, a_canonical.x); fe_to_words(y, a_canonical.y);
+#pragma unroll
+    for (int k = 0; k < 8; k++) { ws_st(w, i, off + k, x[k]); ws_st(w, i, off + 8 + k, y[k]); }
+}
+BPPP_HD void ws_ld_merlin(Merlin &m, const WS &w, size_t i, int off) {
+#pragma unroll
+    for (int k = 0; k < 25; k++) m.st[k] = (uint64_t)ws_ld(w, i, off + 2 * k) | ((uint64_t)ws_ld(w, i, off + 2 * k + 1) << 32);
+    uint32_t pp = ws_ld(w, i, off + 50);
+    m.pos = pp & 0xFFu; m.pos_begin = (pp >> 8) & 0xFFu; m.cur_flags = (pp >> 16) & 0xFFu; m._pad = 0;
+}
+BPPP_HD void ws_st_merlin(const WS &w, size_t i, int off, const Merlin &m) {
+#pragma unroll
+    for (int k = 0; k < 25; k++) { ws_st(w, i, off + 2 * k, (uint32_t)m.st[k]); ws_st(w, i, off + 2 * k + 1, (uint32_t)(m.st[k] >> 32)); }
+    ws_st(w, i, off + 50, m.pos | (m.pos_begin << 8) | (m.cur_flags << 16));
+}
+
+// absorb an affine point (canonical coords) as the reference's app_point does (transcript.rs:6-8)
+BPPP_HD void merlin_append_point(Merlin &m, const char *label, uint32_t label_len, const PtA &a_canonical, bool is_identity) {
+    uint8_t b[33];
+    pta_compress(b, a_canonical, is_identity);
+    merlin_append(m, label, label_len, b, 33);
+}
+// get_challenge (transcript.rs:10-14): 32 bytes big-endian -> scalar; false when >= n (reference panics)
+BPPP_HD bool merlin_challenge_scalar(Merlin &m, const char *label, uint32_t label_len, Sc &out) {
+    uint8_t b[32];
+    merlin_challenge(m, label, label_len, b, 32);
+    return sc_from_be32(out, b);
+}
+
+// status codes shared by the device code, the C ABI (include/bppp.h) and the oracle
+enum : int32_t {
+    ST_FALSE = 0, ST_TRUE = 1,
+    ST_PANIC_INVERT_ZERO = -1,     // reference: Scalar::invert().unwrap() on zero
+    ST_PANIC_CHALLENGE_RANGE = -2, // reference: Scalar::from_repr(..).unwrap() on >= n (transcript.rs:13)
+    ST_BAD_POINT = -3,             // encoding is not a curve point (reference: deserialisation error)
+    ST_BAD_SCALAR = -4,            // scalar >= n (a k256::Scalar cannot hold it)
+    ST_BAD_ARG = -5,
+};
+
+// ---- fixed-base tables ----
+// tab[((g * nwin + w) * (2^W - 1) + (d - 1))] = d * 2^(W w) * G_g, affine, 16 words (x[8], y[8]); zero = identity
+struct FixedTable {
+    const uint4 *tab;
+    int W;       // window bits (1..16)
+    int nwin;    // ceil(256 / W)
+    int ngens;
+};
+
+BPPP_HD uint32_t scalar_window(const WS &w, size_t i, int sc_off, int win, int W) {
+    int bit = win * W;
+    int word = bit >> 5, sh = bit & 31;
+    uint32_t lo = ws_ld(w, i, sc_off + word);
+    uint64_t v = lo;
+    if (sh + W > 32 && word + 1 < 8) v |= (uint64_t)ws_ld(w, i, sc_off + word + 1) << 32;
+    return (uint32_t)(v >> sh) & ((1u << W) - 1u);
+}
+
+BPPP_HD bool table_load(PtA &q, const FixedTable &T, int g, int win, uint32_t d) {
+    size_t idx = ((size_t)(g * T.nwin + win) * ((1u << T.W) - 1u) + (d - 1)) * 4;
+    uint4 a = T.tab[idx], b = T.tab[idx + 1], c = T.tab[idx + 2], e = T.tab[idx + 3];
+    uint32_t x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t y[8] = {c.x, c.y, c.z, c.w, e.x, e.y, e.z, e.w};
+    q.x = fe_from_words(x); q.y = fe_from_words(y);
+    uint32_t any = a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w | c.x | c.y | c.z | c.w | e.x | e.y | e.z | e.w;
+    return any != 0;
+}
+
+// One lane's share of sum_t scalar_t * G_{gen(t)}: items (t, win) are dealt round-robin to `nlanes` lanes.
+// scalars: T consecutive Sc in the workspace starting at word sc_off; term_gen[t] = generator index.
+BPPP_HD Pt msm_fixed_lane(const FixedTable &T, const WS &w, size_t i, int sc_off, const int *term_gen, int nterms, int lane, int nlanes) {
+    Pt acc = pt_identity();
+    int items = nterms * T.nwin;
+#pragma unroll 1
+    for (int it = lane; it < items; it += nlanes) {
+        int t = it / T.nwin, win = it - t * T.nwin;
+        uint32_t d = scalar_window(w, i, sc_off + 8 * t, win, T.W);
+        if (d != 0) {
+            PtA q;
+            if (table_load(q, T, term_gen[t], win, d)) acc = pt_add_mixed(acc, q);
+        }
+    }
+    return acc;
+}
+
+}  // namespace bppp
+
+namespace bppp {
+// Montgomery batch inversion of the Fe field at word offset in_off into out_off for the items
+// t, t + T, t + 2T, ... < n (one thread's strided share, coalesced across threads): one fe_inv per
+// share instead of one per item.  Zero inputs (identity points) produce zero outputs.
+BPPP_HD void batch_inv_strided(const WS &w, int in_off, int out_off, size_t t, size_t T, size_t n) {
+    Fe run = fe_one();
+#pragma unroll 1
+    for (size_t idx = t; idx < n; idx += T) {
+        Fe z = ws_ld_fe(w, idx, in_off);
+        ws_st_fe(w, idx, out_off, run);                 // prefix product before this item
+        if (!fe_is_zero(z)) run = fe_mul(run, z);
+    }
+    Fe rinv = fe_inv(run);
+    size_t cnt = n > t ? (n - t + T - 1) / T : 0;
+#pragma unroll 1
+    for (size_t k = cnt; k-- > 0;) {
+        size_t idx = t + k * T;
+        Fe z = ws_ld_fe(w, idx, in_off);
+        Fe pre = ws_ld_fe(w, idx, out_off);
+        if (fe_is_zero(z)) { Fe zero = fe_zero(); ws_st_fe(w, idx, out_off, zero); }
+        else { ws_st_fe(w, idx, out_off, fe_mul(rinv, pre)); rinv = fe_mul(rinv, z); }
+    }
+}
+}  // namespace bppp

@@ -1,0 +1,106 @@
+/*
+ * bppp.h -- C ABI of the B200-native Bulletproofs++ engine (libbppp.so).
+ *
+ * This is the drop-in boundary for the hot path of distributed-lab/bp-pp: every entry point is what
+ * a Rust shim for the reference's public API would bind over `extern "C"`.
+ * The reference has no FFI of its own; each function cites the reference item it replaces
+ * (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   scalars   32 bytes big-endian, canonical (< n)  -- k256::Scalar::to_bytes / from_repr
+ *   points    BPPP_FMT_COMPRESSED: 33-byte SEC1 compressed (identity = 33 zero bytes), the form
+ *             GroupEncoding::to_bytes yields (src/transcript.rs:7) and serde uses for AffinePoint;
+ *             BPPP_FMT_AFFINE64: 64 bytes x||y big-endian (identity = 64 zero bytes), what a shim holding
+ *             k256::AffinePoint passes without a square root on the device.
+ *   u64 proof one record in reciprocal::SerializableProof field order
+ *             (src/range_proof/reciprocal.rs:37-41, src/circuit.rs:37-46):
+ *               c_l c_r c_o c_s | r[0..4) | x[0..4) | l[0..2) | n[0..1) | r
+ *             r[]/x[] in the reference's push order, innermost WNLA round first (src/wnla.rs:186-188).
+ *             525 bytes compressed, 928 bytes with 64-byte points.
+ *   rng       the reference is generic over RngCore (src/circuit.rs:260-263); the ABI takes the bytes the
+ *             RNG would have produced: 52 draws x 64 bytes per u64 proof, in draw order,
+ *             each draw reduced as Scalar::generate_biased does (big-endian 512 bit mod n).
+ *   status    per proof, int32: 1 = verify true / proved, 0 = verify false, < 0 = BPPP_ST_* (the
+ *             reference would have panicked or failed to deserialise).  Functions return 0 or BPPP_ERR_*
+ *             and never unwind.
+ *   buffers   caller-owned.  `_dev` variants take device pointers valid on the context's GPU and a
+ *             CUDA stream handle (cudaStream_t as void*), enqueue work and return without synchronising.
+ *   threading a context is single-owner (one host thread per context / GPU).
+ */
+#ifndef BPPP_H
+#define BPPP_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bppp_ctx bppp_ctx;
+
+enum { BPPP_FMT_COMPRESSED = 0, BPPP_FMT_AFFINE64 = 1 };
+
+enum {
+    BPPP_ST_FALSE = 0,
+    BPPP_ST_TRUE = 1,
+    BPPP_ST_PANIC_INVERT_ZERO = -1,     /* reference: Scalar::invert().unwrap() on zero */
+    BPPP_ST_PANIC_CHALLENGE_RANGE = -2, /* reference: from_repr().unwrap(), src/transcript.rs:13 */
+    BPPP_ST_BAD_POINT = -3,             /* not a curve point: the reference fails at deserialisation */
+    BPPP_ST_BAD_SCALAR = -4,            /* >= n: not representable as k256::Scalar */
+    BPPP_ST_BAD_ARG = -5
+};
+
+enum {
+    BPPP_OK = 0,
+    BPPP_ERR_ARG = -10,
+    BPPP_ERR_NO_DEVICE = -11,  /* no CUDA device: there is deliberately no CPU fallback */
+    BPPP_ERR_CUDA = -12,
+    BPPP_ERR_GENERATOR = -13,  /* a generator is not a curve point */
+    BPPP_ERR_NOMEM = -14
+};
+
+#define BPPP_U64_NUM_GENS 49        /* g, g_vec[16], h_vec[32]: src/range_proof/u64_proof.rs:12-14,19-28 */
+#define BPPP_U64_PROOF_BYTES 525    /* 13 points + 3 scalars, README.md:30-34 */
+#define BPPP_U64_PROOF_BYTES_AFFINE 928
+#define BPPP_U64_RNG_BYTES 3328     /* 52 draws x 64 bytes */
+
+/* Context for U64RangeProofProtocol { g, g_vec[16], h_vec[32] } (src/range_proof/u64_proof.rs:19-28) on
+ * CUDA device `device`.  gens64 = g || g_vec || h_vec as 49 x 64-byte affine points.  Builds the
+ * fixed-base window tables on the device (window_bits in 4..16; 0 = default 16) and a workspace for
+ * `max_batch` proofs per launch sequence (larger batches are processed in slices). */
+int bppp_ctx_create(bppp_ctx **out, int device, const uint8_t *gens64, int window_bits, size_t max_batch);
+void bppp_ctx_destroy(bppp_ctx *ctx);
+const char *bppp_last_error(void);
+/* bytes of device memory held by the context (tables + workspace), build time of the tables in ms */
+int bppp_ctx_info(const bppp_ctx *ctx, size_t *table_bytes, size_t *workspace_bytes, double *table_build_ms, int *window_bits);
+
+/* U64RangeProofProtocol::commit_value (src/range_proof/u64_proof.rs:37-39): out[i] = x[i]*g + s[i]*h_vec[0] */
+int bppp_u64_commit_batch(bppp_ctx *ctx, size_t n, const uint64_t *x, const uint8_t *blinds32, int fmt, uint8_t *out);
+
+/* U64RangeProofProtocol::verify (src/range_proof/u64_proof.rs:42-54) over n independent proofs, each with
+ * a fresh merlin::Transcript::new(label).  commits: n points, proofs: n records (format `fmt`). */
+int bppp_u64_verify_batch(bppp_ctx *ctx, size_t n, const uint8_t *commits, const uint8_t *proofs, int fmt,
+                          const uint8_t *label, size_t label_len, int32_t *status);
+int bppp_u64_verify_batch_dev(bppp_ctx *ctx, size_t n, const void *d_commits, const void *d_proofs, int fmt,
+                              const uint8_t *label, size_t label_len, void *d_status, void *stream);
+
+/* U64RangeProofProtocol::prove (src/range_proof/u64_proof.rs:57-82) over n independent witnesses.
+ * rng: n x 3328 bytes.  proofs_out: n x 525-byte records (always compressed). */
+int bppp_u64_prove_batch(bppp_ctx *ctx, size_t n, const uint64_t *x, const uint8_t *blinds32, const uint8_t *rng,
+                         const uint8_t *label, size_t label_len, uint8_t *proofs_out, int32_t *status);
+int bppp_u64_prove_batch_dev(bppp_ctx *ctx, size_t n, const void *d_x, const void *d_blinds32, const void *d_rng,
+                             const uint8_t *label, size_t label_len, void *d_proofs_out, void *d_status, void *stream);
+
+/* number of kernels launched by this context since creation (for the bench's gpu_launches claim) */
+uint64_t bppp_launch_count(const bppp_ctx *ctx);
+
+/* Integer-pipe microbenchmarks on `device`: fills out[0..8) with
+ *   [0] IMAD.WIDE.U32 multiply-accumulates/s   [1] fe_mul/s   [2] fe_sqr/s   [3] sc_mul/s
+ *   [4] mixed point additions/s   [5] point doublings/s   [6] full point additions/s   [7] SM clock MHz seen
+ * Used to state the integer roofline the path is bound by. */
+int bppp_microbench(int device, double *out, int n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -23,10 +23,21 @@ def build(force: bool = False) -> str:
     return _SO
 
 
+def use_native():
+    """Rebuild with -march=native on THIS machine and use that build (CPU-baseline timing)."""
+    global _lib, _SO
+    native = os.path.join(_HERE, "_build", "liboracle_native.so")
+    subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "native"])
+    _SO = native
+    _lib = None
+    return lib()
+
+
 def lib():
     global _lib
     if _lib is None:
-        build()
+        if _SO.endswith("liboracle.so"):
+            build()
         _lib = C.CDLL(_SO)
         _lib.oracle_wnla_rounds.restype = C.c_size_t
         _lib.oracle_wnla_rounds.argtypes = [C.c_size_t, C.c_size_t]
