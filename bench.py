@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- u64 range proofs/s (verify headline, prove alongside) on N B200s of one node.
+
+  python bench.py --gpus 1 --steps K --warmup W            # our arm (CUDA engine through the C ABI)
+  torchrun ... bench.py --gpus N ...                       # one rank per GPU, weak scaling, no data-path collective
+  python bench.py --impl reference ...                     # the reference algorithm on the host cores (C oracle port)
+
+A step = one pass of U64RangeProofProtocol::verify over a batch of 65,536 independent proofs (BASELINE config 2).
+`value`  : device-resident inputs, CUDA-event timed.     `e2e` : bppp_u64_verify_batch on pinned HOST buffers,
+host->device and device->host copies inside the timed region.  Prove (config 3) is reported under "prove".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+LABEL = b"u64 range proof"
+METRIC = "u64 range proofs/sec (verify; batch of 65,536 independent proofs)"
+UNIT = "proofs/s"
+
+# ---- algorithmic integer work (DESIGN.md "Roofline"): 32x32->64 multiply-accumulates ("wMAC") ----
+WMAC_PER_FE_MUL = 72          # 64 product + 8 reduction, 8x32 schoolbook accounting
+M_MIXED, M_ADD, M_DBL = 11, 12, 8
+
+
+def msm_fixed_wmac(terms: int, window_bits: int) -> float:
+    nwin = (256 + window_bits - 1) // window_bits
+    return terms * nwin * M_MIXED * WMAC_PER_FE_MUL
+
+
+def straus_wmac(npoints: int) -> float:
+    # signed 4-bit windows, shared doublings: 256 doublings + 65 adds/point + 7-op table/point + 1
+    m = 256 * M_DBL + npoints * (65 * M_ADD + 4 * M_DBL + 3 * M_ADD) + M_ADD
+    return m * WMAC_PER_FE_MUL
+
+
+def xy(p):
+    return p[0].to_bytes(32, "big") + p[1].to_bytes(32, "big")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(3)
+        sm, reasons, mx = [], set(), None
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median over samples taken under load (upper half: idle samples at the edges pull it down)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(ctx, n, ref):
+    """Synthetic config 2/3: x_i uniform u64 (edge values first), seeded blinds and RNG bytes; proofs made by the
+    engine's own prover; every 16th proof tampered (one bit in the l/n scalars)."""
+    import numpy as np
+    rnd = np.random.default_rng(20260101)
+    xs = rnd.integers(0, 2**64, size=n, dtype=np.uint64)
+    xs[:3] = [0, 1, 2**64 - 1]
+    blinds = np.frombuffer(rnd.bytes(32 * n), dtype=np.uint8).reshape(n, 32).copy()
+    blinds[:, 0] &= 0x7F
+    rng = np.frombuffer(rnd.bytes(3328 * n), dtype=np.uint8).copy()
+    commits = ctx.commit_batch(xs.tolist(), blinds.tobytes())
+    proofs, st = ctx.prove_batch(xs.tolist(), blinds.tobytes(), rng.tobytes(), LABEL)
+    assert all(s == 1 for s in st)
+    bad = np.frombuffer(proofs, dtype=np.uint8).reshape(n, 525).copy()
+    tampered = np.arange(0, n, 16)
+    bad[tampered, 396 + (tampered % 96)] ^= 1
+    expect = np.ones(n, dtype=np.int32)
+    expect[tampered] = 0
+    return xs, blinds, rng, np.frombuffer(commits, dtype=np.uint8).reshape(n, 33).copy(), bad, expect
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import bp_pp_b200 as B
+    import bppp_ref as R
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the host baseline)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.batch
+    g, gv, hv = R.synth_generators()
+    gens = b"".join(xy(p) for p in [g] + gv + hv)
+    ctx = B.Context(gens, local_rank, args.window_bits, n)
+    info = ctx.info()
+    xs, blinds, rng, commits, proofs, expect = make_workload(ctx, n, R)
+
+    dev = torch.device("cuda", local_rank)
+    d_commits = torch.from_numpy(commits).to(dev)
+    d_proofs = torch.from_numpy(proofs).to(dev)
+    d_status = torch.empty(n, dtype=torch.int32, device=dev)
+    d_x = torch.from_numpy(xs.view(np.int64)).to(dev)
+    d_blinds = torch.from_numpy(blinds).to(dev)
+    d_rng = torch.from_numpy(rng).to(dev)
+    d_out = torch.empty(n * 525, dtype=torch.uint8, device=dev)
+    d_pst = torch.empty(n, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def verify_step():
+        ctx.verify_batch_dev(n, d_commits.data_ptr(), d_proofs.data_ptr(), LABEL, d_status.data_ptr(), stream=stream.cuda_stream)
+
+    def prove_step():
+        ctx.prove_batch_dev(n, d_x.data_ptr(), d_blinds.data_ptr(), d_rng.data_ptr(), LABEL, d_out.data_ptr(), d_pst.data_ptr(),
+                            stream=stream.cuda_stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step, steps, warmup):
+        for _ in range(warmup):
+            step()
+        barrier()
+        total_ms = 0.0
+        launches0 = ctx.launch_count()
+        for _ in range(steps):
+            flush.fill_(1)                                   # L2 flush between timed iterations (outside the events)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); step(); e1.record(stream)
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        barrier()
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), ctx.launch_count() - launches0
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    v_ms, v_launches = timed(verify_step, args.steps, args.warmup)
+    got = d_status.cpu().numpy()
+    verdicts_ok = bool((got == expect).all())
+    p_steps = max(1, args.steps // 2)
+    p_ms, p_launches = timed(prove_step, p_steps, max(1, args.warmup // 2))
+    prove_ok = bool((d_pst.cpu().numpy() == 1).all())
+
+    # ---- e2e: the public host-buffer entry point, pinned host memory, copies inside the timed region ----
+    h_commits = torch.from_numpy(commits).pin_memory(); h_proofs = torch.from_numpy(proofs).pin_memory()
+    h_status = torch.empty(n, dtype=torch.int32).pin_memory()
+    h_x = torch.from_numpy(xs.view(np.int64)).pin_memory(); h_blinds = torch.from_numpy(blinds).pin_memory()
+    h_rng = torch.from_numpy(rng).pin_memory(); h_out = torch.empty(n * 525, dtype=torch.uint8).pin_memory()
+    h_pst = torch.empty(n, dtype=torch.int32).pin_memory()
+
+    def e2e(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    e_v = e2e(lambda: ctx.verify_batch_ptr(n, h_commits.data_ptr(), h_proofs.data_ptr(), LABEL, h_status.data_ptr()), args.steps, 1)
+    e2e_ok = bool((h_status.numpy() == expect).all())
+    e_p = e2e(lambda: ctx.prove_batch_ptr(n, h_x.data_ptr(), h_blinds.data_ptr(), h_rng.data_ptr(), LABEL, h_out.data_ptr(), h_pst.data_ptr()),
+              p_steps, 1)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- per-kernel device times of one verify / one prove step (CUDA events on the launching stream) ----
+    prof_v = prof_p = None
+    if rank == 0:
+        ctx.profile_begin(); verify_step(); prof_v = ctx.profile_end()
+        ctx.profile_begin(); prove_step(); prof_p = ctx.profile_end()
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return
+    W = info["window_bits"]
+    # dominant kernel of the verify step and its roofline against the integer pipe
+    tot_v = sum(ms for ms, _ in prof_v.values())
+    dom = max(prof_v.items(), key=lambda kv: kv[1][0])
+    name, (dom_ms, dom_cnt) = dom
+    if name.startswith("k_msm_fixed"):
+        wmac_launches = n * msm_fixed_wmac(17 + 49, W)               # both launches of the step together
+    elif name == "k_v_var2":
+        wmac_launches = n * 4 * straus_wmac(2)
+    elif name == "k_v_var5":
+        wmac_launches = n * straus_wmac(5)
+    else:
+        wmac_launches = 0.0
+    mb = B.microbench(local_rank)
+    peak = mb["imad_wide_per_s"] / 1e9
+    achieved = wmac_launches / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    # HBM side of the same step: fixed-base table reads (64 B per window lookup) -- reported, not the binding roof
+    tbl_bytes = n * (17 + 49) * ((256 + W - 1) // W) * 64
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    msm_ms = sum(ms for k, (ms, _) in prof_v.items() if k.startswith("k_msm_fixed"))
+    roofline = {
+        "bound": "integer", "kernel": name, "achieved": round(achieved, 1), "peak": round(peak, 1), "unit": "GMAC/s (32x32->64 IMAD.WIDE)",
+        "frac": round(achieved / peak, 4) if peak else None, "traffic": None,
+        "kernel_share_of_step": round(dom_ms / tot_v, 4), "kernel_ms": round(dom_ms, 3), "kernel_launches": dom_cnt,
+        "peak_source": "bppp_microbench IMAD.WIDE.U32 issue rate measured live on this GPU",
+        "hbm": {"achieved": round(tbl_bytes / (msm_ms * 1e-3) / 1e9, 1) if msm_ms else None, "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(tbl_bytes / (msm_ms * 1e-3) / 1e9 / hbm_peak, 4) if msm_ms else None,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s", "note": "window-table lookups of k_msm_fixed; not the binding roof"},
+    }
+    # ---- CPU baseline: the oracle (reference algorithm) on the host cores, bounded sample; also a parity check ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle_c as OC
+        OC.use_native()
+        cores = os.cpu_count() or 1
+        sample = min(n, max(64, 48 * cores))
+        c_s, p_s = commits[:sample].tobytes(), proofs[:sample].tobytes()
+        t0 = time.perf_counter()
+        overd = OC.u64_verify_batch(gens, c_s, p_s, LABEL, cores)
+        dt = time.perf_counter() - t0
+        cpu = {"value": round(sample / dt, 1), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {sample} proofs of the same batch, {dt:.2f} s wall on {cores} threads",
+               "parity_with_gpu_on_sample": bool((np.array(overd, dtype=np.int32) == got[:sample]).all())}
+    value = world * n * args.steps / (v_ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(v_ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 limbs (256-bit modular integer arithmetic)", "data": "synthetic",
+        "config": {"workload": "verify_batch: 65,536 independent u64 range proofs per GPU, bit-exact verdicts (BASELINE config 2)",
+                   "batch_per_gpu": n, "tampered": "every 16th record", "window_bits": W, "point_format": "33-byte SEC1 compressed (525-byte records)",
+                   "l2": "256 MiB flush between timed iterations; per-step tables 3.3 GB + workspace exceed L2",
+                   "parallelism": f"proof batch sharded x{world}, no data-path collective"},
+        "e2e": {"value": round(world * n * args.steps / e_v, 1), "unit": UNIT, "h2d_bytes_per_step": n * (33 + 525), "d2h_bytes_per_step": n * 4,
+                "verdicts_ok": e2e_ok},
+        "gpu_launches": v_launches,
+        "verdicts_ok": verdicts_ok,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "prove": {"value": round(world * n * p_steps / (p_ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(p_ms / p_steps, 3), "steps": p_steps,
+                  "e2e": {"value": round(world * n * p_steps / e_p, 1), "unit": UNIT, "h2d_bytes_per_step": n * (8 + 32 + 3328), "d2h_bytes_per_step": n * 529},
+                  "gpu_launches": p_launches, "all_proved": prove_ok, "workload": "prove_batch: 65,536 witnesses per GPU (BASELINE config 3)"},
+        "kernels_verify_ms": {k: [round(ms, 3), c] for k, (ms, c) in sorted(prof_v.items(), key=lambda kv: -kv[1][0])},
+        "kernels_prove_ms": {k: [round(ms, 3), c] for k, (ms, c) in sorted(prof_p.items(), key=lambda kv: -kv[1][0])},
+        "microbench": {k: float(f"{v:.4g}") for k, v in mb.items()},
+        "context": {"table_bytes": info["table_bytes"], "workspace_bytes": info["workspace_bytes"], "table_build_ms": round(info["table_build_ms"], 1)},
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference's own algorithm on the host cores: C restatement (oracle/oracle.c, "port"; the Rust
+    reference cannot be built here -- no cargo, k256/merlin un-vendored).  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import bppp_ref as R
+    import oracle_c as OC
+    OC.use_native()
+    cores = os.cpu_count() or 1
+    g, gv, hv = R.synth_generators()
+    gens = b"".join(xy(p) for p in [g] + gv + hv)
+    sample = max(64, 32 * cores)
+    import numpy as np
+    rnd = np.random.default_rng(20260101)
+    xs = rnd.integers(0, 2**64, size=sample, dtype=np.uint64)
+    xs[:3] = [0, 1, 2**64 - 1]
+    blinds = np.frombuffer(rnd.bytes(32 * sample), dtype=np.uint8).reshape(sample, 32).copy()
+    blinds[:, 0] &= 0x7F
+    rng = rnd.bytes(3328 * sample)
+    proofs, st = OC.u64_prove_batch(gens, xs.tolist(), blinds.tobytes(), rng, LABEL, cores)       # untimed set-up
+    commits = b"".join(OC.u64_commit(gens, int(xs[i]), blinds[i].tobytes()) for i in range(sample))
+    for _ in range(min(args.warmup, 1)):
+        OC.u64_verify_batch(gens, commits, proofs, LABEL, cores)
+    t0 = time.perf_counter()
+    ok = True
+    for _ in range(args.steps):
+        v = OC.u64_verify_batch(gens, commits, proofs, LABEL, cores)
+        ok &= all(s == 1 for s in v)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 limbs (256-bit modular integer arithmetic)", "data": "synthetic",
+        "config": {"workload": "verify: the reference algorithm (one scalar multiplication per MSM term, src/util.rs:46-60) on a bounded "
+                               f"sample of {sample} proofs per step of the same synthetic batch", "threads": cores},
+        "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} proofs per step x {args.steps} steps, {dt:.2f} s wall"},
+        "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "all_true": ok,
+        "note": "C restatement of the reference algorithm (not k256); published k256 figures: 3.808 ms/verify, 14.361 ms/prove on one M3 Pro core",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--window-bits", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -60,6 +60,23 @@ class Context:
     def launch_count(self) -> int:
         return int(lib().bppp_launch_count(self._h))
 
+    def profile_begin(self):
+        check(lib().bppp_ctx_profile_begin(self._h), "bppp_ctx_profile_begin")
+
+    def profile_end(self) -> dict:
+        """{kernel name: (total ms, launches)} for everything launched since profile_begin()."""
+        nmax = 64
+        names = C.create_string_buffer(48 * nmax)
+        ms = (C.c_double * nmax)()
+        cnt = (C.c_uint32 * nmax)()
+        n = C.c_int()
+        check(lib().bppp_ctx_profile_end(self._h, names, ms, cnt, C.c_int(nmax), C.byref(n)), "bppp_ctx_profile_end")
+        out = {}
+        for k in range(n.value):
+            nm = names.raw[48 * k:48 * k + 48].split(b"\0")[0].decode()
+            out[nm] = (ms[k], int(cnt[k]))
+        return out
+
     # ---- host-buffer entry points ----
     def commit_batch(self, xs: Sequence[int], blinds32: bytes, fmt: int = FMT_COMPRESSED) -> bytes:
         n = len(xs)
@@ -180,8 +197,8 @@ class U64RangeProofProtocol:
 
 
 def microbench(device: int = 0) -> dict:
-    out = (C.c_double * 8)()
-    check(lib().bppp_microbench(C.c_int(device), out, C.c_int(8)), "bppp_microbench")
+    out = (C.c_double * 10)()
+    check(lib().bppp_microbench(C.c_int(device), out, C.c_int(10)), "bppp_microbench")
     keys = ["imad_wide_per_s", "fe_mul_per_s", "fe_sqr_per_s", "sc_mul_per_s", "pt_add_mixed_per_s",
-            "pt_double_per_s", "pt_add_per_s", "sm_clock_mhz"]
+            "pt_double_per_s", "pt_add_per_s", "sm_clock_mhz", "imad_per_s", "iadd_per_s"]
     return dict(zip(keys, list(out)))

@@ -226,4 +226,112 @@ BPPP_HD Pt pt_mul(const Pt &p, const Sc &k) {
     return acc;
 }
 
+// ---- GLV endomorphism: lambda * (x, y) = (beta * x, y);  k = k1 + k2 * lambda (mod n), |k1|, |k2| < 2^128 ----
+// Lattice basis from the extended Euclidean algorithm on (n, lambda); g1, g2 = round(2^384 b2 / n),
+// round(2^384 (-b1) / n).  Constants and the < 2^128 bound were checked numerically (tests/test_hostemu.py).
+struct GlvSplit {
+    uint32_t k1[4], k2[4];   // magnitudes, little-endian words
+    bool neg1, neg2;
+};
+// (k * g + 2^383) >> 384 for 256-bit k, g: the top 128 bits of the rounded 512-bit product
+BPPP_HD Sc sc_mul_shift384(const Sc &k, const uint32_t g[8]) {
+    uint32_t t[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            c += (uint64_t)k.v[i] * g[j] + t[i + j];
+            t[i + j] = (uint32_t)c; c >>= 32;
+        }
+        t[i + 8] = (uint32_t)c;
+    }
+    Sc r = sc_zero();
+    uint64_t c = (uint64_t)(t[11] >> 31);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { c += t[12 + i]; r.v[i] = (uint32_t)c; c >>= 32; }
+    r.v[4] = (uint32_t)c;
+    return r;
+}
+BPPP_HD GlvSplit glv_split(const Sc &k) {
+    const uint32_t G1[8] = {0x45DBB031u, 0xE893209Au, 0x71E8CA7Fu, 0x3DAA8A14u, 0x9284EB15u, 0xE86C90E4u, 0xA7D46BCDu, 0x3086D221u};
+    const uint32_t G2[8] = {0x8AC47F71u, 0x1571B4AEu, 0x9DF506C6u, 0x221208ACu, 0x0ABFE4C4u, 0x6F547FA9u, 0x010E8828u, 0xE4437ED6u};
+    Sc mb1 = sc_zero(), mb2, lam;   // -b1, -b2 (mod n), lambda
+    mb1.v[0] = 0x0ABFE4C3u; mb1.v[1] = 0x6F547FA9u; mb1.v[2] = 0x010E8828u; mb1.v[3] = 0xE4437ED6u;
+    mb2.v[0] = 0x3DB1562Cu; mb2.v[1] = 0xD765CDA8u; mb2.v[2] = 0x0774346Du; mb2.v[3] = 0x8A280AC5u;
+    mb2.v[4] = 0xFFFFFFFEu; mb2.v[5] = 0xFFFFFFFFu; mb2.v[6] = 0xFFFFFFFFu; mb2.v[7] = 0xFFFFFFFFu;
+    lam.v[0] = 0x1B23BD72u; lam.v[1] = 0xDF02967Cu; lam.v[2] = 0x20816678u; lam.v[3] = 0x122E22EAu;
+    lam.v[4] = 0x8812645Au; lam.v[5] = 0xA5261C02u; lam.v[6] = 0xC05C30E0u; lam.v[7] = 0x5363AD4Cu;
+    Sc c1 = sc_mul_shift384(k, G1), c2 = sc_mul_shift384(k, G2);
+    Sc k2 = sc_add(sc_mul(c1, mb1), sc_mul(c2, mb2));
+    Sc k1 = sc_sub(k, sc_mul(k2, lam));
+    GlvSplit r;
+    r.neg1 = (k1.v[4] | k1.v[5] | k1.v[6] | k1.v[7]) != 0;   // canonical residue >= 2^128 means a negative half
+    r.neg2 = (k2.v[4] | k2.v[5] | k2.v[6] | k2.v[7]) != 0;
+    if (r.neg1) k1 = sc_neg(k1);
+    if (r.neg2) k2 = sc_neg(k2);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { r.k1[i] = k1.v[i]; r.k2[i] = k2.v[i]; }
+    return r;
+}
+// signed 4-bit digits of a 128-bit magnitude: 33 nibbles of m + sum_{i<32} 8*16^i
+struct Digits4h {
+    uint32_t w[5];
+};
+BPPP_HD Digits4h half_signed_digits4(const uint32_t m[4]) {
+    Digits4h d;
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { c += (uint64_t)m[i] + 0x88888888u; d.w[i] = (uint32_t)c; c >>= 32; }
+    d.w[4] = (uint32_t)c;
+    return d;
+}
+BPPP_HD int digits4h_get(const Digits4h &d, int i) {   // i in 0..32
+    uint32_t nib = (d.w[i >> 3] >> (4 * (i & 7))) & 15u;
+    return i < 32 ? (int)nib - 8 : (int)nib;
+}
+BPPP_HD Fe fe_beta() {
+    const uint32_t B[8] = {0x719501EEu, 0xC1396C28u, 0x12F58995u, 0x9CF04975u, 0xAC3434E9u, 0x6E64479Eu, 0x657C0710u, 0x7AE96A2Bu};
+    return fe_from_words(B);
+}
+
+// joint sum_k ks[k] * P_k over NP points: 2*NP half-scalars of 128 bits, 128 shared doublings.
+// tab[k] holds 1P..8P of point k; the lambda-half of a point reuses the same table with X scaled by beta.
+template <int NP>
+BPPP_HD Pt straus_glv(const PtTable8 *tab, const Sc *ks) {
+    Digits4h dg[2 * NP];
+    bool neg[2 * NP];
+#pragma unroll 1
+    for (int k = 0; k < NP; k++) {
+        GlvSplit g = glv_split(ks[k]);
+        dg[2 * k] = half_signed_digits4(g.k1); neg[2 * k] = g.neg1;
+        dg[2 * k + 1] = half_signed_digits4(g.k2); neg[2 * k + 1] = g.neg2;
+    }
+    const Fe beta = fe_beta();
+    Pt acc = pt_identity();
+#pragma unroll 1
+    for (int d = 32; d >= 0; d--) {
+        if (d != 32) {
+#pragma unroll 1
+            for (int r = 0; r < 4; r++) acc = pt_double(acc);
+        }
+#pragma unroll 1
+        for (int h = 0; h < 2 * NP; h++) {
+            int sd = digits4h_get(dg[h], d);
+            if (neg[h]) sd = -sd;
+            Pt e = pt_table8_get(tab[h >> 1], sd);
+            if (h & 1) e.x = fe_mul(e.x, beta);
+            acc = pt_add(acc, e);
+        }
+    }
+    return acc;
+}
+BPPP_HD Pt pt_mul_glv(const Pt &p, const Sc &k) {
+    PtTable8 tab;
+    pt_table8_build(tab, p);
+    return straus_glv<1>(&tab, &k);
+}
+
 }  // namespace bppp

@@ -1,0 +1,90 @@
+// Shared host-side declarations of the engine's translation units (engine_*.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bppp.h"
+#include "u64_prove.cuh"
+#include "u64_verify.cuh"
+
+namespace bppp {
+
+int engine_fail(int code, const std::string &msg);
+#define CUDA_OK(expr)                                                                                             \
+    do {                                                                                                          \
+        cudaError_t _e = (expr);                                                                                  \
+        if (_e != cudaSuccess) return engine_fail(BPPP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+struct TermMap { int gen[NUM_GENS]; };
+
+}  // namespace bppp
+
+struct bppp_ctx {
+    int device = 0;
+    bppp::FixedTable T{};
+    uint4 *d_tab = nullptr;
+    size_t table_bytes = 0;
+    double table_build_ms = 0;
+    size_t max_batch = 0;
+    uint32_t *d_ws = nullptr;       // workspace, max(VL::WORDS, PL::WORDS) * max_batch words
+    size_t ws_words_per_proof = 0;
+    uint8_t *d_in_a = nullptr, *d_in_b = nullptr, *d_in_c = nullptr;   // staging for host-buffer entry points
+    uint8_t *d_out = nullptr;
+    int32_t *d_status = nullptr;
+    cudaStream_t stream = nullptr;
+    // a batch slice is cut into up to MAX_SUB sub-batches, each running its kernel sequence on its own stream,
+    // so that tail waves and low-parallelism kernels of one sub-batch overlap with work of the others
+    static constexpr int MAX_SUB = 8;
+    int nsub = 2;
+    cudaStream_t sub_stream[MAX_SUB] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
+    uint64_t launches = 0;
+    int sm_count = 148;
+    // optional per-launch timing (bppp_ctx_profile_begin/end): CUDA events on the launching stream
+    bool profiling = false;
+    struct ProfRec { const char *name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+};
+
+namespace bppp {
+
+static inline unsigned nblocks(size_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+#define LAUNCH(ctx, kern, grid, block, ...)                                                    \
+    do {                                                                                       \
+        if ((ctx)->profiling) {                                                                \
+            bppp_ctx::ProfRec _r; _r.name = #kern;                                             \
+            cudaEventCreate(&_r.a); cudaEventCreate(&_r.b);                                    \
+            cudaEventRecord(_r.a, st);                                                         \
+            kern<<<(grid), (block), 0, st>>>(__VA_ARGS__);                                     \
+            cudaEventRecord(_r.b, st);                                                         \
+            (ctx)->prof.push_back(_r);                                                         \
+        } else {                                                                               \
+            kern<<<(grid), (block), 0, st>>>(__VA_ARGS__);                                     \
+        }                                                                                      \
+        (ctx)->launches++;                                                                     \
+    } while (0)
+
+static inline TermMap identity_map() { TermMap tm; for (int t = 0; t < NUM_GENS; t++) tm.gen[t] = t; return tm; }
+
+// engine_core.cu
+// sub-batch plan for a slice of n proofs: part k covers [lo[k], lo[k+1]) and owns workspace words starting at
+// d_ws + words_per_proof * lo[k] with row stride (lo[k+1] - lo[k])
+struct SubPlan { int parts; size_t lo[bppp_ctx::MAX_SUB + 1]; };
+SubPlan plan_sub(const bppp_ctx *c, size_t n);
+int fork_streams(bppp_ctx *c, cudaStream_t caller, const SubPlan &sp);
+int join_streams(bppp_ctx *c, cudaStream_t caller, const SubPlan &sp);
+static inline WS sub_ws(const bppp_ctx *c, const SubPlan &sp, int k) {
+    return WS{c->d_ws + c->ws_words_per_proof * sp.lo[k], sp.lo[k + 1] - sp.lo[k]};
+}
+void launch_msm_fixed(bppp_ctx *c, cudaStream_t st, WS w, int sc_off, const TermMap &tm, int nterms, int out_off);
+void launch_batch_inv(bppp_ctx *c, cudaStream_t st, WS w, int in_off, int out_off);
+// engine_var.cu: joint variable-base ladders (one thread per proof)
+void launch_v_var5(bppp_ctx *c, cudaStream_t st, WS w);
+void launch_v_var2(bppp_ctx *c, cudaStream_t st, WS w, int j);
+void launch_p_var2(bppp_ctx *c, cudaStream_t st, WS w, int j);
+
+}  // namespace bppp

@@ -1,0 +1,322 @@
+// libbppp.so, core translation unit: context, fixed-base window tables, the fixed-base MSM and
+// batch-inversion kernels every pipeline shares, and commit_value.
+//
+// A batch of N independent proofs is run in lockstep as a sequence of data-parallel kernels over a
+// word-major workspace in HBM (ws.cuh).  Three kernel shapes carry the work:
+//   * k_msm_fixed   -- fixed-base multi-scalar multiplication from per-generator window tables in HBM
+//                      (LANES threads per proof, warp-shuffle reduction of the partial points);
+//   * k_*_var*      -- joint variable-base Straus ladder for the per-proof proof points (1 thread/proof);
+//   * k_batch_inv   -- Montgomery batch inversion across proofs for the affine normalisations that
+//                      feed the Fiat-Shamir transcript;
+// the transcript itself (Merlin/STROBE/Keccak) and all challenge-derived scalar algebra run on the
+// device, one proof per thread, so a batch never returns to the host between phases.
+// There is no CPU fallback: without a CUDA device every entry point fails with BPPP_ERR_NO_DEVICE.
+#include "engine_common.cuh"
+
+using namespace bppp;
+
+static thread_local std::string g_last_error;
+namespace bppp { int engine_fail(int code, const std::string &msg) { g_last_error = msg; return code; } }
+static int fail(int code, const std::string &msg) { return engine_fail(code, msg); }
+
+template <int LANES>
+__device__ __forceinline__ Pt lanes_reduce(Pt acc) {
+#pragma unroll 1
+    for (int off = LANES / 2; off >= 1; off >>= 1) {
+        Pt o;
+#pragma unroll
+        for (int k = 0; k < 10; k++) {
+            o.x.n[k] = __shfl_xor_sync(0xFFFFFFFFu, acc.x.n[k], off);
+            o.y.n[k] = __shfl_xor_sync(0xFFFFFFFFu, acc.y.n[k], off);
+            o.z.n[k] = __shfl_xor_sync(0xFFFFFFFFu, acc.z.n[k], off);
+        }
+        acc = pt_add(acc, o);
+    }
+    return acc;
+}
+
+// sum_t scalar[t] * G_{gen[t]} for every proof: LANES threads per proof
+template <int LANES>
+#ifndef BPPP_MSM_BLOCK
+#define BPPP_MSM_BLOCK 64
+#endif
+#ifndef BPPP_MSM_MINBLOCKS
+#define BPPP_MSM_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(BPPP_MSM_BLOCK, BPPP_MSM_MINBLOCKS) k_msm_fixed(FixedTable T, WS w, int sc_off, TermMap tm, int nterms, int out_off) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = tid / LANES;
+    int lane = (int)(tid % LANES);
+    bool live = i < w.n;
+    if (!live) i = w.n - 1;
+    Pt acc = msm_fixed_lane(T, w, i, sc_off, tm.gen, nterms, lane, LANES);
+    acc = lanes_reduce<LANES>(acc);
+    if (live && lane == 0) ws_st_pt(w, i, out_off, acc);
+}
+
+__global__ void __launch_bounds__(128) k_batch_inv(WS w, int in_off, int out_off, size_t nthreads) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nthreads) batch_inv_strided(w, in_off, out_off, t, nthreads, w.n);
+}
+
+// ---- commit ----
+__global__ void __launch_bounds__(64) k_c_load(WS w, const uint64_t *xs, const uint8_t *blinds) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w.n) return;
+    Sc s; int32_t st = ST_TRUE;
+    if (!sc_from_be32(s, blinds + 32 * i)) { st = ST_BAD_SCALAR; s = sc_zero(); }
+    ws_st_sc(w, i, VL::FS, sc_from_u64(xs[i]));
+    ws_st_sc(w, i, VL::FS + 8, s);
+    ws_st(w, i, VL::STATUS, (uint32_t)st);
+}
+__global__ void __launch_bounds__(64) k_c_store(WS w, uint8_t *out, int fmt) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w.n) return;
+    bool id;
+    PtA a = ws_affine(w, i, VL::ACC, VL::ZINV, id);
+    if (fmt == FMT_COMPRESSED) pta_compress(out + 33 * i, a, id);
+    else pta_to_xy64(out + 64 * i, a, id);
+}
+
+// ---- fixed-base table construction (one generator per pass) ----
+// scratch layout per entry (word-major over nent = nwin * E entries): Pt at 0..29, zinv at 30..39
+__global__ void k_tab_bases(WS tmp, PtA gen, bool gen_id, int W, int nwin, uint32_t E) {
+    // single thread: B_w = 2^(W w) G, stored at entry (w, d = 1)
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Pt b = pt_from_affine(gen, gen_id);
+    for (int w = 0; w < nwin; w++) {
+        ws_st_pt(tmp, (size_t)w * E + 0, 0, b);
+        for (int k = 0; k < W; k++) b = pt_double(b);
+    }
+}
+// level l >= 1: for m in [2^(l-1), 2^l): E[2m] = 2 E[m], E[2m+1] = E[2m] + B   (entry index = d - 1)
+__global__ void __launch_bounds__(128) k_tab_level(WS tmp, int nwin, uint32_t E, int level) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t per = 1u << (level - 1);
+    if (t >= (size_t)nwin * per) return;
+    uint32_t w = (uint32_t)(t / per), m = per + (uint32_t)(t % per);
+    size_t base = (size_t)w * E;
+    Pt em = ws_ld_pt(tmp, base + (m - 1), 0);
+    Pt b = ws_ld_pt(tmp, base + 0, 0);
+    Pt e2 = pt_double(em);
+    if (2 * m <= E) ws_st_pt(tmp, base + (2 * m - 1), 0, e2);
+    if (2 * m + 1 <= E) ws_st_pt(tmp, base + (2 * m), 0, pt_add(e2, b));
+}
+__global__ void __launch_bounds__(128) k_tab_write(WS tmp, uint4 *dst) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tmp.n) return;
+    bool id;
+    PtA a = ws_affine(tmp, t, 0, 30, id);
+    uint32_t x[8], y[8];
+    fe_to_words(x, a.x); fe_to_words(y, a.y);
+    if (id) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) { x[k] = 0; y[k] = 0; }
+    }
+    dst[4 * t] = make_uint4(x[0], x[1], x[2], x[3]); dst[4 * t + 1] = make_uint4(x[4], x[5], x[6], x[7]);
+    dst[4 * t + 2] = make_uint4(y[0], y[1], y[2], y[3]); dst[4 * t + 3] = make_uint4(y[4], y[5], y[6], y[7]);
+}
+
+#ifndef BPPP_MSM_LANES
+#define BPPP_MSM_LANES 4
+#endif
+static constexpr int MSM_LANES = BPPP_MSM_LANES;
+
+namespace bppp {
+SubPlan plan_sub(const bppp_ctx *c, size_t n) {
+    SubPlan sp;
+    int parts = c->profiling ? 1 : c->nsub;          // per-kernel timing wants kernels back to back on one stream
+    const size_t min_part = 2048;                    // below this a sub-batch cannot fill the GPU anyway
+    while (parts > 1 && n / parts < min_part) parts--;
+    sp.parts = parts;
+    for (int k = 0; k <= parts; k++) sp.lo[k] = n * k / parts;
+    return sp;
+}
+int fork_streams(bppp_ctx *c, cudaStream_t caller, const SubPlan &sp) {
+    if (sp.parts == 1) return BPPP_OK;
+    CUDA_OK(cudaEventRecord(c->ev_fork, caller));
+    for (int k = 0; k < sp.parts; k++) CUDA_OK(cudaStreamWaitEvent(c->sub_stream[k], c->ev_fork, 0));
+    return BPPP_OK;
+}
+int join_streams(bppp_ctx *c, cudaStream_t caller, const SubPlan &sp) {
+    if (sp.parts == 1) return BPPP_OK;
+    for (int k = 0; k < sp.parts; k++) {
+        CUDA_OK(cudaEventRecord(c->ev_join[k], c->sub_stream[k]));
+        CUDA_OK(cudaStreamWaitEvent(caller, c->ev_join[k], 0));
+    }
+    return BPPP_OK;
+}
+void launch_msm_fixed(bppp_ctx *c, cudaStream_t st, WS w, int sc_off, const TermMap &tm, int nterms, int out_off) {
+    size_t threads = w.n * MSM_LANES;
+    LAUNCH(c, k_msm_fixed<MSM_LANES>, nblocks(threads, BPPP_MSM_BLOCK), BPPP_MSM_BLOCK, c->T, w, sc_off, tm, nterms, out_off);
+}
+void launch_batch_inv(bppp_ctx *c, cudaStream_t st, WS w, int in_off, int out_off) {
+    // one inversion per thread, >= 8 items per thread when the batch is large enough to still fill the GPU
+    size_t per = 8;
+    size_t nthreads = (w.n + per - 1) / per;
+    size_t min_threads = (size_t)c->sm_count * 128;
+    if (nthreads < min_threads) nthreads = w.n < min_threads ? w.n : min_threads;
+    LAUNCH(c, k_batch_inv, nblocks(nthreads, 128), 128, w, in_off, out_off, nthreads);
+}
+}  // namespace bppp
+
+static int build_tables(bppp_ctx *c, const PtA *gens, const bool *gen_id) {
+    const int W = c->T.W, nwin = c->T.nwin;
+    const uint32_t E = (1u << W) - 1u;
+    const size_t nent = (size_t)nwin * E;
+    uint32_t *d_tmp = nullptr;
+    CUDA_OK(cudaMalloc(&d_tmp, nent * 40 * sizeof(uint32_t)));
+    cudaStream_t st = c->stream;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    WS tmp{d_tmp, nent};
+    for (int g = 0; g < NUM_GENS; g++) {
+        LAUNCH(c, k_tab_bases, 1, 1, tmp, gens[g], gen_id[g], W, nwin, E);
+        for (int level = 1; level < W; level++) {
+            size_t threads = (size_t)nwin << (level - 1);
+            LAUNCH(c, k_tab_level, nblocks(threads, 128), 128, tmp, nwin, E, level);
+        }
+        launch_batch_inv(c, st, tmp, 20, 30);
+        LAUNCH(c, k_tab_write, nblocks(nent, 128), 128, tmp, c->d_tab + (size_t)g * nent * 4);
+    }
+    cudaEventRecord(e1, st);
+    CUDA_OK(cudaStreamSynchronize(st));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    c->table_build_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CUDA_OK(cudaFree(d_tmp));
+    CUDA_OK(cudaGetLastError());
+    return BPPP_OK;
+}
+
+extern "C" const char *bppp_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int bppp_ctx_create(bppp_ctx **out, int device, const uint8_t *gens64, int window_bits, size_t max_batch) {
+    if (!out || !gens64) return fail(BPPP_ERR_ARG, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BPPP_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(BPPP_ERR_ARG, "bad device index");
+    if (window_bits == 0) window_bits = 16;
+    if (window_bits < 2 || window_bits > 16) return fail(BPPP_ERR_ARG, "window_bits must be in 2..16");
+    if (max_batch == 0) max_batch = 65536;
+    PtA gens[NUM_GENS]; bool gen_id[NUM_GENS];
+    for (int g = 0; g < NUM_GENS; g++) {
+        int s = pta_from_xy64(gens[g], gens64 + 64 * g);
+        if (s < 0) return fail(BPPP_ERR_GENERATOR, "generator " + std::to_string(g) + " is not on the curve");
+        gens[g].x = fe_normalize(gens[g].x); gens[g].y = fe_normalize(gens[g].y);
+        gen_id[g] = s == 1;
+    }
+    CUDA_OK(cudaSetDevice(device));
+    bppp_ctx *c = new bppp_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (const char *e = getenv("BPPP_NSUB")) { int v = atoi(e); if (v >= 1 && v <= bppp_ctx::MAX_SUB) c->nsub = v; }
+    for (int k = 0; k < bppp_ctx::MAX_SUB; k++) {
+        CUDA_OK(cudaStreamCreateWithFlags(&c->sub_stream[k], cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+    }
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    c->T.W = window_bits; c->T.nwin = (256 + window_bits - 1) / window_bits; c->T.ngens = NUM_GENS;
+    size_t nent = (size_t)c->T.nwin * ((1u << window_bits) - 1u);
+    c->table_bytes = (size_t)NUM_GENS * nent * 64;
+    CUDA_OK(cudaMalloc(&c->d_tab, c->table_bytes));
+    c->T.tab = c->d_tab;
+    c->max_batch = max_batch;
+    c->ws_words_per_proof = VL::WORDS > PL::WORDS ? VL::WORDS : PL::WORDS;
+    CUDA_OK(cudaMalloc(&c->d_ws, c->ws_words_per_proof * max_batch * sizeof(uint32_t)));
+    CUDA_OK(cudaMalloc(&c->d_in_a, (size_t)64 * max_batch));
+    CUDA_OK(cudaMalloc(&c->d_in_b, (size_t)U64_PROOF_BYTES_AFFINE * max_batch));
+    CUDA_OK(cudaMalloc(&c->d_in_c, (size_t)U64_RNG_BYTES * max_batch));
+    CUDA_OK(cudaMalloc(&c->d_out, (size_t)U64_PROOF_BYTES_COMPRESSED * max_batch));
+    CUDA_OK(cudaMalloc(&c->d_status, sizeof(int32_t) * max_batch));
+    int rc = build_tables(c, gens, gen_id);
+    if (rc != BPPP_OK) { bppp_ctx_destroy(c); return rc; }
+    *out = c;
+    return BPPP_OK;
+}
+
+extern "C" void bppp_ctx_destroy(bppp_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_tab); cudaFree(c->d_ws); cudaFree(c->d_in_a); cudaFree(c->d_in_b); cudaFree(c->d_in_c);
+    cudaFree(c->d_out); cudaFree(c->d_status);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    for (int k = 0; k < bppp_ctx::MAX_SUB; k++) {
+        if (c->sub_stream[k]) cudaStreamDestroy(c->sub_stream[k]);
+        if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    delete c;
+}
+
+extern "C" int bppp_ctx_info(const bppp_ctx *c, size_t *table_bytes, size_t *workspace_bytes, double *table_build_ms, int *window_bits) {
+    if (!c) return BPPP_ERR_ARG;
+    if (table_bytes) *table_bytes = c->table_bytes;
+    if (workspace_bytes) *workspace_bytes = c->ws_words_per_proof * c->max_batch * sizeof(uint32_t);
+    if (table_build_ms) *table_build_ms = c->table_build_ms;
+    if (window_bits) *window_bits = c->T.W;
+    return BPPP_OK;
+}
+extern "C" uint64_t bppp_launch_count(const bppp_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int bppp_ctx_profile_begin(bppp_ctx *c) {
+    if (!c) return BPPP_ERR_ARG;
+    c->prof.clear();
+    c->profiling = true;
+    return BPPP_OK;
+}
+// Aggregates the launches recorded since profile_begin by kernel name.  names: n_max slots of 48 bytes.
+extern "C" int bppp_ctx_profile_end(bppp_ctx *c, char *names, double *total_ms, uint32_t *counts, int n_max, int *n_out) {
+    if (!c || !names || !total_ms || !counts || !n_out) return BPPP_ERR_ARG;
+    c->profiling = false;
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaDeviceSynchronize());
+    int n = 0;
+    for (auto &r : c->prof) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+        int k = 0;
+        for (; k < n; k++) if (strncmp(names + 48 * k, r.name, 47) == 0) break;
+        if (k == n) {
+            if (n >= n_max) continue;
+            strncpy(names + 48 * k, r.name, 47); names[48 * k + 47] = 0;
+            total_ms[k] = 0; counts[k] = 0; n++;
+        }
+        total_ms[k] += ms; counts[k]++;
+    }
+    c->prof.clear();
+    *n_out = n;
+    return BPPP_OK;
+}
+
+
+// ---- commit ----
+extern "C" int bppp_u64_commit_batch(bppp_ctx *c, size_t n, const uint64_t *x, const uint8_t *blinds32, int fmt, uint8_t *out) {
+    if (!c || (n && (!x || !blinds32 || !out))) return fail(BPPP_ERR_ARG, "null argument");
+    if (fmt != FMT_COMPRESSED && fmt != FMT_AFFINE64) return fail(BPPP_ERR_ARG, "bad point format");
+    CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    size_t osz = fmt == FMT_COMPRESSED ? 33 : 64;
+    TermMap tm = identity_map(); tm.gen[0] = GEN_G; tm.gen[1] = GEN_HVEC;
+    for (size_t off = 0; off < n; off += c->max_batch) {
+        size_t m = n - off < c->max_batch ? n - off : c->max_batch;
+        WS w{c->d_ws, m};
+        CUDA_OK(cudaMemcpyAsync(c->d_in_a, x + off, 8 * m, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(c->d_in_b, blinds32 + 32 * off, 32 * m, cudaMemcpyHostToDevice, st));
+        LAUNCH(c, k_c_load, nblocks(m, 64), 64, w, (const uint64_t *)c->d_in_a, c->d_in_b);
+        launch_msm_fixed(c, st, w, VL::FS, tm, 2, VL::ACC);
+        launch_batch_inv(c, st, w, VL::ACC + 20, VL::ZINV);
+        LAUNCH(c, k_c_store, nblocks(m, 64), 64, w, c->d_out, fmt);
+        CUDA_OK(cudaMemcpyAsync(out + osz * off, c->d_out, osz * m, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+    }
+    CUDA_OK(cudaGetLastError());
+    return BPPP_OK;
+}
+

@@ -1,0 +1,144 @@
+// libbppp.so, prove translation unit: U64RangeProofProtocol::prove over a batch (u64_proof.rs:57-82).
+#include "engine_common.cuh"
+
+using namespace bppp;
+
+static int fail(int code, const std::string &msg) { return engine_fail(code, msg); }
+
+// ---- prove kernels ----
+__global__ void __launch_bounds__(64) k_p_load(WS w, const uint64_t *xs, const uint8_t *blinds) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w.n) u64p_load_one(w, i, xs[i], blinds + 32 * i);
+}
+__global__ void __launch_bounds__(64) k_p_phase1(WS w, Merlin init, const uint8_t *rng) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w.n) u64p_phase1_one(w, i, init, rng + (size_t)U64_RNG_BYTES * i);
+}
+__global__ void __launch_bounds__(64) k_p_phase2(WS w, const uint8_t *rng) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w.n) u64p_phase2_one(w, i, rng + (size_t)U64_RNG_BYTES * i);
+}
+__global__ void __launch_bounds__(64) k_p_phase3(WS w) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w.n) u64p_phase3_one(w, i);
+}
+__global__ void __launch_bounds__(64) k_p_round(WS w, int j) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w.n) u64p_round_one(w, i, j);
+}
+__global__ void __launch_bounds__(64) k_p_output(WS w, uint8_t *proofs, int32_t *status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w.n) return;
+    u64p_output_one(w, i, proofs + (size_t)U64_PROOF_BYTES_COMPRESSED * i);
+    status[i] = (int32_t)ws_ld(w, i, PL::STATUS);
+}
+// V' = V + r_com (reciprocal.rs:141 via SURVEY App. C.2)
+__global__ void __launch_bounds__(64) k_p_vprime(WS w) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w.n) u64p_vprime_one(w, i);
+}
+
+// ---- prove ----
+static int prove_part(bppp_ctx *c, cudaStream_t st, WS w, const uint64_t *d_x, const uint8_t *d_blinds, const uint8_t *d_rng,
+                      const Merlin &init, uint8_t *d_proofs, int32_t *d_status) {
+    const size_t n = w.n;
+    const unsigned g64 = nblocks(n, 64);
+    TermMap tm;
+    LAUNCH(c, k_p_load, g64, 64, w, d_x, d_blinds);
+    // V = x g + s h_0  (reciprocal.rs:88-90)
+    u64p_termmap_commit(tm.gen);
+    launch_msm_fixed(c, st, w, PL::FS, tm, 2, PL::PTS + 30 * PP_V);
+    launch_batch_inv(c, st, w, PL::PTS + 30 * PP_V + 20, PL::ZINV + 10 * PP_V);
+    LAUNCH(c, k_p_phase1, g64, 64, w, init, d_rng);
+    // r_com, c_o, c_l, c_r
+    for (int k = 0; k < 4; k++) {
+        int nterms = u64p_termmap_stage1(tm.gen, k);
+        launch_msm_fixed(c, st, w, PL::FS + 8 * u64p_stage1_scalar_base(k), tm, nterms, PL::PTS + 30 * u64p_stage1_point(k));
+    }
+    LAUNCH(c, k_p_vprime, g64, 64, w);
+    for (int k = 0; k < 5; k++) {
+        int p = u64p_stage1_norm_point(k);
+        launch_batch_inv(c, st, w, PL::PTS + 30 * p + 20, PL::ZINV + 10 * p);
+    }
+    LAUNCH(c, k_p_phase2, g64, 64, w, d_rng);
+    u64p_termmap_cs(tm.gen);
+    launch_msm_fixed(c, st, w, PL::FS, tm, 42, PL::PTS + 30 * PP_CS);
+    launch_batch_inv(c, st, w, PL::PTS + 30 * PP_CS + 20, PL::ZINV + 10 * PP_CS);
+    LAUNCH(c, k_p_phase3, g64, 64, w);
+    // C_0 = v g + <h, l> + <g_vec, n>  (circuit.rs:522-524): 43 terms
+    u64p_termmap_c0(tm.gen);
+    launch_msm_fixed(c, st, w, PL::FS, tm, 43, PL::COM);
+    for (int j = 0; j < 4; j++) {
+        // X_j (49 terms), R_j (25 terms) over the original generators
+        TermMap all = identity_map();
+        launch_msm_fixed(c, st, w, PL::XS, all, NUM_GENS, PL::PTS + 30 * (PP_X + j));
+        u64p_termmap_r(tm.gen, j);
+        launch_msm_fixed(c, st, w, PL::RS, tm, 25, PL::PTS + 30 * (PP_R + j));
+        launch_batch_inv(c, st, w, PL::COM + 20, PL::ZINV + 10 * PP_COM);
+        launch_batch_inv(c, st, w, PL::PTS + 30 * (PP_X + j) + 20, PL::ZINV + 10 * (PP_X + j));
+        launch_batch_inv(c, st, w, PL::PTS + 30 * (PP_R + j) + 20, PL::ZINV + 10 * (PP_R + j));
+        LAUNCH(c, k_p_round, g64, 64, w, j);
+        if (j < 3) launch_p_var2(c, st, w, j);
+    }
+    LAUNCH(c, k_p_output, g64, 64, w, d_proofs, d_status);
+    CUDA_OK(cudaGetLastError());
+    return BPPP_OK;
+}
+
+static int prove_slice(bppp_ctx *c, cudaStream_t st, size_t n, const uint64_t *d_x, const uint8_t *d_blinds, const uint8_t *d_rng,
+                       const Merlin &init, uint8_t *d_proofs, int32_t *d_status) {
+    SubPlan sp = plan_sub(c, n);
+    int rc = fork_streams(c, st, sp);
+    if (rc != BPPP_OK) return rc;
+    for (int k = 0; k < sp.parts; k++) {
+        cudaStream_t s = sp.parts == 1 ? st : c->sub_stream[k];
+        rc = prove_part(c, s, sub_ws(c, sp, k), d_x + sp.lo[k], d_blinds + 32 * sp.lo[k], d_rng + (size_t)U64_RNG_BYTES * sp.lo[k], init,
+                        d_proofs + (size_t)U64_PROOF_BYTES_COMPRESSED * sp.lo[k], d_status + sp.lo[k]);
+        if (rc != BPPP_OK) return rc;
+    }
+    return join_streams(c, st, sp);
+}
+
+extern "C" int bppp_u64_prove_batch_dev(bppp_ctx *c, size_t n, const void *d_x, const void *d_blinds32, const void *d_rng,
+                                        const uint8_t *label, size_t label_len, void *d_proofs_out, void *d_status, void *stream) {
+    if (!c || (n && (!d_x || !d_blinds32 || !d_rng || !d_proofs_out || !d_status))) return fail(BPPP_ERR_ARG, "null argument");
+    CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in the CUDA runtime
+    Merlin init; merlin_init(init, label, (uint32_t)label_len);
+    for (size_t off = 0; off < n; off += c->max_batch) {
+        size_t m = n - off < c->max_batch ? n - off : c->max_batch;
+        int rc = prove_slice(c, st, m, (const uint64_t *)d_x + off, (const uint8_t *)d_blinds32 + 32 * off,
+                             (const uint8_t *)d_rng + (size_t)U64_RNG_BYTES * off, init,
+                             (uint8_t *)d_proofs_out + (size_t)U64_PROOF_BYTES_COMPRESSED * off, (int32_t *)d_status + off);
+        if (rc != BPPP_OK) return rc;
+    }
+    return BPPP_OK;
+}
+
+extern "C" int bppp_u64_prove_batch(bppp_ctx *c, size_t n, const uint64_t *x, const uint8_t *blinds32, const uint8_t *rng,
+                                    const uint8_t *label, size_t label_len, uint8_t *proofs_out, int32_t *status) {
+    if (!c || (n && (!x || !blinds32 || !rng || !proofs_out || !status))) return fail(BPPP_ERR_ARG, "null argument");
+    CUDA_OK(cudaSetDevice(c->device));
+    Merlin init; merlin_init(init, label, (uint32_t)label_len);
+    for (size_t off = 0; off < n; off += c->max_batch) {
+        size_t m = n - off < c->max_batch ? n - off : c->max_batch;
+        SubPlan sp = plan_sub(c, m);
+        for (int k = 0; k < sp.parts; k++) {
+            cudaStream_t st = sp.parts == 1 ? c->stream : c->sub_stream[k];
+            size_t lo = sp.lo[k], cnt = sp.lo[k + 1] - sp.lo[k];
+            CUDA_OK(cudaMemcpyAsync(c->d_in_a + 8 * lo, x + off + lo, 8 * cnt, cudaMemcpyHostToDevice, st));
+            CUDA_OK(cudaMemcpyAsync(c->d_in_b + 32 * lo, blinds32 + 32 * (off + lo), 32 * cnt, cudaMemcpyHostToDevice, st));
+            CUDA_OK(cudaMemcpyAsync(c->d_in_c + (size_t)U64_RNG_BYTES * lo, rng + (size_t)U64_RNG_BYTES * (off + lo), (size_t)U64_RNG_BYTES * cnt,
+                                    cudaMemcpyHostToDevice, st));
+            int rc = prove_part(c, st, sub_ws(c, sp, k), (const uint64_t *)c->d_in_a + lo, c->d_in_b + 32 * lo, c->d_in_c + (size_t)U64_RNG_BYTES * lo,
+                                init, c->d_out + (size_t)U64_PROOF_BYTES_COMPRESSED * lo, c->d_status + lo);
+            if (rc != BPPP_OK) return rc;
+            CUDA_OK(cudaMemcpyAsync(proofs_out + (size_t)U64_PROOF_BYTES_COMPRESSED * (off + lo), c->d_out + (size_t)U64_PROOF_BYTES_COMPRESSED * lo,
+                                    (size_t)U64_PROOF_BYTES_COMPRESSED * cnt, cudaMemcpyDeviceToHost, st));
+            CUDA_OK(cudaMemcpyAsync(status + off + lo, c->d_status + lo, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
+        }
+        for (int k = 0; k < sp.parts; k++) CUDA_OK(cudaStreamSynchronize(sp.parts == 1 ? c->stream : c->sub_stream[k]));
+    }
+    return BPPP_OK;
+}
+

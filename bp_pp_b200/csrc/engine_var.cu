@@ -1,0 +1,29 @@
+// libbppp.so, variable-base translation unit: the joint Straus ladders over per-proof points
+// (one thread per proof, tables of 1P..8P per point in thread-local memory).
+#include "engine_common.cuh"
+
+using namespace bppp;
+
+#ifndef BPPP_VAR_BLOCK
+#define BPPP_VAR_BLOCK 64
+#endif
+#ifndef BPPP_VAR_MINBLOCKS
+#define BPPP_VAR_MINBLOCKS 7
+#endif
+__global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_v_var5(WS w) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w.n) u64v_var5_one(w, i);
+}
+__global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_v_var2(WS w, int j) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w.n) u64v_var2_one(w, i, j);
+}
+__global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_p_var2(WS w, int j) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w.n) u64p_var2_one(w, i, j);
+}
+namespace bppp {
+void launch_v_var5(bppp_ctx *c, cudaStream_t st, WS w) { LAUNCH(c, k_v_var5, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w); }
+void launch_v_var2(bppp_ctx *c, cudaStream_t st, WS w, int j) { LAUNCH(c, k_v_var2, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j); }
+void launch_p_var2(bppp_ctx *c, cudaStream_t st, WS w, int j) { LAUNCH(c, k_p_var2, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j); }
+}  // namespace bppp

@@ -1,0 +1,112 @@
+// libbppp.so, verify translation unit: U64RangeProofProtocol::verify over a batch (u64_proof.rs:42-54).
+#include "engine_common.cuh"
+
+using namespace bppp;
+
+static int fail(int code, const std::string &msg) { return engine_fail(code, msg); }
+
+__global__ void __launch_bounds__(64) k_v_load(WS w, const uint8_t *commits, const uint8_t *proofs, int fmt) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w.n) return;
+    size_t csz = fmt == FMT_COMPRESSED ? 33 : 64, psz = fmt == FMT_COMPRESSED ? U64_PROOF_BYTES_COMPRESSED : U64_PROOF_BYTES_AFFINE;
+    u64v_load_one(w, i, commits + csz * i, proofs + psz * i, fmt);
+}
+__global__ void __launch_bounds__(64) k_v_phase1(WS w, Merlin init) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w.n) u64v_phase1_one(w, i, init);
+}
+__global__ void __launch_bounds__(64) k_v_round(WS w, int j) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w.n) u64v_round_one(w, i, j);
+}
+__global__ void __launch_bounds__(64) k_v_final_scalars(WS w) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w.n) u64v_final_scalars_one(w, i);
+}
+__global__ void __launch_bounds__(64) k_v_verdict(WS w, int32_t *status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w.n) return;
+    u64v_verdict_one(w, i);
+    status[i] = (int32_t)ws_ld(w, i, VL::STATUS);
+}
+
+// ---- verify ----
+static int verify_part(bppp_ctx *c, cudaStream_t st, WS w, const uint8_t *d_commits, const uint8_t *d_proofs, int fmt,
+                       const Merlin &init, int32_t *d_status) {
+    const size_t n = w.n;
+    const unsigned g64 = nblocks(n, 64);
+    LAUNCH(c, k_v_load, g64, 64, w, d_commits, d_proofs, fmt);
+    launch_batch_inv(c, st, w, VL::VP + 20, VL::ZINV);
+    LAUNCH(c, k_v_phase1, g64, 64, w, init);
+    TermMap tm = identity_map();
+    launch_msm_fixed(c, st, w, VL::FS, tm, 17, VL::ACC);      // pt = ps_tau g + <g_vec, pn_tau>  (circuit.rs:206)
+    launch_v_var5(c, st, w);
+    for (int j = 0; j < 4; j++) {
+        launch_batch_inv(c, st, w, VL::COM + 20, VL::ZINV);
+        LAUNCH(c, k_v_round, g64, 64, w, j);
+        launch_v_var2(c, st, w, j);
+    }
+    LAUNCH(c, k_v_final_scalars, g64, 64, w);
+    launch_msm_fixed(c, st, w, VL::FS, tm, NUM_GENS, VL::ACC);  // commit(l, n) over the original generators
+    LAUNCH(c, k_v_verdict, g64, 64, w, d_status);
+    CUDA_OK(cudaGetLastError());
+    return BPPP_OK;
+}
+
+static int verify_slice(bppp_ctx *c, cudaStream_t st, size_t n, const uint8_t *d_commits, const uint8_t *d_proofs, int fmt,
+                        const Merlin &init, int32_t *d_status) {
+    const size_t csz = fmt == FMT_COMPRESSED ? 33 : 64, psz = fmt == FMT_COMPRESSED ? U64_PROOF_BYTES_COMPRESSED : U64_PROOF_BYTES_AFFINE;
+    SubPlan sp = plan_sub(c, n);
+    int rc = fork_streams(c, st, sp);
+    if (rc != BPPP_OK) return rc;
+    for (int k = 0; k < sp.parts; k++) {
+        cudaStream_t s = sp.parts == 1 ? st : c->sub_stream[k];
+        rc = verify_part(c, s, sub_ws(c, sp, k), d_commits + csz * sp.lo[k], d_proofs + psz * sp.lo[k], fmt, init, d_status + sp.lo[k]);
+        if (rc != BPPP_OK) return rc;
+    }
+    return join_streams(c, st, sp);
+}
+
+extern "C" int bppp_u64_verify_batch_dev(bppp_ctx *c, size_t n, const void *d_commits, const void *d_proofs, int fmt,
+                                         const uint8_t *label, size_t label_len, void *d_status, void *stream) {
+    if (!c || (n && (!d_commits || !d_proofs || !d_status))) return fail(BPPP_ERR_ARG, "null argument");
+    if (fmt != FMT_COMPRESSED && fmt != FMT_AFFINE64) return fail(BPPP_ERR_ARG, "bad point format");
+    CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in the CUDA runtime
+    Merlin init; merlin_init(init, label, (uint32_t)label_len);
+    size_t csz = fmt == FMT_COMPRESSED ? 33 : 64, psz = fmt == FMT_COMPRESSED ? U64_PROOF_BYTES_COMPRESSED : U64_PROOF_BYTES_AFFINE;
+    for (size_t off = 0; off < n; off += c->max_batch) {
+        size_t m = n - off < c->max_batch ? n - off : c->max_batch;
+        int rc = verify_slice(c, st, m, (const uint8_t *)d_commits + csz * off, (const uint8_t *)d_proofs + psz * off, fmt, init,
+                              (int32_t *)d_status + off);
+        if (rc != BPPP_OK) return rc;
+    }
+    return BPPP_OK;
+}
+
+extern "C" int bppp_u64_verify_batch(bppp_ctx *c, size_t n, const uint8_t *commits, const uint8_t *proofs, int fmt,
+                                     const uint8_t *label, size_t label_len, int32_t *status) {
+    if (!c || (n && (!commits || !proofs || !status))) return fail(BPPP_ERR_ARG, "null argument");
+    if (fmt != FMT_COMPRESSED && fmt != FMT_AFFINE64) return fail(BPPP_ERR_ARG, "bad point format");
+    CUDA_OK(cudaSetDevice(c->device));
+    size_t csz = fmt == FMT_COMPRESSED ? 33 : 64, psz = fmt == FMT_COMPRESSED ? U64_PROOF_BYTES_COMPRESSED : U64_PROOF_BYTES_AFFINE;
+    Merlin init; merlin_init(init, label, (uint32_t)label_len);
+    // each sub-batch copies in, runs its kernel sequence and copies out on its own stream, so the transfers of one
+    // sub-batch overlap with the kernels of the others (pinned host buffers make the copies truly asynchronous)
+    for (size_t off = 0; off < n; off += c->max_batch) {
+        size_t m = n - off < c->max_batch ? n - off : c->max_batch;
+        SubPlan sp = plan_sub(c, m);
+        for (int k = 0; k < sp.parts; k++) {
+            cudaStream_t st = sp.parts == 1 ? c->stream : c->sub_stream[k];
+            size_t lo = sp.lo[k], cnt = sp.lo[k + 1] - sp.lo[k];
+            CUDA_OK(cudaMemcpyAsync(c->d_in_a + csz * lo, commits + csz * (off + lo), csz * cnt, cudaMemcpyHostToDevice, st));
+            CUDA_OK(cudaMemcpyAsync(c->d_in_b + psz * lo, proofs + psz * (off + lo), psz * cnt, cudaMemcpyHostToDevice, st));
+            int rc = verify_part(c, st, sub_ws(c, sp, k), c->d_in_a + csz * lo, c->d_in_b + psz * lo, fmt, init, c->d_status + lo);
+            if (rc != BPPP_OK) return rc;
+            CUDA_OK(cudaMemcpyAsync(status + off + lo, c->d_status + lo, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
+        }
+        for (int k = 0; k < sp.parts; k++) CUDA_OK(cudaStreamSynchronize(sp.parts == 1 ? c->stream : c->sub_stream[k]));
+    }
+    return BPPP_OK;
+}
+

@@ -192,24 +192,13 @@ BPPP_HD void u64v_phase1_one(const WS &w, size_t i, const Merlin &init) {
     if (zero_inv) set_status(w, i, ST_PANIC_INVERT_ZERO);
 }
 
-// joint variable-base sum_k ks[k] * pts[k] + init, signed 4-bit windows, shared doublings
+// joint variable-base sum_k ks[k] * pts[k] + init: GLV halves, signed 4-bit windows, 128 shared doublings
 template <int NP>
 BPPP_HD Pt straus_var(const PtA *pts, const bool *ident, const Sc *ks, const Pt &init) {
     PtTable8 tab[NP];
-    Digits4 dg[NP];
 #pragma unroll 1
-    for (int k = 0; k < NP; k++) { pt_table8_build(tab[k], pt_from_affine(pts[k], ident[k])); dg[k] = sc_signed_digits4(ks[k]); }
-    Pt acc = pt_identity();   // init is added last (it must not be doubled)
-#pragma unroll 1
-    for (int k = 0; k < NP; k++) acc = pt_add(acc, pt_table8_get(tab[k], digits4_get(dg[k], 64)));
-#pragma unroll 1
-    for (int d = 63; d >= 0; d--) {
-#pragma unroll 1
-        for (int r = 0; r < 4; r++) acc = pt_double(acc);
-#pragma unroll 1
-        for (int k = 0; k < NP; k++) acc = pt_add(acc, pt_table8_get(tab[k], digits4_get(dg[k], d)));
-    }
-    return pt_add(acc, init);
+    for (int k = 0; k < NP; k++) pt_table8_build(tab[k], pt_from_affine(pts[k], ident[k]));
+    return pt_add(straus_glv<NP>(tab, ks), init);   // init is added last (it must not be doubled)
 }
 
 // Phase 2b: com_0 = ACC (fixed part) + tau^-1 c_s - delta c_o + tau c_l - tau^2 c_r + 2 tau^3 V'

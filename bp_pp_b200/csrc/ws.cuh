@@ -72,7 +72,7 @@ BPPP_HD bool merlin_challenge_scalar(Merlin &m, const char *label, uint32_t labe
     return sc_from_be32(out, b);
 }
 
-// status codes shared by the device code, the C ABI (include/bppp.h) and the oracle
+// status codes shared by the device code and the C ABI (include/bppp.h)
 enum : int32_t {
     ST_FALSE = 0, ST_TRUE = 1,
     ST_PANIC_INVERT_ZERO = -1,     // reference: Scalar::invert().unwrap() on zero

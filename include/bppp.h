@@ -24,7 +24,8 @@
  *             reference would have panicked or failed to deserialise).  Functions return 0 or BPPP_ERR_*
  *             and never unwind.
  *   buffers   caller-owned.  `_dev` variants take device pointers valid on the context's GPU and a
- *             CUDA stream handle (cudaStream_t as void*), enqueue work and return without synchronising.
+ *             CUDA stream handle (cudaStream_t as void*; NULL = the legacy default stream), enqueue work and return
+ *             without synchronising; internally the batch fans out over sub-streams that fork from / join into it.
  *   threading a context is single-owner (one host thread per context / GPU).
  */
 #ifndef BPPP_H
@@ -94,11 +95,16 @@ int bppp_u64_prove_batch_dev(bppp_ctx *ctx, size_t n, const void *d_x, const voi
 /* number of kernels launched by this context since creation (for the bench's gpu_launches claim) */
 uint64_t bppp_launch_count(const bppp_ctx *ctx);
 
+/* Per-kernel device timing of everything launched between begin and end (CUDA events on the launching
+ * stream).  end() synchronises and fills up to n_max (name[48], total ms, launch count) triples. */
+int bppp_ctx_profile_begin(bppp_ctx *ctx);
+int bppp_ctx_profile_end(bppp_ctx *ctx, char *names48, double *total_ms, uint32_t *counts, int n_max, int *n_out);
+
 /* Integer-pipe microbenchmarks on `device`: fills out[0..8) with
  *   [0] IMAD.WIDE.U32 multiply-accumulates/s   [1] fe_mul/s   [2] fe_sqr/s   [3] sc_mul/s
  *   [4] mixed point additions/s   [5] point doublings/s   [6] full point additions/s   [7] SM clock MHz seen
  * Used to state the integer roofline the path is bound by. */
-int bppp_microbench(int device, double *out, int n_out);
+int bppp_microbench(int device, double *out, int n_out);   /* n_out >= 10 also fills [8] IMAD/s, [9] IADD/s */
 
 #ifdef __cplusplus
 }

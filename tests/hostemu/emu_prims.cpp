@@ -53,6 +53,14 @@ int emu_pt_add_mixed_proj(const uint8_t *p, const uint8_t *q, uint8_t *r) {
 }
 int emu_pt_double(const uint8_t *p, uint8_t *r) { int s; Pt a = load_pt(p, &s); if (s < 0) return -1; store_pt(r, pt_double(a)); return 0; }
 int emu_pt_mul(const uint8_t *p, const uint8_t *k, uint8_t *r) { int s; Pt a = load_pt(p, &s); Sc kk; if (s < 0 || !sc_from_be32(kk, k)) return -1; store_pt(r, pt_mul(a, kk)); return 0; }
+int emu_pt_mul_glv(const uint8_t *p, const uint8_t *k, uint8_t *r) { int s; Pt a = load_pt(p, &s); Sc kk; if (s < 0 || !sc_from_be32(kk, k)) return -1; store_pt(r, pt_mul_glv(a, kk)); return 0; }
+// GLV split: out = k1 (16 B BE) || k2 (16 B BE) || neg1 || neg2
+void emu_glv_split(const uint8_t *k, uint8_t *out) {
+    Sc kk; sc_from_be32(kk, k);
+    GlvSplit g = glv_split(kk);
+    for (int i = 0; i < 4; i++) for (int b = 0; b < 4; b++) { out[15 - (4 * i + b)] = (uint8_t)(g.k1[i] >> (8 * b)); out[31 - (4 * i + b)] = (uint8_t)(g.k2[i] >> (8 * b)); }
+    out[32] = g.neg1; out[33] = g.neg2;
+}
 int emu_pt_equal(const uint8_t *p, const uint8_t *q, const uint8_t *k) {
     // compare k*p (projective, non-trivial Z) against q
     int s1, s2; Pt a = load_pt(p, &s1), b = load_pt(q, &s2); Sc kk; sc_from_be32(kk, k);

@@ -1,0 +1,57 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/bppp.h declares; no GPU => loud failure."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, has_cuda
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "bppp.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bppp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from bp_pp_b200._lib import EXPORTS, lib
+    L = lib()
+    declared = _header_functions()
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(L, name), f"libbppp.so does not export {name}"
+    assert sorted(EXPORTS) == declared
+
+
+def test_signatures_use_plain_c_types_only():
+    text = open(os.path.join(ROOT, "include", "bppp.h")).read()
+    assert "torch" not in text and "at::" not in text and "std::" not in text
+    assert 'extern "C"' in text
+
+
+@pytest.mark.skipif(has_cuda(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_without_a_gpu():
+    import bp_pp_b200 as B
+    with pytest.raises(B.BpppError) as ei:
+        B.Context(b"\0" * 64 * 49)
+    assert "-11" in str(ei.value) and "no CPU fallback" in str(ei.value)
+    with pytest.raises(B.BpppError):
+        B.microbench(0)
+
+
+def test_argument_validation_in_the_binding():
+    import bp_pp_b200 as B
+    with pytest.raises(ValueError):
+        B.Context(b"\0" * 10)
+    assert B.U64RangeProofProtocol.u64_to_hex(0x1234) == [4, 3, 2, 1] + [0] * 12
+    assert B.U64RangeProofProtocol.u64_to_hex_mapped(0x1123)[:4] == [12, 2, 1, 1]
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "bp_pp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower(), f"{f} mentions the oracle"

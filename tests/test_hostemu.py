@@ -1,0 +1,188 @@
+"""CPU suite: the DEVICE arithmetic and per-proof phase logic (bp_pp_b200/csrc/*.cuh) compiled for the host
+with magnitude assertions, against the oracles.  This is how the kernels' code is exercised without a GPU."""
+import ctypes as C
+import random
+
+from conftest import synth_batch, xy
+
+LABEL = b"u64 range proof"
+
+
+def B(b):
+    return (C.c_uint8 * max(1, len(b))).from_buffer_copy(b if len(b) else b"\0")
+
+
+def O(n):
+    return (C.c_uint8 * n)()
+
+
+def be(x):
+    return x.to_bytes(32, "big")
+
+
+def test_field_ops(emu_prims, ref):
+    L, P = emu_prims, ref.P
+    rnd = random.Random(7)
+    edge = [0, 1, 2, P - 1, P - 2, P, P + 1, 2**256 - 1, 2**255, 977, 2**32 + 977, (1 << 26) - 1, (1 << 52) - 1]
+    vals = edge + [rnd.randrange(2**256) for _ in range(150)]
+    for a in vals:
+        o = O(32); L.emu_fe_norm(B(be(a)), o); assert int.from_bytes(o, "big") == a % P
+        o = O(32); L.emu_fe_sqr(B(be(a)), o); assert int.from_bytes(o, "big") == a * a % P
+        b, c, d = rnd.choice(vals), rnd.choice(vals), rnd.choice(vals)
+        o = O(32); L.emu_fe_mul(B(be(a)), B(be(b)), o); assert int.from_bytes(o, "big") == a * b % P
+        k1, k2 = rnd.randrange(1, 8), rnd.randrange(1, 8)
+        o = O(32); L.emu_fe_expr(B(be(a)), B(be(b)), B(be(c)), B(be(d)), k1, k2, o)
+        assert int.from_bytes(o, "big") == (a * k1 + b * k2 - c) * d % P
+    for a in vals[:40]:
+        o = O(32); L.emu_fe_inv(B(be(a)), o); assert int.from_bytes(o, "big") == pow(a % P, P - 2, P)
+        sq = a * a % P
+        o = O(32); ok = L.emu_fe_sqrt(B(be(sq)), o); r = int.from_bytes(o, "big")
+        assert ok == 1 and r * r % P == sq
+
+
+def test_scalar_ops(emu_prims, ref):
+    L, N = emu_prims, ref.N
+    rnd = random.Random(8)
+    vals = [0, 1, 2, N - 1, N - 2, 2**255, 2**128, 2**129 - 1, (1 << 32) - 1] + [rnd.randrange(N) for _ in range(150)]
+    for a in vals:
+        b = rnd.choice(vals)
+        o = O(32); L.emu_sc_mul(B(be(a)), B(be(b)), o); assert int.from_bytes(o, "big") == a * b % N
+        o = O(32); L.emu_sc_add(B(be(a)), B(be(b)), o); assert int.from_bytes(o, "big") == (a + b) % N
+        o = O(32); L.emu_sc_sub(B(be(a)), B(be(b)), o); assert int.from_bytes(o, "big") == (a - b) % N
+        o = O(32); L.emu_sc_neg(B(be(a)), o); assert int.from_bytes(o, "big") == (-a) % N
+    for a in vals[1:25]:
+        o = O(32); L.emu_sc_inv(B(be(a)), o); assert int.from_bytes(o, "big") == pow(a, -1, N)
+    for w in [b"\xff" * 64, b"\0" * 64, N.to_bytes(64, "big"), (N * N - 1).to_bytes(64, "big")] + [rnd.randbytes(64) for _ in range(100)]:
+        o = O(32); L.emu_sc_wide(B(w), o); assert int.from_bytes(o, "big") == int.from_bytes(w, "big") % N
+    assert L.emu_sc_from_repr(B(be(N))) == 0 and L.emu_sc_from_repr(B(be(N - 1))) == 1
+
+
+def test_group_law_complete_formulas(emu_prims, ref):
+    L, N = emu_prims, ref.N
+    rnd = random.Random(9)
+    unxy = lambda b: None if b == b"\0" * 64 else (int.from_bytes(b[:32], "big"), int.from_bytes(b[32:], "big"))  # noqa: E731
+    pts = [ref.pt_mul(ref.G, rnd.randrange(1, N)) for _ in range(6)]
+    cases = []
+    for p in pts:
+        cases += [(p, rnd.choice(pts)), (p, p), (p, ref.pt_neg(p)), (p, None), (None, p), (None, None)]
+    for p, q in cases:   # identity, P+P and P+(-P) all go through the same branch-free code
+        o = O(64); assert L.emu_pt_add(B(xy(p)), B(xy(q)), o) == 0; assert unxy(bytes(o)) == ref.pt_add(p, q)
+        if q is not None:
+            o = O(64); assert L.emu_pt_add_mixed(B(xy(p)), B(xy(q)), o) == 0; assert unxy(bytes(o)) == ref.pt_add(p, q)
+            o = O(64); assert L.emu_pt_add_mixed_proj(B(xy(p)), B(xy(q)), o) == 0
+            assert unxy(bytes(o)) == ref.pt_add(ref.pt_mul(p, 3), q)
+        o = O(64); assert L.emu_pt_double(B(xy(p)), o) == 0; assert unxy(bytes(o)) == ref.pt_add(p, p)
+    for p in pts[:3] + [None]:
+        for k in [0, 1, 2, 8, 15, 16, N - 1, N - 2, 2**255, int("8" * 64, 16) % N, rnd.randrange(N)]:
+            o = O(64); assert L.emu_pt_mul(B(xy(p)), B(be(k)), o) == 0; assert unxy(bytes(o)) == ref.pt_mul(p, k)
+            assert L.emu_pt_equal(B(xy(p)), B(xy(ref.pt_mul(p, k))), B(be(k))) == 1
+            assert L.emu_pt_equal(B(xy(p)), B(xy(ref.pt_add(ref.pt_mul(p, k), ref.G))), B(be(k))) == 0
+
+
+def test_glv_split_and_multiplication(emu_prims, ref):
+    L, N = emu_prims, ref.N
+    lam = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
+    rnd = random.Random(13)
+    unxy = lambda b: None if b == b"\0" * 64 else (int.from_bytes(b[:32], "big"), int.from_bytes(b[32:], "big"))  # noqa: E731
+    ks = [0, 1, 2, N - 1, N - 2, N // 2, N // 2 + 1, lam, N - lam, 2**255 % N, 2**128, 2**128 - 1] + [rnd.randrange(N) for _ in range(300)]
+    for k in ks:
+        o = O(34); L.emu_glv_split(B(be(k)), o)
+        k1, k2 = int.from_bytes(bytes(o[:16]), "big"), int.from_bytes(bytes(o[16:32]), "big")
+        if o[32]: k1 = -k1
+        if o[33]: k2 = -k2
+        assert (k1 + k2 * lam - k) % N == 0 and abs(k1) < 2**128 and abs(k2) < 2**128
+    p = ref.pt_mul(ref.G, rnd.randrange(1, N))
+    for q in [p, None]:
+        for k in ks[:40]:
+            o = O(64); assert L.emu_pt_mul_glv(B(xy(q)), B(be(k)), o) == 0
+            assert unxy(bytes(o)) == ref.pt_mul(q, k), hex(k)
+
+
+def test_point_encodings(emu_prims, ref):
+    L = emu_prims
+    rnd = random.Random(10)
+    for _ in range(8):
+        p = ref.pt_mul(ref.G, rnd.randrange(1, ref.N))
+        c = ref.pt_to_bytes(p)
+        o = O(64); assert L.emu_pt_decompress(B(c), o) == 0 and bytes(o) == xy(p)
+        o = O(33); assert L.emu_pt_compress(B(xy(p)), o) == 0 and bytes(o) == c
+    o = O(64); assert L.emu_pt_decompress(B(b"\0" * 33), o) == 1          # identity
+    o = O(33); assert L.emu_pt_compress(B(b"\0" * 64), o) == 1 and bytes(o) == b"\0" * 33
+    x = 5
+    while True:
+        try:
+            ref.pt_from_bytes(b"\x02" + be(x)); x += 1
+        except ValueError:
+            break
+    assert L.emu_pt_decompress(B(b"\x02" + be(x)), O(64)) == -1           # x not on the curve
+    assert L.emu_pt_decompress(B(b"\x04" + be(ref.GX)), O(64)) == -1        # bad tag
+    assert L.emu_pt_decompress(B(b"\x02" + be(ref.P)), O(64)) == -1         # x >= p
+    bad = bytearray(xy(ref.G)); bad[63] ^= 1
+    assert L.emu_pt_compress(B(bytes(bad)), O(33)) == -1                    # off-curve affine input
+
+
+def test_keccak_and_merlin(emu_prims, ref):
+    L = emu_prims
+    rnd = random.Random(12)
+    lanes = [rnd.randrange(2**64) for _ in range(25)]
+    arr = (C.c_uint64 * 25)(*lanes); L.emu_keccak(arr); assert list(arr) == ref.keccak_f1600(lanes)
+    o = O(32); L.emu_merlin_simple(B(b"test protocol"), 13, b"some label", 10, B(b"some data"), 9, b"challenge", 9, o, 32)
+    assert bytes(o).hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+    msg = rnd.randbytes(33)
+    o = O(32 * 20); L.emu_merlin_long(B(LABEL), len(LABEL), B(msg), 33, 20, o)
+    t = ref.Transcript(LABEL); exp = b""
+    for i in range(20):   # crosses the 166-byte STROBE rate several times
+        t.append_message(b"wnla_com", msg); t.append_u64(b"l.sz", 32 >> (i & 3)); exp += t.challenge_bytes(b"wnla_challenge", 32)
+    assert bytes(o) == exp
+
+
+def _emu_ctx(emu_u64, gens64, W=4):
+    return C.c_void_p(emu_u64.emu_ctx_create(B(gens64), W))
+
+
+def test_device_verify_logic_matches_oracle(emu_u64, ref, oracle, gens64):
+    n = 6
+    xs, blinds, rngs = synth_batch(ref, n)
+    proofs, st = oracle.u64_prove_batch(gens64, xs, blinds, rngs, LABEL, 4)
+    commits = b"".join(oracle.u64_commit(gens64, xs[i], blinds[32 * i:32 * i + 32]) for i in range(n))
+    ctx = _emu_ctx(emu_u64, gens64)
+    status = (C.c_int32 * n)()
+    emu_u64.emu_u64_verify_batch(ctx, C.c_size_t(n), B(commits), B(proofs), 0, B(LABEL), len(LABEL), status)
+    assert list(status) == [1] * n
+    bad = bytearray(proofs)
+    for i, pos in enumerate([400, 5, 470, 500, 140, 0]):
+        bad[525 * i + pos] ^= 1
+    emu_u64.emu_u64_verify_batch(ctx, C.c_size_t(n), B(commits), B(bytes(bad)), 0, B(LABEL), len(LABEL), status)
+    assert list(status) == oracle.u64_verify_batch(gens64, commits, bytes(bad), LABEL, 4)
+    # 64-byte affine input format gives the same verdicts
+    def to_affine_rec(rec):
+        pts = [oracle.point_decompress(rec[33 * k:33 * k + 33]) for k in range(12)]
+        return b"".join(pts) + rec[396:492] + oracle.point_decompress(rec[492:525])
+    aff = b"".join(to_affine_rec(proofs[525 * i:525 * i + 525]) for i in range(n))
+    acom = b"".join(oracle.point_decompress(commits[33 * i:33 * i + 33]) for i in range(n))
+    emu_u64.emu_u64_verify_batch(ctx, C.c_size_t(n), B(acom), B(aff), 1, B(LABEL), len(LABEL), status)
+    assert list(status) == [1] * n
+    emu_u64.emu_ctx_destroy(ctx)
+
+
+def test_device_prove_logic_matches_oracle(emu_u64, ref, oracle, gens64):
+    n = 5
+    xs, blinds, rngs = synth_batch(ref, n)   # includes x = 0, 1, 2^64 - 1
+    proofs, st = oracle.u64_prove_batch(gens64, xs, blinds, rngs, LABEL, 4)
+    ctx = _emu_ctx(emu_u64, gens64, W=5)      # a window width that does not divide 32
+    out = (C.c_uint8 * (525 * n))(); status = (C.c_int32 * n)()
+    xa = (C.c_uint64 * n)(*xs)
+    emu_u64.emu_u64_prove_batch(ctx, C.c_size_t(n), xa, B(blinds), B(rngs), B(LABEL), len(LABEL), out, status)
+    assert list(status) == [1] * n
+    assert bytes(out) == proofs
+    emu_u64.emu_ctx_destroy(ctx)
+
+
+def test_device_prove_matches_golden(emu_u64, ref, golden, gens64):
+    c = golden["cases"][0]
+    ctx = _emu_ctx(emu_u64, gens64)
+    out = (C.c_uint8 * 525)(); status = (C.c_int32 * 1)()
+    xa = (C.c_uint64 * 1)(c["x"])
+    emu_u64.emu_u64_prove_batch(ctx, C.c_size_t(1), xa, B(bytes.fromhex(c["blind"])), B(ref.synth_rng_bytes(c["rng_index"])), B(LABEL), len(LABEL), out, status)
+    assert bytes(out).hex() == c["proof"]
+    emu_u64.emu_ctx_destroy(ctx)

@@ -1,0 +1,197 @@
+"""CPU suite: the oracles against known answers, each other and the frozen golden vectors."""
+import hashlib
+import json
+import os
+import random
+
+import pytest
+
+from conftest import ROOT, xy
+
+LABEL = b"u64 range proof"
+
+
+def test_keccak_matches_hashlib(ref):
+    st = bytearray(200)
+    st[0] ^= 0x06
+    st[135] ^= 0x80
+    ref.keccak_f1600_bytes(st)
+    assert bytes(st[:32]) == hashlib.sha3_256(b"").digest()
+
+
+def test_merlin_known_answer(ref, oracle):
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "merlin_kat.json")))["merlin_simple"]
+    t = ref.Transcript(b"test protocol")
+    t.append_message(b"some label", b"some data")
+    got = t.challenge_bytes(b"challenge", 32).hex()
+    assert got == kat["challenge32"] == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+    assert oracle.merlin_simple(b"test protocol", b"some label", b"some data", b"challenge", 32).hex() == got
+
+
+def test_group_law_matches_openssl(ref, oracle):
+    from cryptography.hazmat.primitives import serialization
+    from cryptography.hazmat.primitives.asymmetric import ec
+    rnd = random.Random(5)
+    for k in [1, 2, 3, ref.N - 1] + [rnd.randrange(1, ref.N) for _ in range(6)]:
+        pk = ec.derive_private_key(k, ec.SECP256K1()).public_key()
+        comp = pk.public_bytes(serialization.Encoding.X962, serialization.PublicFormat.CompressedPoint)
+        assert ref.pt_to_bytes(ref.pt_mul(ref.G, k)) == comp
+        assert ref.pt_from_bytes(comp) == ref.pt_mul(ref.G, k)
+        assert oracle.point_compress(oracle.point_mul(xy(ref.G), k.to_bytes(32, "big"))) == comp
+        # variable base through ECDH
+        k2 = rnd.randrange(1, ref.N)
+        shared = ec.derive_private_key(k2, ec.SECP256K1()).exchange(ec.ECDH(), pk)
+        assert ref.pt_mul(ref.pt_mul(ref.G, k), k2)[0].to_bytes(32, "big") == shared
+
+
+def test_curve_constants(ref):
+    assert ref.on_curve(ref.G) and ref.pt_mul(ref.G, ref.N) is None
+    lam = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
+    beta = 0x7AE96A2B657C07106E64479EAC3434E99CF0497512F58995C1396C28719501EE
+    assert pow(lam, 3, ref.N) == 1 and pow(beta, 3, ref.P) == 1
+    assert ref.pt_mul(ref.G, lam) == (beta * ref.GX % ref.P, ref.GY)
+
+
+def test_c_oracle_field_and_scalar_ops(ref, oracle):
+    rnd = random.Random(11)
+    be = lambda v: v.to_bytes(32, "big")  # noqa: E731
+    for a in [0, 1, ref.P - 1, 2**255] + [rnd.randrange(ref.P) for _ in range(40)]:
+        b = rnd.randrange(ref.P)
+        assert int.from_bytes(oracle.fe_mul(be(a), be(b)), "big") == a * b % ref.P
+    for a in [1, ref.N - 1, 2**255 % ref.N] + [rnd.randrange(1, ref.N) for _ in range(40)]:
+        b = rnd.randrange(ref.N)
+        assert int.from_bytes(oracle.sc_mul(be(a), be(b)), "big") == a * b % ref.N
+        assert int.from_bytes(oracle.sc_inv(be(a)), "big") == pow(a, -1, ref.N)
+    for w in [b"\xff" * 64, b"\0" * 64] + [rnd.randbytes(64) for _ in range(40)]:
+        assert int.from_bytes(oracle.sc_from_wide(w), "big") == int.from_bytes(w, "big") % ref.N
+    with pytest.raises(ZeroDivisionError):
+        oracle.sc_inv(be(0))
+
+
+def test_golden_generators_are_the_seeded_ones(ref, golden):
+    g, gv, hv = ref.synth_generators()
+    assert [xy(p).hex() for p in [g] + gv + hv] == golden["generators"]
+
+
+def test_c_oracle_reproduces_golden_proofs(ref, oracle, golden, gens64):
+    cases = golden["cases"]
+    xs = [c["x"] for c in cases]
+    blinds = b"".join(bytes.fromhex(c["blind"]) for c in cases)
+    rngs = b"".join(ref.synth_rng_bytes(c["rng_index"]) for c in cases)
+    for c in cases:
+        assert hashlib.sha256(ref.synth_rng_bytes(c["rng_index"])).hexdigest() == c["rng_sha256"]
+    proofs, st = oracle.u64_prove_batch(gens64, xs, blinds, rngs, LABEL, 4)
+    assert st == [0] * len(cases)
+    for i, c in enumerate(cases):
+        assert proofs[525 * i:525 * i + 525].hex() == c["proof"]
+        assert oracle.u64_commit(gens64, c["x"], bytes.fromhex(c["blind"])).hex() == c["commitment"]
+    commits = b"".join(bytes.fromhex(c["commitment"]) for c in cases)
+    assert oracle.u64_verify_batch(gens64, commits, proofs, LABEL, 4) == [1] * len(cases)
+
+
+def test_python_oracle_reproduces_a_golden_proof(ref, golden):
+    g, gv, hv = ref.synth_generators()
+    pub = ref.U64RangeProofProtocol(g, gv, hv)
+    c = golden["cases"][0]
+    s = int.from_bytes(bytes.fromhex(c["blind"]), "big")
+    proof = pub.prove(c["x"], s, ref.Transcript(LABEL), ref.ByteRng(ref.synth_rng_bytes(c["rng_index"])))
+    assert ref.serialize_reciprocal_proof(proof).hex() == c["proof"]
+    assert ref.reciprocal_proof_to_json_obj(proof) == c["json"]
+    assert pub.verify(ref.pt_from_bytes(bytes.fromhex(c["commitment"])), proof, ref.Transcript(LABEL))
+
+
+def test_golden_tamper_verdicts(oracle, golden, gens64):
+    c = golden["cases"][0]
+    rec, com = bytes.fromhex(c["proof"]), bytes.fromhex(c["commitment"])
+    for t in golden["tampers_case0"]:
+        bad = bytearray(rec)
+        bad[t["pos"]] ^= 1 << t["bit"]
+        assert oracle.u64_verify_batch(gens64, com, bytes(bad), LABEL, 1) == [t["verdict"]], t
+    assert oracle.u64_verify_batch(gens64, com, rec, b"u64 range prooF", 1) == [golden["other_case0"]["wrong_label"]] == [0]
+
+
+def test_structure_counts_of_a_u64_proof(ref, golden):
+    # 13 points + 3 scalars, 4 WNLA rounds (README.md:30-34)
+    pr = ref.deserialize_u64_proof(bytes.fromhex(golden["cases"][0]["proof"]))
+    assert len(pr.circuit_proof.r) == len(pr.circuit_proof.x) == 4
+    assert len(pr.circuit_proof.l) == 2 and len(pr.circuit_proof.n) == 1
+
+
+def test_wnla_golden_and_round_trip(ref, oracle):
+    wn = json.load(open(os.path.join(ROOT, "tests", "golden", "wnla_golden.json")))
+    b = bytes.fromhex
+    g, gvec, hvec = b(wn["g"]), b"".join(b(p) for p in wn["g_vec"]), b"".join(b(p) for p in wn["h_vec"])
+    c = b"".join(b(v) for v in wn["c"])
+    rho = b(wn["rho"])
+    rho_i = int.from_bytes(rho, "big")
+    mu = (rho_i * rho_i % ref.N).to_bytes(32, "big")
+    l = b"".join(v.to_bytes(32, "big") for v in wn["l"])
+    n = b"".join(v.to_bytes(32, "big") for v in wn["n"])
+    com = oracle.wnla_commit(g, gvec, hvec, c, rho, mu, l, n)
+    assert com.hex() == wn["commitment"]
+    r, x, lo, no = oracle.wnla_prove(g, gvec, hvec, c, rho, mu, com, l, n, b"wnla test")
+    assert (r + x + lo + no).hex() == wn["proof"]
+    assert oracle.wnla_verify(g, gvec, hvec, c, rho, mu, com, r, x, lo, no, b"wnla test") == 1
+    bad = bytearray(lo)
+    bad[31] ^= 1
+    assert oracle.wnla_verify(g, gvec, hvec, c, rho, mu, com, r, x, bytes(bad), no, b"wnla test") == 0
+    # x.len() != r.len() is the only early `false` (wnla.rs:76-78)
+    assert oracle.wnla_verify(g, gvec, hvec, c, rho, mu, com, r, x + x, lo, no, b"wnla test") == 0
+
+
+def test_ac_works_circuit(ref, oracle):
+    """The reference's `ac_works` (src/tests.rs:44-136): x + y = r, x * y = z, through both oracles."""
+    N = ref.N
+    x, y, r, z = 3, 5, 8, 15
+    pts = [ref.pt_mul(ref.G, int.from_bytes(ref.S("ac-gen", j, 64), "big") % N) for j in range(18)]
+    g, g_vec, h_vec = pts[0], pts[1:2], pts[2:18]
+    W_m = [[0, 0, 1, 0]]
+    W_l = [[0, 1, 0, 0], [0, N - 1, 1, 0]]
+    a_m, a_l = [0], [(-r) % N, (-z) % N]
+    partition = lambda typ, idx: idx if typ == ref.LL else None  # noqa: E731
+    circ = ref.ArithmeticCircuit(1, 2, 1, 2, 2, 4, g, g_vec[:1], h_vec[:11], W_m, W_l, a_m, a_l, True, False, g_vec[1:], h_vec[11:], partition)
+    s_v = int.from_bytes(ref.S("ac-s", 0, 64), "big") % N
+    wit = ref.CircuitWitness([[x, y]], [s_v], [x], [y], [z, r])
+    v = [circ.commit(wit.v[0], wit.s_v[0])]
+    rng = ref.S("ac-rng", 0, (18 + 2 + 1) * 64)
+    proof = circ.prove(v, wit, ref.Transcript(b"circuit test"), ref.ByteRng(rng))
+    assert circ.verify(v, ref.Transcript(b"circuit test"), proof)
+    rec_py = ref.serialize_circuit_proof(proof)
+    be = lambda val: (val % N).to_bytes(32, "big")  # noqa: E731
+    flat = lambda m: b"".join(be(e) for row in m for e in row)  # noqa: E731
+    desc = oracle.make_circuit_desc(1, 2, 1, 2, True, False, xy(g), xy(g_vec[0]), b"".join(xy(p) for p in h_vec[:11]), b"",
+                                    b"".join(xy(p) for p in h_vec[11:]), flat(W_m), flat(W_l), b"".join(be(e) for e in a_m),
+                                    b"".join(be(e) for e in a_l), [-1, -1], [0, 1], [-1, -1], [-1, -1])
+    com33 = oracle.circuit_commit(desc, be(x) + be(y), be(s_v))
+    assert com33 == ref.pt_to_bytes(v[0])
+    rec_c, rounds, ll, nl = oracle.circuit_prove(desc, com33, be(x) + be(y), be(s_v), be(x), be(y), be(z) + be(r), rng, b"circuit test")
+    assert rec_c == rec_py
+    assert oracle.circuit_verify(desc, com33, rec_c, rounds, rounds, ll, nl, b"circuit test") == 1
+    bad = bytearray(rec_c)
+    bad[-1] ^= 1
+    assert oracle.circuit_verify(desc, com33, bytes(bad), rounds, rounds, ll, nl, b"circuit test") == 0
+
+
+def test_reciprocal_generic_dims_py_vs_c(ref, oracle):
+    """reciprocal.rs for (dim_nd, dim_np) = (4, 4): generic path, WNLA over 16 + 4 generators."""
+    N = ref.N
+    nd, np_ = 4, 4
+    pts = [ref.pt_mul(ref.G, int.from_bytes(ref.S("rc-gen", j, 64), "big") % N) for j in range(1 + 4 + 16)]
+    g, g_vec, hs = pts[0], pts[1:5], pts[5:21]
+    h_vec, h_vec_ = hs[:nd + 1 + 9], hs[nd + 1 + 9:]
+    proto = ref.ReciprocalRangeProofProtocol(nd, np_, g, g_vec, h_vec, [], h_vec_)
+    digits = [3, 0, 2, 1]
+    xval = sum(d * np_**i for i, d in enumerate(digits))
+    m = [digits.count(d) for d in range(np_)]
+    s = int.from_bytes(ref.S("rc-s", 0, 64), "big") % N
+    rng = ref.S("rc-rng", 0, (1 + 18 + (nd + 1) + nd) * 64)
+    com = proto.commit_value(xval, s)
+    proof = proto.prove(com, ref.ReciprocalWitness(xval, s, m, digits), ref.Transcript(b"rc"), ref.ByteRng(rng))
+    assert proto.verify(com, proof, ref.Transcript(b"rc"))
+    rec_py = ref.serialize_reciprocal_proof(proof)
+    be = lambda val: (val % N).to_bytes(32, "big")  # noqa: E731
+    rec_c, rounds, ll, nl, com33 = oracle.reciprocal_prove(nd, np_, xy(g), b"".join(xy(p) for p in g_vec), b"".join(xy(p) for p in h_vec), b"",
+                                                             b"".join(xy(p) for p in h_vec_), be(xval), be(s), digits, rng, b"rc")
+    assert rec_c == rec_py and com33 == ref.pt_to_bytes(com)
+    assert oracle.reciprocal_verify(nd, np_, xy(g), b"".join(xy(p) for p in g_vec), b"".join(xy(p) for p in h_vec), b"",
+                                    b"".join(xy(p) for p in h_vec_), com33, rec_c, rounds, rounds, ll, nl, b"rc") == 1

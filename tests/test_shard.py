@@ -1,0 +1,62 @@
+"""CPU suite: batch sharding across ranks (world_size 2, gloo).  The verify inside each rank is the oracle here
+(no GPU in CI); on the GPU box the same slices go through Context.verify_batch."""
+import os
+import socket
+import sys
+
+import pytest
+
+from conftest import ROOT, synth_batch
+
+LABEL = b"u64 range proof"
+
+
+def test_shard_bounds_partition():
+    from bp_pp_b200.shard import shard_bounds
+    for n in [0, 1, 2, 7, 8, 65536, 65537]:
+        for world in [1, 2, 3, 4, 8]:
+            cuts = [shard_bounds(n, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[r][1] == cuts[r + 1][0] for r in range(world - 1))
+            sizes = [b - a for a, b in cuts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(4, 2, 2)
+
+
+def _worker(rank, world, port, n, gens64, commits, proofs, expect, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch.distributed as dist
+    import oracle_c
+    from bp_pp_b200.shard import gather_status, shard_bytes
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    c = shard_bytes(commits, 33, n, world, rank)
+    p = shard_bytes(proofs, 525, n, world, rank)
+    local = oracle_c.u64_verify_batch(gens64, c, p, LABEL, 2)
+    full = gather_status(local, n)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, full == expect))
+
+
+def test_sharded_verify_two_ranks_gloo(ref, oracle, gens64):
+    import torch.multiprocessing as mp
+    n = 7   # ragged split: 4 + 3
+    xs, blinds, rngs = synth_batch(ref, n, start=40)
+    proofs, _ = oracle.u64_prove_batch(gens64, xs, blinds, rngs, LABEL, 4)
+    commits = b"".join(oracle.u64_commit(gens64, xs[i], blinds[32 * i:32 * i + 32]) for i in range(n))
+    bad = bytearray(proofs)
+    bad[525 * 2 + 400] ^= 1
+    bad[525 * 5 + 470] ^= 1
+    expect = oracle.u64_verify_batch(gens64, commits, bytes(bad), LABEL, 4)
+    assert expect == [1, 1, 0, 1, 1, 0, 1]
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, gens64, commits, bytes(bad), expect, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, True), (1, True)]
