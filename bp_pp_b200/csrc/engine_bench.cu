@@ -6,22 +6,30 @@ using namespace bppp;
 static int fail(int code, const std::string &msg) { return engine_fail(code, msg); }
 
 // ---- microbenchmarks ----
+// MODE 0: mad.wide.u32 (IMAD.WIDE.U32, 32x32+64 -> 64)   1: mad.lo.u32 (IMAD)   2: add.u32 (IADD3)
+// inline PTX so that exactly these instructions issue; 8 independent chains per thread, 64 warps per SM
+template <int MODE>
 __global__ void __launch_bounds__(256) k_mb_imad(uint64_t *out, uint32_t seed, int iters) {
     uint64_t acc[8];
-    uint32_t y = seed | 1u;
+    uint32_t lo[8];
+    uint32_t x[8], y = seed | 1u;
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = (uint64_t)(threadIdx.x + k) * 0x9E3779B97F4A7C15ULL;
+    for (int k = 0; k < 8; k++) { acc[k] = (uint64_t)(threadIdx.x + k) * 0x9E3779B97F4A7C15ULL; x[k] = seed * (2 * k + 3) + threadIdx.x; lo[k] = x[k] ^ y; }
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int r = 0; r < 8; r++) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) acc[k] = (uint64_t)(uint32_t)acc[k] * y + acc[k];
+            for (int k = 0; k < 8; k++) {
+                if (MODE == 0) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(x[k]), "r"(y));
+                if (MODE == 1) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[k]) : "r"(x[k]), "r"(y));
+                if (MODE == 2) asm volatile("add.u32 %0, %0, %1;" : "+r"(lo[k]) : "r"(x[k]));
+            }
         }
     }
     uint64_t s = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) s ^= acc[k];
+    for (int k = 0; k < 8; k++) s ^= acc[k] ^ lo[k];
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 template <int OP>
@@ -76,8 +84,14 @@ extern "C" int bppp_microbench(int device, double *out, int n_out) {
     };
     {
         const int iters = 2000;
-        float ms = time_ms([&] { k_mb_imad<<<blocks, 256>>>(d64, 12345u, iters); });
+        float ms = time_ms([&] { k_mb_imad<0><<<blocks, 256>>>(d64, 12345u, iters); });
         out[0] = (double)blocks * 256 * iters * 64 / (ms * 1e-3);
+        if (n_out >= 10) {
+            ms = time_ms([&] { k_mb_imad<1><<<blocks, 256>>>(d64, 12345u, iters); });
+            out[8] = (double)blocks * 256 * iters * 64 / (ms * 1e-3);
+            ms = time_ms([&] { k_mb_imad<2><<<blocks, 256>>>(d64, 12345u, iters); });
+            out[9] = (double)blocks * 256 * iters * 64 / (ms * 1e-3);
+        }
     }
     const int opblocks = sms * 16;
     auto run_op = [&](int op, int iters) -> double {

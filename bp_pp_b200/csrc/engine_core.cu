@@ -11,6 +11,9 @@
 // the transcript itself (Merlin/STROBE/Keccak) and all challenge-derived scalar algebra run on the
 // device, one proof per thread, so a batch never returns to the host between phases.
 // There is no CPU fallback: without a CUDA device every entry point fails with BPPP_ERR_NO_DEVICE.
+#ifndef BPPP_CORE_INLINE
+#define BPPP_FE_NOINLINE 1   // see fe.cuh: call-based fe_mul keeps the MSM loop inside the instruction cache
+#endif
 #include "engine_common.cuh"
 
 using namespace bppp;
@@ -41,7 +44,7 @@ template <int LANES>
 #define BPPP_MSM_BLOCK 64
 #endif
 #ifndef BPPP_MSM_MINBLOCKS
-#define BPPP_MSM_MINBLOCKS 5
+#define BPPP_MSM_MINBLOCKS 7
 #endif
 __global__ void __launch_bounds__(BPPP_MSM_BLOCK, BPPP_MSM_MINBLOCKS) k_msm_fixed(FixedTable T, WS w, int sc_off, TermMap tm, int nterms, int out_off) {
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,7 +202,7 @@ extern "C" int bppp_ctx_create(bppp_ctx **out, int device, const uint8_t *gens64
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BPPP_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(BPPP_ERR_ARG, "bad device index");
     if (window_bits == 0) window_bits = 16;
-    if (window_bits < 2 || window_bits > 16) return fail(BPPP_ERR_ARG, "window_bits must be in 2..16");
+    if (window_bits < 2 || window_bits > 20) return fail(BPPP_ERR_ARG, "window_bits must be in 2..20");
     if (max_batch == 0) max_batch = 65536;
     PtA gens[NUM_GENS]; bool gen_id[NUM_GENS];
     for (int g = 0; g < NUM_GENS; g++) {

@@ -1,4 +1,5 @@
 // libbppp.so, prove translation unit: U64RangeProofProtocol::prove over a batch (u64_proof.rs:57-82).
+#define BPPP_FE_NOINLINE 1   // phase kernels are not hot: call-based fe_mul keeps them small and quick to compile
 #include "engine_common.cuh"
 
 using namespace bppp;

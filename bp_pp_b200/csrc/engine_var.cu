@@ -1,5 +1,8 @@
 // libbppp.so, variable-base translation unit: the joint Straus ladders over per-proof points
 // (one thread per proof, tables of 1P..8P per point in thread-local memory).
+#ifndef BPPP_VAR_INLINE
+#define BPPP_FE_NOINLINE 1   // see fe.cuh: keeps the ladder loop inside the instruction cache
+#endif
 #include "engine_common.cuh"
 
 using namespace bppp;

@@ -21,18 +21,26 @@
 #define BPPP_D inline
 #endif
 
+// Host-side verification build (tests/hostemu): every Fe carries exact upper bounds on its limbs
+// (lim for n[0..8], lim9 for n[9]) and every operation asserts its preconditions on them, so the
+// lazy-reduction discipline of the point formulas is machine-checked on each test run.
 #if defined(BPPP_VERIFY_MAG)
 #include <assert.h>
-#define BPPP_MAG_FIELD int mag;
-#define BPPP_SET_MAG(r, m) ((r).mag = (m))
-#define BPPP_GET_MAG(a) ((a).mag)
+#define BPPP_MAG_FIELD uint64_t lim, lim9;
+#define BPPP_SET_MAG(r, m) ((r).lim = 2ull * (uint64_t)(m) * 0x3FFFFFFull, (r).lim9 = 2ull * (uint64_t)(m) * 0x3FFFFFull)
+#define BPPP_SET_LIM(r, l, l9) ((r).lim = (l), (r).lim9 = (l9))
 #define BPPP_ASSERT(c) assert(c)
 #else
 #define BPPP_MAG_FIELD
 #define BPPP_SET_MAG(r, m) ((void)0)
-#define BPPP_GET_MAG(a) (0)
+#define BPPP_SET_LIM(r, l, l9) ((void)0)
 #define BPPP_ASSERT(c) ((void)0)
 #endif
+
+// A translation unit may define BPPP_FE_NOINLINE: fe_mul / fe_sqr then compile to real device functions taking
+// their operands BY VALUE (nvcc passes the 10-word structs in registers, ~15 MOVs per call, no stack traffic).
+// Fully inlined point formulas are ~100 KB of SASS per ladder step and thrash the instruction cache
+// (ncu on k_v_var2: stall_no_instruction 5.4 warps per issue); with calls the hot loop is < 10 KB.
 
 namespace bppp {
 
@@ -49,9 +57,9 @@ static constexpr uint32_t FE_R1 = 0x400u;
 
 #if defined(BPPP_VERIFY_MAG)
 inline void fe_check(const Fe &a) {
-    for (int i = 0; i < 9; i++) assert((uint64_t)a.n[i] <= 2ull * (uint64_t)a.mag * FE_M26);
-    assert((uint64_t)a.n[9] <= 2ull * (uint64_t)a.mag * FE_M22);
-    assert(a.mag >= 0 && a.mag <= 32);
+    for (int i = 0; i < 9; i++) assert((uint64_t)a.n[i] <= a.lim);
+    assert((uint64_t)a.n[9] <= a.lim9);
+    assert(a.lim <= 0xFFFFFFFFull && a.lim9 <= 0xFFFFFFFFull);   // bounds themselves must fit a 32-bit limb
 }
 #else
 BPPP_HD void fe_check(const Fe &) {}
@@ -92,6 +100,9 @@ BPPP_HD Fe fe_from_words(const uint32_t w[8]) {
 // weak normalisation: any magnitude <= 32 -> magnitude 1 (limbs < 2^26 except a small excess in n[0..1])
 BPPP_HD Fe fe_normalize_weak(const Fe &a) {
     fe_check(a);
+#if defined(BPPP_VERIFY_MAG)
+    assert(a.lim + (a.lim9 >> 22) * 977ull + 64 <= 0xFFFFFFFFull);   // no 32-bit overflow in the carry pass
+#endif
     Fe r;
     uint32_t x = a.n[9] >> 22;
     uint32_t t9 = a.n[9] & FE_M22;
@@ -101,7 +112,7 @@ BPPP_HD Fe fe_normalize_weak(const Fe &a) {
 #pragma unroll
     for (int i = 2; i < 9; i++) { t = a.n[i] + c; c = t >> 26; r.n[i] = t & FE_M26; }
     r.n[9] = t9 + c;
-    BPPP_SET_MAG(r, 1);
+    BPPP_SET_LIM(r, 0x3FFFFFFull, 0x3FFFFFull + 64);
     fe_check(r);
     return r;
 }
@@ -172,21 +183,25 @@ BPPP_HD Fe fe_add(const Fe &a, const Fe &b) {
     Fe r;
 #pragma unroll
     for (int i = 0; i < 10; i++) r.n[i] = a.n[i] + b.n[i];
-    BPPP_SET_MAG(r, BPPP_GET_MAG(a) + BPPP_GET_MAG(b));
+#if defined(BPPP_VERIFY_MAG)
+    r.lim = a.lim + b.lim; r.lim9 = a.lim9 + b.lim9;
+#endif
     fe_check(r);
     return r;
 }
 // -a for a of magnitude <= m; result magnitude m+1
 BPPP_HD Fe fe_negate(const Fe &a, int m) {
-    BPPP_ASSERT(BPPP_GET_MAG(a) <= m);
     Fe r;
     const uint32_t k = 2u * (uint32_t)(m + 1);
+#if defined(BPPP_VERIFY_MAG)
+    assert(a.lim <= (uint64_t)k * 0x3FFFC2Full && a.lim9 <= (uint64_t)k * 0x3FFFFFull && k <= 64);
+#endif
     r.n[0] = 0x3FFFC2Fu * k - a.n[0];
     r.n[1] = 0x3FFFFBFu * k - a.n[1];
 #pragma unroll
     for (int i = 2; i < 9; i++) r.n[i] = FE_M26 * k - a.n[i];
     r.n[9] = FE_M22 * k - a.n[9];
-    BPPP_SET_MAG(r, m + 1);
+    BPPP_SET_LIM(r, (uint64_t)k * 0x3FFFFFFull, (uint64_t)k * 0x3FFFFFull);
     fe_check(r);
     return r;
 }
@@ -196,7 +211,9 @@ BPPP_HD Fe fe_mul_int(const Fe &a, uint32_t k) {
     Fe r;
 #pragma unroll
     for (int i = 0; i < 10; i++) r.n[i] = a.n[i] * k;
-    BPPP_SET_MAG(r, BPPP_GET_MAG(a) * (int)k);
+#if defined(BPPP_VERIFY_MAG)
+    r.lim = a.lim * k; r.lim9 = a.lim9 * k;
+#endif
     fe_check(r);
     return r;
 }
@@ -205,64 +222,80 @@ BPPP_HD Fe fe_cmov(const Fe &a, const Fe &b, bool take_b) {
 #pragma unroll
     for (int i = 0; i < 10; i++) r.n[i] = take_b ? b.n[i] : a.n[i];
 #if defined(BPPP_VERIFY_MAG)
-    r.mag = a.mag > b.mag ? a.mag : b.mag;
+    r.lim = a.lim > b.lim ? a.lim : b.lim; r.lim9 = a.lim9 > b.lim9 ? a.lim9 : b.lim9;
 #endif
     return r;
 }
 
-// Reduce 19 product columns c[0..18] (each < 2^64 - 2^42) to a magnitude-1 element.
+// Reduce 19 product columns c[0..18] (each < 2^63.9) to limbs below 2^27 + 2^12 (top limb < 2^22).
+// Carry-save instead of carry-propagate: every 64-bit column is cut into 26 + 26 + 12 bit pieces that are
+// re-assembled into lazy limbs with independent 3-input adds, so the only serial carry chain left is three
+// steps long (the previous two 10-step chains made the kernels wait on fixed-latency dependencies, ncu
+// "stall_wait" 2.2 per issue).  2^260 = R0 + R1 2^26 and 2^256 = 977 + 64 2^26 (mod p).
 BPPP_HD Fe fe_reduce_columns(uint64_t c[19]) {
-    // pass 1: make columns 10..18 into 26-bit limbs h[0..8] plus a carry h9
-    uint64_t carry = 0;
-    uint32_t h[9];
+    // high columns 10..18 -> lazy limbs H[0..10] at weights 2^(26 (10 + j))
+    uint32_t lo[9], mid[9], hi[9];
 #pragma unroll
-    for (int k = 10; k <= 18; k++) {
-        uint64_t t = c[k] + carry;
-        h[k - 10] = (uint32_t)t & FE_M26;
-        carry = t >> 26;
+    for (int k = 0; k < 9; k++) {
+        uint64_t v = c[10 + k];
+        lo[k] = (uint32_t)v & FE_M26;
+        mid[k] = (uint32_t)(v >> 26) & FE_M26;
+        hi[k] = (uint32_t)(v >> 52);
     }
-    uint64_t h9 = carry;  // < 2^39
-    // fold: 2^(260+26j) = (R0 + R1 2^26) 2^(26j)
+    uint32_t H[11];
+    H[0] = lo[0];
+    H[1] = lo[1] + mid[0];
 #pragma unroll
-    for (int j = 0; j < 9; j++) {
-        c[j] += (uint64_t)h[j] * FE_R0;
-        c[j + 1] += (uint64_t)h[j] * FE_R1;
+    for (int j = 2; j < 9; j++) H[j] = lo[j] + mid[j - 1] + hi[j - 2];
+    H[9] = mid[8] + hi[7];
+    H[10] = hi[8];
+    // fold into the low columns (two more columns appear at positions 10 and 11)
+    uint64_t low[12];
+#pragma unroll
+    for (int k = 0; k < 10; k++) low[k] = c[k];
+    low[10] = 0; low[11] = 0;
+#pragma unroll
+    for (int j = 0; j < 11; j++) {
+        low[j] += (uint64_t)H[j] * FE_R0;
+        low[j + 1] += (uint64_t)H[j] * FE_R1;
     }
-    c[9] += h9 * FE_R0;
-    uint64_t top = h9 * FE_R1;  // weight 2^260
-    // pass 2: carry-propagate columns 0..9
+    // low columns -> lazy limbs L[0..11]  (low[10] < 2^38, low[11] < 2^23, so L[12], L[13] vanish)
+    uint32_t lo2[12], mid2[12], hi2[10];
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        uint64_t v = low[k];
+        lo2[k] = (uint32_t)v & FE_M26;
+        mid2[k] = (uint32_t)(v >> 26) & FE_M26;
+        if (k < 10) hi2[k] = (uint32_t)(v >> 52);
+    }
+    uint32_t L[12];
+    L[0] = lo2[0];
+    L[1] = lo2[1] + mid2[0];
+#pragma unroll
+    for (int j = 2; j < 12; j++) L[j] = lo2[j] + mid2[j - 1] + hi2[j - 2];
+    // top: limbs 10, 11 and the bits of limb 9 above 2^22 wrap around once more
+    uint32_t x = L[9] >> 22;
+    uint64_t e0 = (uint64_t)L[0] + (uint64_t)L[10] * FE_R0 + (uint64_t)x * 977u;
+    uint64_t e1 = (uint64_t)L[1] + (uint64_t)L[10] * FE_R1 + (uint64_t)L[11] * FE_R0 + (uint64_t)(x << 6);
+    uint64_t e2 = (uint64_t)L[2] + (uint64_t)L[11] * FE_R1;
     Fe r;
-    carry = 0;
+    r.n[0] = (uint32_t)e0 & FE_M26; e1 += e0 >> 26;
+    r.n[1] = (uint32_t)e1 & FE_M26; e2 += e1 >> 26;
+    r.n[2] = (uint32_t)e2 & FE_M26;
+    r.n[3] = L[3] + (uint32_t)(e2 >> 26);
 #pragma unroll
-    for (int k = 0; k < 10; k++) {
-        uint64_t t = c[k] + carry;
-        r.n[k] = (uint32_t)t & FE_M26;
-        carry = t >> 26;
-    }
-    top += carry;  // weight 2^260, < 2^50
-    // fold the 2^260 overflow and bits >= 2^256 of limb 9 together
-    uint64_t t0 = (uint64_t)r.n[0] + top * FE_R0;   // < 2^64
-    uint64_t t1 = (uint64_t)r.n[1] + top * FE_R1;
-    r.n[0] = (uint32_t)t0 & FE_M26; t1 += t0 >> 26;
-    r.n[1] = (uint32_t)t1 & FE_M26;
-    uint64_t t2 = (uint64_t)r.n[2] + (t1 >> 26);
-    r.n[2] = (uint32_t)t2 & FE_M26;
-    uint32_t cc = (uint32_t)(t2 >> 26);  // < 2^8
-#pragma unroll
-    for (int k = 3; k < 9; k++) { uint32_t t = r.n[k] + cc; r.n[k] = t & FE_M26; cc = t >> 26; }
-    uint32_t t9 = r.n[9] + cc;
-    uint32_t x = t9 >> 22;          // < 2^5
-    r.n[9] = t9 & FE_M22;
-    r.n[0] += x * 977u;             // < 2^26 + 2^15
-    r.n[1] += x << 6;               // < 2^26 + 2^11
-    BPPP_SET_MAG(r, 1);
+    for (int k = 4; k < 9; k++) r.n[k] = L[k];
+    r.n[9] = L[9] & FE_M22;
+    BPPP_SET_LIM(r, (1ull << 27) + (1ull << 12) + 128, 0x3FFFFFull);
     fe_check(r);
     return r;
 }
 
-BPPP_HD Fe fe_mul(const Fe &a, const Fe &b) {
+BPPP_HD Fe fe_mul_inl(const Fe &a, const Fe &b) {
     fe_check(a); fe_check(b);
-    BPPP_ASSERT(BPPP_GET_MAG(a) * BPPP_GET_MAG(b) <= 64);
+#if defined(BPPP_VERIFY_MAG)
+    assert((unsigned __int128)10 * a.lim * b.lim < ((unsigned __int128)15 << 60));   // columns < 2^63.9: room for the folds
+#endif
     uint64_t c[19];
 #pragma unroll
     for (int k = 0; k < 19; k++) c[k] = 0;
@@ -274,9 +307,11 @@ BPPP_HD Fe fe_mul(const Fe &a, const Fe &b) {
     return fe_reduce_columns(c);
 }
 
-BPPP_HD Fe fe_sqr(const Fe &a) {
+BPPP_HD Fe fe_sqr_inl(const Fe &a) {
     fe_check(a);
-    BPPP_ASSERT(BPPP_GET_MAG(a) <= 8);
+#if defined(BPPP_VERIFY_MAG)
+    assert(a.lim < (1ull << 31) && (unsigned __int128)10 * a.lim * a.lim < ((unsigned __int128)15 << 60));
+#endif
     uint64_t c[19];
 #pragma unroll
     for (int k = 0; k < 19; k++) c[k] = 0;
@@ -291,6 +326,28 @@ BPPP_HD Fe fe_sqr(const Fe &a) {
     }
     return fe_reduce_columns(c);
 }
+
+#if defined(__CUDACC__) && defined(BPPP_FE_NOINLINE)
+static __device__ __noinline__ Fe fe_mul_call(Fe a, Fe b) { return fe_mul_inl(a, b); }
+static __device__ __noinline__ Fe fe_sqr_call(Fe a) { return fe_sqr_inl(a); }
+__host__ __device__ __forceinline__ Fe fe_mul(const Fe &a, const Fe &b) {
+#if defined(__CUDA_ARCH__)
+    return fe_mul_call(a, b);
+#else
+    return fe_mul_inl(a, b);
+#endif
+}
+__host__ __device__ __forceinline__ Fe fe_sqr(const Fe &a) {
+#if defined(__CUDA_ARCH__)
+    return fe_sqr_call(a);
+#else
+    return fe_sqr_inl(a);
+#endif
+}
+#else
+BPPP_HD Fe fe_mul(const Fe &a, const Fe &b) { return fe_mul_inl(a, b); }
+BPPP_HD Fe fe_sqr(const Fe &a) { return fe_sqr_inl(a); }
+#endif
 
 BPPP_HD Fe fe_sqr_n(Fe a, int n) {
 #pragma unroll 1

@@ -28,7 +28,8 @@ BPPP_HD void ws_st_sc(const WS &w, size_t i, int off, const Sc &a) {
 BPPP_HD Fe ws_ld_fe(const WS &w, size_t i, int off) { Fe r;
 #pragma unroll
     for (int k = 0; k < 10; k++) r.n[k] = ws_ld(w, i, off + k);
-    BPPP_SET_MAG(r, 1); return r; }
+    BPPP_SET_LIM(r, (1ull << 27) + (1ull << 12) + 128, 0x3FFFFFull + 64);   // stored values are fe_mul / weak-normalised outputs
+    return r; }
 BPPP_HD void ws_st_fe(const WS &w, size_t i, int off, const Fe &a) {
 #pragma unroll
     for (int k = 0; k < 10; k++) ws_st(w, i, off + k, a.n[k]); }
@@ -100,29 +101,53 @@ BPPP_HD uint32_t scalar_window(const WS &w, size_t i, int sc_off, int win, int W
     return (uint32_t)(v >> sh) & ((1u << W) - 1u);
 }
 
-BPPP_HD bool table_load(PtA &q, const FixedTable &T, int g, int win, uint32_t d) {
+struct TableEntryRaw { uint4 a, b, c, e; };   // x words 0..7, y words 0..7
+BPPP_HD TableEntryRaw table_fetch(const FixedTable &T, int g, int win, uint32_t d) {
     size_t idx = ((size_t)(g * T.nwin + win) * ((1u << T.W) - 1u) + (d - 1)) * 4;
-    uint4 a = T.tab[idx], b = T.tab[idx + 1], c = T.tab[idx + 2], e = T.tab[idx + 3];
-    uint32_t x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    uint32_t y[8] = {c.x, c.y, c.z, c.w, e.x, e.y, e.z, e.w};
+    TableEntryRaw r;
+#if defined(__CUDA_ARCH__)
+    r.a = __ldg(T.tab + idx); r.b = __ldg(T.tab + idx + 1); r.c = __ldg(T.tab + idx + 2); r.e = __ldg(T.tab + idx + 3);
+#else
+    r.a = T.tab[idx]; r.b = T.tab[idx + 1]; r.c = T.tab[idx + 2]; r.e = T.tab[idx + 3];
+#endif
+    return r;
+}
+BPPP_HD bool table_decode(PtA &q, const TableEntryRaw &r) {
+    uint32_t x[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
+    uint32_t y[8] = {r.c.x, r.c.y, r.c.z, r.c.w, r.e.x, r.e.y, r.e.z, r.e.w};
     q.x = fe_from_words(x); q.y = fe_from_words(y);
-    uint32_t any = a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w | c.x | c.y | c.z | c.w | e.x | e.y | e.z | e.w;
+    uint32_t any = r.a.x | r.a.y | r.a.z | r.a.w | r.b.x | r.b.y | r.b.z | r.b.w | r.c.x | r.c.y | r.c.z | r.c.w | r.e.x | r.e.y | r.e.z | r.e.w;
     return any != 0;
 }
 
 // One lane's share of sum_t scalar_t * G_{gen(t)}: items (t, win) are dealt round-robin to `nlanes` lanes.
 // scalars: T consecutive Sc in the workspace starting at word sc_off; term_gen[t] = generator index.
+// The table entry of the next item is fetched (64 B from HBM) before the current mixed addition is computed.
 BPPP_HD Pt msm_fixed_lane(const FixedTable &T, const WS &w, size_t i, int sc_off, const int *term_gen, int nterms, int lane, int nlanes) {
     Pt acc = pt_identity();
-    int items = nterms * T.nwin;
-#pragma unroll 1
-    for (int it = lane; it < items; it += nlanes) {
+    const int items = nterms * T.nwin;
+    TableEntryRaw cur, nxt;
+    uint32_t dcur = 0, dnxt = 0;
+    int it = lane;
+    if (it < items) {
         int t = it / T.nwin, win = it - t * T.nwin;
-        uint32_t d = scalar_window(w, i, sc_off + 8 * t, win, T.W);
-        if (d != 0) {
-            PtA q;
-            if (table_load(q, T, term_gen[t], win, d)) acc = pt_add_mixed(acc, q);
+        dcur = scalar_window(w, i, sc_off + 8 * t, win, T.W);
+        if (dcur) cur = table_fetch(T, term_gen[t], win, dcur);
+    }
+#pragma unroll 1
+    for (; it < items; it += nlanes) {
+        int itn = it + nlanes;
+        dnxt = 0;
+        if (itn < items) {
+            int t = itn / T.nwin, win = itn - t * T.nwin;
+            dnxt = scalar_window(w, i, sc_off + 8 * t, win, T.W);
+            if (dnxt) nxt = table_fetch(T, term_gen[t], win, dnxt);
         }
+        if (dcur != 0) {
+            PtA q;
+            if (table_decode(q, cur)) acc = pt_add_mixed(acc, q);
+        }
+        cur = nxt; dcur = dnxt;
     }
     return acc;
 }

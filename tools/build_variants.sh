@@ -6,13 +6,16 @@ NV="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcomp
 mkdir -p _obj/var ../variants
 build() { # name  var_flags  core_flags
   name=$1
-  ( $NV $2 -c -o _obj/var/${name}_var.o engine_var.cu ) &
-  ( $NV $3 -c -o _obj/var/${name}_core.o engine_core.cu ) &
+  ( $NV $2 -Xptxas -v -c -o _obj/var/${name}_var.o engine_var.cu 2> _obj/var/${name}_var.log ) &
+  ( $NV $3 -Xptxas -v -c -o _obj/var/${name}_core.o engine_core.cu 2> _obj/var/${name}_core.log ) &
   wait
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libbppp_${name}.so _obj/var/${name}_var.o _obj/var/${name}_core.o _obj/engine_verify.o _obj/engine_prove.o _obj/engine_bench.o
   echo built $name
+  grep -h -A2 "k_v_var2\|k_msm_fixed" _obj/var/${name}_var.log _obj/var/${name}_core.log | grep -E "Used|spill" | paste - - | sed 's/ptxas info    ://g' | cut -c1-200
 }
 rm -f ../variants/*.so
-build v64x5_l2   "-DBPPP_VAR_BLOCK=64 -DBPPP_VAR_MINBLOCKS=5"  "-DBPPP_MSM_LANES=2" &
-build v64x6_l4b64  "-DBPPP_VAR_BLOCK=64 -DBPPP_VAR_MINBLOCKS=6" "-DBPPP_MSM_LANES=4 -DBPPP_MSM_BLOCK=64 -DBPPP_MSM_MINBLOCKS=5" &
+build mb8   "-DBPPP_VAR_MINBLOCKS=8"  "-DBPPP_MSM_MINBLOCKS=8" &
+build mb9   "-DBPPP_VAR_MINBLOCKS=9"  "-DBPPP_MSM_MINBLOCKS=9" &
+build mb10  "-DBPPP_VAR_MINBLOCKS=10" "-DBPPP_MSM_MINBLOCKS=10" &
+build mb12  "-DBPPP_VAR_MINBLOCKS=12" "-DBPPP_MSM_MINBLOCKS=12" &
 wait

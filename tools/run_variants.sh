@@ -1,2 +1,5 @@
-for ns in 1 2 4 8; do BPPP_NSUB=$ns timeout 200 python tools/variant_bench.py; done
-for v in v64x5_l2 v64x6_l4b64; do for ns in 1 4; do BPPP_LIB=$PWD/bp_pp_b200/variants/libbppp_$v.so BPPP_NSUB=$ns BPPP_PROFILE=1 timeout 200 python tools/variant_bench.py; done; done
+python -c "
+import sys; sys.path.insert(0,'.')
+import bp_pp_b200 as B, json; print(json.dumps(B.microbench(0)))"
+BPPP_NSUB=2 BPPP_PROFILE=1 timeout 200 python tools/variant_bench.py
+BPPP_W=20 BPPP_NSUB=2 BPPP_PROFILE=1 timeout 300 python tools/variant_bench.py
