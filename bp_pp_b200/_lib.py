@@ -15,6 +15,7 @@ EXPORTS = [
     "bppp_ctx_create", "bppp_ctx_destroy", "bppp_last_error", "bppp_ctx_info", "bppp_u64_commit_batch",
     "bppp_u64_verify_batch", "bppp_u64_verify_batch_dev", "bppp_u64_prove_batch", "bppp_u64_prove_batch_dev",
     "bppp_launch_count", "bppp_microbench", "bppp_ctx_profile_begin", "bppp_ctx_profile_end",
+    "bppp_msm", "bppp_points_upload", "bppp_scalars_upload", "bppp_device_free", "bppp_msm_uploaded", "bppp_points_sum",
 ]
 
 _lib = None
@@ -36,6 +37,8 @@ def lib():
         L.bppp_launch_count.argtypes = [C.c_void_p]
         L.bppp_ctx_destroy.argtypes = [C.c_void_p]
         L.bppp_ctx_destroy.restype = None
+        L.bppp_device_free.restype = None
+        L.bppp_device_free.argtypes = [C.c_int, C.c_void_p]
         _lib = L
     return _lib
 

@@ -202,3 +202,52 @@ def microbench(device: int = 0) -> dict:
     keys = ["imad_wide_per_s", "fe_mul_per_s", "fe_sqr_per_s", "sc_mul_per_s", "pt_add_mixed_per_s",
             "pt_double_per_s", "pt_add_per_s", "sm_clock_mhz", "imad_per_s", "iadd_per_s"]
     return dict(zip(keys, list(out)))
+
+
+# ---- generic entry points (arbitrary sizes) ----
+def _psz(fmt: int) -> int:
+    return 33 if fmt == FMT_COMPRESSED else 64
+
+
+def msm(points: bytes, scalars32: bytes, points_fmt: int = FMT_AFFINE64, out_fmt: int = FMT_COMPRESSED, device: int = 0) -> bytes:
+    """`util::vector_mul` over points (src/util.rs:46-60): sum scalars[i] * points[i], zero-extending the shorter side."""
+    npts, nsc = len(points) // _psz(points_fmt), len(scalars32) // 32
+    out = (C.c_uint8 * _psz(out_fmt))()
+    check(lib().bppp_msm(C.c_int(device), _in(points), C.c_int(points_fmt), C.c_size_t(npts), _in(scalars32), C.c_size_t(nsc),
+                         C.c_int(out_fmt), out), "bppp_msm")
+    return bytes(out)
+
+
+def points_sum(points: bytes, points_fmt: int = FMT_COMPRESSED, out_fmt: int = FMT_COMPRESSED, device: int = 0) -> bytes:
+    n = len(points) // _psz(points_fmt)
+    out = (C.c_uint8 * _psz(out_fmt))()
+    check(lib().bppp_points_sum(C.c_int(device), _in(points), C.c_int(points_fmt), C.c_size_t(n), C.c_int(out_fmt), out), "bppp_points_sum")
+    return bytes(out)
+
+
+class UploadedMsm:
+    """Points and scalars decoded once and kept in HBM; `run()` times the MSM alone on the device."""
+
+    def __init__(self, points: bytes, scalars32: bytes, points_fmt: int = FMT_AFFINE64, device: int = 0):
+        self.device, self.n = device, min(len(points) // _psz(points_fmt), len(scalars32) // 32)
+        self._p, self._s = C.c_void_p(), C.c_void_p()
+        check(lib().bppp_points_upload(C.c_int(device), _in(points), C.c_int(points_fmt), C.c_size_t(self.n), C.byref(self._p)), "bppp_points_upload")
+        check(lib().bppp_scalars_upload(C.c_int(device), _in(scalars32), C.c_size_t(self.n), C.byref(self._s)), "bppp_scalars_upload")
+
+    def run(self, out_fmt: int = FMT_COMPRESSED):
+        out = (C.c_uint8 * _psz(out_fmt))()
+        ms = C.c_float()
+        check(lib().bppp_msm_uploaded(C.c_int(self.device), self._p, self._s, C.c_size_t(self.n), C.c_int(out_fmt), out, C.byref(ms)), "bppp_msm_uploaded")
+        return bytes(out), ms.value
+
+    def close(self):
+        for h in (self._p, self._s):
+            if h.value:
+                lib().bppp_device_free(C.c_int(self.device), h)
+        self._p, self._s = C.c_void_p(), C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,437 @@
+// libbppp.so, variable-base MSM translation unit: sum_i k_i * P_i over arbitrary points, the device-side
+// replacement of util::vector_mul<ProjectivePoint> (reference src/util.rs:46-60, which performs one full
+// scalar multiplication per term) for large n -- WNLA X/R commitments (src/wnla.rs:152-160), wnla.commit
+// (src/wnla.rs:66-72) and the circuit commitments (src/circuit.rs:335-345,469-470,522-524).
+//
+// Pippenger with signed c-bit windows:
+//   k_msm_digits      signed digits of every scalar -> (bucket key, point index | sign) pairs, window-major
+//   cub radix sort    pairs by bucket key (the only library call; it moves 8-byte pairs, no curve arithmetic)
+//   k_msm_segments    one thread per 32 consecutive sorted pairs: mixed-adds runs of equal key; runs that lie inside
+//                     the segment go straight to their bucket, runs crossing a segment edge leave a partial sum
+//   k_msm_merge       partial sums of the same bucket are added (only buckets spanning several segments)
+//   k_msm_chunks      per window: chunked running-sum reduction  sum_b (b+1) B_b  (two adds per bucket)
+//   k_pt_sum_groups   tree sums;  k_msm_horner: sum_w 2^(c w) W_w
+// Small inputs (n <= 1024) use one GLV scalar multiplication per point and the same tree sum.
+#define BPPP_FE_NOINLINE 1
+#include "engine_generic.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+using namespace bppp;
+
+static int fail(int code, const std::string &msg) { return engine_fail(code, msg); }
+
+namespace bppp {
+
+// ---- point / scalar array helpers (AoS words in device memory) ----
+__device__ __forceinline__ bool load_dev_point(PtA &q, const uint32_t *pts, size_t idx) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(pts + 16 * idx);
+    TableEntryRaw r; r.a = __ldg(p); r.b = __ldg(p + 1); r.c = __ldg(p + 2); r.e = __ldg(p + 3);
+    return table_decode(q, r);
+}
+__device__ __forceinline__ Pt ld_pt30(const uint32_t *p) { Pt r;
+#pragma unroll
+    for (int k = 0; k < 10; k++) { r.x.n[k] = p[k]; r.y.n[k] = p[10 + k]; r.z.n[k] = p[20 + k]; }
+    return r; }
+__device__ __forceinline__ void st_pt30(uint32_t *p, const Pt &a) {
+#pragma unroll
+    for (int k = 0; k < 10; k++) { p[k] = a.x.n[k]; p[10 + k] = a.y.n[k]; p[20 + k] = a.z.n[k]; } }
+
+__global__ void k_decode_points(const uint8_t *in, int fmt, uint32_t *out, int32_t *bad, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PtA a;
+    int s = fmt == FMT_COMPRESSED ? pta_decompress(a, in + 33 * i) : pta_from_xy64(a, in + 64 * i);
+    uint32_t x[8], y[8];
+    if (s == 0) { fe_to_words(x, fe_normalize(a.x)); fe_to_words(y, fe_normalize(a.y)); }
+    else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) { x[k] = 0; y[k] = 0; }
+        if (s < 0) atomicExch(bad, (int32_t)ST_BAD_POINT);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { out[16 * i + k] = x[k]; out[16 * i + 8 + k] = y[k]; }
+}
+__global__ void k_decode_scalars(const uint8_t *in, uint32_t *out, int32_t *bad, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Sc s;
+    if (!sc_from_be32(s, in + 32 * i)) { atomicExch(bad, (int32_t)ST_BAD_SCALAR); s = sc_zero(); }
+#pragma unroll
+    for (int k = 0; k < 8; k++) out[8 * i + k] = s.v[k];
+}
+__global__ void k_encode_scalars(const uint32_t *in, uint8_t *out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Sc s;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s.v[k] = in[8 * i + k];
+    sc_to_be32(out + 32 * i, s);
+}
+// projective (30 words each) -> affine bytes; one inversion per point (used for a handful of outputs)
+__global__ void k_encode_points(const uint32_t *pts30, int fmt, uint8_t *out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Pt p = ld_pt30(pts30 + 30 * i);
+    bool id = pt_is_identity(p);
+    PtA a = pt_to_affine_with_zinv(p, fe_inv(p.z));
+    if (fmt == FMT_COMPRESSED) pta_compress(out + 33 * i, a, id); else pta_to_xy64(out + 64 * i, a, id);
+}
+
+// ---- Pippenger ----
+__global__ void k_msm_digits(const uint32_t *sc, size_t n, int c, int nwin, uint32_t *keys, uint32_t *vals) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k[9];
+#pragma unroll
+    for (int j = 0; j < 8; j++) k[j] = sc[8 * i + j];
+    k[8] = 0;
+    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1u;
+    uint32_t carry = 0;
+    for (int w = 0; w < nwin; w++) {
+        int bit = w * c, word = bit >> 5, sh = bit & 31;
+        uint64_t v = word < 8 ? k[word] : 0;
+        if (word + 1 < 9) v |= (uint64_t)k[word + 1] << 32;
+        uint32_t raw = ((uint32_t)(v >> sh) & mask) + carry;
+        uint32_t neg = 0, mag = raw;
+        carry = 0;
+        if (raw > half) { mag = (1u << c) - raw; neg = 1; carry = 1; }
+        keys[(size_t)w * n + i] = mag == 0 ? 0xFFFFFFFFu : (uint32_t)w * half + (mag - 1);
+        vals[(size_t)w * n + i] = (uint32_t)i | (neg << 31);
+    }
+}
+
+static constexpr int MSM_SEG = 32;
+
+// bucket sums and partials are stored AoS, 30 words per point
+__global__ void __launch_bounds__(64) k_msm_segments(const uint32_t *pts, const uint32_t *keys, const uint32_t *vals, size_t total, uint32_t nb,
+                                                      uint32_t *buckets, uint32_t *partials, uint32_t *pkeys, size_t nseg) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nseg) return;
+    size_t p0 = t * MSM_SEG, p1 = p0 + MSM_SEG < total ? p0 + MSM_SEG : total;
+    uint32_t head_key = 0xFFFFFFFFu, tail_key = 0xFFFFFFFFu;
+    Pt acc = pt_identity();
+    uint32_t cur = keys[p0];
+    bool is_head = true;      // the first run may have started in the previous segment
+    bool head_open = p0 > 0 && keys[p0 - 1] == cur;
+#pragma unroll 1
+    for (size_t p = p0; p < p1; p++) {
+        uint32_t k = keys[p];
+        if (k != cur) {
+            // run `cur` ended inside this segment
+            if (cur < nb) {
+                if (is_head && head_open) { st_pt30(partials + 30 * (2 * t), acc); head_key = cur; }
+                else st_pt30(buckets + 30 * (size_t)cur, acc);
+            }
+            acc = pt_identity(); cur = k; is_head = false;
+        }
+        if (k < nb) {
+            uint32_t v = vals[p];
+            PtA q;
+            if (load_dev_point(q, pts, v & 0x7FFFFFFFu)) {
+                if (v >> 31) q.y = fe_normalize_weak(fe_negate(q.y, 1));
+                acc = pt_add_mixed(acc, q);
+            }
+        }
+    }
+    if (cur < nb) {
+        bool tail_open = p1 < total && keys[p1] == cur;
+        if (is_head && head_open) { st_pt30(partials + 30 * (2 * t), acc); head_key = cur; }       // whole segment is one open run
+        else if (tail_open) { st_pt30(partials + 30 * (2 * t + 1), acc); tail_key = cur; }
+        else st_pt30(buckets + 30 * (size_t)cur, acc);
+    }
+    pkeys[2 * t] = head_key; pkeys[2 * t + 1] = tail_key;
+}
+// buckets whose run crosses segment edges: the first partial of each key run owns the sum
+__global__ void __launch_bounds__(64) k_msm_merge(const uint32_t *partials, const uint32_t *pkeys, size_t np, uint32_t nb, uint32_t *buckets) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= np) return;
+    uint32_t k = pkeys[j];
+    if (k >= nb) return;
+    // previous non-empty partial with the same key? then that one owns the run
+    for (size_t q = j; q-- > 0;) {
+        uint32_t kq = pkeys[q];
+        if (kq == 0xFFFFFFFFu) continue;
+        if (kq == k) return;
+        break;
+    }
+    Pt acc = ld_pt30(partials + 30 * j);
+#pragma unroll 1
+    for (size_t q = j + 1; q < np; q++) {
+        uint32_t kq = pkeys[q];
+        if (kq == 0xFFFFFFFFu) continue;
+        if (kq != k) break;
+        acc = pt_add(acc, ld_pt30(partials + 30 * q));
+    }
+    st_pt30(buckets + 30 * (size_t)k, acc);
+}
+__global__ void k_pt_fill_identity(uint32_t *pts30, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_pt30(pts30 + 30 * i, pt_identity());
+}
+// per window w, chunk j of CH buckets: out[w * nchunks + j] = sum_{b in chunk} (b + 1) B_b
+__global__ void __launch_bounds__(64) k_msm_chunks(const uint32_t *buckets, int nwin, uint32_t half, uint32_t CH, uint32_t nchunks, uint32_t *out) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nwin * nchunks) return;
+    uint32_t w = (uint32_t)(t / nchunks), j = (uint32_t)(t % nchunks);
+    uint32_t base = j * CH, top = base + CH < half ? base + CH : half;
+    Pt S = pt_identity(), T = pt_identity();
+#pragma unroll 1
+    for (uint32_t b = top; b-- > base;) {
+        S = pt_add(S, ld_pt30(buckets + 30 * ((size_t)w * half + b)));
+        T = pt_add(T, S);
+    }
+    // + base * S: double-and-add
+    Pt BS = pt_identity();
+#pragma unroll 1
+    for (int bit = 15; bit >= 0; bit--) {     // base < half <= 2^15
+        BS = pt_double(BS);
+        if ((base >> bit) & 1u) BS = pt_add(BS, S);
+    }
+    st_pt30(out + 30 * t, pt_add(T, BS));
+}
+// out[g] = sum_{t < group} in[g * group + t]  (entries beyond count_in are skipped)
+__global__ void __launch_bounds__(64) k_pt_sum_groups(const uint32_t *in, size_t count_in, uint32_t group, uint32_t *out, size_t count_out) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= count_out) return;
+    Pt acc = pt_identity();
+#pragma unroll 1
+    for (uint32_t t = 0; t < group; t++) {
+        size_t idx = g * group + t;
+        if (idx < count_in) acc = pt_add(acc, ld_pt30(in + 30 * idx));
+    }
+    st_pt30(out + 30 * g, acc);
+}
+// result = sum_w 2^(c w) W_w, optionally + *addend
+__global__ void k_msm_horner(const uint32_t *win, int c, int nwin, const uint32_t *addend, uint32_t *out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Pt acc = ld_pt30(win + 30 * (nwin - 1));
+    for (int w = nwin - 2; w >= 0; w--) {
+        for (int k = 0; k < c; k++) acc = pt_double(acc);
+        acc = pt_add(acc, ld_pt30(win + 30 * w));
+    }
+    if (addend) acc = pt_add(acc, ld_pt30(addend));
+    st_pt30(out, acc);
+}
+// small n: one GLV scalar multiplication per point
+__global__ void __launch_bounds__(64) k_msm_small(const uint32_t *pts, const uint32_t *sc, size_t n, uint32_t *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PtA q; Sc k;
+#pragma unroll
+    for (int j = 0; j < 8; j++) k.v[j] = sc[8 * i + j];
+    bool ok = load_dev_point(q, pts, i);
+    Pt r = pt_mul_glv(pt_from_affine(q, !ok), k);
+    st_pt30(out + 30 * i, r);
+}
+
+static std::atomic<uint64_t> g_generic_launches{0};
+uint64_t generic_launch_count() { return g_generic_launches.load(); }
+#define GL(kern, grid, block, ...) do { kern<<<(grid), (block), 0, st>>>(__VA_ARGS__); g_generic_launches++; } while (0)
+
+static int tree_sum(cudaStream_t st, uint32_t *a, uint32_t *b, size_t count, uint32_t **result) {
+    // repeatedly sums groups of 16 until one point remains; a holds the input, b is scratch of >= count/16 + 1 points
+    uint32_t *in = a, *out = b;
+    while (count > 1) {
+        size_t nout = (count + 15) / 16;
+        GL(k_pt_sum_groups, nblocks(nout, 64), 64, in, count, 16u, out, nout);
+        std::swap(in, out); count = nout;
+    }
+    *result = in;
+    return BPPP_OK;
+}
+
+int msm_choose_window(size_t n) {
+    int lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n) lg++;
+    int c = lg - 3;
+    if (c < 4) c = 4;
+    if (c > 16) c = 16;
+    return c;
+}
+
+// d_out30: projective result (30 words, device).  d_addend30 may be null.  Synchronises before returning.
+int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, size_t n, const uint32_t *d_addend30, uint32_t *d_out30) {
+    if (n == 0) {
+        if (d_addend30) CUDA_OK(cudaMemcpyAsync(d_out30, d_addend30, 120, cudaMemcpyDeviceToDevice, st));
+        else GL(k_pt_fill_identity, 1, 1, d_out30, (size_t)1);
+        CUDA_OK(cudaStreamSynchronize(st));
+        return BPPP_OK;
+    }
+    if (n <= 1024) {
+        uint32_t *a = nullptr, *b = nullptr, *res = nullptr;
+        CUDA_OK(cudaMalloc(&a, 120 * (n + 1)));
+        CUDA_OK(cudaMalloc(&b, 120 * (n / 16 + 2)));
+        GL(k_msm_small, nblocks(n, 64), 64, d_pts, d_sc, n, a);
+        size_t count = n;
+        if (d_addend30) { CUDA_OK(cudaMemcpyAsync(a + 30 * n, d_addend30, 120, cudaMemcpyDeviceToDevice, st)); count = n + 1; }
+        tree_sum(st, a, b, count, &res);
+        CUDA_OK(cudaMemcpyAsync(d_out30, res, 120, cudaMemcpyDeviceToDevice, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        cudaFree(a); cudaFree(b);
+        CUDA_OK(cudaGetLastError());
+        return BPPP_OK;
+    }
+    const int c = msm_choose_window(n);
+    const int nwin = (256 + c) / c;            // 257 bits of signed digits
+    const uint32_t half = 1u << (c - 1);
+    const uint32_t nb = (uint32_t)nwin * half;
+    const size_t total = (size_t)nwin * n;
+    const size_t nseg = (total + MSM_SEG - 1) / MSM_SEG;
+    uint32_t CH = 64; if (CH > half) CH = half;
+    const uint32_t nchunks = (half + CH - 1) / CH;
+    uint32_t *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr, *buckets = nullptr, *partials = nullptr, *pkeys = nullptr;
+    uint32_t *chunks = nullptr, *tmp = nullptr;
+    void *cub_tmp = nullptr; size_t cub_bytes = 0;
+    CUDA_OK(cudaMalloc(&keys, 4 * total)); CUDA_OK(cudaMalloc(&vals, 4 * total));
+    CUDA_OK(cudaMalloc(&keys2, 4 * total)); CUDA_OK(cudaMalloc(&vals2, 4 * total));
+    CUDA_OK(cudaMalloc(&buckets, (size_t)120 * nb));
+    CUDA_OK(cudaMalloc(&partials, (size_t)120 * 2 * nseg)); CUDA_OK(cudaMalloc(&pkeys, 8 * nseg));
+    CUDA_OK(cudaMalloc(&chunks, (size_t)120 * nwin * nchunks)); CUDA_OK(cudaMalloc(&tmp, (size_t)120 * ((size_t)nwin * nchunks / 16 + 2)));
+    int end_bit = 1; while ((1ull << end_bit) < (unsigned long long)nb) end_bit++;
+    end_bit = 32;   // invalid keys are 0xFFFFFFFF and must sort last
+    CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys, keys2, vals, vals2, total, 0, end_bit, st));
+    CUDA_OK(cudaMalloc(&cub_tmp, cub_bytes));
+    GL(k_msm_digits, nblocks(n, 128), 128, d_sc, n, c, nwin, keys, vals);
+    CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys2, vals, vals2, total, 0, end_bit, st));
+    g_generic_launches += 4;
+    GL(k_pt_fill_identity, nblocks(nb, 128), 128, buckets, (size_t)nb);
+    GL(k_msm_segments, nblocks(nseg, 64), 64, d_pts, keys2, vals2, total, nb, buckets, partials, pkeys, nseg);
+    GL(k_msm_merge, nblocks(2 * nseg, 64), 64, partials, pkeys, 2 * nseg, nb, buckets);
+    GL(k_msm_chunks, nblocks((size_t)nwin * nchunks, 64), 64, buckets, nwin, half, CH, nchunks, chunks);
+    // per-window sum of chunk results: groups of 16 until nwin points remain
+    uint32_t *in = chunks, *out = tmp;
+    size_t per = nchunks;
+    while (per > 1) {
+        // group within each window: windows are contiguous blocks of `per` entries; pad-free because per is a power of two or 1
+        uint32_t group = per >= 16 ? 16u : (uint32_t)per;
+        size_t nout = (size_t)nwin * (per / group);
+        GL(k_pt_sum_groups, nblocks(nout, 64), 64, in, (size_t)nwin * per, group, out, nout);
+        std::swap(in, out); per /= group;
+    }
+    GL(k_msm_horner, 1, 1, in, c, nwin, d_addend30, d_out30);
+    CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(keys); cudaFree(vals); cudaFree(keys2); cudaFree(vals2); cudaFree(buckets); cudaFree(partials); cudaFree(pkeys);
+    cudaFree(chunks); cudaFree(tmp); cudaFree(cub_tmp);
+    CUDA_OK(cudaGetLastError());
+    return BPPP_OK;
+}
+
+int decode_points_to_device(cudaStream_t st, const uint8_t *h_pts, int fmt, size_t n, uint32_t **d_words) {
+    size_t psz = fmt == FMT_COMPRESSED ? 33 : 64;
+    uint8_t *d_raw = nullptr; int32_t *d_bad = nullptr; uint32_t *d_w = nullptr;
+    CUDA_OK(cudaMalloc(&d_raw, psz * (n ? n : 1))); CUDA_OK(cudaMalloc(&d_bad, 4)); CUDA_OK(cudaMalloc(&d_w, 64 * (n ? n : 1)));
+    CUDA_OK(cudaMemsetAsync(d_bad, 0, 4, st));
+    CUDA_OK(cudaMemcpyAsync(d_raw, h_pts, psz * n, cudaMemcpyHostToDevice, st));
+    if (n) GL(k_decode_points, nblocks(n, 64), 64, d_raw, fmt, d_w, d_bad, n);
+    int32_t bad = 0;
+    CUDA_OK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(d_raw); cudaFree(d_bad);
+    if (bad) { cudaFree(d_w); return fail(BPPP_ERR_ARG, "a point is not on the curve"); }
+    *d_words = d_w;
+    return BPPP_OK;
+}
+int decode_scalars_to_device(cudaStream_t st, const uint8_t *h_sc, size_t n, uint32_t **d_words) {
+    uint8_t *d_raw = nullptr; int32_t *d_bad = nullptr; uint32_t *d_w = nullptr;
+    CUDA_OK(cudaMalloc(&d_raw, 32 * (n ? n : 1))); CUDA_OK(cudaMalloc(&d_bad, 4)); CUDA_OK(cudaMalloc(&d_w, 32 * (n ? n : 1)));
+    CUDA_OK(cudaMemsetAsync(d_bad, 0, 4, st));
+    CUDA_OK(cudaMemcpyAsync(d_raw, h_sc, 32 * n, cudaMemcpyHostToDevice, st));
+    if (n) GL(k_decode_scalars, nblocks(n, 128), 128, d_raw, d_w, d_bad, n);
+    int32_t bad = 0;
+    CUDA_OK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(d_raw); cudaFree(d_bad);
+    if (bad) { cudaFree(d_w); return fail(BPPP_ERR_ARG, "a scalar is not canonical (>= n)"); }
+    *d_words = d_w;
+    return BPPP_OK;
+}
+int encode_points_from_device(cudaStream_t st, const uint32_t *d_pts30, size_t n, int fmt, uint8_t *h_out) {
+    size_t psz = fmt == FMT_COMPRESSED ? 33 : 64;
+    uint8_t *d_raw = nullptr;
+    CUDA_OK(cudaMalloc(&d_raw, psz * (n ? n : 1)));
+    if (n) GL(k_encode_points, nblocks(n, 64), 64, d_pts30, fmt, d_raw, n);
+    CUDA_OK(cudaMemcpyAsync(h_out, d_raw, psz * n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(d_raw);
+    CUDA_OK(cudaGetLastError());
+    return BPPP_OK;
+}
+
+}  // namespace bppp
+
+static int pick_device(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BPPP_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(BPPP_ERR_ARG, "bad device index");
+    CUDA_OK(cudaSetDevice(device));
+    return BPPP_OK;
+}
+
+// util::vector_mul<ProjectivePoint> (src/util.rs:46-60) with zero-extension of the shorter operand
+extern "C" int bppp_msm(int device, const uint8_t *points, int points_fmt, size_t n_points, const uint8_t *scalars32, size_t n_scalars,
+                        int out_fmt, uint8_t *out) {
+    if ((n_points && !points) || (n_scalars && !scalars32) || !out) return fail(BPPP_ERR_ARG, "null argument");
+    int rc = pick_device(device);
+    if (rc != BPPP_OK) return rc;
+    size_t n = n_points < n_scalars ? n_points : n_scalars;   // missing terms multiply the identity or zero
+    cudaStream_t st = nullptr;
+    uint32_t *d_pts = nullptr, *d_sc = nullptr, *d_out = nullptr;
+    // decode everything the caller passed so malformed trailing entries are still rejected, as deserialisation would
+    rc = decode_points_to_device(st, points, points_fmt, n_points, &d_pts);
+    if (rc != BPPP_OK) return rc;
+    rc = decode_scalars_to_device(st, scalars32, n_scalars, &d_sc);
+    if (rc != BPPP_OK) { cudaFree(d_pts); return rc; }
+    CUDA_OK(cudaMalloc(&d_out, 120));
+    rc = msm_device(st, d_pts, d_sc, n, nullptr, d_out);
+    if (rc == BPPP_OK) rc = encode_points_from_device(st, d_out, 1, out_fmt, out);
+    cudaFree(d_pts); cudaFree(d_sc); cudaFree(d_out);
+    return rc;
+}
+
+// Device-resident variant for throughput measurement: points already decoded by bppp_points_upload.
+extern "C" int bppp_points_upload(int device, const uint8_t *points, int points_fmt, size_t n, void **handle) {
+    if (!handle || (n && !points)) return fail(BPPP_ERR_ARG, "null argument");
+    int rc = pick_device(device);
+    if (rc != BPPP_OK) return rc;
+    uint32_t *d = nullptr;
+    rc = decode_points_to_device(nullptr, points, points_fmt, n, &d);
+    if (rc == BPPP_OK) *handle = d;
+    return rc;
+}
+extern "C" int bppp_scalars_upload(int device, const uint8_t *scalars32, size_t n, void **handle) {
+    if (!handle || (n && !scalars32)) return fail(BPPP_ERR_ARG, "null argument");
+    int rc = pick_device(device);
+    if (rc != BPPP_OK) return rc;
+    uint32_t *d = nullptr;
+    rc = decode_scalars_to_device(nullptr, scalars32, n, &d);
+    if (rc == BPPP_OK) *handle = d;
+    return rc;
+}
+extern "C" void bppp_device_free(int device, void *handle) { if (handle) { cudaSetDevice(device); cudaFree(handle); } }
+// MSM over uploaded arrays; *elapsed_ms (optional) = device time of the MSM alone (CUDA events)
+extern "C" int bppp_msm_uploaded(int device, const void *points_handle, const void *scalars_handle, size_t n, int out_fmt, uint8_t *out, float *elapsed_ms) {
+    if (!out || (n && (!points_handle || !scalars_handle))) return fail(BPPP_ERR_ARG, "null argument");
+    int rc = pick_device(device);
+    if (rc != BPPP_OK) return rc;
+    uint32_t *d_out = nullptr;
+    CUDA_OK(cudaMalloc(&d_out, 120));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, nullptr);
+    rc = msm_device(nullptr, (const uint32_t *)points_handle, (const uint32_t *)scalars_handle, n, nullptr, d_out);
+    cudaEventRecord(e1, nullptr); cudaEventSynchronize(e1);
+    if (elapsed_ms) cudaEventElapsedTime(elapsed_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc == BPPP_OK) rc = encode_points_from_device(nullptr, d_out, 1, out_fmt, out);
+    cudaFree(d_out);
+    return rc;
+}
+// sum of n points (e.g. the partial sums gathered from the ranks of a split MSM)
+extern "C" int bppp_points_sum(int device, const uint8_t *points, int points_fmt, size_t n, int out_fmt, uint8_t *out) {
+    if (!out || (n && !points)) return fail(BPPP_ERR_ARG, "null argument");
+    int rc = pick_device(device);
+    if (rc != BPPP_OK) return rc;
+    std::vector<uint8_t> ones(32 * (n ? n : 1), 0);
+    for (size_t i = 0; i < n; i++) ones[32 * i + 31] = 1;
+    return bppp_msm(device, points, points_fmt, n, ones.data(), n, out_fmt, out);
+}

@@ -95,6 +95,21 @@ int bppp_u64_prove_batch_dev(bppp_ctx *ctx, size_t n, const void *d_x, const voi
 /* number of kernels launched by this context since creation (for the bench's gpu_launches claim) */
 uint64_t bppp_launch_count(const bppp_ctx *ctx);
 
+/* ---- generic (arbitrary-size, single-instance) entry points ------------------------------------------------ */
+
+/* util::vector_mul<ProjectivePoint> (src/util.rs:46-60): out = sum_i scalars[i] * points[i], the shorter operand
+ * zero-extended as the reference does.  Pippenger on the device for n > 1024.  points_fmt / out_fmt: BPPP_FMT_*. */
+int bppp_msm(int device, const uint8_t *points, int points_fmt, size_t n_points, const uint8_t *scalars32, size_t n_scalars,
+             int out_fmt, uint8_t *out);
+/* The same with operands decoded and resident in HBM (handles from *_upload); *elapsed_ms = device time of the MSM. */
+int bppp_points_upload(int device, const uint8_t *points, int points_fmt, size_t n, void **handle);
+int bppp_scalars_upload(int device, const uint8_t *scalars32, size_t n, void **handle);
+void bppp_device_free(int device, void *handle);
+int bppp_msm_uploaded(int device, const void *points_handle, const void *scalars_handle, size_t n, int out_fmt, uint8_t *out,
+                      float *elapsed_ms);
+/* sum of n points: combines the per-rank partial sums of an MSM split by point range across GPUs */
+int bppp_points_sum(int device, const uint8_t *points, int points_fmt, size_t n, int out_fmt, uint8_t *out);
+
 /* Per-kernel device timing of everything launched between begin and end (CUDA events on the launching
  * stream).  end() synchronises and fills up to n_max (name[48], total ms, launch count) triples. */
 int bppp_ctx_profile_begin(bppp_ctx *ctx);
