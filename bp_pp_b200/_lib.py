@@ -16,6 +16,7 @@ EXPORTS = [
     "bppp_u64_verify_batch", "bppp_u64_verify_batch_dev", "bppp_u64_prove_batch", "bppp_u64_prove_batch_dev",
     "bppp_launch_count", "bppp_microbench", "bppp_ctx_profile_begin", "bppp_ctx_profile_end",
     "bppp_msm", "bppp_points_upload", "bppp_scalars_upload", "bppp_device_free", "bppp_msm_uploaded", "bppp_points_sum",
+    "bppp_wnla_commit", "bppp_wnla_prove", "bppp_wnla_verify",
 ]
 
 _lib = None

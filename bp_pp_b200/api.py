@@ -251,3 +251,41 @@ class UploadedMsm:
             self.close()
         except Exception:
             pass
+
+
+class WeightNormLinearArgument:
+    """Mirror of `bp_pp::wnla::WeightNormLinearArgument` (src/wnla.rs:12-19) for arbitrary lengths.
+    Points are 64-byte affine, scalars 32-byte big-endian; `prove`/`verify` use a fresh Transcript::new(label)."""
+
+    def __init__(self, g: bytes, g_vec: bytes, h_vec: bytes, c: bytes, rho: bytes, mu: bytes, device: int = 0):
+        self.g, self.g_vec, self.h_vec, self.c, self.rho, self.mu, self.device = g, g_vec, h_vec, c, rho, mu, device
+
+    def _pub(self):
+        return (C.c_int(self.device), _in(self.g), _in(self.g_vec), C.c_size_t(len(self.g_vec) // 64), _in(self.h_vec),
+                C.c_size_t(len(self.h_vec) // 64), _in(self.c), C.c_size_t(len(self.c) // 32), _in(self.rho), _in(self.mu))
+
+    # src/wnla.rs:66-72
+    def commit(self, l: bytes, n: bytes) -> bytes:
+        out = (C.c_uint8 * 33)()
+        check(lib().bppp_wnla_commit(*self._pub(), _in(l), C.c_size_t(len(l) // 32), _in(n), C.c_size_t(len(n) // 32), out), "bppp_wnla_commit")
+        return bytes(out)
+
+    # src/wnla.rs:125-190 -> (r, x, l, n) byte strings, r/x innermost round first
+    def prove(self, commitment: bytes, label: bytes, l: bytes, n: bytes):
+        ln, nn = len(l) // 32, len(n) // 32
+        r_out, x_out = (C.c_uint8 * (33 * 64))(), (C.c_uint8 * (33 * 64))()
+        l_out, n_out = (C.c_uint8 * max(32 * ln, 1))(), (C.c_uint8 * max(32 * nn, 1))()
+        rounds, lo, no, st = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_int32()
+        check(lib().bppp_wnla_prove(*self._pub(), _in(commitment), _in(l), C.c_size_t(ln), _in(n), C.c_size_t(nn), _in(label), C.c_size_t(len(label)),
+                                    r_out, x_out, C.byref(rounds), l_out, C.byref(lo), n_out, C.byref(no), C.byref(st)), "bppp_wnla_prove")
+        if st.value != ST_TRUE:
+            raise BpppError(f"wnla prove: the reference would panic here (status {st.value})")
+        return bytes(r_out)[:33 * rounds.value], bytes(x_out)[:33 * rounds.value], bytes(l_out)[:32 * lo.value], bytes(n_out)[:32 * no.value]
+
+    # src/wnla.rs:75-121 -> 1 / 0 / negative status
+    def verify(self, commitment: bytes, label: bytes, r: bytes, x: bytes, l: bytes, n: bytes) -> int:
+        verdict = C.c_int32()
+        check(lib().bppp_wnla_verify(*self._pub(), _in(commitment), _in(r), C.c_size_t(len(r) // 33), _in(x), C.c_size_t(len(x) // 33), _in(l),
+                                     C.c_size_t(len(l) // 32), _in(n), C.c_size_t(len(n) // 32), _in(label), C.c_size_t(len(label)), C.byref(verdict)),
+              "bppp_wnla_verify")
+        return verdict.value

@@ -110,6 +110,25 @@ int bppp_msm_uploaded(int device, const void *points_handle, const void *scalars
 /* sum of n points: combines the per-rank partial sums of an MSM split by point range across GPUs */
 int bppp_points_sum(int device, const uint8_t *points, int points_fmt, size_t n, int out_fmt, uint8_t *out);
 
+/* WeightNormLinearArgument { g, g_vec, h_vec, c, rho, mu } (src/wnla.rs:12-19) for arbitrary lengths on one GPU.
+ * Points 64-byte affine, scalars 32-byte big-endian, commitments / proof points 33-byte compressed.  Mismatched
+ * lengths are zero-extended exactly as the reference does (src/util.rs:24-26).  Fresh Transcript::new(label).
+ *   commit  src/wnla.rs:66-72      prove  src/wnla.rs:125-190      verify  src/wnla.rs:75-121
+ * prove: r_out / x_out need 33 * rounds bytes (rounds <= 64), innermost round first (src/wnla.rs:186-188); l_out / n_out
+ * need 32 * ln / 32 * nn bytes.  *status / *verdict: 1, 0 (verify false) or a BPPP_ST_* panic / malformed code. */
+int bppp_wnla_commit(int device, const uint8_t *g64, const uint8_t *gvec64, size_t gn, const uint8_t *hvec64, size_t hn,
+                     const uint8_t *c32, size_t cn, const uint8_t *rho32, const uint8_t *mu32, const uint8_t *l32, size_t ln,
+                     const uint8_t *n32, size_t nn, uint8_t *out33);
+int bppp_wnla_prove(int device, const uint8_t *g64, const uint8_t *gvec64, size_t gn, const uint8_t *hvec64, size_t hn,
+                    const uint8_t *c32, size_t cn, const uint8_t *rho32, const uint8_t *mu32, const uint8_t *commit33,
+                    const uint8_t *l32, size_t ln, const uint8_t *n32, size_t nn, const uint8_t *label, size_t label_len,
+                    uint8_t *r_out, uint8_t *x_out, size_t *rounds_out, uint8_t *l_out, size_t *l_out_len, uint8_t *n_out,
+                    size_t *n_out_len, int32_t *status);
+int bppp_wnla_verify(int device, const uint8_t *g64, const uint8_t *gvec64, size_t gn, const uint8_t *hvec64, size_t hn,
+                     const uint8_t *c32, size_t cn, const uint8_t *rho32, const uint8_t *mu32, const uint8_t *commit33,
+                     const uint8_t *r33, size_t rn, const uint8_t *x33, size_t xn, const uint8_t *l32, size_t ln,
+                     const uint8_t *n32, size_t nn, const uint8_t *label, size_t label_len, int32_t *verdict);
+
 /* Per-kernel device timing of everything launched between begin and end (CUDA events on the launching
  * stream).  end() synchronises and fills up to n_max (name[48], total ms, launch count) triples. */
 int bppp_ctx_profile_begin(bppp_ctx *ctx);

@@ -75,3 +75,57 @@ def test_points_sum_combines_partial_sums(oracle, ref):
     full = B.msm(b"".join(pts), b"".join(sc))
     parts = [B.msm(b"".join(pts[a:a + 500]), b"".join(sc[a:a + 500])) for a in range(0, n, 500)]   # 8 "ranks"
     assert B.points_sum(b"".join(parts)) == full
+
+
+def _wnla_instance(oracle, ref, gn, hn, ln, nn, seed):
+    rnd = random.Random(seed)
+    pts = _points(oracle, ref, 1 + gn + hn, seed=seed)
+    g, gvec, hvec = pts[0], b"".join(pts[1:1 + gn]), b"".join(pts[1 + gn:])
+    c = b"".join(_be(rnd.randrange(ref.N)) for _ in range(hn))
+    rho = rnd.randrange(1, ref.N)
+    mu = rho * rho % ref.N
+    l = b"".join(_be(rnd.randrange(ref.N)) for _ in range(ln))
+    n = b"".join(_be(rnd.randrange(ref.N)) for _ in range(nn))
+    return g, gvec, hvec, c, _be(rho), _be(mu), l, n
+
+
+@pytest.mark.parametrize("gn,hn,ln,nn", [(4, 4, 4, 4), (8, 8, 8, 8), (16, 32, 32, 16), (5, 7, 7, 5), (3, 9, 6, 2), (64, 64, 64, 64), (1200, 1200, 1200, 1200)])
+def test_wnla_commit_prove_verify_match_oracle(oracle, ref, gn, hn, ln, nn):
+    import bp_pp_b200 as B
+    g, gvec, hvec, c, rho, mu, l, n = _wnla_instance(oracle, ref, gn, hn, ln, nn, seed=1000 + gn + hn)
+    label = b"wnla test"
+    w = B.WeightNormLinearArgument(g, gvec, hvec, c, rho, mu)
+    com = oracle.wnla_commit(g, gvec, hvec, c, rho, mu, l, n)
+    assert w.commit(l, n) == com
+    r, x, lo, no = w.prove(com, label, l, n)
+    assert (r, x, lo, no) == oracle.wnla_prove(g, gvec, hvec, c, rho, mu, com, l, n, label)
+    # when |l| != |h_vec| the prover absorbs l.len() (wnla.rs:165) but the verifier |h_vec| (wnla.rs:91): the reference
+    # itself then rejects its own proof; parity with the oracle is what is asserted
+    expect = oracle.wnla_verify(g, gvec, hvec, c, rho, mu, com, r, x, lo, no, label)
+    assert expect == (1 if (ln == hn and nn == gn) or len(r) == 0 else 0)
+    assert w.verify(com, label, r, x, lo, no) == expect
+    if len(lo):
+        bad = bytearray(lo); bad[31] ^= 1
+        assert w.verify(com, label, r, x, bytes(bad), no) == 0
+    if len(r) >= 33:
+        swapped = x[:33] + r[33:]
+        assert w.verify(com, label, swapped, x, lo, no) == oracle.wnla_verify(g, gvec, hvec, c, rho, mu, com, swapped, x, lo, no, label)
+        assert w.verify(com, label, r + r[:33], x, lo, no) == 0          # x.len() != r.len()
+    assert w.verify(com, b"other label", r, x, lo, no) == (expect if len(r) == 0 else 0)
+
+
+def test_wnla_golden_fixture(oracle):
+    import json
+    import bp_pp_b200 as B
+    from conftest import ROOT
+    wn = json.load(open(os.path.join(ROOT, "tests", "golden", "wnla_golden.json")))
+    b = bytes.fromhex
+    rho = b(wn["rho"]); rho_i = int.from_bytes(rho, "big")
+    N = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+    w = B.WeightNormLinearArgument(b(wn["g"]), b"".join(b(p) for p in wn["g_vec"]), b"".join(b(p) for p in wn["h_vec"]),
+                                   b"".join(b(v) for v in wn["c"]), rho, _be(rho_i * rho_i % N))
+    l = b"".join(_be(v) for v in wn["l"]); n = b"".join(_be(v) for v in wn["n"])
+    assert w.commit(l, n).hex() == wn["commitment"]
+    r, x, lo, no = w.prove(b(wn["commitment"]), b"wnla test", l, n)
+    assert (r + x + lo + no).hex() == wn["proof"]
+    assert w.verify(b(wn["commitment"]), b"wnla test", r, x, lo, no) == 1
