@@ -17,6 +17,8 @@ EXPORTS = [
     "bppp_launch_count", "bppp_microbench", "bppp_ctx_profile_begin", "bppp_ctx_profile_end",
     "bppp_msm", "bppp_points_upload", "bppp_scalars_upload", "bppp_device_free", "bppp_msm_uploaded", "bppp_points_sum",
     "bppp_wnla_commit", "bppp_wnla_prove", "bppp_wnla_verify",
+    "bppp_circuit_commit", "bppp_circuit_prove", "bppp_circuit_verify",
+    "bppp_reciprocal_commit_value", "bppp_reciprocal_prove", "bppp_reciprocal_verify",
 ]
 
 _lib = None

@@ -289,3 +289,105 @@ class WeightNormLinearArgument:
                                      C.c_size_t(len(l) // 32), _in(n), C.c_size_t(len(n) // 32), _in(label), C.c_size_t(len(label)), C.byref(verdict)),
               "bppp_wnla_verify")
         return verdict.value
+
+
+class ReciprocalRangeProofProtocol:
+    """Mirror of `bp_pp::range_proof::reciprocal::ReciprocalRangeProofProtocol` (reciprocal.rs:64-84), any (dim_nd, dim_np)."""
+
+    def __init__(self, dim_nd: int, dim_np: int, g: bytes, g_vec: bytes, h_vec: bytes, g_vec_: bytes, h_vec_: bytes, device: int = 0):
+        self.dim_nd, self.dim_np, self.g, self.g_vec, self.h_vec, self.g_vec_, self.h_vec_, self.device = dim_nd, dim_np, g, g_vec, h_vec, g_vec_, h_vec_, device
+
+    def _pub(self):
+        return (C.c_int(self.device), C.c_size_t(self.dim_nd), C.c_size_t(self.dim_np), _in(self.g), _in(self.g_vec), C.c_size_t(len(self.g_vec) // 64),
+                _in(self.h_vec), C.c_size_t(len(self.h_vec) // 64), _in(self.g_vec_), C.c_size_t(len(self.g_vec_) // 64), _in(self.h_vec_),
+                C.c_size_t(len(self.h_vec_) // 64))
+
+    # reciprocal.rs:88-90
+    def commit_value(self, x32: bytes, s32: bytes) -> bytes:
+        out = (C.c_uint8 * 33)()
+        check(lib().bppp_reciprocal_commit_value(C.c_int(self.device), _in(self.g), _in(self.h_vec[:64]), _in(x32), _in(s32), out), "bppp_reciprocal_commit_value")
+        return bytes(out)
+
+    # reciprocal.rs:110-146 -> (record, rounds, l_len, n_len, commitment33)
+    def prove(self, x32: bytes, s32: bytes, digits, rng: bytes, label: bytes):
+        cap = 33 * (5 + 2 * 64) + 32 * 16
+        out = (C.c_uint8 * cap)()
+        ro, lo, no, st = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_int32()
+        com = (C.c_uint8 * 33)()
+        dg = (C.c_uint32 * max(self.dim_nd, 1))(*digits)
+        check(lib().bppp_reciprocal_prove(*self._pub(), _in(x32), _in(s32), dg, _in(rng), C.c_size_t(len(rng)), _in(label), C.c_size_t(len(label)), out,
+                                          C.c_size_t(cap), C.byref(ro), C.byref(lo), C.byref(no), com, C.byref(st)), "bppp_reciprocal_prove")
+        if st.value != ST_TRUE:
+            raise BpppError(f"reciprocal prove: the reference would panic here (status {st.value})")
+        n = 33 * (5 + 2 * ro.value) + 32 * (lo.value + no.value)
+        return bytes(out)[:n], ro.value, lo.value, no.value, bytes(com)
+
+    # reciprocal.rs:98-107 -> 1 / 0 / negative status
+    def verify(self, commitment33: bytes, rec: bytes, rounds_r: int, rounds_x: int, l_len: int, n_len: int, label: bytes) -> int:
+        verdict = C.c_int32()
+        check(lib().bppp_reciprocal_verify(*self._pub(), _in(commitment33), _in(rec), C.c_size_t(rounds_r), C.c_size_t(rounds_x), C.c_size_t(l_len),
+                                           C.c_size_t(n_len), _in(label), C.c_size_t(len(label)), C.byref(verdict)), "bppp_reciprocal_verify")
+        return verdict.value
+
+
+class CircuitDesc(C.Structure):
+    """`bppp_circuit_desc` of include/bppp.h."""
+    _u8p = C.POINTER(C.c_uint8)
+    _fields_ = [
+        ("dim_nm", C.c_size_t), ("dim_no", C.c_size_t), ("k", C.c_size_t), ("dim_nv", C.c_size_t), ("f_l", C.c_int), ("f_m", C.c_int),
+        ("g64", _u8p), ("gvec64", _u8p), ("hvec64", _u8p), ("gvec2_64", _u8p), ("hvec2_64", _u8p),
+        ("gn", C.c_size_t), ("hn", C.c_size_t), ("gn2", C.c_size_t), ("hn2", C.c_size_t),
+        ("W_m32", _u8p), ("W_l32", _u8p), ("a_m32", _u8p), ("a_l32", _u8p),
+        ("part_lo", C.POINTER(C.c_int32)), ("part_ll", C.POINTER(C.c_int32)), ("part_lr", C.POINTER(C.c_int32)), ("part_no", C.POINTER(C.c_int32)),
+        ("part_n", C.c_size_t),
+    ]
+
+
+class ArithmeticCircuit:
+    """Mirror of `bp_pp::circuit::ArithmeticCircuit` (circuit.rs:95-139): dense row-major W_m / W_l (32-byte scalars) and the
+    partition function tabulated as four index lists (-1 = None)."""
+
+    def __init__(self, dim_nm, dim_no, k, dim_nv, g, g_vec, h_vec, W_m, W_l, a_m, a_l, f_l, f_m, g_vec_, h_vec_, part_lo, part_ll, part_lr, part_no, device=0):
+        self.device = device
+        self._keep = []
+        d = CircuitDesc()
+
+        def pb(b):
+            a = _in(b); self._keep.append(a); return C.cast(a, CircuitDesc._u8p)
+
+        def pi(v):
+            a = (C.c_int32 * max(len(v), 1))(*v); self._keep.append(a); return C.cast(a, C.POINTER(C.c_int32))
+
+        d.dim_nm, d.dim_no, d.k, d.dim_nv, d.f_l, d.f_m = dim_nm, dim_no, k, dim_nv, int(f_l), int(f_m)
+        d.g64, d.gvec64, d.hvec64, d.gvec2_64, d.hvec2_64 = pb(g), pb(g_vec), pb(h_vec), pb(g_vec_), pb(h_vec_)
+        d.gn, d.hn, d.gn2, d.hn2 = len(g_vec) // 64, len(h_vec) // 64, len(g_vec_) // 64, len(h_vec_) // 64
+        d.W_m32, d.W_l32, d.a_m32, d.a_l32 = pb(W_m), pb(W_l), pb(a_m), pb(a_l)
+        d.part_lo, d.part_ll, d.part_lr, d.part_no = pi(part_lo), pi(part_ll), pi(part_lr), pi(part_no)
+        d.part_n = len(part_lo)
+        self.desc = d
+
+    # circuit.rs:146-151
+    def commit(self, v32: bytes, s32: bytes) -> bytes:
+        out = (C.c_uint8 * 33)()
+        check(lib().bppp_circuit_commit(C.c_int(self.device), C.byref(self.desc), _in(v32), _in(s32), out), "bppp_circuit_commit")
+        return bytes(out)
+
+    # circuit.rs:260-556 -> (record, rounds, l_len, n_len)
+    def prove(self, commits33: bytes, v32: bytes, sv32: bytes, wl32: bytes, wr32: bytes, wo32: bytes, rng: bytes, label: bytes):
+        cap = 33 * (4 + 2 * 64) + 32 * 16
+        out = (C.c_uint8 * cap)()
+        ro, lo, no, st = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_int32()
+        check(lib().bppp_circuit_prove(C.c_int(self.device), C.byref(self.desc), _in(commits33), _in(v32), _in(sv32), _in(wl32), _in(wr32), _in(wo32), _in(rng),
+                                       C.c_size_t(len(rng)), _in(label), C.c_size_t(len(label)), out, C.c_size_t(cap), C.byref(ro), C.byref(lo), C.byref(no),
+                                       C.byref(st)), "bppp_circuit_prove")
+        if st.value != ST_TRUE:
+            raise BpppError(f"circuit prove: the reference would panic here (status {st.value})")
+        n = 33 * (4 + 2 * ro.value) + 32 * (lo.value + no.value)
+        return bytes(out)[:n], ro.value, lo.value, no.value
+
+    # circuit.rs:154-256
+    def verify(self, commits33: bytes, rec: bytes, rounds_r: int, rounds_x: int, l_len: int, n_len: int, label: bytes) -> int:
+        verdict = C.c_int32()
+        check(lib().bppp_circuit_verify(C.c_int(self.device), C.byref(self.desc), _in(commits33), _in(rec), C.c_size_t(rounds_r), C.c_size_t(rounds_x),
+                                        C.c_size_t(l_len), C.c_size_t(n_len), _in(label), C.c_size_t(len(label)), C.byref(verdict)), "bppp_circuit_verify")
+        return verdict.value

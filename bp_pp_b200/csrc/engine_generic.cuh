@@ -17,4 +17,24 @@ int decode_scalars_to_device(cudaStream_t st, const uint8_t *h_sc, size_t n, uin
 int encode_points_from_device(cudaStream_t st, const uint32_t *d_pts30, size_t n, int fmt, uint8_t *h_out);
 uint64_t generic_launch_count();
 
+// engine_wnla.cu -- device-resident WNLA instance.  pts = [H (Lh) | G (Lg) | g] affine words; c scalar words.
+struct WnlaDev {
+    size_t Lh = 0, Lg = 0;            // padded lengths
+    size_t len_h = 0, len_g = 0;      // true generator lengths (verify absorbs these, wnla.rs:91-92)
+    uint32_t *pts = nullptr, *c = nullptr;
+    Sc rho, mu;
+    void release() { cudaFree(pts); cudaFree(c); pts = c = nullptr; }
+};
+struct WnlaProofHost { std::vector<uint8_t> r33, x33, l32, n32; };   // r/x in push order (innermost round first)
+int upload_padded_scalars(cudaStream_t st, const uint8_t *h32, size_t n, size_t L, uint32_t **d);
+int wnla_load(cudaStream_t st, WnlaDev &w, const uint8_t *g64, const uint8_t *gvec64, size_t gn, const uint8_t *hvec64, size_t hn, const uint8_t *c32, size_t cn,
+              const uint8_t *rho32, const uint8_t *mu32, size_t ln, size_t nn);
+int wnla_commit_dev(cudaStream_t st, const WnlaDev &w, const uint32_t *d_l, const uint32_t *d_n, uint32_t *d_out30);
+int wnla_prove_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, uint32_t *d_l, uint32_t *d_n, size_t len_l, size_t len_n, WnlaProofHost &proof,
+                   int32_t *status);
+int wnla_verify_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, const uint8_t *r33, size_t rn, const uint8_t *x33, size_t xn,
+                    const uint8_t *l32, size_t ln, const uint8_t *n32, size_t nn, int32_t *verdict);
+int point_bytes_to_pt30(cudaStream_t st, const uint8_t *p, int fmt, uint32_t *d_out30);
+uint64_t wnla_launch_count();
+
 }  // namespace bppp

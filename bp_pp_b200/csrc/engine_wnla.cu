@@ -234,16 +234,7 @@ static int sum_partials_to_host(cudaStream_t st, const uint32_t *d_partials, siz
     return BPPP_OK;
 }
 
-// Device-resident WNLA instance.  pts = [H (Lh) | G (Lg) | g] affine words; c, l, n scalars words.
-struct WnlaDev {
-    size_t Lh = 0, Lg = 0;            // padded lengths
-    size_t len_h = 0, len_g = 0;      // true generator lengths (verify absorbs these, wnla.rs:91-92)
-    uint32_t *pts = nullptr, *c = nullptr;
-    Sc rho, mu;
-    void release() { cudaFree(pts); cudaFree(c); pts = c = nullptr; }
-};
-
-static int upload_padded_scalars(cudaStream_t st, const uint8_t *h32, size_t n, size_t L, uint32_t **d) {
+int upload_padded_scalars(cudaStream_t st, const uint8_t *h32, size_t n, size_t L, uint32_t **d) {
     std::vector<uint8_t> buf(32 * (L ? L : 1), 0);
     memcpy(buf.data(), h32, 32 * n);
     return decode_scalars_to_device(st, buf.data(), L, d);
@@ -284,7 +275,6 @@ int wnla_commit_dev(cudaStream_t st, const WnlaDev &w, const uint32_t *d_l, cons
     return rc;
 }
 
-struct WnlaProofHost { std::vector<uint8_t> r33, x33, l32, n32; };   // r/x in push order (innermost round first)
 
 // wnla.rs:125-190.  d_com30: commitment (projective, device).  d_l / d_n: padded witness arrays (consumed).
 int wnla_prove_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, uint32_t *d_l, uint32_t *d_n, size_t len_l, size_t len_n, WnlaProofHost &proof,
@@ -441,6 +431,16 @@ int wnla_verify_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, c
 }
 
 uint64_t wnla_launch_count() { return g_wnla_launches.load(); }
+
+int point_bytes_to_pt30(cudaStream_t st, const uint8_t *p, int fmt, uint32_t *d_out30) {
+    uint32_t *d16 = nullptr;
+    int rc = decode_points_to_device(st, p, fmt, 1, &d16);
+    if (rc != BPPP_OK) return rc;
+    k_decode_one_point30<<<1, 1, 0, st>>>(d16, d_out30);
+    CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(d16);
+    return BPPP_OK;
+}
 
 }  // namespace bppp
 

@@ -129,6 +129,45 @@ int bppp_wnla_verify(int device, const uint8_t *g64, const uint8_t *gvec64, size
                      const uint8_t *r33, size_t rn, const uint8_t *x33, size_t xn, const uint8_t *l32, size_t ln,
                      const uint8_t *n32, size_t nn, const uint8_t *label, size_t label_len, int32_t *verdict);
 
+/* ArithmeticCircuit<P> (src/circuit.rs:95-139) with dense row-major W_m (dim_nm x dim_nw) and W_l (dim_nl x dim_nw),
+ * dim_nl = dim_nv * k, dim_nw = 2 dim_nm + dim_no, and the partition closure tabulated: part_xx[j] = index or -1 for
+ * j < part_n (PartitionType LO / LL / LR / NO, src/circuit.rs:15-20).  Generators 64-byte affine. */
+typedef struct bppp_circuit_desc {
+    size_t dim_nm, dim_no, k, dim_nv;
+    int f_l, f_m;
+    const uint8_t *g64, *gvec64, *hvec64, *gvec2_64, *hvec2_64;   /* g, g_vec, h_vec, g_vec_, h_vec_ */
+    size_t gn, hn, gn2, hn2;
+    const uint8_t *W_m32, *W_l32, *a_m32, *a_l32;
+    const int32_t *part_lo, *part_ll, *part_lr, *part_no;
+    size_t part_n;
+} bppp_circuit_desc;
+/* ArithmeticCircuit::commit / prove / verify (src/circuit.rs:146-151, 260-556, 154-256); fresh Transcript::new(label).
+ * prove: witness v (k x dim_nv), s_v (k), w_l, w_r (dim_nm), w_o (dim_no); rng = (18 + dim_nv + dim_nm) x 64 bytes in draw
+ * order; out record = c_l c_r c_o c_s | r[rounds] | x[rounds] | l | n.  The host evaluates the coefficient vectors
+ * (scalar field), the GPU every commitment and the WNLA. */
+int bppp_circuit_commit(int device, const bppp_circuit_desc *desc, const uint8_t *v32, const uint8_t *s32, uint8_t *out33);
+int bppp_circuit_prove(int device, const bppp_circuit_desc *desc, const uint8_t *commits33, const uint8_t *v32, const uint8_t *sv32,
+                       const uint8_t *wl32, const uint8_t *wr32, const uint8_t *wo32, const uint8_t *rng, size_t rng_len,
+                       const uint8_t *label, size_t label_len, uint8_t *out, size_t out_cap, size_t *rounds_out,
+                       size_t *l_len_out, size_t *n_len_out, int32_t *status);
+int bppp_circuit_verify(int device, const bppp_circuit_desc *desc, const uint8_t *commits33, const uint8_t *rec, size_t rounds_r,
+                        size_t rounds_x, size_t l_len, size_t n_len, const uint8_t *label, size_t label_len, int32_t *verdict);
+
+/* ReciprocalRangeProofProtocol { dim_nd, dim_np, g, g_vec, h_vec, g_vec_, h_vec_ } (src/range_proof/reciprocal.rs:64-84)
+ * for arbitrary dimensions: commit_value (:88-90), prove (:110-146), verify (:98-107); make_circuit (:150-214) is built
+ * internally from the challenge.  digits: dim_nd values < dim_np.  rng = (1 + 18 + (dim_nd + 1) + dim_nd) x 64 bytes.
+ * out record = c_l c_r c_o c_s | r[rounds] | x[rounds] | l | n | r. */
+int bppp_reciprocal_commit_value(int device, const uint8_t *g64, const uint8_t *h0_64, const uint8_t *x32, const uint8_t *s32, uint8_t *out33);
+int bppp_reciprocal_prove(int device, size_t dim_nd, size_t dim_np, const uint8_t *g64, const uint8_t *gvec64, size_t gn,
+                          const uint8_t *hvec64, size_t hn, const uint8_t *gvec2_64, size_t gn2, const uint8_t *hvec2_64, size_t hn2,
+                          const uint8_t *x32, const uint8_t *s32, const uint32_t *digits, const uint8_t *rng, size_t rng_len,
+                          const uint8_t *label, size_t label_len, uint8_t *out, size_t out_cap, size_t *rounds_out,
+                          size_t *l_len_out, size_t *n_len_out, uint8_t *commit33_out, int32_t *status);
+int bppp_reciprocal_verify(int device, size_t dim_nd, size_t dim_np, const uint8_t *g64, const uint8_t *gvec64, size_t gn,
+                           const uint8_t *hvec64, size_t hn, const uint8_t *gvec2_64, size_t gn2, const uint8_t *hvec2_64, size_t hn2,
+                           const uint8_t *commit33, const uint8_t *rec, size_t rounds_r, size_t rounds_x, size_t l_len, size_t n_len,
+                           const uint8_t *label, size_t label_len, int32_t *verdict);
+
 /* Per-kernel device timing of everything launched between begin and end (CUDA events on the launching
  * stream).  end() synchronises and fills up to n_max (name[48], total ms, launch count) triples. */
 int bppp_ctx_profile_begin(bppp_ctx *ctx);

@@ -129,3 +129,75 @@ def test_wnla_golden_fixture(oracle):
     r, x, lo, no = w.prove(b(wn["commitment"]), b"wnla test", l, n)
     assert (r + x + lo + no).hex() == wn["proof"]
     assert w.verify(b(wn["commitment"]), b"wnla test", r, x, lo, no) == 1
+
+
+def _reciprocal_case(oracle, ref, nd, np_, hn2, seed):
+    rnd = random.Random(seed)
+    pts = _points(oracle, ref, 1 + nd + (nd + 10) + hn2, seed=seed)
+    g, gvec = pts[0], b"".join(pts[1:1 + nd])
+    hvec, hvec2 = b"".join(pts[1 + nd:1 + nd + nd + 10]), b"".join(pts[1 + nd + nd + 10:])
+    digits = [rnd.randrange(np_) for _ in range(nd)]
+    x = sum(d * pow(np_, i, ref.N) for i, d in enumerate(digits)) % ref.N
+    s = rnd.randrange(ref.N)
+    rng = rnd.randbytes((1 + 18 + (nd + 1) + nd) * 64)
+    return g, gvec, hvec, hvec2, digits, _be(x), _be(s), rng
+
+
+@pytest.mark.parametrize("nd,np_,hn2", [(4, 4, 2), (16, 16, 6), (6, 3, 0), (64, 16, 54)])
+def test_reciprocal_generic_dims_match_oracle(oracle, ref, nd, np_, hn2):
+    import bp_pp_b200 as B
+    g, gvec, hvec, hvec2, digits, x32, s32, rng = _reciprocal_case(oracle, ref, nd, np_, hn2, seed=500 + nd)
+    label = b"reciprocal"
+    proto = B.ReciprocalRangeProofProtocol(nd, np_, g, gvec, hvec, b"", hvec2)
+    rec_o, rounds, ll, nl, com_o = oracle.reciprocal_prove(nd, np_, g, gvec, hvec, b"", hvec2, x32, s32, digits, rng, label)
+    rec, rounds2, ll2, nl2, com = proto.prove(x32, s32, digits, rng, label)
+    assert com == com_o == proto.commit_value(x32, s32)
+    assert (rounds2, ll2, nl2) == (rounds, ll, nl)
+    assert rec == rec_o
+    assert proto.verify(com, rec, rounds, rounds, ll, nl, label) == 1
+    assert oracle.reciprocal_verify(nd, np_, g, gvec, hvec, b"", hvec2, com, rec, rounds, rounds, ll, nl, label) == 1
+    bad = bytearray(rec); bad[-40] ^= 1        # inside n / l scalars
+    assert proto.verify(com, bytes(bad), rounds, rounds, ll, nl, label) == oracle.reciprocal_verify(nd, np_, g, gvec, hvec, b"", hvec2, com, bytes(bad), rounds, rounds, ll, nl, label) == 0
+    assert proto.verify(com, rec, rounds, rounds, ll, nl, b"other") == 0
+
+
+def test_generic_reciprocal_equals_the_u64_fast_path(oracle, ref, golden, gens64):
+    """dim_nd = dim_np = 16 with h split 26 + 6 is exactly the u64 protocol (u64_proof.rs:43-51): the batched closed-form kernels
+    and the generic dense-matrix path must emit the same bytes."""
+    import bp_pp_b200 as B
+    c = golden["cases"][0]
+    g, gvec, hvec = gens64[:64], gens64[64:64 * 17], gens64[64 * 17:]
+    proto = B.ReciprocalRangeProofProtocol(16, 16, g, gvec, hvec[:64 * 26], b"", hvec[64 * 26:])
+    digits = [(c["x"] >> (4 * i)) & 15 for i in range(16)]
+    rec, rounds, ll, nl, com = proto.prove(_be(c["x"]), bytes.fromhex(c["blind"]), digits, ref.synth_rng_bytes(c["rng_index"]), b"u64 range proof")
+    assert rec.hex() == c["proof"] and com.hex() == c["commitment"] and (rounds, ll, nl) == (4, 2, 1)
+    assert proto.verify(com, rec, 4, 4, 2, 1, b"u64 range proof") == 1
+
+
+def test_ac_works_circuit_on_gpu(oracle, ref):
+    """The reference's `ac_works` (src/tests.rs:44-136) through the generic circuit entry points."""
+    import bp_pp_b200 as B
+    N = ref.N
+    x, y, r, z = 3, 5, 8, 15
+    pts = _points(oracle, ref, 18, seed=31)
+    g, g_vec, h_vec = pts[0], pts[1:2], pts[2:18]
+    be = lambda v: (v % N).to_bytes(32, "big")  # noqa: E731
+    flat = lambda m: b"".join(be(e) for row in m for e in row)  # noqa: E731
+    W_m = [[0, 0, 1, 0]]
+    W_l = [[0, 1, 0, 0], [0, N - 1, 1, 0]]
+    a_m, a_l = [0], [(-r) % N, (-z) % N]
+    args = (1, 2, 1, 2, True, False, g, g_vec[0], b"".join(h_vec[:11]), b"", b"".join(h_vec[11:]), flat(W_m), flat(W_l), b"".join(be(e) for e in a_m),
+            b"".join(be(e) for e in a_l), [-1, -1], [0, 1], [-1, -1], [-1, -1])
+    desc = oracle.make_circuit_desc(*args)
+    circ = B.ArithmeticCircuit(1, 2, 1, 2, g, g_vec[0], b"".join(h_vec[:11]), flat(W_m), flat(W_l), b"".join(be(e) for e in a_m), b"".join(be(e) for e in a_l),
+                               True, False, b"", b"".join(h_vec[11:]), [-1, -1], [0, 1], [-1, -1], [-1, -1])
+    s_v = random.Random(4).randrange(N)
+    rng = random.Random(5).randbytes((18 + 2 + 1) * 64)
+    com = circ.commit(be(x) + be(y), be(s_v))
+    assert com == oracle.circuit_commit(desc, be(x) + be(y), be(s_v))
+    rec, rounds, ll, nl = circ.prove(com, be(x) + be(y), be(s_v), be(x), be(y), be(z) + be(r), rng, b"circuit test")
+    rec_o, rounds_o, ll_o, nl_o = oracle.circuit_prove(desc, com, be(x) + be(y), be(s_v), be(x), be(y), be(z) + be(r), rng, b"circuit test")
+    assert (rec, rounds, ll, nl) == (rec_o, rounds_o, ll_o, nl_o)
+    assert circ.verify(com, rec, rounds, rounds, ll, nl, b"circuit test") == 1
+    bad = bytearray(rec); bad[-1] ^= 1
+    assert circ.verify(com, bytes(bad), rounds, rounds, ll, nl, b"circuit test") == 0
