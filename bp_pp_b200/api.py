@@ -391,3 +391,10 @@ class ArithmeticCircuit:
         check(lib().bppp_circuit_verify(C.c_int(self.device), C.byref(self.desc), _in(commits33), _in(rec), C.c_size_t(rounds_r), C.c_size_t(rounds_x),
                                         C.c_size_t(l_len), C.c_size_t(n_len), _in(label), C.c_size_t(len(label)), C.byref(verdict)), "bppp_circuit_verify")
         return verdict.value
+
+
+def points_generate(base64: bytes, step64: bytes, n: int, device: int = 0) -> bytes:
+    """n synthetic generators base + i*step as 64-byte affine points (computed on the GPU)."""
+    out = (C.c_uint8 * max(64 * n, 1))()
+    check(lib().bppp_points_generate(C.c_int(device), _in(base64), _in(step64), C.c_size_t(n), out), "bppp_points_generate")
+    return bytes(out)[:64 * n]

@@ -426,6 +426,33 @@ extern "C" int bppp_msm_uploaded(int device, const void *points_handle, const vo
     cudaFree(d_out);
     return rc;
 }
+// synthetic generators for large-n measurements: out[i] = base + i * step (affine 64-byte points), computed on the device
+__global__ void __launch_bounds__(64) k_points_generate(const uint32_t *two16, size_t n, uint8_t *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PtA base, step;
+    bool okb = load_dev_point(base, two16, 0), oks = load_dev_point(step, two16, 1);
+    Pt r = pt_add(pt_from_affine(base, !okb), pt_mul_glv(pt_from_affine(step, !oks), sc_from_u64((uint64_t)i)));
+    bool id = pt_is_identity(r);
+    PtA a = pt_to_affine_with_zinv(r, fe_inv(r.z));
+    pta_to_xy64(out + 64 * i, a, id);
+}
+extern "C" int bppp_points_generate(int device, const uint8_t *base64, const uint8_t *step64, size_t n, uint8_t *out64) {
+    if (!base64 || !step64 || (n && !out64)) return fail(BPPP_ERR_ARG, "null argument");
+    int rc = pick_device(device);
+    if (rc != BPPP_OK) return rc;
+    uint8_t two[128]; memcpy(two, base64, 64); memcpy(two + 64, step64, 64);
+    uint32_t *d_two = nullptr; uint8_t *d_out = nullptr;
+    rc = decode_points_to_device(nullptr, two, FMT_AFFINE64, 2, &d_two);
+    if (rc != BPPP_OK) return rc;
+    CUDA_OK(cudaMalloc(&d_out, 64 * (n ? n : 1)));
+    if (n) k_points_generate<<<nblocks(n, 64), 64>>>(d_two, n, d_out);
+    CUDA_OK(cudaMemcpy(out64, d_out, 64 * n, cudaMemcpyDeviceToHost));
+    cudaFree(d_two); cudaFree(d_out);
+    CUDA_OK(cudaGetLastError());
+    return BPPP_OK;
+}
+
 // sum of n points (e.g. the partial sums gathered from the ranks of a split MSM)
 extern "C" int bppp_points_sum(int device, const uint8_t *points, int points_fmt, size_t n, int out_fmt, uint8_t *out) {
     if (!out || (n && !points)) return fail(BPPP_ERR_ARG, "null argument");

@@ -37,3 +37,25 @@ def gather_status(local: Sequence[int], n: int) -> List[int]:
     for r in range(world):
         full += outs[r][:sizes[r]].tolist()
     return full
+
+
+def msm_sharded(points: bytes, scalars32: bytes, device: int, points_fmt: int = 1) -> bytes:
+    """One large MSM split by point range over the ranks of the process group (one GPU each): every rank computes the
+    partial sum of its contiguous block on its own GPU, the 33-byte partial points are all-gathered (NCCL when the group
+    is NCCL: the only data-path collective in this package, a few hundred bytes) and every rank adds them.
+    `points`/`scalars32` hold the FULL vectors on every rank (generators are replicated); returns the 33-byte sum."""
+    import torch
+    import torch.distributed as dist
+    from . import api
+    world, rank = dist.get_world_size(), dist.get_rank()
+    psz = 33 if points_fmt == api.FMT_COMPRESSED else 64
+    n = min(len(points) // psz, len(scalars32) // 32)
+    lo, hi = shard_bounds(n, world, rank)
+    part = api.msm(points[psz * lo:psz * hi], scalars32[32 * lo:32 * hi], points_fmt, api.FMT_COMPRESSED, device)
+    use_cuda = dist.get_backend() == "nccl"
+    dev = torch.device("cuda", device) if use_cuda else torch.device("cpu")
+    mine = torch.frombuffer(bytearray(part), dtype=torch.uint8).to(dev)
+    gathered = [torch.empty(33, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    allparts = b"".join(bytes(t.cpu().numpy().tobytes()) for t in gathered)
+    return api.points_sum(allparts, api.FMT_COMPRESSED, api.FMT_COMPRESSED, device)

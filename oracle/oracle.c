@@ -497,7 +497,7 @@ static scv vector_tensor_mul(arena *A, scv a, scv b) {
 }
 /* dense row-major matrix */
 typedef struct { sc *v; size_t rows, cols; } scm;
-static scm scm_new(arena *A, size_t rows, size_t cols) { scm m = {(sc *)aalloc(A, (rows * cols ? rows * cols : 1) * sizeof(sc)), rows, cols}; for (size_t i = 0; i < rows * cols; i++) m.v[i] = SC_ZERO; return m; }
+static scm scm_new(arena *A, size_t rows, size_t cols) { scm m = {(sc *)aalloc(A, ((rows * cols) != 0 ? rows * cols : 1) * sizeof(sc)), rows, cols}; for (size_t i = 0; i < rows * cols; i++) m.v[i] = SC_ZERO; return m; }
 /* util.rs:118-132 */
 static scm diag_inv(arena *A, const sc *x, size_t n) {
     sc xi = inv_or_panic(x, A), val = SC_ONE;

