@@ -6,9 +6,9 @@
 // Pippenger with signed c-bit windows:
 //   k_msm_digits      signed digits of every scalar -> (bucket key, point index | sign) pairs, window-major
 //   cub radix sort    pairs by bucket key (the only library call; it moves 8-byte pairs, no curve arithmetic)
-//   k_msm_segments    one thread per 32 consecutive sorted pairs: mixed-adds runs of equal key; runs that lie inside
-//                     the segment go straight to their bucket, runs crossing a segment edge leave a partial sum
-//   k_msm_merge       partial sums of the same bucket are added (only buckets spanning several segments)
+//   k_msm_bounds      first / one-past-last sorted position of every bucket
+//   k_msm_buckets     one thread per bucket: mixed-adds its points; buckets above MSM_HEAVY entries (skewed scalars) are
+//                     deferred to k_msm_heavy (one 128-thread block per such bucket, shared-memory tree reduction)
 //   k_msm_chunks      per window: chunked running-sum reduction  sum_b (b+1) B_b  (two adds per bucket)
 //   k_pt_sum_groups   tree sums;  k_msm_horner: sum_w 2^(c w) W_w
 // Small inputs (n <= 1024) use one GLV scalar multiplication per point and the same tree sum.
@@ -101,69 +101,55 @@ __global__ void k_msm_digits(const uint32_t *sc, size_t n, int c, int nwin, uint
     }
 }
 
-static constexpr int MSM_SEG = 32;
+static constexpr uint32_t MSM_HEAVY = 512;   // bucket sizes above this go to the block-per-bucket kernel
 
-// bucket sums and partials are stored AoS, 30 words per point
-__global__ void __launch_bounds__(64) k_msm_segments(const uint32_t *pts, const uint32_t *keys, const uint32_t *vals, size_t total, uint32_t nb,
-                                                      uint32_t *buckets, uint32_t *partials, uint32_t *pkeys, size_t nseg) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nseg) return;
-    size_t p0 = t * MSM_SEG, p1 = p0 + MSM_SEG < total ? p0 + MSM_SEG : total;
-    uint32_t head_key = 0xFFFFFFFFu, tail_key = 0xFFFFFFFFu;
-    Pt acc = pt_identity();
-    uint32_t cur = keys[p0];
-    bool is_head = true;      // the first run may have started in the previous segment
-    bool head_open = p0 > 0 && keys[p0 - 1] == cur;
-#pragma unroll 1
-    for (size_t p = p0; p < p1; p++) {
-        uint32_t k = keys[p];
-        if (k != cur) {
-            // run `cur` ended inside this segment
-            if (cur < nb) {
-                if (is_head && head_open) { st_pt30(partials + 30 * (2 * t), acc); head_key = cur; }
-                else st_pt30(buckets + 30 * (size_t)cur, acc);
-            }
-            acc = pt_identity(); cur = k; is_head = false;
-        }
-        if (k < nb) {
-            uint32_t v = vals[p];
-            PtA q;
-            if (load_dev_point(q, pts, v & 0x7FFFFFFFu)) {
-                if (v >> 31) q.y = fe_normalize_weak(fe_negate(q.y, 1));
-                acc = pt_add_mixed(acc, q);
-            }
-        }
-    }
-    if (cur < nb) {
-        bool tail_open = p1 < total && keys[p1] == cur;
-        if (is_head && head_open) { st_pt30(partials + 30 * (2 * t), acc); head_key = cur; }       // whole segment is one open run
-        else if (tail_open) { st_pt30(partials + 30 * (2 * t + 1), acc); tail_key = cur; }
-        else st_pt30(buckets + 30 * (size_t)cur, acc);
-    }
-    pkeys[2 * t] = head_key; pkeys[2 * t + 1] = tail_key;
-}
-// buckets whose run crosses segment edges: the first partial of each key run owns the sum
-__global__ void __launch_bounds__(64) k_msm_merge(const uint32_t *partials, const uint32_t *pkeys, size_t np, uint32_t nb, uint32_t *buckets) {
-    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= np) return;
-    uint32_t k = pkeys[j];
+__global__ void k_msm_bounds(const uint32_t *keys, size_t total, uint32_t nb, uint32_t *start, uint32_t *end) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    uint32_t k = keys[p];
     if (k >= nb) return;
-    // previous non-empty partial with the same key? then that one owns the run
-    for (size_t q = j; q-- > 0;) {
-        uint32_t kq = pkeys[q];
-        if (kq == 0xFFFFFFFFu) continue;
-        if (kq == k) return;
-        break;
-    }
-    Pt acc = ld_pt30(partials + 30 * j);
+    if (p == 0 || keys[p - 1] != k) start[k] = (uint32_t)p;
+    if (p + 1 == total || keys[p + 1] != k) end[k] = (uint32_t)(p + 1);
+}
+__device__ __forceinline__ Pt msm_accumulate_range(const uint32_t *pts, const uint32_t *vals, uint32_t p0, uint32_t p1, uint32_t stride) {
+    Pt acc = pt_identity();
 #pragma unroll 1
-    for (size_t q = j + 1; q < np; q++) {
-        uint32_t kq = pkeys[q];
-        if (kq == 0xFFFFFFFFu) continue;
-        if (kq != k) break;
-        acc = pt_add(acc, ld_pt30(partials + 30 * q));
+    for (uint32_t p = p0; p < p1; p += stride) {
+        uint32_t v = vals[p];
+        PtA q;
+        if (load_dev_point(q, pts, v & 0x7FFFFFFFu)) {
+            if (v >> 31) q.y = fe_normalize_weak(fe_negate(q.y, 1));
+            acc = pt_add_mixed(acc, q);
+        }
     }
-    st_pt30(buckets + 30 * (size_t)k, acc);
+    return acc;
+}
+// bucket sums are stored AoS, 30 words per point
+__global__ void __launch_bounds__(64, 7) k_msm_buckets(const uint32_t *pts, const uint32_t *vals, const uint32_t *start, const uint32_t *end, uint32_t nb,
+                                                        uint32_t *buckets, uint32_t *heavy, uint32_t *heavy_count, uint32_t heavy_cap) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint32_t p0 = start[b], p1 = end[b];
+    if (p1 - p0 > MSM_HEAVY) {
+        uint32_t slot = atomicAdd(heavy_count, 1u);
+        if (slot < heavy_cap) { heavy[slot] = (uint32_t)b; st_pt30(buckets + 30 * b, pt_identity()); return; }
+    }
+    st_pt30(buckets + 30 * b, msm_accumulate_range(pts, vals, p0, p1, 1));
+}
+__global__ void __launch_bounds__(128) k_msm_heavy(const uint32_t *pts, const uint32_t *vals, const uint32_t *start, const uint32_t *end, const uint32_t *heavy,
+                                                    const uint32_t *heavy_count, uint32_t heavy_cap, uint32_t *buckets) {
+    __shared__ uint32_t sh[128 * 30];
+    uint32_t cnt = *heavy_count; if (cnt > heavy_cap) cnt = heavy_cap;
+    if (blockIdx.x >= cnt) return;
+    uint32_t b = heavy[blockIdx.x];
+    Pt acc = msm_accumulate_range(pts, vals, start[b] + threadIdx.x, end[b], 128);
+    st_pt30(sh + 30 * threadIdx.x, acc);
+    __syncthreads();
+    for (int s = 64; s >= 1; s >>= 1) {
+        if ((int)threadIdx.x < s) st_pt30(sh + 30 * threadIdx.x, pt_add(ld_pt30(sh + 30 * threadIdx.x), ld_pt30(sh + 30 * (threadIdx.x + s))));
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_pt30(buckets + 30 * (size_t)b, ld_pt30(sh));
 }
 __global__ void k_pt_fill_identity(uint32_t *pts30, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -229,6 +215,24 @@ static std::atomic<uint64_t> g_generic_launches{0};
 uint64_t generic_launch_count() { return g_generic_launches.load(); }
 #define GL(kern, grid, block, ...) do { kern<<<(grid), (block), 0, st>>>(__VA_ARGS__); g_generic_launches++; } while (0)
 
+// per-device scratch slab that only grows (single host thread per device, like the contexts)
+struct Carver { size_t total = 0; size_t take(size_t bytes) { size_t o = total; total += (bytes + 255) & ~(size_t)255; return o; } };
+static uint8_t *g_slab[16] = {};
+static size_t g_slab_cap[16] = {};
+static int scratch_reserve(size_t bytes, uint8_t **out) {
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) return fail(BPPP_ERR_ARG, "device index out of range");
+    if (g_slab_cap[dev] < bytes) {
+        if (g_slab[dev]) { CUDA_OK(cudaDeviceSynchronize()); cudaFree(g_slab[dev]); g_slab[dev] = nullptr; g_slab_cap[dev] = 0; }
+        size_t want = bytes + bytes / 4;
+        CUDA_OK(cudaMalloc(&g_slab[dev], want));
+        g_slab_cap[dev] = want;
+    }
+    *out = g_slab[dev];
+    return BPPP_OK;
+}
+
 static int tree_sum(cudaStream_t st, uint32_t *a, uint32_t *b, size_t count, uint32_t **result) {
     // repeatedly sums groups of 16 until one point remains; a holds the input, b is scratch of >= count/16 + 1 points
     uint32_t *in = a, *out = b;
@@ -277,33 +281,38 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     const uint32_t half = 1u << (c - 1);
     const uint32_t nb = (uint32_t)nwin * half;
     const size_t total = (size_t)nwin * n;
-    const size_t nseg = (total + MSM_SEG - 1) / MSM_SEG;
     uint32_t CH = 64; if (CH > half) CH = half;
     const uint32_t nchunks = (half + CH - 1) / CH;
-    uint32_t *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr, *buckets = nullptr, *partials = nullptr, *pkeys = nullptr;
-    uint32_t *chunks = nullptr, *tmp = nullptr;
-    void *cub_tmp = nullptr; size_t cub_bytes = 0;
-    CUDA_OK(cudaMalloc(&keys, 4 * total)); CUDA_OK(cudaMalloc(&vals, 4 * total));
-    CUDA_OK(cudaMalloc(&keys2, 4 * total)); CUDA_OK(cudaMalloc(&vals2, 4 * total));
-    CUDA_OK(cudaMalloc(&buckets, (size_t)120 * nb));
-    CUDA_OK(cudaMalloc(&partials, (size_t)120 * 2 * nseg)); CUDA_OK(cudaMalloc(&pkeys, 8 * nseg));
-    CUDA_OK(cudaMalloc(&chunks, (size_t)120 * nwin * nchunks)); CUDA_OK(cudaMalloc(&tmp, (size_t)120 * ((size_t)nwin * nchunks / 16 + 2)));
-    int end_bit = 1; while ((1ull << end_bit) < (unsigned long long)nb) end_bit++;
-    end_bit = 32;   // invalid keys are 0xFFFFFFFF and must sort last
-    CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys, keys2, vals, vals2, total, 0, end_bit, st));
-    CUDA_OK(cudaMalloc(&cub_tmp, cub_bytes));
+    const uint32_t heavy_cap = 4096;
+    size_t cub_bytes = 0;
+    CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, total, 0, 32, st));
+    // one cached slab per device, carved into the working arrays (cudaMalloc per call cost more than the kernels)
+    Carver cv;
+    size_t o_keys = cv.take(4 * total), o_vals = cv.take(4 * total), o_keys2 = cv.take(4 * total), o_vals2 = cv.take(4 * total);
+    size_t o_start = cv.take(4 * (size_t)nb), o_end = cv.take(4 * (size_t)nb), o_buckets = cv.take((size_t)120 * nb);
+    size_t o_heavy = cv.take(4 * (size_t)heavy_cap + 256), o_chunks = cv.take((size_t)120 * nwin * nchunks);
+    size_t o_tmp = cv.take((size_t)120 * ((size_t)nwin * nchunks / 16 + 2)), o_cub = cv.take(cub_bytes);
+    uint8_t *slab = nullptr;
+    int rc = scratch_reserve(cv.total, &slab);
+    if (rc != BPPP_OK) return rc;
+    uint32_t *keys = (uint32_t *)(slab + o_keys), *vals = (uint32_t *)(slab + o_vals), *keys2 = (uint32_t *)(slab + o_keys2), *vals2 = (uint32_t *)(slab + o_vals2);
+    uint32_t *start = (uint32_t *)(slab + o_start), *end = (uint32_t *)(slab + o_end), *buckets = (uint32_t *)(slab + o_buckets);
+    uint32_t *heavy_count = (uint32_t *)(slab + o_heavy), *heavy = heavy_count + 64, *chunks = (uint32_t *)(slab + o_chunks), *tmp = (uint32_t *)(slab + o_tmp);
+    void *cub_tmp = slab + o_cub;
+    CUDA_OK(cudaMemsetAsync(start, 0, 4 * (size_t)nb, st));          // empty buckets keep start == end == 0
+    CUDA_OK(cudaMemsetAsync(end, 0, 4 * (size_t)nb, st));
+    CUDA_OK(cudaMemsetAsync(heavy_count, 0, 4, st));
     GL(k_msm_digits, nblocks(n, 128), 128, d_sc, n, c, nwin, keys, vals);
-    CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys2, vals, vals2, total, 0, end_bit, st));
+    CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys2, vals, vals2, total, 0, 32, st));   // invalid keys are 0xFFFFFFFF: they sort last
     g_generic_launches += 4;
-    GL(k_pt_fill_identity, nblocks(nb, 128), 128, buckets, (size_t)nb);
-    GL(k_msm_segments, nblocks(nseg, 64), 64, d_pts, keys2, vals2, total, nb, buckets, partials, pkeys, nseg);
-    GL(k_msm_merge, nblocks(2 * nseg, 64), 64, partials, pkeys, 2 * nseg, nb, buckets);
+    GL(k_msm_bounds, nblocks(total, 256), 256, keys2, total, nb, start, end);
+    GL(k_msm_buckets, nblocks(nb, 64), 64, d_pts, vals2, start, end, nb, buckets, heavy, heavy_count, heavy_cap);
+    GL(k_msm_heavy, heavy_cap, 128, d_pts, vals2, start, end, heavy, heavy_count, heavy_cap, buckets);
     GL(k_msm_chunks, nblocks((size_t)nwin * nchunks, 64), 64, buckets, nwin, half, CH, nchunks, chunks);
     // per-window sum of chunk results: groups of 16 until nwin points remain
     uint32_t *in = chunks, *out = tmp;
     size_t per = nchunks;
     while (per > 1) {
-        // group within each window: windows are contiguous blocks of `per` entries; pad-free because per is a power of two or 1
         uint32_t group = per >= 16 ? 16u : (uint32_t)per;
         size_t nout = (size_t)nwin * (per / group);
         GL(k_pt_sum_groups, nblocks(nout, 64), 64, in, (size_t)nwin * per, group, out, nout);
@@ -311,8 +320,6 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     }
     GL(k_msm_horner, 1, 1, in, c, nwin, d_addend30, d_out30);
     CUDA_OK(cudaStreamSynchronize(st));
-    cudaFree(keys); cudaFree(vals); cudaFree(keys2); cudaFree(vals2); cudaFree(buckets); cudaFree(partials); cudaFree(pkeys);
-    cudaFree(chunks); cudaFree(tmp); cudaFree(cub_tmp);
     CUDA_OK(cudaGetLastError());
     return BPPP_OK;
 }
