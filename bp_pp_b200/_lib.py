@@ -15,7 +15,7 @@ EXPORTS = [
     "bppp_ctx_create", "bppp_ctx_destroy", "bppp_last_error", "bppp_ctx_info", "bppp_u64_commit_batch",
     "bppp_u64_verify_batch", "bppp_u64_verify_batch_dev", "bppp_u64_prove_batch", "bppp_u64_prove_batch_dev",
     "bppp_launch_count", "bppp_microbench", "bppp_ctx_profile_begin", "bppp_ctx_profile_end",
-    "bppp_msm", "bppp_points_upload", "bppp_scalars_upload", "bppp_device_free", "bppp_msm_uploaded", "bppp_points_sum", "bppp_points_generate",
+    "bppp_msm", "bppp_points_upload", "bppp_scalars_upload", "bppp_device_free", "bppp_msm_uploaded", "bppp_points_sum", "bppp_points_generate", "bppp_points_convert",
     "bppp_wnla_commit", "bppp_wnla_prove", "bppp_wnla_verify",
     "bppp_circuit_commit", "bppp_circuit_prove", "bppp_circuit_verify",
     "bppp_reciprocal_commit_value", "bppp_reciprocal_prove", "bppp_reciprocal_verify",

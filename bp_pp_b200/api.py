@@ -398,3 +398,22 @@ def points_generate(base64: bytes, step64: bytes, n: int, device: int = 0) -> by
     out = (C.c_uint8 * max(64 * n, 1))()
     check(lib().bppp_points_generate(C.c_int(device), _in(base64), _in(step64), C.c_size_t(n), out), "bppp_points_generate")
     return bytes(out)[:64 * n]
+
+
+def points_convert(points: bytes, in_fmt: int, out_fmt: int, device: int = 0) -> bytes:
+    """SEC1 compressed <-> 64-byte affine for an array of points (SerializableProof <-> Proof conversions)."""
+    n = len(points) // _psz(in_fmt)
+    out = (C.c_uint8 * max(_psz(out_fmt) * n, 1))()
+    check(lib().bppp_points_convert(C.c_int(device), _in(points), C.c_int(in_fmt), C.c_size_t(n), C.c_int(out_fmt), out), "bppp_points_convert")
+    return bytes(out)[:_psz(out_fmt) * n]
+
+
+def u64_proofs_to_affine(proofs: bytes, device: int = 0) -> bytes:
+    """525-byte compressed u64 records -> 928-byte records with 64-byte points (BPPP_FMT_AFFINE64)."""
+    n = len(proofs) // U64_PROOF_BYTES
+    import numpy as np
+    rec = np.frombuffer(proofs, dtype=np.uint8).reshape(n, U64_PROOF_BYTES)
+    pts = np.concatenate([rec[:, :396].reshape(n, 12, 33), rec[:, 492:525].reshape(n, 1, 33)], axis=1)
+    aff = np.frombuffer(points_convert(pts.tobytes(), FMT_COMPRESSED, FMT_AFFINE64, device), dtype=np.uint8).reshape(n, 13, 64)
+    out = np.concatenate([aff[:, :12].reshape(n, 768), rec[:, 396:492], aff[:, 12].reshape(n, 64)], axis=1)
+    return out.tobytes()

@@ -433,6 +433,30 @@ extern "C" int bppp_msm_uploaded(int device, const void *points_handle, const vo
     cudaFree(d_out);
     return rc;
 }
+// SEC1 compressed <-> 64-byte affine conversion of a point array: the device-side counterpart of the
+// SerializableProof <-> Proof conversions (src/wnla.rs:41-61, src/circuit.rs:48-76, src/range_proof/reciprocal.rs:43-59)
+__global__ void k_words_to_bytes(const uint32_t *words, int fmt, uint8_t *out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PtA a; bool ok = load_dev_point(a, words, i);
+    if (fmt == FMT_COMPRESSED) pta_compress(out + 33 * i, a, !ok); else pta_to_xy64(out + 64 * i, a, !ok);
+}
+extern "C" int bppp_points_convert(int device, const uint8_t *in, int in_fmt, size_t n, int out_fmt, uint8_t *out) {
+    if (n && (!in || !out)) return fail(BPPP_ERR_ARG, "null argument");
+    int rc = pick_device(device);
+    if (rc != BPPP_OK) return rc;
+    uint32_t *d_w = nullptr; uint8_t *d_out = nullptr;
+    rc = decode_points_to_device(nullptr, in, in_fmt, n, &d_w);
+    if (rc != BPPP_OK) return rc;
+    size_t osz = out_fmt == FMT_COMPRESSED ? 33 : 64;
+    CUDA_OK(cudaMalloc(&d_out, osz * (n ? n : 1)));
+    if (n) k_words_to_bytes<<<nblocks(n, 128), 128>>>(d_w, out_fmt, d_out, n);
+    CUDA_OK(cudaMemcpy(out, d_out, osz * n, cudaMemcpyDeviceToHost));
+    cudaFree(d_w); cudaFree(d_out);
+    CUDA_OK(cudaGetLastError());
+    return BPPP_OK;
+}
+
 // synthetic generators for large-n measurements: out[i] = base + i * step (affine 64-byte points), computed on the device
 __global__ void __launch_bounds__(64) k_points_generate(const uint32_t *two16, size_t n, uint8_t *out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -6,11 +6,24 @@ using namespace bppp;
 
 static int fail(int code, const std::string &msg) { return engine_fail(code, msg); }
 
-__global__ void __launch_bounds__(64) k_v_load(WS w, const uint8_t *commits, const uint8_t *proofs, int fmt) {
+// phase 0a: one thread per (proof, point); 16 point slots per proof so that a proof's threads share a half-warp.
+// flags[i]: bits 0..13 identity mask, bit 31 = a point failed to decode (merged with atomicOr)
+__global__ void __launch_bounds__(128) k_v_decode(WS w, const uint8_t *commits, const uint8_t *proofs, int fmt, uint32_t *flags) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = t >> 4; int k = (int)(t & 15);
+    if (i >= w.n || k >= VP_COUNT) return;
+    size_t csz = fmt == FMT_COMPRESSED ? 33 : 64, psz = fmt == FMT_COMPRESSED ? U64_PROOF_BYTES_COMPRESSED : U64_PROOF_BYTES_AFFINE;
+    uint32_t bit; bool bad;
+    u64v_decode_point_one(w, i, k, commits + csz * i, proofs + psz * i, fmt, &bit, &bad);
+    uint32_t f = bit | (bad ? 0x80000000u : 0u);
+    if (f) atomicOr(flags + i, f);
+}
+__global__ void __launch_bounds__(64) k_v_load_finish(WS w, const uint8_t *proofs, int fmt, const uint32_t *flags) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w.n) return;
-    size_t csz = fmt == FMT_COMPRESSED ? 33 : 64, psz = fmt == FMT_COMPRESSED ? U64_PROOF_BYTES_COMPRESSED : U64_PROOF_BYTES_AFFINE;
-    u64v_load_one(w, i, commits + csz * i, proofs + psz * i, fmt);
+    size_t psz = fmt == FMT_COMPRESSED ? U64_PROOF_BYTES_COMPRESSED : U64_PROOF_BYTES_AFFINE;
+    uint32_t f = flags[i];
+    u64v_load_finish_one(w, i, proofs + psz * i, fmt, f & 0x7FFFFFFFu, (f >> 31) != 0);
 }
 __global__ void __launch_bounds__(64) k_v_phase1(WS w, Merlin init) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -36,7 +49,11 @@ static int verify_part(bppp_ctx *c, cudaStream_t st, WS w, const uint8_t *d_comm
                        const Merlin &init, int32_t *d_status) {
     const size_t n = w.n;
     const unsigned g64 = nblocks(n, 64);
-    LAUNCH(c, k_v_load, g64, 64, w, d_commits, d_proofs, fmt);
+    // decode flags live in the workspace's IDMASK row until k_v_load_finish rewrites it
+    uint32_t *flags = w.p + (size_t)VL::IDMASK * w.n;
+    CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n, st));
+    LAUNCH(c, k_v_decode, nblocks(n * 16, 128), 128, w, d_commits, d_proofs, fmt, flags);
+    LAUNCH(c, k_v_load_finish, g64, 64, w, d_proofs, fmt, flags);
     launch_batch_inv(c, st, w, VL::VP + 20, VL::ZINV);
     LAUNCH(c, k_v_phase1, g64, 64, w, init);
     TermMap tm = identity_map();

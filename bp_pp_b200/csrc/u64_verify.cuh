@@ -49,30 +49,28 @@ BPPP_HD void set_status(const WS &w, size_t i, int32_t st) {
     if (cur >= 0) ws_st(w, i, VL::STATUS, (uint32_t)st);
 }
 
-// Phase 0: decode one proof + commitment into the workspace; V' = V + r (projective).
+// Phase 0a: decode ONE point of one proof (one thread per (proof, point): 14x the parallelism of a per-proof loop, and the
+// square roots of SEC1 decompression are the bulk of this phase).  STATUS / IDMASK must be pre-set by u64v_load_init.
 // Record order (reciprocal::SerializableProof, reciprocal.rs:37-41 / circuit.rs:37-46):
 //   c_l c_r c_o c_s | r[0..3] | x[0..3] | l[0..1] | n[0] | r
-BPPP_HD void u64v_load_one(const WS &w, size_t i, const uint8_t *commit, const uint8_t *proof, int fmt) {
+BPPP_HD void u64v_decode_point_one(const WS &w, size_t i, int k, const uint8_t *commit, const uint8_t *proof, int fmt, uint32_t *idmask_bit, bool *bad) {
     const int psz = fmt == FMT_COMPRESSED ? 33 : 64;
-    int32_t status = ST_TRUE;
-    uint32_t idmask = 0;
-    PtA vpt, rpt;
-    bool vid = false, rid = false;
-#pragma unroll 1
-    for (int k = 0; k < VP_COUNT; k++) {
-        const uint8_t *src;
-        if (k == VP_V) src = commit;
-        else if (k == VP_RR) src = proof + 12 * psz + 96;
-        else src = proof + (k - 1) * psz;       // slots 1..12 are the first 12 record points in order
-        PtA a;
-        int s = fmt == FMT_COMPRESSED ? pta_decompress(a, src) : pta_from_xy64(a, src);
-        if (s < 0) { status = ST_BAD_POINT; a.x = fe_zero(); a.y = fe_zero(); BPPP_SET_MAG(a.x, 1); BPPP_SET_MAG(a.y, 1); s = 1; }
-        if (s == 1) idmask |= 1u << k;
-        a.x = fe_normalize(a.x); a.y = fe_normalize(a.y);
-        ws_st_pta(w, i, VL::PT + 16 * k, a);
-        if (k == VP_V) { vpt = a; vid = s == 1; }
-        if (k == VP_RR) { rpt = a; rid = s == 1; }
-    }
+    const uint8_t *src;
+    if (k == VP_V) src = commit;
+    else if (k == VP_RR) src = proof + 12 * psz + 96;
+    else src = proof + (k - 1) * psz;       // slots 1..12 are the first 12 record points in order
+    PtA a;
+    int s = fmt == FMT_COMPRESSED ? pta_decompress(a, src) : pta_from_xy64(a, src);
+    *bad = s < 0;
+    if (s < 0) { a.x = fe_zero(); a.y = fe_zero(); BPPP_SET_MAG(a.x, 1); BPPP_SET_MAG(a.y, 1); s = 1; }
+    *idmask_bit = s == 1 ? (1u << k) : 0u;
+    a.x = fe_normalize(a.x); a.y = fe_normalize(a.y);
+    ws_st_pta(w, i, VL::PT + 16 * k, a);
+}
+// Phase 0b: scalars, V' = V + r (projective), status
+BPPP_HD void u64v_load_finish_one(const WS &w, size_t i, const uint8_t *proof, int fmt, uint32_t idmask, bool bad_point) {
+    const int psz = fmt == FMT_COMPRESSED ? 33 : 64;
+    int32_t status = bad_point ? (int32_t)ST_BAD_POINT : (int32_t)ST_TRUE;
     const uint8_t *sc_src = proof + 12 * psz;
 #pragma unroll 1
     for (int k = 0; k < 3; k++) {
@@ -80,10 +78,18 @@ BPPP_HD void u64v_load_one(const WS &w, size_t i, const uint8_t *commit, const u
         if (!sc_from_be32(s, sc_src + 32 * k)) { if (status >= 0) status = ST_BAD_SCALAR; s = sc_zero(); }
         ws_st_sc(w, i, VL::L + 8 * k, s);
     }
-    Pt vp = pt_add(pt_from_affine(vpt, vid), pt_from_affine(rpt, rid));   // reciprocal.rs:104
+    PtA vpt = ws_ld_pta(w, i, VL::PT + 16 * VP_V), rpt = ws_ld_pta(w, i, VL::PT + 16 * VP_RR);
+    Pt vp = pt_add(pt_from_affine(vpt, idmask & (1u << VP_V)), pt_from_affine(rpt, idmask & (1u << VP_RR)));   // reciprocal.rs:104
     ws_st_pt(w, i, VL::VP, vp);
     ws_st(w, i, VL::STATUS, (uint32_t)status);
     ws_st(w, i, VL::IDMASK, idmask);
+}
+// whole phase 0 for one proof (host emulation and small batches)
+BPPP_HD void u64v_load_one(const WS &w, size_t i, const uint8_t *commit, const uint8_t *proof, int fmt) {
+    uint32_t idmask = 0; bool bad = false;
+#pragma unroll 1
+    for (int k = 0; k < VP_COUNT; k++) { uint32_t bit; bool b; u64v_decode_point_one(w, i, k, commit, proof, fmt, &bit, &b); idmask |= bit; bad |= b; }
+    u64v_load_finish_one(w, i, proof, fmt, idmask, bad);
 }
 
 // to_affine of a stored projective point with its batch-inverted Z

@@ -107,6 +107,9 @@ int bppp_scalars_upload(int device, const uint8_t *scalars32, size_t n, void **h
 void bppp_device_free(int device, void *handle);
 int bppp_msm_uploaded(int device, const void *points_handle, const void *scalars_handle, size_t n, int out_fmt, uint8_t *out,
                       float *elapsed_ms);
+/* SEC1 compressed <-> 64-byte affine for an array of points: the SerializableProof <-> Proof conversions
+ * (src/wnla.rs:41-61, src/circuit.rs:48-76, src/range_proof/reciprocal.rs:43-59); fails if a point is not on the curve */
+int bppp_points_convert(int device, const uint8_t *in, int in_fmt, size_t n, int out_fmt, uint8_t *out);
 /* synthetic generator vectors for large-n measurements: out[i] = base + i * step, 64-byte affine, computed on the device */
 int bppp_points_generate(int device, const uint8_t *base64, const uint8_t *step64, size_t n, uint8_t *out64);
 /* sum of n points: combines the per-rank partial sums of an MSM split by point range across GPUs */
