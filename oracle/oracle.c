@@ -87,35 +87,78 @@ static void mul_wide(u64 t[8], const u256 *a, const u256 *b) {
 /* base field mod p (k256 FieldElement): always canonical here          */
 /* ------------------------------------------------------------------ */
 typedef u256 fe;
-static void fe_norm(fe *r, u64 carry) {
-    /* r + carry*2^256 -> canonical */
-    while (carry) {
-        u128 c = (u128)carry * PC;
-        carry = 0;
-        for (int i = 0; i < 4; i++) { c += r->v[i]; r->v[i] = (u64)c; c >>= 64; }
-        carry = (u64)c;
+/* Elements are kept weakly reduced (any representative below 2^256); fe_canon gives the canonical one.
+ * 2^256 = PC (mod p), so a carry/borrow out of the top limb is folded back as +/- PC. */
+static inline void fe_canon(fe *r) { if (u256_geq(r, &FP)) u256_sub(r, r, &FP); }
+static inline void fe_add_small(fe *r, u64 x) { /* r += x, folding carries */
+    while (x) {
+        u128 c = (u128)r->v[0] + x; r->v[0] = (u64)c; c >>= 64;
+        c += r->v[1]; r->v[1] = (u64)c; c >>= 64;
+        c += r->v[2]; r->v[2] = (u64)c; c >>= 64;
+        c += r->v[3]; r->v[3] = (u64)c; c >>= 64;
+        x = (u64)c * PC;
     }
-    if (u256_geq(r, &FP)) u256_sub(r, r, &FP);
 }
-static void fe_add(fe *r, const fe *a, const fe *b) { u64 c = u256_add(r, a, b); fe_norm(r, c); }
-static void fe_sub(fe *r, const fe *a, const fe *b) { if (u256_sub(r, a, b)) u256_add(r, r, &FP); }
-static void fe_neg(fe *r, const fe *a) { fe z = {{0, 0, 0, 0}}; fe_sub(r, &z, a); }
-static void fe_mul(fe *r, const fe *a, const fe *b) {
-    u64 t[8];
-    mul_wide(t, a, b);
-    /* fold high half: hi * (2^32 + 977) */
-    u128 c = 0; u64 lo[5];
-    for (int i = 0; i < 4; i++) { c += (u128)t[4 + i] * PC + t[i]; lo[i] = (u64)c; c >>= 64; }
-    lo[4] = (u64)c;
-    fe x = {{lo[0], lo[1], lo[2], lo[3]}};
-    *r = x;
-    fe_norm(r, lo[4]);
+static inline void fe_norm(fe *r, u64 carry) { if (carry) fe_add_small(r, carry * PC); fe_canon(r); }
+static inline u64 addc(u64 a, u64 b, u64 cin, u64 *cout) { u64 s = a + b; u64 c1 = s < a; u64 t = s + cin; *cout = c1 | (t < s); return t; }
+static inline u64 subb(u64 a, u64 b, u64 bin, u64 *bout) { u64 d = a - b; u64 b1 = a < b; u64 t = d - bin; *bout = b1 | (d < bin); return t; }
+static inline void fe_add(fe *r, const fe *a, const fe *b) {
+    u64 c, r0 = addc(a->v[0], b->v[0], 0, &c), r1 = addc(a->v[1], b->v[1], c, &c), r2 = addc(a->v[2], b->v[2], c, &c), r3 = addc(a->v[3], b->v[3], c, &c);
+    /* fold the carry: + PC; a second carry can only happen when the sum wrapped to < PC, so one more fold terminates */
+    u64 k = (0 - c) & PC;
+    r0 = addc(r0, k, 0, &c); r1 = addc(r1, 0, c, &c); r2 = addc(r2, 0, c, &c); r3 = addc(r3, 0, c, &c);
+    r0 += (0 - c) & PC;
+    r->v[0] = r0; r->v[1] = r1; r->v[2] = r2; r->v[3] = r3;
 }
-static void fe_sqr(fe *r, const fe *a) { fe_mul(r, a, a); }
-static void fe_mul_small(fe *r, const fe *a, u64 k) {
-    u128 c = 0;
-    for (int i = 0; i < 4; i++) { c += (u128)a->v[i] * k; r->v[i] = (u64)c; c >>= 64; }
-    fe_norm(r, (u64)c);
+static inline void fe_sub(fe *r, const fe *a, const fe *b) {
+    u64 bw, r0 = subb(a->v[0], b->v[0], 0, &bw), r1 = subb(a->v[1], b->v[1], bw, &bw), r2 = subb(a->v[2], b->v[2], bw, &bw), r3 = subb(a->v[3], b->v[3], bw, &bw);
+    /* a - b + 2^256 = a - b + PC (mod p): take PC off again; a second borrow means the value was < PC before, so once more */
+    u64 k = (0 - bw) & PC;
+    r0 = subb(r0, k, 0, &bw); r1 = subb(r1, 0, bw, &bw); r2 = subb(r2, 0, bw, &bw); r3 = subb(r3, 0, bw, &bw);
+    r0 -= (0 - bw) & PC;
+    r->v[0] = r0; r->v[1] = r1; r->v[2] = r2; r->v[3] = r3;
+}
+static inline void fe_neg(fe *r, const fe *a) { fe z = {{0, 0, 0, 0}}; fe_sub(r, &z, a); }
+static inline void fe_mul(fe *r, const fe *a, const fe *b) {
+    const u64 a0 = a->v[0], a1 = a->v[1], a2 = a->v[2], a3 = a->v[3];
+    u64 t[8]; u128 c;
+    c = (u128)a0 * b->v[0]; t[0] = (u64)c; c >>= 64;
+    c += (u128)a0 * b->v[1]; t[1] = (u64)c; c >>= 64;
+    c += (u128)a0 * b->v[2]; t[2] = (u64)c; c >>= 64;
+    c += (u128)a0 * b->v[3]; t[3] = (u64)c; t[4] = (u64)(c >> 64);
+    c = (u128)a1 * b->v[0] + t[1]; t[1] = (u64)c; c >>= 64;
+    c += (u128)a1 * b->v[1] + t[2]; t[2] = (u64)c; c >>= 64;
+    c += (u128)a1 * b->v[2] + t[3]; t[3] = (u64)c; c >>= 64;
+    c += (u128)a1 * b->v[3] + t[4]; t[4] = (u64)c; t[5] = (u64)(c >> 64);
+    c = (u128)a2 * b->v[0] + t[2]; t[2] = (u64)c; c >>= 64;
+    c += (u128)a2 * b->v[1] + t[3]; t[3] = (u64)c; c >>= 64;
+    c += (u128)a2 * b->v[2] + t[4]; t[4] = (u64)c; c >>= 64;
+    c += (u128)a2 * b->v[3] + t[5]; t[5] = (u64)c; t[6] = (u64)(c >> 64);
+    c = (u128)a3 * b->v[0] + t[3]; t[3] = (u64)c; c >>= 64;
+    c += (u128)a3 * b->v[1] + t[4]; t[4] = (u64)c; c >>= 64;
+    c += (u128)a3 * b->v[2] + t[5]; t[5] = (u64)c; c >>= 64;
+    c += (u128)a3 * b->v[3] + t[6]; t[6] = (u64)c; t[7] = (u64)(c >> 64);
+    /* fold the high half: hi * (2^32 + 977) + lo */
+    c = (u128)t[4] * PC + t[0]; r->v[0] = (u64)c; c >>= 64;
+    c += (u128)t[5] * PC + t[1]; r->v[1] = (u64)c; c >>= 64;
+    c += (u128)t[6] * PC + t[2]; r->v[2] = (u64)c; c >>= 64;
+    c += (u128)t[7] * PC + t[3]; r->v[3] = (u64)c; c >>= 64;
+    if (c) {                                   /* c < 2^34: c * PC < 2^67 spans two limbs */
+        u128 x = c * PC;
+        u128 d = (u128)r->v[0] + (u64)x; r->v[0] = (u64)d; d >>= 64;
+        d += (u128)r->v[1] + (u64)(x >> 64); r->v[1] = (u64)d; d >>= 64;
+        d += r->v[2]; r->v[2] = (u64)d; d >>= 64;
+        d += r->v[3]; r->v[3] = (u64)d; d >>= 64;
+        if (d) fe_add_small(r, PC);
+    }
+}
+static inline void fe_sqr(fe *r, const fe *a) { fe_mul(r, a, a); }
+static inline void fe_mul_small(fe *r, const fe *a, u64 k) {
+    u128 c = (u128)a->v[0] * k; r->v[0] = (u64)c; c >>= 64;
+    c += (u128)a->v[1] * k; r->v[1] = (u64)c; c >>= 64;
+    c += (u128)a->v[2] * k; r->v[2] = (u64)c; c >>= 64;
+    c += (u128)a->v[3] * k; r->v[3] = (u64)c; c >>= 64;
+    if (c) fe_add_small(r, (u64)c * PC);
 }
 static void fe_pow(fe *r, const fe *a, const u256 *e) {
     fe acc = {{1, 0, 0, 0}};
@@ -135,8 +178,10 @@ static int fe_sqrt(fe *r, const fe *a) {
     fe s, chk;
     fe_pow(&s, a, &e);
     fe_sqr(&chk, &s);
+    fe_canon(&s); fe_canon(&chk);
     *r = s;
-    return u256_eq(&chk, a);
+    fe ac = *a; fe_canon(&ac);
+    return u256_eq(&chk, &ac);
 }
 
 /* ------------------------------------------------------------------ */
@@ -180,10 +225,45 @@ static void sc_reduce_wide(sc *r, const u64 *t, int nlimbs) {
     while (u256_geq(&x, &FN)) u256_sub(&x, &x, &FN);
     *r = x;
 }
+static inline void mul_wide4(u64 t[8], const u256 *a, const u256 *b) {
+    const u64 a0 = a->v[0], a1 = a->v[1], a2 = a->v[2], a3 = a->v[3];
+    u128 c;
+    c = (u128)a0 * b->v[0]; t[0] = (u64)c; c >>= 64;
+    c += (u128)a0 * b->v[1]; t[1] = (u64)c; c >>= 64;
+    c += (u128)a0 * b->v[2]; t[2] = (u64)c; c >>= 64;
+    c += (u128)a0 * b->v[3]; t[3] = (u64)c; t[4] = (u64)(c >> 64);
+    c = (u128)a1 * b->v[0] + t[1]; t[1] = (u64)c; c >>= 64;
+    c += (u128)a1 * b->v[1] + t[2]; t[2] = (u64)c; c >>= 64;
+    c += (u128)a1 * b->v[2] + t[3]; t[3] = (u64)c; c >>= 64;
+    c += (u128)a1 * b->v[3] + t[4]; t[4] = (u64)c; t[5] = (u64)(c >> 64);
+    c = (u128)a2 * b->v[0] + t[2]; t[2] = (u64)c; c >>= 64;
+    c += (u128)a2 * b->v[1] + t[3]; t[3] = (u64)c; c >>= 64;
+    c += (u128)a2 * b->v[2] + t[4]; t[4] = (u64)c; c >>= 64;
+    c += (u128)a2 * b->v[3] + t[5]; t[5] = (u64)c; t[6] = (u64)(c >> 64);
+    c = (u128)a3 * b->v[0] + t[3]; t[3] = (u64)c; c >>= 64;
+    c += (u128)a3 * b->v[1] + t[4]; t[4] = (u64)c; c >>= 64;
+    c += (u128)a3 * b->v[2] + t[5]; t[5] = (u64)c; c >>= 64;
+    c += (u128)a3 * b->v[3] + t[6]; t[6] = (u64)c; t[7] = (u64)(c >> 64);
+}
+/* 512 -> 256 bits mod n with 2^256 = NC (mod n), NC = NC[0] + NC[1] 2^64 + 2^128 */
 static void sc_mul(sc *r, const sc *a, const sc *b) {
     u64 t[8];
-    mul_wide(t, a, b);
-    sc_reduce_wide(r, t, 8);
+    mul_wide4(t, a, b);
+    /* fold 1: lo + hi * NC -> 7 limbs */
+    u64 m[7]; u128 c;
+    c = (u128)t[4] * NC[0] + t[0]; m[0] = (u64)c; c >>= 64;
+    c += (u128)t[5] * NC[0] + t[1]; u64 x1 = (u64)c; c >>= 64;
+    c += (u128)t[6] * NC[0] + t[2]; u64 x2 = (u64)c; c >>= 64;
+    c += (u128)t[7] * NC[0] + t[3]; u64 x3 = (u64)c; u64 x4 = (u64)(c >> 64);
+    c = (u128)t[4] * NC[1] + x1; m[1] = (u64)c; c >>= 64;
+    c += (u128)t[5] * NC[1] + x2; x2 = (u64)c; c >>= 64;
+    c += (u128)t[6] * NC[1] + x3; x3 = (u64)c; c >>= 64;
+    c += (u128)t[7] * NC[1] + x4; x4 = (u64)c; u64 x5 = (u64)(c >> 64);
+    c = (u128)t[4] + x2; m[2] = (u64)c; c >>= 64;          /* + hi << 128 */
+    c += (u128)t[5] + x3; m[3] = (u64)c; c >>= 64;
+    c += (u128)t[6] + x4; m[4] = (u64)c; c >>= 64;
+    c += (u128)t[7] + x5; m[5] = (u64)c; m[6] = (u64)(c >> 64);
+    sc_reduce_wide(r, m, 7);
 }
 static void sc_from_u64(sc *r, u64 x) { r->v[0] = x; r->v[1] = r->v[2] = r->v[3] = 0; }
 static void sc_pow_u64(sc *r, const sc *a, u64 e) { /* util.rs:97-99 pow_vartime */
@@ -194,16 +274,25 @@ static void sc_pow_u64(sc *r, const sc *a, u64 e) { /* util.rs:97-99 pow_vartime
     }
     *r = acc;
 }
-/* Scalar::invert().unwrap(): returns 0 (-> panic) on zero */
+/* Scalar::invert().unwrap(): returns 0 (-> panic) on zero.  Binary extended Euclid mod n (variable time). */
+static inline void u256_shr1(u256 *a, u64 top) {
+    a->v[0] = (a->v[0] >> 1) | (a->v[1] << 63); a->v[1] = (a->v[1] >> 1) | (a->v[2] << 63);
+    a->v[2] = (a->v[2] >> 1) | (a->v[3] << 63); a->v[3] = (a->v[3] >> 1) | (top << 63);
+}
+static inline void sc_half(sc *x) { /* x / 2 mod n */
+    if (x->v[0] & 1) { u64 c = u256_add(x, x, &FN); u256_shr1(x, c); } else u256_shr1(x, 0);
+}
 static int sc_inv(sc *r, const sc *a) {
     if (u256_is_zero(a)) return 0;
-    u256 e = FN; e.v[0] -= 2;
-    sc acc = SC_ONE;
-    for (int i = 255; i >= 0; i--) {
-        sc_mul(&acc, &acc, &acc);
-        if ((e.v[i / 64] >> (i % 64)) & 1) sc_mul(&acc, &acc, a);
+    u256 u = *a, v = FN; sc x1 = SC_ONE, x2 = SC_ZERO;
+    const u256 one = {{1, 0, 0, 0}};
+    while (!u256_eq(&u, &one) && !u256_eq(&v, &one)) {
+        while (!(u.v[0] & 1)) { u256_shr1(&u, 0); sc_half(&x1); }
+        while (!(v.v[0] & 1)) { u256_shr1(&v, 0); sc_half(&x2); }
+        if (u256_geq(&u, &v)) { u256_sub(&u, &u, &v); sc_sub(&x1, &x1, &x2); }
+        else { u256_sub(&v, &v, &u); sc_sub(&x2, &x2, &x1); }
     }
-    *r = acc;
+    *r = u256_eq(&u, &one) ? x1 : x2;
     return 1;
 }
 /* Scalar::generate_biased: 64 bytes big-endian mod n [recalled] */
@@ -255,27 +344,55 @@ static void pt_double(pt *r, const pt *p) {
 }
 static void pt_neg(pt *r, const pt *p) { r->x = p->x; fe_neg(&r->y, &p->y); r->z = p->z; }
 static void pt_sub(pt *r, const pt *p, const pt *q) { pt nq; pt_neg(&nq, q); pt_add(r, p, &nq); }
-static int pt_is_identity(const pt *p) { return u256_is_zero(&p->z); }
+static int pt_is_identity(const pt *p) { fe z = p->z; fe_canon(&z); return u256_is_zero(&z); }
 /* ProjectivePoint::eq */
 static int pt_eq(const pt *p, const pt *q) {
     fe a, b, c, d;
     fe_mul(&a, &p->x, &q->z); fe_mul(&b, &q->x, &p->z);
     fe_mul(&c, &p->y, &q->z); fe_mul(&d, &q->y, &p->z);
+    fe_canon(&a); fe_canon(&b); fe_canon(&c); fe_canon(&d);
     return u256_eq(&a, &b) && u256_eq(&c, &d);
 }
-/* ProjectivePoint * Scalar: fixed 4-bit windows (one full multiplication per call, as the
- * reference does; no sharing between terms of an MSM) */
+/* ProjectivePoint * Scalar: one full multiplication per call, as the reference does (no sharing between the terms of an
+ * MSM).  Like k256 it uses the GLV endomorphism lambda (x, y) = (beta x, y): k = k1 + k2 lambda with |k1|, |k2| < 2^128,
+ * signed 4-bit windows over the two halves, 128 doublings. */
+static const sc GLV_G1 = {{0xE893209A45DBB031ULL, 0x3DAA8A1471E8CA7FULL, 0xE86C90E49284EB15ULL, 0x3086D221A7D46BCDULL}};
+static const sc GLV_G2 = {{0x1571B4AE8AC47F71ULL, 0x221208AC9DF506C6ULL, 0x6F547FA90ABFE4C4ULL, 0xE4437ED6010E8828ULL}};
+static const sc GLV_MB1 = {{0x6F547FA90ABFE4C3ULL, 0xE4437ED6010E8828ULL, 0, 0}};
+static const sc GLV_MB2 = {{0xD765CDA83DB1562CULL, 0x8A280AC50774346DULL, 0xFFFFFFFFFFFFFFFEULL, 0xFFFFFFFFFFFFFFFFULL}};
+static const sc GLV_LAMBDA = {{0xDF02967C1B23BD72ULL, 0x122E22EA20816678ULL, 0xA5261C028812645AULL, 0x5363AD4CC05C30E0ULL}};
+static const fe GLV_BETA = {{0xC1396C28719501EEULL, 0x9CF0497512F58995ULL, 0x6E64479EAC3434E9ULL, 0x7AE96A2B657C0710ULL}};
+static void mul_shift384(sc *r, const sc *k, const sc *g) {
+    u64 t[8];
+    mul_wide4(t, k, g);
+    u128 c = (u128)t[6] + (t[5] >> 63);
+    r->v[0] = (u64)c; c >>= 64; c += t[7]; r->v[1] = (u64)c; r->v[2] = (u64)(c >> 64); r->v[3] = 0;
+}
 static void pt_mul(pt *r, const pt *p, const sc *k) {
-    pt tab[16];
-    tab[0] = PT_IDENTITY; tab[1] = *p;
-    for (int i = 2; i < 16; i++) {
-        if (i & 1) pt_add(&tab[i], &tab[i - 1], p); else pt_double(&tab[i], &tab[i / 2]);
-    }
-    pt acc = PT_IDENTITY;
-    for (int w = 63; w >= 0; w--) {
-        if (w != 63) { pt_double(&acc, &acc); pt_double(&acc, &acc); pt_double(&acc, &acc); pt_double(&acc, &acc); }
-        unsigned d = (unsigned)(k->v[w / 16] >> (4 * (w % 16))) & 15;
-        pt_add(&acc, &acc, &tab[d]);
+    sc c1, c2, k1, k2, t;
+    mul_shift384(&c1, k, &GLV_G1); mul_shift384(&c2, k, &GLV_G2);
+    sc_mul(&c1, &c1, &GLV_MB1); sc_mul(&c2, &c2, &GLV_MB2); sc_add(&k2, &c1, &c2);
+    sc_mul(&t, &k2, &GLV_LAMBDA); sc_sub(&k1, k, &t);
+    int neg1 = (k1.v[2] | k1.v[3]) != 0, neg2 = (k2.v[2] | k2.v[3]) != 0;
+    if (neg1) sc_neg(&k1, &k1);
+    if (neg2) sc_neg(&k2, &k2);
+    pt tab[8], ltab[8];   /* 1P .. 8P and lambda * them */
+    tab[0] = *p; pt_double(&tab[1], p); pt_add(&tab[2], &tab[1], p); pt_double(&tab[3], &tab[1]);
+    pt_add(&tab[4], &tab[3], p); pt_double(&tab[5], &tab[2]); pt_add(&tab[6], &tab[5], p); pt_double(&tab[7], &tab[3]);
+    for (int i = 0; i < 8; i++) { ltab[i] = tab[i]; fe_mul(&ltab[i].x, &ltab[i].x, &GLV_BETA); }
+    /* signed digits: (k + 0x88..8) nibbles minus 8, plus an unsigned 33rd digit */
+    u64 d1[3], d2[3]; u128 c;
+    c = (u128)k1.v[0] + 0x8888888888888888ULL; d1[0] = (u64)c; c >>= 64; c += (u128)k1.v[1] + 0x8888888888888888ULL; d1[1] = (u64)c; d1[2] = (u64)(c >> 64);
+    c = (u128)k2.v[0] + 0x8888888888888888ULL; d2[0] = (u64)c; c >>= 64; c += (u128)k2.v[1] + 0x8888888888888888ULL; d2[1] = (u64)c; d2[2] = (u64)(c >> 64);
+    pt acc = PT_IDENTITY, e;
+    for (int w = 32; w >= 0; w--) {
+        if (w != 32) { pt_double(&acc, &acc); pt_double(&acc, &acc); pt_double(&acc, &acc); pt_double(&acc, &acc); }
+        int a = (int)((d1[w / 16] >> (4 * (w % 16))) & 15), b = (int)((d2[w / 16] >> (4 * (w % 16))) & 15);
+        if (w < 32) { a -= 8; b -= 8; }
+        if (neg1) a = -a;
+        if (neg2) b = -b;
+        if (a) { e = tab[(a < 0 ? -a : a) - 1]; if (a < 0) fe_neg(&e.y, &e.y); pt_add(&acc, &acc, &e); }
+        if (b) { e = ltab[(b < 0 ? -b : b) - 1]; if (b < 0) fe_neg(&e.y, &e.y); pt_add(&acc, &acc, &e); }
     }
     *r = acc;
 }
@@ -284,6 +401,7 @@ static void pt_to_bytes(u8 out[33], const pt *p) {
     if (pt_is_identity(p)) { memset(out, 0, 33); return; }
     fe zi, x, y;
     fe_inv(&zi, &p->z); fe_mul(&x, &p->x, &zi); fe_mul(&y, &p->y, &zi);
+    fe_canon(&x); fe_canon(&y);
     out[0] = 2 + (u8)(y.v[0] & 1);
     u256_to_be(out + 1, &x);
 }
@@ -298,6 +416,7 @@ static int pt_from_bytes(pt *r, const u8 in[33]) {
     if (u256_geq(&x, &FP)) return 0;
     fe_sqr(&y2, &x); fe_mul(&y2, &y2, &x); fe_add(&y2, &y2, &seven);
     if (!fe_sqrt(&y, &y2)) return 0;
+    fe_canon(&y);
     if ((y.v[0] & 1) != (u64)(in[0] & 1)) fe_neg(&y, &y);
     r->x = x; r->y = y; r->z = SC_ONE;
     return 1;
@@ -311,6 +430,7 @@ static int pt_from_xy(pt *r, const u8 in[64]) {
     u256_from_be(&x, in); u256_from_be(&y, in + 32);
     if (u256_geq(&x, &FP) || u256_geq(&y, &FP)) return 0;
     fe_sqr(&l, &y); fe_sqr(&rr, &x); fe_mul(&rr, &rr, &x); fe_add(&rr, &rr, &seven);
+    fe_canon(&l); fe_canon(&rr);
     if (!u256_eq(&l, &rr)) return 0;
     r->x = x; r->y = y; r->z = SC_ONE;
     return 1;
@@ -319,6 +439,7 @@ static void pt_to_xy(u8 out[64], const pt *p) {
     if (pt_is_identity(p)) { memset(out, 0, 64); return; }
     fe zi, x, y;
     fe_inv(&zi, &p->z); fe_mul(&x, &p->x, &zi); fe_mul(&y, &p->y, &zi);
+    fe_canon(&x); fe_canon(&y);
     u256_to_be(out, &x); u256_to_be(out + 32, &y);
 }
 
@@ -1367,8 +1488,8 @@ int oracle_point_add(const u8 *p64, const u8 *q64, u8 *out64) {
 }
 int oracle_point_decompress(const u8 *in33, u8 *out64) { pt p; if (!pt_from_bytes(&p, in33)) return ORACLE_BAD_POINT; pt_to_xy(out64, &p); return ORACLE_OK; }
 int oracle_point_compress(const u8 *in64, u8 *out33) { pt p; if (!pt_from_xy(&p, in64)) return ORACLE_BAD_POINT; pt_to_bytes(out33, &p); return ORACLE_OK; }
-void oracle_fe_mul(const u8 *a32, const u8 *b32, u8 *out32) { fe a, b, r; u256_from_be(&a, a32); u256_from_be(&b, b32); fe_norm(&a, 0); fe_norm(&b, 0); fe_mul(&r, &a, &b); u256_to_be(out32, &r); }
-void oracle_fe_inv(const u8 *a32, u8 *out32) { fe a, r; u256_from_be(&a, a32); fe_norm(&a, 0); fe_inv(&r, &a); u256_to_be(out32, &r); }
+void oracle_fe_mul(const u8 *a32, const u8 *b32, u8 *out32) { fe a, b, r; u256_from_be(&a, a32); u256_from_be(&b, b32); fe_norm(&a, 0); fe_norm(&b, 0); fe_mul(&r, &a, &b); fe_canon(&r); u256_to_be(out32, &r); }
+void oracle_fe_inv(const u8 *a32, u8 *out32) { fe a, r; u256_from_be(&a, a32); fe_norm(&a, 0); fe_inv(&r, &a); fe_canon(&r); u256_to_be(out32, &r); }
 void oracle_sc_mul(const u8 *a32, const u8 *b32, u8 *out32) { sc a, b, r; u64 t[4]; u256_from_be(&a, a32); u256_from_be(&b, b32); memcpy(t, a.v, 32); sc_reduce_wide(&a, t, 4); memcpy(t, b.v, 32); sc_reduce_wide(&b, t, 4); sc_mul(&r, &a, &b); u256_to_be(out32, &r); }
 int oracle_sc_inv(const u8 *a32, u8 *out32) { sc a, r; if (!sc_from_repr(&a, a32)) return ORACLE_BAD_SCALAR; if (!sc_inv(&r, &a)) return ORACLE_PANIC_INVERT_ZERO; u256_to_be(out32, &r); return ORACLE_OK; }
 void oracle_sc_from_wide(const u8 *in64, u8 *out32) { sc r; sc_from_wide_be(&r, in64); u256_to_be(out32, &r); }
