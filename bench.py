@@ -263,6 +263,22 @@ def run_ours(args):
                 "frac": round(tbl_bytes / (msm_ms * 1e-3) / 1e9 / hbm_peak, 4) if msm_ms else None,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s", "note": "window-table lookups of k_msm_fixed; not the binding roof"},
     }
+    # ---- MSM points/s (BASELINE metric, config 5 shape): variable-base Pippenger, operands resident in HBM, device time ----
+    msm_res = None
+    if world == 1:
+        base64, step64 = xy(R.pt_mul(R.G, 11)), xy(R.pt_mul(R.G, 29))
+        mrnd = np.random.default_rng(5)
+        msm_res = {}
+        for logn in (20, 21):
+            mn = 1 << logn
+            mpts = B.points_generate(base64, step64, mn, local_rank)
+            msc = np.frombuffer(mrnd.bytes(32 * mn), dtype=np.uint8).reshape(mn, 32).copy()
+            msc[:, 0] &= 0x7F
+            up = B.UploadedMsm(mpts, msc.tobytes(), device=local_rank)
+            up.run()
+            best = min(up.run()[1] for _ in range(3))
+            up.close()
+            msm_res[f"2^{logn}"] = {"ms": round(best, 3), "points_per_s": round(mn / best * 1e3)}
     # ---- CPU baseline: the oracle (reference algorithm) on the host cores, bounded sample; also a parity check ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -296,6 +312,7 @@ def run_ours(args):
         "prove": {"value": round(world * n * p_steps / (p_ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(p_ms / p_steps, 3), "steps": p_steps,
                   "e2e": {"value": round(world * n * p_steps / e_p, 1), "unit": UNIT, "h2d_bytes_per_step": n * (8 + 32 + 3328), "d2h_bytes_per_step": n * 529},
                   "gpu_launches": p_launches, "all_proved": prove_ok, "workload": "prove_batch: 65,536 witnesses per GPU (BASELINE config 3)"},
+        "msm": msm_res,
         "verify_affine64_input": {"value": round(world * n * max(1, args.steps // 2) / (va_ms * 1e-3), 1), "unit": UNIT, "verdicts_ok": va_ok,
                                   "note": "same step with 928-byte records (64-byte affine points): SEC1 square roots skipped"},
         "kernels_verify_ms": {k: [round(ms, 3), c] for k, (ms, c) in sorted(prof_v.items(), key=lambda kv: -kv[1][0])},

@@ -60,3 +60,44 @@ def test_sharded_verify_two_ranks_gloo(ref, oracle, gens64):
     for p in procs:
         p.join(60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _msm_worker(rank, world, port, pts, sc, expect, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch.distributed as dist
+    import oracle_c
+    import bp_pp_b200.api as api
+    from bp_pp_b200.shard import msm_sharded
+    # no GPU in CI: stand the oracle in for the two device calls; the split / all_gather / combine logic is what is under test
+    api.msm = lambda P, S, points_fmt=1, out_fmt=0, device=0: oracle_c.msm(P, S)
+    api.points_sum = lambda P, points_fmt=0, out_fmt=0, device=0: oracle_c.msm(b"".join(oracle_c.point_decompress(P[33 * i:33 * i + 33]) for i in range(len(P) // 33)),
+                                                                               (1).to_bytes(32, "big") * (len(P) // 33))
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    res = msm_sharded(pts, sc, 0)
+    dist.barrier(); dist.destroy_process_group()
+    q.put((rank, res == expect))
+
+
+def test_msm_split_by_point_range_two_ranks_gloo(ref, oracle):
+    import random
+    import torch.multiprocessing as mp
+    from conftest import xy
+    rnd = random.Random(3)
+    n = 9   # ragged: 5 + 4
+    p, qq = xy(ref.pt_mul(ref.G, 5)), xy(ref.pt_mul(ref.G, 9))
+    pts = []
+    for _ in range(n):
+        pts.append(p); p = oracle.point_add(p, qq)
+    pts = b"".join(pts)
+    sc = b"".join(rnd.randrange(ref.N).to_bytes(32, "big") for _ in range(n))
+    expect = oracle.msm(pts, sc)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_msm_worker, args=(r, 2, port, pts, sc, expect, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for pr in procs:
+        pr.join(60)
+    assert sorted(res) == [(0, True), (1, True)]
