@@ -168,6 +168,62 @@ BPPP_HD void pta_to_xy64(uint8_t out[64], const PtA &a_canonical, bool is_identi
     }
 }
 
+// ---- XYZZ ("extended Jacobian") accumulator for sums of AFFINE points: x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2 ----
+// Mixed addition costs 8 M + 2 S (madd-2008-s) against 11 M for the complete projective formula, which is what the
+// fixed-base and Pippenger accumulation loops are made of.  The formula is incomplete, so the exceptional inputs are
+// handled explicitly and exactly (scalars chosen by an adversarial prover can steer an accumulator onto them):
+// identity accumulator (flag), P1 == Q (affine doubling), P1 == -Q (identity).
+struct PtX {
+    Fe x, y, zz, zzz;
+    bool inf;
+};
+BPPP_HD PtX ptx_identity() { PtX r; r.x = fe_zero(); r.y = fe_zero(); r.zz = fe_zero(); r.zzz = fe_zero(); r.inf = true;
+    BPPP_SET_MAG(r.x, 1); BPPP_SET_MAG(r.y, 1); BPPP_SET_MAG(r.zz, 1); BPPP_SET_MAG(r.zzz, 1); return r; }
+// 2Q for affine Q (mdbl-2008-s-1)
+BPPP_HD PtX ptx_double_affine(const PtA &q) {
+    PtX r;
+    Fe U = fe_mul_int(q.y, 2);                       // 2y            mag 2
+    Fe V = fe_sqr(U);                                // 4y^2
+    Fe W = fe_mul(U, V);                             // 8y^3
+    Fe S = fe_mul(q.x, V);
+    Fe M = fe_mul_int(fe_sqr(q.x), 3);               // 3x^2          mag 3
+    r.x = fe_normalize_weak(fe_sub(fe_sqr(M), fe_mul_int(S, 2), 2));
+    r.y = fe_normalize_weak(fe_sub(fe_mul(M, fe_sub(S, r.x, 1)), fe_mul(W, q.y), 1));
+    r.zz = V; r.zzz = W;
+    r.inf = fe_normalizes_to_zero(q.y);              // cannot happen on an odd-order curve; kept for exactness
+    return r;
+}
+// P + Q, Q affine and not the identity
+BPPP_HD PtX ptx_add_mixed(const PtX &p, const PtA &q) {
+    PtX r;
+    if (p.inf) { r.x = q.x; r.y = q.y; r.zz = fe_one(); r.zzz = fe_one(); r.inf = false; return r; }
+    Fe U2 = fe_mul(q.x, p.zz);
+    Fe S2 = fe_mul(q.y, p.zzz);
+    Fe P = fe_sub(U2, p.x, 1);                       // mag 3
+    Fe R = fe_sub(S2, p.y, 1);                       // mag 3
+    if (fe_normalizes_to_zero(P)) {                  // same x: P1 = +-Q
+        if (fe_normalizes_to_zero(R)) return ptx_double_affine(q);
+        return ptx_identity();
+    }
+    Fe PP = fe_sqr(P);
+    Fe PPP = fe_mul(P, PP);
+    Fe Q = fe_mul(p.x, PP);
+    Fe RR = fe_sqr(R);
+    r.x = fe_normalize_weak(fe_sub(RR, fe_add(PPP, fe_mul_int(Q, 2)), 3));
+    r.y = fe_normalize_weak(fe_sub(fe_mul(R, fe_sub(Q, r.x, 1)), fe_mul(p.y, PPP), 1));
+    r.zz = fe_mul(p.zz, PP);
+    r.zzz = fe_mul(p.zzz, PPP);
+    r.inf = false;
+    return r;
+}
+// to homogeneous projective: (X ZZZ : Y ZZ : ZZ ZZZ)
+BPPP_HD Pt ptx_to_pt(const PtX &p) {
+    Pt r;
+    r.x = fe_mul(p.x, p.zzz); r.y = fe_mul(p.y, p.zz); r.z = fe_mul(p.zz, p.zzz);
+    if (p.inf) r = pt_identity();
+    return r;
+}
+
 // ---- variable-base scalar multiplication, signed 4-bit fixed windows ----
 // k + C with C = sum_{i<64} 8*16^i gives unsigned nibbles d'_i; the signed digit is d'_i - 8 in [-8, 7]
 // for i < 64, plus an unsigned top digit d'_64 in {0, 1}.  No data-dependent recoding.

@@ -112,17 +112,17 @@ __global__ void k_msm_bounds(const uint32_t *keys, size_t total, uint32_t nb, ui
     if (p + 1 == total || keys[p + 1] != k) end[k] = (uint32_t)(p + 1);
 }
 __device__ __forceinline__ Pt msm_accumulate_range(const uint32_t *pts, const uint32_t *vals, uint32_t p0, uint32_t p1, uint32_t stride) {
-    Pt acc = pt_identity();
+    PtX acc = ptx_identity();             // XYZZ accumulator: 8 M + 2 S per point, exceptional cases handled exactly
 #pragma unroll 1
     for (uint32_t p = p0; p < p1; p += stride) {
         uint32_t v = vals[p];
         PtA q;
         if (load_dev_point(q, pts, v & 0x7FFFFFFFu)) {
             if (v >> 31) q.y = fe_normalize_weak(fe_negate(q.y, 1));
-            acc = pt_add_mixed(acc, q);
+            acc = ptx_add_mixed(acc, q);
         }
     }
-    return acc;
+    return ptx_to_pt(acc);
 }
 // bucket sums are stored AoS, 30 words per point
 __global__ void __launch_bounds__(64, 7) k_msm_buckets(const uint32_t *pts, const uint32_t *vals, const uint32_t *start, const uint32_t *end, uint32_t nb,

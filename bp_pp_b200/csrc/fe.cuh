@@ -171,6 +171,16 @@ BPPP_HD bool fe_is_zero_canonical(const Fe &a) {
     return m == 0;
 }
 BPPP_HD bool fe_is_zero(const Fe &a) { return fe_is_zero_canonical(fe_normalize(a)); }
+// value == 0 (mod p) for a lazily reduced element, without the full normalisation: after one weak pass the value is
+// below 2^256 + 2^235, so it is a multiple of p only if it is exactly 0 or exactly p
+BPPP_HD bool fe_normalizes_to_zero(const Fe &a) {
+    Fe t = fe_normalize_weak(a);
+    uint32_t z = t.n[0] | t.n[1] | t.n[9];
+    uint32_t pm = (t.n[0] ^ 0x3FFFC2Fu) | (t.n[1] ^ 0x3FFFFBFu) | (t.n[9] ^ FE_M22);
+#pragma unroll
+    for (int i = 2; i < 9; i++) { z |= t.n[i]; pm |= t.n[i] ^ FE_M26; }
+    return z == 0 || pm == 0;
+}
 BPPP_HD bool fe_equal_canonical(const Fe &a, const Fe &b) {
     uint32_t m = 0;
 #pragma unroll

@@ -124,7 +124,7 @@ BPPP_HD bool table_decode(PtA &q, const TableEntryRaw &r) {
 // scalars: T consecutive Sc in the workspace starting at word sc_off; term_gen[t] = generator index.
 // The table entry of the next item is fetched (64 B from HBM) before the current mixed addition is computed.
 BPPP_HD Pt msm_fixed_lane(const FixedTable &T, const WS &w, size_t i, int sc_off, const int *term_gen, int nterms, int lane, int nlanes) {
-    Pt acc = pt_identity();
+    PtX acc = ptx_identity();             // XYZZ accumulator: 8 M + 2 S per table point (ec.cuh)
     const int items = nterms * T.nwin;
     TableEntryRaw cur, nxt;
     uint32_t dcur = 0, dnxt = 0;
@@ -145,11 +145,11 @@ BPPP_HD Pt msm_fixed_lane(const FixedTable &T, const WS &w, size_t i, int sc_off
         }
         if (dcur != 0) {
             PtA q;
-            if (table_decode(q, cur)) acc = pt_add_mixed(acc, q);
+            if (table_decode(q, cur)) acc = ptx_add_mixed(acc, q);
         }
         cur = nxt; dcur = dnxt;
     }
-    return acc;
+    return ptx_to_pt(acc);
 }
 
 }  // namespace bppp

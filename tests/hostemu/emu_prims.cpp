@@ -51,6 +51,12 @@ int emu_pt_add_mixed_proj(const uint8_t *p, const uint8_t *q, uint8_t *r) {
     Pt a3 = pt_add(pt_double(a), a);       // 3P projective
     store_pt(r, pt_add_mixed(a3, b)); return 0;
 }
+// sum of n affine points (64 B each, none the identity) through the XYZZ accumulator
+int emu_ptx_sum(const uint8_t *pts, int n, uint8_t *r) {
+    PtX acc = ptx_identity();
+    for (int i = 0; i < n; i++) { PtA a; int s = pta_from_xy64(a, pts + 64 * i); if (s != 0) return -1; acc = ptx_add_mixed(acc, a); }
+    store_pt(r, ptx_to_pt(acc)); return 0;
+}
 int emu_pt_double(const uint8_t *p, uint8_t *r) { int s; Pt a = load_pt(p, &s); if (s < 0) return -1; store_pt(r, pt_double(a)); return 0; }
 int emu_pt_mul(const uint8_t *p, const uint8_t *k, uint8_t *r) { int s; Pt a = load_pt(p, &s); Sc kk; if (s < 0 || !sc_from_be32(kk, k)) return -1; store_pt(r, pt_mul(a, kk)); return 0; }
 int emu_pt_mul_glv(const uint8_t *p, const uint8_t *k, uint8_t *r) { int s; Pt a = load_pt(p, &s); Sc kk; if (s < 0 || !sc_from_be32(kk, k)) return -1; store_pt(r, pt_mul_glv(a, kk)); return 0; }

@@ -79,6 +79,23 @@ def test_group_law_complete_formulas(emu_prims, ref):
             assert L.emu_pt_equal(B(xy(p)), B(xy(ref.pt_add(ref.pt_mul(p, k), ref.G))), B(be(k))) == 0
 
 
+def test_xyzz_accumulator_including_exceptional_cases(emu_prims, ref):
+    L = emu_prims
+    rnd = random.Random(21)
+    unxy = lambda b: None if b == b"\0" * 64 else (int.from_bytes(b[:32], "big"), int.from_bytes(b[32:], "big"))  # noqa: E731
+    pts = [ref.pt_mul(ref.G, rnd.randrange(1, ref.N)) for _ in range(8)]
+    p, q = pts[0], pts[1]
+    seqs = [pts, [p], [p, p], [p, p, p], [p, ref.pt_neg(p)], [p, ref.pt_neg(p), q], [p, q, ref.pt_neg(ref.pt_add(p, q))],
+            [p, q, ref.pt_add(p, q)], [p, p, ref.pt_neg(p), ref.pt_neg(p), q], pts + [ref.pt_neg(x) for x in pts]]
+    for seq in seqs:
+        exp = None
+        for x in seq:
+            exp = ref.pt_add(exp, x)
+        o = O(64)
+        assert L.emu_ptx_sum(B(b"".join(xy(x) for x in seq)), len(seq), o) == 0
+        assert unxy(bytes(o)) == exp
+
+
 def test_glv_split_and_multiplication(emu_prims, ref):
     L, N = emu_prims, ref.N
     lam = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
