@@ -254,9 +254,21 @@ def run_ours(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     msm_ms = sum(ms for k, (ms, _) in prof_v.items() if k.startswith("k_msm_fixed"))
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of the same kernel and batch
+    traffic, traffic_src = None, None
+    cap = os.path.join(ROOT, "profiles", f"r1_ncu_full_final_{name.split('<')[0]}.txt")
+    if os.path.exists(cap):
+        tot = 0.0
+        for ln in open(cap):
+            for key in ("dram__bytes_read.sum [", "dram__bytes_write.sum ["):
+                if ln.startswith(key):
+                    unit = ln.split("[")[1].split("]")[0]
+                    tot += float(ln.split("=")[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0)
+        traffic, traffic_src = tot, os.path.relpath(cap, ROOT)
     roofline = {
         "bound": "integer", "kernel": name, "achieved": round(achieved, 1), "peak": round(peak, 1), "unit": "GMAC/s (32x32->64 IMAD.WIDE)",
-        "frac": round(achieved / peak, 4) if peak else None, "traffic": None,
+        "frac": round(achieved / peak, 4) if peak else None, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
+        "traffic_source": traffic_src, "traffic_note": "per-thread ladder tables (1P..8P) and register spills live in local memory; the kernel is integer-bound, DRAM < 0.4 TB/s",
         "kernel_share_of_step": round(dom_ms / tot_v, 4), "kernel_ms": round(dom_ms, 3), "kernel_launches": dom_cnt,
         "peak_source": "bppp_microbench IMAD.WIDE.U32 issue rate measured live on this GPU",
         "hbm": {"achieved": round(tbl_bytes / (msm_ms * 1e-3) / 1e9, 1) if msm_ms else None, "peak": hbm_peak, "unit": "GB/s",
