@@ -224,6 +224,64 @@ BPPP_HD Pt ptx_to_pt(const PtX &p) {
     return r;
 }
 
+// ---- Jacobian accumulator (x = X/Z^2, y = Y/Z^3) for ladders over AFFINE per-proof tables ----
+// doubling 2 M + 5 S (a = 0), mixed addition 8 M + 3 S, against 6 M + 2 S (+ two x21) and 12 M for the complete
+// projective formulas.  Incomplete formulas: the identity (flag), P1 == Q (affine doubling) and P1 == -Q are handled
+// explicitly and exactly -- tampered proofs do reach them (e.g. X_j == R_j).
+struct PtJ {
+    Fe x, y, z;
+    bool inf;
+};
+BPPP_HD PtJ ptj_identity() { PtJ r; r.x = fe_zero(); r.y = fe_zero(); r.z = fe_zero(); r.inf = true;
+    BPPP_SET_MAG(r.x, 1); BPPP_SET_MAG(r.y, 1); BPPP_SET_MAG(r.z, 1); return r; }
+BPPP_HD PtJ ptj_from_affine(const PtA &a) { PtJ r; r.x = a.x; r.y = a.y; r.z = fe_one(); r.inf = false; return r; }
+// 2P (dbl-2009-l).  Coordinates in: x, y weak-normalised, z limbs <= 4 * 2^26.  The curve has odd order, so Y != 0 unless P = O.
+BPPP_HD PtJ ptj_double(const PtJ &p) {
+    PtJ r;
+    Fe A = fe_sqr(p.x), B = fe_sqr(p.y), C = fe_sqr(B);
+    Fe t = fe_sqr(fe_add(p.x, B));
+    Fe D = fe_normalize_weak(fe_mul_int(fe_sub(t, fe_add(A, C), 2), 2));       // 2 ((X+B)^2 - A - C)
+    Fe E = fe_mul_int(A, 3);
+    Fe F = fe_sqr(E);
+    r.x = fe_normalize_weak(fe_sub(F, fe_mul_int(D, 2), 1));
+    r.y = fe_normalize_weak(fe_sub(fe_mul(E, fe_sub(D, r.x, 1)), fe_mul_int(C, 8), 8));
+    r.z = fe_mul_int(fe_mul(p.y, p.z), 2);
+    r.inf = p.inf;
+    return r;
+}
+// P + Q, Q affine and not the identity
+BPPP_HD PtJ ptj_add_mixed(const PtJ &p, const PtA &q) {
+    if (p.inf) return ptj_from_affine(q);
+    Fe Z1Z1 = fe_sqr(p.z);
+    Fe U2 = fe_mul(q.x, Z1Z1);
+    Fe S2 = fe_mul(fe_mul(q.y, p.z), Z1Z1);
+    Fe H = fe_sub(U2, p.x, 1);
+    Fe Rh = fe_sub(S2, p.y, 1);                       // (S2 - Y1)
+    if (fe_normalizes_to_zero(H)) {                   // same x: P1 = +-Q
+        if (fe_normalizes_to_zero(Rh)) return ptj_double(ptj_from_affine(q));
+        return ptj_identity();
+    }
+    PtJ r;
+    Fe HH = fe_sqr(H);
+    Fe I = fe_mul_int(HH, 4);
+    Fe J = fe_mul(H, I);
+    Fe rr = fe_mul_int(Rh, 2);
+    Fe V = fe_mul(p.x, I);
+    r.x = fe_normalize_weak(fe_sub(fe_sqr(rr), fe_add(J, fe_mul_int(V, 2)), 3));
+    r.y = fe_normalize_weak(fe_sub(fe_mul(rr, fe_sub(V, r.x, 1)), fe_mul_int(fe_mul(p.y, J), 2), 2));
+    r.z = fe_mul_int(fe_mul(p.z, H), 2);              // (Z1 + H)^2 - Z1Z1 - HH = 2 Z1 H
+    r.inf = false;
+    return r;
+}
+// to homogeneous projective (X Z : Y : Z^3)
+BPPP_HD Pt ptj_to_pt(const PtJ &p) {
+    Pt r;
+    Fe zz = fe_sqr(p.z);
+    r.x = fe_mul(p.x, p.z); r.y = fe_normalize_weak(p.y); r.z = fe_mul(zz, p.z);
+    if (p.inf) r = pt_identity();
+    return r;
+}
+
 // ---- variable-base scalar multiplication, signed 4-bit fixed windows ----
 // k + C with C = sum_{i<64} 8*16^i gives unsigned nibbles d'_i; the signed digit is d'_i - 8 in [-8, 7]
 // for i < 64, plus an unsigned top digit d'_64 in {0, 1}.  No data-dependent recoding.

@@ -25,6 +25,16 @@ __global__ void __launch_bounds__(64) k_v_load_finish(WS w, const uint8_t *proof
     uint32_t f = flags[i];
     u64v_load_finish_one(w, i, proofs + psz * i, fmt, f & 0x7FFFFFFFu, (f >> 31) != 0);
 }
+// ladder tables: build (one thread per (proof, point)), then batch-invert every Z and normalise in place
+__global__ void __launch_bounds__(64) k_v_tables_build(WS w) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = t >> 4; int p = (int)(t & 15);
+    if (i < w.n && p < VL::TAB_POINTS) u64v_table_build_one(w, i, p);
+}
+__global__ void __launch_bounds__(128) k_v_tables_normalize(WS w, size_t nthreads) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nthreads) u64v_tables_normalize_strided(w, t, nthreads);
+}
 __global__ void __launch_bounds__(64) k_v_phase1(WS w, Merlin init) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < w.n) u64v_phase1_one(w, i, init);
@@ -56,6 +66,11 @@ static int verify_part(bppp_ctx *c, cudaStream_t st, WS w, const uint8_t *d_comm
     LAUNCH(c, k_v_load_finish, g64, 64, w, d_proofs, fmt, flags);
     launch_batch_inv(c, st, w, VL::VP + 20, VL::ZINV);
     LAUNCH(c, k_v_phase1, g64, 64, w, init);
+    {   // affine 1P..8P tables of the 13 per-proof points: one batch inversion serves all 104 entries of every proof
+        LAUNCH(c, k_v_tables_build, nblocks(n * 16, 64), 64, w);
+        size_t items = n * VL::TAB_ENTRIES, nthreads = (items + 63) / 64;
+        LAUNCH(c, k_v_tables_normalize, nblocks(nthreads, 128), 128, w, nthreads);
+    }
     TermMap tm = identity_map();
     launch_msm_fixed(c, st, w, VL::FS, tm, 17, VL::ACC);      // pt = ps_tau g + <g_vec, pn_tau>  (circuit.rs:206)
     launch_v_var5(c, st, w);

@@ -36,8 +36,15 @@ struct VL {
     static constexpr int Y = MU + 8;                    // y_0..y_3
     static constexpr int FS = Y + 32;                   // fixed-base scalars (<= 49)
     static constexpr int VS = FS + 8 * NUM_GENS;        // variable-base scalars (<= 5)
-    static constexpr int WORDS = VS + 40;
+    // ladder tables: 13 points (c_l c_r c_o c_s r[0..3] x[0..3] V') x 8 multiples, 40 words per entry:
+    // projective X Y Z (30) + 1/Z (10) while being built, then affine x y (16 canonical words) in place
+    static constexpr int TAB = VS + 40;
+    static constexpr int TAB_POINTS = 13, TAB_ENTRIES = TAB_POINTS * 8, TAB_STRIDE = 40;
+    static constexpr int WORDS = TAB + TAB_ENTRIES * TAB_STRIDE;
 };
+// table point ids: input slot k (1..12) -> k - 1; V' -> 12
+BPPP_HD int vtab_of_slot(int slot) { return slot - 1; }
+static constexpr int VTAB_VP = 12;
 
 enum { FMT_COMPRESSED = 0, FMT_AFFINE64 = 1 };
 static constexpr int U64_PROOF_BYTES_COMPRESSED = 525;          // 13*33 + 3*32 (README.md:30-34)
@@ -199,6 +206,7 @@ BPPP_HD void u64v_phase1_one(const WS &w, size_t i, const Merlin &init) {
 }
 
 // joint variable-base sum_k ks[k] * pts[k] + init: GLV halves, signed 4-bit windows, 128 shared doublings
+// (complete projective formulas, per-thread tables; used by the prover's re-commit and the generic fold kernel)
 template <int NP>
 BPPP_HD Pt straus_var(const PtA *pts, const bool *ident, const Sc *ks, const Pt &init) {
     PtTable8 tab[NP];
@@ -207,18 +215,99 @@ BPPP_HD Pt straus_var(const PtA *pts, const bool *ident, const Sc *ks, const Pt 
     return pt_add(straus_glv<NP>(tab, ks), init);   // init is added last (it must not be doubled)
 }
 
+// ---- verifier ladders over AFFINE tables in the workspace (Jacobian accumulator, ec.cuh) ----
+// Phase T1: 1P..8P of one of the 13 per-proof points, projective, into the table region
+BPPP_HD void u64v_table_build_one(const WS &w, size_t i, int t) {
+    uint32_t idmask = ws_ld(w, i, VL::IDMASK);
+    PtA a; bool id;
+    if (t == VTAB_VP) { a = ws_ld_pta(w, i, VL::VPA); id = idmask & (1u << 14); }
+    else { a = ws_ld_pta(w, i, VL::PT + 16 * (t + 1)); id = idmask & (1u << (t + 1)); }
+    PtTable8 tab;
+    pt_table8_build(tab, pt_from_affine(a, id));
+#pragma unroll 1
+    for (int e = 0; e < 8; e++) ws_st_pt(w, i, VL::TAB + (t * 8 + e) * VL::TAB_STRIDE, tab.m[e]);
+}
+// Phase T3 (after the batch inversion of every Z): entry -> affine canonical words in place; identity -> zero sentinel
+BPPP_HD void u64v_table_finish_one(const WS &w, size_t i, int entry) {
+    const int off = VL::TAB + entry * VL::TAB_STRIDE;
+    bool id;
+    PtA a = ws_affine(w, i, off, off + 30, id);
+    if (id) { a.x = fe_zero(); a.y = fe_zero(); }
+    ws_st_pta(w, i, off, a);
+}
+// Phases T2+T3 fused: Montgomery batch inversion of every table entry's Z over this thread's strided share of the
+// (entry, proof) items, writing the affine words in place on the way back (no separate 1/Z round trip through HBM)
+BPPP_HD void u64v_tables_normalize_strided(const WS &w, size_t t, size_t T) {
+    const size_t total = (size_t)VL::TAB_ENTRIES * w.n;
+    Fe run = fe_one();
+#pragma unroll 1
+    for (size_t idx = t; idx < total; idx += T) {
+        size_t e = idx / w.n, i = idx - e * w.n;
+        const int off = VL::TAB + (int)e * VL::TAB_STRIDE;
+        Fe z = ws_ld_fe(w, i, off + 20);
+        ws_st_fe(w, i, off + 30, run);                  // prefix product before this item
+        if (!fe_normalizes_to_zero(z)) run = fe_mul(run, z);
+    }
+    Fe rinv = fe_inv(run);
+    size_t cnt = total > t ? (total - t + T - 1) / T : 0;
+#pragma unroll 1
+    for (size_t k = cnt; k-- > 0;) {
+        size_t idx = t + k * T;
+        size_t e = idx / w.n, i = idx - e * w.n;
+        const int off = VL::TAB + (int)e * VL::TAB_STRIDE;
+        Pt p = ws_ld_pt(w, i, off);
+        PtA a;
+        if (fe_normalizes_to_zero(p.z)) { a.x = fe_zero(); a.y = fe_zero(); }       // identity -> zero sentinel
+        else {
+            Fe zi = fe_mul(rinv, ws_ld_fe(w, i, off + 30));
+            rinv = fe_mul(rinv, p.z);
+            a = pt_to_affine_with_zinv(p, zi);
+        }
+        ws_st_pta(w, i, off, a);
+    }
+}
+// acc = sum_k ks[k] * P_{tids[k]} + init from the affine tables
+template <int NP>
+BPPP_HD Pt straus_tables(const WS &w, size_t i, const int *tids, const Sc *ks, const Pt &init) {
+    Digits4h dg[2 * NP];
+    bool neg[2 * NP];
+#pragma unroll 1
+    for (int k = 0; k < NP; k++) {
+        GlvSplit g = glv_split(ks[k]);
+        dg[2 * k] = half_signed_digits4(g.k1); neg[2 * k] = g.neg1;
+        dg[2 * k + 1] = half_signed_digits4(g.k2); neg[2 * k + 1] = g.neg2;
+    }
+    const Fe beta = fe_beta();
+    PtJ acc = ptj_identity();
+#pragma unroll 1
+    for (int d = 32; d >= 0; d--) {
+        if (d != 32) {
+#pragma unroll 1
+            for (int r = 0; r < 4; r++) acc = ptj_double(acc);
+        }
+#pragma unroll 1
+        for (int h = 0; h < 2 * NP; h++) {
+            int sd = digits4h_get(dg[h], d);
+            if (neg[h]) sd = -sd;
+            if (sd == 0) continue;
+            int a = sd < 0 ? -sd : sd;
+            PtA q = ws_ld_pta(w, i, VL::TAB + (tids[h >> 1] * 8 + (a - 1)) * VL::TAB_STRIDE);
+            if (fe_is_zero_canonical(q.x) && fe_is_zero_canonical(q.y)) continue;       // identity point: nothing to add
+            if (sd < 0) q.y = fe_normalize_weak(fe_negate(q.y, 1));
+            if (h & 1) q.x = fe_mul(q.x, beta);
+            acc = ptj_add_mixed(acc, q);
+        }
+    }
+    return pt_add(ptj_to_pt(acc), init);
+}
+
 // Phase 2b: com_0 = ACC (fixed part) + tau^-1 c_s - delta c_o + tau c_l - tau^2 c_r + 2 tau^3 V'
 BPPP_HD void u64v_var5_one(const WS &w, size_t i) {
-    uint32_t idmask = ws_ld(w, i, VL::IDMASK);
-    PtA pts[5]; bool ident[5]; Sc ks[5];
-    const int slots[4] = {VP_CS, VP_CO, VP_CL, VP_CR};
-#pragma unroll 1
-    for (int k = 0; k < 4; k++) { pts[k] = ws_ld_pta(w, i, VL::PT + 16 * slots[k]); ident[k] = idmask & (1u << slots[k]); }
-    pts[4] = ws_ld_pta(w, i, VL::VPA); ident[4] = idmask & (1u << 14);
+    const int tids[5] = {vtab_of_slot(VP_CS), vtab_of_slot(VP_CO), vtab_of_slot(VP_CL), vtab_of_slot(VP_CR), VTAB_VP};
+    Sc ks[5];
 #pragma unroll 1
     for (int k = 0; k < 5; k++) ks[k] = ws_ld_sc(w, i, VL::VS + 8 * k);
-    Pt com = straus_var<5>(pts, ident, ks, ws_ld_pt(w, i, VL::ACC));
-    ws_st_pt(w, i, VL::COM, com);
+    ws_st_pt(w, i, VL::COM, straus_tables<5>(w, i, tids, ks, ws_ld_pt(w, i, VL::ACC)));
 }
 
 // WNLA round j = 0..3 (wnla.rs:84-102): transcript -> y_j, fold c, scalars for com' = com + y X + (y^2-1) R
@@ -249,13 +338,9 @@ BPPP_HD void u64v_round_one(const WS &w, size_t i, int j) {
 
 // com' = com + y X + (y^2 - 1) R  (wnla.rs:100-102)
 BPPP_HD void u64v_var2_one(const WS &w, size_t i, int j) {
-    uint32_t idmask = ws_ld(w, i, VL::IDMASK);
-    const int xs = VP_X + (3 - j), rs = VP_R + (3 - j);
-    PtA pts[2] = {ws_ld_pta(w, i, VL::PT + 16 * xs), ws_ld_pta(w, i, VL::PT + 16 * rs)};
-    bool ident[2] = {(bool)(idmask & (1u << xs)), (bool)(idmask & (1u << rs))};
+    const int tids[2] = {vtab_of_slot(VP_X + (3 - j)), vtab_of_slot(VP_R + (3 - j))};
     Sc ks[2] = {ws_ld_sc(w, i, VL::VS), ws_ld_sc(w, i, VL::VS + 8)};
-    Pt com = straus_var<2>(pts, ident, ks, ws_ld_pt(w, i, VL::COM));
-    ws_st_pt(w, i, VL::COM, com);
+    ws_st_pt(w, i, VL::COM, straus_tables<2>(w, i, tids, ks, ws_ld_pt(w, i, VL::COM)));
 }
 
 // Base case (wnla.rs:80-82): scalars of commit(l, n) over the ORIGINAL generators.  After 4 folds

@@ -57,6 +57,18 @@ int emu_ptx_sum(const uint8_t *pts, int n, uint8_t *r) {
     for (int i = 0; i < n; i++) { PtA a; int s = pta_from_xy64(a, pts + 64 * i); if (s != 0) return -1; acc = ptx_add_mixed(acc, a); }
     store_pt(r, ptx_to_pt(acc)); return 0;
 }
+// Jacobian accumulator: k * base via double-and-add over the bits of k, then + sum of extra affine points
+int emu_ptj_ladder(const uint8_t *base, const uint8_t *k32, const uint8_t *extra, int n_extra, uint8_t *r) {
+    PtA b; if (pta_from_xy64(b, base) != 0) return -1;
+    uint32_t w[8]; be32_to_words(w, k32);
+    PtJ acc = ptj_identity();
+    for (int bit = 255; bit >= 0; bit--) {
+        acc = ptj_double(acc);
+        if ((w[bit >> 5] >> (bit & 31)) & 1) acc = ptj_add_mixed(acc, b);
+    }
+    for (int i = 0; i < n_extra; i++) { PtA a; if (pta_from_xy64(a, extra + 64 * i) != 0) return -1; acc = ptj_add_mixed(acc, a); }
+    store_pt(r, ptj_to_pt(acc)); return 0;
+}
 int emu_pt_double(const uint8_t *p, uint8_t *r) { int s; Pt a = load_pt(p, &s); if (s < 0) return -1; store_pt(r, pt_double(a)); return 0; }
 int emu_pt_mul(const uint8_t *p, const uint8_t *k, uint8_t *r) { int s; Pt a = load_pt(p, &s); Sc kk; if (s < 0 || !sc_from_be32(kk, k)) return -1; store_pt(r, pt_mul(a, kk)); return 0; }
 int emu_pt_mul_glv(const uint8_t *p, const uint8_t *k, uint8_t *r) { int s; Pt a = load_pt(p, &s); Sc kk; if (s < 0 || !sc_from_be32(kk, k)) return -1; store_pt(r, pt_mul_glv(a, kk)); return 0; }

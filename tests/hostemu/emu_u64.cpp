@@ -69,6 +69,8 @@ int emu_u64_verify_batch(void *ctx, size_t n, const uint8_t *commits, const uint
     for (size_t i = 0; i < n; i++) u64v_load_one(w, i, commits + csz * i, proofs + psz * i, fmt);
     emu_batch_inv(w, n, VL::VP + 20, VL::ZINV);
     for (size_t i = 0; i < n; i++) u64v_phase1_one(w, i, init);
+    for (size_t i = 0; i < n; i++) for (int t = 0; t < VL::TAB_POINTS; t++) u64v_table_build_one(w, i, t);
+    { size_t T = (n * VL::TAB_ENTRIES + 6) / 7; for (size_t t = 0; t < T; t++) u64v_tables_normalize_strided(w, t, T); }
     int tg17[17]; for (int t = 0; t < 17; t++) tg17[t] = t;
     emu_msm_fixed(c, w, n, VL::FS, tg17, 17, VL::ACC, 8);
     for (size_t i = 0; i < n; i++) u64v_var5_one(w, i);

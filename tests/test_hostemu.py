@@ -96,6 +96,26 @@ def test_xyzz_accumulator_including_exceptional_cases(emu_prims, ref):
         assert unxy(bytes(o)) == exp
 
 
+def test_jacobian_accumulator_including_exceptional_cases(emu_prims, ref):
+    L, N = emu_prims, ref.N
+    rnd = random.Random(22)
+    unxy = lambda b: None if b == b"\0" * 64 else (int.from_bytes(b[:32], "big"), int.from_bytes(b[32:], "big"))  # noqa: E731
+    p = ref.pt_mul(ref.G, rnd.randrange(1, N))
+    q = ref.pt_mul(ref.G, rnd.randrange(1, N))
+    for k in [0, 1, 2, 3, 5, N - 1, N - 2, 2**255, rnd.randrange(N), rnd.randrange(N)]:
+        kp = ref.pt_mul(p, k)
+        extras = [[], [q], [p], [ref.pt_neg(p)], [q, ref.pt_neg(q)], [q, q, q]]
+        if kp is not None:
+            extras += [[kp], [ref.pt_neg(kp)], [ref.pt_neg(kp), kp, kp]]     # acc == Q (doubling) and acc == -Q (identity)
+        for ex in extras:
+            exp = kp
+            for e in ex:
+                exp = ref.pt_add(exp, e)
+            o = O(64)
+            assert L.emu_ptj_ladder(B(xy(p)), B(be(k)), B(b"".join(xy(e) for e in ex)), len(ex), o) == 0
+            assert unxy(bytes(o)) == exp, (hex(k), len(ex))
+
+
 def test_glv_split_and_multiplication(emu_prims, ref):
     L, N = emu_prims, ref.N
     lam = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72

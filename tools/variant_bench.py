@@ -33,7 +33,7 @@ def main():
            "verify_per_s": round(n / vm * 1e3), "prove_ms": round(pm, 2), "prove_per_s": round(n / pm * 1e3), "ok": ok and pok}
     if os.environ.get("BPPP_PROFILE"):
         ctx.profile_begin(); v(); pv = ctx.profile_end()
-        res["kernels_verify"] = {k: round(ms, 2) for k, (ms, c) in sorted(pv.items(), key=lambda kv: -kv[1][0])[:6]}
+        res["kernels_verify"] = {k: round(ms, 2) for k, (ms, c) in sorted(pv.items(), key=lambda kv: -kv[1][0])[:12]}
         ctx.profile_begin(); p(); pp = ctx.profile_end()
         res["kernels_prove"] = {k: round(ms, 2) for k, (ms, c) in sorted(pp.items(), key=lambda kv: -kv[1][0])[:4]}
     print(json.dumps(res), flush=True)
