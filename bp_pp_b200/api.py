@@ -308,6 +308,11 @@ class ReciprocalRangeProofProtocol:
         check(lib().bppp_reciprocal_commit_value(C.c_int(self.device), _in(self.g), _in(self.h_vec[:64]), _in(x32), _in(s32), out), "bppp_reciprocal_commit_value")
         return bytes(out)
 
+    # reciprocal.rs:93-95: s * h_vec[0] + <h_vec[9..], r>
+    def commit_poles(self, r32: bytes, s32: bytes) -> bytes:
+        nr = len(r32) // 32
+        return msm(self.h_vec[:64] + self.h_vec[64 * 9:64 * (9 + nr)], s32 + r32, FMT_AFFINE64, FMT_COMPRESSED, self.device)
+
     # reciprocal.rs:110-146 -> (record, rounds, l_len, n_len, commitment33)
     def prove(self, x32: bytes, s32: bytes, digits, rng: bytes, label: bytes):
         cap = 33 * (5 + 2 * 64) + 32 * 16

@@ -55,3 +55,14 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.lower(), f"{f} mentions the oracle"
+
+
+def test_serializable_proof_json_framing(golden):
+    """bp_pp_b200.serde reproduces the serde_json object the oracle emits for reciprocal::SerializableProof and round-trips."""
+    from bp_pp_b200 import serde
+    c = golden["cases"][0]
+    rec = bytes.fromhex(c["proof"])
+    obj = serde.reciprocal_record_to_obj(rec)
+    assert obj == c["json"]
+    assert serde.reciprocal_obj_to_record(obj) == rec
+    assert serde.loads_reciprocal(serde.dumps_reciprocal(rec)) == rec

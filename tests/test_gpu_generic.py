@@ -152,6 +152,9 @@ def test_reciprocal_generic_dims_match_oracle(oracle, ref, nd, np_, hn2):
     rec_o, rounds, ll, nl, com_o = oracle.reciprocal_prove(nd, np_, g, gvec, hvec, b"", hvec2, x32, s32, digits, rng, label)
     rec, rounds2, ll2, nl2, com = proto.prove(x32, s32, digits, rng, label)
     assert com == com_o == proto.commit_value(x32, s32)
+    r_wit = [pow((d + 12345) % ref.N, -1, ref.N) for d in digits]          # any scalars: commit_poles is a plain MSM
+    r32 = b"".join(_be(v) for v in r_wit)
+    assert proto.commit_poles(r32, s32) == oracle.msm(hvec[:64] + hvec[64 * 9:64 * (9 + nd)], s32 + r32)
     assert (rounds2, ll2, nl2) == (rounds, ll, nl)
     assert rec == rec_o
     assert proto.verify(com, rec, rounds, rounds, ll, nl, label) == 1
