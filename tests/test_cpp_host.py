@@ -1,0 +1,54 @@
+"""include/bppp.hpp (the C++ host layer that mirrors the reference's Rust items) compiles against libbppp.so, refuses to
+run without a GPU, and on a GPU produces the oracle's bytes."""
+import os
+import struct
+import subprocess
+
+import pytest
+
+from conftest import ROOT, has_cuda, synth_batch
+
+LABEL = b"u64 range proof"
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory):
+    from bp_pp_b200._lib import SO_PATH
+    out = str(tmp_path_factory.mktemp("cpp") / "hpp_roundtrip")
+    libdir = os.path.dirname(SO_PATH)
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "hpp_roundtrip.cpp"),
+           "-o", out, "-L", libdir, "-l:" + os.path.basename(SO_PATH), "-Wl,-rpath," + libdir]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return out
+
+
+def _stdin(ref, gens64):
+    xs, blinds, rngs = synth_batch(ref, 4)
+    i = 3
+    return xs[i], blinds[32 * i:32 * i + 32], rngs[3328 * i:3328 * i + 3328]
+
+
+@pytest.mark.skipif(has_cuda(), reason="checks the no-GPU failure mode")
+def test_cpp_layer_fails_loudly_without_a_gpu(exe, ref, gens64):
+    x, blind, rng = _stdin(ref, gens64)
+    r = subprocess.run([exe], input=gens64 + struct.pack("<Q", x) + blind + rng, capture_output=True, timeout=120)
+    assert r.returncode == 4
+    assert b"no CPU fallback" in r.stdout and b"commit=" not in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_layer_matches_the_oracle(exe, ref, oracle, gens64):
+    x, blind, rng = _stdin(ref, gens64)
+    r = subprocess.run([exe], input=gens64 + struct.pack("<Q", x) + blind + rng, capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    kv = dict(line.split("=", 1) for line in r.stdout.decode().splitlines())
+    proofs, st = oracle.u64_prove_batch(gens64, [x], blind, rng, LABEL, 1)
+    assert st == [0]
+    assert kv["commit"] == oracle.u64_commit(gens64, x, blind).hex()
+    assert kv["proof"] == proofs.hex()
+    assert kv["verify"] == "1" and kv["verify_tampered"] == "0" and kv["malformed"] == "-3"
+    assert kv["wnla_rounds"] == "2" and kv["wnla_verify"] == "1"
+    sc = lambda v: v.to_bytes(32, "big")
+    com = oracle.wnla_commit(gens64[:64], gens64[64:64 + 4 * 64], gens64[17 * 64:21 * 64], b"".join(map(sc, [1, 2, 4, 2])), sc(2), sc(4),
+                             b"".join(map(sc, [2, 1, 4, 1])), b"".join(map(sc, [1, 4, 2, 2])))
+    assert kv["wnla_commit"] == com.hex()

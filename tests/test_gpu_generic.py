@@ -114,6 +114,22 @@ def test_wnla_commit_prove_verify_match_oracle(oracle, ref, gn, hn, ln, nn):
     assert w.verify(com, b"other label", r, x, lo, no) == (expect if len(r) == 0 else 0)
 
 
+def test_wnla_with_mu_unrelated_to_rho(oracle, ref):
+    """mu != rho^2: the WNLA relation does not hold, so the reference's verify rejects its own proof; commit and proof
+    bytes still have to match, and so does the verdict."""
+    import bp_pp_b200 as B
+    g, gvec, hvec, c, rho, _, l, n = _wnla_instance(oracle, ref, 8, 8, 8, 8, seed=77)
+    mu = _be(random.Random(78).randrange(1, ref.N))
+    w = B.WeightNormLinearArgument(g, gvec, hvec, c, rho, mu)
+    com = oracle.wnla_commit(g, gvec, hvec, c, rho, mu, l, n)
+    assert w.commit(l, n) == com
+    out = w.prove(com, b"t", l, n)
+    assert out == oracle.wnla_prove(g, gvec, hvec, c, rho, mu, com, l, n, b"t")
+    expect = oracle.wnla_verify(g, gvec, hvec, c, rho, mu, com, *out, b"t")
+    assert expect == 0
+    assert w.verify(com, b"t", *out) == expect
+
+
 def test_wnla_golden_fixture(oracle):
     import json
     import bp_pp_b200 as B
