@@ -113,7 +113,7 @@ BPPP_HD PtA pt_to_affine_with_zinv(const Pt &p, const Fe &zinv) {
 BPPP_HD void pta_compress(uint8_t out[33], const PtA &a_canonical, bool is_identity) {
     uint32_t w[8];
     fe_to_words(w, a_canonical.x);
-    out[0] = is_identity ? 0 : (uint8_t)(2u + (a_canonical.y.n[0] & 1u));
+    out[0] = is_identity ? 0 : (uint8_t)(2u + (a_canonical.y.v[0] & 1u));
     words_to_be32(out + 1, w);
     if (is_identity) {
 #pragma unroll
@@ -141,7 +141,7 @@ BPPP_HD int pta_decompress(PtA &r, const uint8_t in[33]) {
     Fe y = fe_sqrt_candidate(y2);
     if (!fe_is_zero(fe_sub(fe_sqr(y), y2, 2))) return -1;
     y = fe_normalize(y);
-    if ((y.n[0] & 1u) != (uint32_t)(in[0] & 1u)) y = fe_normalize(fe_negate(y, 1));
+    if ((y.v[0] & 1u) != (uint32_t)(in[0] & 1u)) y = fe_normalize(fe_negate(y, 1));
     r.x = x; r.y = y;
     return 0;
 }

@@ -34,8 +34,8 @@ __global__ void __launch_bounds__(256) k_mb_imad(uint64_t *out, uint32_t seed, i
 }
 template <int OP>
 __global__ void __launch_bounds__(64) k_mb_op(uint32_t *out, uint32_t seed, int iters) {
-    Fe a = fe_from_u32((seed + threadIdx.x) & FE_M26), b = fe_from_u32((seed * 3 + 1 + blockIdx.x) & FE_M26);
-    a.n[3] = threadIdx.x + 5; b.n[7] = blockIdx.x + 9; b.n[9] = 77;
+    Fe a = fe_from_u32(seed + threadIdx.x), b = fe_from_u32(seed * 3 + 1 + blockIdx.x);
+    a.v[3] = threadIdx.x + 5; b.v[7] = blockIdx.x + 9; b.v[5] = 77;
     Pt p; p.x = a; p.y = b; p.z = fe_from_u32(1);
     PtA q; q.x = b; q.y = a;
     Sc s, u;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(64) k_mb_op(uint32_t *out, uint32_t seed, int 
     }
     uint32_t r = 0;
 #pragma unroll
-    for (int k = 0; k < 10; k++) r ^= a.n[k] ^ p.x.n[k] ^ p.y.n[k] ^ p.z.n[k];
+    for (int k = 0; k < FE_W; k++) r ^= a.v[k] ^ p.x.v[k] ^ p.y.v[k] ^ p.z.v[k];
 #pragma unroll
     for (int k = 0; k < 8; k++) r ^= s.v[k];
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;

@@ -91,7 +91,7 @@ int commit_hg(const Circuit &c, const SV &hs, const SV &gs, const Sc &gsc, uint8
     memcpy(&sc[8 * (c.hn + c.gn)], gsc.v, 32);
     uint32_t *d_sc = nullptr, *d_o = d_out30;
     CUDA_OK(cudaMalloc(&d_sc, 32 * n));
-    if (!d_o) CUDA_OK(cudaMalloc(&d_o, 120));
+    if (!d_o) CUDA_OK(cudaMalloc(&d_o, PT_BYTES));
     CUDA_OK(cudaMemcpy(d_sc, sc.data(), 32 * n, cudaMemcpyHostToDevice));
     int rc = msm_device(nullptr, c.d_pts, d_sc, n, nullptr, d_o);
     if (rc == BPPP_OK && out33) rc = encode_points_from_device(nullptr, d_o, 1, FMT_COMPRESSED, out33);
@@ -269,7 +269,7 @@ int circuit_prove(const Circuit &c, const std::vector<std::vector<uint8_t>> &v33
     SV cvec = concat(cr_tau, cl_tau);
     Sc vv = sc_add(ps_tau, sc_mul(tau3, v_0));
     uint32_t *d_com30 = nullptr;
-    CUDA_OK(cudaMalloc(&d_com30, 120));
+    CUDA_OK(cudaMalloc(&d_com30, PT_BYTES));
     if ((rc = commit_hg(c, l, n, vv, nullptr, d_com30)) != BPPP_OK) { cudaFree(d_com30); return rc; }                       // :522-524
     size_t hn_all = (c.hvec64.size() + c.hvec2_64.size()) / 64, gn_all = (c.gvec64.size() + c.gvec2_64.size()) / 64;
     while (l.size() < hn_all) { l.push_back(sc_zero()); cvec.push_back(sc_zero()); }                                        // :526-529
@@ -309,7 +309,7 @@ int circuit_verify(const Circuit &c, const std::vector<std::vector<uint8_t>> &v3
     SV pn_tau = vadd(vsub(vscale(cc.nO, t3d), vscale(cc.nL, tau2)), vscale(cc.nR, tau));
     Sc ps_tau = sc_sub(sc_add(wvmul(pn_tau, pn_tau, mu), sc_mul(sc_mul(vmul(lambda_vec, c.a_l), tau3), two)), sc_mul(sc_mul(vmul(mu_vec, c.a_m), tau3), two));
     uint32_t *d_pt30 = nullptr, *d_com30 = nullptr;
-    CUDA_OK(cudaMalloc(&d_pt30, 120)); CUDA_OK(cudaMalloc(&d_com30, 120));
+    CUDA_OK(cudaMalloc(&d_pt30, PT_BYTES)); CUDA_OK(cudaMalloc(&d_com30, PT_BYTES));
     int rc = commit_hg(c, SV(), pn_tau, ps_tau, nullptr, d_pt30);                                      // pt, circuit.rs:206
     SV cr_tau = make_cr_tau(tau, tau_inv, tau2, tau3, beta);
     SV c_l0 = collect_cl0(c, lambda, mu);

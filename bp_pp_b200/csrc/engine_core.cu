@@ -28,10 +28,10 @@ __device__ __forceinline__ Pt lanes_reduce(Pt acc) {
     for (int off = LANES / 2; off >= 1; off >>= 1) {
         Pt o;
 #pragma unroll
-        for (int k = 0; k < 10; k++) {
-            o.x.n[k] = __shfl_xor_sync(0xFFFFFFFFu, acc.x.n[k], off);
-            o.y.n[k] = __shfl_xor_sync(0xFFFFFFFFu, acc.y.n[k], off);
-            o.z.n[k] = __shfl_xor_sync(0xFFFFFFFFu, acc.z.n[k], off);
+        for (int k = 0; k < FE_W; k++) {
+            o.x.v[k] = __shfl_xor_sync(0xFFFFFFFFu, acc.x.v[k], off);
+            o.y.v[k] = __shfl_xor_sync(0xFFFFFFFFu, acc.y.v[k], off);
+            o.z.v[k] = __shfl_xor_sync(0xFFFFFFFFu, acc.z.v[k], off);
         }
         acc = pt_add(acc, o);
     }
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(64) k_c_store(WS w, uint8_t *out, int fmt) {
 }
 
 // ---- fixed-base table construction (one generator per pass) ----
-// scratch layout per entry (word-major over nent = nwin * E entries): Pt at 0..29, zinv at 30..39
+// scratch layout per entry (word-major over nent = nwin * E entries): Pt at 0..PT_W-1, zinv after it
 __global__ void k_tab_bases(WS tmp, PtA gen, bool gen_id, int W, int nwin, uint32_t E) {
     // single thread: B_w = 2^(W w) G, stored at entry (w, d = 1)
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128) k_tab_write(WS tmp, uint4 *dst) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= tmp.n) return;
     bool id;
-    PtA a = ws_affine(tmp, t, 0, 30, id);
+    PtA a = ws_affine(tmp, t, 0, PT_W, id);
     uint32_t x[8], y[8];
     fe_to_words(x, a.x); fe_to_words(y, a.y);
     if (id) {
@@ -168,7 +168,7 @@ static int build_tables(bppp_ctx *c, const PtA *gens, const bool *gen_id) {
     const uint32_t E = (1u << W) - 1u;
     const size_t nent = (size_t)nwin * E;
     uint32_t *d_tmp = nullptr;
-    CUDA_OK(cudaMalloc(&d_tmp, nent * 40 * sizeof(uint32_t)));
+    CUDA_OK(cudaMalloc(&d_tmp, nent * (size_t)(4 * FE_W) * sizeof(uint32_t)));
     cudaStream_t st = c->stream;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -180,7 +180,7 @@ static int build_tables(bppp_ctx *c, const PtA *gens, const bool *gen_id) {
             size_t threads = (size_t)nwin << (level - 1);
             LAUNCH(c, k_tab_level, nblocks(threads, 128), 128, tmp, nwin, E, level);
         }
-        launch_batch_inv(c, st, tmp, 20, 30);
+        launch_batch_inv(c, st, tmp, 2 * FE_W, PT_W);
         LAUNCH(c, k_tab_write, nblocks(nent, 128), 128, tmp, c->d_tab + (size_t)g * nent * 4);
     }
     cudaEventRecord(e1, st);
@@ -314,7 +314,7 @@ extern "C" int bppp_u64_commit_batch(bppp_ctx *c, size_t n, const uint64_t *x, c
         CUDA_OK(cudaMemcpyAsync(c->d_in_b, blinds32 + 32 * off, 32 * m, cudaMemcpyHostToDevice, st));
         LAUNCH(c, k_c_load, nblocks(m, 64), 64, w, (const uint64_t *)c->d_in_a, c->d_in_b);
         launch_msm_fixed(c, st, w, VL::FS, tm, 2, VL::ACC);
-        launch_batch_inv(c, st, w, VL::ACC + 20, VL::ZINV);
+        launch_batch_inv(c, st, w, VL::ACC + 2 * FE_W, VL::ZINV);
         LAUNCH(c, k_c_store, nblocks(m, 64), 64, w, c->d_out, fmt);
         CUDA_OK(cudaMemcpyAsync(out + osz * off, c->d_out, osz * m, cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaStreamSynchronize(st));

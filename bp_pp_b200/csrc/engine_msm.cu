@@ -31,11 +31,11 @@ __device__ __forceinline__ bool load_dev_point(PtA &q, const uint32_t *pts, size
 }
 __device__ __forceinline__ Pt ld_pt30(const uint32_t *p) { Pt r;
 #pragma unroll
-    for (int k = 0; k < 10; k++) { r.x.n[k] = p[k]; r.y.n[k] = p[10 + k]; r.z.n[k] = p[20 + k]; }
+    for (int k = 0; k < FE_W; k++) { r.x.v[k] = p[k]; r.y.v[k] = p[FE_W + k]; r.z.v[k] = p[2 * FE_W + k]; }
     return r; }
 __device__ __forceinline__ void st_pt30(uint32_t *p, const Pt &a) {
 #pragma unroll
-    for (int k = 0; k < 10; k++) { p[k] = a.x.n[k]; p[10 + k] = a.y.n[k]; p[20 + k] = a.z.n[k]; } }
+    for (int k = 0; k < FE_W; k++) { p[k] = a.x.v[k]; p[FE_W + k] = a.y.v[k]; p[2 * FE_W + k] = a.z.v[k]; } }
 
 __global__ void k_decode_points(const uint8_t *in, int fmt, uint32_t *out, int32_t *bad, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,11 +68,11 @@ __global__ void k_encode_scalars(const uint32_t *in, uint8_t *out, size_t n) {
     for (int k = 0; k < 8; k++) s.v[k] = in[8 * i + k];
     sc_to_be32(out + 32 * i, s);
 }
-// projective (30 words each) -> affine bytes; one inversion per point (used for a handful of outputs)
+// projective (PT_W words each) -> affine bytes; one inversion per point (used for a handful of outputs)
 __global__ void k_encode_points(const uint32_t *pts30, int fmt, uint8_t *out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Pt p = ld_pt30(pts30 + 30 * i);
+    Pt p = ld_pt30(pts30 + PT_W * i);
     bool id = pt_is_identity(p);
     PtA a = pt_to_affine_with_zinv(p, fe_inv(p.z));
     if (fmt == FMT_COMPRESSED) pta_compress(out + 33 * i, a, id); else pta_to_xy64(out + 64 * i, a, id);
@@ -124,7 +124,7 @@ __device__ __forceinline__ Pt msm_accumulate_range(const uint32_t *pts, const ui
     }
     return ptx_to_pt(acc);
 }
-// bucket sums are stored AoS, 30 words per point
+// bucket sums are stored AoS, PT_W words per point
 __global__ void __launch_bounds__(64, 7) k_msm_buckets(const uint32_t *pts, const uint32_t *vals, const uint32_t *start, const uint32_t *end, uint32_t nb,
                                                         uint32_t *buckets, uint32_t *heavy, uint32_t *heavy_count, uint32_t heavy_cap) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,28 +132,28 @@ __global__ void __launch_bounds__(64, 7) k_msm_buckets(const uint32_t *pts, cons
     uint32_t p0 = start[b], p1 = end[b];
     if (p1 - p0 > MSM_HEAVY) {
         uint32_t slot = atomicAdd(heavy_count, 1u);
-        if (slot < heavy_cap) { heavy[slot] = (uint32_t)b; st_pt30(buckets + 30 * b, pt_identity()); return; }
+        if (slot < heavy_cap) { heavy[slot] = (uint32_t)b; st_pt30(buckets + PT_W * b, pt_identity()); return; }
     }
-    st_pt30(buckets + 30 * b, msm_accumulate_range(pts, vals, p0, p1, 1));
+    st_pt30(buckets + PT_W * b, msm_accumulate_range(pts, vals, p0, p1, 1));
 }
 __global__ void __launch_bounds__(128) k_msm_heavy(const uint32_t *pts, const uint32_t *vals, const uint32_t *start, const uint32_t *end, const uint32_t *heavy,
                                                     const uint32_t *heavy_count, uint32_t heavy_cap, uint32_t *buckets) {
-    __shared__ uint32_t sh[128 * 30];
+    __shared__ uint32_t sh[128 * PT_W];
     uint32_t cnt = *heavy_count; if (cnt > heavy_cap) cnt = heavy_cap;
     if (blockIdx.x >= cnt) return;
     uint32_t b = heavy[blockIdx.x];
     Pt acc = msm_accumulate_range(pts, vals, start[b] + threadIdx.x, end[b], 128);
-    st_pt30(sh + 30 * threadIdx.x, acc);
+    st_pt30(sh + PT_W * threadIdx.x, acc);
     __syncthreads();
     for (int s = 64; s >= 1; s >>= 1) {
-        if ((int)threadIdx.x < s) st_pt30(sh + 30 * threadIdx.x, pt_add(ld_pt30(sh + 30 * threadIdx.x), ld_pt30(sh + 30 * (threadIdx.x + s))));
+        if ((int)threadIdx.x < s) st_pt30(sh + PT_W * threadIdx.x, pt_add(ld_pt30(sh + PT_W * threadIdx.x), ld_pt30(sh + PT_W * (threadIdx.x + s))));
         __syncthreads();
     }
-    if (threadIdx.x == 0) st_pt30(buckets + 30 * (size_t)b, ld_pt30(sh));
+    if (threadIdx.x == 0) st_pt30(buckets + PT_W * (size_t)b, ld_pt30(sh));
 }
 __global__ void k_pt_fill_identity(uint32_t *pts30, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) st_pt30(pts30 + 30 * i, pt_identity());
+    if (i < n) st_pt30(pts30 + PT_W * i, pt_identity());
 }
 // per window w, chunk j of CH buckets: out[w * nchunks + j] = sum_{b in chunk} (b + 1) B_b
 __global__ void __launch_bounds__(64) k_msm_chunks(const uint32_t *buckets, int nwin, uint32_t half, uint32_t CH, uint32_t nchunks, uint32_t *out) {
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(64) k_msm_chunks(const uint32_t *buckets, int 
     Pt S = pt_identity(), T = pt_identity();
 #pragma unroll 1
     for (uint32_t b = top; b-- > base;) {
-        S = pt_add(S, ld_pt30(buckets + 30 * ((size_t)w * half + b)));
+        S = pt_add(S, ld_pt30(buckets + PT_W * ((size_t)w * half + b)));
         T = pt_add(T, S);
     }
     // + base * S: double-and-add
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(64) k_msm_chunks(const uint32_t *buckets, int 
         BS = pt_double(BS);
         if ((base >> bit) & 1u) BS = pt_add(BS, S);
     }
-    st_pt30(out + 30 * t, pt_add(T, BS));
+    st_pt30(out + PT_W * t, pt_add(T, BS));
 }
 // out[g] = sum_{t < group} in[g * group + t]  (entries beyond count_in are skipped)
 __global__ void __launch_bounds__(64) k_pt_sum_groups(const uint32_t *in, size_t count_in, uint32_t group, uint32_t *out, size_t count_out) {
@@ -184,17 +184,17 @@ __global__ void __launch_bounds__(64) k_pt_sum_groups(const uint32_t *in, size_t
 #pragma unroll 1
     for (uint32_t t = 0; t < group; t++) {
         size_t idx = g * group + t;
-        if (idx < count_in) acc = pt_add(acc, ld_pt30(in + 30 * idx));
+        if (idx < count_in) acc = pt_add(acc, ld_pt30(in + PT_W * idx));
     }
-    st_pt30(out + 30 * g, acc);
+    st_pt30(out + PT_W * g, acc);
 }
 // result = sum_w 2^(c w) W_w, optionally + *addend
 __global__ void k_msm_horner(const uint32_t *win, int c, int nwin, const uint32_t *addend, uint32_t *out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    Pt acc = ld_pt30(win + 30 * (nwin - 1));
+    Pt acc = ld_pt30(win + PT_W * (nwin - 1));
     for (int w = nwin - 2; w >= 0; w--) {
         for (int k = 0; k < c; k++) acc = pt_double(acc);
-        acc = pt_add(acc, ld_pt30(win + 30 * w));
+        acc = pt_add(acc, ld_pt30(win + PT_W * w));
     }
     if (addend) acc = pt_add(acc, ld_pt30(addend));
     st_pt30(out, acc);
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(64) k_msm_small(const uint32_t *pts, const uin
     for (int j = 0; j < 8; j++) k.v[j] = sc[8 * i + j];
     bool ok = load_dev_point(q, pts, i);
     Pt r = pt_mul_glv(pt_from_affine(q, !ok), k);
-    st_pt30(out + 30 * i, r);
+    st_pt30(out + PT_W * i, r);
 }
 
 static std::atomic<uint64_t> g_generic_launches{0};
@@ -254,23 +254,23 @@ int msm_choose_window(size_t n) {
     return c;
 }
 
-// d_out30: projective result (30 words, device).  d_addend30 may be null.  Synchronises before returning.
+// d_out30: projective result (PT_W words, device).  d_addend30 may be null.  Synchronises before returning.
 int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, size_t n, const uint32_t *d_addend30, uint32_t *d_out30) {
     if (n == 0) {
-        if (d_addend30) CUDA_OK(cudaMemcpyAsync(d_out30, d_addend30, 120, cudaMemcpyDeviceToDevice, st));
+        if (d_addend30) CUDA_OK(cudaMemcpyAsync(d_out30, d_addend30, PT_BYTES, cudaMemcpyDeviceToDevice, st));
         else GL(k_pt_fill_identity, 1, 1, d_out30, (size_t)1);
         CUDA_OK(cudaStreamSynchronize(st));
         return BPPP_OK;
     }
     if (n <= 1024) {
         uint32_t *a = nullptr, *b = nullptr, *res = nullptr;
-        CUDA_OK(cudaMalloc(&a, 120 * (n + 1)));
-        CUDA_OK(cudaMalloc(&b, 120 * (n / 16 + 2)));
+        CUDA_OK(cudaMalloc(&a, PT_BYTES * (n + 1)));
+        CUDA_OK(cudaMalloc(&b, PT_BYTES * (n / 16 + 2)));
         GL(k_msm_small, nblocks(n, 64), 64, d_pts, d_sc, n, a);
         size_t count = n;
-        if (d_addend30) { CUDA_OK(cudaMemcpyAsync(a + 30 * n, d_addend30, 120, cudaMemcpyDeviceToDevice, st)); count = n + 1; }
+        if (d_addend30) { CUDA_OK(cudaMemcpyAsync(a + PT_W * n, d_addend30, PT_BYTES, cudaMemcpyDeviceToDevice, st)); count = n + 1; }
         tree_sum(st, a, b, count, &res);
-        CUDA_OK(cudaMemcpyAsync(d_out30, res, 120, cudaMemcpyDeviceToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(d_out30, res, PT_BYTES, cudaMemcpyDeviceToDevice, st));
         CUDA_OK(cudaStreamSynchronize(st));
         cudaFree(a); cudaFree(b);
         CUDA_OK(cudaGetLastError());
@@ -289,9 +289,9 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     // one cached slab per device, carved into the working arrays (cudaMalloc per call cost more than the kernels)
     Carver cv;
     size_t o_keys = cv.take(4 * total), o_vals = cv.take(4 * total), o_keys2 = cv.take(4 * total), o_vals2 = cv.take(4 * total);
-    size_t o_start = cv.take(4 * (size_t)nb), o_end = cv.take(4 * (size_t)nb), o_buckets = cv.take((size_t)120 * nb);
-    size_t o_heavy = cv.take(4 * (size_t)heavy_cap + 256), o_chunks = cv.take((size_t)120 * nwin * nchunks);
-    size_t o_tmp = cv.take((size_t)120 * ((size_t)nwin * nchunks / 16 + 2)), o_cub = cv.take(cub_bytes);
+    size_t o_start = cv.take(4 * (size_t)nb), o_end = cv.take(4 * (size_t)nb), o_buckets = cv.take((size_t)PT_BYTES * nb);
+    size_t o_heavy = cv.take(4 * (size_t)heavy_cap + 256), o_chunks = cv.take((size_t)PT_BYTES * nwin * nchunks);
+    size_t o_tmp = cv.take((size_t)PT_BYTES * ((size_t)nwin * nchunks / 16 + 2)), o_cub = cv.take(cub_bytes);
     uint8_t *slab = nullptr;
     int rc = scratch_reserve(cv.total, &slab);
     if (rc != BPPP_OK) return rc;
@@ -389,7 +389,7 @@ extern "C" int bppp_msm(int device, const uint8_t *points, int points_fmt, size_
     if (rc != BPPP_OK) return rc;
     rc = decode_scalars_to_device(st, scalars32, n_scalars, &d_sc);
     if (rc != BPPP_OK) { cudaFree(d_pts); return rc; }
-    CUDA_OK(cudaMalloc(&d_out, 120));
+    CUDA_OK(cudaMalloc(&d_out, PT_BYTES));
     rc = msm_device(st, d_pts, d_sc, n, nullptr, d_out);
     if (rc == BPPP_OK) rc = encode_points_from_device(st, d_out, 1, out_fmt, out);
     cudaFree(d_pts); cudaFree(d_sc); cudaFree(d_out);
@@ -422,7 +422,7 @@ extern "C" int bppp_msm_uploaded(int device, const void *points_handle, const vo
     int rc = pick_device(device);
     if (rc != BPPP_OK) return rc;
     uint32_t *d_out = nullptr;
-    CUDA_OK(cudaMalloc(&d_out, 120));
+    CUDA_OK(cudaMalloc(&d_out, PT_BYTES));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, nullptr);
     rc = msm_device(nullptr, (const uint32_t *)points_handle, (const uint32_t *)scalars_handle, n, nullptr, d_out);

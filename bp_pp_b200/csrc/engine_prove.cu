@@ -48,23 +48,23 @@ static int prove_part(bppp_ctx *c, cudaStream_t st, WS w, const uint64_t *d_x, c
     LAUNCH(c, k_p_load, g64, 64, w, d_x, d_blinds);
     // V = x g + s h_0  (reciprocal.rs:88-90)
     u64p_termmap_commit(tm.gen);
-    launch_msm_fixed(c, st, w, PL::FS, tm, 2, PL::PTS + 30 * PP_V);
-    launch_batch_inv(c, st, w, PL::PTS + 30 * PP_V + 20, PL::ZINV + 10 * PP_V);
+    launch_msm_fixed(c, st, w, PL::FS, tm, 2, PL::PTS + PT_W * PP_V);
+    launch_batch_inv(c, st, w, PL::PTS + PT_W * PP_V + 2 * FE_W, PL::ZINV + FE_W * PP_V);
     LAUNCH(c, k_p_phase1, g64, 64, w, init, d_rng);
     // r_com, c_o, c_l, c_r
     for (int k = 0; k < 4; k++) {
         int nterms = u64p_termmap_stage1(tm.gen, k);
-        launch_msm_fixed(c, st, w, PL::FS + 8 * u64p_stage1_scalar_base(k), tm, nterms, PL::PTS + 30 * u64p_stage1_point(k));
+        launch_msm_fixed(c, st, w, PL::FS + 8 * u64p_stage1_scalar_base(k), tm, nterms, PL::PTS + PT_W * u64p_stage1_point(k));
     }
     LAUNCH(c, k_p_vprime, g64, 64, w);
     for (int k = 0; k < 5; k++) {
         int p = u64p_stage1_norm_point(k);
-        launch_batch_inv(c, st, w, PL::PTS + 30 * p + 20, PL::ZINV + 10 * p);
+        launch_batch_inv(c, st, w, PL::PTS + PT_W * p + 2 * FE_W, PL::ZINV + FE_W * p);
     }
     LAUNCH(c, k_p_phase2, g64, 64, w, d_rng);
     u64p_termmap_cs(tm.gen);
-    launch_msm_fixed(c, st, w, PL::FS, tm, 42, PL::PTS + 30 * PP_CS);
-    launch_batch_inv(c, st, w, PL::PTS + 30 * PP_CS + 20, PL::ZINV + 10 * PP_CS);
+    launch_msm_fixed(c, st, w, PL::FS, tm, 42, PL::PTS + PT_W * PP_CS);
+    launch_batch_inv(c, st, w, PL::PTS + PT_W * PP_CS + 2 * FE_W, PL::ZINV + FE_W * PP_CS);
     LAUNCH(c, k_p_phase3, g64, 64, w);
     // C_0 = v g + <h, l> + <g_vec, n>  (circuit.rs:522-524): 43 terms
     u64p_termmap_c0(tm.gen);
@@ -72,12 +72,12 @@ static int prove_part(bppp_ctx *c, cudaStream_t st, WS w, const uint64_t *d_x, c
     for (int j = 0; j < 4; j++) {
         // X_j (49 terms), R_j (25 terms) over the original generators
         TermMap all = identity_map();
-        launch_msm_fixed(c, st, w, PL::XS, all, NUM_GENS, PL::PTS + 30 * (PP_X + j));
+        launch_msm_fixed(c, st, w, PL::XS, all, NUM_GENS, PL::PTS + PT_W * (PP_X + j));
         u64p_termmap_r(tm.gen, j);
-        launch_msm_fixed(c, st, w, PL::RS, tm, 25, PL::PTS + 30 * (PP_R + j));
-        launch_batch_inv(c, st, w, PL::COM + 20, PL::ZINV + 10 * PP_COM);
-        launch_batch_inv(c, st, w, PL::PTS + 30 * (PP_X + j) + 20, PL::ZINV + 10 * (PP_X + j));
-        launch_batch_inv(c, st, w, PL::PTS + 30 * (PP_R + j) + 20, PL::ZINV + 10 * (PP_R + j));
+        launch_msm_fixed(c, st, w, PL::RS, tm, 25, PL::PTS + PT_W * (PP_R + j));
+        launch_batch_inv(c, st, w, PL::COM + 2 * FE_W, PL::ZINV + FE_W * PP_COM);
+        launch_batch_inv(c, st, w, PL::PTS + PT_W * (PP_X + j) + 2 * FE_W, PL::ZINV + FE_W * (PP_X + j));
+        launch_batch_inv(c, st, w, PL::PTS + PT_W * (PP_R + j) + 2 * FE_W, PL::ZINV + FE_W * (PP_R + j));
         LAUNCH(c, k_p_round, g64, 64, w, j);
         if (j < 3) launch_p_var2(c, st, w, j);
     }

@@ -64,7 +64,7 @@ static int verify_part(bppp_ctx *c, cudaStream_t st, WS w, const uint8_t *d_comm
     CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n, st));
     LAUNCH(c, k_v_decode, nblocks(n * 16, 128), 128, w, d_commits, d_proofs, fmt, flags);
     LAUNCH(c, k_v_load_finish, g64, 64, w, d_proofs, fmt, flags);
-    launch_batch_inv(c, st, w, VL::VP + 20, VL::ZINV);
+    launch_batch_inv(c, st, w, VL::VP + 2 * FE_W, VL::ZINV);
     LAUNCH(c, k_v_phase1, g64, 64, w, init);
     {   // affine 1P..8P tables of the 13 per-proof points: one batch inversion serves all 104 entries of every proof
         LAUNCH(c, k_v_tables_build, nblocks(n * 16, 64), 64, w);
@@ -75,7 +75,7 @@ static int verify_part(bppp_ctx *c, cudaStream_t st, WS w, const uint8_t *d_comm
     launch_msm_fixed(c, st, w, VL::FS, tm, 17, VL::ACC);      // pt = ps_tau g + <g_vec, pn_tau>  (circuit.rs:206)
     launch_v_var5(c, st, w);
     for (int j = 0; j < 4; j++) {
-        launch_batch_inv(c, st, w, VL::COM + 20, VL::ZINV);
+        launch_batch_inv(c, st, w, VL::COM + 2 * FE_W, VL::ZINV);
         LAUNCH(c, k_v_round, g64, 64, w, j);
         launch_v_var2(c, st, w, j);
     }

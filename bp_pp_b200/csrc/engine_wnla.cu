@@ -36,11 +36,11 @@ __device__ __forceinline__ void st_sc8(uint32_t *p, const Sc &a) {
     for (int k = 0; k < 8; k++) p[k] = a.v[k]; }
 __device__ __forceinline__ Pt ld_pt30g(const uint32_t *p) { Pt r;
 #pragma unroll
-    for (int k = 0; k < 10; k++) { r.x.n[k] = p[k]; r.y.n[k] = p[10 + k]; r.z.n[k] = p[20 + k]; }
+    for (int k = 0; k < FE_W; k++) { r.x.v[k] = p[k]; r.y.v[k] = p[FE_W + k]; r.z.v[k] = p[2 * FE_W + k]; }
     return r; }
 __device__ __forceinline__ void st_pt30g(uint32_t *p, const Pt &a) {
 #pragma unroll
-    for (int k = 0; k < 10; k++) { p[k] = a.x.n[k]; p[10 + k] = a.y.n[k]; p[20 + k] = a.z.n[k]; } }
+    for (int k = 0; k < FE_W; k++) { p[k] = a.x.v[k]; p[FE_W + k] = a.y.v[k]; p[2 * FE_W + k] = a.z.v[k]; } }
 __device__ __forceinline__ bool ld_pta16(PtA &q, const uint32_t *pts, size_t idx) {
     uint32_t x[8], y[8], any = 0;
 #pragma unroll
@@ -281,7 +281,7 @@ int wnla_prove_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, ui
                    int32_t *status) {
     std::vector<std::vector<uint8_t>> rs, xs;
     uint32_t *d_x30 = nullptr, *d_r30 = nullptr, *d_three = nullptr;
-    CUDA_OK(cudaMalloc(&d_x30, 120)); CUDA_OK(cudaMalloc(&d_r30, 120)); CUDA_OK(cudaMalloc(&d_three, 360));
+    CUDA_OK(cudaMalloc(&d_x30, PT_BYTES)); CUDA_OK(cudaMalloc(&d_r30, PT_BYTES)); CUDA_OK(cudaMalloc(&d_three, 3 * PT_BYTES));
     int rc = BPPP_OK;
     bool first_round = true;
     while (len_l + len_n >= 6) {     // wnla.rs:126
@@ -305,9 +305,9 @@ int wnla_prove_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, ui
         rc = msm_device(st, w.pts, d_sr, Lt, nullptr, d_r30); if (rc != BPPP_OK) break;
         cudaFree(d_sx); cudaFree(d_sr); cudaFree(d_part);
         // transcript (wnla.rs:162-168)
-        CUDA_OK(cudaMemcpyAsync(d_three, d_com30, 120, cudaMemcpyDeviceToDevice, st));
-        CUDA_OK(cudaMemcpyAsync(d_three + 30, d_x30, 120, cudaMemcpyDeviceToDevice, st));
-        CUDA_OK(cudaMemcpyAsync(d_three + 60, d_r30, 120, cudaMemcpyDeviceToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(d_three, d_com30, PT_BYTES, cudaMemcpyDeviceToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(d_three + PT_W, d_x30, PT_BYTES, cudaMemcpyDeviceToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(d_three + 2 * PT_W, d_r30, PT_BYTES, cudaMemcpyDeviceToDevice, st));
         uint8_t b[99];
         rc = encode_points_from_device(st, d_three, 3, FMT_COMPRESSED, b); if (rc != BPPP_OK) break;
         host_append_point33(t, BPPP_LBL("wnla_com"), b);
@@ -372,7 +372,7 @@ int wnla_verify_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, c
     rc = decode_scalars_to_device(st, l32, ln, &d_l);
     if (rc == BPPP_OK) rc = decode_scalars_to_device(st, n32, nn, &d_n);
     if (rc != BPPP_OK) { cudaFree(d_xr); cudaFree(d_l); *verdict = ST_BAD_SCALAR; return BPPP_OK; }
-    CUDA_OK(cudaMalloc(&d_x30, 120)); CUDA_OK(cudaMalloc(&d_r30, 120));
+    CUDA_OK(cudaMalloc(&d_x30, PT_BYTES)); CUDA_OK(cudaMalloc(&d_r30, PT_BYTES));
     std::vector<Sc> ys(R), rhos(R);
     Sc rho = w.rho, mu = w.mu;
     size_t len_h = w.len_h, len_g = w.len_g;
@@ -401,7 +401,7 @@ int wnla_verify_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, c
         uint32_t *d_sc = nullptr, *d_cl = nullptr, *d_part = nullptr, *d_f30 = nullptr;
         CUDA_OK(cudaMalloc(&d_sc, 32 * Lt)); CUDA_OK(cudaMalloc(&d_cl, 32 * (Lh ? Lh : 1)));
         CUDA_OK(cudaMalloc(&d_ys, 32 * (size_t)(R ? R : 1))); CUDA_OK(cudaMalloc(&d_rhos, 32 * (size_t)(R ? R : 1)));
-        CUDA_OK(cudaMalloc(&d_f30, 120));
+        CUDA_OK(cudaMalloc(&d_f30, PT_BYTES));
         if (R) { CUDA_OK(cudaMemcpyAsync(d_ys, ys.data(), 32 * (size_t)R, cudaMemcpyHostToDevice, st)); CUDA_OK(cudaMemcpyAsync(d_rhos, rhos.data(), 32 * (size_t)R, cudaMemcpyHostToDevice, st)); }
         WL(k_wnla_final_scalars, nblocks(Lh + Lg, 128), 128, Lh, Lg, R, d_ys, d_rhos, d_l, ln, d_n, nn, w.c, Lh, d_sc, d_cl);
         size_t nblk = (Lh + 127) / 128;
@@ -462,7 +462,7 @@ extern "C" int bppp_wnla_commit(int device, const uint8_t *g64, const uint8_t *g
     uint32_t *d_l = nullptr, *d_n = nullptr, *d_out = nullptr;
     rc = upload_padded_scalars(st, l32, ln, w.Lh, &d_l);
     if (rc == BPPP_OK) rc = upload_padded_scalars(st, n32, nn, w.Lg, &d_n);
-    if (rc == BPPP_OK) { CUDA_OK(cudaMalloc(&d_out, 120)); rc = wnla_commit_dev(st, w, d_l, d_n, d_out); }
+    if (rc == BPPP_OK) { CUDA_OK(cudaMalloc(&d_out, PT_BYTES)); rc = wnla_commit_dev(st, w, d_l, d_n, d_out); }
     if (rc == BPPP_OK) rc = encode_points_from_device(st, d_out, 1, FMT_COMPRESSED, out33);
     cudaFree(d_l); cudaFree(d_n); cudaFree(d_out); w.release();
     return rc;
@@ -484,7 +484,7 @@ extern "C" int bppp_wnla_prove(int device, const uint8_t *g64, const uint8_t *gv
     if (rc == BPPP_OK) rc = upload_padded_scalars(st, n32, nn, w.Lg, &d_n);
     if (rc == BPPP_OK) rc = decode_points_to_device(st, commit33, FMT_COMPRESSED, 1, &d_com16);
     if (rc != BPPP_OK) { cudaFree(d_l); cudaFree(d_n); w.release(); return rc; }
-    CUDA_OK(cudaMalloc(&d_com30, 120));
+    CUDA_OK(cudaMalloc(&d_com30, PT_BYTES));
     k_decode_one_point30<<<1, 1, 0, st>>>(d_com16, d_com30);
     Merlin t; merlin_init(t, label, (uint32_t)label_len);
     WnlaProofHost proof;
@@ -512,7 +512,7 @@ extern "C" int bppp_wnla_verify(int device, const uint8_t *g64, const uint8_t *g
     uint32_t *d_com16 = nullptr, *d_com30 = nullptr;
     rc = decode_points_to_device(st, commit33, FMT_COMPRESSED, 1, &d_com16);
     if (rc != BPPP_OK) { w.release(); *verdict = ST_BAD_POINT; return BPPP_OK; }
-    CUDA_OK(cudaMalloc(&d_com30, 120));
+    CUDA_OK(cudaMalloc(&d_com30, PT_BYTES));
     k_decode_one_point30<<<1, 1, 0, st>>>(d_com16, d_com30);
     Merlin t; merlin_init(t, label, (uint32_t)label_len);
     rc = wnla_verify_dev(st, w, t, d_com30, r33, rn, x33, xn, l32, ln, n32, nn, verdict);

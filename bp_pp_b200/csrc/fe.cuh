@@ -1,12 +1,19 @@
 // secp256k1 base field F_p, p = 2^256 - 2^32 - 977, for sm_100a.
 //
-// Representation: 10 limbs of 26 bits held in 32-bit registers, lazily reduced.
-//   value = sum n[i] * 2^(26 i)   (any representative mod p)
-// "Magnitude" m bounds the limbs: n[i] <= 2m(2^26-1) for i<9, n[9] <= 2m(2^22-1).
-// fe_mul/fe_sqr accept magnitudes with ma*mb <= 64 and return magnitude 1; add/negate/mul_int
-// are carry-free limb-wise operations that only grow the magnitude.  The product columns are
-// 64-bit sums of 32x32->64 multiply-accumulates (IMAD.WIDE.U32 on the FMA pipe, 64-bit
-// accumulate for free) so there is no carry chain on the ALU pipe inside the product.
+// Representation: 8 saturated 32-bit limbs, little-endian, value = sum v[i] * 2^(32 i) < 2^256 -- ANY representative
+// mod p in that range (p .. 2^256-1 is allowed); only fe_normalize produces the canonical one.  Every operation returns
+// a value below 2^256, so there is no magnitude bookkeeping: the `m` arguments of fe_negate / fe_sub are kept for source
+// compatibility and ignored.
+//
+// Multiplication is the 8x8 schoolbook product on IMAD.WIDE.U32 with hardware carry chains (PTX mad.lo.cc / madc.hi.cc
+// pairs, which ptxas fuses into one IMAD.WIDE.U32[.X] with a carry predicate): the products of one row that start at
+// even limb positions tile an accumulator without overlap, the odd ones a second accumulator, so a row is two
+// independent carry chains of four wide MADs.  64 wide MADs + 9 for the reduction (2^256 = 2^32 + 977 mod p) and ~65
+// adds: 138 SASS instructions per fe_mul, against 298 (113 wide MADs) for the earlier 10 x 26-bit lazy representation;
+// measured 82-105 G fe_mul/s on a B200 against 46.6 G (profiles/r1_fe_representation.txt).
+//
+// Host builds (tests/hostemu) compile the portable branches below; they mirror the device steps one to one (same folds,
+// same rare-carry handling) and assert the bounds each step relies on when BPPP_VERIFY_MAG is defined.
 //
 // This replaces k256::FieldElement (not in /root/reference; Cargo.lock:411-414) on the device.
 // The internal representation is unobservable; only canonical bytes leave the device.
@@ -21,320 +28,428 @@
 #define BPPP_D inline
 #endif
 
-// Host-side verification build (tests/hostemu): every Fe carries exact upper bounds on its limbs
-// (lim for n[0..8], lim9 for n[9]) and every operation asserts its preconditions on them, so the
-// lazy-reduction discipline of the point formulas is machine-checked on each test run.
 #if defined(BPPP_VERIFY_MAG)
 #include <assert.h>
-#define BPPP_MAG_FIELD uint64_t lim, lim9;
-#define BPPP_SET_MAG(r, m) ((r).lim = 2ull * (uint64_t)(m) * 0x3FFFFFFull, (r).lim9 = 2ull * (uint64_t)(m) * 0x3FFFFFull)
-#define BPPP_SET_LIM(r, l, l9) ((r).lim = (l), (r).lim9 = (l9))
 #define BPPP_ASSERT(c) assert(c)
 #else
-#define BPPP_MAG_FIELD
-#define BPPP_SET_MAG(r, m) ((void)0)
-#define BPPP_SET_LIM(r, l, l9) ((void)0)
 #define BPPP_ASSERT(c) ((void)0)
 #endif
+// magnitude bookkeeping of the earlier lazy representation: nothing to track any more
+#define BPPP_SET_MAG(r, m) ((void)0)
+#define BPPP_SET_LIM(r, l, l9) ((void)0)
 
 // A translation unit may define BPPP_FE_NOINLINE: fe_mul / fe_sqr then compile to real device functions taking
-// their operands BY VALUE (nvcc passes the 10-word structs in registers, ~15 MOVs per call, no stack traffic).
-// Fully inlined point formulas are ~100 KB of SASS per ladder step and thrash the instruction cache
-// (ncu on k_v_var2: stall_no_instruction 5.4 warps per issue); with calls the hot loop is < 10 KB.
+// their operands BY VALUE (nvcc passes the 8-word structs in registers, no stack traffic).  Fully inlined point
+// formulas thrash the instruction cache (ncu on k_v_var2: stall_no_instruction 5.4 warps per issue); with calls
+// the hot loop is a few KB.
 
 namespace bppp {
 
+static constexpr int FE_W = 8;          // 32-bit words per field element (registers and workspace)
+static constexpr int PT_W = 3 * FE_W;   // projective / Jacobian point
+
 struct Fe {
-    uint32_t n[10];
-    BPPP_MAG_FIELD
+    uint32_t v[8];
 };
 
-static constexpr uint32_t FE_M26 = 0x3FFFFFFu;
-static constexpr uint32_t FE_M22 = 0x3FFFFFu;
-// 2^260 = R0 + R1 * 2^26 (mod p);  2^256 = 977 + 64 * 2^26 (mod p)
-static constexpr uint32_t FE_R0 = 0x3D10u;
-static constexpr uint32_t FE_R1 = 0x400u;
+static constexpr uint32_t FE_C0 = 977u;           // 2^256 = 2^32 + 977 (mod p)
+static constexpr uint32_t FE_P0 = 0xFFFFFC2Fu;    // p = {P0, P1, ~0 x 6}
+static constexpr uint32_t FE_P1 = 0xFFFFFFFEu;
 
-#if defined(BPPP_VERIFY_MAG)
-inline void fe_check(const Fe &a) {
-    for (int i = 0; i < 9; i++) assert((uint64_t)a.n[i] <= a.lim);
-    assert((uint64_t)a.n[9] <= a.lim9);
-    assert(a.lim <= 0xFFFFFFFFull && a.lim9 <= 0xFFFFFFFFull);   // bounds themselves must fit a 32-bit limb
-}
-#else
 BPPP_HD void fe_check(const Fe &) {}
-#endif
 
 BPPP_HD Fe fe_zero() {
     Fe r;
 #pragma unroll
-    for (int i = 0; i < 10; i++) r.n[i] = 0;
-    BPPP_SET_MAG(r, 0);
+    for (int i = 0; i < 8; i++) r.v[i] = 0;
     return r;
 }
-BPPP_HD Fe fe_from_u32(uint32_t x) {  // x < 2^26
+BPPP_HD Fe fe_from_u32(uint32_t x) {
     Fe r = fe_zero();
-    r.n[0] = x;
-    BPPP_SET_MAG(r, 1);
+    r.v[0] = x;
     return r;
 }
 BPPP_HD Fe fe_one() { return fe_from_u32(1); }
 
-// 8 x u32 little-endian words (a canonical or any 256-bit integer) -> Fe, magnitude 1
+// 8 x u32 little-endian words (any 256-bit integer) -> Fe
 BPPP_HD Fe fe_from_words(const uint32_t w[8]) {
     Fe r;
-    r.n[0] = w[0] & FE_M26;
-    r.n[1] = ((w[0] >> 26) | (w[1] << 6)) & FE_M26;
-    r.n[2] = ((w[1] >> 20) | (w[2] << 12)) & FE_M26;
-    r.n[3] = ((w[2] >> 14) | (w[3] << 18)) & FE_M26;
-    r.n[4] = ((w[3] >> 8) | (w[4] << 24)) & FE_M26;
-    r.n[5] = (w[4] >> 2) & FE_M26;
-    r.n[6] = ((w[4] >> 28) | (w[5] << 4)) & FE_M26;
-    r.n[7] = ((w[5] >> 22) | (w[6] << 10)) & FE_M26;
-    r.n[8] = ((w[6] >> 16) | (w[7] << 16)) & FE_M26;
-    r.n[9] = w[7] >> 10;
-    BPPP_SET_MAG(r, 1);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = w[i];
     return r;
 }
+BPPP_HD Fe fe_normalize_weak(const Fe &a) { return a; }
 
-// weak normalisation: any magnitude <= 32 -> magnitude 1 (limbs < 2^26 except a small excess in n[0..1])
-BPPP_HD Fe fe_normalize_weak(const Fe &a) {
-    fe_check(a);
-#if defined(BPPP_VERIFY_MAG)
-    assert(a.lim + (a.lim9 >> 22) * 977ull + 64 <= 0xFFFFFFFFull);   // no 32-bit overflow in the carry pass
+// r = a + b * (2^32 + 977) for b in {0, 1}; returns the carry out of 2^256
+BPPP_HD uint32_t fe_add_fold(Fe &r, uint32_t b) {
+    uint32_t c;
+#if defined(__CUDA_ARCH__)
+    asm volatile("mad.lo.cc.u32 %0, %9, 977, %0;\n\t addc.cc.u32 %1, %1, %9;\n\t addc.cc.u32 %2, %2, 0;\n\t addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t addc.cc.u32 %5, %5, 0;\n\t addc.cc.u32 %6, %6, 0;\n\t addc.cc.u32 %7, %7, 0;\n\t addc.u32 %8, 0, 0;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "=r"(c)
+        : "r"(b));
+#else
+    uint64_t t = (uint64_t)r.v[0] + (uint64_t)b * FE_C0; r.v[0] = (uint32_t)t;
+    t = (t >> 32) + r.v[1] + b; r.v[1] = (uint32_t)t;
+    for (int i = 2; i < 8; i++) { t = (t >> 32) + r.v[i]; r.v[i] = (uint32_t)t; }
+    c = (uint32_t)(t >> 32);
 #endif
-    Fe r;
-    uint32_t x = a.n[9] >> 22;
-    uint32_t t9 = a.n[9] & FE_M22;
-    uint32_t t = a.n[0] + x * 977u;
-    uint32_t c = t >> 26; r.n[0] = t & FE_M26;
-    t = a.n[1] + (x << 6) + c; c = t >> 26; r.n[1] = t & FE_M26;
-#pragma unroll
-    for (int i = 2; i < 9; i++) { t = a.n[i] + c; c = t >> 26; r.n[i] = t & FE_M26; }
-    r.n[9] = t9 + c;
-    BPPP_SET_LIM(r, 0x3FFFFFFull, 0x3FFFFFull + 64);
-    fe_check(r);
-    return r;
+    return c;
+}
+// after a wrap past 2^256 the residue is below 2^68: adding 2^32 + 977 once more cannot carry past limb 2
+BPPP_HD void fe_add_fold_low(Fe &r, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("mad.lo.cc.u32 %0, %3, 977, %0;\n\t addc.cc.u32 %1, %1, %3;\n\t addc.u32 %2, %2, 0;" : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]) : "r"(b));
+#else
+    if (b) { BPPP_ASSERT((r.v[3] | r.v[4] | r.v[5] | r.v[6] | r.v[7]) == 0 && r.v[2] < 16); }
+    uint64_t t = (uint64_t)r.v[0] + (uint64_t)b * FE_C0; r.v[0] = (uint32_t)t;
+    t = (t >> 32) + r.v[1] + b; r.v[1] = (uint32_t)t;
+    t = (t >> 32) + r.v[2]; r.v[2] = (uint32_t)t;
+    BPPP_ASSERT((t >> 32) == 0);
+#endif
 }
 
-// full normalisation to the canonical representative in [0, p)
+// canonical representative in [0, p):  v >= p  <=>  v + (2^32 + 977) carries out of 2^256, and then v - p is that sum
 BPPP_HD Fe fe_normalize(const Fe &a) {
-    Fe r = fe_normalize_weak(a);
-    // after the weak pass: value < 2^256 + small.  One more fold of bit 256 and a final conditional -p.
-    uint32_t x = r.n[9] >> 22;
-    r.n[9] &= FE_M22;
-    uint32_t t = r.n[0] + x * 977u, c = t >> 26; r.n[0] = t & FE_M26;
-    t = r.n[1] + (x << 6) + c; c = t >> 26; r.n[1] = t & FE_M26;
+    Fe t = a;
+    uint32_t c = fe_add_fold(t, 1u);
+    Fe r;
 #pragma unroll
-    for (int i = 2; i < 10; i++) { t = r.n[i] + c; c = t >> 26; r.n[i] = t & FE_M26; }
-    // now r < 2^256 (n[9] may be exactly 2^22 only if everything below overflowed; fold once more)
-    x = r.n[9] >> 22;
-    r.n[9] &= FE_M22;
-    t = r.n[0] + x * 977u; c = t >> 26; r.n[0] = t & FE_M26;
-    t = r.n[1] + (x << 6) + c; c = t >> 26; r.n[1] = t & FE_M26;
-#pragma unroll
-    for (int i = 2; i < 10; i++) { t = r.n[i] + c; c = t >> 26; r.n[i] = t & FE_M26; }
-    // r in [0, 2^256): subtract p if r >= p.  r >= p  <=>  n[9]==M22, n[2..8]==M26, and (n[1],n[0]) >= (0x3FFFFBF, 0x3FFFC2F)
-    uint32_t m = r.n[9] ^ FE_M22;
-#pragma unroll
-    for (int i = 2; i < 9; i++) m |= r.n[i] ^ FE_M26;
-    bool ge = (m == 0) && ((r.n[1] > 0x3FFFFBFu) || (r.n[1] == 0x3FFFFBFu && r.n[0] >= 0x3FFFC2Fu));
-    if (ge) {
-        // r - p = r + (2^32 + 977) - 2^256
-        t = r.n[0] + 977u; c = t >> 26; r.n[0] = t & FE_M26;
-        t = r.n[1] + 64u + c; c = t >> 26; r.n[1] = t & FE_M26;
-#pragma unroll
-        for (int i = 2; i < 9; i++) { t = r.n[i] + c; c = t >> 26; r.n[i] = t & FE_M26; }
-        r.n[9] = (r.n[9] + c) & FE_M22;
-    }
-    BPPP_SET_MAG(r, 1);
+    for (int i = 0; i < 8; i++) r.v[i] = c ? t.v[i] : a.v[i];
     return r;
 }
 
 // canonical Fe -> 8 x u32 little-endian words
 BPPP_HD void fe_to_words(uint32_t w[8], const Fe &a_canonical) {
-    const uint32_t *n = a_canonical.n;
-    w[0] = n[0] | (n[1] << 26);
-    w[1] = (n[1] >> 6) | (n[2] << 20);
-    w[2] = (n[2] >> 12) | (n[3] << 14);
-    w[3] = (n[3] >> 18) | (n[4] << 8);
-    w[4] = (n[4] >> 24) | (n[5] << 2) | (n[6] << 28);
-    w[5] = (n[6] >> 4) | (n[7] << 22);
-    w[6] = (n[7] >> 10) | (n[8] << 16);
-    w[7] = (n[8] >> 16) | (n[9] << 10);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = a_canonical.v[i];
 }
 
 BPPP_HD bool fe_is_zero_canonical(const Fe &a) {
     uint32_t m = 0;
 #pragma unroll
-    for (int i = 0; i < 10; i++) m |= a.n[i];
+    for (int i = 0; i < 8; i++) m |= a.v[i];
     return m == 0;
 }
-BPPP_HD bool fe_is_zero(const Fe &a) { return fe_is_zero_canonical(fe_normalize(a)); }
-// value == 0 (mod p) for a lazily reduced element, without the full normalisation: after one weak pass the value is
-// below 2^256 + 2^235, so it is a multiple of p only if it is exactly 0 or exactly p
+// value == 0 (mod p): the only multiples of p below 2^256 are 0 and p
 BPPP_HD bool fe_normalizes_to_zero(const Fe &a) {
-    Fe t = fe_normalize_weak(a);
-    uint32_t z = t.n[0] | t.n[1] | t.n[9];
-    uint32_t pm = (t.n[0] ^ 0x3FFFC2Fu) | (t.n[1] ^ 0x3FFFFBFu) | (t.n[9] ^ FE_M22);
+    uint32_t z = a.v[0] | a.v[1], pm = (a.v[0] ^ FE_P0) | (a.v[1] ^ FE_P1);
 #pragma unroll
-    for (int i = 2; i < 9; i++) { z |= t.n[i]; pm |= t.n[i] ^ FE_M26; }
+    for (int i = 2; i < 8; i++) { z |= a.v[i]; pm |= ~a.v[i]; }
     return z == 0 || pm == 0;
 }
+BPPP_HD bool fe_is_zero(const Fe &a) { return fe_normalizes_to_zero(a); }
 BPPP_HD bool fe_equal_canonical(const Fe &a, const Fe &b) {
     uint32_t m = 0;
 #pragma unroll
-    for (int i = 0; i < 10; i++) m |= a.n[i] ^ b.n[i];
+    for (int i = 0; i < 8; i++) m |= a.v[i] ^ b.v[i];
     return m == 0;
 }
-BPPP_HD bool fe_is_odd_canonical(const Fe &a) { return a.n[0] & 1u; }
+BPPP_HD bool fe_is_odd_canonical(const Fe &a) { return a.v[0] & 1u; }
 
 BPPP_HD Fe fe_add(const Fe &a, const Fe &b) {
     Fe r;
-#pragma unroll
-    for (int i = 0; i < 10; i++) r.n[i] = a.n[i] + b.n[i];
-#if defined(BPPP_VERIFY_MAG)
-    r.lim = a.lim + b.lim; r.lim9 = a.lim9 + b.lim9;
+    uint32_t c;
+#if defined(__CUDA_ARCH__)
+    asm volatile("add.cc.u32 %0, %9, %17;\n\t addc.cc.u32 %1, %10, %18;\n\t addc.cc.u32 %2, %11, %19;\n\t addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t addc.cc.u32 %5, %14, %22;\n\t addc.cc.u32 %6, %15, %23;\n\t addc.cc.u32 %7, %16, %24;\n\t addc.u32 %8, 0, 0;"
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]), "=&r"(r.v[7]), "=&r"(c)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+#else
+    uint64_t t = 0;
+    for (int i = 0; i < 8; i++) { t = (t >> 32) + a.v[i] + b.v[i]; r.v[i] = (uint32_t)t; }
+    c = (uint32_t)(t >> 32);
 #endif
-    fe_check(r);
+    // a + b - 2^256 + (2^32 + 977); a second wrap needs a, b both in [p, 2^256) and then leaves a residue < 2^34
+    uint32_t c2 = fe_add_fold(r, c);
+    fe_add_fold_low(r, c2);
     return r;
 }
-// -a for a of magnitude <= m; result magnitude m+1
-BPPP_HD Fe fe_negate(const Fe &a, int m) {
+
+// a - b (the magnitude argument of the lazy representation is ignored)
+BPPP_HD Fe fe_sub(const Fe &a, const Fe &b, int = 0) {
     Fe r;
-    const uint32_t k = 2u * (uint32_t)(m + 1);
-#if defined(BPPP_VERIFY_MAG)
-    assert(a.lim <= (uint64_t)k * 0x3FFFC2Full && a.lim9 <= (uint64_t)k * 0x3FFFFFull && k <= 64);
+    uint32_t bw;   // 0 or 1
+#if defined(__CUDA_ARCH__)
+    asm volatile("sub.cc.u32 %0, %9, %17;\n\t subc.cc.u32 %1, %10, %18;\n\t subc.cc.u32 %2, %11, %19;\n\t subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t subc.cc.u32 %5, %14, %22;\n\t subc.cc.u32 %6, %15, %23;\n\t subc.cc.u32 %7, %16, %24;\n\t subc.u32 %8, 0, 0;"
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]), "=&r"(r.v[7]), "=&r"(bw)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    bw &= 1u;   // subc yields 0 - 0 - borrow = 0 or 0xFFFFFFFF
+    // borrowed: r = a - b + 2^256, subtract 2^32 + 977 to make it a - b + p
+    uint32_t k0 = bw * FE_C0, bw2;
+    asm volatile("sub.cc.u32 %0, %0, %9;\n\t subc.cc.u32 %1, %1, %10;\n\t subc.cc.u32 %2, %2, 0;\n\t subc.cc.u32 %3, %3, 0;\n\t"
+        "subc.cc.u32 %4, %4, 0;\n\t subc.cc.u32 %5, %5, 0;\n\t subc.cc.u32 %6, %6, 0;\n\t subc.cc.u32 %7, %7, 0;\n\t subc.u32 %8, 0, 0;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "=r"(bw2)
+        : "r"(k0), "r"(bw));
+    bw2 &= 1u;
+    // second borrow (a - b + 2^256 < 2^32 + 977, i.e. b > a + p): r is now within 2^34 of 2^256, subtract once more;
+    // only the low three limbs can change
+    uint32_t k2 = bw2 * FE_C0;
+    asm volatile("sub.cc.u32 %0, %0, %3;\n\t subc.cc.u32 %1, %1, %4;\n\t subc.u32 %2, %2, 0;" : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]) : "r"(k2), "r"(bw2));
+#else
+    int64_t t = 0;
+    for (int i = 0; i < 8; i++) { t = (int64_t)a.v[i] - b.v[i] + (t >> 32); r.v[i] = (uint32_t)t; }
+    bw = (uint32_t)((t >> 32) & 1);
+    t = (int64_t)r.v[0] - (int64_t)(bw * FE_C0); r.v[0] = (uint32_t)t;
+    t = (int64_t)r.v[1] - bw + (t >> 32); r.v[1] = (uint32_t)t;
+    for (int i = 2; i < 8; i++) { t = (int64_t)r.v[i] + (t >> 32); r.v[i] = (uint32_t)t; }
+    uint32_t bw2 = (uint32_t)((t >> 32) & 1);
+    if (bw2) { BPPP_ASSERT((r.v[3] & r.v[4] & r.v[5] & r.v[6] & r.v[7]) == 0xFFFFFFFFu && r.v[2] >= 0xFFFFFFF0u); }
+    t = (int64_t)r.v[0] - (int64_t)(bw2 * FE_C0); r.v[0] = (uint32_t)t;
+    t = (int64_t)r.v[1] - bw2 + (t >> 32); r.v[1] = (uint32_t)t;
+    t = (int64_t)r.v[2] + (t >> 32); r.v[2] = (uint32_t)t;
+    BPPP_ASSERT((t >> 32) == 0);
 #endif
-    r.n[0] = 0x3FFFC2Fu * k - a.n[0];
-    r.n[1] = 0x3FFFFBFu * k - a.n[1];
-#pragma unroll
-    for (int i = 2; i < 9; i++) r.n[i] = FE_M26 * k - a.n[i];
-    r.n[9] = FE_M22 * k - a.n[9];
-    BPPP_SET_LIM(r, (uint64_t)k * 0x3FFFFFFull, (uint64_t)k * 0x3FFFFFull);
-    fe_check(r);
     return r;
 }
-// a - b for b of magnitude <= mb; result magnitude mag(a) + mb + 1
-BPPP_HD Fe fe_sub(const Fe &a, const Fe &b, int mb) { return fe_add(a, fe_negate(b, mb)); }
+BPPP_HD Fe fe_negate(const Fe &a, int = 0) { return fe_sub(fe_zero(), a); }
+
+// a * k for a small constant k (k * 977 must fit 32 bits)
 BPPP_HD Fe fe_mul_int(const Fe &a, uint32_t k) {
     Fe r;
-#pragma unroll
-    for (int i = 0; i < 10; i++) r.n[i] = a.n[i] * k;
-#if defined(BPPP_VERIFY_MAG)
-    r.lim = a.lim * k; r.lim9 = a.lim9 * k;
+    uint32_t top;
+#if defined(__CUDA_ARCH__)
+    asm volatile("mul.lo.u32 %0, %9, %17;\n\t mul.hi.u32 %1, %9, %17;\n\t mul.lo.u32 %2, %11, %17;\n\t mul.hi.u32 %3, %11, %17;\n\t"
+        "mul.lo.u32 %4, %13, %17;\n\t mul.hi.u32 %5, %13, %17;\n\t mul.lo.u32 %6, %15, %17;\n\t mul.hi.u32 %7, %15, %17;\n\t"
+        "mad.lo.cc.u32 %1, %10, %17, %1;\n\t madc.hi.cc.u32 %2, %10, %17, %2;\n\t madc.lo.cc.u32 %3, %12, %17, %3;\n\t madc.hi.cc.u32 %4, %12, %17, %4;\n\t"
+        "madc.lo.cc.u32 %5, %14, %17, %5;\n\t madc.hi.cc.u32 %6, %14, %17, %6;\n\t madc.lo.cc.u32 %7, %16, %17, %7;\n\t madc.hi.u32 %8, %16, %17, 0;"
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]), "=&r"(r.v[7]), "=&r"(top)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]), "r"(k));
+    // fold top (< k): r += top * (2^32 + 977)
+    uint32_t c;
+    asm volatile("mad.lo.cc.u32 %0, %9, 977, %0;\n\t addc.cc.u32 %1, %1, %9;\n\t addc.cc.u32 %2, %2, 0;\n\t addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t addc.cc.u32 %5, %5, 0;\n\t addc.cc.u32 %6, %6, 0;\n\t addc.cc.u32 %7, %7, 0;\n\t addc.u32 %8, 0, 0;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "=r"(c)
+        : "r"(top));
+#else
+    BPPP_ASSERT((uint64_t)k * FE_C0 <= 0xFFFFFFFFull);
+    uint64_t t = 0;
+    for (int i = 0; i < 8; i++) { t = (t >> 32) + (uint64_t)a.v[i] * k; r.v[i] = (uint32_t)t; }
+    top = (uint32_t)(t >> 32);
+    t = (uint64_t)r.v[0] + (uint64_t)top * FE_C0; r.v[0] = (uint32_t)t;
+    t = (t >> 32) + r.v[1] + top; r.v[1] = (uint32_t)t;
+    for (int i = 2; i < 8; i++) { t = (t >> 32) + r.v[i]; r.v[i] = (uint32_t)t; }
+    uint32_t c = (uint32_t)(t >> 32);
 #endif
-    fe_check(r);
+    fe_add_fold_low(r, c);
     return r;
 }
 BPPP_HD Fe fe_cmov(const Fe &a, const Fe &b, bool take_b) {
     Fe r;
 #pragma unroll
-    for (int i = 0; i < 10; i++) r.n[i] = take_b ? b.n[i] : a.n[i];
-#if defined(BPPP_VERIFY_MAG)
-    r.lim = a.lim > b.lim ? a.lim : b.lim; r.lim9 = a.lim9 > b.lim9 ? a.lim9 : b.lim9;
+    for (int i = 0; i < 8; i++) r.v[i] = take_b ? b.v[i] : a.v[i];
+    return r;
+}
+
+// ---- 512-bit product -> Fe ------------------------------------------------------------------------------------
+// T = L + 2^256 H  ->  L + H * (2^32 + 977): first fold leaves a 34-bit overflow V, second fold a possible single
+// carry whose residue is below 2^68.
+BPPP_HD Fe fe_reduce512(uint32_t T[16]) {
+    Fe r;
+#if defined(__CUDA_ARCH__)
+    uint32_t R8, R9;
+    // T[0..8) += {T8, T10, T12, T14} * 977 at even positions, carry -> R8
+    asm volatile("mad.lo.cc.u32 %0, %9, %13, %0;\n\t madc.hi.cc.u32 %1, %9, %13, %1;\n\t madc.lo.cc.u32 %2, %10, %13, %2;\n\t madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t madc.hi.cc.u32 %5, %11, %13, %5;\n\t madc.lo.cc.u32 %6, %12, %13, %6;\n\t madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]), "=r"(R8)
+        : "r"(T[8]), "r"(T[10]), "r"(T[12]), "r"(T[14]), "r"(FE_C0));
+    // T[1..8), R8 += {T9, T11, T13, T15} * 977 at odd positions (R8 <= 1 + 976: no carry out)
+    asm volatile("mad.lo.cc.u32 %0, %8, %12, %0;\n\t madc.hi.cc.u32 %1, %8, %12, %1;\n\t madc.lo.cc.u32 %2, %9, %12, %2;\n\t madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t madc.hi.cc.u32 %5, %10, %12, %5;\n\t madc.lo.cc.u32 %6, %11, %12, %6;\n\t madc.hi.u32 %7, %11, %12, %7;"
+        : "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]), "+r"(R8)
+        : "r"(T[9]), "r"(T[11]), "r"(T[13]), "r"(T[15]), "r"(FE_C0));
+    // + H << 32
+    asm volatile("add.cc.u32 %0, %0, %9;\n\t addc.cc.u32 %1, %1, %10;\n\t addc.cc.u32 %2, %2, %11;\n\t addc.cc.u32 %3, %3, %12;\n\t"
+        "addc.cc.u32 %4, %4, %13;\n\t addc.cc.u32 %5, %5, %14;\n\t addc.cc.u32 %6, %6, %15;\n\t addc.cc.u32 %7, %7, %16;\n\t addc.u32 %8, 0, 0;"
+        : "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]), "+r"(R8), "=r"(R9)
+        : "r"(T[8]), "r"(T[9]), "r"(T[10]), "r"(T[11]), "r"(T[12]), "r"(T[13]), "r"(T[14]), "r"(T[15]));
+    // W = V * (2^32 + 977), V = R8 + R9 2^32 < 2^34
+    uint32_t W0, W1, W2;
+    asm volatile("mul.lo.u32 %0, %3, 977;\n\t mul.hi.u32 %1, %3, 977;\n\t mad.lo.u32 %1, %4, 977, %1;\n\t add.cc.u32 %1, %1, %3;\n\t addc.u32 %2, %4, 0;"
+        : "=&r"(W0), "=&r"(W1), "=&r"(W2) : "r"(R8), "r"(R9));
+    uint32_t c2;
+    asm volatile("add.cc.u32 %0, %0, %9;\n\t addc.cc.u32 %1, %1, %10;\n\t addc.cc.u32 %2, %2, %11;\n\t addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t addc.cc.u32 %5, %5, 0;\n\t addc.cc.u32 %6, %6, 0;\n\t addc.cc.u32 %7, %7, 0;\n\t addc.u32 %8, 0, 0;"
+        : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]), "=r"(c2)
+        : "r"(W0), "r"(W1), "r"(W2));
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.v[k] = T[k];
+    fe_add_fold_low(r, c2);
+#else
+    // same steps with 64-bit temporaries
+    uint64_t t = 0, R[10];
+    for (int k = 0; k < 8; k++) R[k] = T[k];
+    R[8] = R[9] = 0;
+    uint64_t carry = 0;
+    for (int k = 0; k < 8; k++) { t = R[k] + (uint64_t)T[8 + k] * FE_C0 + carry; R[k] = (uint32_t)t; carry = t >> 32; }
+    R[8] = carry;                                         // <= 977
+    BPPP_ASSERT(R[8] <= 977);
+    carry = 0;
+    for (int k = 1; k < 9; k++) { t = R[k] + T[7 + k] + carry; R[k] = (uint32_t)t; carry = t >> 32; }
+    R[9] = carry;
+    BPPP_ASSERT(R[9] <= 1);
+    uint64_t V = R[8] | (R[9] << 32);
+    uint64_t W0 = (uint32_t)(V * FE_C0), Whi = (V * FE_C0) >> 32;     // V * 977 < 2^44
+    uint64_t W1 = Whi + (uint32_t)V, W2 = (V >> 32) + (W1 >> 32);
+    W1 = (uint32_t)W1;
+    BPPP_ASSERT(W2 < 8);
+    t = R[0] + W0; r.v[0] = (uint32_t)t;
+    t = (t >> 32) + R[1] + W1; r.v[1] = (uint32_t)t;
+    t = (t >> 32) + R[2] + W2; r.v[2] = (uint32_t)t;
+    for (int k = 3; k < 8; k++) { t = (t >> 32) + R[k]; r.v[k] = (uint32_t)t; }
+    fe_add_fold_low(r, (uint32_t)(t >> 32));
 #endif
     return r;
 }
 
-// Reduce 19 product columns c[0..18] (each < 2^63.9) to limbs below 2^27 + 2^12 (top limb < 2^22).
-// Carry-save instead of carry-propagate: every 64-bit column is cut into 26 + 26 + 12 bit pieces that are
-// re-assembled into lazy limbs with independent 3-input adds, so the only serial carry chain left is three
-// steps long (the previous two 10-step chains made the kernels wait on fixed-latency dependencies, ncu
-// "stall_wait" 2.2 per issue).  2^260 = R0 + R1 2^26 and 2^256 = 977 + 64 2^26 (mod p).
-BPPP_HD Fe fe_reduce_columns(uint64_t c[19]) {
-    // high columns 10..18 -> lazy limbs H[0..10] at weights 2^(26 (10 + j))
-    uint32_t lo[9], mid[9], hi[9];
-#pragma unroll
-    for (int k = 0; k < 9; k++) {
-        uint64_t v = c[10 + k];
-        lo[k] = (uint32_t)v & FE_M26;
-        mid[k] = (uint32_t)(v >> 26) & FE_M26;
-        hi[k] = (uint32_t)(v >> 52);
-    }
-    uint32_t H[11];
-    H[0] = lo[0];
-    H[1] = lo[1] + mid[0];
-#pragma unroll
-    for (int j = 2; j < 9; j++) H[j] = lo[j] + mid[j - 1] + hi[j - 2];
-    H[9] = mid[8] + hi[7];
-    H[10] = hi[8];
-    // fold into the low columns (two more columns appear at positions 10 and 11)
-    uint64_t low[12];
-#pragma unroll
-    for (int k = 0; k < 10; k++) low[k] = c[k];
-    low[10] = 0; low[11] = 0;
-#pragma unroll
-    for (int j = 0; j < 11; j++) {
-        low[j] += (uint64_t)H[j] * FE_R0;
-        low[j + 1] += (uint64_t)H[j] * FE_R1;
-    }
-    // low columns -> lazy limbs L[0..11]  (low[10] < 2^38, low[11] < 2^23, so L[12], L[13] vanish)
-    uint32_t lo2[12], mid2[12], hi2[10];
-#pragma unroll
-    for (int k = 0; k < 12; k++) {
-        uint64_t v = low[k];
-        lo2[k] = (uint32_t)v & FE_M26;
-        mid2[k] = (uint32_t)(v >> 26) & FE_M26;
-        if (k < 10) hi2[k] = (uint32_t)(v >> 52);
-    }
-    uint32_t L[12];
-    L[0] = lo2[0];
-    L[1] = lo2[1] + mid2[0];
-#pragma unroll
-    for (int j = 2; j < 12; j++) L[j] = lo2[j] + mid2[j - 1] + hi2[j - 2];
-    // top: limbs 10, 11 and the bits of limb 9 above 2^22 wrap around once more
-    uint32_t x = L[9] >> 22;
-    uint64_t e0 = (uint64_t)L[0] + (uint64_t)L[10] * FE_R0 + (uint64_t)x * 977u;
-    uint64_t e1 = (uint64_t)L[1] + (uint64_t)L[10] * FE_R1 + (uint64_t)L[11] * FE_R0 + (uint64_t)(x << 6);
-    uint64_t e2 = (uint64_t)L[2] + (uint64_t)L[11] * FE_R1;
-    Fe r;
-    r.n[0] = (uint32_t)e0 & FE_M26; e1 += e0 >> 26;
-    r.n[1] = (uint32_t)e1 & FE_M26; e2 += e1 >> 26;
-    r.n[2] = (uint32_t)e2 & FE_M26;
-    r.n[3] = L[3] + (uint32_t)(e2 >> 26);
-#pragma unroll
-    for (int k = 4; k < 9; k++) r.n[k] = L[k];
-    r.n[9] = L[9] & FE_M22;
-    BPPP_SET_LIM(r, (1ull << 27) + (1ull << 12) + 128, 0x3FFFFFull);
-    fe_check(r);
-    return r;
+#if defined(__CUDA_ARCH__)
+// acc[0..8) += {a0..a3} * b as four adjacent 64-bit products, carry out into a limb that was still zero
+BPPP_D void fe_chain4_carry(uint32_t *acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b, uint32_t &top) {
+    asm volatile("mad.lo.cc.u32 %0, %9, %13, %0;\n\t madc.hi.cc.u32 %1, %9, %13, %1;\n\t madc.lo.cc.u32 %2, %10, %13, %2;\n\t madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t madc.hi.cc.u32 %5, %11, %13, %5;\n\t madc.lo.cc.u32 %6, %12, %13, %6;\n\t madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(top)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
 }
+// same, but the last product is the first one at its position: its high limb was zero and nothing can carry out
+BPPP_D void fe_chain4_top(uint32_t *acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b, uint32_t &top) {
+    asm volatile("mad.lo.cc.u32 %0, %8, %12, %0;\n\t madc.hi.cc.u32 %1, %8, %12, %1;\n\t madc.lo.cc.u32 %2, %9, %12, %2;\n\t madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t madc.hi.cc.u32 %5, %10, %12, %5;\n\t madc.lo.cc.u32 %6, %11, %12, %6;\n\t madc.hi.u32 %7, %11, %12, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "=r"(top)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+BPPP_D void fe_mul4(uint32_t *acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+    asm volatile("mul.lo.u32 %0, %8, %12;\n\t mul.hi.u32 %1, %8, %12;\n\t mul.lo.u32 %2, %9, %12;\n\t mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t mul.hi.u32 %5, %10, %12;\n\t mul.lo.u32 %6, %11, %12;\n\t mul.hi.u32 %7, %11, %12;"
+        : "=&r"(acc[0]), "=&r"(acc[1]), "=&r"(acc[2]), "=&r"(acc[3]), "=&r"(acc[4]), "=&r"(acc[5]), "=&r"(acc[6]), "=&r"(acc[7])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+// n adjacent 64-bit products acc[0..2n) += a * {b0..}, carry added into acc[2n] (which may already hold carries)
+BPPP_D void fe_chain1(uint32_t *acc, uint32_t a, uint32_t b0) {
+    asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\t madc.hi.cc.u32 %1, %3, %4, %1;\n\t addc.u32 %2, %2, 0;" : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]) : "r"(a), "r"(b0));
+}
+BPPP_D void fe_chain2(uint32_t *acc, uint32_t a, uint32_t b0, uint32_t b1) {
+    asm volatile("mad.lo.cc.u32 %0, %5, %6, %0;\n\t madc.hi.cc.u32 %1, %5, %6, %1;\n\t madc.lo.cc.u32 %2, %5, %7, %2;\n\t madc.hi.cc.u32 %3, %5, %7, %3;\n\t addc.u32 %4, %4, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]) : "r"(a), "r"(b0), "r"(b1));
+}
+BPPP_D void fe_chain3(uint32_t *acc, uint32_t a, uint32_t b0, uint32_t b1, uint32_t b2) {
+    asm volatile("mad.lo.cc.u32 %0, %7, %8, %0;\n\t madc.hi.cc.u32 %1, %7, %8, %1;\n\t madc.lo.cc.u32 %2, %7, %9, %2;\n\t madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+        "madc.lo.cc.u32 %4, %7, %10, %4;\n\t madc.hi.cc.u32 %5, %7, %10, %5;\n\t addc.u32 %6, %6, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]) : "r"(a), "r"(b0), "r"(b1), "r"(b2));
+}
+// T[1..16) = E[1..16) + O[0..15): two single-block chains, the carry handed over in a register
+BPPP_D void fe_merge_even_odd(uint32_t *T, const uint32_t *E, const uint32_t *O) {
+    uint32_t c;
+    asm volatile("add.cc.u32 %0, %9, %17;\n\t addc.cc.u32 %1, %10, %18;\n\t addc.cc.u32 %2, %11, %19;\n\t addc.cc.u32 %3, %12, %20;\n\t"
+                 "addc.cc.u32 %4, %13, %21;\n\t addc.cc.u32 %5, %14, %22;\n\t addc.cc.u32 %6, %15, %23;\n\t addc.cc.u32 %7, %16, %24;\n\t addc.u32 %8, 0, 0;"
+                 : "=&r"(T[1]), "=&r"(T[2]), "=&r"(T[3]), "=&r"(T[4]), "=&r"(T[5]), "=&r"(T[6]), "=&r"(T[7]), "=&r"(T[8]), "=&r"(c)
+                 : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]),
+                   "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]));
+    asm volatile("add.cc.u32 %7, %7, 0xFFFFFFFF;\n\t"      // carry flag <- c
+                 "addc.cc.u32 %0, %8, %15;\n\t addc.cc.u32 %1, %9, %16;\n\t addc.cc.u32 %2, %10, %17;\n\t addc.cc.u32 %3, %11, %18;\n\t"
+                 "addc.cc.u32 %4, %12, %19;\n\t addc.cc.u32 %5, %13, %20;\n\t addc.u32 %6, %14, %21;"
+                 : "=&r"(T[9]), "=&r"(T[10]), "=&r"(T[11]), "=&r"(T[12]), "=&r"(T[13]), "=&r"(T[14]), "=&r"(T[15]), "+r"(c)
+                 : "r"(E[9]), "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
+                   "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+}
+#endif
 
 BPPP_HD Fe fe_mul_inl(const Fe &a, const Fe &b) {
-    fe_check(a); fe_check(b);
-#if defined(BPPP_VERIFY_MAG)
-    assert((unsigned __int128)10 * a.lim * b.lim < ((unsigned __int128)15 << 60));   // columns < 2^63.9: room for the folds
-#endif
-    uint64_t c[19];
+    uint32_t T[16];
+#if defined(__CUDA_ARCH__)
+    // E: products starting at even limb positions (index = position); O: odd positions (index = position - 1)
+    uint32_t E[16], O[16];
+    E[8] = 0;
+    fe_mul4(E, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
+    fe_mul4(O, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
 #pragma unroll
-    for (int k = 0; k < 19; k++) c[k] = 0;
-#pragma unroll
-    for (int i = 0; i < 10; i++) {
-#pragma unroll
-        for (int j = 0; j < 10; j++) c[i + j] += (uint64_t)a.n[i] * b.n[j];
+    for (int i = 1; i < 8; i++) {
+        if (i & 1) {
+            fe_chain4_carry(O + i - 1, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i], O[i + 7]);
+            fe_chain4_top(E + i + 1, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i], E[i + 8]);
+        } else {
+            fe_chain4_carry(E + i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i], E[i + 8]);
+            fe_chain4_top(O + i, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i], O[i + 7]);
+        }
     }
-    return fe_reduce_columns(c);
+    T[0] = E[0];
+    fe_merge_even_odd(T, E, O);
+#else
+    for (int k = 0; k < 16; k++) T[k] = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; j < 8; j++) {
+            uint64_t t = (uint64_t)T[i + j] + (uint64_t)a.v[j] * b.v[i] + carry;
+            T[i + j] = (uint32_t)t; carry = t >> 32;
+        }
+        T[i + 8] = (uint32_t)carry;
+    }
+#endif
+    return fe_reduce512(T);
 }
 
 BPPP_HD Fe fe_sqr_inl(const Fe &a) {
-    fe_check(a);
-#if defined(BPPP_VERIFY_MAG)
-    assert(a.lim < (1ull << 31) && (unsigned __int128)10 * a.lim * a.lim < ((unsigned __int128)15 << 60));
-#endif
-    uint64_t c[19];
+    uint32_t T[16];
+#if defined(__CUDA_ARCH__)
+    // off-diagonal products a_i a_j (i < j) once, into the even / odd position accumulators
+    uint32_t E[16], O[16];
 #pragma unroll
-    for (int k = 0; k < 19; k++) c[k] = 0;
-    uint32_t d[10];
-#pragma unroll
-    for (int i = 0; i < 10; i++) d[i] = a.n[i] << 1;   // magnitude <= 8 => limbs < 2^30, doubled < 2^31
-#pragma unroll
-    for (int i = 0; i < 10; i++) {
-        c[2 * i] += (uint64_t)a.n[i] * a.n[i];
-#pragma unroll
-        for (int j = i + 1; j < 10; j++) c[i + j] += (uint64_t)d[i] * a.n[j];
+    for (int k = 0; k < 16; k++) { E[k] = 0; O[k] = 0; }
+    const uint32_t *v = a.v;
+    // row 0
+    fe_mul4(O, v[1], v[3], v[5], v[7], v[0]);                            // positions 1 3 5 7
+    asm volatile("mul.lo.u32 %0, %6, %9;\n\t mul.hi.u32 %1, %6, %9;\n\t mul.lo.u32 %2, %7, %9;\n\t mul.hi.u32 %3, %7, %9;\n\t mul.lo.u32 %4, %8, %9;\n\t mul.hi.u32 %5, %8, %9;"
+        : "=&r"(E[2]), "=&r"(E[3]), "=&r"(E[4]), "=&r"(E[5]), "=&r"(E[6]), "=&r"(E[7]) : "r"(v[2]), "r"(v[4]), "r"(v[6]), "r"(v[0]));   // positions 2 4 6
+    // row 1
+    fe_chain3(O + 2, v[1], v[2], v[4], v[6]);                            // 3 5 7
+    fe_chain3(E + 4, v[1], v[3], v[5], v[7]);                            // 4 6 8
+    // row 2
+    fe_chain3(O + 4, v[2], v[3], v[5], v[7]);                            // 5 7 9
+    fe_chain2(E + 6, v[2], v[4], v[6]);                                  // 6 8
+    // row 3
+    fe_chain2(O + 6, v[3], v[4], v[6]);                                  // 7 9
+    fe_chain2(E + 8, v[3], v[5], v[7]);                                  // 8 10
+    // row 4
+    fe_chain2(O + 8, v[4], v[5], v[7]);                                  // 9 11
+    fe_chain1(E + 10, v[4], v[6]);                                       // 10
+    // row 5
+    fe_chain1(O + 10, v[5], v[6]);                                       // 11
+    fe_chain1(E + 12, v[5], v[7]);                                       // 12
+    // row 6
+    fe_chain1(O + 12, v[6], v[7]);                                       // 13
+    // S = E + (O << 32), then T = 2 S + sum a_i^2 2^(64 i)
+    T[0] = 0;
+    fe_merge_even_odd(T, E, O);
+    // T = 2 T (S < 2^511: nothing shifts out)
+    asm volatile("add.cc.u32 %0, %0, %0;\n\t addc.cc.u32 %1, %1, %1;\n\t addc.cc.u32 %2, %2, %2;\n\t addc.cc.u32 %3, %3, %3;\n\t addc.cc.u32 %4, %4, %4;\n\t"
+                 "addc.cc.u32 %5, %5, %5;\n\t addc.cc.u32 %6, %6, %6;\n\t addc.cc.u32 %7, %7, %7;\n\t addc.cc.u32 %8, %8, %8;\n\t addc.cc.u32 %9, %9, %9;\n\t"
+                 "addc.cc.u32 %10, %10, %10;\n\t addc.cc.u32 %11, %11, %11;\n\t addc.cc.u32 %12, %12, %12;\n\t addc.cc.u32 %13, %13, %13;\n\t addc.u32 %14, %14, %14;"
+                 : "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]), "+r"(T[8]), "+r"(T[9]), "+r"(T[10]), "+r"(T[11]),
+                   "+r"(T[12]), "+r"(T[13]), "+r"(T[14]), "+r"(T[15]));
+    // T += sum a_k^2 2^(64 k): one chain over all 16 limbs
+    asm volatile("mad.lo.cc.u32 %0, %16, %16, %0;\n\t madc.hi.cc.u32 %1, %16, %16, %1;\n\t madc.lo.cc.u32 %2, %17, %17, %2;\n\t madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+                 "madc.lo.cc.u32 %4, %18, %18, %4;\n\t madc.hi.cc.u32 %5, %18, %18, %5;\n\t madc.lo.cc.u32 %6, %19, %19, %6;\n\t madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+                 "madc.lo.cc.u32 %8, %20, %20, %8;\n\t madc.hi.cc.u32 %9, %20, %20, %9;\n\t madc.lo.cc.u32 %10, %21, %21, %10;\n\t madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+                 "madc.lo.cc.u32 %12, %22, %22, %12;\n\t madc.hi.cc.u32 %13, %22, %22, %13;\n\t madc.lo.cc.u32 %14, %23, %23, %14;\n\t madc.hi.u32 %15, %23, %23, %15;"
+                 : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]), "+r"(T[8]), "+r"(T[9]), "+r"(T[10]), "+r"(T[11]),
+                   "+r"(T[12]), "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
+                 : "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
+#else
+    for (int k = 0; k < 16; k++) T[k] = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; j < 8; j++) {
+            uint64_t t = (uint64_t)T[i + j] + (uint64_t)a.v[j] * a.v[i] + carry;
+            T[i + j] = (uint32_t)t; carry = t >> 32;
+        }
+        T[i + 8] = (uint32_t)carry;
     }
-    return fe_reduce_columns(c);
+#endif
+    return fe_reduce512(T);
 }
 
 #if defined(__CUDACC__) && defined(BPPP_FE_NOINLINE)
@@ -365,7 +480,7 @@ BPPP_HD Fe fe_sqr_n(Fe a, int n) {
     return a;
 }
 
-// a^(p-2): 255 squarings + 15 multiplications.  a of magnitude <= 8.  fe_inv(0) = 0.
+// a^(p-2): 255 squarings + 15 multiplications.  fe_inv(0) = 0.
 BPPP_HD Fe fe_inv(const Fe &a) {
     Fe x2 = fe_mul(fe_sqr(a), a);
     Fe x3 = fe_mul(fe_sqr(x2), a);

@@ -31,9 +31,9 @@ struct PL {
     static constexpr int S = 3;                               // blinding
     static constexpr int MERLIN = S + 8;
     static constexpr int PTS = MERLIN + 52;
-    static constexpr int COM = PTS + 30 * PP_COM;
-    static constexpr int ZINV = PTS + 30 * PP_COUNT;
-    static constexpr int OUT = ZINV + 10 * PP_COUNT;          // 13 x (8 x-words + tag)
+    static constexpr int COM = PTS + PT_W * PP_COM;
+    static constexpr int ZINV = PTS + PT_W * PP_COUNT;
+    static constexpr int OUT = ZINV + FE_W * PP_COUNT;          // 13 x (8 x-words + tag)
     static constexpr int RND = OUT + 9 * PO_COUNT;            // 52 reduced draws
     static constexpr int INVE = RND + 8 * RD_COUNT;           // 1/(e+j), j < 16
     static constexpr int E = INVE + 128;
@@ -123,13 +123,13 @@ BPPP_HD void u64p_load_one(const WS &w, size_t i, uint64_t x, const uint8_t *bli
 
 // affine + SEC1 record of prover point `slot`; also stashes the compressed form for output position `po` (or -1)
 BPPP_HD PtA u64p_affine(const WS &w, size_t i, int slot, int po, bool &id) {
-    PtA a = ws_affine(w, i, PL::PTS + 30 * slot, PL::ZINV + 10 * slot, id);
+    PtA a = ws_affine(w, i, PL::PTS + PT_W * slot, PL::ZINV + FE_W * slot, id);
     if (po >= 0) {
         uint32_t xw[8];
         fe_to_words(xw, a.x);
 #pragma unroll
         for (int k = 0; k < 8; k++) ws_st(w, i, PL::OUT + 9 * po + k, id ? 0u : xw[k]);
-        ws_st(w, i, PL::OUT + 9 * po + 8, id ? 0u : (2u + (a.y.n[0] & 1u)));
+        ws_st(w, i, PL::OUT + 9 * po + 8, id ? 0u : (2u + (a.y.v[0] & 1u)));
     }
     return a;
 }
@@ -186,7 +186,7 @@ BPPP_HD void u64p_phase1_one(const WS &w, size_t i, const Merlin &init, const ui
 
 // circuit_commitment = circuit.commit(v, s + r_blind) == V + r_com
 BPPP_HD void u64p_vprime_one(const WS &w, size_t i) {
-    ws_st_pt(w, i, PL::PTS + 30 * PP_VP, pt_add(ws_ld_pt(w, i, PL::PTS + 30 * PP_V), ws_ld_pt(w, i, PL::PTS + 30 * PP_RCOM)));
+    ws_st_pt(w, i, PL::PTS + PT_W * PP_VP, pt_add(ws_ld_pt(w, i, PL::PTS + PT_W * PP_V), ws_ld_pt(w, i, PL::PTS + PT_W * PP_RCOM)));
 }
 
 struct CircuitCoefs {   // closed-form c_nL, c_nR, c_lL (see u64_verify.cuh header)
@@ -482,8 +482,8 @@ BPPP_HD void u64p_round_one(const WS &w, size_t i, int j) {
 BPPP_HD void u64p_var2_one(const WS &w, size_t i, int j) {
     bool ident[2];
     PtA pts[2];
-    pts[0] = ws_affine(w, i, PL::PTS + 30 * (PP_X + j), PL::ZINV + 10 * (PP_X + j), ident[0]);
-    pts[1] = ws_affine(w, i, PL::PTS + 30 * (PP_R + j), PL::ZINV + 10 * (PP_R + j), ident[1]);
+    pts[0] = ws_affine(w, i, PL::PTS + PT_W * (PP_X + j), PL::ZINV + FE_W * (PP_X + j), ident[0]);
+    pts[1] = ws_affine(w, i, PL::PTS + PT_W * (PP_R + j), PL::ZINV + FE_W * (PP_R + j), ident[1]);
     Sc ks[2] = {ws_ld_sc(w, i, PL::VS), ws_ld_sc(w, i, PL::VS + 8)};
     Pt com = straus_var<2>(pts, ident, ks, ws_ld_pt(w, i, PL::COM));
     ws_st_pt(w, i, PL::COM, com);

@@ -26,20 +26,20 @@ struct VL {
     static constexpr int L = VPA + 16;                  // l[2]
     static constexpr int N = L + 16;                    // n[1]
     static constexpr int MERLIN = N + 8;                // 51 words (+1 pad)
-    static constexpr int VP = MERLIN + 52;              // V' projective (30)
-    static constexpr int ZINV = VP + 30;                // 10
-    static constexpr int COM = ZINV + 10;               // running WNLA commitment, projective (30)
-    static constexpr int ACC = COM + 30;                // fixed-base MSM result (30)
-    static constexpr int C = ACC + 30;                  // c vector, 32 scalars
+    static constexpr int VP = MERLIN + 52;              // V' projective (PT_W)
+    static constexpr int ZINV = VP + PT_W;              // FE_W
+    static constexpr int COM = ZINV + FE_W;             // running WNLA commitment, projective (PT_W)
+    static constexpr int ACC = COM + PT_W;              // fixed-base MSM result (PT_W)
+    static constexpr int C = ACC + PT_W;                // c vector, 32 scalars
     static constexpr int RHO = C + 256;
     static constexpr int MU = RHO + 8;
     static constexpr int Y = MU + 8;                    // y_0..y_3
     static constexpr int FS = Y + 32;                   // fixed-base scalars (<= 49)
     static constexpr int VS = FS + 8 * NUM_GENS;        // variable-base scalars (<= 5)
-    // ladder tables: 13 points (c_l c_r c_o c_s r[0..3] x[0..3] V') x 8 multiples, 40 words per entry:
-    // projective X Y Z (30) + 1/Z (10) while being built, then affine x y (16 canonical words) in place
+    // ladder tables: 13 points (c_l c_r c_o c_s r[0..3] x[0..3] V') x 8 multiples, 4 field elements per entry:
+    // projective X Y Z + 1/Z while being built, then affine x y (16 canonical words) in place
     static constexpr int TAB = VS + 40;
-    static constexpr int TAB_POINTS = 13, TAB_ENTRIES = TAB_POINTS * 8, TAB_STRIDE = 40;
+    static constexpr int TAB_POINTS = 13, TAB_ENTRIES = TAB_POINTS * 8, TAB_STRIDE = 4 * FE_W;
     static constexpr int WORDS = TAB + TAB_ENTRIES * TAB_STRIDE;
 };
 // table point ids: input slot k (1..12) -> k - 1; V' -> 12
@@ -231,7 +231,7 @@ BPPP_HD void u64v_table_build_one(const WS &w, size_t i, int t) {
 BPPP_HD void u64v_table_finish_one(const WS &w, size_t i, int entry) {
     const int off = VL::TAB + entry * VL::TAB_STRIDE;
     bool id;
-    PtA a = ws_affine(w, i, off, off + 30, id);
+    PtA a = ws_affine(w, i, off, off + PT_W, id);
     if (id) { a.x = fe_zero(); a.y = fe_zero(); }
     ws_st_pta(w, i, off, a);
 }
@@ -244,8 +244,8 @@ BPPP_HD void u64v_tables_normalize_strided(const WS &w, size_t t, size_t T) {
     for (size_t idx = t; idx < total; idx += T) {
         size_t e = idx / w.n, i = idx - e * w.n;
         const int off = VL::TAB + (int)e * VL::TAB_STRIDE;
-        Fe z = ws_ld_fe(w, i, off + 20);
-        ws_st_fe(w, i, off + 30, run);                  // prefix product before this item
+        Fe z = ws_ld_fe(w, i, off + 2 * FE_W);
+        ws_st_fe(w, i, off + PT_W, run);                  // prefix product before this item
         if (!fe_normalizes_to_zero(z)) run = fe_mul(run, z);
     }
     Fe rinv = fe_inv(run);
@@ -259,7 +259,7 @@ BPPP_HD void u64v_tables_normalize_strided(const WS &w, size_t t, size_t T) {
         PtA a;
         if (fe_normalizes_to_zero(p.z)) { a.x = fe_zero(); a.y = fe_zero(); }       // identity -> zero sentinel
         else {
-            Fe zi = fe_mul(rinv, ws_ld_fe(w, i, off + 30));
+            Fe zi = fe_mul(rinv, ws_ld_fe(w, i, off + PT_W));
             rinv = fe_mul(rinv, p.z);
             a = pt_to_affine_with_zinv(p, zi);
         }

@@ -27,14 +27,13 @@ BPPP_HD void ws_st_sc(const WS &w, size_t i, int off, const Sc &a) {
     for (int k = 0; k < 8; k++) ws_st(w, i, off + k, a.v[k]); }
 BPPP_HD Fe ws_ld_fe(const WS &w, size_t i, int off) { Fe r;
 #pragma unroll
-    for (int k = 0; k < 10; k++) r.n[k] = ws_ld(w, i, off + k);
-    BPPP_SET_LIM(r, (1ull << 27) + (1ull << 12) + 128, 0x3FFFFFull + 64);   // stored values are fe_mul / weak-normalised outputs
+    for (int k = 0; k < FE_W; k++) r.v[k] = ws_ld(w, i, off + k);
     return r; }
 BPPP_HD void ws_st_fe(const WS &w, size_t i, int off, const Fe &a) {
 #pragma unroll
-    for (int k = 0; k < 10; k++) ws_st(w, i, off + k, a.n[k]); }
-BPPP_HD Pt ws_ld_pt(const WS &w, size_t i, int off) { Pt r; r.x = ws_ld_fe(w, i, off); r.y = ws_ld_fe(w, i, off + 10); r.z = ws_ld_fe(w, i, off + 20); return r; }
-BPPP_HD void ws_st_pt(const WS &w, size_t i, int off, const Pt &a) { ws_st_fe(w, i, off, a.x); ws_st_fe(w, i, off + 10, a.y); ws_st_fe(w, i, off + 20, a.z); }
+    for (int k = 0; k < FE_W; k++) ws_st(w, i, off + k, a.v[k]); }
+BPPP_HD Pt ws_ld_pt(const WS &w, size_t i, int off) { Pt r; r.x = ws_ld_fe(w, i, off); r.y = ws_ld_fe(w, i, off + FE_W); r.z = ws_ld_fe(w, i, off + 2 * FE_W); return r; }
+BPPP_HD void ws_st_pt(const WS &w, size_t i, int off, const Pt &a) { ws_st_fe(w, i, off, a.x); ws_st_fe(w, i, off + FE_W, a.y); ws_st_fe(w, i, off + 2 * FE_W, a.z); }
 // affine point stored as 16 canonical words (x[8], y[8]); (0,0) = identity sentinel
 BPPP_HD PtA ws_ld_pta(const WS &w, size_t i, int off) {
     uint32_t x[8], y[8];

@@ -37,7 +37,7 @@ int main() {
         hex("commit", v);
         hex("proof", proof.record);
         std::printf("verify=%d\n", (int)proto.verify(v, proof, "u64 range proof"));
-        auto bad = proof; bad.record[524] ^= 1;
+        auto bad = proof; bad.record[491] ^= 1;   // last byte of the scalar n
         std::printf("verify_tampered=%d\n", (int)proto.verify(v, bad, "u64 range proof"));
         auto mal = proof; std::memset(mal.record.data(), 0xff, 33);
         try { proto.verify(v, mal, "u64 range proof"); std::printf("malformed=accepted\n"); }

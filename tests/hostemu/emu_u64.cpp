@@ -67,7 +67,7 @@ int emu_u64_verify_batch(void *ctx, size_t n, const uint8_t *commits, const uint
     Merlin init; merlin_init(init, label, label_len);
     size_t csz = fmt == FMT_COMPRESSED ? 33 : 64, psz = fmt == FMT_COMPRESSED ? U64_PROOF_BYTES_COMPRESSED : U64_PROOF_BYTES_AFFINE;
     for (size_t i = 0; i < n; i++) u64v_load_one(w, i, commits + csz * i, proofs + psz * i, fmt);
-    emu_batch_inv(w, n, VL::VP + 20, VL::ZINV);
+    emu_batch_inv(w, n, VL::VP + 2 * FE_W, VL::ZINV);
     for (size_t i = 0; i < n; i++) u64v_phase1_one(w, i, init);
     for (size_t i = 0; i < n; i++) for (int t = 0; t < VL::TAB_POINTS; t++) u64v_table_build_one(w, i, t);
     { size_t T = (n * VL::TAB_ENTRIES + 6) / 7; for (size_t t = 0; t < T; t++) u64v_tables_normalize_strided(w, t, T); }
@@ -75,7 +75,7 @@ int emu_u64_verify_batch(void *ctx, size_t n, const uint8_t *commits, const uint
     emu_msm_fixed(c, w, n, VL::FS, tg17, 17, VL::ACC, 8);
     for (size_t i = 0; i < n; i++) u64v_var5_one(w, i);
     for (int j = 0; j < 4; j++) {
-        emu_batch_inv(w, n, VL::COM + 20, VL::ZINV);
+        emu_batch_inv(w, n, VL::COM + 2 * FE_W, VL::ZINV);
         for (size_t i = 0; i < n; i++) u64v_round_one(w, i, j);
         for (size_t i = 0; i < n; i++) u64v_var2_one(w, i, j);
     }
@@ -97,30 +97,30 @@ extern "C" int emu_u64_prove_batch(void *ctx, size_t n, const uint64_t *xs, cons
     int tm[NUM_GENS];
     for (size_t i = 0; i < n; i++) u64p_load_one(w, i, xs[i], blinds + 32 * i);
     u64p_termmap_commit(tm);
-    emu_msm_fixed(c, w, n, PL::FS, tm, 2, PL::PTS + 30 * PP_V, 8);
-    emu_batch_inv(w, n, PL::PTS + 30 * PP_V + 20, PL::ZINV + 10 * PP_V);
+    emu_msm_fixed(c, w, n, PL::FS, tm, 2, PL::PTS + PT_W * PP_V, 8);
+    emu_batch_inv(w, n, PL::PTS + PT_W * PP_V + 2 * FE_W, PL::ZINV + FE_W * PP_V);
     for (size_t i = 0; i < n; i++) u64p_phase1_one(w, i, init, rng + (size_t)U64_RNG_BYTES * i);
     for (int k = 0; k < 4; k++) {
         int nt = u64p_termmap_stage1(tm, k);
-        emu_msm_fixed(c, w, n, PL::FS + 8 * u64p_stage1_scalar_base(k), tm, nt, PL::PTS + 30 * u64p_stage1_point(k), 8);
+        emu_msm_fixed(c, w, n, PL::FS + 8 * u64p_stage1_scalar_base(k), tm, nt, PL::PTS + PT_W * u64p_stage1_point(k), 8);
     }
     for (size_t i = 0; i < n; i++) u64p_vprime_one(w, i);
-    for (int k = 0; k < 5; k++) { int p = u64p_stage1_norm_point(k); emu_batch_inv(w, n, PL::PTS + 30 * p + 20, PL::ZINV + 10 * p); }
+    for (int k = 0; k < 5; k++) { int p = u64p_stage1_norm_point(k); emu_batch_inv(w, n, PL::PTS + PT_W * p + 2 * FE_W, PL::ZINV + FE_W * p); }
     for (size_t i = 0; i < n; i++) u64p_phase2_one(w, i, rng + (size_t)U64_RNG_BYTES * i);
     u64p_termmap_cs(tm);
-    emu_msm_fixed(c, w, n, PL::FS, tm, 42, PL::PTS + 30 * PP_CS, 8);
-    emu_batch_inv(w, n, PL::PTS + 30 * PP_CS + 20, PL::ZINV + 10 * PP_CS);
+    emu_msm_fixed(c, w, n, PL::FS, tm, 42, PL::PTS + PT_W * PP_CS, 8);
+    emu_batch_inv(w, n, PL::PTS + PT_W * PP_CS + 2 * FE_W, PL::ZINV + FE_W * PP_CS);
     for (size_t i = 0; i < n; i++) u64p_phase3_one(w, i);
     u64p_termmap_c0(tm);
     emu_msm_fixed(c, w, n, PL::FS, tm, 43, PL::COM, 8);
     for (int j = 0; j < 4; j++) {
         int all[NUM_GENS]; for (int t = 0; t < NUM_GENS; t++) all[t] = t;
-        emu_msm_fixed(c, w, n, PL::XS, all, NUM_GENS, PL::PTS + 30 * (PP_X + j), 8);
+        emu_msm_fixed(c, w, n, PL::XS, all, NUM_GENS, PL::PTS + PT_W * (PP_X + j), 8);
         u64p_termmap_r(tm, j);
-        emu_msm_fixed(c, w, n, PL::RS, tm, 25, PL::PTS + 30 * (PP_R + j), 8);
-        emu_batch_inv(w, n, PL::COM + 20, PL::ZINV + 10 * PP_COM);
-        emu_batch_inv(w, n, PL::PTS + 30 * (PP_X + j) + 20, PL::ZINV + 10 * (PP_X + j));
-        emu_batch_inv(w, n, PL::PTS + 30 * (PP_R + j) + 20, PL::ZINV + 10 * (PP_R + j));
+        emu_msm_fixed(c, w, n, PL::RS, tm, 25, PL::PTS + PT_W * (PP_R + j), 8);
+        emu_batch_inv(w, n, PL::COM + 2 * FE_W, PL::ZINV + FE_W * PP_COM);
+        emu_batch_inv(w, n, PL::PTS + PT_W * (PP_X + j) + 2 * FE_W, PL::ZINV + FE_W * (PP_X + j));
+        emu_batch_inv(w, n, PL::PTS + PT_W * (PP_R + j) + 2 * FE_W, PL::ZINV + FE_W * (PP_R + j));
         for (size_t i = 0; i < n; i++) u64p_round_one(w, i, j);
         if (j < 3) for (size_t i = 0; i < n; i++) u64p_var2_one(w, i, j);
     }

@@ -40,6 +40,23 @@ def test_field_ops(emu_prims, ref):
         assert ok == 1 and r * r % P == sq
 
 
+def test_field_ops_on_non_canonical_representatives(emu_prims, ref):
+    """every pair of edge values, including the representatives in [p, 2^256) that trigger the rare double wrap
+    of fe_add / double borrow of fe_sub / second fold of the product reduction"""
+    L, P = emu_prims, ref.P
+    top = 2**256
+    edge = [0, 1, 976, 977, 978, 2**32 + 976, 2**32 + 977, 2**32 + 978, P - 1, P, P + 1, P + 977, top - 2**32, top - 978, top - 977, top - 2, top - 1,
+            2**255, 2**224 - 1, (2**256 - 1) // 3]
+    for a in edge:
+        for b in edge:
+            o = O(32); L.emu_fe_mul(B(be(a)), B(be(b)), o); assert int.from_bytes(o, "big") == a * b % P
+            for c in (0, 1, P, top - 1, 2**32 + 977):
+                o = O(32); L.emu_fe_expr(B(be(a)), B(be(b)), B(be(c)), B(be(1)), 1, 1, o)
+                assert int.from_bytes(o, "big") == (a + b - c) % P
+                o = O(32); L.emu_fe_expr(B(be(a)), B(be(b)), B(be(c)), B(be(top - 1)), 7, 8, o)
+                assert int.from_bytes(o, "big") == (7 * a + 8 * b - c) * (top - 1) % P
+
+
 def test_scalar_ops(emu_prims, ref):
     L, N = emu_prims, ref.N
     rnd = random.Random(8)
