@@ -173,6 +173,8 @@ BPPP_HD void pta_to_xy64(uint8_t out[64], const PtA &a_canonical, bool is_identi
 // fixed-base and Pippenger accumulation loops are made of.  The formula is incomplete, so the exceptional inputs are
 // handled explicitly and exactly (scalars chosen by an adversarial prover can steer an accumulator onto them):
 // identity accumulator (flag), P1 == Q (affine doubling), P1 == -Q (identity).
+template <bool INL> BPPP_HD Fe fe_mul_t(const Fe &a, const Fe &b) { if (INL) return fe_mul_inl(a, b); return fe_mul(a, b); }
+template <bool INL> BPPP_HD Fe fe_sqr_t(const Fe &a) { if (INL) return fe_sqr_inl(a); return fe_sqr(a); }
 struct PtX {
     Fe x, y, zz, zzz;
     bool inf;
@@ -180,42 +182,44 @@ struct PtX {
 BPPP_HD PtX ptx_identity() { PtX r; r.x = fe_zero(); r.y = fe_zero(); r.zz = fe_zero(); r.zzz = fe_zero(); r.inf = true;
     BPPP_SET_MAG(r.x, 1); BPPP_SET_MAG(r.y, 1); BPPP_SET_MAG(r.zz, 1); BPPP_SET_MAG(r.zzz, 1); return r; }
 // 2Q for affine Q (mdbl-2008-s-1)
-BPPP_HD PtX ptx_double_affine(const PtA &q) {
+template <bool INL> BPPP_HD PtX ptx_double_affine_t(const PtA &q) {
     PtX r;
     Fe U = fe_mul_int(q.y, 2);                       // 2y            mag 2
-    Fe V = fe_sqr(U);                                // 4y^2
-    Fe W = fe_mul(U, V);                             // 8y^3
-    Fe S = fe_mul(q.x, V);
-    Fe M = fe_mul_int(fe_sqr(q.x), 3);               // 3x^2          mag 3
-    r.x = fe_normalize_weak(fe_sub(fe_sqr(M), fe_mul_int(S, 2), 2));
-    r.y = fe_normalize_weak(fe_sub(fe_mul(M, fe_sub(S, r.x, 1)), fe_mul(W, q.y), 1));
+    Fe V = fe_sqr_t<INL>(U);                                // 4y^2
+    Fe W = fe_mul_t<INL>(U, V);                             // 8y^3
+    Fe S = fe_mul_t<INL>(q.x, V);
+    Fe M = fe_mul_int(fe_sqr_t<INL>(q.x), 3);               // 3x^2          mag 3
+    r.x = fe_normalize_weak(fe_sub(fe_sqr_t<INL>(M), fe_mul_int(S, 2), 2));
+    r.y = fe_normalize_weak(fe_sub(fe_mul_t<INL>(M, fe_sub(S, r.x, 1)), fe_mul_t<INL>(W, q.y), 1));
     r.zz = V; r.zzz = W;
     r.inf = fe_normalizes_to_zero(q.y);              // cannot happen on an odd-order curve; kept for exactness
     return r;
 }
 // P + Q, Q affine and not the identity
-BPPP_HD PtX ptx_add_mixed(const PtX &p, const PtA &q) {
+template <bool INL> BPPP_HD PtX ptx_add_mixed_t(const PtX &p, const PtA &q) {
     PtX r;
     if (p.inf) { r.x = q.x; r.y = q.y; r.zz = fe_one(); r.zzz = fe_one(); r.inf = false; return r; }
-    Fe U2 = fe_mul(q.x, p.zz);
-    Fe S2 = fe_mul(q.y, p.zzz);
+    Fe U2 = fe_mul_t<INL>(q.x, p.zz);
+    Fe S2 = fe_mul_t<INL>(q.y, p.zzz);
     Fe P = fe_sub(U2, p.x, 1);                       // mag 3
     Fe R = fe_sub(S2, p.y, 1);                       // mag 3
     if (fe_normalizes_to_zero(P)) {                  // same x: P1 = +-Q
-        if (fe_normalizes_to_zero(R)) return ptx_double_affine(q);
+        if (fe_normalizes_to_zero(R)) return ptx_double_affine_t<INL>(q);
         return ptx_identity();
     }
-    Fe PP = fe_sqr(P);
-    Fe PPP = fe_mul(P, PP);
-    Fe Q = fe_mul(p.x, PP);
-    Fe RR = fe_sqr(R);
+    Fe PP = fe_sqr_t<INL>(P);
+    Fe PPP = fe_mul_t<INL>(P, PP);
+    Fe Q = fe_mul_t<INL>(p.x, PP);
+    Fe RR = fe_sqr_t<INL>(R);
     r.x = fe_normalize_weak(fe_sub(RR, fe_add(PPP, fe_mul_int(Q, 2)), 3));
-    r.y = fe_normalize_weak(fe_sub(fe_mul(R, fe_sub(Q, r.x, 1)), fe_mul(p.y, PPP), 1));
-    r.zz = fe_mul(p.zz, PP);
-    r.zzz = fe_mul(p.zzz, PPP);
+    r.y = fe_normalize_weak(fe_sub(fe_mul_t<INL>(R, fe_sub(Q, r.x, 1)), fe_mul_t<INL>(p.y, PPP), 1));
+    r.zz = fe_mul_t<INL>(p.zz, PP);
+    r.zzz = fe_mul_t<INL>(p.zzz, PPP);
     r.inf = false;
     return r;
 }
+BPPP_HD PtX ptx_double_affine(const PtA &q) { return ptx_double_affine_t<false>(q); }
+BPPP_HD PtX ptx_add_mixed(const PtX &p, const PtA &q) { return ptx_add_mixed_t<false>(p, q); }
 // to homogeneous projective: (X ZZZ : Y ZZ : ZZ ZZZ)
 BPPP_HD Pt ptx_to_pt(const PtX &p) {
     Pt r;
@@ -236,42 +240,84 @@ BPPP_HD PtJ ptj_identity() { PtJ r; r.x = fe_zero(); r.y = fe_zero(); r.z = fe_z
     BPPP_SET_MAG(r.x, 1); BPPP_SET_MAG(r.y, 1); BPPP_SET_MAG(r.z, 1); return r; }
 BPPP_HD PtJ ptj_from_affine(const PtA &a) { PtJ r; r.x = a.x; r.y = a.y; r.z = fe_one(); r.inf = false; return r; }
 // 2P (dbl-2009-l).  Coordinates in: x, y weak-normalised, z limbs <= 4 * 2^26.  The curve has odd order, so Y != 0 unless P = O.
-BPPP_HD PtJ ptj_double(const PtJ &p) {
+template <bool INL> BPPP_HD PtJ ptj_double_t(const PtJ &p) {
     PtJ r;
-    Fe A = fe_sqr(p.x), B = fe_sqr(p.y), C = fe_sqr(B);
-    Fe t = fe_sqr(fe_add(p.x, B));
+    Fe A = fe_sqr_t<INL>(p.x), B = fe_sqr_t<INL>(p.y), C = fe_sqr_t<INL>(B);
+    Fe t = fe_sqr_t<INL>(fe_add(p.x, B));
     Fe D = fe_normalize_weak(fe_mul_int(fe_sub(t, fe_add(A, C), 2), 2));       // 2 ((X+B)^2 - A - C)
     Fe E = fe_mul_int(A, 3);
-    Fe F = fe_sqr(E);
+    Fe F = fe_sqr_t<INL>(E);
     r.x = fe_normalize_weak(fe_sub(F, fe_mul_int(D, 2), 1));
-    r.y = fe_normalize_weak(fe_sub(fe_mul(E, fe_sub(D, r.x, 1)), fe_mul_int(C, 8), 8));
-    r.z = fe_mul_int(fe_mul(p.y, p.z), 2);
+    r.y = fe_normalize_weak(fe_sub(fe_mul_t<INL>(E, fe_sub(D, r.x, 1)), fe_mul_int(C, 8), 8));
+    r.z = fe_mul_int(fe_mul_t<INL>(p.y, p.z), 2);
     r.inf = p.inf;
     return r;
 }
 // P + Q, Q affine and not the identity
-BPPP_HD PtJ ptj_add_mixed(const PtJ &p, const PtA &q) {
+template <bool INL> BPPP_HD PtJ ptj_add_mixed_t(const PtJ &p, const PtA &q) {
     if (p.inf) return ptj_from_affine(q);
-    Fe Z1Z1 = fe_sqr(p.z);
-    Fe U2 = fe_mul(q.x, Z1Z1);
-    Fe S2 = fe_mul(fe_mul(q.y, p.z), Z1Z1);
+    Fe Z1Z1 = fe_sqr_t<INL>(p.z);
+    Fe U2 = fe_mul_t<INL>(q.x, Z1Z1);
+    Fe S2 = fe_mul_t<INL>(fe_mul_t<INL>(q.y, p.z), Z1Z1);
     Fe H = fe_sub(U2, p.x, 1);
     Fe Rh = fe_sub(S2, p.y, 1);                       // (S2 - Y1)
     if (fe_normalizes_to_zero(H)) {                   // same x: P1 = +-Q
-        if (fe_normalizes_to_zero(Rh)) return ptj_double(ptj_from_affine(q));
+        if (fe_normalizes_to_zero(Rh)) return ptj_double_t<INL>(ptj_from_affine(q));
         return ptj_identity();
     }
     PtJ r;
-    Fe HH = fe_sqr(H);
+    Fe HH = fe_sqr_t<INL>(H);
     Fe I = fe_mul_int(HH, 4);
-    Fe J = fe_mul(H, I);
+    Fe J = fe_mul_t<INL>(H, I);
     Fe rr = fe_mul_int(Rh, 2);
-    Fe V = fe_mul(p.x, I);
-    r.x = fe_normalize_weak(fe_sub(fe_sqr(rr), fe_add(J, fe_mul_int(V, 2)), 3));
-    r.y = fe_normalize_weak(fe_sub(fe_mul(rr, fe_sub(V, r.x, 1)), fe_mul_int(fe_mul(p.y, J), 2), 2));
-    r.z = fe_mul_int(fe_mul(p.z, H), 2);              // (Z1 + H)^2 - Z1Z1 - HH = 2 Z1 H
+    Fe V = fe_mul_t<INL>(p.x, I);
+    r.x = fe_normalize_weak(fe_sub(fe_sqr_t<INL>(rr), fe_add(J, fe_mul_int(V, 2)), 3));
+    r.y = fe_normalize_weak(fe_sub(fe_mul_t<INL>(rr, fe_sub(V, r.x, 1)), fe_mul_int(fe_mul_t<INL>(p.y, J), 2), 2));
+    r.z = fe_mul_int(fe_mul_t<INL>(p.z, H), 2);              // (Z1 + H)^2 - Z1Z1 - HH = 2 Z1 H
     r.inf = false;
     return r;
+}
+BPPP_HD PtJ ptj_double(const PtJ &p) { return ptj_double_t<false>(p); }
+BPPP_HD PtJ ptj_add_mixed(const PtJ &p, const PtA &q) { return ptj_add_mixed_t<false>(p, q); }
+// The accumulation loops call the *_hot forms.  With BPPP_PT_NOINLINE the call boundary moves from the field
+// multiplication up to the point operation: one real function per formula with its 7-11 field products inlined, so the
+// 16 + 8 argument / result moves of a by-value fe_mul call are paid once per point operation instead of once per
+// product, and ptxas can interleave the carry chains of independent products.
+// (BPPP_PT_NOINLINE selects all three; BPPP_PTJ_DBL_NOINLINE / BPPP_PTJ_ADD_NOINLINE / BPPP_PTX_ADD_NOINLINE one each.)
+#if defined(BPPP_PT_NOINLINE)
+#define BPPP_PTJ_DBL_NOINLINE 1
+#define BPPP_PTJ_ADD_NOINLINE 1
+#define BPPP_PTX_ADD_NOINLINE 1
+#endif
+#if defined(__CUDACC__) && defined(BPPP_PTJ_DBL_NOINLINE)
+static __device__ __noinline__ PtJ ptj_double_call(PtJ p) { return ptj_double_t<true>(p); }
+#endif
+#if defined(__CUDACC__) && defined(BPPP_PTJ_ADD_NOINLINE)
+static __device__ __noinline__ PtJ ptj_add_mixed_call(PtJ p, PtA q) { return ptj_add_mixed_t<true>(p, q); }
+#endif
+#if defined(__CUDACC__) && defined(BPPP_PTX_ADD_NOINLINE)
+static __device__ __noinline__ PtX ptx_add_mixed_call(PtX p, PtA q) { return ptx_add_mixed_t<true>(p, q); }
+#endif
+BPPP_HD PtJ ptj_double_hot(const PtJ &p) {
+#if defined(__CUDA_ARCH__) && defined(BPPP_PTJ_DBL_NOINLINE)
+    return ptj_double_call(p);
+#else
+    return ptj_double(p);
+#endif
+}
+BPPP_HD PtJ ptj_add_mixed_hot(const PtJ &p, const PtA &q) {
+#if defined(__CUDA_ARCH__) && defined(BPPP_PTJ_ADD_NOINLINE)
+    return ptj_add_mixed_call(p, q);
+#else
+    return ptj_add_mixed(p, q);
+#endif
+}
+BPPP_HD PtX ptx_add_mixed_hot(const PtX &p, const PtA &q) {
+#if defined(__CUDA_ARCH__) && defined(BPPP_PTX_ADD_NOINLINE)
+    return ptx_add_mixed_call(p, q);
+#else
+    return ptx_add_mixed(p, q);
+#endif
 }
 // to homogeneous projective (X Z : Y : Z^3)
 BPPP_HD Pt ptj_to_pt(const PtJ &p) {

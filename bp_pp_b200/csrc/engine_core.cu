@@ -14,6 +14,9 @@
 #ifndef BPPP_CORE_INLINE
 #define BPPP_FE_NOINLINE 1   // see fe.cuh: call-based fe_mul keeps the MSM loop inside the instruction cache
 #endif
+#ifndef BPPP_CORE_PT_INLINE
+#define BPPP_PT_NOINLINE 1   // ec.cuh: the XYZZ mixed addition of k_msm_fixed is one real function with its 10 products
+#endif                       // inlined (measured -6 % on the kernel; the Jacobian ladders are faster with per-product calls)
 #include "engine_common.cuh"
 
 using namespace bppp;

@@ -119,7 +119,7 @@ __device__ __forceinline__ Pt msm_accumulate_range(const uint32_t *pts, const ui
         PtA q;
         if (load_dev_point(q, pts, v & 0x7FFFFFFFu)) {
             if (v >> 31) q.y = fe_normalize_weak(fe_negate(q.y, 1));
-            acc = ptx_add_mixed(acc, q);
+            acc = ptx_add_mixed_hot(acc, q);
         }
     }
     return ptx_to_pt(acc);

@@ -358,22 +358,22 @@ BPPP_D void fe_merge_even_odd(uint32_t *T, const uint32_t *E, const uint32_t *O)
 }
 #endif
 
-BPPP_HD Fe fe_mul_inl(const Fe &a, const Fe &b) {
-    uint32_t T[16];
+// T[0..16) = a * b (8 x 8 limbs).  Shared with the scalar field (sc.cuh).
+BPPP_HD void wide_mul8(uint32_t T[16], const uint32_t a[8], const uint32_t b[8]) {
 #if defined(__CUDA_ARCH__)
     // E: products starting at even limb positions (index = position); O: odd positions (index = position - 1)
     uint32_t E[16], O[16];
     E[8] = 0;
-    fe_mul4(E, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
-    fe_mul4(O, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
+    fe_mul4(E, a[0], a[2], a[4], a[6], b[0]);
+    fe_mul4(O, a[1], a[3], a[5], a[7], b[0]);
 #pragma unroll
     for (int i = 1; i < 8; i++) {
         if (i & 1) {
-            fe_chain4_carry(O + i - 1, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i], O[i + 7]);
-            fe_chain4_top(E + i + 1, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i], E[i + 8]);
+            fe_chain4_carry(O + i - 1, a[0], a[2], a[4], a[6], b[i], O[i + 7]);
+            fe_chain4_top(E + i + 1, a[1], a[3], a[5], a[7], b[i], E[i + 8]);
         } else {
-            fe_chain4_carry(E + i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i], E[i + 8]);
-            fe_chain4_top(O + i, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i], O[i + 7]);
+            fe_chain4_carry(E + i, a[0], a[2], a[4], a[6], b[i], E[i + 8]);
+            fe_chain4_top(O + i, a[1], a[3], a[5], a[7], b[i], O[i + 7]);
         }
     }
     T[0] = E[0];
@@ -383,23 +383,20 @@ BPPP_HD Fe fe_mul_inl(const Fe &a, const Fe &b) {
     for (int i = 0; i < 8; i++) {
         uint64_t carry = 0;
         for (int j = 0; j < 8; j++) {
-            uint64_t t = (uint64_t)T[i + j] + (uint64_t)a.v[j] * b.v[i] + carry;
+            uint64_t t = (uint64_t)T[i + j] + (uint64_t)a[j] * b[i] + carry;
             T[i + j] = (uint32_t)t; carry = t >> 32;
         }
         T[i + 8] = (uint32_t)carry;
     }
 #endif
-    return fe_reduce512(T);
 }
-
-BPPP_HD Fe fe_sqr_inl(const Fe &a) {
-    uint32_t T[16];
+// T[0..16) = a^2
+BPPP_HD void wide_sqr8(uint32_t T[16], const uint32_t v[8]) {
 #if defined(__CUDA_ARCH__)
     // off-diagonal products a_i a_j (i < j) once, into the even / odd position accumulators
     uint32_t E[16], O[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) { E[k] = 0; O[k] = 0; }
-    const uint32_t *v = a.v;
     // row 0
     fe_mul4(O, v[1], v[3], v[5], v[7], v[0]);                            // positions 1 3 5 7
     asm volatile("mul.lo.u32 %0, %6, %9;\n\t mul.hi.u32 %1, %6, %9;\n\t mul.lo.u32 %2, %7, %9;\n\t mul.hi.u32 %3, %7, %9;\n\t mul.lo.u32 %4, %8, %9;\n\t mul.hi.u32 %5, %8, %9;"
@@ -439,16 +436,18 @@ BPPP_HD Fe fe_sqr_inl(const Fe &a) {
                    "+r"(T[12]), "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
                  : "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
 #else
-    for (int k = 0; k < 16; k++) T[k] = 0;
-    for (int i = 0; i < 8; i++) {
-        uint64_t carry = 0;
-        for (int j = 0; j < 8; j++) {
-            uint64_t t = (uint64_t)T[i + j] + (uint64_t)a.v[j] * a.v[i] + carry;
-            T[i + j] = (uint32_t)t; carry = t >> 32;
-        }
-        T[i + 8] = (uint32_t)carry;
-    }
+    wide_mul8(T, v, v);
 #endif
+}
+
+BPPP_HD Fe fe_mul_inl(const Fe &a, const Fe &b) {
+    uint32_t T[16];
+    wide_mul8(T, a.v, b.v);
+    return fe_reduce512(T);
+}
+BPPP_HD Fe fe_sqr_inl(const Fe &a) {
+    uint32_t T[16];
+    wide_sqr8(T, a.v);
     return fe_reduce512(T);
 }
 

@@ -283,7 +283,7 @@ BPPP_HD Pt straus_tables(const WS &w, size_t i, const int *tids, const Sc *ks, c
     for (int d = 32; d >= 0; d--) {
         if (d != 32) {
 #pragma unroll 1
-            for (int r = 0; r < 4; r++) acc = ptj_double(acc);
+            for (int r = 0; r < 4; r++) acc = ptj_double_hot(acc);
         }
 #pragma unroll 1
         for (int h = 0; h < 2 * NP; h++) {
@@ -295,7 +295,7 @@ BPPP_HD Pt straus_tables(const WS &w, size_t i, const int *tids, const Sc *ks, c
             if (fe_is_zero_canonical(q.x) && fe_is_zero_canonical(q.y)) continue;       // identity point: nothing to add
             if (sd < 0) q.y = fe_normalize_weak(fe_negate(q.y, 1));
             if (h & 1) q.x = fe_mul(q.x, beta);
-            acc = ptj_add_mixed(acc, q);
+            acc = ptj_add_mixed_hot(acc, q);
         }
     }
     return pt_add(ptj_to_pt(acc), init);

@@ -144,7 +144,7 @@ BPPP_HD Pt msm_fixed_lane(const FixedTable &T, const WS &w, size_t i, int sc_off
         }
         if (dcur != 0) {
             PtA q;
-            if (table_decode(q, cur)) acc = ptx_add_mixed(acc, q);
+            if (table_decode(q, cur)) acc = ptx_add_mixed_hot(acc, q);
         }
         cur = nxt; dcur = dnxt;
     }

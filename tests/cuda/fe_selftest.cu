@@ -7,10 +7,11 @@
 #include <cuda_runtime.h>
 #define BPPP_FE_NOINLINE 1
 #include "ec.cuh"
+#include "sc.cuh"
 using namespace bppp;
 
-enum { OP_MUL, OP_SQR, OP_ADD, OP_SUB, OP_NEG, OP_MULINT3, OP_MULINT8, OP_MULINT21, OP_NORM, OP_ISZERO, OP_EXPR, OP_INV, OP_PT, OP_PTJ, OP_PTX, OP_COUNT };
-static const char *NAMES[] = {"mul", "sqr", "add", "sub", "neg", "mul_int3", "mul_int8", "mul_int21", "normalize", "is_zero", "expr(calls)", "inv/sqrt", "pt rcb", "pt jacobian", "pt xyzz"};
+enum { OP_MUL, OP_SQR, OP_ADD, OP_SUB, OP_NEG, OP_MULINT3, OP_MULINT8, OP_MULINT21, OP_NORM, OP_ISZERO, OP_EXPR, OP_INV, OP_PT, OP_PTJ, OP_PTX, OP_SCMUL, OP_SCSQR, OP_SCWIDE, OP_SCINV, OP_COUNT };
+static const char *NAMES[] = {"mul", "sqr", "add", "sub", "neg", "mul_int3", "mul_int8", "mul_int21", "normalize", "is_zero", "expr(calls)", "inv/sqrt", "pt rcb", "pt jacobian", "pt xyzz", "sc_mul", "sc_sqr", "sc_reduce512", "sc_inv"};
 
 __host__ __device__ inline Fe apply(int op, const Fe &a, const Fe &b) {
     switch (op) {
@@ -43,7 +44,11 @@ __host__ __device__ inline Fe apply(int op, const Fe &a, const Fe &b) {
         PtJ r = ptj_add_mixed(ptj_double(ptj_double(p)), q);
         return fe_add(fe_add(r.x, r.y), r.z);
     }
-    default: {
+    case OP_SCMUL: { Sc x, y; for (int k = 0; k < 8; k++) { x.v[k] = a.v[k]; y.v[k] = b.v[k]; } Sc r = sc_mul(x, y); return fe_from_words(r.v); }
+    case OP_SCSQR: { Sc x; for (int k = 0; k < 8; k++) x.v[k] = a.v[k]; Sc r = sc_sqr(x); return fe_from_words(r.v); }
+    case OP_SCWIDE: { uint32_t t[16]; for (int k = 0; k < 8; k++) { t[k] = a.v[k]; t[8 + k] = b.v[k]; } Sc r = sc_reduce512(t); return fe_from_words(r.v); }
+    case OP_SCINV: { Sc x; for (int k = 0; k < 8; k++) x.v[k] = a.v[k]; x.v[7] &= 0x7FFFFFFFu; Sc r = sc_inv(x); return fe_from_words(r.v); }
+    case OP_PTX: {
         PtX p = ptx_identity();
         PtA q; q.x = b; q.y = a;
         PtA q2; q2.x = a; q2.y = b;
@@ -52,6 +57,7 @@ __host__ __device__ inline Fe apply(int op, const Fe &a, const Fe &b) {
         return fe_add(fe_add(r.x, r.y), r.z);
     }
     }
+    return fe_zero();
 }
 __global__ void k_apply(int op, const Fe *a, const Fe *b, Fe *r, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

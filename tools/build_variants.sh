@@ -9,13 +9,11 @@ build() { # name  var_flags  core_flags
   ( $NV $2 -Xptxas -v -c -o _obj/var/${name}_var.o engine_var.cu 2> _obj/var/${name}_var.log ) &
   ( $NV $3 -Xptxas -v -c -o _obj/var/${name}_core.o engine_core.cu 2> _obj/var/${name}_core.log ) &
   wait
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libbppp_${name}.so _obj/var/${name}_var.o _obj/var/${name}_core.o _obj/engine_verify.o _obj/engine_prove.o _obj/engine_bench.o
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libbppp_${name}.so _obj/var/${name}_var.o _obj/var/${name}_core.o _obj/engine_verify.o _obj/engine_prove.o _obj/engine_bench.o _obj/engine_msm.o _obj/engine_wnla.o _obj/engine_circuit.o
   echo built $name
   grep -h -A2 "k_v_var2\|k_msm_fixed" _obj/var/${name}_var.log _obj/var/${name}_core.log | grep -E "Used|spill" | paste - - | sed 's/ptxas info    ://g' | cut -c1-200
 }
 rm -f ../variants/*.so
-build mb8   "-DBPPP_VAR_MINBLOCKS=8"  "-DBPPP_MSM_MINBLOCKS=8" &
-build mb9   "-DBPPP_VAR_MINBLOCKS=9"  "-DBPPP_MSM_MINBLOCKS=9" &
-build mb10  "-DBPPP_VAR_MINBLOCKS=10" "-DBPPP_MSM_MINBLOCKS=10" &
-build mb12  "-DBPPP_VAR_MINBLOCKS=12" "-DBPPP_MSM_MINBLOCKS=12" &
+build dblc   "-DBPPP_PTJ_DBL_NOINLINE"  "" &
+build addc   "-DBPPP_PTJ_ADD_NOINLINE"  "" &
 wait
