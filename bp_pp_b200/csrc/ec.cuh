@@ -173,8 +173,12 @@ BPPP_HD void pta_to_xy64(uint8_t out[64], const PtA &a_canonical, bool is_identi
 // fixed-base and Pippenger accumulation loops are made of.  The formula is incomplete, so the exceptional inputs are
 // handled explicitly and exactly (scalars chosen by an adversarial prover can steer an accumulator onto them):
 // identity accumulator (flag), P1 == Q (affine doubling), P1 == -Q (identity).
-template <bool INL> BPPP_HD Fe fe_mul_t(const Fe &a, const Fe &b) { if (INL) return fe_mul_inl(a, b); return fe_mul(a, b); }
-template <bool INL> BPPP_HD Fe fe_sqr_t(const Fe &a) { if (INL) return fe_sqr_inl(a); return fe_sqr(a); }
+// INL = true: field operations inlined into the point formula and branch-free (see fe_fold_add); false: the default
+// call-based products and short-fold additions
+template <bool INL> BPPP_HD Fe fe_mul_t(const Fe &a, const Fe &b) { if (INL) return fe_mul_inl_t<false>(a, b); return fe_mul(a, b); }
+// fe_sub with the ignored magnitude argument of the formulas
+template <bool BR> BPPP_HD Fe fe_subm_t(const Fe &a, const Fe &b, int = 0) { return fe_sub_t<BR>(a, b); }
+template <bool INL> BPPP_HD Fe fe_sqr_t(const Fe &a) { if (INL) return fe_sqr_inl_t<false>(a); return fe_sqr(a); }
 struct PtX {
     Fe x, y, zz, zzz;
     bool inf;
@@ -184,13 +188,13 @@ BPPP_HD PtX ptx_identity() { PtX r; r.x = fe_zero(); r.y = fe_zero(); r.zz = fe_
 // 2Q for affine Q (mdbl-2008-s-1)
 template <bool INL> BPPP_HD PtX ptx_double_affine_t(const PtA &q) {
     PtX r;
-    Fe U = fe_mul_int(q.y, 2);                       // 2y            mag 2
+    Fe U = fe_mul_int_t<!INL>(q.y, 2);                       // 2y            mag 2
     Fe V = fe_sqr_t<INL>(U);                                // 4y^2
     Fe W = fe_mul_t<INL>(U, V);                             // 8y^3
     Fe S = fe_mul_t<INL>(q.x, V);
-    Fe M = fe_mul_int(fe_sqr_t<INL>(q.x), 3);               // 3x^2          mag 3
-    r.x = fe_normalize_weak(fe_sub(fe_sqr_t<INL>(M), fe_mul_int(S, 2), 2));
-    r.y = fe_normalize_weak(fe_sub(fe_mul_t<INL>(M, fe_sub(S, r.x, 1)), fe_mul_t<INL>(W, q.y), 1));
+    Fe M = fe_mul_int_t<!INL>(fe_sqr_t<INL>(q.x), 3);               // 3x^2          mag 3
+    r.x = fe_normalize_weak(fe_subm_t<!INL>(fe_sqr_t<INL>(M), fe_mul_int_t<!INL>(S, 2), 2));
+    r.y = fe_normalize_weak(fe_subm_t<!INL>(fe_mul_t<INL>(M, fe_subm_t<!INL>(S, r.x, 1)), fe_mul_t<INL>(W, q.y), 1));
     r.zz = V; r.zzz = W;
     r.inf = fe_normalizes_to_zero(q.y);              // cannot happen on an odd-order curve; kept for exactness
     return r;
@@ -201,8 +205,8 @@ template <bool INL> BPPP_HD PtX ptx_add_mixed_t(const PtX &p, const PtA &q) {
     if (p.inf) { r.x = q.x; r.y = q.y; r.zz = fe_one(); r.zzz = fe_one(); r.inf = false; return r; }
     Fe U2 = fe_mul_t<INL>(q.x, p.zz);
     Fe S2 = fe_mul_t<INL>(q.y, p.zzz);
-    Fe P = fe_sub(U2, p.x, 1);                       // mag 3
-    Fe R = fe_sub(S2, p.y, 1);                       // mag 3
+    Fe P = fe_subm_t<!INL>(U2, p.x, 1);                       // mag 3
+    Fe R = fe_subm_t<!INL>(S2, p.y, 1);                       // mag 3
     if (fe_normalizes_to_zero(P)) {                  // same x: P1 = +-Q
         if (fe_normalizes_to_zero(R)) return ptx_double_affine_t<INL>(q);
         return ptx_identity();
@@ -211,8 +215,8 @@ template <bool INL> BPPP_HD PtX ptx_add_mixed_t(const PtX &p, const PtA &q) {
     Fe PPP = fe_mul_t<INL>(P, PP);
     Fe Q = fe_mul_t<INL>(p.x, PP);
     Fe RR = fe_sqr_t<INL>(R);
-    r.x = fe_normalize_weak(fe_sub(RR, fe_add(PPP, fe_mul_int(Q, 2)), 3));
-    r.y = fe_normalize_weak(fe_sub(fe_mul_t<INL>(R, fe_sub(Q, r.x, 1)), fe_mul_t<INL>(p.y, PPP), 1));
+    r.x = fe_normalize_weak(fe_subm_t<!INL>(RR, fe_add_t<!INL>(PPP, fe_mul_int_t<!INL>(Q, 2)), 3));
+    r.y = fe_normalize_weak(fe_subm_t<!INL>(fe_mul_t<INL>(R, fe_subm_t<!INL>(Q, r.x, 1)), fe_mul_t<INL>(p.y, PPP), 1));
     r.zz = fe_mul_t<INL>(p.zz, PP);
     r.zzz = fe_mul_t<INL>(p.zzz, PPP);
     r.inf = false;
@@ -243,13 +247,13 @@ BPPP_HD PtJ ptj_from_affine(const PtA &a) { PtJ r; r.x = a.x; r.y = a.y; r.z = f
 template <bool INL> BPPP_HD PtJ ptj_double_t(const PtJ &p) {
     PtJ r;
     Fe A = fe_sqr_t<INL>(p.x), B = fe_sqr_t<INL>(p.y), C = fe_sqr_t<INL>(B);
-    Fe t = fe_sqr_t<INL>(fe_add(p.x, B));
-    Fe D = fe_normalize_weak(fe_mul_int(fe_sub(t, fe_add(A, C), 2), 2));       // 2 ((X+B)^2 - A - C)
-    Fe E = fe_mul_int(A, 3);
+    Fe t = fe_sqr_t<INL>(fe_add_t<!INL>(p.x, B));
+    Fe D = fe_normalize_weak(fe_mul_int_t<!INL>(fe_subm_t<!INL>(t, fe_add_t<!INL>(A, C), 2), 2));       // 2 ((X+B)^2 - A - C)
+    Fe E = fe_mul_int_t<!INL>(A, 3);
     Fe F = fe_sqr_t<INL>(E);
-    r.x = fe_normalize_weak(fe_sub(F, fe_mul_int(D, 2), 1));
-    r.y = fe_normalize_weak(fe_sub(fe_mul_t<INL>(E, fe_sub(D, r.x, 1)), fe_mul_int(C, 8), 8));
-    r.z = fe_mul_int(fe_mul_t<INL>(p.y, p.z), 2);
+    r.x = fe_normalize_weak(fe_subm_t<!INL>(F, fe_mul_int_t<!INL>(D, 2), 1));
+    r.y = fe_normalize_weak(fe_subm_t<!INL>(fe_mul_t<INL>(E, fe_subm_t<!INL>(D, r.x, 1)), fe_mul_int_t<!INL>(C, 8), 8));
+    r.z = fe_mul_int_t<!INL>(fe_mul_t<INL>(p.y, p.z), 2);
     r.inf = p.inf;
     return r;
 }
@@ -259,21 +263,21 @@ template <bool INL> BPPP_HD PtJ ptj_add_mixed_t(const PtJ &p, const PtA &q) {
     Fe Z1Z1 = fe_sqr_t<INL>(p.z);
     Fe U2 = fe_mul_t<INL>(q.x, Z1Z1);
     Fe S2 = fe_mul_t<INL>(fe_mul_t<INL>(q.y, p.z), Z1Z1);
-    Fe H = fe_sub(U2, p.x, 1);
-    Fe Rh = fe_sub(S2, p.y, 1);                       // (S2 - Y1)
+    Fe H = fe_subm_t<!INL>(U2, p.x, 1);
+    Fe Rh = fe_subm_t<!INL>(S2, p.y, 1);                       // (S2 - Y1)
     if (fe_normalizes_to_zero(H)) {                   // same x: P1 = +-Q
         if (fe_normalizes_to_zero(Rh)) return ptj_double_t<INL>(ptj_from_affine(q));
         return ptj_identity();
     }
     PtJ r;
     Fe HH = fe_sqr_t<INL>(H);
-    Fe I = fe_mul_int(HH, 4);
+    Fe I = fe_mul_int_t<!INL>(HH, 4);
     Fe J = fe_mul_t<INL>(H, I);
-    Fe rr = fe_mul_int(Rh, 2);
+    Fe rr = fe_mul_int_t<!INL>(Rh, 2);
     Fe V = fe_mul_t<INL>(p.x, I);
-    r.x = fe_normalize_weak(fe_sub(fe_sqr_t<INL>(rr), fe_add(J, fe_mul_int(V, 2)), 3));
-    r.y = fe_normalize_weak(fe_sub(fe_mul_t<INL>(rr, fe_sub(V, r.x, 1)), fe_mul_int(fe_mul_t<INL>(p.y, J), 2), 2));
-    r.z = fe_mul_int(fe_mul_t<INL>(p.z, H), 2);              // (Z1 + H)^2 - Z1Z1 - HH = 2 Z1 H
+    r.x = fe_normalize_weak(fe_subm_t<!INL>(fe_sqr_t<INL>(rr), fe_add_t<!INL>(J, fe_mul_int_t<!INL>(V, 2)), 3));
+    r.y = fe_normalize_weak(fe_subm_t<!INL>(fe_mul_t<INL>(rr, fe_subm_t<!INL>(V, r.x, 1)), fe_mul_int_t<!INL>(fe_mul_t<INL>(p.y, J), 2), 2));
+    r.z = fe_mul_int_t<!INL>(fe_mul_t<INL>(p.z, H), 2);              // (Z1 + H)^2 - Z1Z1 - HH = 2 Z1 H
     r.inf = false;
     return r;
 }

@@ -109,6 +109,114 @@ BPPP_HD void fe_add_fold_low(Fe &r, uint32_t b) {
 #endif
 }
 
+
+// r += k * (2^32 + 977) over all eight limbs, returns the carry out of 2^256 (k * 977 < 2^32)
+BPPP_HD uint32_t fe_add_fold_k(Fe &r, uint32_t k) {
+    uint32_t c;
+#if defined(__CUDA_ARCH__)
+    asm volatile("mad.lo.cc.u32 %0, %9, 977, %0;\n\t addc.cc.u32 %1, %1, %9;\n\t addc.cc.u32 %2, %2, 0;\n\t addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t addc.cc.u32 %5, %5, 0;\n\t addc.cc.u32 %6, %6, 0;\n\t addc.cc.u32 %7, %7, 0;\n\t addc.u32 %8, 0, 0;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "=r"(c)
+        : "r"(k));
+#else
+    uint64_t t = (uint64_t)r.v[0] + (uint64_t)k * FE_C0; r.v[0] = (uint32_t)t;
+    t = (t >> 32) + r.v[1] + k; r.v[1] = (uint32_t)t;
+    for (int i = 2; i < 8; i++) { t = (t >> 32) + r.v[i]; r.v[i] = (uint32_t)t; }
+    c = (uint32_t)(t >> 32);
+#endif
+    return c;
+}
+// r -= k * (2^32 + 977), k in {0, 1}, straight-line: full borrow chain, then the second subtraction a wrap needs
+BPPP_HD void fe_sub_fold_full(Fe &r, uint32_t k) {
+#if defined(__CUDA_ARCH__)
+    uint32_t k0 = k * FE_C0, bw2;
+    asm volatile("sub.cc.u32 %0, %0, %9;\n\t subc.cc.u32 %1, %1, %10;\n\t subc.cc.u32 %2, %2, 0;\n\t subc.cc.u32 %3, %3, 0;\n\t"
+        "subc.cc.u32 %4, %4, 0;\n\t subc.cc.u32 %5, %5, 0;\n\t subc.cc.u32 %6, %6, 0;\n\t subc.cc.u32 %7, %7, 0;\n\t subc.u32 %8, 0, 0;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "=r"(bw2)
+        : "r"(k0), "r"(k));
+    bw2 &= 1u;
+    uint32_t k2 = bw2 * FE_C0;
+    asm volatile("sub.cc.u32 %0, %0, %3;\n\t subc.cc.u32 %1, %1, %4;\n\t subc.u32 %2, %2, 0;" : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]) : "r"(k2), "r"(bw2));
+#else
+    int64_t t = (int64_t)r.v[0] - (int64_t)(k * FE_C0); r.v[0] = (uint32_t)t;
+    t = (int64_t)r.v[1] - k + (t >> 32); r.v[1] = (uint32_t)t;
+    for (int i = 2; i < 8; i++) { t = (int64_t)r.v[i] + (t >> 32); r.v[i] = (uint32_t)t; }
+    uint32_t bw2 = (uint32_t)((t >> 32) & 1);
+    if (bw2) { BPPP_ASSERT((r.v[3] & r.v[4] & r.v[5] & r.v[6] & r.v[7]) == 0xFFFFFFFFu && r.v[2] >= 0xFFFFFFF0u); }
+    t = (int64_t)r.v[0] - (int64_t)(bw2 * FE_C0); r.v[0] = (uint32_t)t;
+    t = (int64_t)r.v[1] - bw2 + (t >> 32); r.v[1] = (uint32_t)t;
+    t = (int64_t)r.v[2] + (t >> 32); r.v[2] = (uint32_t)t;
+    BPPP_ASSERT((t >> 32) == 0);
+#endif
+}
+
+#if defined(__CUDACC__)
+#define BPPP_HD_NOINLINE static __host__ __device__ __noinline__
+#else
+#define BPPP_HD_NOINLINE static inline
+#endif
+// Out-of-line tails of the short folds below (taken with probability ~2^-32 per operation).
+// A carry of 1 enters limb 3; if it runs off the top the value wrapped past 2^256 and is tiny: add 2^32 + 977 once more.
+BPPP_HD_NOINLINE Fe fe_carry_slow(Fe r) {
+    uint64_t t = 1;
+    for (int i = 3; i < 8; i++) { t += r.v[i]; r.v[i] = (uint32_t)t; t >>= 32; }
+    fe_add_fold_low(r, (uint32_t)t);
+    return r;
+}
+// A borrow of 1 enters limb 3; if it runs off the top the value was below 2^32 + 977 before the subtraction and is now
+// just under 2^256: subtract 2^32 + 977 once more (only limbs 0..2 change).
+BPPP_HD_NOINLINE Fe fe_borrow_slow(Fe r) {
+    int64_t t = -1;
+    for (int i = 3; i < 8; i++) { t += r.v[i]; r.v[i] = (uint32_t)t; t >>= 32; }
+    if (t) {
+        BPPP_ASSERT((r.v[3] & r.v[4] & r.v[5] & r.v[6] & r.v[7]) == 0xFFFFFFFFu);
+        int64_t u = (int64_t)r.v[0] - FE_C0; r.v[0] = (uint32_t)u;
+        u = (int64_t)r.v[1] - 1 + (u >> 32); r.v[1] = (uint32_t)u;
+        u = (int64_t)r.v[2] + (u >> 32); r.v[2] = (uint32_t)u;
+        BPPP_ASSERT((u >> 32) == 0);
+    }
+    return r;
+}
+// r += k (2^32 + 977) for a small k (k * 977 < 2^32).  BR = true: three limbs and a rarely taken branch (best inside
+// the call-based field functions); BR = false: straight-line full-width chains (best where several field operations are
+// inlined into one block and ptxas interleaves them -- a branch would end the scheduling region).
+template <bool BR>
+BPPP_HD void fe_fold_add(Fe &r, uint32_t k) {
+    if (!BR) {
+        uint32_t c2 = fe_add_fold_k(r, k);
+        fe_add_fold_low(r, c2);
+        return;
+    }
+    uint32_t c;
+#if defined(__CUDA_ARCH__)
+    asm volatile("mad.lo.cc.u32 %0, %4, 977, %0;\n\t addc.cc.u32 %1, %1, %4;\n\t addc.cc.u32 %2, %2, 0;\n\t addc.u32 %3, 0, 0;"
+                 : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "=r"(c) : "r"(k));
+#else
+    uint64_t t = (uint64_t)r.v[0] + (uint64_t)k * FE_C0; r.v[0] = (uint32_t)t;
+    t = (t >> 32) + r.v[1] + k; r.v[1] = (uint32_t)t;
+    t = (t >> 32) + r.v[2]; r.v[2] = (uint32_t)t;
+    c = (uint32_t)(t >> 32);
+#endif
+    if (__builtin_expect(c != 0, 0)) r = fe_carry_slow(r);
+}
+// r -= k (2^32 + 977) for k in {0, 1}
+template <bool BR>
+BPPP_HD void fe_fold_sub(Fe &r, uint32_t k) {
+    if (!BR) { fe_sub_fold_full(r, k); return; }
+    uint32_t b;
+#if defined(__CUDA_ARCH__)
+    uint32_t k0 = k * FE_C0;
+    asm volatile("sub.cc.u32 %0, %0, %4;\n\t subc.cc.u32 %1, %1, %5;\n\t subc.cc.u32 %2, %2, 0;\n\t subc.u32 %3, 0, 0;"
+                 : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "=r"(b) : "r"(k0), "r"(k));
+#else
+    int64_t t = (int64_t)r.v[0] - (int64_t)(k * FE_C0); r.v[0] = (uint32_t)t;
+    t = (int64_t)r.v[1] - k + (t >> 32); r.v[1] = (uint32_t)t;
+    t = (int64_t)r.v[2] + (t >> 32); r.v[2] = (uint32_t)t;
+    b = (uint32_t)((t >> 32) & 1);
+#endif
+    if (__builtin_expect(b != 0, 0)) r = fe_borrow_slow(r);
+}
+
 // canonical representative in [0, p):  v >= p  <=>  v + (2^32 + 977) carries out of 2^256, and then v - p is that sum
 BPPP_HD Fe fe_normalize(const Fe &a) {
     Fe t = a;
@@ -147,7 +255,8 @@ BPPP_HD bool fe_equal_canonical(const Fe &a, const Fe &b) {
 }
 BPPP_HD bool fe_is_odd_canonical(const Fe &a) { return a.v[0] & 1u; }
 
-BPPP_HD Fe fe_add(const Fe &a, const Fe &b) {
+template <bool BR>
+BPPP_HD Fe fe_add_t(const Fe &a, const Fe &b) {
     Fe r;
     uint32_t c;
 #if defined(__CUDA_ARCH__)
@@ -161,14 +270,14 @@ BPPP_HD Fe fe_add(const Fe &a, const Fe &b) {
     for (int i = 0; i < 8; i++) { t = (t >> 32) + a.v[i] + b.v[i]; r.v[i] = (uint32_t)t; }
     c = (uint32_t)(t >> 32);
 #endif
-    // a + b - 2^256 + (2^32 + 977); a second wrap needs a, b both in [p, 2^256) and then leaves a residue < 2^34
-    uint32_t c2 = fe_add_fold(r, c);
-    fe_add_fold_low(r, c2);
+    fe_fold_add<BR>(r, c);    // carried: a + b - 2^256 + (2^32 + 977)
     return r;
 }
+BPPP_HD Fe fe_add(const Fe &a, const Fe &b) { return fe_add_t<true>(a, b); }
 
 // a - b (the magnitude argument of the lazy representation is ignored)
-BPPP_HD Fe fe_sub(const Fe &a, const Fe &b, int = 0) {
+template <bool BR>
+BPPP_HD Fe fe_sub_t(const Fe &a, const Fe &b) {
     Fe r;
     uint32_t bw;   // 0 or 1
 #if defined(__CUDA_ARCH__)
@@ -178,39 +287,31 @@ BPPP_HD Fe fe_sub(const Fe &a, const Fe &b, int = 0) {
         : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
           "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
     bw &= 1u;   // subc yields 0 - 0 - borrow = 0 or 0xFFFFFFFF
-    // borrowed: r = a - b + 2^256, subtract 2^32 + 977 to make it a - b + p
-    uint32_t k0 = bw * FE_C0, bw2;
-    asm volatile("sub.cc.u32 %0, %0, %9;\n\t subc.cc.u32 %1, %1, %10;\n\t subc.cc.u32 %2, %2, 0;\n\t subc.cc.u32 %3, %3, 0;\n\t"
-        "subc.cc.u32 %4, %4, 0;\n\t subc.cc.u32 %5, %5, 0;\n\t subc.cc.u32 %6, %6, 0;\n\t subc.cc.u32 %7, %7, 0;\n\t subc.u32 %8, 0, 0;"
-        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "=r"(bw2)
-        : "r"(k0), "r"(bw));
-    bw2 &= 1u;
-    // second borrow (a - b + 2^256 < 2^32 + 977, i.e. b > a + p): r is now within 2^34 of 2^256, subtract once more;
-    // only the low three limbs can change
-    uint32_t k2 = bw2 * FE_C0;
-    asm volatile("sub.cc.u32 %0, %0, %3;\n\t subc.cc.u32 %1, %1, %4;\n\t subc.u32 %2, %2, 0;" : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]) : "r"(k2), "r"(bw2));
 #else
     int64_t t = 0;
     for (int i = 0; i < 8; i++) { t = (int64_t)a.v[i] - b.v[i] + (t >> 32); r.v[i] = (uint32_t)t; }
     bw = (uint32_t)((t >> 32) & 1);
-    t = (int64_t)r.v[0] - (int64_t)(bw * FE_C0); r.v[0] = (uint32_t)t;
-    t = (int64_t)r.v[1] - bw + (t >> 32); r.v[1] = (uint32_t)t;
-    for (int i = 2; i < 8; i++) { t = (int64_t)r.v[i] + (t >> 32); r.v[i] = (uint32_t)t; }
-    uint32_t bw2 = (uint32_t)((t >> 32) & 1);
-    if (bw2) { BPPP_ASSERT((r.v[3] & r.v[4] & r.v[5] & r.v[6] & r.v[7]) == 0xFFFFFFFFu && r.v[2] >= 0xFFFFFFF0u); }
-    t = (int64_t)r.v[0] - (int64_t)(bw2 * FE_C0); r.v[0] = (uint32_t)t;
-    t = (int64_t)r.v[1] - bw2 + (t >> 32); r.v[1] = (uint32_t)t;
-    t = (int64_t)r.v[2] + (t >> 32); r.v[2] = (uint32_t)t;
-    BPPP_ASSERT((t >> 32) == 0);
 #endif
+    fe_fold_sub<BR>(r, bw);   // borrowed: a - b + 2^256 - (2^32 + 977) = a - b + p
     return r;
 }
+BPPP_HD Fe fe_sub(const Fe &a, const Fe &b, int = 0) { return fe_sub_t<true>(a, b); }
 BPPP_HD Fe fe_negate(const Fe &a, int = 0) { return fe_sub(fe_zero(), a); }
 
-// a * k for a small constant k (k * 977 must fit 32 bits)
-BPPP_HD Fe fe_mul_int(const Fe &a, uint32_t k) {
+// a * k for a small constant k (k * 977 must fit 32 bits); powers of two are funnel shifts
+template <bool BR>
+BPPP_HD Fe fe_mul_int_t(const Fe &a, uint32_t k) {
     Fe r;
     uint32_t top;
+    if (k == 2 || k == 4 || k == 8) {
+        const int sh = k == 2 ? 1 : (k == 4 ? 2 : 3);
+        top = a.v[7] >> (32 - sh);
+#pragma unroll
+        for (int i = 7; i > 0; i--) r.v[i] = (a.v[i] << sh) | (a.v[i - 1] >> (32 - sh));
+        r.v[0] = a.v[0] << sh;
+        fe_fold_add<BR>(r, top);
+        return r;
+    }
 #if defined(__CUDA_ARCH__)
     asm volatile("mul.lo.u32 %0, %9, %17;\n\t mul.hi.u32 %1, %9, %17;\n\t mul.lo.u32 %2, %11, %17;\n\t mul.hi.u32 %3, %11, %17;\n\t"
         "mul.lo.u32 %4, %13, %17;\n\t mul.hi.u32 %5, %13, %17;\n\t mul.lo.u32 %6, %15, %17;\n\t mul.hi.u32 %7, %15, %17;\n\t"
@@ -218,25 +319,16 @@ BPPP_HD Fe fe_mul_int(const Fe &a, uint32_t k) {
         "madc.lo.cc.u32 %5, %14, %17, %5;\n\t madc.hi.cc.u32 %6, %14, %17, %6;\n\t madc.lo.cc.u32 %7, %16, %17, %7;\n\t madc.hi.u32 %8, %16, %17, 0;"
         : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]), "=&r"(r.v[7]), "=&r"(top)
         : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]), "r"(k));
-    // fold top (< k): r += top * (2^32 + 977)
-    uint32_t c;
-    asm volatile("mad.lo.cc.u32 %0, %9, 977, %0;\n\t addc.cc.u32 %1, %1, %9;\n\t addc.cc.u32 %2, %2, 0;\n\t addc.cc.u32 %3, %3, 0;\n\t"
-        "addc.cc.u32 %4, %4, 0;\n\t addc.cc.u32 %5, %5, 0;\n\t addc.cc.u32 %6, %6, 0;\n\t addc.cc.u32 %7, %7, 0;\n\t addc.u32 %8, 0, 0;"
-        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "=r"(c)
-        : "r"(top));
 #else
     BPPP_ASSERT((uint64_t)k * FE_C0 <= 0xFFFFFFFFull);
     uint64_t t = 0;
     for (int i = 0; i < 8; i++) { t = (t >> 32) + (uint64_t)a.v[i] * k; r.v[i] = (uint32_t)t; }
     top = (uint32_t)(t >> 32);
-    t = (uint64_t)r.v[0] + (uint64_t)top * FE_C0; r.v[0] = (uint32_t)t;
-    t = (t >> 32) + r.v[1] + top; r.v[1] = (uint32_t)t;
-    for (int i = 2; i < 8; i++) { t = (t >> 32) + r.v[i]; r.v[i] = (uint32_t)t; }
-    uint32_t c = (uint32_t)(t >> 32);
 #endif
-    fe_add_fold_low(r, c);
+    fe_fold_add<BR>(r, top);  // top < k
     return r;
 }
+BPPP_HD Fe fe_mul_int(const Fe &a, uint32_t k) { return fe_mul_int_t<true>(a, k); }
 BPPP_HD Fe fe_cmov(const Fe &a, const Fe &b, bool take_b) {
     Fe r;
 #pragma unroll
@@ -247,6 +339,7 @@ BPPP_HD Fe fe_cmov(const Fe &a, const Fe &b, bool take_b) {
 // ---- 512-bit product -> Fe ------------------------------------------------------------------------------------
 // T = L + 2^256 H  ->  L + H * (2^32 + 977): first fold leaves a 34-bit overflow V, second fold a possible single
 // carry whose residue is below 2^68.
+template <bool BR>
 BPPP_HD Fe fe_reduce512(uint32_t T[16]) {
     Fe r;
 #if defined(__CUDA_ARCH__)
@@ -272,13 +365,21 @@ BPPP_HD Fe fe_reduce512(uint32_t T[16]) {
     asm volatile("mul.lo.u32 %0, %3, 977;\n\t mul.hi.u32 %1, %3, 977;\n\t mad.lo.u32 %1, %4, 977, %1;\n\t add.cc.u32 %1, %1, %3;\n\t addc.u32 %2, %4, 0;"
         : "=&r"(W0), "=&r"(W1), "=&r"(W2) : "r"(R8), "r"(R9));
     uint32_t c2;
-    asm volatile("add.cc.u32 %0, %0, %9;\n\t addc.cc.u32 %1, %1, %10;\n\t addc.cc.u32 %2, %2, %11;\n\t addc.cc.u32 %3, %3, 0;\n\t"
-        "addc.cc.u32 %4, %4, 0;\n\t addc.cc.u32 %5, %5, 0;\n\t addc.cc.u32 %6, %6, 0;\n\t addc.cc.u32 %7, %7, 0;\n\t addc.u32 %8, 0, 0;"
-        : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]), "=r"(c2)
-        : "r"(W0), "r"(W1), "r"(W2));
+    if (BR) {
+        asm volatile("add.cc.u32 %0, %0, %4;\n\t addc.cc.u32 %1, %1, %5;\n\t addc.cc.u32 %2, %2, %6;\n\t addc.u32 %3, 0, 0;"
+            : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "=r"(c2) : "r"(W0), "r"(W1), "r"(W2));
 #pragma unroll
-    for (int k = 0; k < 8; k++) r.v[k] = T[k];
-    fe_add_fold_low(r, c2);
+        for (int k = 0; k < 8; k++) r.v[k] = T[k];
+        if (__builtin_expect(c2 != 0, 0)) r = fe_carry_slow(r);
+    } else {
+        asm volatile("add.cc.u32 %0, %0, %9;\n\t addc.cc.u32 %1, %1, %10;\n\t addc.cc.u32 %2, %2, %11;\n\t addc.cc.u32 %3, %3, 0;\n\t"
+            "addc.cc.u32 %4, %4, 0;\n\t addc.cc.u32 %5, %5, 0;\n\t addc.cc.u32 %6, %6, 0;\n\t addc.cc.u32 %7, %7, 0;\n\t addc.u32 %8, 0, 0;"
+            : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]), "=r"(c2)
+            : "r"(W0), "r"(W1), "r"(W2));
+#pragma unroll
+        for (int k = 0; k < 8; k++) r.v[k] = T[k];
+        fe_add_fold_low(r, c2);
+    }
 #else
     // same steps with 64-bit temporaries
     uint64_t t = 0, R[10];
@@ -300,8 +401,8 @@ BPPP_HD Fe fe_reduce512(uint32_t T[16]) {
     t = R[0] + W0; r.v[0] = (uint32_t)t;
     t = (t >> 32) + R[1] + W1; r.v[1] = (uint32_t)t;
     t = (t >> 32) + R[2] + W2; r.v[2] = (uint32_t)t;
-    for (int k = 3; k < 8; k++) { t = (t >> 32) + R[k]; r.v[k] = (uint32_t)t; }
-    fe_add_fold_low(r, (uint32_t)(t >> 32));
+    for (int k = 3; k < 8; k++) r.v[k] = (uint32_t)R[k];
+    if (t >> 32) r = fe_carry_slow(r);
 #endif
     return r;
 }
@@ -440,16 +541,20 @@ BPPP_HD void wide_sqr8(uint32_t T[16], const uint32_t v[8]) {
 #endif
 }
 
-BPPP_HD Fe fe_mul_inl(const Fe &a, const Fe &b) {
+template <bool BR>
+BPPP_HD Fe fe_mul_inl_t(const Fe &a, const Fe &b) {
     uint32_t T[16];
     wide_mul8(T, a.v, b.v);
-    return fe_reduce512(T);
+    return fe_reduce512<BR>(T);
 }
-BPPP_HD Fe fe_sqr_inl(const Fe &a) {
+template <bool BR>
+BPPP_HD Fe fe_sqr_inl_t(const Fe &a) {
     uint32_t T[16];
     wide_sqr8(T, a.v);
-    return fe_reduce512(T);
+    return fe_reduce512<BR>(T);
 }
+BPPP_HD Fe fe_mul_inl(const Fe &a, const Fe &b) { return fe_mul_inl_t<true>(a, b); }
+BPPP_HD Fe fe_sqr_inl(const Fe &a) { return fe_sqr_inl_t<true>(a); }
 
 #if defined(__CUDACC__) && defined(BPPP_FE_NOINLINE)
 static __device__ __noinline__ Fe fe_mul_call(Fe a, Fe b) { return fe_mul_inl(a, b); }

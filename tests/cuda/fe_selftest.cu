@@ -10,8 +10,8 @@
 #include "sc.cuh"
 using namespace bppp;
 
-enum { OP_MUL, OP_SQR, OP_ADD, OP_SUB, OP_NEG, OP_MULINT3, OP_MULINT8, OP_MULINT21, OP_NORM, OP_ISZERO, OP_EXPR, OP_INV, OP_PT, OP_PTJ, OP_PTX, OP_SCMUL, OP_SCSQR, OP_SCWIDE, OP_SCINV, OP_COUNT };
-static const char *NAMES[] = {"mul", "sqr", "add", "sub", "neg", "mul_int3", "mul_int8", "mul_int21", "normalize", "is_zero", "expr(calls)", "inv/sqrt", "pt rcb", "pt jacobian", "pt xyzz", "sc_mul", "sc_sqr", "sc_reduce512", "sc_inv"};
+enum { OP_MUL, OP_SQR, OP_ADD, OP_SUB, OP_NEG, OP_MULINT3, OP_MULINT8, OP_MULINT21, OP_NORM, OP_ISZERO, OP_EXPR, OP_INV, OP_PT, OP_PTJ, OP_PTX, OP_SCMUL, OP_SCSQR, OP_SCWIDE, OP_SCINV, OP_FULL, OP_PTX_INL, OP_PTJ_INL, OP_COUNT };
+static const char *NAMES[] = {"mul", "sqr", "add", "sub", "neg", "mul_int3", "mul_int8", "mul_int21", "normalize", "is_zero", "expr(calls)", "inv/sqrt", "pt rcb", "pt jacobian", "pt xyzz", "sc_mul", "sc_sqr", "sc_reduce512", "sc_inv", "straight-line folds", "xyzz inlined", "jacobian inlined"};
 
 __host__ __device__ inline Fe apply(int op, const Fe &a, const Fe &b) {
     switch (op) {
@@ -48,6 +48,25 @@ __host__ __device__ inline Fe apply(int op, const Fe &a, const Fe &b) {
     case OP_SCSQR: { Sc x; for (int k = 0; k < 8; k++) x.v[k] = a.v[k]; Sc r = sc_sqr(x); return fe_from_words(r.v); }
     case OP_SCWIDE: { uint32_t t[16]; for (int k = 0; k < 8; k++) { t[k] = a.v[k]; t[8 + k] = b.v[k]; } Sc r = sc_reduce512(t); return fe_from_words(r.v); }
     case OP_SCINV: { Sc x; for (int k = 0; k < 8; k++) x.v[k] = a.v[k]; x.v[7] &= 0x7FFFFFFFu; Sc r = sc_inv(x); return fe_from_words(r.v); }
+    case OP_FULL: {   // the branch-free variants used inside inlined point formulas
+        Fe t = fe_add_t<false>(fe_mul_inl_t<false>(a, b), fe_sqr_inl_t<false>(a));
+        Fe u = fe_sub_t<false>(fe_mul_int_t<false>(t, 8), b);
+        Fe w = fe_sub_t<false>(fe_add_t<false>(a, b), fe_mul_int_t<false>(u, 3));
+        return fe_add_t<false>(fe_sub_t<false>(fe_zero(), w), fe_mul_int_t<false>(fe_add_t<false>(a, a), 2));
+    }
+    case OP_PTX_INL: {
+        PtX p = ptx_identity();
+        PtA q; q.x = b; q.y = a;
+        PtA q2; q2.x = a; q2.y = b;
+        p = ptx_add_mixed_t<true>(p, q); p = ptx_add_mixed_t<true>(p, q2); p = ptx_add_mixed_t<true>(p, q2); p = ptx_add_mixed_t<true>(p, q);
+        return fe_add(fe_add(p.x, p.y), fe_add(p.zz, p.zzz));
+    }
+    case OP_PTJ_INL: {
+        PtJ p; p.x = a; p.y = b; p.z = fe_from_u32(5); p.inf = false;
+        PtA q; q.x = b; q.y = a;
+        PtJ r = ptj_add_mixed_t<true>(ptj_double_t<true>(ptj_double_t<true>(p)), q);
+        return fe_add(fe_add(r.x, r.y), r.z);
+    }
     case OP_PTX: {
         PtX p = ptx_identity();
         PtA q; q.x = b; q.y = a;
