@@ -578,10 +578,22 @@ BPPP_HD Fe fe_mul(const Fe &a, const Fe &b) { return fe_mul_inl(a, b); }
 BPPP_HD Fe fe_sqr(const Fe &a) { return fe_sqr_inl(a); }
 #endif
 
+#if defined(__CUDACC__) && defined(BPPP_FE_NOINLINE)
+// the long squaring runs of fe_inv / fe_sqrt_candidate as one call: no per-squaring argument marshalling
+static __device__ __noinline__ Fe fe_sqr_n_call(Fe a, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) a = fe_sqr_inl_t<false>(a);
+    return a;
+}
+#endif
 BPPP_HD Fe fe_sqr_n(Fe a, int n) {
+#if defined(__CUDA_ARCH__) && defined(BPPP_FE_NOINLINE)
+    return fe_sqr_n_call(a, n);
+#else
 #pragma unroll 1
     for (int i = 0; i < n; i++) a = fe_sqr(a);
     return a;
+#endif
 }
 
 // a^(p-2): 255 squarings + 15 multiplications.  fe_inv(0) = 0.

@@ -37,7 +37,7 @@ struct VL {
     static constexpr int FS = Y + 32;                   // fixed-base scalars (<= 49)
     static constexpr int VS = FS + 8 * NUM_GENS;        // variable-base scalars (<= 5)
     // ladder tables: 13 points (c_l c_r c_o c_s r[0..3] x[0..3] V') x 8 multiples, 4 field elements per entry:
-    // projective X Y Z + 1/Z while being built, then affine x y (16 canonical words) in place
+    // projective X Y Z + 1/Z while being built, then affine x y (16 canonical words) in place, followed by beta x (the GLV endomorphism image)
     static constexpr int TAB = VS + 40;
     static constexpr int TAB_POINTS = 13, TAB_ENTRIES = TAB_POINTS * 8, TAB_STRIDE = 4 * FE_W;
     static constexpr int WORDS = TAB + TAB_ENTRIES * TAB_STRIDE;
@@ -234,11 +234,13 @@ BPPP_HD void u64v_table_finish_one(const WS &w, size_t i, int entry) {
     PtA a = ws_affine(w, i, off, off + PT_W, id);
     if (id) { a.x = fe_zero(); a.y = fe_zero(); }
     ws_st_pta(w, i, off, a);
+    ws_st_fe(w, i, off + 2 * FE_W, fe_mul(a.x, fe_beta()));
 }
 // Phases T2+T3 fused: Montgomery batch inversion of every table entry's Z over this thread's strided share of the
 // (entry, proof) items, writing the affine words in place on the way back (no separate 1/Z round trip through HBM)
 BPPP_HD void u64v_tables_normalize_strided(const WS &w, size_t t, size_t T) {
     const size_t total = (size_t)VL::TAB_ENTRIES * w.n;
+    const Fe beta = fe_beta();
     Fe run = fe_one();
 #pragma unroll 1
     for (size_t idx = t; idx < total; idx += T) {
@@ -264,6 +266,7 @@ BPPP_HD void u64v_tables_normalize_strided(const WS &w, size_t t, size_t T) {
             a = pt_to_affine_with_zinv(p, zi);
         }
         ws_st_pta(w, i, off, a);
+        ws_st_fe(w, i, off + 2 * FE_W, fe_mul(a.x, beta));     // x of the endomorphism image (beta x, y), any representative
     }
 }
 // acc = sum_k ks[k] * P_{tids[k]} + init from the affine tables
@@ -277,7 +280,6 @@ BPPP_HD Pt straus_tables(const WS &w, size_t i, const int *tids, const Sc *ks, c
         dg[2 * k] = half_signed_digits4(g.k1); neg[2 * k] = g.neg1;
         dg[2 * k + 1] = half_signed_digits4(g.k2); neg[2 * k + 1] = g.neg2;
     }
-    const Fe beta = fe_beta();
     PtJ acc = ptj_identity();
 #pragma unroll 1
     for (int d = 32; d >= 0; d--) {
@@ -291,10 +293,12 @@ BPPP_HD Pt straus_tables(const WS &w, size_t i, const int *tids, const Sc *ks, c
             if (neg[h]) sd = -sd;
             if (sd == 0) continue;
             int a = sd < 0 ? -sd : sd;
-            PtA q = ws_ld_pta(w, i, VL::TAB + (tids[h >> 1] * 8 + (a - 1)) * VL::TAB_STRIDE);
+            const int off = VL::TAB + (tids[h >> 1] * 8 + (a - 1)) * VL::TAB_STRIDE;
+            PtA q;
+            q.x = ws_ld_fe(w, i, off + ((h & 1) ? 2 * FE_W : 0));                       // odd halves use (beta x, y)
+            q.y = ws_ld_fe(w, i, off + FE_W);
             if (fe_is_zero_canonical(q.x) && fe_is_zero_canonical(q.y)) continue;       // identity point: nothing to add
             if (sd < 0) q.y = fe_normalize_weak(fe_negate(q.y, 1));
-            if (h & 1) q.x = fe_mul(q.x, beta);
             acc = ptj_add_mixed_hot(acc, q);
         }
     }
