@@ -120,7 +120,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout: one JSON line only
+        # one JSON line on stdout only: NCCL prints its version banner to stdout at every level from VERSION up (WARN
+        # included), so anything it has to say goes to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = args.batch
@@ -265,10 +267,16 @@ def run_ours(args):
                     unit = ln.split("[")[1].split("]")[0]
                     tot += float(ln.split("=")[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0)
         traffic, traffic_src = tot, os.path.relpath(cap, ROOT)
+    pipe_busy = None
+    if os.path.exists(cap):
+        for ln in open(cap):
+            if ln.startswith("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"):
+                pipe_busy = round(float(ln.split("=")[1]) / 100.0, 4)
     roofline = {
         "bound": "integer", "kernel": name, "achieved": round(achieved, 1), "peak": round(peak, 1), "unit": "GMAC/s (32x32->64 IMAD.WIDE)",
         "frac": round(achieved / peak, 4) if peak else None, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
-        "traffic_source": traffic_src, "traffic_note": "per-thread ladder tables (1P..8P) and register spills live in local memory; the kernel is integer-bound, DRAM < 0.4 TB/s",
+        "traffic_source": traffic_src, "traffic_note": "the per-proof ladder tables (13 points x 8 multiples) are re-read from L2/HBM by every ladder; the kernel is bound by the FMA-heavy integer pipe, DRAM stays below 0.2 TB/s",
+        "fma_heavy_pipe_busy_ncu": pipe_busy, "pipe_note": "sm__pipe_fmaheavy_cycles_active of the same kernel in the committed ncu capture: the unit every IMAD.WIDE issues to",
         "kernel_share_of_step": round(dom_ms / tot_v, 4), "kernel_ms": round(dom_ms, 3), "kernel_launches": dom_cnt,
         "peak_source": "bppp_microbench IMAD.WIDE.U32 issue rate measured live on this GPU",
         "hbm": {"achieved": round(tbl_bytes / (msm_ms * 1e-3) / 1e9, 1) if msm_ms else None, "peak": hbm_peak, "unit": "GB/s",

@@ -24,14 +24,14 @@ BPPP_HD Pt pt_from_affine(const PtA &a, bool is_identity) {
     if (is_identity) r = pt_identity();
     return r;
 }
-BPPP_HD Pt pt_neg(const Pt &p) {  // p.y magnitude <= 1
+BPPP_HD Pt pt_neg(const Pt &p) {
     Pt r = p; r.y = fe_normalize_weak(fe_negate(p.y, 1)); return r;
 }
 BPPP_HD Pt pt_cmov(const Pt &a, const Pt &b, bool take_b) {
     Pt r; r.x = fe_cmov(a.x, b.x, take_b); r.y = fe_cmov(a.y, b.y, take_b); r.z = fe_cmov(a.z, b.z, take_b); return r;
 }
 
-// All point routines take coordinates of magnitude 1 and return magnitude 1.
+// Coordinates are any representatives below 2^256 (fe.cuh); the magnitude arguments of fe_negate / fe_sub are vestigial.
 
 // P + Q, both projective.  12 M + 2 mul-by-21.
 BPPP_HD Pt pt_add(const Pt &p, const Pt &q) {

@@ -56,7 +56,7 @@ def _build_emu(name, extra=()):
 
 @pytest.fixture(scope="session")
 def emu_prims():
-    """bp_pp_b200/csrc/{fe,sc,ec,merlin}.cuh compiled for the host with magnitude assertions."""
+    """bp_pp_b200/csrc/{fe,sc,ec,merlin}.cuh compiled for the host with the bound assertions of fe.cuh (BPPP_VERIFY_MAG)."""
     return _build_emu("emu_prims")
 
 

@@ -1,5 +1,5 @@
 """CPU suite: the DEVICE arithmetic and per-proof phase logic (bp_pp_b200/csrc/*.cuh) compiled for the host
-with magnitude assertions, against the oracles.  This is how the kernels' code is exercised without a GPU."""
+with the bound assertions of fe.cuh enabled, against the oracles.  This is how the kernels' code is exercised without a GPU."""
 import ctypes as C
 import random
 
