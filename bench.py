@@ -27,20 +27,8 @@ LABEL = b"u64 range proof"
 METRIC = "u64 range proofs/sec (verify; batch of 65,536 independent proofs)"
 UNIT = "proofs/s"
 
-# ---- algorithmic integer work (DESIGN.md "Roofline"): 32x32->64 multiply-accumulates ("wMAC") ----
-WMAC_PER_FE_MUL = 72          # 64 product + 8 reduction, 8x32 schoolbook accounting
-M_MIXED, M_ADD, M_DBL = 11, 12, 8
-
-
-def msm_fixed_wmac(terms: int, window_bits: int) -> float:
-    nwin = (256 + window_bits - 1) // window_bits
-    return terms * nwin * M_MIXED * WMAC_PER_FE_MUL
-
-
-def straus_wmac(npoints: int) -> float:
-    # signed 4-bit windows, shared doublings: 256 doublings + 65 adds/point + 7-op table/point + 1
-    m = 256 * M_DBL + npoints * (65 * M_ADD + 4 * M_DBL + 3 * M_ADD) + M_ADD
-    return m * WMAC_PER_FE_MUL
+# ---- algorithmic integer work: roofline.py (SURVEY 8d accounting) ----
+from roofline import msm_fixed_wmac, prove_wmac, straus_wmac, verify_wmac  # noqa: E402
 
 
 def xy(p):
@@ -279,6 +267,9 @@ def run_ours(args):
         "fma_heavy_pipe_busy_ncu": pipe_busy, "pipe_note": "sm__pipe_fmaheavy_cycles_active of the same kernel in the committed ncu capture: the unit every IMAD.WIDE issues to",
         "kernel_share_of_step": round(dom_ms / tot_v, 4), "kernel_ms": round(dom_ms, 3), "kernel_launches": dom_cnt,
         "peak_source": "bppp_microbench IMAD.WIDE.U32 issue rate measured live on this GPU",
+        "step": {"wmac_per_proof": round(verify_wmac(W)), "achieved": round(n * verify_wmac(W) / (v_ms / args.steps * 1e-3) / 1e9, 1),
+                 "frac": round(n * verify_wmac(W) / (v_ms / args.steps * 1e-3) / 1e9 / peak, 4) if peak else None,
+                 "note": "whole verify step per GPU: roofline.py verify_wmac(W) x proofs / step time (reference-algorithm work, SURVEY 8d accounting)"},
         "hbm": {"achieved": round(tbl_bytes / (msm_ms * 1e-3) / 1e9, 1) if msm_ms else None, "peak": hbm_peak, "unit": "GB/s",
                 "frac": round(tbl_bytes / (msm_ms * 1e-3) / 1e9 / hbm_peak, 4) if msm_ms else None,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s", "note": "window-table lookups of k_msm_fixed; not the binding roof"},
@@ -289,7 +280,7 @@ def run_ours(args):
         base64, step64 = xy(R.pt_mul(R.G, 11)), xy(R.pt_mul(R.G, 29))
         mrnd = np.random.default_rng(5)
         msm_res = {}
-        for logn in (20, 21):
+        for logn in (16, 20, 21):
             mn = 1 << logn
             mpts = B.points_generate(base64, step64, mn, local_rank)
             msc = np.frombuffer(mrnd.bytes(32 * mn), dtype=np.uint8).reshape(mn, 32).copy()

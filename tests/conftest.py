@@ -80,3 +80,41 @@ def has_cuda():
         return torch.cuda.is_available()
     except Exception:
         return False
+
+
+def synth_circuit(ref, k, nv, nm, no, f_l, f_m, seed):
+    """A random dense ArithmeticCircuit with a witness built to satisfy W_l w + f_l v + a_l = 0 and
+    w_L o w_R = W_m w + f_m v + a_m (circuit.rs:95-139).  k > 1 and f_m = true are the branches the reference's own tests
+    never reach (circuit.rs:559-570,603-611).  Returns python-int structures; callers flatten them for the C ABIs."""
+    import random
+    N = ref.N
+    rnd = random.Random(seed)
+    nl, nw = k * nv, 2 * nm + no
+    pts = [ref.pt_mul(ref.G, int.from_bytes(ref.S("ac2-gen", j, 64), "big") % N) for j in range(1 + nm + 16)]
+    g, g_vec, h_all = pts[0], pts[1:1 + nm], pts[1 + nm:]
+    W_m = [[rnd.randrange(N) if rnd.random() < 0.5 else 0 for _ in range(nw)] for _ in range(nm)]
+    W_l = [[rnd.randrange(N) if rnd.random() < 0.5 else 0 for _ in range(nw)] for _ in range(nl)]
+    wl = [rnd.randrange(N) for _ in range(nm)]
+    wr = [rnd.randrange(N) for _ in range(nm)]
+    wo = [rnd.randrange(N) for _ in range(no)]
+    w = wl + wr + wo
+    v = [[rnd.randrange(N) for _ in range(nv)] for _ in range(k)]
+    vflat = [x for row in v for x in row]
+    dot = lambda row: sum(a * b for a, b in zip(row, w)) % N  # noqa: E731
+    a_l = [(-dot(W_l[i]) - (vflat[i] if f_l else 0)) % N for i in range(nl)]
+    a_m = [(wl[i] * wr[i] - dot(W_m[i]) - (vflat[i] if (f_m and i < len(vflat)) else 0)) % N for i in range(nm)]
+    s_v = [rnd.randrange(N) for _ in range(k)]
+    return dict(k=k, nv=nv, nm=nm, no=no, nl=nl, nw=nw, f_l=f_l, f_m=f_m, g=g, g_vec=g_vec, h_vec=h_all[:9 + nv], h_vec_=h_all[9 + nv:],
+                W_m=W_m, W_l=W_l, a_m=a_m, a_l=a_l, wl=wl, wr=wr, wo=wo, v=v, s_v=s_v, part_ll=list(range(no)))
+
+
+def circuit_bytes(ref, c):
+    """Flattened byte arguments of a synth_circuit for oracle_c.make_circuit_desc / bp_pp_b200.ArithmeticCircuit."""
+    be = lambda val: (val % ref.N).to_bytes(32, "big")  # noqa: E731
+    flat = lambda m: b"".join(be(e) for row in m for e in row)  # noqa: E731
+    vec = lambda a: b"".join(be(e) for e in a)  # noqa: E731
+    pv = lambda ps: b"".join(xy(p) for p in ps)  # noqa: E731
+    none = [-1] * c["no"]
+    return dict(g=xy(c["g"]), g_vec=pv(c["g_vec"]), h_vec=pv(c["h_vec"]), h_vec_=pv(c["h_vec_"]), W_m=flat(c["W_m"]), W_l=flat(c["W_l"]), a_m=vec(c["a_m"]),
+                a_l=vec(c["a_l"]), wl=vec(c["wl"]), wr=vec(c["wr"]), wo=vec(c["wo"]), v=flat(c["v"]), s_v=vec(c["s_v"]), part_lo=none, part_ll=c["part_ll"],
+                part_lr=none, part_no=none)

@@ -222,6 +222,33 @@ def test_ac_works_circuit_on_gpu(oracle, ref):
     assert circ.verify(com, bytes(bad), rounds, rounds, ll, nl, b"circuit test") == 0
 
 
+@pytest.mark.parametrize("k,f_l,f_m", [(2, True, False), (2, False, True), (2, True, True), (1, True, True), (3, True, False)])
+def test_circuit_k_and_f_m_branches_on_gpu(oracle, ref, k, f_l, f_m):
+    """k > 1 commitments and f_m = true (circuit.rs:559-570,603-611; never reached by the reference's tests): the CUDA path
+    against the C oracle, byte for byte, verdicts included."""
+    import bp_pp_b200 as B
+    from conftest import circuit_bytes, synth_circuit
+    nv = 2
+    c = synth_circuit(ref, k, nv, k * nv if f_m else 2, 2, f_l, f_m, seed=11 + k)
+    b = circuit_bytes(ref, c)
+    desc = oracle.make_circuit_desc(c["nm"], c["no"], k, nv, f_l, f_m, b["g"], b["g_vec"], b["h_vec"], b"", b["h_vec_"], b["W_m"], b["W_l"], b["a_m"], b["a_l"],
+                                    b["part_lo"], b["part_ll"], b["part_lr"], b["part_no"])
+    circ = B.ArithmeticCircuit(c["nm"], c["no"], k, nv, b["g"], b["g_vec"], b["h_vec"], b["W_m"], b["W_l"], b["a_m"], b["a_l"], f_l, f_m, b"", b["h_vec_"],
+                               b["part_lo"], b["part_ll"], b["part_lr"], b["part_no"])
+    coms = b"".join(circ.commit(b["v"][64 * i:64 * i + 64], b["s_v"][32 * i:32 * i + 32]) for i in range(k))
+    assert coms == b"".join(oracle.circuit_commit(desc, b["v"][64 * i:64 * i + 64], b["s_v"][32 * i:32 * i + 32]) for i in range(k))
+    rng = random.Random(9).randbytes(64 * 64)
+    out = circ.prove(coms, b["v"], b["s_v"], b["wl"], b["wr"], b["wo"], rng, b"c2")
+    assert out == oracle.circuit_prove(desc, coms, b["v"], b["s_v"], b["wl"], b["wr"], b["wo"], rng, b"c2")
+    rec, rounds, ll, nl = out
+    expect = oracle.circuit_verify(desc, coms, rec, rounds, rounds, ll, nl, b"c2")
+    if f_l and not f_m:
+        assert expect == 1
+    assert circ.verify(coms, rec, rounds, rounds, ll, nl, b"c2") == expect
+    bad = bytearray(rec); bad[-1] ^= 1
+    assert circ.verify(coms, bytes(bad), rounds, rounds, ll, nl, b"c2") == oracle.circuit_verify(desc, coms, bytes(bad), rounds, rounds, ll, nl, b"c2")
+
+
 def test_config4_wide_reciprocal_dim_1024(oracle, ref):
     """BASELINE config 4: dim_nd = 1024 digits, dim_np = 16, WNLA over 2^11 + 2^11 generators (10 rounds), vs the oracle."""
     import bp_pp_b200 as B

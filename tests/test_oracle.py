@@ -172,6 +172,35 @@ def test_ac_works_circuit(ref, oracle):
     assert oracle.circuit_verify(desc, com33, bytes(bad), rounds, rounds, ll, nl, b"circuit test") == 0
 
 
+@pytest.mark.parametrize("k,f_l,f_m,valid", [(2, True, False, True), (2, False, True, None), (2, True, True, None), (1, True, True, None)])
+def test_circuit_branches_the_reference_never_tests(ref, oracle, k, f_l, f_m, valid):
+    """k > 1 and f_m = true (circuit.rs:559-570,603-611) through both oracles: identical proof bytes and verdicts.  With
+    f_l only, a satisfying witness verifies; with f_m the reference's prover and verifier disagree with each other on an
+    instance built from the paper's relation (verdict false in both oracles) -- parity is what is asserted there."""
+    from conftest import circuit_bytes, synth_circuit
+    nv = 2
+    c = synth_circuit(ref, k, nv, k * nv if f_m else 2, 2, f_l, f_m, seed=5)
+    part = lambda typ, idx: idx if (typ == ref.LL and idx < c["no"]) else None  # noqa: E731
+    circ = ref.ArithmeticCircuit(c["nm"], c["no"], k, c["nl"], nv, c["nw"], c["g"], c["g_vec"], c["h_vec"], c["W_m"], c["W_l"], c["a_m"], c["a_l"], f_l, f_m,
+                                 [], c["h_vec_"], part)
+    wit = ref.CircuitWitness(c["v"], c["s_v"], c["wl"], c["wr"], c["wo"])
+    vs = [circ.commit(c["v"][i], c["s_v"][i]) for i in range(k)]
+    rng = ref.S("ac2-rng", 0, 64 * 64)
+    proof = circ.prove(vs, wit, ref.Transcript(b"c2"), ref.ByteRng(rng))
+    verdict_py = circ.verify(vs, ref.Transcript(b"c2"), proof)
+    if valid is not None:
+        assert verdict_py is valid
+    b = circuit_bytes(ref, c)
+    desc = oracle.make_circuit_desc(c["nm"], c["no"], k, nv, f_l, f_m, b["g"], b["g_vec"], b["h_vec"], b"", b["h_vec_"], b["W_m"], b["W_l"], b["a_m"], b["a_l"],
+                                    b["part_lo"], b["part_ll"], b["part_lr"], b["part_no"])
+    coms = b"".join(ref.pt_to_bytes(p) for p in vs)
+    for i in range(k):
+        assert oracle.circuit_commit(desc, b["v"][64 * i:64 * i + 64], b["s_v"][32 * i:32 * i + 32]) == coms[33 * i:33 * i + 33]
+    rec_c, rounds, ll, nl = oracle.circuit_prove(desc, coms, b["v"], b["s_v"], b["wl"], b["wr"], b["wo"], rng, b"c2")
+    assert rec_c == ref.serialize_circuit_proof(proof)
+    assert oracle.circuit_verify(desc, coms, rec_c, rounds, rounds, ll, nl, b"c2") == int(verdict_py)
+
+
 def test_reciprocal_generic_dims_py_vs_c(ref, oracle):
     """reciprocal.rs for (dim_nd, dim_np) = (4, 4): generic path, WNLA over 16 + 4 generators."""
     N = ref.N
