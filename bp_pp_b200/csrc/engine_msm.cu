@@ -7,8 +7,9 @@
 //   k_msm_digits      signed digits of every scalar -> (bucket key, point index | sign) pairs, window-major
 //   cub radix sort    pairs by bucket key (the only library call; it moves 8-byte pairs, no curve arithmetic)
 //   k_msm_bounds      first / one-past-last sorted position of every bucket
-//   k_msm_buckets     one thread per bucket: mixed-adds its points; buckets above MSM_HEAVY entries (skewed scalars) are
-//                     deferred to k_msm_heavy (one 128-thread block per such bucket, shared-memory tree reduction)
+//   k_msm_buckets     one thread per bucket: mixed-adds its points; buckets above the heavy threshold (skewed scalars, the
+//                     partially filled top window) are deferred to k_msm_heavy: one 128-thread block per segment of at
+//                     most MSM_SEG entries, shared-memory tree reduction; k_msm_heavy_sum adds the segments of a bucket
 //   k_msm_chunks      per window: chunked running-sum reduction  sum_b (b+1) B_b  (two adds per bucket)
 //   k_pt_sum_groups   tree sums;  k_msm_horner: sum_w 2^(c w) W_w
 // Small inputs (n <= 1024) use one GLV scalar multiplication per point and the same tree sum.
@@ -101,7 +102,9 @@ __global__ void k_msm_digits(const uint32_t *sc, size_t n, int c, int nwin, uint
     }
 }
 
-static constexpr uint32_t MSM_HEAVY = 512;   // bucket sizes above this go to the block-per-bucket kernel
+// Buckets holding more than `heavy_thr` entries go to the block-per-bucket kernel.  The threshold follows the mean bucket
+// size (max(32, 2 n / 2^(c-1))): skewed scalars, and the partially filled top window of every MSM (its few buckets share
+// all n points), would otherwise serialise the launch behind a handful of threads.
 
 __global__ void k_msm_bounds(const uint32_t *keys, size_t total, uint32_t nb, uint32_t *start, uint32_t *end) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -125,24 +128,63 @@ __device__ __forceinline__ Pt msm_accumulate_range(const uint32_t *pts, const ui
     return ptx_to_pt(acc);
 }
 // bucket sums are stored AoS, PT_W words per point
+static constexpr uint32_t MSM_SEG = 2048;     // entries per heavy-bucket work item (16 per thread of a 128-thread block)
+// Heavy work items: region M (slots [0, capM)) holds buckets of thr < size <= MSM_SEG, one slot each; region L (slots
+// [capM, capM + capL)) holds the segments of larger buckets.  capL = 2 total / MSM_SEG can never overflow (every such bucket
+// needs at most size / MSM_SEG + 1 <= 2 size / MSM_SEG slots); a bucket that finds region M full is summed in place.
+struct HeavyQueue {
+    uint32_t *count;      // [0] region M, [1] region L
+    uint32_t *bucket;     // per slot: bucket id
+    uint32_t *seg;        // per slot: segment index within its bucket
+    uint32_t *seg_out;    // per slot of region L: partial sum (PT_W words)
+    uint32_t capM, capL;
+};
 __global__ void __launch_bounds__(64, 7) k_msm_buckets(const uint32_t *pts, const uint32_t *vals, const uint32_t *start, const uint32_t *end, uint32_t nb,
-                                                        uint32_t *buckets, uint32_t *heavy, uint32_t *heavy_count, uint32_t heavy_cap) {
+                                                        uint32_t *buckets, HeavyQueue hq, uint32_t heavy_thr) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
-    uint32_t p0 = start[b], p1 = end[b];
-    if (p1 - p0 > MSM_HEAVY) {
-        uint32_t slot = atomicAdd(heavy_count, 1u);
-        if (slot < heavy_cap) { heavy[slot] = (uint32_t)b; st_pt30(buckets + PT_W * b, pt_identity()); return; }
+    uint32_t p0 = start[b], p1 = end[b], size = p1 - p0;
+    if (size > MSM_SEG) {
+        uint32_t nseg = (size + MSM_SEG - 1) / MSM_SEG;
+        uint32_t slot = hq.capM + atomicAdd(hq.count + 1, nseg);
+        for (uint32_t k = 0; k < nseg; k++) { hq.bucket[slot + k] = (uint32_t)b; hq.seg[slot + k] = k; }
+        return;                                            // k_msm_heavy_sum writes the bucket
+    }
+    if (size > heavy_thr) {
+        uint32_t slot = atomicAdd(hq.count, 1u);
+        if (slot < hq.capM) { hq.bucket[slot] = (uint32_t)b; hq.seg[slot] = 0; return; }      // k_msm_heavy writes the bucket
     }
     st_pt30(buckets + PT_W * b, msm_accumulate_range(pts, vals, p0, p1, 1));
 }
-__global__ void __launch_bounds__(128) k_msm_heavy(const uint32_t *pts, const uint32_t *vals, const uint32_t *start, const uint32_t *end, const uint32_t *heavy,
-                                                    const uint32_t *heavy_count, uint32_t heavy_cap, uint32_t *buckets) {
+__global__ void __launch_bounds__(128) k_msm_heavy(const uint32_t *pts, const uint32_t *vals, const uint32_t *start, const uint32_t *end, HeavyQueue hq,
+                                                    uint32_t *buckets) {
     __shared__ uint32_t sh[128 * PT_W];
-    uint32_t cnt = *heavy_count; if (cnt > heavy_cap) cnt = heavy_cap;
-    if (blockIdx.x >= cnt) return;
-    uint32_t b = heavy[blockIdx.x];
-    Pt acc = msm_accumulate_range(pts, vals, start[b] + threadIdx.x, end[b], 128);
+    const uint32_t slot = blockIdx.x;
+    const bool large = slot >= hq.capM;
+    uint32_t cnt = large ? hq.count[1] : hq.count[0];
+    if (!large && cnt > hq.capM) cnt = hq.capM;
+    if ((large ? slot - hq.capM : slot) >= cnt) return;
+    uint32_t b = hq.bucket[slot], k = hq.seg[slot];
+    uint32_t p0 = start[b] + k * MSM_SEG, p1 = end[b];
+    if (p1 - p0 > MSM_SEG && large) p1 = p0 + MSM_SEG;
+    Pt acc = msm_accumulate_range(pts, vals, p0 + threadIdx.x, p1, 128);
+    st_pt30(sh + PT_W * threadIdx.x, acc);
+    __syncthreads();
+    for (int s = 64; s >= 1; s >>= 1) {
+        if ((int)threadIdx.x < s) st_pt30(sh + PT_W * threadIdx.x, pt_add(ld_pt30(sh + PT_W * threadIdx.x), ld_pt30(sh + PT_W * (threadIdx.x + s))));
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_pt30(large ? hq.seg_out + PT_W * (size_t)(slot - hq.capM) : buckets + PT_W * (size_t)b, ld_pt30(sh));
+}
+// region L: the block of a bucket's first segment adds the partial sums of all its segments (they occupy adjacent slots)
+__global__ void __launch_bounds__(128) k_msm_heavy_sum(const uint32_t *start, const uint32_t *end, HeavyQueue hq, uint32_t *buckets) {
+    __shared__ uint32_t sh[128 * PT_W];
+    const uint32_t i = blockIdx.x;                          // index within region L
+    if (i >= hq.count[1] || hq.seg[hq.capM + i] != 0) return;
+    uint32_t b = hq.bucket[hq.capM + i];
+    uint32_t nseg = (end[b] - start[b] + MSM_SEG - 1) / MSM_SEG;
+    Pt acc = pt_identity();
+    for (uint32_t k = threadIdx.x; k < nseg; k += 128) acc = pt_add(acc, ld_pt30(hq.seg_out + PT_W * (size_t)(i + k)));
     st_pt30(sh + PT_W * threadIdx.x, acc);
     __syncthreads();
     for (int s = 64; s >= 1; s >>= 1) {
@@ -169,10 +211,13 @@ __global__ void __launch_bounds__(64) k_msm_chunks(const uint32_t *buckets, int 
     }
     // + base * S: double-and-add
     Pt BS = pt_identity();
+    if (base) {
+        BS = S;
 #pragma unroll 1
-    for (int bit = 15; bit >= 0; bit--) {     // base < half <= 2^15
-        BS = pt_double(BS);
-        if ((base >> bit) & 1u) BS = pt_add(BS, S);
+        for (int bit = 30 - __clz(base); bit >= 0; bit--) {     // below the leading one of base (< 2^15)
+            BS = pt_double(BS);
+            if ((base >> bit) & 1u) BS = pt_add(BS, S);
+        }
     }
     st_pt30(out + PT_W * t, pt_add(T, BS));
 }
@@ -191,9 +236,17 @@ __global__ void __launch_bounds__(64) k_pt_sum_groups(const uint32_t *in, size_t
 // result = sum_w 2^(c w) W_w, optionally + *addend
 __global__ void k_msm_horner(const uint32_t *win, int c, int nwin, const uint32_t *addend, uint32_t *out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    // One thread, 256 dependent doublings: latency is what counts, so the doublings run on the Jacobian formula with the
+    // field arithmetic inlined (ptxas overlaps the independent squarings of one doubling).
     Pt acc = ld_pt30(win + PT_W * (nwin - 1));
     for (int w = nwin - 2; w >= 0; w--) {
-        for (int k = 0; k < c; k++) acc = pt_double(acc);
+        if (!fe_normalizes_to_zero(acc.z)) {
+            PtJ j;
+            j.x = fe_mul(acc.x, acc.z); j.y = fe_mul(acc.y, fe_sqr(acc.z)); j.z = acc.z; j.inf = false;      // (X/Z, Y/Z) = (Xj/Z^2, Yj/Z^3)
+#pragma unroll 1
+            for (int k = 0; k < c; k++) j = ptj_double_t<true>(j);
+            acc = ptj_to_pt(j);
+        }
         acc = pt_add(acc, ld_pt30(win + PT_W * w));
     }
     if (addend) acc = pt_add(acc, ld_pt30(addend));
@@ -281,33 +334,38 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     const uint32_t half = 1u << (c - 1);
     const uint32_t nb = (uint32_t)nwin * half;
     const size_t total = (size_t)nwin * n;
-    uint32_t CH = 64; if (CH > half) CH = half;
+    uint32_t CH = 16; if (CH > half) CH = half;        // 2 CH sequential additions per thread: short chains, many threads
     const uint32_t nchunks = (half + CH - 1) / CH;
-    const uint32_t heavy_cap = 4096;
+    HeavyQueue hq;
+    hq.capM = 8192; hq.capL = (uint32_t)(2 * total / MSM_SEG + 2);
+    const size_t hslots = (size_t)hq.capM + hq.capL;
+    uint32_t heavy_thr = (uint32_t)(2 * ((n + half - 1) / half)); if (heavy_thr < 32) heavy_thr = 32;
     size_t cub_bytes = 0;
     CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, total, 0, 32, st));
     // one cached slab per device, carved into the working arrays (cudaMalloc per call cost more than the kernels)
     Carver cv;
     size_t o_keys = cv.take(4 * total), o_vals = cv.take(4 * total), o_keys2 = cv.take(4 * total), o_vals2 = cv.take(4 * total);
     size_t o_start = cv.take(4 * (size_t)nb), o_end = cv.take(4 * (size_t)nb), o_buckets = cv.take((size_t)PT_BYTES * nb);
-    size_t o_heavy = cv.take(4 * (size_t)heavy_cap + 256), o_chunks = cv.take((size_t)PT_BYTES * nwin * nchunks);
+    size_t o_heavy = cv.take(256 + 8 * hslots), o_segout = cv.take((size_t)PT_BYTES * hq.capL), o_chunks = cv.take((size_t)PT_BYTES * nwin * nchunks);
     size_t o_tmp = cv.take((size_t)PT_BYTES * ((size_t)nwin * nchunks / 16 + 2)), o_cub = cv.take(cub_bytes);
     uint8_t *slab = nullptr;
     int rc = scratch_reserve(cv.total, &slab);
     if (rc != BPPP_OK) return rc;
     uint32_t *keys = (uint32_t *)(slab + o_keys), *vals = (uint32_t *)(slab + o_vals), *keys2 = (uint32_t *)(slab + o_keys2), *vals2 = (uint32_t *)(slab + o_vals2);
     uint32_t *start = (uint32_t *)(slab + o_start), *end = (uint32_t *)(slab + o_end), *buckets = (uint32_t *)(slab + o_buckets);
-    uint32_t *heavy_count = (uint32_t *)(slab + o_heavy), *heavy = heavy_count + 64, *chunks = (uint32_t *)(slab + o_chunks), *tmp = (uint32_t *)(slab + o_tmp);
+    uint32_t *chunks = (uint32_t *)(slab + o_chunks), *tmp = (uint32_t *)(slab + o_tmp);
+    hq.count = (uint32_t *)(slab + o_heavy); hq.bucket = hq.count + 64; hq.seg = hq.bucket + hslots; hq.seg_out = (uint32_t *)(slab + o_segout);
     void *cub_tmp = slab + o_cub;
     CUDA_OK(cudaMemsetAsync(start, 0, 4 * (size_t)nb, st));          // empty buckets keep start == end == 0
     CUDA_OK(cudaMemsetAsync(end, 0, 4 * (size_t)nb, st));
-    CUDA_OK(cudaMemsetAsync(heavy_count, 0, 4, st));
+    CUDA_OK(cudaMemsetAsync(hq.count, 0, 8, st));
     GL(k_msm_digits, nblocks(n, 128), 128, d_sc, n, c, nwin, keys, vals);
     CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys2, vals, vals2, total, 0, 32, st));   // invalid keys are 0xFFFFFFFF: they sort last
     g_generic_launches += 4;
     GL(k_msm_bounds, nblocks(total, 256), 256, keys2, total, nb, start, end);
-    GL(k_msm_buckets, nblocks(nb, 64), 64, d_pts, vals2, start, end, nb, buckets, heavy, heavy_count, heavy_cap);
-    GL(k_msm_heavy, heavy_cap, 128, d_pts, vals2, start, end, heavy, heavy_count, heavy_cap, buckets);
+    GL(k_msm_buckets, nblocks(nb, 64), 64, d_pts, vals2, start, end, nb, buckets, hq, heavy_thr);
+    GL(k_msm_heavy, (unsigned)hslots, 128, d_pts, vals2, start, end, hq, buckets);
+    GL(k_msm_heavy_sum, hq.capL, 128, start, end, hq, buckets);
     GL(k_msm_chunks, nblocks((size_t)nwin * nchunks, 64), 64, buckets, nwin, half, CH, nchunks, chunks);
     // per-window sum of chunk results: groups of 16 until nwin points remain
     uint32_t *in = chunks, *out = tmp;

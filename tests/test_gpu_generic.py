@@ -49,6 +49,13 @@ def test_msm_zero_extension_and_degenerate_buckets(oracle, ref):
     # every scalar equal and tiny: one giant bucket in window 0 (exercises the segment merge path)
     S = _be(3) * n
     assert B.msm(P, S) == oracle.msm(P, S)
+    # three distinct tiny scalars over 7000 points: buckets of ~2333 entries, above the 2048-entry segment size (several
+    # segments per bucket, summed by k_msm_heavy_sum), next to medium-heavy buckets
+    n2 = 7000
+    pts2 = B.points_generate(pts[0], pts[1], n2)
+    rnd = random.Random(12)
+    S7 = b"".join(_be(rnd.choice((1, 2, 2**40 + 3)) if i % 50 else rnd.randrange(ref.N)) for i in range(n2))
+    assert B.msm(pts2, S7) == oracle.msm(pts2, S7)
     # all points identical with opposite scalars: sum is the identity
     P2 = pts[0] * 2000
     S2 = (_be(5) + _be(ref.N - 5)) * 1000
