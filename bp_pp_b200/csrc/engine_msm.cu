@@ -14,6 +14,7 @@
 //   k_pt_sum_groups   tree sums;  k_msm_horner: sum_w 2^(c w) W_w
 // Small inputs (n <= 1024) use one GLV scalar multiplication per point and the same tree sum.
 #define BPPP_FE_NOINLINE 1
+#define BPPP_PTX_ADD_NOINLINE 1   // ec.cuh: the bucket accumulation's XYZZ addition as one call with inlined products
 #include "engine_generic.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
@@ -97,7 +98,7 @@ __global__ void k_msm_digits(const uint32_t *sc, size_t n, int c, int nwin, uint
         uint32_t neg = 0, mag = raw;
         carry = 0;
         if (raw > half) { mag = (1u << c) - raw; neg = 1; carry = 1; }
-        keys[(size_t)w * n + i] = mag == 0 ? 0xFFFFFFFFu : (uint32_t)w * half + (mag - 1);
+        keys[(size_t)w * n + i] = mag == 0 ? (uint32_t)nwin * half : (uint32_t)w * half + (mag - 1);     // zero digits: key nb, sorts last
         vals[(size_t)w * n + i] = (uint32_t)i | (neg << 31);
     }
 }
@@ -340,8 +341,9 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     hq.capM = 8192; hq.capL = (uint32_t)(2 * total / MSM_SEG + 2);
     const size_t hslots = (size_t)hq.capM + hq.capL;
     uint32_t heavy_thr = (uint32_t)(2 * ((n + half - 1) / half)); if (heavy_thr < 32) heavy_thr = 32;
+    int key_bits = 1; while (((uint64_t)1 << key_bits) <= (uint64_t)nb) key_bits++;      // keys are 0 .. nb
     size_t cub_bytes = 0;
-    CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, total, 0, 32, st));
+    CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, total, 0, key_bits, st));
     // one cached slab per device, carved into the working arrays (cudaMalloc per call cost more than the kernels)
     Carver cv;
     size_t o_keys = cv.take(4 * total), o_vals = cv.take(4 * total), o_keys2 = cv.take(4 * total), o_vals2 = cv.take(4 * total);
@@ -360,7 +362,7 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     CUDA_OK(cudaMemsetAsync(end, 0, 4 * (size_t)nb, st));
     CUDA_OK(cudaMemsetAsync(hq.count, 0, 8, st));
     GL(k_msm_digits, nblocks(n, 128), 128, d_sc, n, c, nwin, keys, vals);
-    CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys2, vals, vals2, total, 0, 32, st));   // invalid keys are 0xFFFFFFFF: they sort last
+    CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys2, vals, vals2, total, 0, key_bits, st));   // only the bits a key can have
     g_generic_launches += 4;
     GL(k_msm_bounds, nblocks(total, 256), 256, keys2, total, nb, start, end);
     GL(k_msm_buckets, nblocks(nb, 64), 64, d_pts, vals2, start, end, nb, buckets, hq, heavy_thr);
