@@ -21,8 +21,12 @@ ST_FALSE, ST_TRUE = 0, 1
 ST_PANIC_INVERT_ZERO, ST_PANIC_CHALLENGE_RANGE, ST_BAD_POINT, ST_BAD_SCALAR = -1, -2, -3, -4
 
 
-def _in(b: bytes):
-    return (C.c_uint8 * max(len(b), 1)).from_buffer_copy(b if len(b) else b"\0")
+def _in(b):
+    """Read-only buffer argument.  `bytes` go through as a pointer to their own storage (no copy: these are 100 MB+ for the
+    large generic calls); other buffer types are copied into a ctypes array."""
+    if isinstance(b, bytes):
+        return b if len(b) else b"\0"
+    return (C.c_uint8 * max(len(b), 1)).from_buffer_copy(bytes(b) if len(b) else b"\0")
 
 
 class Context:

@@ -173,12 +173,17 @@ __global__ void k_wnla_fold_scalars(const uint32_t *c, const uint32_t *l, const 
 }
 // com' = com + y X + (y^2 - 1) R   (wnla.rs:100-102; equals wnla'.commit(l', n') of wnla.rs:186)
 __global__ void k_wnla_next_commitment(const uint32_t *com30, const uint32_t *x30, const uint32_t *r30, ScParam y_p, uint32_t *out30) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    // two threads of one warp: the scalar multiplications y X and (y^2 - 1) R run side by side (a single thread is
+    // latency-bound on ~130 dependent doublings each), thread 0 adds them to com
+    __shared__ uint32_t sh[PT_W];
+    const int t = threadIdx.x;
+    if (blockIdx.x != 0 || t >= 2) return;
     Sc y = from_param(y_p);
-    Pt acc = ld_pt30g(com30);
-    acc = pt_add(acc, pt_mul_glv(ld_pt30g(x30), y));
-    acc = pt_add(acc, pt_mul_glv(ld_pt30g(r30), sc_sub(sc_sqr(y), sc_one())));
-    st_pt30g(out30, acc);
+    Sc k = t ? sc_sub(sc_sqr(y), sc_one()) : y;
+    Pt part = pt_mul_glv(ld_pt30g(t ? r30 : x30), k);
+    if (t == 1) st_pt30g(sh, part);
+    __syncwarp(0x3);
+    if (t == 0) st_pt30g(out30, pt_add(pt_add(ld_pt30g(com30), part), ld_pt30g(sh)));
 }
 // verifier: base-case scalars over the ORIGINAL generators (see file header).  ys / rhos: R scalars each.
 __global__ void k_wnla_final_scalars(size_t Lh, size_t Lg, int R, const uint32_t *ys, const uint32_t *rhos, const uint32_t *l, size_t ln, const uint32_t *n, size_t nn,
@@ -327,7 +332,7 @@ int wnla_prove_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, ui
         if (Lg2) WL(k_wnla_fold_points, nblocks(Lg2, 64), 64, w.pts + 16 * Lh, Lg, to_param(y), to_param(w.rho), 1, pts2 + 16 * Lh2);
         CUDA_OK(cudaMemcpyAsync(pts2 + 16 * (Lh2 + Lg2), w.pts + 16 * (Lh + Lg), 64, cudaMemcpyDeviceToDevice, st));
         WL(k_wnla_fold_scalars, nblocks(std::max(Lh2, Lg2), 128), 128, w.c, d_l, d_n, Lh, Lg, to_param(y), to_param(rho_inv), c2, l2, n2, 1);
-        WL(k_wnla_next_commitment, 1, 1, d_com30, d_x30, d_r30, to_param(y), d_com30);
+        WL(k_wnla_next_commitment, 1, 2, d_com30, d_x30, d_r30, to_param(y), d_com30);
         CUDA_OK(cudaStreamSynchronize(st));
         cudaFree(w.pts); cudaFree(w.c); cudaFree(d_l); cudaFree(d_n);
         w.pts = pts2; w.c = c2; d_l = l2; d_n = n2;
@@ -391,7 +396,7 @@ int wnla_verify_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, c
         ys[j] = y; rhos[j] = rho;
         WL(k_decode_one_point30, 1, 1, d_xr + 16 * (size_t)idx, d_x30);
         WL(k_decode_one_point30, 1, 1, d_xr + 16 * ((size_t)R + idx), d_r30);
-        WL(k_wnla_next_commitment, 1, 1, d_com30, d_x30, d_r30, to_param(y), d_com30);
+        WL(k_wnla_next_commitment, 1, 2, d_com30, d_x30, d_r30, to_param(y), d_com30);
         len_h = (len_h + 1) / 2; len_g = (len_g + 1) / 2;
         rho = mu; mu = sc_sqr(mu);
     }
