@@ -331,7 +331,7 @@ def run_ours(args):
         "microbench": {k: float(f"{v:.4g}") for k, v in mb.items()},
         "context": {"table_bytes": info["table_bytes"], "workspace_bytes": info["workspace_bytes"], "table_build_ms": round(info["table_build_ms"], 1)},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
 
@@ -380,10 +380,34 @@ def run_reference(args):
         "all_true": ok,
         "note": "C restatement of the reference algorithm (not k256); published k256 figures: 3.808 ms/verify, 14.361 ms/prove on one M3 Pro core",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner with printf when
+    the box exports NCCL_DEBUG), so file descriptor 1 is pointed at stderr for the whole run and the result line is written
+    to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

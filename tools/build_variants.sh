@@ -15,5 +15,4 @@ build() { # name  var_flags  core_flags
 }
 rm -f ../variants/*.so
 build dblc   "-DBPPP_PTJ_DBL_NOINLINE"  "" &
-build addc   "-DBPPP_PTJ_ADD_NOINLINE"  "" &
 wait
