@@ -119,28 +119,54 @@ BPPP_HD bool table_decode(PtA &q, const TableEntryRaw &r) {
     return any != 0;
 }
 
+// the two workspace words a W-bit window can straddle, and the window cut out of them
+struct WindowWords { uint32_t lo, hi; };
+BPPP_HD WindowWords scalar_window_words(const WS &w, size_t i, int sc_off, int win, int W) {
+    int word = (win * W) >> 5;
+    WindowWords r;
+    r.lo = ws_ld(w, i, sc_off + word);
+    r.hi = word + 1 < 8 ? ws_ld(w, i, sc_off + word + 1) : 0u;
+    return r;
+}
+BPPP_HD uint32_t window_of_words(const WindowWords &ww, int win, int W) {
+    int sh = (win * W) & 31;
+    uint64_t v = (uint64_t)ww.lo | ((uint64_t)ww.hi << 32);
+    return (uint32_t)(v >> sh) & ((1u << W) - 1u);
+}
+
 // One lane's share of sum_t scalar_t * G_{gen(t)}: items (t, win) are dealt round-robin to `nlanes` lanes.
 // scalars: T consecutive Sc in the workspace starting at word sc_off; term_gen[t] = generator index.
-// The table entry of the next item is fetched (64 B from HBM) before the current mixed addition is computed.
+// Software pipeline, two stages deep: while the mixed addition of item k runs, the 64-byte table entry of item k+1 is
+// in flight from HBM and so are the scalar words of item k+2 (the window -> address -> entry chain is two dependent loads;
+// ncu showed the first one exposed as long-scoreboard stalls).
 BPPP_HD Pt msm_fixed_lane(const FixedTable &T, const WS &w, size_t i, int sc_off, const int *term_gen, int nterms, int lane, int nlanes) {
     PtX acc = ptx_identity();             // XYZZ accumulator: 8 M + 2 S per table point (ec.cuh)
     const int items = nterms * T.nwin;
     TableEntryRaw cur, nxt;
     uint32_t dcur = 0, dnxt = 0;
+    WindowWords ww_next; ww_next.lo = 0; ww_next.hi = 0;
     int it = lane;
     if (it < items) {
         int t = it / T.nwin, win = it - t * T.nwin;
-        dcur = scalar_window(w, i, sc_off + 8 * t, win, T.W);
+        dcur = window_of_words(scalar_window_words(w, i, sc_off + 8 * t, win, T.W), win, T.W);
         if (dcur) cur = table_fetch(T, term_gen[t], win, dcur);
+    }
+    if (it + nlanes < items) {
+        int t = (it + nlanes) / T.nwin, win = (it + nlanes) - t * T.nwin;
+        ww_next = scalar_window_words(w, i, sc_off + 8 * t, win, T.W);
     }
 #pragma unroll 1
     for (; it < items; it += nlanes) {
-        int itn = it + nlanes;
+        const int itn = it + nlanes, itnn = it + 2 * nlanes;
         dnxt = 0;
         if (itn < items) {
             int t = itn / T.nwin, win = itn - t * T.nwin;
-            dnxt = scalar_window(w, i, sc_off + 8 * t, win, T.W);
+            dnxt = window_of_words(ww_next, win, T.W);
             if (dnxt) nxt = table_fetch(T, term_gen[t], win, dnxt);
+        }
+        if (itnn < items) {
+            int t = itnn / T.nwin, win = itnn - t * T.nwin;
+            ww_next = scalar_window_words(w, i, sc_off + 8 * t, win, T.W);
         }
         if (dcur != 0) {
             PtA q;
