@@ -234,6 +234,7 @@ extern "C" int bppp_ctx_create(bppp_ctx **out, int device, const uint8_t *gens64
     c->T.tab = c->d_tab;
     c->max_batch = max_batch;
     c->ws_words_per_proof = VL::WORDS > PL::WORDS ? VL::WORDS : PL::WORDS;
+    c->ws_words_per_proof = (c->ws_words_per_proof + 3) & ~(size_t)3;      // sub-batch bases stay 16-byte aligned (vtab_entry)
     CUDA_OK(cudaMalloc(&c->d_ws, c->ws_words_per_proof * max_batch * sizeof(uint32_t)));
     CUDA_OK(cudaMalloc(&c->d_in_a, (size_t)64 * max_batch));
     CUDA_OK(cudaMalloc(&c->d_in_b, (size_t)U64_PROOF_BYTES_AFFINE * max_batch));

@@ -37,11 +37,39 @@ struct VL {
     static constexpr int FS = Y + 32;                   // fixed-base scalars (<= 49)
     static constexpr int VS = FS + 8 * NUM_GENS;        // variable-base scalars (<= 5)
     // ladder tables: 13 points (c_l c_r c_o c_s r[0..3] x[0..3] V') x 8 multiples, 4 field elements per entry:
-    // projective X Y Z + 1/Z while being built, then affine x y (16 canonical words) in place, followed by beta x (the GLV endomorphism image)
+    // projective X Y Z + the running product of the batch inversion while being built (word-major like the rest of the record)
     static constexpr int TAB = VS + 40;
     static constexpr int TAB_POINTS = 13, TAB_ENTRIES = TAB_POINTS * 8, TAB_STRIDE = 4 * FE_W;
-    static constexpr int WORDS = TAB + TAB_ENTRIES * TAB_STRIDE;
+    // the finished tables, array-of-structures: proof i, entry e at TABA * n + (i * TAB_ENTRIES + e) * TABA_STRIDE words
+    // = x[8] y[8] (beta x)[8].  A ladder step picks its entry by a per-proof digit, so one entry must be one contiguous
+    // 64-byte read ([x|y] for the k1 halves, [y|beta x] for the k2 halves) instead of 16 words scattered over 16 lines.
+    static constexpr int TABA = (TAB + TAB_ENTRIES * TAB_STRIDE + 3) & ~3;
+    static constexpr int TABA_STRIDE = 3 * FE_W;
+    static constexpr int WORDS = TABA + TAB_ENTRIES * TABA_STRIDE;
 };
+BPPP_HD uint32_t *vtab_entry(const WS &w, size_t i, int entry) {
+    return w.p + (size_t)VL::TABA * w.n + ((size_t)i * VL::TAB_ENTRIES + entry) * VL::TABA_STRIDE;
+}
+// 8 words <-> Fe through 16-byte accesses (the pointers are 16-byte aligned: TABA and the per-proof record size are
+// multiples of 4 words, TABA_STRIDE of 8)
+BPPP_HD Fe vtab_ld_fe(const uint32_t *p) {
+    Fe r;
+#if defined(__CUDA_ARCH__)
+    uint4 a = __ldg(reinterpret_cast<const uint4 *>(p)), b = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+#else
+    for (int k = 0; k < 8; k++) r.v[k] = p[k];
+#endif
+    return r;
+}
+BPPP_HD void vtab_st_fe(uint32_t *p, const Fe &a) {
+#if defined(__CUDA_ARCH__)
+    reinterpret_cast<uint4 *>(p)[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    reinterpret_cast<uint4 *>(p)[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+#else
+    for (int k = 0; k < 8; k++) p[k] = a.v[k];
+#endif
+}
 // table point ids: input slot k (1..12) -> k - 1; V' -> 12
 BPPP_HD int vtab_of_slot(int slot) { return slot - 1; }
 static constexpr int VTAB_VP = 12;
@@ -227,17 +255,8 @@ BPPP_HD void u64v_table_build_one(const WS &w, size_t i, int t) {
 #pragma unroll 1
     for (int e = 0; e < 8; e++) ws_st_pt(w, i, VL::TAB + (t * 8 + e) * VL::TAB_STRIDE, tab.m[e]);
 }
-// Phase T3 (after the batch inversion of every Z): entry -> affine canonical words in place; identity -> zero sentinel
-BPPP_HD void u64v_table_finish_one(const WS &w, size_t i, int entry) {
-    const int off = VL::TAB + entry * VL::TAB_STRIDE;
-    bool id;
-    PtA a = ws_affine(w, i, off, off + PT_W, id);
-    if (id) { a.x = fe_zero(); a.y = fe_zero(); }
-    ws_st_pta(w, i, off, a);
-    ws_st_fe(w, i, off + 2 * FE_W, fe_mul(a.x, fe_beta()));
-}
 // Phases T2+T3 fused: Montgomery batch inversion of every table entry's Z over this thread's strided share of the
-// (entry, proof) items, writing the affine words in place on the way back (no separate 1/Z round trip through HBM)
+// (entry, proof) items, writing the affine entries (array-of-structures region) on the way back
 BPPP_HD void u64v_tables_normalize_strided(const WS &w, size_t t, size_t T) {
     const size_t total = (size_t)VL::TAB_ENTRIES * w.n;
     const Fe beta = fe_beta();
@@ -265,8 +284,9 @@ BPPP_HD void u64v_tables_normalize_strided(const WS &w, size_t t, size_t T) {
             rinv = fe_mul(rinv, p.z);
             a = pt_to_affine_with_zinv(p, zi);
         }
-        ws_st_pta(w, i, off, a);
-        ws_st_fe(w, i, off + 2 * FE_W, fe_mul(a.x, beta));     // x of the endomorphism image (beta x, y), any representative
+        uint32_t *dst = vtab_entry(w, i, (int)e);
+        vtab_st_fe(dst, a.x); vtab_st_fe(dst + FE_W, a.y);
+        vtab_st_fe(dst + 2 * FE_W, fe_normalize(fe_mul(a.x, beta)));     // x of the endomorphism image (beta x, y)
     }
 }
 // acc = sum_k ks[k] * P_{tids[k]} + init from the affine tables
@@ -293,10 +313,10 @@ BPPP_HD Pt straus_tables(const WS &w, size_t i, const int *tids, const Sc *ks, c
             if (neg[h]) sd = -sd;
             if (sd == 0) continue;
             int a = sd < 0 ? -sd : sd;
-            const int off = VL::TAB + (tids[h >> 1] * 8 + (a - 1)) * VL::TAB_STRIDE;
+            const uint32_t *ent = vtab_entry(w, i, tids[h >> 1] * 8 + (a - 1));
             PtA q;
-            q.x = ws_ld_fe(w, i, off + ((h & 1) ? 2 * FE_W : 0));                       // odd halves use (beta x, y)
-            q.y = ws_ld_fe(w, i, off + FE_W);
+            q.x = vtab_ld_fe(ent + ((h & 1) ? 2 * FE_W : 0));                           // odd halves use (beta x, y)
+            q.y = vtab_ld_fe(ent + FE_W);
             if (fe_is_zero_canonical(q.x) && fe_is_zero_canonical(q.y)) continue;       // identity point: nothing to add
             if (sd < 0) q.y = fe_normalize_weak(fe_negate(q.y, 1));
             acc = ptj_add_mixed_hot(acc, q);
