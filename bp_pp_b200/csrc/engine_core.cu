@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(BPPP_MSM_BLOCK, BPPP_MSM_MINBLOCKS) k_msm_fixe
     int lane = (int)(tid % LANES);
     bool live = i < w.n;
     if (!live) i = w.n - 1;
-    Pt acc = msm_fixed_lane(T, w, i, sc_off, tm.gen, nterms, lane, LANES);
+    Pt acc = T.sgn ? msm_fixed_lane_signed(T, w, i, sc_off, tm.gen, nterms, lane, LANES) : msm_fixed_lane(T, w, i, sc_off, tm.gen, nterms, lane, LANES);
     acc = lanes_reduce<LANES>(acc);
     if (live && lane == 0) ws_st_pt(w, i, out_off, acc);
 }
@@ -168,7 +168,7 @@ void launch_batch_inv(bppp_ctx *c, cudaStream_t st, WS w, int in_off, int out_of
 
 static int build_tables(bppp_ctx *c, const PtA *gens, const bool *gen_id) {
     const int W = c->T.W, nwin = c->T.nwin;
-    const uint32_t E = (1u << W) - 1u;
+    const uint32_t E = c->T.E;
     const size_t nent = (size_t)nwin * E;
     uint32_t *d_tmp = nullptr;
     CUDA_OK(cudaMalloc(&d_tmp, nent * (size_t)(4 * FE_W) * sizeof(uint32_t)));
@@ -205,7 +205,11 @@ extern "C" int bppp_ctx_create(bppp_ctx **out, int device, const uint8_t *gens64
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BPPP_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(BPPP_ERR_ARG, "bad device index");
     if (window_bits == 0) window_bits = 16;
-    if (window_bits < 2 || window_bits > 20) return fail(BPPP_ERR_ARG, "window_bits must be in 2..20");
+    // 2..20: unsigned windows; 21..23: signed windows (2^(W-1) entries each); a negative value asks for signed windows of
+    // |window_bits| bits at any size (tests)
+    const bool signed_windows = window_bits < 0 || window_bits > 20;
+    if (window_bits < 0) window_bits = -window_bits;
+    if (window_bits < 2 || window_bits > 23) return fail(BPPP_ERR_ARG, "window_bits must be in 2..23 (or negative for signed windows)");
     if (max_batch == 0) max_batch = 65536;
     PtA gens[NUM_GENS]; bool gen_id[NUM_GENS];
     for (int g = 0; g < NUM_GENS; g++) {
@@ -227,8 +231,8 @@ extern "C" int bppp_ctx_create(bppp_ctx **out, int device, const uint8_t *gens64
         CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
     }
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    c->T.W = window_bits; c->T.nwin = (256 + window_bits - 1) / window_bits; c->T.ngens = NUM_GENS;
-    size_t nent = (size_t)c->T.nwin * ((1u << window_bits) - 1u);
+    fixed_table_shape(c->T, window_bits, signed_windows); c->T.ngens = NUM_GENS;
+    size_t nent = (size_t)c->T.nwin * c->T.E;
     c->table_bytes = (size_t)NUM_GENS * nent * 64;
     CUDA_OK(cudaMalloc(&c->d_tab, c->table_bytes));
     c->T.tab = c->d_tab;

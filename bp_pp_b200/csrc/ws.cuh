@@ -83,13 +83,23 @@ enum : int32_t {
 };
 
 // ---- fixed-base tables ----
-// tab[((g * nwin + w) * (2^W - 1) + (d - 1))] = d * 2^(W w) * G_g, affine, 16 words (x[8], y[8]); zero = identity
+// tab[((g * nwin + w) * E + (d - 1))] = d * 2^(W w) * G_g, affine, 16 words (x[8], y[8]); zero = identity.
+// Unsigned windows: E = 2^W - 1 entries, nwin = ceil(256 / W).  Signed windows (sgn): digits in (-2^(W-1), 2^(W-1)], so
+// E = 2^(W-1) entries serve W bits -- one more bit per window for the same memory -- and nwin = ceil(257 / W) leaves
+// room for the final carry; a negative digit adds the negated entry.
 struct FixedTable {
     const uint4 *tab;
-    int W;       // window bits (1..16)
-    int nwin;    // ceil(256 / W)
+    int W;       // window bits
+    int nwin;
     int ngens;
+    uint32_t E;  // entries per (generator, window)
+    int sgn;
 };
+BPPP_HD void fixed_table_shape(FixedTable &T, int W, bool sgn) {
+    T.W = W; T.sgn = sgn ? 1 : 0;
+    T.nwin = sgn ? (257 + W - 1) / W : (256 + W - 1) / W;
+    T.E = sgn ? (1u << (W - 1)) : ((1u << W) - 1u);
+}
 
 BPPP_HD uint32_t scalar_window(const WS &w, size_t i, int sc_off, int win, int W) {
     int bit = win * W;
@@ -102,7 +112,7 @@ BPPP_HD uint32_t scalar_window(const WS &w, size_t i, int sc_off, int win, int W
 
 struct TableEntryRaw { uint4 a, b, c, e; };   // x words 0..7, y words 0..7
 BPPP_HD TableEntryRaw table_fetch(const FixedTable &T, int g, int win, uint32_t d) {
-    size_t idx = ((size_t)(g * T.nwin + win) * ((1u << T.W) - 1u) + (d - 1)) * 4;
+    size_t idx = ((size_t)(g * T.nwin + win) * T.E + (d - 1)) * 4;
     TableEntryRaw r;
 #if defined(__CUDA_ARCH__)
     r.a = __ldg(T.tab + idx); r.b = __ldg(T.tab + idx + 1); r.c = __ldg(T.tab + idx + 2); r.e = __ldg(T.tab + idx + 3);
@@ -171,6 +181,92 @@ BPPP_HD Pt msm_fixed_lane(const FixedTable &T, const WS &w, size_t i, int sc_off
         if (dcur != 0) {
             PtA q;
             if (table_decode(q, cur)) acc = ptx_add_mixed_hot(acc, q);
+        }
+        cur = nxt; dcur = dnxt;
+    }
+    return ptx_to_pt(acc);
+}
+
+
+// ---- signed windows ----
+// Three workspace words starting at the word that holds the first bit of window win - 1 (of window 0 for win = 0): they
+// cover window win - 1 (needed for the carry into win) and window win itself (2 W <= 46 bits from a bit offset < 32).
+struct WindowWords3 { uint32_t a, b, c; };
+BPPP_HD WindowWords3 scalar_window_words3(const WS &w, size_t i, int sc_off, int win, int W) {
+    int word = (win ? (win - 1) * W : 0) >> 5;
+    WindowWords3 r;
+    r.a = word < 8 ? ws_ld(w, i, sc_off + word) : 0u;
+    r.b = word + 1 < 8 ? ws_ld(w, i, sc_off + word + 1) : 0u;
+    r.c = word + 2 < 8 ? ws_ld(w, i, sc_off + word + 2) : 0u;
+    return r;
+}
+BPPP_HD uint32_t words3_bits(const WindowWords3 &ww, int rel, int W) {     // W bits from bit offset rel < 64
+    uint64_t v = rel < 32 ? (((uint64_t)ww.a | ((uint64_t)ww.b << 32)) >> rel) : (((uint64_t)ww.b | ((uint64_t)ww.c << 32)) >> (rel - 32));
+    return (uint32_t)v & ((1u << W) - 1u);
+}
+struct SignedDigit { uint32_t mag; bool neg; };
+// digit of window win: value + carry-in, recentred.  The carry out of window j is 1 iff value_j + carry_j > 2^(W-1), which
+// is decided by value_j alone unless value_j == 2^(W-1) exactly; only then does it look further down (probability 2^-W).
+BPPP_HD SignedDigit signed_window_digit(const FixedTable &T, const WS &w, size_t i, int sc_off, int win, const WindowWords3 &ww) {
+    const int W = T.W;
+    const uint32_t H = 1u << (W - 1);
+    const int base = ((win ? (win - 1) * W : 0) >> 5) * 32;
+    uint32_t v = words3_bits(ww, win * W - base, W);
+    uint32_t carry = 0;
+    if (win) {
+        uint32_t vp = words3_bits(ww, (win - 1) * W - base, W);
+        carry = vp > H ? 1u : 0u;
+        if (vp == H) {
+#pragma unroll 1
+            for (int j = win - 2; j >= 0; j--) {
+                uint32_t vj = scalar_window(w, i, sc_off, j, W);
+                if (vj != H) { carry = vj > H ? 1u : 0u; break; }
+            }
+        }
+    }
+    uint32_t d = v + carry;
+    SignedDigit r;
+    if (win < T.nwin - 1 && d > H) { r.mag = (1u << W) - d; r.neg = true; }
+    else { r.mag = d; r.neg = false; }
+    return r;
+}
+// msm_fixed_lane for signed tables: same two-stage software pipeline
+BPPP_HD Pt msm_fixed_lane_signed(const FixedTable &T, const WS &w, size_t i, int sc_off, const int *term_gen, int nterms, int lane, int nlanes) {
+    PtX acc = ptx_identity();
+    const int items = nterms * T.nwin;
+    TableEntryRaw cur, nxt;
+    SignedDigit dcur, dnxt;
+    dcur.mag = 0; dcur.neg = false;
+    WindowWords3 ww_next; ww_next.a = ww_next.b = ww_next.c = 0;
+    int it = lane;
+    if (it < items) {
+        int t = it / T.nwin, win = it - t * T.nwin;
+        dcur = signed_window_digit(T, w, i, sc_off + 8 * t, win, scalar_window_words3(w, i, sc_off + 8 * t, win, T.W));
+        if (dcur.mag) cur = table_fetch(T, term_gen[t], win, dcur.mag);
+    }
+    if (it + nlanes < items) {
+        int t = (it + nlanes) / T.nwin, win = (it + nlanes) - t * T.nwin;
+        ww_next = scalar_window_words3(w, i, sc_off + 8 * t, win, T.W);
+    }
+#pragma unroll 1
+    for (; it < items; it += nlanes) {
+        const int itn = it + nlanes, itnn = it + 2 * nlanes;
+        dnxt.mag = 0; dnxt.neg = false;
+        if (itn < items) {
+            int t = itn / T.nwin, win = itn - t * T.nwin;
+            dnxt = signed_window_digit(T, w, i, sc_off + 8 * t, win, ww_next);
+            if (dnxt.mag) nxt = table_fetch(T, term_gen[t], win, dnxt.mag);
+        }
+        if (itnn < items) {
+            int t = itnn / T.nwin, win = itnn - t * T.nwin;
+            ww_next = scalar_window_words3(w, i, sc_off + 8 * t, win, T.W);
+        }
+        if (dcur.mag != 0) {
+            PtA q;
+            if (table_decode(q, cur)) {
+                if (dcur.neg) q.y = fe_negate(q.y, 1);
+                acc = ptx_add_mixed_hot(acc, q);
+            }
         }
         cur = nxt; dcur = dnxt;
     }

@@ -67,8 +67,10 @@ enum {
 
 /* Context for U64RangeProofProtocol { g, g_vec[16], h_vec[32] } (src/range_proof/u64_proof.rs:19-28) on
  * CUDA device `device`.  gens64 = g || g_vec || h_vec as 49 x 64-byte affine points.  Builds the
- * fixed-base window tables on the device (window_bits in 4..16; 0 = default 16) and a workspace for
- * `max_batch` proofs per launch sequence (larger batches are processed in slices). */
+ * fixed-base window tables on the device and a workspace for `max_batch` proofs per launch sequence (larger
+ * batches are processed in slices).  window_bits: 0 = default 16 (3.3 GB of tables); 2..20 = unsigned windows
+ * (20: 42.7 GB); 21..23 = signed windows with 2^(W-1) entries each (22: 78.9 GB); a negative value requests
+ * signed windows of |window_bits| bits at any width. */
 int bppp_ctx_create(bppp_ctx **out, int device, const uint8_t *gens64, int window_bits, size_t max_batch);
 void bppp_ctx_destroy(bppp_ctx *ctx);
 const char *bppp_last_error(void);

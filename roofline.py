@@ -17,7 +17,9 @@ NORMALISATIONS_VERIFY, NORMALISATIONS_PROVE = 5, 18
 
 
 def windows(window_bits: int) -> int:
-    return (256 + window_bits - 1) // window_bits
+    """windows of the fixed-base tables: unsigned digits up to 20 bits, signed digits (one spare bit for the carry) above"""
+    w = abs(window_bits)
+    return (257 + w - 1) // w if (window_bits < 0 or window_bits > 20) else (256 + w - 1) // w
 
 
 def msm_fixed_wmac(terms: int, window_bits: int) -> float:

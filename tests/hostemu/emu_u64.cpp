@@ -19,8 +19,11 @@ struct EmuCtx {
 extern "C" {
 void *emu_ctx_create(const uint8_t *gens64, int W) {
     EmuCtx *c = new EmuCtx();
-    int nwin = (256 + W - 1) / W;
-    size_t E = (1u << W) - 1;
+    bool sgn = W < 0;                          // negative: signed windows of |W| bits (ws.cuh:FixedTable)
+    if (sgn) W = -W;
+    fixed_table_shape(c->T, W, sgn);
+    int nwin = c->T.nwin;
+    size_t E = c->T.E;
     c->tab.assign((size_t)NUM_GENS * nwin * E * 4, uint4{0, 0, 0, 0});
     for (int g = 0; g < NUM_GENS; g++) {
         PtA a; int s = pta_from_xy64(a, gens64 + 64 * g);
@@ -43,7 +46,7 @@ void *emu_ctx_create(const uint8_t *gens64, int W) {
             for (int k = 0; k < W; k++) base = pt_double(base);
         }
     }
-    c->T.tab = c->tab.data(); c->T.W = W; c->T.nwin = nwin; c->T.ngens = NUM_GENS;
+    c->T.tab = c->tab.data(); c->T.ngens = NUM_GENS;
     return c;
 }
 void emu_ctx_destroy(void *p) { delete (EmuCtx *)p; }
@@ -51,7 +54,8 @@ void emu_ctx_destroy(void *p) { delete (EmuCtx *)p; }
 static void emu_msm_fixed(EmuCtx *c, const WS &w, size_t n, int sc_off, const int *term_gen, int nterms, int out_off, int nlanes) {
     for (size_t i = 0; i < n; i++) {
         Pt acc = pt_identity();
-        for (int lane = 0; lane < nlanes; lane++) acc = pt_add(acc, msm_fixed_lane(c->T, w, i, sc_off, term_gen, nterms, lane, nlanes));
+        for (int lane = 0; lane < nlanes; lane++)
+            acc = pt_add(acc, c->T.sgn ? msm_fixed_lane_signed(c->T, w, i, sc_off, term_gen, nterms, lane, nlanes) : msm_fixed_lane(c->T, w, i, sc_off, term_gen, nterms, lane, nlanes));
         ws_st_pt(w, i, out_off, acc);
     }
 }
@@ -83,6 +87,27 @@ int emu_u64_verify_batch(void *ctx, size_t n, const uint8_t *commits, const uint
     int tg49[49]; for (int t = 0; t < 49; t++) tg49[t] = t;
     emu_msm_fixed(c, w, n, VL::FS, tg49, 49, VL::ACC, 8);
     for (size_t i = 0; i < n; i++) { u64v_verdict_one(w, i); status[i] = (int32_t)ws_ld(w, i, VL::STATUS); }
+    return 0;
+}
+// commit_value (engine_core.cu:bppp_u64_commit_batch): x g + s h_0 through the fixed-base lane code, 3 lanes
+int emu_u64_commit_batch(void *ctx, size_t n, const uint64_t *xs, const uint8_t *blinds, uint8_t *out33) {
+    EmuCtx *c = (EmuCtx *)ctx;
+    std::vector<uint32_t> buf((size_t)VL::WORDS * n, 0);
+    WS w{buf.data(), n};
+    for (size_t i = 0; i < n; i++) {
+        Sc s;
+        if (!sc_from_be32(s, blinds + 32 * i)) return -1;
+        ws_st_sc(w, i, VL::FS, sc_from_u64(xs[i]));
+        ws_st_sc(w, i, VL::FS + 8, s);
+    }
+    int tg[2] = {GEN_G, GEN_HVEC};
+    emu_msm_fixed(c, w, n, VL::FS, tg, 2, VL::ACC, 3);
+    emu_batch_inv(w, n, VL::ACC + 2 * FE_W, VL::ZINV);
+    for (size_t i = 0; i < n; i++) {
+        bool id;
+        PtA a = ws_affine(w, i, VL::ACC, VL::ZINV, id);
+        pta_compress(out33 + 33 * i, a, id);
+    }
     return 0;
 }
 }

@@ -3,6 +3,8 @@ with the bound assertions of fe.cuh enabled, against the oracles.  This is how t
 import ctypes as C
 import random
 
+import pytest
+
 from conftest import synth_batch, xy
 
 LABEL = b"u64 range proof"
@@ -194,6 +196,29 @@ def _emu_ctx(emu_u64, gens64, W=4):
     return C.c_void_p(emu_u64.emu_ctx_create(B(gens64), W))
 
 
+def test_signed_window_digits_on_adversarial_scalars(emu_u64, ref, gens64):
+    """Signed fixed-base windows: scalars made of windows equal to 2^(W-1) exactly (the carry has to look further down),
+    all-ones, n - 1 and small values, through the commit path x*g + s*h_0 against plain integer arithmetic."""
+    for W in (-4, -6):
+        w = -W
+        H = 1 << (w - 1)
+        chain = sum(H << (w * k) for k in range(256 // w - 1))
+        blinds = [chain, chain + 1, chain - 1, (chain << w) % ref.N, ref.N - 1, ref.N - 2, 1, 0, H, H + 1, (1 << 255) + chain % (1 << 200), 2**256 % ref.N]
+        blinds = [b % ref.N for b in blinds]
+        xs = [0, 1, 2**64 - 1, H, H - 1, H + 1, 5, 6, 7, 8, 9, 10]
+        n = len(xs)
+        ctx = _emu_ctx(emu_u64, gens64, W=W)
+        out = (C.c_uint8 * (33 * n))()
+        xa = (C.c_uint64 * n)(*xs)
+        emu_u64.emu_u64_commit_batch(ctx, C.c_size_t(n), xa, B(b"".join(be(b) for b in blinds)), out)
+        g = (int.from_bytes(gens64[:32], "big"), int.from_bytes(gens64[32:64], "big"))
+        h0 = (int.from_bytes(gens64[64 * 17:64 * 17 + 32], "big"), int.from_bytes(gens64[64 * 17 + 32:64 * 18], "big"))
+        for i in range(n):
+            expect = ref.pt_add(ref.pt_mul(g, xs[i]), ref.pt_mul(h0, blinds[i]))
+            assert bytes(out)[33 * i:33 * i + 33] == ref.pt_to_bytes(expect), (W, i)
+        emu_u64.emu_ctx_destroy(ctx)
+
+
 def test_device_verify_logic_matches_oracle(emu_u64, ref, oracle, gens64):
     n = 6
     xs, blinds, rngs = synth_batch(ref, n)
@@ -219,11 +244,12 @@ def test_device_verify_logic_matches_oracle(emu_u64, ref, oracle, gens64):
     emu_u64.emu_ctx_destroy(ctx)
 
 
-def test_device_prove_logic_matches_oracle(emu_u64, ref, oracle, gens64):
+@pytest.mark.parametrize("W", [5, -5, -7])     # 5: a width that does not divide 32; negative: signed windows (ws.cuh:FixedTable)
+def test_device_prove_logic_matches_oracle(emu_u64, ref, oracle, gens64, W):
     n = 5
     xs, blinds, rngs = synth_batch(ref, n)   # includes x = 0, 1, 2^64 - 1
     proofs, st = oracle.u64_prove_batch(gens64, xs, blinds, rngs, LABEL, 4)
-    ctx = _emu_ctx(emu_u64, gens64, W=5)      # a window width that does not divide 32
+    ctx = _emu_ctx(emu_u64, gens64, W=W)
     out = (C.c_uint8 * (525 * n))(); status = (C.c_int32 * n)()
     xa = (C.c_uint64 * n)(*xs)
     emu_u64.emu_u64_prove_batch(ctx, C.c_size_t(n), xa, B(blinds), B(rngs), B(LABEL), len(LABEL), out, status)
