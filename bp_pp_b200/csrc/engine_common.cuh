@@ -16,7 +16,10 @@ int engine_fail(int code, const std::string &msg);
 #define CUDA_OK(expr)                                                                                             \
     do {                                                                                                          \
         cudaError_t _e = (expr);                                                                                  \
-        if (_e != cudaSuccess) return engine_fail(BPPP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+        if (_e != cudaSuccess) {                                                                                  \
+            (void)cudaGetLastError();   /* a recoverable error (e.g. out of memory) must not poison the next call */ \
+            return engine_fail(_e == cudaErrorMemoryAllocation ? BPPP_ERR_NOMEM : BPPP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+        }                                                                                                         \
     } while (0)
 
 struct TermMap { int gen[NUM_GENS]; };

@@ -220,6 +220,7 @@ extern "C" int bppp_ctx_create(bppp_ctx **out, int device, const uint8_t *gens64
     }
     CUDA_OK(cudaSetDevice(device));
     bppp_ctx *c = new bppp_ctx();
+    struct Guard { bppp_ctx *c; ~Guard() { if (c) bppp_ctx_destroy(c); } } guard{c};      // any early return below frees what was allocated
     c->device = device;
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
@@ -246,7 +247,8 @@ extern "C" int bppp_ctx_create(bppp_ctx **out, int device, const uint8_t *gens64
     CUDA_OK(cudaMalloc(&c->d_out, (size_t)U64_PROOF_BYTES_COMPRESSED * max_batch));
     CUDA_OK(cudaMalloc(&c->d_status, sizeof(int32_t) * max_batch));
     int rc = build_tables(c, gens, gen_id);
-    if (rc != BPPP_OK) { bppp_ctx_destroy(c); return rc; }
+    if (rc != BPPP_OK) return rc;
+    guard.c = nullptr;
     *out = c;
     return BPPP_OK;
 }

@@ -18,6 +18,7 @@
 #include "engine_generic.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <mutex>
 
 using namespace bppp;
 
@@ -273,6 +274,7 @@ uint64_t generic_launch_count() { return g_generic_launches.load(); }
 struct Carver { size_t total = 0; size_t take(size_t bytes) { size_t o = total; total += (bytes + 255) & ~(size_t)255; return o; } };
 static uint8_t *g_slab[16] = {};
 static size_t g_slab_cap[16] = {};
+static std::mutex g_slab_mu[16];     // one Pippenger run at a time per device: the slab is shared by every caller in the process
 static int scratch_reserve(size_t bytes, uint8_t **out) {
     int dev = 0;
     CUDA_OK(cudaGetDevice(&dev));
@@ -350,6 +352,9 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     size_t o_start = cv.take(4 * (size_t)nb), o_end = cv.take(4 * (size_t)nb), o_buckets = cv.take((size_t)PT_BYTES * nb);
     size_t o_heavy = cv.take(256 + 8 * hslots), o_segout = cv.take((size_t)PT_BYTES * hq.capL), o_chunks = cv.take((size_t)PT_BYTES * nwin * nchunks);
     size_t o_tmp = cv.take((size_t)PT_BYTES * ((size_t)nwin * nchunks / 16 + 2)), o_cub = cv.take(cub_bytes);
+    int dev_for_lock = 0;
+    CUDA_OK(cudaGetDevice(&dev_for_lock));
+    std::lock_guard<std::mutex> slab_lock(g_slab_mu[dev_for_lock & 15]);     // released after the final synchronise below
     uint8_t *slab = nullptr;
     int rc = scratch_reserve(cv.total, &slab);
     if (rc != BPPP_OK) return rc;

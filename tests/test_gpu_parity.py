@@ -231,3 +231,13 @@ def test_signed_and_unsigned_window_tables_agree_with_the_oracle(gens64, batch, 
     import oracle_c
     assert c.verify_batch(batch["commits"][:33 * n], bytes(bad), LABEL) == oracle_c.u64_verify_batch(gens64, batch["commits"][:33 * n], bytes(bad), LABEL, THREADS)
     c.close()
+
+
+def test_context_creation_failure_is_clean(gens64):
+    """A workspace that cannot be allocated fails with an error (no crash, nothing leaked that blocks the next context)."""
+    import bp_pp_b200 as B
+    with pytest.raises(B.BpppError):
+        B.Context(gens64, 0, 8, 1 << 27)            # ~3.7 TB of workspace
+    c = B.Context(gens64, 0, 8, 16)
+    assert c.info()["window_bits"] == 8
+    c.close()
