@@ -18,6 +18,14 @@ rnd = random.Random(1)
 pts = B.points_generate(xy(g), xy(gv[0]), 1300)
 sc = b"".join(rnd.randrange(R.N).to_bytes(32, "big") for _ in range(1300))
 print("msm:", B.msm(pts, sc).hex()[:16], B.msm(pts[:64 * 50], sc[:32 * 50]).hex()[:16])
+# skewed scalars: medium-heavy buckets and multi-segment buckets (k_msm_heavy / k_msm_heavy_sum)
+pts7 = B.points_generate(xy(g), xy(gv[1]), 7000)
+sc7 = b"".join((rnd.choice((1, 2, 2**40 + 3)) if i % 50 else rnd.randrange(R.N)).to_bytes(32, "big") for i in range(7000))
+print("msm skewed:", B.msm(pts7, sc7).hex()[:16])
+# signed fixed-base windows
+proto_s = B.U64RangeProofProtocol(xy(g), [xy(p) for p in gv], [xy(p) for p in hv], window_bits=-5, max_batch=40)
+ps, sts = proto_s.prove_batch(xs, blinds, rng, b"u64 range proof")
+print("signed windows:", ps == proofs, proto_s.verify_batch(commits, ps, b"u64 range proof") == [1] * n)
 w = B.WeightNormLinearArgument(pts[:64], pts[64:64 * 9], pts[64 * 9:64 * 17], sc[:32 * 8], sc[32 * 8:32 * 9], sc[32 * 9:32 * 10])
 l, nn = sc[32 * 10:32 * 18], sc[32 * 18:32 * 26]
 com = w.commit(l, nn)
