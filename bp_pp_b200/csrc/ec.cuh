@@ -41,18 +41,18 @@ BPPP_HD Pt pt_add(const Pt &p, const Pt &q) {
     Fe t3 = fe_mul(fe_add(p.x, p.y), fe_add(q.x, q.y));        // (X1+Y1)(X2+Y2)
     Fe t4 = fe_mul(fe_add(p.y, p.z), fe_add(q.y, q.z));        // (Y1+Z1)(Y2+Z2)
     Fe t5 = fe_mul(fe_add(p.x, p.z), fe_add(q.x, q.z));        // (X1+Z1)(X2+Z2)
-    Fe xy = fe_sub(t3, fe_add(t0, t1), 2);                     // X1Y2+X2Y1        mag 4
-    Fe yz = fe_sub(t4, fe_add(t1, t2), 2);                     // Y1Z2+Y2Z1        mag 4
-    Fe xz = fe_sub(t5, fe_add(t0, t2), 2);                     // X1Z2+X2Z1        mag 4
-    Fe x3 = fe_mul_int(t0, 3);                                 // 3 X1X2           mag 3
-    Fe bz = fe_normalize_weak(fe_mul_int(t2, 21));             // b3 Z1Z2          mag 1
-    Fe zp = fe_add(t1, bz);                                    // Y1Y2 + b3Z1Z2    mag 2
-    Fe zm = fe_sub(t1, bz, 1);                                 // Y1Y2 - b3Z1Z2    mag 3
-    Fe bxz = fe_normalize_weak(fe_mul_int(fe_normalize_weak(xz), 21));  // b3 (X1Z2+X2Z1)  mag 1
+    Fe xy = fe_sub(t3, fe_add(t0, t1), 2);   // X1Y2+X2Y1
+    Fe yz = fe_sub(t4, fe_add(t1, t2), 2);   // Y1Z2+Y2Z1
+    Fe xz = fe_sub(t5, fe_add(t0, t2), 2);   // X1Z2+X2Z1
+    Fe x3 = fe_mul_int(t0, 3);   // 3 X1X2
+    Fe bz = fe_normalize_weak(fe_mul_int(t2, 21));   // b3 Z1Z2
+    Fe zp = fe_add(t1, bz);   // Y1Y2 + b3Z1Z2
+    Fe zm = fe_sub(t1, bz, 1);   // Y1Y2 - b3Z1Z2
+    Fe bxz = fe_normalize_weak(fe_mul_int(fe_normalize_weak(xz), 21));   // b3 (X1Z2+X2Z1)
     Pt r;
-    r.x = fe_normalize_weak(fe_sub(fe_mul(xy, zm), fe_mul(yz, bxz), 1));       // mag 3 -> 1
-    r.y = fe_normalize_weak(fe_add(fe_mul(zm, zp), fe_mul(x3, bxz)));          // mag 2 -> 1
-    r.z = fe_normalize_weak(fe_add(fe_mul(yz, zp), fe_mul(x3, xy)));           // mag 2 -> 1
+    r.x = fe_normalize_weak(fe_sub(fe_mul(xy, zm), fe_mul(yz, bxz), 1));
+    r.y = fe_normalize_weak(fe_add(fe_mul(zm, zp), fe_mul(x3, bxz)));
+    r.z = fe_normalize_weak(fe_add(fe_mul(yz, zp), fe_mul(x3, xy)));
     return r;
 }
 
@@ -61,13 +61,13 @@ BPPP_HD Pt pt_add_mixed(const Pt &p, const PtA &q) {
     Fe t0 = fe_mul(p.x, q.x);                                  // X1X2
     Fe t1 = fe_mul(p.y, q.y);                                  // Y1Y2
     Fe t3 = fe_mul(fe_add(p.x, p.y), fe_add(q.x, q.y));
-    Fe xy = fe_sub(t3, fe_add(t0, t1), 2);                     // X1Y2+X2Y1        mag 4
-    Fe yz = fe_add(fe_mul(q.y, p.z), p.y);                     // Y2Z1+Y1          mag 2
-    Fe xz = fe_add(fe_mul(q.x, p.z), p.x);                     // X2Z1+X1          mag 2
-    Fe x3 = fe_mul_int(t0, 3);                                 // mag 3
-    Fe bz = fe_normalize_weak(fe_mul_int(p.z, 21));            // b3 Z1            mag 1
-    Fe zp = fe_add(t1, bz);                                    // mag 2
-    Fe zm = fe_sub(t1, bz, 1);                                 // mag 3
+    Fe xy = fe_sub(t3, fe_add(t0, t1), 2);   // X1Y2+X2Y1
+    Fe yz = fe_add(fe_mul(q.y, p.z), p.y);   // Y2Z1+Y1
+    Fe xz = fe_add(fe_mul(q.x, p.z), p.x);   // X2Z1+X1
+    Fe x3 = fe_mul_int(t0, 3);
+    Fe bz = fe_normalize_weak(fe_mul_int(p.z, 21));   // b3 Z1
+    Fe zp = fe_add(t1, bz);
+    Fe zm = fe_sub(t1, bz, 1);
     Fe bxz = fe_normalize_weak(fe_mul_int(fe_normalize_weak(xz), 21));
     Pt r;
     r.x = fe_normalize_weak(fe_sub(fe_mul(xy, zm), fe_mul(yz, bxz), 1));
@@ -82,10 +82,10 @@ BPPP_HD Pt pt_double(const Pt &p) {
     Fe zz = fe_sqr(p.z);                                       // Z^2
     Fe yz = fe_mul(p.y, p.z);
     Fe xy = fe_mul(p.x, p.y);
-    Fe bzz = fe_normalize_weak(fe_mul_int(zz, 21));            // b3 Z^2           mag 1
-    Fe y8 = fe_mul_int(yy, 8);                                 // 8 Y^2            mag 8
-    Fe t0 = fe_sub(yy, fe_mul_int(bzz, 3), 3);                 // Y^2 - 9b Z^2     mag 5
-    Fe yp = fe_add(yy, bzz);                                   // Y^2 + 3b Z^2     mag 2
+    Fe bzz = fe_normalize_weak(fe_mul_int(zz, 21));   // b3 Z^2
+    Fe y8 = fe_mul_int(yy, 8);   // 8 Y^2
+    Fe t0 = fe_sub(yy, fe_mul_int(bzz, 3), 3);   // Y^2 - 9b Z^2
+    Fe yp = fe_add(yy, bzz);   // Y^2 + 3b Z^2
     Pt r;
     r.x = fe_normalize_weak(fe_mul_int(fe_mul(t0, xy), 2));                    // 2 XY (Y^2 - 9bZ^2)
     r.y = fe_normalize_weak(fe_add(fe_mul(t0, yp), fe_mul(bzz, y8)));          // + 24 b Y^2 Z^2 = b3Z^2 * 8Y^2
@@ -188,11 +188,11 @@ BPPP_HD PtX ptx_identity() { PtX r; r.x = fe_zero(); r.y = fe_zero(); r.zz = fe_
 // 2Q for affine Q (mdbl-2008-s-1)
 template <bool INL> BPPP_HD PtX ptx_double_affine_t(const PtA &q) {
     PtX r;
-    Fe U = fe_mul_int_t<!INL>(q.y, 2);                       // 2y            mag 2
+    Fe U = fe_mul_int_t<!INL>(q.y, 2);   // 2y
     Fe V = fe_sqr_t<INL>(U);                                // 4y^2
     Fe W = fe_mul_t<INL>(U, V);                             // 8y^3
     Fe S = fe_mul_t<INL>(q.x, V);
-    Fe M = fe_mul_int_t<!INL>(fe_sqr_t<INL>(q.x), 3);               // 3x^2          mag 3
+    Fe M = fe_mul_int_t<!INL>(fe_sqr_t<INL>(q.x), 3);   // 3x^2
     r.x = fe_normalize_weak(fe_subm_t<!INL>(fe_sqr_t<INL>(M), fe_mul_int_t<!INL>(S, 2), 2));
     r.y = fe_normalize_weak(fe_subm_t<!INL>(fe_mul_t<INL>(M, fe_subm_t<!INL>(S, r.x, 1)), fe_mul_t<INL>(W, q.y), 1));
     r.zz = V; r.zzz = W;
@@ -205,8 +205,8 @@ template <bool INL> BPPP_HD PtX ptx_add_mixed_t(const PtX &p, const PtA &q) {
     if (p.inf) { r.x = q.x; r.y = q.y; r.zz = fe_one(); r.zzz = fe_one(); r.inf = false; return r; }
     Fe U2 = fe_mul_t<INL>(q.x, p.zz);
     Fe S2 = fe_mul_t<INL>(q.y, p.zzz);
-    Fe P = fe_subm_t<!INL>(U2, p.x, 1);                       // mag 3
-    Fe R = fe_subm_t<!INL>(S2, p.y, 1);                       // mag 3
+    Fe P = fe_subm_t<!INL>(U2, p.x, 1);
+    Fe R = fe_subm_t<!INL>(S2, p.y, 1);
     if (fe_normalizes_to_zero(P)) {                  // same x: P1 = +-Q
         if (fe_normalizes_to_zero(R)) return ptx_double_affine_t<INL>(q);
         return ptx_identity();
