@@ -296,7 +296,7 @@ def run_ours(args):
         import oracle_c as OC
         OC.use_native()
         cores = os.cpu_count() or 1
-        sample = min(n, max(64, 48 * cores))
+        sample = min(n, max(256, 192 * cores))       # ~6 ms of single-thread work per proof: 10-30 s of CPU work in total
         c_s, p_s = commits[:sample].tobytes(), proofs[:sample].tobytes()
         t0 = time.perf_counter()
         overd = OC.u64_verify_batch(gens, c_s, p_s, LABEL, cores)
@@ -349,7 +349,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     g, gv, hv = R.synth_generators()
     gens = b"".join(xy(p) for p in [g] + gv + hv)
-    sample = max(64, 32 * cores)
+    sample = max(128, 96 * cores)              # ~10 s of CPU work per step
     import numpy as np
     rnd = np.random.default_rng(20260101)
     xs = rnd.integers(0, 2**64, size=sample, dtype=np.uint64)
