@@ -26,6 +26,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 LABEL = b"u64 range proof"
 METRIC = "u64 range proofs/sec (verify; batch of 65,536 independent proofs)"
 UNIT = "proofs/s"
+WORKLOAD = "verify_batch: 65,536 independent u64 range proofs per GPU, bit-exact verdicts (BASELINE config 2)"
 
 # ---- algorithmic integer work: roofline.py (SURVEY 8d accounting) ----
 from roofline import msm_fixed_wmac, prove_wmac, straus_wmac, verify_wmac, windows as fixed_windows  # noqa: E402
@@ -309,7 +310,7 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(v_ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 limbs (256-bit modular integer arithmetic)", "data": "synthetic",
-        "config": {"workload": "verify_batch: 65,536 independent u64 range proofs per GPU, bit-exact verdicts (BASELINE config 2)",
+        "config": {"workload": WORKLOAD,
                    "batch_per_gpu": n, "tampered": "every 16th record", "window_bits": W, "table_windows": fixed_windows(W), "table_gb": round(info["table_bytes"] / 1e9, 1), "point_format": "33-byte SEC1 compressed (525-byte records)",
                    "l2": "256 MiB flush between timed iterations; the window tables (tens of GB) and the workspace exceed L2",
                    "parallelism": f"proof batch sharded x{world}, no data-path collective"},
@@ -372,8 +373,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 limbs (256-bit modular integer arithmetic)", "data": "synthetic",
-        "config": {"workload": "verify: the reference algorithm (one scalar multiplication per MSM term, src/util.rs:46-60) on a bounded "
-                               f"sample of {sample} proofs per step of the same synthetic batch", "threads": cores},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": 65536,
+                   "reference_arm": "the reference algorithm (one scalar multiplication per MSM term, src/util.rs:46-60) on a bounded "
+                                    f"sample of {sample} proofs per step drawn the same way as the batch", "threads": cores},
         "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} proofs per step x {args.steps} steps, {dt:.2f} s wall"},
         "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
