@@ -59,6 +59,31 @@ def test_field_ops_on_non_canonical_representatives(emu_prims, ref):
                 assert int.from_bytes(o, "big") == (7 * a + 8 * b - c) * (top - 1) % P
 
 
+def test_field_and_scalar_ops_property(emu_prims, ref):
+    """hypothesis: the device field / scalar code (host build) against Python integers on operands biased towards limb
+    boundaries (all-ones / all-zero limbs, values around p, n and 2^256)."""
+    from hypothesis import given, settings, strategies as st
+    L, P, N = emu_prims, ref.P, ref.N
+    limb = st.sampled_from([0, 1, 2, 0xFFFFFFFF, 0xFFFFFFFE, 0x80000000, 0x7FFFFFFF, 977, 0xFFFFFC2F]) | st.integers(0, 2**32 - 1)
+    words = st.lists(limb, min_size=8, max_size=8).map(lambda ws: sum(w << (32 * k) for k, w in enumerate(ws)))
+    near = st.sampled_from([0, P, N, 2**256 - 1, 2**255]).flatmap(lambda c: st.integers(-2**33, 2**33).map(lambda d: (c + d) % 2**256))
+    val = words | near | st.integers(0, 2**256 - 1)
+
+    @settings(max_examples=400, deadline=None)
+    @given(val, val, val, st.integers(1, 8), st.integers(1, 8))
+    def check(a, b, c, k1, k2):
+        o = O(32); L.emu_fe_mul(B(be(a)), B(be(b)), o); assert int.from_bytes(o, "big") == a * b % P
+        o = O(32); L.emu_fe_sqr(B(be(a)), o); assert int.from_bytes(o, "big") == a * a % P
+        o = O(32); L.emu_fe_expr(B(be(a)), B(be(b)), B(be(c)), B(be(b)), k1, k2, o)
+        assert int.from_bytes(o, "big") == (a * k1 + b * k2 - c) * b % P
+        sa, sb = a % N, b % N
+        o = O(32); L.emu_sc_mul(B(be(sa)), B(be(sb)), o); assert int.from_bytes(o, "big") == sa * sb % N
+        o = O(32); L.emu_sc_wide(B(be(a) + be(b)), o); assert int.from_bytes(o, "big") == ((a << 256) | b) % N
+        o = O(32); L.emu_sc_sub(B(be(sa)), B(be(sb)), o); assert int.from_bytes(o, "big") == (sa - sb) % N
+
+    check()
+
+
 def test_scalar_ops(emu_prims, ref):
     L, N = emu_prims, ref.N
     rnd = random.Random(8)
