@@ -63,11 +63,18 @@ def main():
         c, l, nn = rand_scalars(rnd, n), rand_scalars(rnd, n), rand_scalars(rnd, n)
         rho = rnd.randrange(1, R.N)
         w = B.WeightNormLinearArgument(g, gvec, hvec, c, rho.to_bytes(32, "big"), (rho * rho % R.N).to_bytes(32, "big"))
-        t0 = time.perf_counter(); com = w.commit(l, nn); t_c = time.perf_counter() - t0
-        t0 = time.perf_counter(); r, x, lo, no = w.prove(com, b"wnla big", l, nn); t_p = time.perf_counter() - t0
-        t0 = time.perf_counter(); ok = w.verify(com, b"wnla big", r, x, lo, no); t_v = time.perf_counter() - t0
-        wn[f"2^{logn}"] = {"commit_s": round(t_c, 3), "prove_s": round(t_p, 3), "verify_s": round(t_v, 3), "rounds": len(r) // 33, "verified": ok == 1,
-                           "note": "wall clock through the host-buffer C ABI, uploads included"}
+        def best_of(fn, reps=2):      # the first call of a size also grows the cached device scratch slab
+            ts, out = [], None
+            for _ in range(reps):
+                t0 = time.perf_counter(); out = fn(); ts.append(time.perf_counter() - t0)
+            return out, ts
+        com, t_c = best_of(lambda: w.commit(l, nn))
+        (r, x, lo, no), t_p = best_of(lambda: w.prove(com, b"wnla big", l, nn))
+        ok, t_v = best_of(lambda: w.verify(com, b"wnla big", r, x, lo, no))
+        wn[f"2^{logn}"] = {"commit_s": round(min(t_c), 3), "prove_s": round(min(t_p), 3), "verify_s": round(min(t_v), 3),
+                           "first_call_s": {"commit": round(t_c[0], 3), "prove": round(t_p[0], 3), "verify": round(t_v[0], 3)},
+                           "rounds": len(r) // 33, "verified": ok == 1,
+                           "note": "wall clock through the host-buffer C ABI, uploads included; best of 2 calls"}
     out["wnla_standalone"] = wn
     # ---- wide reciprocal (config 4) ----
     nd, np_ = 1024, 16
