@@ -241,3 +241,26 @@ def test_context_creation_failure_is_clean(gens64):
     c = B.Context(gens64, 0, 8, 16)
     assert c.info()["window_bits"] == 8
     c.close()
+
+
+def test_device_resident_entry_points_on_a_side_stream(ctx, batch):
+    """bppp_u64_{prove,verify}_batch_dev: operands already in HBM, work enqueued on the caller's (non-default) stream,
+    results identical to the host-buffer entry points."""
+    import numpy as np
+    import torch
+    n = batch["n"]
+    dev = torch.device("cuda", 0)
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        d_x = torch.from_numpy(np.array(batch["xs"], dtype=np.uint64).view(np.int64)).to(dev)
+        d_bl = torch.frombuffer(bytearray(batch["blinds"]), dtype=torch.uint8).to(dev)
+        d_rng = torch.frombuffer(bytearray(batch["rngs"]), dtype=torch.uint8).to(dev)
+        d_out = torch.zeros(525 * n, dtype=torch.uint8, device=dev)
+        d_pst = torch.zeros(n, dtype=torch.int32, device=dev)
+        ctx.prove_batch_dev(n, d_x.data_ptr(), d_bl.data_ptr(), d_rng.data_ptr(), LABEL, d_out.data_ptr(), d_pst.data_ptr(), stream=side.cuda_stream)
+        d_com = torch.frombuffer(bytearray(batch["commits"]), dtype=torch.uint8).to(dev)
+        d_vst = torch.zeros(n, dtype=torch.int32, device=dev)
+        ctx.verify_batch_dev(n, d_com.data_ptr(), d_out.data_ptr(), LABEL, d_vst.data_ptr(), stream=side.cuda_stream)
+    side.synchronize()
+    assert bytes(d_out.cpu().numpy()) == batch["proofs"]
+    assert d_pst.cpu().tolist() == [1] * n and d_vst.cpu().tolist() == [1] * n
