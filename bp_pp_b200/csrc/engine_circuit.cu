@@ -59,6 +59,23 @@ SV vmat(const SV &a, const Mat &m) {
     return r;
 }
 
+// the same over the column block [from, to) of the first `rows` rows of m, without materialising the block
+SV vmat_cols(const SV &a, const Mat &m, size_t rows_m, size_t from, size_t to) {
+    SV r(to - from, sc_zero());
+    const Sc one = sc_one();
+    size_t rows = std::min(a.size(), rows_m);
+    for (size_t i = 0; i < rows; i++) {
+        if (sc_is_zero(a[i])) continue;
+        const Sc *row = &m.v[i * m.cols];
+        for (size_t j = from; j < to; j++) {
+            const Sc &e = row[j];
+            if (sc_is_zero(e)) continue;
+            r[j - from] = sc_add(r[j - from], sc_eq(e, one) ? a[i] : sc_mul(a[i], e));
+        }
+    }
+    return r;
+}
+
 struct Panic { int32_t code; };
 Sc inv_or_panic(const Sc &a) { if (sc_is_zero(a)) throw Panic{ST_PANIC_INVERT_ZERO}; return sc_inv(a); }
 
@@ -124,20 +141,28 @@ Mat sub_cols(const Mat &W, size_t rows, size_t from, size_t to) {
     for (size_t i = 0; i < rows; i++) for (size_t j = from; j < to; j++) m.v[i * m.cols + (j - from)] = W.v[i * W.cols + j];
     return m;
 }
-Mat map_f(const Circuit &c, size_t isz, size_t jsz, int typ, const Mat &Wx) {
-    Mat m; m.rows = isz; m.cols = jsz; m.v.assign(isz * jsz, sc_zero());
+// vector_mul_on_matrix(a, map_f(..)) of circuit.rs:627-653 without building map_f's isz x jsz matrix (dim_nl x dim_nv scalars,
+// almost all zero): out[j] = sum_i a[i] Wx[i][partition(typ, j)] for the j the partition maps, zero elsewhere
+SV vmat_mapped(const SV &a, const Circuit &c, size_t isz, size_t jsz, int typ, const Mat &Wx) {
+    SV r(jsz, sc_zero());
+    const Sc one = sc_one();
+    size_t rows = std::min(a.size(), isz);
     for (size_t j = 0; j < jsz; j++) {
         int j_ = c.part_get(typ, j);
-        if (j_ < 0) continue;
-        for (size_t i = 0; i < isz; i++) m.v[i * jsz + j] = Wx.v[i * Wx.cols + (size_t)j_];
+        if (j_ < 0 || (size_t)j_ >= Wx.cols) continue;
+        Sc acc = sc_zero();
+        for (size_t i = 0; i < rows; i++) {
+            const Sc &e = Wx.v[i * Wx.cols + (size_t)j_];
+            if (sc_is_zero(e) || sc_is_zero(a[i])) continue;
+            acc = sc_add(acc, sc_eq(e, one) ? a[i] : sc_mul(a[i], e));
+        }
+        r[j] = acc;
     }
-    return m;
+    return r;
 }
 struct Coefs { SV nL, nR, nO, lL, lR, lO; };
 Coefs collect_c(const Circuit &c, const SV &lambda_vec, const SV &mu_vec, const Sc &mu) {
     size_t nm = c.dim_nm;
-    Mat M_lnL = sub_cols(c.W_l, c.dim_nl, 0, nm), M_mnL = sub_cols(c.W_m, c.dim_nm, 0, nm);
-    Mat M_lnR = sub_cols(c.W_l, c.dim_nl, nm, 2 * nm), M_mnR = sub_cols(c.W_m, c.dim_nm, nm, 2 * nm);
     Mat W_lO = sub_cols(c.W_l, c.dim_nl, 2 * nm, c.W_l.cols), W_mO = sub_cols(c.W_m, c.dim_nm, 2 * nm, c.W_m.cols);
     // diag_inv(mu, nm) (util.rs:118-132) applied as a diagonal scaling
     Sc mu_inv = inv_or_panic(mu);
@@ -145,12 +170,12 @@ Coefs collect_c(const Circuit &c, const SV &lambda_vec, const SV &mu_vec, const 
     for (size_t i = 0; i < nm; i++) { val = sc_mul(val, mu_inv); dinv[i] = val; }
     auto scale_diag = [&](SV v) { v.resize(nm, sc_zero()); for (size_t j = 0; j < nm; j++) v[j] = sc_mul(v[j], dinv[j]); return v; };
     Coefs r;
-    r.nL = scale_diag(vsub(vmat(lambda_vec, M_lnL), vmat(mu_vec, M_mnL)));
-    r.nR = scale_diag(vsub(vmat(lambda_vec, M_lnR), vmat(mu_vec, M_mnR)));
-    r.nO = scale_diag(vsub(vmat(lambda_vec, map_f(c, c.dim_nl, c.dim_nm, P_NO, W_lO)), vmat(mu_vec, map_f(c, c.dim_nm, c.dim_nm, P_NO, W_mO))));
-    r.lL = vsub(vmat(lambda_vec, map_f(c, c.dim_nl, c.dim_nv, P_LL, W_lO)), vmat(mu_vec, map_f(c, c.dim_nm, c.dim_nv, P_LL, W_mO)));
-    r.lR = vsub(vmat(lambda_vec, map_f(c, c.dim_nl, c.dim_nv, P_LR, W_lO)), vmat(mu_vec, map_f(c, c.dim_nm, c.dim_nv, P_LR, W_mO)));
-    r.lO = vsub(vmat(lambda_vec, map_f(c, c.dim_nl, c.dim_nv, P_LO, W_lO)), vmat(mu_vec, map_f(c, c.dim_nm, c.dim_nv, P_LO, W_mO)));
+    r.nL = scale_diag(vsub(vmat_cols(lambda_vec, c.W_l, c.dim_nl, 0, nm), vmat_cols(mu_vec, c.W_m, c.dim_nm, 0, nm)));
+    r.nR = scale_diag(vsub(vmat_cols(lambda_vec, c.W_l, c.dim_nl, nm, 2 * nm), vmat_cols(mu_vec, c.W_m, c.dim_nm, nm, 2 * nm)));
+    r.nO = scale_diag(vsub(vmat_mapped(lambda_vec, c, c.dim_nl, c.dim_nm, P_NO, W_lO), vmat_mapped(mu_vec, c, c.dim_nm, c.dim_nm, P_NO, W_mO)));
+    r.lL = vsub(vmat_mapped(lambda_vec, c, c.dim_nl, c.dim_nv, P_LL, W_lO), vmat_mapped(mu_vec, c, c.dim_nm, c.dim_nv, P_LL, W_mO));
+    r.lR = vsub(vmat_mapped(lambda_vec, c, c.dim_nl, c.dim_nv, P_LR, W_lO), vmat_mapped(mu_vec, c, c.dim_nm, c.dim_nv, P_LR, W_mO));
+    r.lO = vsub(vmat_mapped(lambda_vec, c, c.dim_nl, c.dim_nv, P_LO, W_lO), vmat_mapped(mu_vec, c, c.dim_nm, c.dim_nv, P_LO, W_mO));
     return r;
 }
 SV make_cr_tau(const Sc &tau, const Sc &tau_inv, const Sc &tau2, const Sc &tau3, const Sc &beta) {
