@@ -302,8 +302,13 @@ def run_ours(args):
         t0 = time.perf_counter()
         overd = OC.u64_verify_batch(gens, c_s, p_s, LABEL, cores)
         dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        OC.bench_point_mul(gens[:64], (R.N - 12345).to_bytes(32, "big"), 2000)
+        ec_us = (time.perf_counter() - t1) / 2000 * 1e6
         cpu = {"value": round(sample / dt, 1), "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {sample} proofs of the same batch, {dt:.2f} s wall on {cores} threads",
+               "ec_mult_us_single_thread": round(ec_us, 1),
+               "ec_mult_note": "one variable-base scalar multiplication in the C port on this host; k256 on an M3 Pro core: 25.7 us (BASELINE.md)",
                "parity_with_gpu_on_sample": bool((np.array(overd, dtype=np.int32) == got[:sample]).all())}
     value = world * n * args.steps / (v_ms * 1e-3)
     line = {
@@ -369,6 +374,9 @@ def run_reference(args):
         ok &= all(s == 1 for s in v)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
+    t1 = time.perf_counter()
+    OC.bench_point_mul(gens[:64], (R.N - 12345).to_bytes(32, "big"), 2000)
+    ec_us = (time.perf_counter() - t1) / 2000 * 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
@@ -377,7 +385,7 @@ def run_reference(args):
                    "reference_arm": "the reference algorithm (one scalar multiplication per MSM term, src/util.rs:46-60) on a bounded "
                                     f"sample of {sample} proofs per step drawn the same way as the batch", "threads": cores},
         "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} proofs per step x {args.steps} steps, {dt:.2f} s wall"},
+                         "sample": f"{sample} proofs per step x {args.steps} steps, {dt:.2f} s wall", "ec_mult_us_single_thread": round(ec_us, 1)},
         "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "all_true": ok,
         "note": "C restatement of the reference algorithm (not k256); published k256 figures: 3.808 ms/verify, 14.361 ms/prove on one M3 Pro core",
