@@ -85,6 +85,7 @@ static inline WS sub_ws(const bppp_ctx *c, const SubPlan &sp, int k) {
 }
 void launch_msm_fixed(bppp_ctx *c, cudaStream_t st, WS w, int sc_off, const TermMap &tm, int nterms, int out_off);
 void launch_batch_inv(bppp_ctx *c, cudaStream_t st, WS w, int in_off, int out_off);
+void launch_batch_inv_list(bppp_ctx *c, cudaStream_t st, WS w, const InvList &L);
 // engine_var.cu: joint variable-base ladders (one thread per proof)
 void launch_v_var5(bppp_ctx *c, cudaStream_t st, WS w);
 void launch_v_var2(bppp_ctx *c, cudaStream_t st, WS w, int j);

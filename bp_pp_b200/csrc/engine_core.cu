@@ -65,6 +65,11 @@ __global__ void __launch_bounds__(128) k_batch_inv(WS w, int in_off, int out_off
     if (t < nthreads) batch_inv_strided(w, in_off, out_off, t, nthreads, w.n);
 }
 
+__global__ void __launch_bounds__(128) k_batch_inv_list(WS w, InvList L, size_t nthreads) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nthreads) batch_inv_list_strided(w, L, t, nthreads);
+}
+
 // ---- commit ----
 __global__ void __launch_bounds__(64) k_c_load(WS w, const uint64_t *xs, const uint8_t *blinds) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -155,6 +160,13 @@ int join_streams(bppp_ctx *c, cudaStream_t caller, const SubPlan &sp) {
 void launch_msm_fixed(bppp_ctx *c, cudaStream_t st, WS w, int sc_off, const TermMap &tm, int nterms, int out_off) {
     size_t threads = w.n * MSM_LANES;
     LAUNCH(c, k_msm_fixed<MSM_LANES>, nblocks(threads, BPPP_MSM_BLOCK), BPPP_MSM_BLOCK, c->T, w, sc_off, tm, nterms, out_off);
+}
+void launch_batch_inv_list(bppp_ctx *c, cudaStream_t st, WS w, const InvList &L) {
+    size_t items = (size_t)L.n * w.n, per = 8;
+    size_t nthreads = (items + per - 1) / per;
+    size_t min_threads = (size_t)c->sm_count * 128;
+    if (nthreads < min_threads) nthreads = items < min_threads ? items : min_threads;
+    LAUNCH(c, k_batch_inv_list, nblocks(nthreads, 128), 128, w, L, nthreads);
 }
 void launch_batch_inv(bppp_ctx *c, cudaStream_t st, WS w, int in_off, int out_off) {
     // one inversion per thread, >= 8 items per thread when the batch is large enough to still fill the GPU

@@ -57,9 +57,10 @@ static int prove_part(bppp_ctx *c, cudaStream_t st, WS w, const uint64_t *d_x, c
         launch_msm_fixed(c, st, w, PL::FS + 8 * u64p_stage1_scalar_base(k), tm, nterms, PL::PTS + PT_W * u64p_stage1_point(k));
     }
     LAUNCH(c, k_p_vprime, g64, 64, w);
-    for (int k = 0; k < 5; k++) {
-        int p = u64p_stage1_norm_point(k);
-        launch_batch_inv(c, st, w, PL::PTS + PT_W * p + 2 * FE_W, PL::ZINV + FE_W * p);
+    {   // the five first-stage normalisations in one launch
+        InvList L; L.n = 5;
+        for (int k = 0; k < 5; k++) { int p = u64p_stage1_norm_point(k); L.in[k] = PL::PTS + PT_W * p + 2 * FE_W; L.out[k] = PL::ZINV + FE_W * p; }
+        launch_batch_inv_list(c, st, w, L);
     }
     LAUNCH(c, k_p_phase2, g64, 64, w, d_rng);
     u64p_termmap_cs(tm.gen);
@@ -75,9 +76,13 @@ static int prove_part(bppp_ctx *c, cudaStream_t st, WS w, const uint64_t *d_x, c
         launch_msm_fixed(c, st, w, PL::XS, all, NUM_GENS, PL::PTS + PT_W * (PP_X + j));
         u64p_termmap_r(tm.gen, j);
         launch_msm_fixed(c, st, w, PL::RS, tm, 25, PL::PTS + PT_W * (PP_R + j));
-        launch_batch_inv(c, st, w, PL::COM + 2 * FE_W, PL::ZINV + FE_W * PP_COM);
-        launch_batch_inv(c, st, w, PL::PTS + PT_W * (PP_X + j) + 2 * FE_W, PL::ZINV + FE_W * (PP_X + j));
-        launch_batch_inv(c, st, w, PL::PTS + PT_W * (PP_R + j) + 2 * FE_W, PL::ZINV + FE_W * (PP_R + j));
+        {   // com_j, X_j, R_j normalised together for the transcript
+            InvList L; L.n = 3;
+            L.in[0] = PL::COM + 2 * FE_W; L.out[0] = PL::ZINV + FE_W * PP_COM;
+            L.in[1] = PL::PTS + PT_W * (PP_X + j) + 2 * FE_W; L.out[1] = PL::ZINV + FE_W * (PP_X + j);
+            L.in[2] = PL::PTS + PT_W * (PP_R + j) + 2 * FE_W; L.out[2] = PL::ZINV + FE_W * (PP_R + j);
+            launch_batch_inv_list(c, st, w, L);
+        }
         LAUNCH(c, k_p_round, g64, 64, w, j);
         if (j < 3) launch_p_var2(c, st, w, j);
     }

@@ -298,6 +298,32 @@ BPPP_HD void batch_inv_strided(const WS &w, int in_off, int out_off, size_t t, s
         else { ws_st_fe(w, idx, out_off, fe_mul(rinv, pre)); rinv = fe_mul(rinv, z); }
     }
 }
+// The same over a short list of (input, output) field offsets per proof: flat item index = f * n + proof, so consecutive
+// threads still touch consecutive proofs.  One launch and one inversion chain serve several independent normalisations
+// (the prover needs five after its first stage and three per WNLA round); each thread also gets more items per inversion.
+struct InvList { int n; int in[8]; int out[8]; };
+BPPP_HD void batch_inv_list_strided(const WS &w, const InvList &L, size_t t, size_t T) {
+    const size_t total = (size_t)L.n * w.n;
+    Fe run = fe_one();
+#pragma unroll 1
+    for (size_t idx = t; idx < total; idx += T) {
+        size_t f = idx / w.n, i = idx - f * w.n;
+        Fe z = ws_ld_fe(w, i, L.in[f]);
+        ws_st_fe(w, i, L.out[f], run);
+        if (!fe_is_zero(z)) run = fe_mul(run, z);
+    }
+    Fe rinv = fe_inv(run);
+    size_t cnt = total > t ? (total - t + T - 1) / T : 0;
+#pragma unroll 1
+    for (size_t k = cnt; k-- > 0;) {
+        size_t idx = t + k * T;
+        size_t f = idx / w.n, i = idx - f * w.n;
+        Fe z = ws_ld_fe(w, i, L.in[f]);
+        Fe pre = ws_ld_fe(w, i, L.out[f]);
+        if (fe_is_zero(z)) { Fe zero = fe_zero(); ws_st_fe(w, i, L.out[f], zero); }
+        else { ws_st_fe(w, i, L.out[f], fe_mul(rinv, pre)); rinv = fe_mul(rinv, z); }
+    }
+}
 // The same over `nfields` Fe fields per proof (field f: input at in_off + f * stride, output at out_off + f * stride):
 // flat item index = f * n + proof, so consecutive threads still touch consecutive proofs.
 BPPP_HD void batch_inv_multi_strided(const WS &w, int in_off, int out_off, int stride, int nfields, size_t t, size_t T) {
