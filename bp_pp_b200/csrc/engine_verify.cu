@@ -6,12 +6,12 @@ using namespace bppp;
 
 static int fail(int code, const std::string &msg) { return engine_fail(code, msg); }
 
-// phase 0a: one thread per (proof, point); 16 point slots per proof so that a proof's threads share a half-warp.
+// phase 0a: one thread per (point, proof), point-major.
 // flags[i]: bits 0..13 identity mask, bit 31 = a point failed to decode (merged with atomicOr)
 __global__ void __launch_bounds__(128) k_v_decode(WS w, const uint8_t *commits, const uint8_t *proofs, int fmt, uint32_t *flags) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t i = t >> 4; int k = (int)(t & 15);
-    if (i >= w.n || k >= VP_COUNT) return;
+    int k = (int)(t / w.n); size_t i = t - (size_t)k * w.n;       // point-major: coalesced stores of the decoded words
+    if (k >= VP_COUNT) return;
     size_t csz = fmt == FMT_COMPRESSED ? 33 : 64, psz = fmt == FMT_COMPRESSED ? U64_PROOF_BYTES_COMPRESSED : U64_PROOF_BYTES_AFFINE;
     uint32_t bit; bool bad;
     u64v_decode_point_one(w, i, k, commits + csz * i, proofs + psz * i, fmt, &bit, &bad);
@@ -27,9 +27,11 @@ __global__ void __launch_bounds__(64) k_v_load_finish(WS w, const uint8_t *proof
 }
 // ladder tables: build (one thread per (proof, point)), then batch-invert every Z and normalise in place
 __global__ void __launch_bounds__(64) k_v_tables_build(WS w) {
+    // point-major thread order: a warp handles one table point of 32 consecutive proofs, so its word-major loads and
+    // stores are contiguous (proof-major order put 16 different points, i.e. 16 different rows, into every access)
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t i = t >> 4; int p = (int)(t & 15);
-    if (i < w.n && p < VL::TAB_POINTS) u64v_table_build_one(w, i, p);
+    int p = (int)(t / w.n); size_t i = t - (size_t)p * w.n;
+    if (p < VL::TAB_POINTS) u64v_table_build_one(w, i, p);
 }
 __global__ void __launch_bounds__(128) k_v_tables_normalize(WS w, size_t nthreads) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -62,12 +64,12 @@ static int verify_part(bppp_ctx *c, cudaStream_t st, WS w, const uint8_t *d_comm
     // decode flags live in the workspace's IDMASK row until k_v_load_finish rewrites it
     uint32_t *flags = w.p + (size_t)VL::IDMASK * w.n;
     CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n, st));
-    LAUNCH(c, k_v_decode, nblocks(n * 16, 128), 128, w, d_commits, d_proofs, fmt, flags);
+    LAUNCH(c, k_v_decode, nblocks(n * VP_COUNT, 128), 128, w, d_commits, d_proofs, fmt, flags);
     LAUNCH(c, k_v_load_finish, g64, 64, w, d_proofs, fmt, flags);
     launch_batch_inv(c, st, w, VL::VP + 2 * FE_W, VL::ZINV);
     LAUNCH(c, k_v_phase1, g64, 64, w, init);
     {   // affine 1P..8P tables of the 13 per-proof points: one batch inversion serves all 104 entries of every proof
-        LAUNCH(c, k_v_tables_build, nblocks(n * 16, 64), 64, w);
+        LAUNCH(c, k_v_tables_build, nblocks(n * VL::TAB_POINTS, 64), 64, w);
         size_t items = n * VL::TAB_ENTRIES, nthreads = (items + 63) / 64;
         LAUNCH(c, k_v_tables_normalize, nblocks(nthreads, 128), 128, w, nthreads);
     }
