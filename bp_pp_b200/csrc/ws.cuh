@@ -149,35 +149,39 @@ BPPP_HD uint32_t window_of_words(const WindowWords &ww, int win, int W) {
 // Software pipeline, two stages deep: while the mixed addition of item k runs, the 64-byte table entry of item k+1 is
 // in flight from HBM and so are the scalar words of item k+2 (the window -> address -> entry chain is two dependent loads;
 // ncu showed the first one exposed as long-scoreboard stalls).
+// (term, window) of an item index, advanced by `step` items without dividing (step <= nwin)
+struct ItemPos { int t, win; };
+BPPP_HD ItemPos item_pos(int it, int nwin) { ItemPos p; p.t = it / nwin; p.win = it - p.t * nwin; return p; }
+BPPP_HD void item_advance(ItemPos &p, int step, int nwin) { p.win += step; if (p.win >= nwin) { p.win -= nwin; p.t++; } }
+
 BPPP_HD Pt msm_fixed_lane(const FixedTable &T, const WS &w, size_t i, int sc_off, const int *term_gen, int nterms, int lane, int nlanes) {
     PtX acc = ptx_identity();             // XYZZ accumulator: 8 M + 2 S per table point (ec.cuh)
     const int items = nterms * T.nwin;
+    const bool small_step = nlanes <= T.nwin;
     TableEntryRaw cur, nxt;
     uint32_t dcur = 0, dnxt = 0;
     WindowWords ww_next; ww_next.lo = 0; ww_next.hi = 0;
     int it = lane;
+    ItemPos p1 = item_pos(it, T.nwin);                     // position of the item whose entry is fetched next
     if (it < items) {
-        int t = it / T.nwin, win = it - t * T.nwin;
-        dcur = window_of_words(scalar_window_words(w, i, sc_off + 8 * t, win, T.W), win, T.W);
-        if (dcur) cur = table_fetch(T, term_gen[t], win, dcur);
+        dcur = window_of_words(scalar_window_words(w, i, sc_off + 8 * p1.t, p1.win, T.W), p1.win, T.W);
+        if (dcur) cur = table_fetch(T, term_gen[p1.t], p1.win, dcur);
     }
-    if (it + nlanes < items) {
-        int t = (it + nlanes) / T.nwin, win = (it + nlanes) - t * T.nwin;
-        ww_next = scalar_window_words(w, i, sc_off + 8 * t, win, T.W);
-    }
+    if (small_step) item_advance(p1, nlanes, T.nwin); else p1 = item_pos(it + nlanes, T.nwin);
+    ItemPos p2 = p1;                                       // position of the item whose scalar words are loaded next
+    if (it + nlanes < items) ww_next = scalar_window_words(w, i, sc_off + 8 * p1.t, p1.win, T.W);
+    if (small_step) item_advance(p2, nlanes, T.nwin); else p2 = item_pos(it + 2 * nlanes, T.nwin);
 #pragma unroll 1
     for (; it < items; it += nlanes) {
         const int itn = it + nlanes, itnn = it + 2 * nlanes;
         dnxt = 0;
         if (itn < items) {
-            int t = itn / T.nwin, win = itn - t * T.nwin;
-            dnxt = window_of_words(ww_next, win, T.W);
-            if (dnxt) nxt = table_fetch(T, term_gen[t], win, dnxt);
+            dnxt = window_of_words(ww_next, p1.win, T.W);
+            if (dnxt) nxt = table_fetch(T, term_gen[p1.t], p1.win, dnxt);
         }
-        if (itnn < items) {
-            int t = itnn / T.nwin, win = itnn - t * T.nwin;
-            ww_next = scalar_window_words(w, i, sc_off + 8 * t, win, T.W);
-        }
+        if (itnn < items) ww_next = scalar_window_words(w, i, sc_off + 8 * p2.t, p2.win, T.W);
+        p1 = p2;
+        if (small_step) item_advance(p2, nlanes, T.nwin); else p2 = item_pos(itnn + nlanes, T.nwin);
         if (dcur != 0) {
             PtA q;
             if (table_decode(q, cur)) acc = ptx_add_mixed_hot(acc, q);
@@ -186,7 +190,6 @@ BPPP_HD Pt msm_fixed_lane(const FixedTable &T, const WS &w, size_t i, int sc_off
     }
     return ptx_to_pt(acc);
 }
-
 
 // ---- signed windows ----
 // Three workspace words starting at the word that holds the first bit of window win - 1 (of window 0 for win = 0): they
@@ -234,33 +237,32 @@ BPPP_HD SignedDigit signed_window_digit(const FixedTable &T, const WS &w, size_t
 BPPP_HD Pt msm_fixed_lane_signed(const FixedTable &T, const WS &w, size_t i, int sc_off, const int *term_gen, int nterms, int lane, int nlanes) {
     PtX acc = ptx_identity();
     const int items = nterms * T.nwin;
+    const bool small_step = nlanes <= T.nwin;
     TableEntryRaw cur, nxt;
     SignedDigit dcur, dnxt;
     dcur.mag = 0; dcur.neg = false;
     WindowWords3 ww_next; ww_next.a = ww_next.b = ww_next.c = 0;
     int it = lane;
+    ItemPos p1 = item_pos(it, T.nwin);
     if (it < items) {
-        int t = it / T.nwin, win = it - t * T.nwin;
-        dcur = signed_window_digit(T, w, i, sc_off + 8 * t, win, scalar_window_words3(w, i, sc_off + 8 * t, win, T.W));
-        if (dcur.mag) cur = table_fetch(T, term_gen[t], win, dcur.mag);
+        dcur = signed_window_digit(T, w, i, sc_off + 8 * p1.t, p1.win, scalar_window_words3(w, i, sc_off + 8 * p1.t, p1.win, T.W));
+        if (dcur.mag) cur = table_fetch(T, term_gen[p1.t], p1.win, dcur.mag);
     }
-    if (it + nlanes < items) {
-        int t = (it + nlanes) / T.nwin, win = (it + nlanes) - t * T.nwin;
-        ww_next = scalar_window_words3(w, i, sc_off + 8 * t, win, T.W);
-    }
+    if (small_step) item_advance(p1, nlanes, T.nwin); else p1 = item_pos(it + nlanes, T.nwin);
+    ItemPos p2 = p1;
+    if (it + nlanes < items) ww_next = scalar_window_words3(w, i, sc_off + 8 * p1.t, p1.win, T.W);
+    if (small_step) item_advance(p2, nlanes, T.nwin); else p2 = item_pos(it + 2 * nlanes, T.nwin);
 #pragma unroll 1
     for (; it < items; it += nlanes) {
         const int itn = it + nlanes, itnn = it + 2 * nlanes;
         dnxt.mag = 0; dnxt.neg = false;
         if (itn < items) {
-            int t = itn / T.nwin, win = itn - t * T.nwin;
-            dnxt = signed_window_digit(T, w, i, sc_off + 8 * t, win, ww_next);
-            if (dnxt.mag) nxt = table_fetch(T, term_gen[t], win, dnxt.mag);
+            dnxt = signed_window_digit(T, w, i, sc_off + 8 * p1.t, p1.win, ww_next);
+            if (dnxt.mag) nxt = table_fetch(T, term_gen[p1.t], p1.win, dnxt.mag);
         }
-        if (itnn < items) {
-            int t = itnn / T.nwin, win = itnn - t * T.nwin;
-            ww_next = scalar_window_words3(w, i, sc_off + 8 * t, win, T.W);
-        }
+        if (itnn < items) ww_next = scalar_window_words3(w, i, sc_off + 8 * p2.t, p2.win, T.W);
+        p1 = p2;
+        if (small_step) item_advance(p2, nlanes, T.nwin); else p2 = item_pos(itnn + nlanes, T.nwin);
         if (dcur.mag != 0) {
             PtA q;
             if (table_decode(q, cur)) {
