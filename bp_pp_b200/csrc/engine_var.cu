@@ -25,8 +25,25 @@ __global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_p_var2(W
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < w.n) u64p_var2_one(w, i, j);
 }
+__global__ void __launch_bounds__(64) k_p_tables_build(WS w, int j) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int p = (int)(t / w.n); size_t i = t - (size_t)p * w.n;
+    if (p < 2) u64p_table_build_one(w, i, j, p);
+}
+__global__ void __launch_bounds__(128) k_p_tables_normalize(WS w, size_t nthreads) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nthreads) tables_normalize_strided(w, ptab_region(), t, nthreads);
+}
 namespace bppp {
 void launch_v_var5(bppp_ctx *c, cudaStream_t st, WS w) { LAUNCH(c, k_v_var5, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w); }
 void launch_v_var2(bppp_ctx *c, cudaStream_t st, WS w, int j) { LAUNCH(c, k_v_var2, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j); }
-void launch_p_var2(bppp_ctx *c, cudaStream_t st, WS w, int j) { LAUNCH(c, k_p_var2, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j); }
+void launch_p_var2(bppp_ctx *c, cudaStream_t st, WS w, int j) {
+    // tables of X_j, R_j (point-major), one cross-proof inversion for their 16 entries, then the ladder
+    LAUNCH(c, k_p_tables_build, nblocks(w.n * 2, 64), 64, w, j);
+    size_t items = w.n * PL::TAB_ENTRIES, nthreads = (items + 15) / 16;
+    size_t min_threads = (size_t)c->sm_count * 128;
+    if (nthreads < min_threads) nthreads = items < min_threads ? items : min_threads;
+    LAUNCH(c, k_p_tables_normalize, nblocks(nthreads, 128), 128, w, nthreads);
+    LAUNCH(c, k_p_var2, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
+}
 }  // namespace bppp

@@ -52,8 +52,13 @@ struct PL {
     static constexpr int FS = VS + 16;                        // fixed-base scalars; stage 1 uses 83 (FS..XS)
     static constexpr int XS = FS + 8 * NUM_GENS;              // X_j scalars (49), directly after FS
     static constexpr int RS = XS + 8 * NUM_GENS;              // R_j scalars (25)
-    static constexpr int WORDS = RS + 8 * 25;
+    // ladder tables of the round's two re-commit points X_j, R_j (u64_verify.cuh:TabRegion)
+    static constexpr int TAB = (RS + 8 * 25 + 3) & ~3;
+    static constexpr int TAB_ENTRIES = 16;
+    static constexpr int TABA = TAB + TAB_ENTRIES * TAB_STRIDE_W;
+    static constexpr int WORDS = TABA + TAB_ENTRIES * TABA_STRIDE_W;
 };
+BPPP_HD TabRegion ptab_region() { TabRegion r; r.tab = PL::TAB; r.taba = PL::TABA; r.entries = PL::TAB_ENTRIES; return r; }
 
 BPPP_HD void pset_status(const WS &w, size_t i, int32_t st) {
     int32_t cur = (int32_t)ws_ld(w, i, PL::STATUS);
@@ -479,13 +484,22 @@ BPPP_HD void u64p_round_one(const WS &w, size_t i, int j) {
 }
 
 // next commitment C' = C + y X_j + (y^2 - 1) R_j  (== wnla'.commit(l', n'), wnla.rs:186)
+// 1P..8P of X_j (t = 0) or R_j (t = 1), projective, into the prover's table region
+BPPP_HD void u64p_table_build_one(const WS &w, size_t i, int j, int t) {
+    bool id;
+    const int slot = (t ? PP_R : PP_X) + j;
+    PtA a = ws_affine(w, i, PL::PTS + PT_W * slot, PL::ZINV + FE_W * slot, id);
+    PtTable8 tab;
+    pt_table8_build(tab, pt_from_affine(a, id));
+#pragma unroll 1
+    for (int e = 0; e < 8; e++) ws_st_pt(w, i, PL::TAB + (t * 8 + e) * TAB_STRIDE_W, tab.m[e]);
+}
+// com_{j+1} = com_j + y X_j + (y^2 - 1) R_j from the normalised tables (same ladder as the verifier's rounds)
 BPPP_HD void u64p_var2_one(const WS &w, size_t i, int j) {
-    bool ident[2];
-    PtA pts[2];
-    pts[0] = ws_affine(w, i, PL::PTS + PT_W * (PP_X + j), PL::ZINV + FE_W * (PP_X + j), ident[0]);
-    pts[1] = ws_affine(w, i, PL::PTS + PT_W * (PP_R + j), PL::ZINV + FE_W * (PP_R + j), ident[1]);
+    (void)j;
+    const int tids[2] = {0, 1};
     Sc ks[2] = {ws_ld_sc(w, i, PL::VS), ws_ld_sc(w, i, PL::VS + 8)};
-    Pt com = straus_var<2>(pts, ident, ks, ws_ld_pt(w, i, PL::COM));
+    Pt com = straus_tables<2>(w, ptab_region(), i, tids, ks, ws_ld_pt(w, i, PL::COM));
     ws_st_pt(w, i, PL::COM, com);
 }
 

@@ -47,8 +47,14 @@ struct VL {
     static constexpr int TABA_STRIDE = 3 * FE_W;
     static constexpr int WORDS = TABA + TAB_ENTRIES * TABA_STRIDE;
 };
-BPPP_HD uint32_t *vtab_entry(const WS &w, size_t i, int entry) {
-    return w.p + (size_t)VL::TABA * w.n + ((size_t)i * VL::TAB_ENTRIES + entry) * VL::TABA_STRIDE;
+// A ladder-table region of a per-proof record: `entries` table entries, built word-major at word offset `tab`
+// (TAB_STRIDE words each), finished array-of-structures at word offset `taba` (TABA_STRIDE words each).  The verifier's
+// region holds 13 points, the prover's (u64_prove.cuh) the two points of a WNLA round.
+struct TabRegion { int tab, taba, entries; };
+static constexpr int TAB_STRIDE_W = 4 * FE_W, TABA_STRIDE_W = 3 * FE_W;
+BPPP_HD TabRegion vtab_region() { TabRegion r; r.tab = VL::TAB; r.taba = VL::TABA; r.entries = VL::TAB_ENTRIES; return r; }
+BPPP_HD uint32_t *tab_entry(const WS &w, const TabRegion &R, size_t i, int entry) {
+    return w.p + (size_t)R.taba * w.n + ((size_t)i * R.entries + entry) * TABA_STRIDE_W;
 }
 // 8 words <-> Fe through 16-byte accesses (the pointers are 16-byte aligned: TABA and the per-proof record size are
 // multiples of 4 words, TABA_STRIDE of 8)
@@ -257,14 +263,14 @@ BPPP_HD void u64v_table_build_one(const WS &w, size_t i, int t) {
 }
 // Phases T2+T3 fused: Montgomery batch inversion of every table entry's Z over this thread's strided share of the
 // (entry, proof) items, writing the affine entries (array-of-structures region) on the way back
-BPPP_HD void u64v_tables_normalize_strided(const WS &w, size_t t, size_t T) {
-    const size_t total = (size_t)VL::TAB_ENTRIES * w.n;
+BPPP_HD void tables_normalize_strided(const WS &w, const TabRegion &R, size_t t, size_t T) {
+    const size_t total = (size_t)R.entries * w.n;
     const Fe beta = fe_beta();
     Fe run = fe_one();
 #pragma unroll 1
     for (size_t idx = t; idx < total; idx += T) {
         size_t e = idx / w.n, i = idx - e * w.n;
-        const int off = VL::TAB + (int)e * VL::TAB_STRIDE;
+        const int off = R.tab + (int)e * TAB_STRIDE_W;
         Fe z = ws_ld_fe(w, i, off + 2 * FE_W);
         ws_st_fe(w, i, off + PT_W, run);                  // prefix product before this item
         if (!fe_normalizes_to_zero(z)) run = fe_mul(run, z);
@@ -275,7 +281,7 @@ BPPP_HD void u64v_tables_normalize_strided(const WS &w, size_t t, size_t T) {
     for (size_t k = cnt; k-- > 0;) {
         size_t idx = t + k * T;
         size_t e = idx / w.n, i = idx - e * w.n;
-        const int off = VL::TAB + (int)e * VL::TAB_STRIDE;
+        const int off = R.tab + (int)e * TAB_STRIDE_W;
         Pt p = ws_ld_pt(w, i, off);
         PtA a;
         if (fe_normalizes_to_zero(p.z)) { a.x = fe_zero(); a.y = fe_zero(); }       // identity -> zero sentinel
@@ -284,14 +290,15 @@ BPPP_HD void u64v_tables_normalize_strided(const WS &w, size_t t, size_t T) {
             rinv = fe_mul(rinv, p.z);
             a = pt_to_affine_with_zinv(p, zi);
         }
-        uint32_t *dst = vtab_entry(w, i, (int)e);
+        uint32_t *dst = tab_entry(w, R, i, (int)e);
         vtab_st_fe(dst, a.x); vtab_st_fe(dst + FE_W, a.y);
         vtab_st_fe(dst + 2 * FE_W, fe_normalize(fe_mul(a.x, beta)));     // x of the endomorphism image (beta x, y)
     }
 }
+BPPP_HD void u64v_tables_normalize_strided(const WS &w, size_t t, size_t T) { tables_normalize_strided(w, vtab_region(), t, T); }
 // acc = sum_k ks[k] * P_{tids[k]} + init from the affine tables
 template <int NP>
-BPPP_HD Pt straus_tables(const WS &w, size_t i, const int *tids, const Sc *ks, const Pt &init) {
+BPPP_HD Pt straus_tables(const WS &w, const TabRegion &R, size_t i, const int *tids, const Sc *ks, const Pt &init) {
     Digits4h dg[2 * NP];
     bool neg[2 * NP];
 #pragma unroll 1
@@ -313,7 +320,7 @@ BPPP_HD Pt straus_tables(const WS &w, size_t i, const int *tids, const Sc *ks, c
             if (neg[h]) sd = -sd;
             if (sd == 0) continue;
             int a = sd < 0 ? -sd : sd;
-            const uint32_t *ent = vtab_entry(w, i, tids[h >> 1] * 8 + (a - 1));
+            const uint32_t *ent = tab_entry(w, R, i, tids[h >> 1] * 8 + (a - 1));
             PtA q;
             q.x = vtab_ld_fe(ent + ((h & 1) ? 2 * FE_W : 0));                           // odd halves use (beta x, y)
             q.y = vtab_ld_fe(ent + FE_W);
@@ -331,7 +338,7 @@ BPPP_HD void u64v_var5_one(const WS &w, size_t i) {
     Sc ks[5];
 #pragma unroll 1
     for (int k = 0; k < 5; k++) ks[k] = ws_ld_sc(w, i, VL::VS + 8 * k);
-    ws_st_pt(w, i, VL::COM, straus_tables<5>(w, i, tids, ks, ws_ld_pt(w, i, VL::ACC)));
+    ws_st_pt(w, i, VL::COM, straus_tables<5>(w, vtab_region(), i, tids, ks, ws_ld_pt(w, i, VL::ACC)));
 }
 
 // WNLA round j = 0..3 (wnla.rs:84-102): transcript -> y_j, fold c, scalars for com' = com + y X + (y^2-1) R
@@ -364,7 +371,7 @@ BPPP_HD void u64v_round_one(const WS &w, size_t i, int j) {
 BPPP_HD void u64v_var2_one(const WS &w, size_t i, int j) {
     const int tids[2] = {vtab_of_slot(VP_X + (3 - j)), vtab_of_slot(VP_R + (3 - j))};
     Sc ks[2] = {ws_ld_sc(w, i, VL::VS), ws_ld_sc(w, i, VL::VS + 8)};
-    ws_st_pt(w, i, VL::COM, straus_tables<2>(w, i, tids, ks, ws_ld_pt(w, i, VL::COM)));
+    ws_st_pt(w, i, VL::COM, straus_tables<2>(w, vtab_region(), i, tids, ks, ws_ld_pt(w, i, VL::COM)));
 }
 
 // Base case (wnla.rs:80-82): scalars of commit(l, n) over the ORIGINAL generators.  After 4 folds

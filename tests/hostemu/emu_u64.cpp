@@ -147,7 +147,11 @@ extern "C" int emu_u64_prove_batch(void *ctx, size_t n, const uint64_t *xs, cons
         emu_batch_inv(w, n, PL::PTS + PT_W * (PP_X + j) + 2 * FE_W, PL::ZINV + FE_W * (PP_X + j));
         emu_batch_inv(w, n, PL::PTS + PT_W * (PP_R + j) + 2 * FE_W, PL::ZINV + FE_W * (PP_R + j));
         for (size_t i = 0; i < n; i++) u64p_round_one(w, i, j);
-        if (j < 3) for (size_t i = 0; i < n; i++) u64p_var2_one(w, i, j);
+        if (j < 3) {
+            for (int t = 0; t < 2; t++) for (size_t i = 0; i < n; i++) u64p_table_build_one(w, i, j, t);
+            { size_t T = (n * PL::TAB_ENTRIES + 4) / 5; for (size_t t = 0; t < T; t++) tables_normalize_strided(w, ptab_region(), t, T); }
+            for (size_t i = 0; i < n; i++) u64p_var2_one(w, i, j);
+        }
     }
     for (size_t i = 0; i < n; i++) { u64p_output_one(w, i, proofs + (size_t)U64_PROOF_BYTES_COMPRESSED * i); status[i] = (int32_t)ws_ld(w, i, PL::STATUS); }
     return 0;
