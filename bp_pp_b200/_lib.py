@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("BPPP_LIB") or os.path.join(_HERE, "libbppp.so")   # BPPP_LIB: kernel-variant experiments
 
 EXPORTS = [
-    "bppp_ctx_create", "bppp_ctx_destroy", "bppp_last_error", "bppp_ctx_info", "bppp_u64_commit_batch",
+    "bppp_ctx_create", "bppp_ctx_create_shared", "bppp_ctx_destroy", "bppp_last_error", "bppp_ctx_info", "bppp_u64_commit_batch",
     "bppp_u64_verify_batch", "bppp_u64_verify_batch_dev", "bppp_u64_prove_batch", "bppp_u64_prove_batch_dev",
     "bppp_launch_count", "bppp_microbench", "bppp_ctx_profile_begin", "bppp_ctx_profile_end",
     "bppp_msm", "bppp_points_upload", "bppp_scalars_upload", "bppp_device_free", "bppp_msm_uploaded", "bppp_points_sum", "bppp_points_generate", "bppp_points_convert",

@@ -32,13 +32,23 @@ def _in(b):
 class Context:
     """Owns the device-side state of one U64RangeProofProtocol on one GPU (tables + workspace)."""
 
-    def __init__(self, gens64: bytes, device: int = 0, window_bits: int = 0, max_batch: int = 65536):
+    def __init__(self, gens64: bytes, device: int = 0, window_bits: int = 0, max_batch: int = 65536, _shared_from=None):
+        self._h = C.c_void_p()
+        self._parent = _shared_from          # keeps the owner of the tables alive
+        if _shared_from is not None:
+            check(lib().bppp_ctx_create_shared(C.byref(self._h), _shared_from._h, C.c_size_t(max_batch)), "bppp_ctx_create_shared")
+            self.device = _shared_from.device
+            return
         if len(gens64) != 64 * 49:
             raise ValueError("gens64 must be 49 x 64 bytes: g || g_vec[16] || h_vec[32]")
-        self._h = C.c_void_p()
         check(lib().bppp_ctx_create(C.byref(self._h), C.c_int(device), _in(gens64), C.c_int(window_bits),
                                     C.c_size_t(max_batch)), "bppp_ctx_create")
         self.device = device
+
+    def shared(self, max_batch: int = 0) -> "Context":
+        """Another context on the same GPU sharing this one's window tables, with its own workspace and streams: batches
+        submitted through different contexts run side by side."""
+        return Context(b"", self.device, 0, max_batch, _shared_from=self)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -27,9 +28,11 @@ struct TermMap { int gen[NUM_GENS]; };
 }  // namespace bppp
 
 struct bppp_ctx {
+    std::mutex mu;                  // entry points serialise per context (one workspace, one staging area); use one context per host thread for concurrency
     int device = 0;
     bppp::FixedTable T{};
     uint4 *d_tab = nullptr;
+    bool owns_tab = false;          // false for a context created by bppp_ctx_create_shared
     size_t table_bytes = 0;
     double table_build_ms = 0;
     size_t max_batch = 0;
@@ -38,6 +41,7 @@ struct bppp_ctx {
     uint8_t *d_in_a = nullptr, *d_in_b = nullptr, *d_in_c = nullptr;   // staging for host-buffer entry points
     uint8_t *d_out = nullptr;
     int32_t *d_status = nullptr;
+    int32_t *d_flag = nullptr;      // one word: set by a kernel when an input the call must reject was seen
     cudaStream_t stream = nullptr;
     // a batch slice is cut into up to MAX_SUB sub-batches, each running its kernel sequence on its own stream,
     // so that tail waves and low-parallelism kernels of one sub-batch overlap with work of the others
@@ -47,6 +51,8 @@ struct bppp_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
     uint64_t launches = 0;
     int sm_count = 148;
+    int active_parts = 1;           // sub-batches of the slice in flight (they run concurrently: lane choices look at their sum)
+    int msm_lanes_override = 0, var_lanes_override = 0;   // BPPP_MSM_LANES_RT / BPPP_VAR_LANES_RT (experiments)
     // optional per-launch timing (bppp_ctx_profile_begin/end): CUDA events on the launching stream
     bool profiling = false;
     struct ProfRec { const char *name; cudaEvent_t a, b; };
@@ -71,13 +77,32 @@ static inline unsigned nblocks(size_t n, unsigned bs) { return (unsigned)((n + b
         (ctx)->launches++;                                                                     \
     } while (0)
 
+#if defined(__CUDACC__)
+// sum of the partial points held by the LANES adjacent threads of one proof (butterfly over warp shuffles, complete additions)
+template <int LANES>
+__device__ __forceinline__ Pt lanes_reduce(Pt acc) {
+#pragma unroll 1
+    for (int off = LANES / 2; off >= 1; off >>= 1) {
+        Pt o;
+#pragma unroll
+        for (int k = 0; k < FE_W; k++) {
+            o.x.v[k] = __shfl_xor_sync(0xFFFFFFFFu, acc.x.v[k], off);
+            o.y.v[k] = __shfl_xor_sync(0xFFFFFFFFu, acc.y.v[k], off);
+            o.z.v[k] = __shfl_xor_sync(0xFFFFFFFFu, acc.z.v[k], off);
+        }
+        acc = pt_add(acc, o);
+    }
+    return acc;
+}
+#endif
+
 static inline TermMap identity_map() { TermMap tm; for (int t = 0; t < NUM_GENS; t++) tm.gen[t] = t; return tm; }
 
 // engine_core.cu
 // sub-batch plan for a slice of n proofs: part k covers [lo[k], lo[k+1]) and owns workspace words starting at
 // d_ws + words_per_proof * lo[k] with row stride (lo[k+1] - lo[k])
 struct SubPlan { int parts; size_t lo[bppp_ctx::MAX_SUB + 1]; };
-SubPlan plan_sub(const bppp_ctx *c, size_t n);
+SubPlan plan_sub(bppp_ctx *c, size_t n);     // also records the number of concurrent parts in c->active_parts
 int fork_streams(bppp_ctx *c, cudaStream_t caller, const SubPlan &sp);
 int join_streams(bppp_ctx *c, cudaStream_t caller, const SubPlan &sp);
 static inline WS sub_ws(const bppp_ctx *c, const SubPlan &sp, int k) {

@@ -25,22 +25,6 @@ static thread_local std::string g_last_error;
 namespace bppp { int engine_fail(int code, const std::string &msg) { g_last_error = msg; return code; } }
 static int fail(int code, const std::string &msg) { return engine_fail(code, msg); }
 
-template <int LANES>
-__device__ __forceinline__ Pt lanes_reduce(Pt acc) {
-#pragma unroll 1
-    for (int off = LANES / 2; off >= 1; off >>= 1) {
-        Pt o;
-#pragma unroll
-        for (int k = 0; k < FE_W; k++) {
-            o.x.v[k] = __shfl_xor_sync(0xFFFFFFFFu, acc.x.v[k], off);
-            o.y.v[k] = __shfl_xor_sync(0xFFFFFFFFu, acc.y.v[k], off);
-            o.z.v[k] = __shfl_xor_sync(0xFFFFFFFFu, acc.z.v[k], off);
-        }
-        acc = pt_add(acc, o);
-    }
-    return acc;
-}
-
 // sum_t scalar[t] * G_{gen[t]} for every proof: LANES threads per proof
 template <int LANES>
 #ifndef BPPP_MSM_BLOCK
@@ -71,11 +55,12 @@ __global__ void __launch_bounds__(128) k_batch_inv_list(WS w, InvList L, size_t 
 }
 
 // ---- commit ----
-__global__ void __launch_bounds__(64) k_c_load(WS w, const uint64_t *xs, const uint8_t *blinds) {
+__global__ void __launch_bounds__(64) k_c_load(WS w, const uint64_t *xs, const uint8_t *blinds, int32_t *bad_flag) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w.n) return;
     Sc s; int32_t st = ST_TRUE;
-    if (!sc_from_be32(s, blinds + 32 * i)) { st = ST_BAD_SCALAR; s = sc_zero(); }
+    // a k256::Scalar cannot hold a value >= n: the call fails (BPPP_ERR_ARG) instead of committing with a zero blinding
+    if (!sc_from_be32(s, blinds + 32 * i)) { st = ST_BAD_SCALAR; s = sc_zero(); atomicOr(bad_flag, 1); }
     ws_st_sc(w, i, VL::FS, sc_from_u64(xs[i]));
     ws_st_sc(w, i, VL::FS + 8, s);
     ws_st(w, i, VL::STATUS, (uint32_t)st);
@@ -134,12 +119,13 @@ __global__ void __launch_bounds__(128) k_tab_write(WS tmp, uint4 *dst) {
 static constexpr int MSM_LANES = BPPP_MSM_LANES;
 
 namespace bppp {
-SubPlan plan_sub(const bppp_ctx *c, size_t n) {
+SubPlan plan_sub(bppp_ctx *c, size_t n) {
     SubPlan sp;
     int parts = c->profiling ? 1 : c->nsub;          // per-kernel timing wants kernels back to back on one stream
     const size_t min_part = 2048;                    // below this a sub-batch cannot fill the GPU anyway
     while (parts > 1 && n / parts < min_part) parts--;
     sp.parts = parts;
+    c->active_parts = parts;
     for (int k = 0; k <= parts; k++) sp.lo[k] = n * k / parts;
     return sp;
 }
@@ -157,9 +143,23 @@ int join_streams(bppp_ctx *c, cudaStream_t caller, const SubPlan &sp) {
     }
     return BPPP_OK;
 }
+// lanes per proof: MSM_LANES when the batch alone fills the GPU, more for small (sub-)batches so that a rank holding a
+// 1/8 share of a batch (strong scaling) still has ~14 warps per SM; BPPP_MSM_LANES_RT overrides (experiments)
+int msm_lanes_for(const bppp_ctx *c, size_t n) {
+    if (c->msm_lanes_override) return c->msm_lanes_override;
+    const size_t full = (size_t)c->sm_count * 448;     // threads of one full wave at 7 blocks x 64
+    int lanes = MSM_LANES;
+    n *= (size_t)c->active_parts;
+    while (lanes < 16 && n * lanes * 2 <= full) lanes *= 2;
+    return lanes;
+}
 void launch_msm_fixed(bppp_ctx *c, cudaStream_t st, WS w, int sc_off, const TermMap &tm, int nterms, int out_off) {
-    size_t threads = w.n * MSM_LANES;
-    LAUNCH(c, k_msm_fixed<MSM_LANES>, nblocks(threads, BPPP_MSM_BLOCK), BPPP_MSM_BLOCK, c->T, w, sc_off, tm, nterms, out_off);
+    int lanes = msm_lanes_for(c, w.n);
+    while (lanes > MSM_LANES && nterms * c->T.nwin < 32 * lanes) lanes /= 2;     // short sums: the lane reduction (log2 lanes full additions) must stay small
+    size_t threads = w.n * lanes;
+    if (lanes >= 16) LAUNCH(c, k_msm_fixed<16>, nblocks(threads, BPPP_MSM_BLOCK), BPPP_MSM_BLOCK, c->T, w, sc_off, tm, nterms, out_off);
+    else if (lanes == 8) LAUNCH(c, k_msm_fixed<8>, nblocks(threads, BPPP_MSM_BLOCK), BPPP_MSM_BLOCK, c->T, w, sc_off, tm, nterms, out_off);
+    else LAUNCH(c, k_msm_fixed<MSM_LANES>, nblocks(threads, BPPP_MSM_BLOCK), BPPP_MSM_BLOCK, c->T, w, sc_off, tm, nterms, out_off);
 }
 void launch_batch_inv_list(bppp_ctx *c, cudaStream_t st, WS w, const InvList &L) {
     size_t items = (size_t)L.n * w.n, per = 8;
@@ -208,6 +208,33 @@ static int build_tables(bppp_ctx *c, const PtA *gens, const bool *gen_id) {
     return BPPP_OK;
 }
 
+// streams, events, workspace and staging buffers of a context for `max_batch` proofs per launch sequence
+static int alloc_work(bppp_ctx *c, size_t max_batch) {
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, c->device));
+    c->sm_count = prop.multiProcessorCount;
+    CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (const char *e = getenv("BPPP_NSUB")) { int v = atoi(e); if (v >= 1 && v <= bppp_ctx::MAX_SUB) c->nsub = v; }
+    if (const char *e = getenv("BPPP_MSM_LANES_RT")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16) c->msm_lanes_override = v; }
+    if (const char *e = getenv("BPPP_VAR_LANES_RT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->var_lanes_override = v; }
+    for (int k = 0; k < bppp_ctx::MAX_SUB; k++) {
+        CUDA_OK(cudaStreamCreateWithFlags(&c->sub_stream[k], cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+    }
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    c->max_batch = max_batch;
+    c->ws_words_per_proof = VL::WORDS > PL::WORDS ? VL::WORDS : PL::WORDS;
+    c->ws_words_per_proof = (c->ws_words_per_proof + 3) & ~(size_t)3;      // sub-batch bases stay 16-byte aligned (vtab_entry)
+    CUDA_OK(cudaMalloc(&c->d_ws, c->ws_words_per_proof * max_batch * sizeof(uint32_t)));
+    CUDA_OK(cudaMalloc(&c->d_in_a, (size_t)64 * max_batch));
+    CUDA_OK(cudaMalloc(&c->d_in_b, (size_t)U64_PROOF_BYTES_AFFINE * max_batch));
+    CUDA_OK(cudaMalloc(&c->d_in_c, (size_t)U64_RNG_BYTES * max_batch));
+    CUDA_OK(cudaMalloc(&c->d_out, (size_t)U64_PROOF_BYTES_COMPRESSED * max_batch));
+    CUDA_OK(cudaMalloc(&c->d_status, sizeof(int32_t) * max_batch));
+    CUDA_OK(cudaMalloc(&c->d_flag, sizeof(int32_t)));
+    return BPPP_OK;
+}
+
 extern "C" const char *bppp_last_error(void) { return g_last_error.c_str(); }
 
 extern "C" int bppp_ctx_create(bppp_ctx **out, int device, const uint8_t *gens64, int window_bits, size_t max_batch) {
@@ -234,31 +261,34 @@ extern "C" int bppp_ctx_create(bppp_ctx **out, int device, const uint8_t *gens64
     bppp_ctx *c = new bppp_ctx();
     struct Guard { bppp_ctx *c; ~Guard() { if (c) bppp_ctx_destroy(c); } } guard{c};      // any early return below frees what was allocated
     c->device = device;
-    cudaDeviceProp prop;
-    CUDA_OK(cudaGetDeviceProperties(&prop, device));
-    c->sm_count = prop.multiProcessorCount;
-    CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    if (const char *e = getenv("BPPP_NSUB")) { int v = atoi(e); if (v >= 1 && v <= bppp_ctx::MAX_SUB) c->nsub = v; }
-    for (int k = 0; k < bppp_ctx::MAX_SUB; k++) {
-        CUDA_OK(cudaStreamCreateWithFlags(&c->sub_stream[k], cudaStreamNonBlocking));
-        CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
-    }
-    CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     fixed_table_shape(c->T, window_bits, signed_windows); c->T.ngens = NUM_GENS;
     size_t nent = (size_t)c->T.nwin * c->T.E;
     c->table_bytes = (size_t)NUM_GENS * nent * 64;
     CUDA_OK(cudaMalloc(&c->d_tab, c->table_bytes));
+    c->owns_tab = true;
     c->T.tab = c->d_tab;
-    c->max_batch = max_batch;
-    c->ws_words_per_proof = VL::WORDS > PL::WORDS ? VL::WORDS : PL::WORDS;
-    c->ws_words_per_proof = (c->ws_words_per_proof + 3) & ~(size_t)3;      // sub-batch bases stay 16-byte aligned (vtab_entry)
-    CUDA_OK(cudaMalloc(&c->d_ws, c->ws_words_per_proof * max_batch * sizeof(uint32_t)));
-    CUDA_OK(cudaMalloc(&c->d_in_a, (size_t)64 * max_batch));
-    CUDA_OK(cudaMalloc(&c->d_in_b, (size_t)U64_PROOF_BYTES_AFFINE * max_batch));
-    CUDA_OK(cudaMalloc(&c->d_in_c, (size_t)U64_RNG_BYTES * max_batch));
-    CUDA_OK(cudaMalloc(&c->d_out, (size_t)U64_PROOF_BYTES_COMPRESSED * max_batch));
-    CUDA_OK(cudaMalloc(&c->d_status, sizeof(int32_t) * max_batch));
-    int rc = build_tables(c, gens, gen_id);
+    int rc = alloc_work(c, max_batch);
+    if (rc != BPPP_OK) return rc;
+    rc = build_tables(c, gens, gen_id);
+    if (rc != BPPP_OK) return rc;
+    guard.c = nullptr;
+    *out = c;
+    return BPPP_OK;
+}
+
+// A second context on the same GPU that shares the parent's window tables (read-only after construction) and owns its own
+// workspace, staging buffers and streams: independent batches can then be in flight side by side (one host thread per
+// context), which is what keeps the GPU full when each batch is small.  The parent must outlive it.
+extern "C" int bppp_ctx_create_shared(bppp_ctx **out, const bppp_ctx *parent, size_t max_batch) {
+    if (!out || !parent) return fail(BPPP_ERR_ARG, "null argument");
+    *out = nullptr;
+    CUDA_OK(cudaSetDevice(parent->device));
+    bppp_ctx *c = new bppp_ctx();
+    struct Guard { bppp_ctx *c; ~Guard() { if (c) bppp_ctx_destroy(c); } } guard{c};
+    c->device = parent->device;
+    c->T = parent->T; c->d_tab = parent->d_tab; c->owns_tab = false;
+    c->table_bytes = parent->table_bytes; c->table_build_ms = 0;
+    int rc = alloc_work(c, max_batch ? max_batch : parent->max_batch);
     if (rc != BPPP_OK) return rc;
     guard.c = nullptr;
     *out = c;
@@ -268,8 +298,9 @@ extern "C" int bppp_ctx_create(bppp_ctx **out, int device, const uint8_t *gens64
 extern "C" void bppp_ctx_destroy(bppp_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_tab); cudaFree(c->d_ws); cudaFree(c->d_in_a); cudaFree(c->d_in_b); cudaFree(c->d_in_c);
-    cudaFree(c->d_out); cudaFree(c->d_status);
+    if (c->owns_tab) cudaFree(c->d_tab);
+    cudaFree(c->d_ws); cudaFree(c->d_in_a); cudaFree(c->d_in_b); cudaFree(c->d_in_c);
+    cudaFree(c->d_out); cudaFree(c->d_status); cudaFree(c->d_flag);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (int k = 0; k < bppp_ctx::MAX_SUB; k++) {
         if (c->sub_stream[k]) cudaStreamDestroy(c->sub_stream[k]);
@@ -325,21 +356,26 @@ extern "C" int bppp_ctx_profile_end(bppp_ctx *c, char *names, double *total_ms, 
 extern "C" int bppp_u64_commit_batch(bppp_ctx *c, size_t n, const uint64_t *x, const uint8_t *blinds32, int fmt, uint8_t *out) {
     if (!c || (n && (!x || !blinds32 || !out))) return fail(BPPP_ERR_ARG, "null argument");
     if (fmt != FMT_COMPRESSED && fmt != FMT_AFFINE64) return fail(BPPP_ERR_ARG, "bad point format");
+    std::lock_guard<std::mutex> lock(c->mu);
     CUDA_OK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     size_t osz = fmt == FMT_COMPRESSED ? 33 : 64;
     TermMap tm = identity_map(); tm.gen[0] = GEN_G; tm.gen[1] = GEN_HVEC;
+    int32_t bad = 0;
+    CUDA_OK(cudaMemsetAsync(c->d_flag, 0, sizeof(int32_t), st));
     for (size_t off = 0; off < n; off += c->max_batch) {
         size_t m = n - off < c->max_batch ? n - off : c->max_batch;
         WS w{c->d_ws, m};
         CUDA_OK(cudaMemcpyAsync(c->d_in_a, x + off, 8 * m, cudaMemcpyHostToDevice, st));
         CUDA_OK(cudaMemcpyAsync(c->d_in_b, blinds32 + 32 * off, 32 * m, cudaMemcpyHostToDevice, st));
-        LAUNCH(c, k_c_load, nblocks(m, 64), 64, w, (const uint64_t *)c->d_in_a, c->d_in_b);
+        LAUNCH(c, k_c_load, nblocks(m, 64), 64, w, (const uint64_t *)c->d_in_a, c->d_in_b, c->d_flag);
         launch_msm_fixed(c, st, w, VL::FS, tm, 2, VL::ACC);
         launch_batch_inv(c, st, w, VL::ACC + 2 * FE_W, VL::ZINV);
         LAUNCH(c, k_c_store, nblocks(m, 64), 64, w, c->d_out, fmt);
         CUDA_OK(cudaMemcpyAsync(out + osz * off, c->d_out, osz * m, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaMemcpyAsync(&bad, c->d_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaStreamSynchronize(st));
+        if (bad) return fail(BPPP_ERR_ARG, "commit: a blinding factor is not a canonical scalar (>= n); no commitment is returned for such input");
     }
     CUDA_OK(cudaGetLastError());
     return BPPP_OK;

@@ -108,6 +108,7 @@ static int prove_slice(bppp_ctx *c, cudaStream_t st, size_t n, const uint64_t *d
 extern "C" int bppp_u64_prove_batch_dev(bppp_ctx *c, size_t n, const void *d_x, const void *d_blinds32, const void *d_rng,
                                         const uint8_t *label, size_t label_len, void *d_proofs_out, void *d_status, void *stream) {
     if (!c || (n && (!d_x || !d_blinds32 || !d_rng || !d_proofs_out || !d_status))) return fail(BPPP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lock(c->mu);
     CUDA_OK(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in the CUDA runtime
     Merlin init; merlin_init(init, label, (uint32_t)label_len);
@@ -124,6 +125,7 @@ extern "C" int bppp_u64_prove_batch_dev(bppp_ctx *c, size_t n, const void *d_x, 
 extern "C" int bppp_u64_prove_batch(bppp_ctx *c, size_t n, const uint64_t *x, const uint8_t *blinds32, const uint8_t *rng,
                                     const uint8_t *label, size_t label_len, uint8_t *proofs_out, int32_t *status) {
     if (!c || (n && (!x || !blinds32 || !rng || !proofs_out || !status))) return fail(BPPP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lock(c->mu);
     CUDA_OK(cudaSetDevice(c->device));
     Merlin init; merlin_init(init, label, (uint32_t)label_len);
     for (size_t off = 0; off < n; off += c->max_batch) {

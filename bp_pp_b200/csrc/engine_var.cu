@@ -25,6 +25,37 @@ __global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_p_var2(W
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < w.n) u64p_var2_one(w, i, j);
 }
+// The same ladders with LANES adjacent threads per proof (straus_tables_partial): the GLV halves are shared out, every lane
+// repeats the doublings, the partial sums meet through warp shuffles.  More total work, a shorter dependent chain and
+// LANES times the warps: selected when the (sub-)batch alone leaves most of the GPU idle.
+template <int LANES>
+__global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_v_var5_lanes(WS w) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = t / LANES; const int lane = (int)(t % LANES);
+    const bool live = i < w.n;
+    if (!live) i = w.n - 1;
+    Pt part = lanes_reduce<LANES>(u64v_var5_partial(w, i, lane, LANES));
+    if (live && lane == 0) ws_st_pt(w, i, VL::COM, pt_add(part, ws_ld_pt(w, i, VL::ACC)));
+}
+template <int LANES>
+__global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_v_var2_lanes(WS w, int j) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = t / LANES; const int lane = (int)(t % LANES);
+    const bool live = i < w.n;
+    if (!live) i = w.n - 1;
+    Pt part = lanes_reduce<LANES>(u64v_var2_partial(w, i, j, lane, LANES));
+    if (live && lane == 0) ws_st_pt(w, i, VL::COM, pt_add(part, ws_ld_pt(w, i, VL::COM)));
+}
+template <int LANES>
+__global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_p_var2_lanes(WS w, int j) {
+    (void)j;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = t / LANES; const int lane = (int)(t % LANES);
+    const bool live = i < w.n;
+    if (!live) i = w.n - 1;
+    Pt part = lanes_reduce<LANES>(u64p_var2_partial(w, i, lane, LANES));
+    if (live && lane == 0) ws_st_pt(w, i, PL::COM, pt_add(part, ws_ld_pt(w, i, PL::COM)));
+}
 __global__ void __launch_bounds__(64) k_p_tables_build(WS w, int j) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int p = (int)(t / w.n); size_t i = t - (size_t)p * w.n;
@@ -35,8 +66,27 @@ __global__ void __launch_bounds__(128) k_p_tables_normalize(WS w, size_t nthread
     if (t < nthreads) tables_normalize_strided(w, ptab_region(), t, nthreads);
 }
 namespace bppp {
-void launch_v_var5(bppp_ctx *c, cudaStream_t st, WS w) { LAUNCH(c, k_v_var5, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w); }
-void launch_v_var2(bppp_ctx *c, cudaStream_t st, WS w, int j) { LAUNCH(c, k_v_var2, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j); }
+// lanes per proof for the ladders: 1 while the batch itself gives ~10 warps per SM, then 2, then 4
+static int var_lanes_for(const bppp_ctx *c, size_t n) {
+    if (c->var_lanes_override) return c->var_lanes_override;
+    const size_t full = (size_t)c->sm_count * 448;
+    n *= (size_t)c->active_parts;
+    if (n * 4 >= full * 3) return 1;
+    if (n * 8 >= full * 3) return 2;
+    return 4;
+}
+void launch_v_var5(bppp_ctx *c, cudaStream_t st, WS w) {
+    const int lanes = var_lanes_for(c, w.n);
+    if (lanes == 1) LAUNCH(c, k_v_var5, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w);
+    else if (lanes == 2) LAUNCH(c, k_v_var5_lanes<2>, nblocks(w.n * 2, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w);
+    else LAUNCH(c, k_v_var5_lanes<4>, nblocks(w.n * 4, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w);
+}
+void launch_v_var2(bppp_ctx *c, cudaStream_t st, WS w, int j) {
+    const int lanes = var_lanes_for(c, w.n);
+    if (lanes == 1) LAUNCH(c, k_v_var2, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
+    else if (lanes == 2) LAUNCH(c, k_v_var2_lanes<2>, nblocks(w.n * 2, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
+    else LAUNCH(c, k_v_var2_lanes<4>, nblocks(w.n * 4, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
+}
 void launch_p_var2(bppp_ctx *c, cudaStream_t st, WS w, int j) {
     // tables of X_j, R_j (point-major), one cross-proof inversion for their 16 entries, then the ladder
     LAUNCH(c, k_p_tables_build, nblocks(w.n * 2, 64), 64, w, j);
@@ -44,6 +94,9 @@ void launch_p_var2(bppp_ctx *c, cudaStream_t st, WS w, int j) {
     size_t min_threads = (size_t)c->sm_count * 128;
     if (nthreads < min_threads) nthreads = items < min_threads ? items : min_threads;
     LAUNCH(c, k_p_tables_normalize, nblocks(nthreads, 128), 128, w, nthreads);
-    LAUNCH(c, k_p_var2, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
+    const int lanes = var_lanes_for(c, w.n);
+    if (lanes == 1) LAUNCH(c, k_p_var2, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
+    else if (lanes == 2) LAUNCH(c, k_p_var2_lanes<2>, nblocks(w.n * 2, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
+    else LAUNCH(c, k_p_var2_lanes<4>, nblocks(w.n * 4, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
 }
 }  // namespace bppp

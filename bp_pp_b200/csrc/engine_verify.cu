@@ -106,6 +106,7 @@ extern "C" int bppp_u64_verify_batch_dev(bppp_ctx *c, size_t n, const void *d_co
                                          const uint8_t *label, size_t label_len, void *d_status, void *stream) {
     if (!c || (n && (!d_commits || !d_proofs || !d_status))) return fail(BPPP_ERR_ARG, "null argument");
     if (fmt != FMT_COMPRESSED && fmt != FMT_AFFINE64) return fail(BPPP_ERR_ARG, "bad point format");
+    std::lock_guard<std::mutex> lock(c->mu);
     CUDA_OK(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in the CUDA runtime
     Merlin init; merlin_init(init, label, (uint32_t)label_len);
@@ -123,6 +124,7 @@ extern "C" int bppp_u64_verify_batch(bppp_ctx *c, size_t n, const uint8_t *commi
                                      const uint8_t *label, size_t label_len, int32_t *status) {
     if (!c || (n && (!commits || !proofs || !status))) return fail(BPPP_ERR_ARG, "null argument");
     if (fmt != FMT_COMPRESSED && fmt != FMT_AFFINE64) return fail(BPPP_ERR_ARG, "bad point format");
+    std::lock_guard<std::mutex> lock(c->mu);
     CUDA_OK(cudaSetDevice(c->device));
     size_t csz = fmt == FMT_COMPRESSED ? 33 : 64, psz = fmt == FMT_COMPRESSED ? U64_PROOF_BYTES_COMPRESSED : U64_PROOF_BYTES_AFFINE;
     Merlin init; merlin_init(init, label, (uint32_t)label_len);

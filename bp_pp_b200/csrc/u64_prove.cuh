@@ -503,6 +503,12 @@ BPPP_HD void u64p_var2_one(const WS &w, size_t i, int j) {
     ws_st_pt(w, i, PL::COM, com);
 }
 
+BPPP_HD Pt u64p_var2_partial(const WS &w, size_t i, int lane, int nlanes) {
+    const int tids[2] = {0, 1};
+    Sc ks[2] = {ws_ld_sc(w, i, PL::VS), ws_ld_sc(w, i, PL::VS + 8)};
+    return ptj_to_pt(straus_tables_partial<2>(w, ptab_region(), i, tids, ks, lane, nlanes));
+}
+
 // 525-byte record: c_l c_r c_o c_s | r[0..4) | x[0..4) | l[0..2) | n[0] | r
 BPPP_HD void u64p_output_one(const WS &w, size_t i, uint8_t *out) {
 #pragma unroll 1

@@ -296,13 +296,17 @@ BPPP_HD void tables_normalize_strided(const WS &w, const TabRegion &R, size_t t,
     }
 }
 BPPP_HD void u64v_tables_normalize_strided(const WS &w, size_t t, size_t T) { tables_normalize_strided(w, vtab_region(), t, T); }
-// acc = sum_k ks[k] * P_{tids[k]} + init from the affine tables
+// One lane's share of sum_k ks[k] * P_{tids[k]} from the affine tables: the 2 NP GLV halves are dealt round-robin to
+// `nlanes` lanes (half h belongs to lane h % nlanes); every lane runs the full 128-doubling chain over its own halves.
+// nlanes = 1 is the whole sum.  More lanes shorten the dependent chain of one proof (fewer additions per lane) at the
+// price of repeating the doublings: used when the batch alone cannot fill the GPU (engine_var.cu).
 template <int NP>
-BPPP_HD Pt straus_tables(const WS &w, const TabRegion &R, size_t i, const int *tids, const Sc *ks, const Pt &init) {
+BPPP_HD PtJ straus_tables_partial(const WS &w, const TabRegion &R, size_t i, const int *tids, const Sc *ks, int lane, int nlanes) {
     Digits4h dg[2 * NP];
     bool neg[2 * NP];
 #pragma unroll 1
     for (int k = 0; k < NP; k++) {
+        if (nlanes > 1 && (2 * k) % nlanes != lane && (2 * k + 1) % nlanes != lane) continue;
         GlvSplit g = glv_split(ks[k]);
         dg[2 * k] = half_signed_digits4(g.k1); neg[2 * k] = g.neg1;
         dg[2 * k + 1] = half_signed_digits4(g.k2); neg[2 * k + 1] = g.neg2;
@@ -315,7 +319,7 @@ BPPP_HD Pt straus_tables(const WS &w, const TabRegion &R, size_t i, const int *t
             for (int r = 0; r < 4; r++) acc = ptj_double_hot(acc);
         }
 #pragma unroll 1
-        for (int h = 0; h < 2 * NP; h++) {
+        for (int h = lane; h < 2 * NP; h += nlanes) {
             int sd = digits4h_get(dg[h], d);
             if (neg[h]) sd = -sd;
             if (sd == 0) continue;
@@ -329,7 +333,12 @@ BPPP_HD Pt straus_tables(const WS &w, const TabRegion &R, size_t i, const int *t
             acc = ptj_add_mixed_hot(acc, q);
         }
     }
-    return pt_add(ptj_to_pt(acc), init);
+    return acc;
+}
+// acc = sum_k ks[k] * P_{tids[k]} + init from the affine tables
+template <int NP>
+BPPP_HD Pt straus_tables(const WS &w, const TabRegion &R, size_t i, const int *tids, const Sc *ks, const Pt &init) {
+    return pt_add(ptj_to_pt(straus_tables_partial<NP>(w, R, i, tids, ks, 0, 1)), init);
 }
 
 // Phase 2b: com_0 = ACC (fixed part) + tau^-1 c_s - delta c_o + tau c_l - tau^2 c_r + 2 tau^3 V'
@@ -339,6 +348,15 @@ BPPP_HD void u64v_var5_one(const WS &w, size_t i) {
 #pragma unroll 1
     for (int k = 0; k < 5; k++) ks[k] = ws_ld_sc(w, i, VL::VS + 8 * k);
     ws_st_pt(w, i, VL::COM, straus_tables<5>(w, vtab_region(), i, tids, ks, ws_ld_pt(w, i, VL::ACC)));
+}
+
+// one lane's partial sum of the same five terms (the caller reduces the lanes and adds ACC)
+BPPP_HD Pt u64v_var5_partial(const WS &w, size_t i, int lane, int nlanes) {
+    const int tids[5] = {vtab_of_slot(VP_CS), vtab_of_slot(VP_CO), vtab_of_slot(VP_CL), vtab_of_slot(VP_CR), VTAB_VP};
+    Sc ks[5];
+#pragma unroll 1
+    for (int k = 0; k < 5; k++) ks[k] = ws_ld_sc(w, i, VL::VS + 8 * k);
+    return ptj_to_pt(straus_tables_partial<5>(w, vtab_region(), i, tids, ks, lane, nlanes));
 }
 
 // WNLA round j = 0..3 (wnla.rs:84-102): transcript -> y_j, fold c, scalars for com' = com + y X + (y^2-1) R
@@ -372,6 +390,12 @@ BPPP_HD void u64v_var2_one(const WS &w, size_t i, int j) {
     const int tids[2] = {vtab_of_slot(VP_X + (3 - j)), vtab_of_slot(VP_R + (3 - j))};
     Sc ks[2] = {ws_ld_sc(w, i, VL::VS), ws_ld_sc(w, i, VL::VS + 8)};
     ws_st_pt(w, i, VL::COM, straus_tables<2>(w, vtab_region(), i, tids, ks, ws_ld_pt(w, i, VL::COM)));
+}
+
+BPPP_HD Pt u64v_var2_partial(const WS &w, size_t i, int j, int lane, int nlanes) {
+    const int tids[2] = {vtab_of_slot(VP_X + (3 - j)), vtab_of_slot(VP_R + (3 - j))};
+    Sc ks[2] = {ws_ld_sc(w, i, VL::VS), ws_ld_sc(w, i, VL::VS + 8)};
+    return ptj_to_pt(straus_tables_partial<2>(w, vtab_region(), i, tids, ks, lane, nlanes));
 }
 
 // Base case (wnla.rs:80-82): scalars of commit(l, n) over the ORIGINAL generators.  After 4 folds

@@ -8,9 +8,27 @@ import json
 from typing import Dict, List
 
 
+_ID33 = bytes(33)
+
+
+def _pt(b: bytes) -> str:
+    """One point.  The identity is the 1-byte SEC1 encoding "00" on the wire (k256 `AffinePoint: Serialize` goes through
+    sec1::EncodedPoint) although it is 33 zero bytes inside the engine's records (GroupEncoding::to_bytes)."""
+    return "00" if b == _ID33 else b.hex().upper()
+
+
+def _unpt(h: str) -> bytes:
+    b = bytes.fromhex(h)
+    if b == b"\0":
+        return _ID33
+    if len(b) != 33:
+        raise ValueError("a compressed point is 33 bytes (or the single byte 00 for the identity)")
+    return b
+
+
 def _pts(b: bytes) -> List[str]:
     assert len(b) % 33 == 0
-    return [b[i:i + 33].hex().upper() for i in range(0, len(b), 33)]
+    return [_pt(b[i:i + 33]) for i in range(0, len(b), 33)]
 
 
 def _scs(b: bytes) -> List[str]:
@@ -29,7 +47,7 @@ def circuit_record_to_obj(rec: bytes, rounds: int, l_len: int, n_len: int) -> Di
     r, x = rec[o:o + 33 * rounds], rec[o + 33 * rounds:o + 66 * rounds]
     o += 66 * rounds
     l, n = rec[o:o + 32 * l_len], rec[o + 32 * l_len:o + 32 * (l_len + n_len)]
-    d = {"c_l": rec[0:33].hex().upper(), "c_r": rec[33:66].hex().upper(), "c_o": rec[66:99].hex().upper(), "c_s": rec[99:132].hex().upper()}
+    d = {"c_l": _pt(rec[0:33]), "c_r": _pt(rec[33:66]), "c_o": _pt(rec[66:99]), "c_s": _pt(rec[99:132])}
     d.update(wnla_proof_to_obj(r, x, l, n))
     return d
 
@@ -38,16 +56,16 @@ def reciprocal_record_to_obj(rec: bytes, rounds: int = 4, l_len: int = 2, n_len:
     """reciprocal::SerializableProof { circuit_proof, r }; defaults are the u64 shape (525-byte record)."""
     body = 132 + 66 * rounds + 32 * (l_len + n_len)
     assert len(rec) == body + 33
-    return {"circuit_proof": circuit_record_to_obj(rec[:body], rounds, l_len, n_len), "r": rec[body:].hex().upper()}
+    return {"circuit_proof": circuit_record_to_obj(rec[:body], rounds, l_len, n_len), "r": _pt(rec[body:])}
 
 
 def reciprocal_obj_to_record(obj: Dict) -> bytes:
     cp = obj["circuit_proof"]
-    h = bytes.fromhex
-    out = h(cp["c_l"]) + h(cp["c_r"]) + h(cp["c_o"]) + h(cp["c_s"])
-    out += b"".join(h(p) for p in cp["r"]) + b"".join(h(p) for p in cp["x"])
+    h, p = bytes.fromhex, _unpt
+    out = p(cp["c_l"]) + p(cp["c_r"]) + p(cp["c_o"]) + p(cp["c_s"])
+    out += b"".join(p(q) for q in cp["r"]) + b"".join(p(q) for q in cp["x"])
     out += b"".join(h(s) for s in cp["l"]) + b"".join(h(s) for s in cp["n"])
-    return out + h(obj["r"])
+    return out + p(obj["r"])
 
 
 def dumps_reciprocal(rec: bytes, **kw) -> str:

@@ -26,7 +26,9 @@
  *   buffers   caller-owned.  `_dev` variants take device pointers valid on the context's GPU and a
  *             CUDA stream handle (cudaStream_t as void*; NULL = the legacy default stream), enqueue work and return
  *             without synchronising; internally the batch fans out over sub-streams that fork from / join into it.
- *   threading a context is single-owner (one host thread per context / GPU).
+ *   threading entry points taking a context serialise on it (internal mutex): one workspace, one staging area.  For
+ *             concurrency use one context per host thread (bppp_ctx_create_shared shares the tables).  `_dev` calls only
+ *             enqueue: two of them on the SAME context must be ordered on one stream (they share the workspace).
  */
 #ifndef BPPP_H
 #define BPPP_H
@@ -72,6 +74,11 @@ enum {
  * (20: 42.7 GB); 21..23 = signed windows with 2^(W-1) entries each (22: 78.9 GB); a negative value requests
  * signed windows of |window_bits| bits at any width. */
 int bppp_ctx_create(bppp_ctx **out, int device, const uint8_t *gens64, int window_bits, size_t max_batch);
+/* A further context on the same GPU sharing `parent`'s window tables (read-only after construction) with its own workspace,
+ * staging buffers and streams (max_batch 0 = the parent's).  Independent batches submitted through different contexts run
+ * side by side, which keeps the GPU full when each batch is small (a rank's 1/8 share of a 65,536 batch).  The parent
+ * must outlive every context that shares its tables. */
+int bppp_ctx_create_shared(bppp_ctx **out, const bppp_ctx *parent, size_t max_batch);
 void bppp_ctx_destroy(bppp_ctx *ctx);
 const char *bppp_last_error(void);
 /* bytes of device memory held by the context (tables + workspace), build time of the tables in ms */

@@ -60,6 +60,7 @@ public:
     // u64_proof.rs:37-39
     CompressedPoint commit_value(uint64_t x, const Scalar &s) const { return commit_batch({x}, {s}).at(0); }
     std::vector<CompressedPoint> commit_batch(const std::vector<uint64_t> &xs, const std::vector<Scalar> &blinds) const {
+        if (blinds.size() != xs.size()) throw Error("commit_batch: xs / blinds length mismatch");
         std::vector<CompressedPoint> out(xs.size());
         check(bppp_u64_commit_batch(ctx_, xs.size(), xs.data(), flat(blinds), BPPP_FMT_COMPRESSED, out.empty() ? nullptr : out[0].data()), "bppp_u64_commit_batch");
         return out;
@@ -80,23 +81,32 @@ public:
     reciprocal::Proof prove(uint64_t x, const Scalar &s, const std::string &transcript_label, const std::vector<uint8_t> &rng_bytes) const {
         return prove_batch({x}, {s}, rng_bytes, transcript_label).at(0);
     }
-    // u64_proof.rs:42-54 over N proofs: true / false exactly as the reference; Malformed for encodings the reference could not deserialise
-    std::vector<bool> verify_batch(const std::vector<CompressedPoint> &vs, const std::vector<reciprocal::Proof> &proofs, const std::string &label) const {
+    // u64_proof.rs:42-54 over N proofs, one status per proof (BPPP_ST_*): 1 / 0 are the reference's true / false; a negative
+    // status marks a record the reference could not have deserialised (BAD_POINT / BAD_SCALAR) or on which it would have
+    // panicked.  One bad record never affects the verdicts of the others.
+    std::vector<int32_t> verify_batch_status(const std::vector<CompressedPoint> &vs, const std::vector<reciprocal::Proof> &proofs, const std::string &label) const {
         const size_t n = vs.size();
         if (proofs.size() != n) throw Error("verify_batch: length mismatch");
         std::vector<int32_t> st(n);
         static_assert(sizeof(reciprocal::Proof) == BPPP_U64_PROOF_BYTES, "Proof must be the packed 525-byte record");
         check(bppp_u64_verify_batch(ctx_, n, n ? vs[0].data() : nullptr, n ? proofs[0].record.data() : nullptr, BPPP_FMT_COMPRESSED,
                                     (const uint8_t *)label.data(), label.size(), st.data()), "bppp_u64_verify_batch");
-        std::vector<bool> out(n);
-        for (size_t i = 0; i < n; i++) {
-            if (st[i] == BPPP_ST_PANIC_INVERT_ZERO || st[i] == BPPP_ST_PANIC_CHALLENGE_RANGE) throw Panic(st[i], "verify: the reference would panic on proof " + std::to_string(i));
-            if (st[i] < 0) throw Malformed(st[i], "verify: proof " + std::to_string(i) + " does not deserialise");
-            out[i] = st[i] == BPPP_ST_TRUE;
-        }
+        return st;
+    }
+    // the same as booleans: only status 1 is true (a malformed or panicking record is "not verified"; use verify_batch_status to tell them apart)
+    std::vector<bool> verify_batch(const std::vector<CompressedPoint> &vs, const std::vector<reciprocal::Proof> &proofs, const std::string &label) const {
+        std::vector<int32_t> st = verify_batch_status(vs, proofs, label);
+        std::vector<bool> out(st.size());
+        for (size_t i = 0; i < st.size(); i++) out[i] = st[i] == BPPP_ST_TRUE;
         return out;
     }
-    bool verify(const CompressedPoint &v, const reciprocal::Proof &proof, const std::string &transcript_label) const { return verify_batch({v}, {proof}, transcript_label).at(0); }
+    // single proof: true / false exactly as the reference; throws Panic where it panics, Malformed where it could not deserialise
+    bool verify(const CompressedPoint &v, const reciprocal::Proof &proof, const std::string &transcript_label) const {
+        int32_t st = verify_batch_status({v}, {proof}, transcript_label).at(0);
+        if (st == BPPP_ST_PANIC_INVERT_ZERO || st == BPPP_ST_PANIC_CHALLENGE_RANGE) throw Panic(st, "verify: the reference would panic on this proof");
+        if (st < 0) throw Malformed(st, "verify: the proof does not deserialise");
+        return st == BPPP_ST_TRUE;
+    }
 
     // u64_proof.rs:84-102
     static std::vector<uint64_t> u64_to_hex(uint64_t x) { std::vector<uint64_t> d(16); for (auto &v : d) { v = x % 16; x /= 16; } return d; }

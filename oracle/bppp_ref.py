@@ -1092,7 +1092,11 @@ def serialize_circuit_proof(cp: CircuitProof) -> bytes:
 
 
 def _hex_pt(p) -> str:
-    return pt_to_bytes(p).hex().upper()  # serdect upper-hex [recalled]
+    # k256's `AffinePoint: Serialize` goes through sec1::EncodedPoint, whose identity encoding is the single byte 00
+    # (SEC1 2.3.3), not the 33 zero bytes GroupEncoding::to_bytes yields for the transcript; serdect upper-hex [recalled]
+    if p is None:
+        return "00"
+    return pt_to_bytes(p).hex().upper()
 
 
 def _hex_sc(s) -> str:

@@ -66,3 +66,18 @@ def test_serializable_proof_json_framing(golden):
     assert obj == c["json"]
     assert serde.reciprocal_obj_to_record(obj) == rec
     assert serde.loads_reciprocal(serde.dumps_reciprocal(rec)) == rec
+
+
+def test_serde_identity_point_is_the_one_byte_sec1_encoding(golden):
+    """k256 serialises AffinePoint::IDENTITY as the single SEC1 byte 00 (not 33 zero bytes): the JSON framing must emit
+    and accept that form while the engine's record keeps the 33-byte GroupEncoding form."""
+    from bp_pp_b200 import serde
+    rec = bytearray(bytes.fromhex(golden["cases"][0]["proof"]))
+    rec[33:66] = bytes(33)            # c_r := identity
+    rec[492:525] = bytes(33)          # r := identity
+    obj = serde.reciprocal_record_to_obj(bytes(rec))
+    assert obj["circuit_proof"]["c_r"] == "00" and obj["r"] == "00"
+    assert serde.reciprocal_obj_to_record(obj) == bytes(rec)
+    import pytest
+    with pytest.raises(ValueError):
+        serde.reciprocal_obj_to_record({**obj, "r": "0000"})

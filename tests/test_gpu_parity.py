@@ -264,3 +264,68 @@ def test_device_resident_entry_points_on_a_side_stream(ctx, batch):
     side.synchronize()
     assert bytes(d_out.cpu().numpy()) == batch["proofs"]
     assert d_pst.cpu().tolist() == [1] * n and d_vst.cpu().tolist() == [1] * n
+
+
+def test_commit_rejects_a_non_canonical_blinding(ctx):
+    """A k256::Scalar cannot hold a value >= n: commit_batch must fail rather than return an unblinded x*g (ADVICE r1)."""
+    import bp_pp_b200 as B
+    n_be = (0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141).to_bytes(32, "big")
+    with pytest.raises(B.BpppError):
+        ctx.commit_batch([5, 6], (7).to_bytes(32, "big") + n_be)
+    assert len(ctx.commit_batch([5, 6], (7).to_bytes(32, "big") * 2)) == 66       # the context stays usable
+
+
+@pytest.mark.parametrize("var_lanes,msm_lanes", [(1, 4), (2, 8), (4, 16)])
+def test_lane_variants_are_byte_identical(gens64, batch, oracle, var_lanes, msm_lanes, monkeypatch):
+    """Intra-proof parallelism for small (sub-)batches: the ladders with 2 / 4 lanes per proof (GLV halves shared out,
+    partial sums met through warp shuffles) and the fixed-base sums with 8 / 16 lanes must give the single-lane bytes."""
+    import bp_pp_b200 as B
+    monkeypatch.setenv("BPPP_VAR_LANES_RT", str(var_lanes))
+    monkeypatch.setenv("BPPP_MSM_LANES_RT", str(msm_lanes))
+    n = 200
+    c = B.Context(gens64, 0, 8, n)
+    xs, blinds, rngs = batch["xs"][:n], batch["blinds"][:32 * n], batch["rngs"][:3328 * n]
+    proofs, st = c.prove_batch(xs, blinds, rngs, LABEL)
+    assert st == [1] * n and proofs == batch["proofs"][:525 * n]
+    rnd = random.Random(99)
+    recs, coms = [], []
+    for i in range(n):
+        rec, com = batch["proofs"][525 * i:525 * i + 525], batch["commits"][33 * i:33 * i + 33]
+        if i % 3 == 1:
+            rec, com = _tamper(rec, com, (i // 3) % 8, rnd, oracle)
+        recs.append(rec); coms.append(com)
+    recs, coms = b"".join(recs), b"".join(coms)
+    assert c.verify_batch(coms, recs, LABEL) == oracle.u64_verify_batch(gens64, coms, recs, LABEL, THREADS)
+    c.close()
+
+
+def test_small_batches_pick_lanes_automatically(ctx, batch):
+    """The default lane choice (by batch size) at sizes on both sides of every threshold the 16-bit context can reach."""
+    for n in (1, 7, 64, 384):
+        proofs, st = ctx.prove_batch(batch["xs"][:n], batch["blinds"][:32 * n], batch["rngs"][:3328 * n], LABEL)
+        assert proofs == batch["proofs"][:525 * n] and st == [1] * n
+        assert ctx.verify_batch(batch["commits"][:33 * n], proofs, LABEL) == [1] * n
+
+
+def test_shared_table_contexts_run_side_by_side(ctx, batch):
+    """bppp_ctx_create_shared: contexts sharing one set of window tables, each with its own workspace, driven from
+    concurrent host threads: every thread must get the oracle's bytes."""
+    import threading
+    n = batch["n"]
+    others = [ctx.shared(n) for _ in range(3)]
+    results = {}
+
+    def work(k, c):
+        for _ in range(3):
+            proofs, st = c.prove_batch(batch["xs"], batch["blinds"], batch["rngs"], LABEL)
+            verdicts = c.verify_batch(batch["commits"], proofs, LABEL)
+        results[k] = (proofs, st, verdicts)
+
+    threads = [threading.Thread(target=work, args=(k, c)) for k, c in enumerate([ctx] + others)]
+    for t in threads: t.start()
+    for t in threads: t.join()
+    for k in range(4):
+        proofs, st, verdicts = results[k]
+        assert proofs == batch["proofs"] and st == [1] * n and verdicts == [1] * n
+    for c in others:
+        c.close()
