@@ -8,12 +8,12 @@ batch entry points `commit_batch` / `prove_batch` / `verify_batch` over N indepe
 curve, field, transcript and protocol arithmetic runs on the GPU inside libbppp.so (CUDA, sm_100a)
 through the C ABI declared in include/bppp.h; this module only marshals bytes.
 """
-from .api import (BpppError, Context, U64RangeProofProtocol, FMT_AFFINE64, FMT_COMPRESSED, G_VEC_FULL_SZ,
+from .api import (BpppError, Context, MultiContext, U64RangeProofProtocol, FMT_AFFINE64, FMT_COMPRESSED, G_VEC_FULL_SZ,
                   H_VEC_CIRCUIT_SZ, H_VEC_FULL_SZ, ST_BAD_POINT, ST_BAD_SCALAR, ST_FALSE, ST_PANIC_CHALLENGE_RANGE,
                   ST_PANIC_INVERT_ZERO, ST_TRUE, U64_PROOF_BYTES, U64_RNG_BYTES, ArithmeticCircuit, ReciprocalRangeProofProtocol, UploadedMsm, WeightNormLinearArgument, microbench, msm, points_convert, points_generate, u64_proofs_to_affine,
                   points_sum)
 
-__all__ = ["BpppError", "Context", "U64RangeProofProtocol", "FMT_AFFINE64", "FMT_COMPRESSED", "G_VEC_FULL_SZ",
+__all__ = ["BpppError", "Context", "MultiContext", "U64RangeProofProtocol", "FMT_AFFINE64", "FMT_COMPRESSED", "G_VEC_FULL_SZ",
            "H_VEC_CIRCUIT_SZ", "H_VEC_FULL_SZ", "ST_BAD_POINT", "ST_BAD_SCALAR", "ST_FALSE",
            "ST_PANIC_CHALLENGE_RANGE", "ST_PANIC_INVERT_ZERO", "ST_TRUE", "U64_PROOF_BYTES", "U64_RNG_BYTES",
            "microbench", "msm", "points_sum", "UploadedMsm", "WeightNormLinearArgument", "ReciprocalRangeProofProtocol", "ArithmeticCircuit", "points_generate", "points_convert", "u64_proofs_to_affine"]

@@ -12,8 +12,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("BPPP_LIB") or os.path.join(_HERE, "libbppp.so")   # BPPP_LIB: kernel-variant experiments
 
 EXPORTS = [
-    "bppp_ctx_create", "bppp_ctx_create_shared", "bppp_ctx_destroy", "bppp_last_error", "bppp_ctx_info", "bppp_u64_commit_batch",
+    "bppp_ctx_create", "bppp_ctx_create_shared", "bppp_ctx_set_inflight", "bppp_ctx_destroy", "bppp_last_error", "bppp_ctx_info", "bppp_u64_commit_batch",
     "bppp_u64_verify_batch", "bppp_u64_verify_batch_dev", "bppp_u64_prove_batch", "bppp_u64_prove_batch_dev",
+    "bppp_u64_verify_begin", "bppp_u64_verify_circuit", "bppp_u64_verify_round", "bppp_u64_verify_finish",
+    "bppp_u64_prove_begin", "bppp_u64_prove_reciprocal", "bppp_u64_prove_circuit", "bppp_u64_prove_tau", "bppp_u64_prove_round",
+    "bppp_u64_prove_finish", "bppp_u64_step_abort",
+    "bppp_multi_ctx_create", "bppp_multi_ctx_destroy", "bppp_multi_device_count", "bppp_multi_ctx_get", "bppp_multi_u64_commit_batch",
+    "bppp_multi_u64_verify_batch", "bppp_multi_u64_prove_batch",
     "bppp_launch_count", "bppp_microbench", "bppp_ctx_profile_begin", "bppp_ctx_profile_end",
     "bppp_msm", "bppp_points_upload", "bppp_scalars_upload", "bppp_device_free", "bppp_msm_uploaded", "bppp_points_sum", "bppp_points_generate", "bppp_points_convert",
     "bppp_wnla_commit", "bppp_wnla_prove", "bppp_wnla_verify",
@@ -40,6 +45,10 @@ def lib():
         L.bppp_launch_count.argtypes = [C.c_void_p]
         L.bppp_ctx_destroy.argtypes = [C.c_void_p]
         L.bppp_ctx_destroy.restype = None
+        L.bppp_multi_ctx_destroy.argtypes = [C.c_void_p]
+        L.bppp_multi_ctx_destroy.restype = None
+        L.bppp_multi_ctx_get.restype = C.c_void_p
+        L.bppp_multi_ctx_get.argtypes = [C.c_void_p, C.c_int]
         L.bppp_device_free.restype = None
         L.bppp_device_free.argtypes = [C.c_int, C.c_void_p]
         _lib = L

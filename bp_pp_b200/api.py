@@ -50,6 +50,10 @@ class Context:
         submitted through different contexts run side by side."""
         return Context(b"", self.device, 0, max_batch, _shared_from=self)
 
+    def set_inflight(self, batches: int):
+        """Hint that `batches` independent batches are kept in flight on this GPU (affects lane choices only)."""
+        check(lib().bppp_ctx_set_inflight(self._h, C.c_int(batches)), "bppp_ctx_set_inflight")
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             lib().bppp_ctx_destroy(self._h)
@@ -125,6 +129,103 @@ class Context:
                                          C.c_size_t(len(label)), out, status), "bppp_u64_prove_batch")
         return bytes(out)[:U64_PROOF_BYTES * n], list(status)[:n]
 
+    # ---- phase-stepped entry points for caller-owned transcripts (include/bppp.h) ----
+    def verify_with_transcripts(self, commits: bytes, proofs: bytes, transcripts: Sequence) -> List[int]:
+        """U64RangeProofProtocol::verify (u64_proof.rs:42-54 -> reciprocal.rs:98-107 -> circuit.rs:154-256 ->
+        wnla.rs:75-121) for n proofs, proof i continuing the caller-owned transcripts[i] (any prior state).  The host does
+        every app_point / get_challenge of SURVEY App. B on the caller's objects; the GPU does all group arithmetic.
+        The transcripts are left exactly where the reference leaves them."""
+        from .transcript import app_point, get_challenge
+        n = len(transcripts)
+        if len(commits) != 33 * n or len(proofs) != U64_PROOF_BYTES * n:
+            raise ValueError("commits / proofs / transcripts length mismatch")
+        L = lib()
+        rec = lambda i, k: proofs[U64_PROOF_BYTES * i + 33 * k:U64_PROOF_BYTES * i + 33 * k + 33]      # noqa: E731  record point k
+        vp = (C.c_uint8 * (33 * n))()
+        check(L.bppp_u64_verify_begin(self._h, C.c_size_t(n), _in(commits), _in(proofs), C.c_int(FMT_COMPRESSED), vp), "bppp_u64_verify_begin")
+        try:
+            vp = bytes(vp)
+            chal = bytearray()
+            for i, t in enumerate(transcripts):
+                app_point(b"reciprocal_commitment", commits[33 * i:33 * i + 33], t)                  # reciprocal.rs:99
+                chal += get_challenge(b"reciprocal_challenge", t)                                    # :100
+                app_point(b"commitment_cl", rec(i, 0), t); app_point(b"commitment_cr", rec(i, 1), t)  # circuit.rs:155-159
+                app_point(b"commitment_co", rec(i, 2), t); app_point(b"commitment_v", vp[33 * i:33 * i + 33], t)
+                for lbl in (b"circuit_rho", b"circuit_lambda", b"circuit_beta", b"circuit_delta"):   # :161-164
+                    chal += get_challenge(lbl, t)
+                app_point(b"commitment_cs", rec(i, 3), t)                                            # :189
+                chal += get_challenge(b"circuit_tau", t)                                             # :191
+            com = (C.c_uint8 * (33 * n))()
+            check(L.bppp_u64_verify_circuit(self._h, _in(bytes(chal)), com), "bppp_u64_verify_circuit")
+            for j in range(4):                                                                       # wnla.rs:88-94
+                ys = bytearray()
+                cb = bytes(com)
+                for i, t in enumerate(transcripts):
+                    app_point(b"wnla_com", cb[33 * i:33 * i + 33], t)
+                    app_point(b"wnla_x", rec(i, 8 + (3 - j)), t)
+                    app_point(b"wnla_r", rec(i, 4 + (3 - j)), t)
+                    t.append_u64(b"l.sz", 32 >> j); t.append_u64(b"n.sz", 16 >> j)
+                    ys += get_challenge(b"wnla_challenge", t)
+                check(L.bppp_u64_verify_round(self._h, C.c_int(j), _in(bytes(ys)), com), "bppp_u64_verify_round")
+            status = (C.c_int32 * n)()
+            check(L.bppp_u64_verify_finish(self._h, status), "bppp_u64_verify_finish")
+            return list(status)
+        except Exception:
+            L.bppp_u64_step_abort(self._h)
+            raise
+
+    def prove_with_transcripts(self, xs: Sequence[int], blinds32: bytes, rng: bytes, transcripts: Sequence) -> Tuple[bytes, List[int]]:
+        """U64RangeProofProtocol::prove (u64_proof.rs:57-82 -> reciprocal.rs:110-146 -> circuit.rs:260-556 ->
+        wnla.rs:125-190) for n witnesses, witness i continuing the caller-owned transcripts[i]."""
+        from .transcript import app_point, get_challenge
+        n = len(transcripts)
+        if len(xs) != n or len(blinds32) != 32 * n or len(rng) != U64_RNG_BYTES * n:
+            raise ValueError("xs / blinds32 / rng / transcripts length mismatch")
+        L = lib()
+        xa = (C.c_uint64 * n)(*xs)
+        v = (C.c_uint8 * (33 * n))()
+        check(L.bppp_u64_prove_begin(self._h, C.c_size_t(n), xa, _in(blinds32), _in(rng), v), "bppp_u64_prove_begin")
+        try:
+            v = bytes(v)
+            es = bytearray()
+            for i, t in enumerate(transcripts):
+                app_point(b"reciprocal_commitment", v[33 * i:33 * i + 33], t)                        # reciprocal.rs:114
+                es += get_challenge(b"reciprocal_challenge", t)                                      # :115
+            p4 = (C.c_uint8 * (132 * n))()
+            check(L.bppp_u64_prove_reciprocal(self._h, _in(bytes(es)), p4), "bppp_u64_prove_reciprocal")
+            p4 = bytes(p4)
+            chal = bytearray()
+            for i, t in enumerate(transcripts):                                                      # circuit.rs:347-355
+                for k, lbl in enumerate((b"commitment_cl", b"commitment_cr", b"commitment_co", b"commitment_v")):
+                    app_point(lbl, p4[132 * i + 33 * k:132 * i + 33 * k + 33], t)
+                for lbl in (b"circuit_rho", b"circuit_lambda", b"circuit_beta", b"circuit_delta"):
+                    chal += get_challenge(lbl, t)
+            cs = (C.c_uint8 * (33 * n))()
+            check(L.bppp_u64_prove_circuit(self._h, _in(bytes(chal)), cs), "bppp_u64_prove_circuit")
+            cs = bytes(cs)
+            taus = bytearray()
+            for i, t in enumerate(transcripts):                                                      # circuit.rs:472-474
+                app_point(b"commitment_cs", cs[33 * i:33 * i + 33], t)
+                taus += get_challenge(b"circuit_tau", t)
+            p3 = (C.c_uint8 * (99 * n))()
+            check(L.bppp_u64_prove_tau(self._h, _in(bytes(taus)), p3), "bppp_u64_prove_tau")
+            for j in range(4):                                                                       # wnla.rs:162-168
+                pb = bytes(p3)
+                ys = bytearray()
+                for i, t in enumerate(transcripts):
+                    for k, lbl in enumerate((b"wnla_com", b"wnla_x", b"wnla_r")):
+                        app_point(lbl, pb[99 * i + 33 * k:99 * i + 33 * k + 33], t)
+                    t.append_u64(b"l.sz", 32 >> j); t.append_u64(b"n.sz", 16 >> j)
+                    ys += get_challenge(b"wnla_challenge", t)
+                check(L.bppp_u64_prove_round(self._h, C.c_int(j), _in(bytes(ys)), p3), "bppp_u64_prove_round")
+            out = (C.c_uint8 * (U64_PROOF_BYTES * n))()
+            status = (C.c_int32 * n)()
+            check(L.bppp_u64_prove_finish(self._h, out, status), "bppp_u64_prove_finish")
+            return bytes(out), list(status)
+        except Exception:
+            L.bppp_u64_step_abort(self._h)
+            raise
+
     # ---- raw-pointer entry points (host numpy/pinned buffers or device pointers) ----
     def verify_batch_ptr(self, n: int, commits_ptr: int, proofs_ptr: int, label: bytes, status_ptr: int,
                          fmt: int = FMT_COMPRESSED):
@@ -152,6 +253,56 @@ class Context:
               "bppp_u64_prove_batch_dev")
 
 
+class MultiContext:
+    """One process driving several GPUs (bppp_multi_ctx): the batch is cut into contiguous per-device ranges, one host
+    thread per device inside the library, generators and tables replicated, no data-path collective."""
+
+    def __init__(self, gens64: bytes, devices: Sequence[int], window_bits: int = 0, max_batch_per_device: int = 65536):
+        if len(gens64) != 64 * 49:
+            raise ValueError("gens64 must be 49 x 64 bytes: g || g_vec[16] || h_vec[32]")
+        self._h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        check(lib().bppp_multi_ctx_create(C.byref(self._h), devs, C.c_int(len(devices)), _in(gens64), C.c_int(window_bits),
+                                          C.c_size_t(max_batch_per_device)), "bppp_multi_ctx_create")
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().bppp_multi_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def commit_batch(self, xs: Sequence[int], blinds32: bytes, fmt: int = FMT_COMPRESSED) -> bytes:
+        n = len(xs)
+        osz = 33 if fmt == FMT_COMPRESSED else 64
+        out = (C.c_uint8 * max(osz * n, 1))()
+        xa = (C.c_uint64 * max(n, 1))(*xs)
+        check(lib().bppp_multi_u64_commit_batch(self._h, C.c_size_t(n), xa, _in(blinds32), C.c_int(fmt), out), "bppp_multi_u64_commit_batch")
+        return bytes(out)[:osz * n]
+
+    def verify_batch(self, commits: bytes, proofs: bytes, label: bytes, fmt: int = FMT_COMPRESSED) -> List[int]:
+        csz = 33 if fmt == FMT_COMPRESSED else 64
+        n = len(commits) // csz
+        status = (C.c_int32 * max(n, 1))()
+        check(lib().bppp_multi_u64_verify_batch(self._h, C.c_size_t(n), _in(commits), _in(proofs), C.c_int(fmt), _in(label),
+                                                C.c_size_t(len(label)), status), "bppp_multi_u64_verify_batch")
+        return list(status)[:n]
+
+    def prove_batch(self, xs: Sequence[int], blinds32: bytes, rng: bytes, label: bytes) -> Tuple[bytes, List[int]]:
+        n = len(xs)
+        xa = (C.c_uint64 * max(n, 1))(*xs)
+        out = (C.c_uint8 * max(U64_PROOF_BYTES * n, 1))()
+        status = (C.c_int32 * max(n, 1))()
+        check(lib().bppp_multi_u64_prove_batch(self._h, C.c_size_t(n), xa, _in(blinds32), _in(rng), _in(label), C.c_size_t(len(label)),
+                                               out, status), "bppp_multi_u64_prove_batch")
+        return bytes(out)[:U64_PROOF_BYTES * n], list(status)[:n]
+
+
 class U64RangeProofProtocol:
     """Mirror of `bp_pp::range_proof::u64_proof::U64RangeProofProtocol` (u64_proof.rs:19-102).
 
@@ -177,7 +328,23 @@ class U64RangeProofProtocol:
     def commit_batch(self, xs: Sequence[int], blinds32: bytes, fmt: int = FMT_COMPRESSED) -> bytes:
         return self.ctx.commit_batch(xs, blinds32, fmt)
 
-    # u64_proof.rs:57-82
+    # u64_proof.rs:57-82 with the reference's own signature: prove(&self, x, s, t: &mut Transcript, rng)
+    def prove_t(self, x: int, s: bytes, t, rng_bytes: bytes) -> bytes:
+        """`t` is the caller's transcript (bp_pp_b200.transcript.Transcript or anything with append_message /
+        append_u64 / challenge_bytes) in any prior state; it is advanced exactly as the reference advances it."""
+        proofs, status = self.ctx.prove_with_transcripts([x], s, rng_bytes, [t])
+        if status[0] != ST_TRUE:
+            raise BpppError(f"prove: the reference would panic here (status {status[0]})")
+        return proofs
+
+    # u64_proof.rs:42-54 with the reference's own signature: verify(&self, v, proof, t: &mut Transcript) -> bool
+    def verify_t(self, v: bytes, proof: bytes, t) -> bool:
+        status = self.ctx.verify_with_transcripts(v, proof, [t])
+        if status[0] < 0:
+            raise BpppError(f"verify: malformed input or reference panic (status {status[0]})")
+        return status[0] == ST_TRUE
+
+    # u64_proof.rs:57-82 with a fresh Transcript::new(transcript_label) (the batch entry points' convention)
     def prove(self, x: int, s: bytes, transcript_label: bytes, rng_bytes: bytes) -> bytes:
         proofs, status = self.ctx.prove_batch([x], s, rng_bytes, transcript_label)
         if status[0] != ST_TRUE:

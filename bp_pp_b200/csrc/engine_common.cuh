@@ -51,7 +51,10 @@ struct bppp_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
     uint64_t launches = 0;
     int sm_count = 148;
-    int active_parts = 1;           // sub-batches of the slice in flight (they run concurrently: lane choices look at their sum)
+    // phase-stepped session (bppp_u64_{verify,prove}_begin .. _finish): one at a time per context, lives in the workspace
+    struct Step { int kind = 0; size_t n = 0; int stage = 0; int fmt = 0; } step;
+    int active_parts = 1;
+    int inflight_hint = 1;          // bppp_ctx_set_inflight: independent batches the caller keeps in flight on sibling contexts           // sub-batches of the slice in flight (they run concurrently: lane choices look at their sum)
     int msm_lanes_override = 0, var_lanes_override = 0;   // BPPP_MSM_LANES_RT / BPPP_VAR_LANES_RT (experiments)
     // optional per-launch timing (bppp_ctx_profile_begin/end): CUDA events on the launching stream
     bool profiling = false;
@@ -111,6 +114,9 @@ static inline WS sub_ws(const bppp_ctx *c, const SubPlan &sp, int k) {
 void launch_msm_fixed(bppp_ctx *c, cudaStream_t st, WS w, int sc_off, const TermMap &tm, int nterms, int out_off);
 void launch_batch_inv(bppp_ctx *c, cudaStream_t st, WS w, int in_off, int out_off);
 void launch_batch_inv_list(bppp_ctx *c, cudaStream_t st, WS w, const InvList &L);
+// compressed SEC1 bytes of up to 4 projective workspace points per proof (with their batch-inverted Z): out[(i * L.n + k) * 33]
+struct EmitList { int n; int pt[4]; int zinv[4]; };
+void launch_emit_points(bppp_ctx *c, cudaStream_t st, WS w, const EmitList &L, uint8_t *d_out);
 // engine_var.cu: joint variable-base ladders (one thread per proof)
 void launch_v_var5(bppp_ctx *c, cudaStream_t st, WS w);
 void launch_v_var2(bppp_ctx *c, cudaStream_t st, WS w, int j);

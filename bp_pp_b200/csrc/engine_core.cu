@@ -54,6 +54,15 @@ __global__ void __launch_bounds__(128) k_batch_inv_list(WS w, InvList L, size_t 
     if (t < nthreads) batch_inv_list_strided(w, L, t, nthreads);
 }
 
+__global__ void __launch_bounds__(64) k_emit_points(WS w, EmitList L, uint8_t *out) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= w.n * (size_t)L.n) return;
+    size_t i = t / L.n; int k = (int)(t % L.n);
+    bool id;
+    PtA a = ws_affine(w, i, L.pt[k], L.zinv[k], id);
+    pta_compress(out + 33 * t, a, id);
+}
+
 // ---- commit ----
 __global__ void __launch_bounds__(64) k_c_load(WS w, const uint64_t *xs, const uint8_t *blinds, int32_t *bad_flag) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -148,10 +157,12 @@ int join_streams(bppp_ctx *c, cudaStream_t caller, const SubPlan &sp) {
 int msm_lanes_for(const bppp_ctx *c, size_t n) {
     if (c->msm_lanes_override) return c->msm_lanes_override;
     const size_t full = (size_t)c->sm_count * 448;     // threads of one full wave at 7 blocks x 64
-    int lanes = MSM_LANES;
-    n *= (size_t)c->active_parts;
-    while (lanes < 16 && n * lanes * 2 <= full) lanes *= 2;
-    return lanes;
+    n *= (size_t)c->active_parts * (size_t)c->inflight_hint;
+    // measured on a B200 (tools/batch_sweep.py --lane-sweep, profiles/r2_lane_sweep.json): 8 lanes pay below ~16k proofs
+    // in flight, 16 below ~4k
+    if (n * 16 <= full) return 16;
+    if (n * 4 <= full) return 8;
+    return MSM_LANES;
 }
 void launch_msm_fixed(bppp_ctx *c, cudaStream_t st, WS w, int sc_off, const TermMap &tm, int nterms, int out_off) {
     int lanes = msm_lanes_for(c, w.n);
@@ -167,6 +178,9 @@ void launch_batch_inv_list(bppp_ctx *c, cudaStream_t st, WS w, const InvList &L)
     size_t min_threads = (size_t)c->sm_count * 128;
     if (nthreads < min_threads) nthreads = items < min_threads ? items : min_threads;
     LAUNCH(c, k_batch_inv_list, nblocks(nthreads, 128), 128, w, L, nthreads);
+}
+void launch_emit_points(bppp_ctx *c, cudaStream_t st, WS w, const EmitList &L, uint8_t *d_out) {
+    LAUNCH(c, k_emit_points, nblocks(w.n * L.n, 64), 64, w, L, d_out);
 }
 void launch_batch_inv(bppp_ctx *c, cudaStream_t st, WS w, int in_off, int out_off) {
     // one inversion per thread, >= 8 items per thread when the batch is large enough to still fill the GPU
@@ -319,6 +333,11 @@ extern "C" int bppp_ctx_info(const bppp_ctx *c, size_t *table_bytes, size_t *wor
     return BPPP_OK;
 }
 extern "C" uint64_t bppp_launch_count(const bppp_ctx *c) { return c ? c->launches : 0; }
+extern "C" int bppp_ctx_set_inflight(bppp_ctx *c, int batches) {
+    if (!c || batches < 1 || batches > 64) return fail(BPPP_ERR_ARG, "batches in flight must be in 1..64");
+    c->inflight_hint = batches;
+    return BPPP_OK;
+}
 
 extern "C" int bppp_ctx_profile_begin(bppp_ctx *c) {
     if (!c) return BPPP_ERR_ARG;

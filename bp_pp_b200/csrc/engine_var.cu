@@ -66,14 +66,15 @@ __global__ void __launch_bounds__(128) k_p_tables_normalize(WS w, size_t nthread
     if (t < nthreads) tables_normalize_strided(w, ptab_region(), t, nthreads);
 }
 namespace bppp {
-// lanes per proof for the ladders: 1 while the batch itself gives ~10 warps per SM, then 2, then 4
+// lanes per proof for the ladders, by the number of proofs in flight on the GPU
 static int var_lanes_for(const bppp_ctx *c, size_t n) {
     if (c->var_lanes_override) return c->var_lanes_override;
     const size_t full = (size_t)c->sm_count * 448;
-    n *= (size_t)c->active_parts;
-    if (n * 4 >= full * 3) return 1;
-    if (n * 8 >= full * 3) return 2;
-    return 4;
+    n *= (size_t)c->active_parts * (size_t)c->inflight_hint;
+    // measured (tools/batch_sweep.py --lane-sweep): 4 lanes win up to ~8k proofs in flight, 2 lanes up to ~16k
+    if (n * 8 <= full) return 4;
+    if (n * 4 <= full) return 2;
+    return 1;
 }
 void launch_v_var5(bppp_ctx *c, cudaStream_t st, WS w) {
     const int lanes = var_lanes_for(c, w.n);

@@ -37,13 +37,14 @@ __global__ void __launch_bounds__(128) k_v_tables_normalize(WS w, size_t nthread
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nthreads) u64v_tables_normalize_strided(w, t, nthreads);
 }
-__global__ void __launch_bounds__(64) k_v_phase1(WS w, Merlin init) {
+// ext != nullptr: challenges of a caller-owned transcript, ext_stride bytes per proof (ws.cuh: Tx)
+__global__ void __launch_bounds__(64) k_v_phase1(WS w, Merlin init, const uint8_t *ext, int ext_stride) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < w.n) u64v_phase1_one(w, i, init);
+    if (i < w.n) u64v_phase1_one(w, i, init, ext ? ext + (size_t)ext_stride * i : nullptr);
 }
-__global__ void __launch_bounds__(64) k_v_round(WS w, int j) {
+__global__ void __launch_bounds__(64) k_v_round(WS w, int j, const uint8_t *ext, int ext_stride) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < w.n) u64v_round_one(w, i, j);
+    if (i < w.n) u64v_round_one(w, i, j, ext ? ext + (size_t)ext_stride * i : nullptr);
 }
 __global__ void __launch_bounds__(64) k_v_final_scalars(WS w) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,7 +68,7 @@ static int verify_part(bppp_ctx *c, cudaStream_t st, WS w, const uint8_t *d_comm
     LAUNCH(c, k_v_decode, nblocks(n * VP_COUNT, 128), 128, w, d_commits, d_proofs, fmt, flags);
     LAUNCH(c, k_v_load_finish, g64, 64, w, d_proofs, fmt, flags);
     launch_batch_inv(c, st, w, VL::VP + 2 * FE_W, VL::ZINV);
-    LAUNCH(c, k_v_phase1, g64, 64, w, init);
+    LAUNCH(c, k_v_phase1, g64, 64, w, init, (const uint8_t *)nullptr, 0);
     {   // affine 1P..8P tables of the 13 per-proof points: one batch inversion serves all 104 entries of every proof
         LAUNCH(c, k_v_tables_build, nblocks(n * VL::TAB_POINTS, 64), 64, w);
         size_t items = n * VL::TAB_ENTRIES, nthreads = (items + 63) / 64;
@@ -78,7 +79,7 @@ static int verify_part(bppp_ctx *c, cudaStream_t st, WS w, const uint8_t *d_comm
     launch_v_var5(c, st, w);
     for (int j = 0; j < 4; j++) {
         launch_batch_inv(c, st, w, VL::COM + 2 * FE_W, VL::ZINV);
-        LAUNCH(c, k_v_round, g64, 64, w, j);
+        LAUNCH(c, k_v_round, g64, 64, w, j, (const uint8_t *)nullptr, 0);
         launch_v_var2(c, st, w, j);
     }
     LAUNCH(c, k_v_final_scalars, g64, 64, w);
@@ -147,3 +148,108 @@ extern "C" int bppp_u64_verify_batch(bppp_ctx *c, size_t n, const uint8_t *commi
     return BPPP_OK;
 }
 
+
+// ---- phase-stepped verify for a caller-owned transcript (include/bppp.h) -------------------------------------------
+// The same kernels as verify_part, cut at the transcript's challenge points: every step returns the compressed points
+// the host has to append (those it does not already hold) and takes the challenges it drew.
+static int step_check(bppp_ctx *c, int kind, int stage, const char *what) {
+    if (!c) return fail(BPPP_ERR_ARG, "null context");
+    if (c->step.kind != kind || c->step.stage != stage) return fail(BPPP_ERR_ARG, std::string(what) + ": called out of order for this context's stepped session");
+    return BPPP_OK;
+}
+extern "C" int bppp_u64_verify_begin(bppp_ctx *c, size_t n, const uint8_t *commits, const uint8_t *proofs, int fmt, uint8_t *vprime33_out) {
+    if (!c || !n || !commits || !proofs || !vprime33_out) return fail(BPPP_ERR_ARG, "null argument");
+    if (fmt != FMT_COMPRESSED && fmt != FMT_AFFINE64) return fail(BPPP_ERR_ARG, "bad point format");
+    if (n > c->max_batch) return fail(BPPP_ERR_ARG, "a stepped session holds at most max_batch proofs");
+    std::lock_guard<std::mutex> lock(c->mu);
+    CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    c->step = {}; c->active_parts = 1;
+    const size_t csz = fmt == FMT_COMPRESSED ? 33 : 64, psz = fmt == FMT_COMPRESSED ? U64_PROOF_BYTES_COMPRESSED : U64_PROOF_BYTES_AFFINE;
+    WS w{c->d_ws, n};
+    uint32_t *flags = w.p + (size_t)VL::IDMASK * w.n;
+    CUDA_OK(cudaMemcpyAsync(c->d_in_a, commits, csz * n, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(c->d_in_b, proofs, psz * n, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n, st));
+    LAUNCH(c, k_v_decode, nblocks(n * VP_COUNT, 128), 128, w, c->d_in_a, c->d_in_b, fmt, flags);
+    LAUNCH(c, k_v_load_finish, nblocks(n, 64), 64, w, c->d_in_b, fmt, flags);
+    launch_batch_inv(c, st, w, VL::VP + 2 * FE_W, VL::ZINV);
+    EmitList L; L.n = 1; L.pt[0] = VL::VP; L.zinv[0] = VL::ZINV;     // V' = V + r: "commitment_v" (circuit.rs:159)
+    launch_emit_points(c, st, w, L, c->d_out);
+    CUDA_OK(cudaMemcpyAsync(vprime33_out, c->d_out, 33 * n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaGetLastError());
+    c->step.kind = 1; c->step.n = n; c->step.stage = 1; c->step.fmt = fmt;
+    return BPPP_OK;
+}
+extern "C" int bppp_u64_verify_circuit(bppp_ctx *c, const uint8_t *chal, uint8_t *com33_out) {
+    int rc = step_check(c, 1, 1, "bppp_u64_verify_circuit");
+    if (rc != BPPP_OK) return rc;
+    if (!chal || !com33_out) return fail(BPPP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lock(c->mu);
+    CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t n = c->step.n;
+    WS w{c->d_ws, n};
+    Merlin unused{};
+    CUDA_OK(cudaMemcpyAsync(c->d_in_c, chal, 192 * n, cudaMemcpyHostToDevice, st));
+    LAUNCH(c, k_v_phase1, nblocks(n, 64), 64, w, unused, (const uint8_t *)c->d_in_c, 192);
+    LAUNCH(c, k_v_tables_build, nblocks(n * VL::TAB_POINTS, 64), 64, w);
+    size_t items = n * VL::TAB_ENTRIES, nthreads = (items + 63) / 64;
+    LAUNCH(c, k_v_tables_normalize, nblocks(nthreads, 128), 128, w, nthreads);
+    TermMap tm = identity_map();
+    launch_msm_fixed(c, st, w, VL::FS, tm, 17, VL::ACC);
+    launch_v_var5(c, st, w);
+    launch_batch_inv(c, st, w, VL::COM + 2 * FE_W, VL::ZINV);
+    EmitList L; L.n = 1; L.pt[0] = VL::COM; L.zinv[0] = VL::ZINV;    // "wnla_com" of round 0 (wnla.rs:88)
+    launch_emit_points(c, st, w, L, c->d_out);
+    CUDA_OK(cudaMemcpyAsync(com33_out, c->d_out, 33 * n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaGetLastError());
+    c->step.stage = 2;
+    return BPPP_OK;
+}
+extern "C" int bppp_u64_verify_round(bppp_ctx *c, int j, const uint8_t *y32, uint8_t *com33_out) {
+    if (j < 0 || j > 3) return fail(BPPP_ERR_ARG, "round index out of range");
+    int rc = step_check(c, 1, 2 + j, "bppp_u64_verify_round");
+    if (rc != BPPP_OK) return rc;
+    if (!y32 || (j < 3 && !com33_out)) return fail(BPPP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lock(c->mu);
+    CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t n = c->step.n;
+    WS w{c->d_ws, n};
+    CUDA_OK(cudaMemcpyAsync(c->d_in_c, y32, 32 * n, cudaMemcpyHostToDevice, st));
+    LAUNCH(c, k_v_round, nblocks(n, 64), 64, w, j, (const uint8_t *)c->d_in_c, 32);
+    launch_v_var2(c, st, w, j);
+    if (j < 3) {
+        launch_batch_inv(c, st, w, VL::COM + 2 * FE_W, VL::ZINV);
+        EmitList L; L.n = 1; L.pt[0] = VL::COM; L.zinv[0] = VL::ZINV;
+        launch_emit_points(c, st, w, L, c->d_out);
+        CUDA_OK(cudaMemcpyAsync(com33_out, c->d_out, 33 * n, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaGetLastError());
+    c->step.stage = 3 + j;
+    return BPPP_OK;
+}
+extern "C" int bppp_u64_verify_finish(bppp_ctx *c, int32_t *status) {
+    int rc = step_check(c, 1, 6, "bppp_u64_verify_finish");
+    if (rc != BPPP_OK) return rc;
+    if (!status) return fail(BPPP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lock(c->mu);
+    CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t n = c->step.n;
+    WS w{c->d_ws, n};
+    TermMap tm = identity_map();
+    LAUNCH(c, k_v_final_scalars, nblocks(n, 64), 64, w);
+    launch_msm_fixed(c, st, w, VL::FS, tm, NUM_GENS, VL::ACC);
+    LAUNCH(c, k_v_verdict, nblocks(n, 64), 64, w, c->d_status);
+    CUDA_OK(cudaMemcpyAsync(status, c->d_status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaGetLastError());
+    c->step = {};
+    return BPPP_OK;
+}
+extern "C" void bppp_u64_step_abort(bppp_ctx *c) { if (c) { std::lock_guard<std::mutex> lock(c->mu); c->step = {}; } }

@@ -140,13 +140,13 @@ BPPP_HD PtA u64p_affine(const WS &w, size_t i, int slot, int po, bool &id) {
 }
 
 // Phase 1 (reciprocal.rs:114-122; circuit.rs:264-345): e, reciprocals, blinders, scalars of r_com, c_o, c_l, c_r
-BPPP_HD void u64p_phase1_one(const WS &w, size_t i, const Merlin &init, const uint8_t *rng) {
-    Merlin m = init;
+BPPP_HD void u64p_phase1_one(const WS &w, size_t i, const Merlin &init, const uint8_t *rng, const uint8_t *ext = nullptr) {
+    Tx m; tx_init(m, init, ext);      // ext: e
     bool id, bad = false, zero_inv = false;
     PtA V = u64p_affine(w, i, PP_V, -1, id);
-    merlin_append_point(m, BPPP_LBL("reciprocal_commitment"), V, id);
-    Sc e; bad |= !merlin_challenge_scalar(m, BPPP_LBL("reciprocal_challenge"), e);
-    ws_st_merlin(w, i, PL::MERLIN, m);
+    tx_point(m, BPPP_LBL("reciprocal_commitment"), V, id);
+    Sc e; bad |= !tx_challenge(m, BPPP_LBL("reciprocal_challenge"), e);
+    tx_store(m, w, i, PL::MERLIN);
     ws_st_sc(w, i, PL::E, e);
     // 1/(e + j), j < 16: the 16 distinct inverses behind both r_i = 1/(d_i + e) (reciprocal.rs:117-119)
     // and W_l's pole columns (reciprocal.rs:179-183).  One inversion (Montgomery's trick).
@@ -214,21 +214,21 @@ BPPP_HD void u64_circuit_coefs(CircuitCoefs &cc, const WS &w, size_t i, const Sc
 }
 
 // Phase 2 (circuit.rs:347-470): rho, lambda, beta, delta; ls, ns; f_[0..8); rs; scalars of c_s
-BPPP_HD void u64p_phase2_one(const WS &w, size_t i, const uint8_t *rng) {
-    Merlin m; ws_ld_merlin(m, w, i, PL::MERLIN);
+BPPP_HD void u64p_phase2_one(const WS &w, size_t i, const uint8_t *rng, const uint8_t *ext = nullptr) {
+    Tx m; tx_load(m, w, i, PL::MERLIN, ext);      // ext: rho, lambda, beta, delta
     bool id, bad = false, zero_inv = false;
     PtA a;
-    a = u64p_affine(w, i, PP_CL, PO_CL, id); merlin_append_point(m, BPPP_LBL("commitment_cl"), a, id);
-    a = u64p_affine(w, i, PP_CR, PO_CR, id); merlin_append_point(m, BPPP_LBL("commitment_cr"), a, id);
-    a = u64p_affine(w, i, PP_CO, PO_CO, id); merlin_append_point(m, BPPP_LBL("commitment_co"), a, id);
-    a = u64p_affine(w, i, PP_VP, -1, id);    merlin_append_point(m, BPPP_LBL("commitment_v"), a, id);
+    a = u64p_affine(w, i, PP_CL, PO_CL, id); tx_point(m, BPPP_LBL("commitment_cl"), a, id);
+    a = u64p_affine(w, i, PP_CR, PO_CR, id); tx_point(m, BPPP_LBL("commitment_cr"), a, id);
+    a = u64p_affine(w, i, PP_CO, PO_CO, id); tx_point(m, BPPP_LBL("commitment_co"), a, id);
+    a = u64p_affine(w, i, PP_VP, -1, id);    tx_point(m, BPPP_LBL("commitment_v"), a, id);
     (void)u64p_affine(w, i, PP_RCOM, PO_RCOM, id);
     Sc rho, lambda, beta, delta;
-    bad |= !merlin_challenge_scalar(m, BPPP_LBL("circuit_rho"), rho);
-    bad |= !merlin_challenge_scalar(m, BPPP_LBL("circuit_lambda"), lambda);
-    bad |= !merlin_challenge_scalar(m, BPPP_LBL("circuit_beta"), beta);
-    bad |= !merlin_challenge_scalar(m, BPPP_LBL("circuit_delta"), delta);
-    ws_st_merlin(w, i, PL::MERLIN, m);
+    bad |= !tx_challenge(m, BPPP_LBL("circuit_rho"), rho);
+    bad |= !tx_challenge(m, BPPP_LBL("circuit_lambda"), lambda);
+    bad |= !tx_challenge(m, BPPP_LBL("circuit_beta"), beta);
+    bad |= !tx_challenge(m, BPPP_LBL("circuit_delta"), delta);
+    tx_store(m, w, i, PL::MERLIN);
     // draws 20..52: ls (17), ns (16)   (circuit.rs:371-372)
 #pragma unroll 1
     for (int k = 19; k < 52; k++) ws_st_sc(w, i, PL::RND + 8 * k, sc_from_wide_be64(rng + 64 * k));
@@ -368,14 +368,14 @@ BPPP_HD void u64p_xr_scalars(const WS &w, size_t i, int j) {
 }
 
 // Phase 3 (circuit.rs:472-533): tau; l, n, c; scalars of the WNLA commitment C_0 and of X_0, R_0
-BPPP_HD void u64p_phase3_one(const WS &w, size_t i) {
-    Merlin m; ws_ld_merlin(m, w, i, PL::MERLIN);
+BPPP_HD void u64p_phase3_one(const WS &w, size_t i, const uint8_t *ext = nullptr) {
+    Tx m; tx_load(m, w, i, PL::MERLIN, ext);      // ext: tau
     bool id;
     PtA cs = u64p_affine(w, i, PP_CS, PO_CS, id);
-    merlin_append_point(m, BPPP_LBL("commitment_cs"), cs, id);
+    tx_point(m, BPPP_LBL("commitment_cs"), cs, id);
     Sc tau;
-    if (!merlin_challenge_scalar(m, BPPP_LBL("circuit_tau"), tau)) pset_status(w, i, ST_PANIC_CHALLENGE_RANGE);
-    ws_st_merlin(w, i, PL::MERLIN, m);
+    if (!tx_challenge(m, BPPP_LBL("circuit_tau"), tau)) pset_status(w, i, ST_PANIC_CHALLENGE_RANGE);
+    tx_store(m, w, i, PL::MERLIN);
     if (sc_is_zero(tau)) { pset_status(w, i, ST_PANIC_INVERT_ZERO); tau = sc_one(); }
     Sc tau_inv = sc_inv(tau), tau2 = sc_sqr(tau), tau3 = sc_mul(tau2, tau);
     Sc e = ws_ld_sc(w, i, PL::E), lambda = ws_ld_sc(w, i, PL::LAMBDA), mu = ws_ld_sc(w, i, PL::MU);
@@ -449,19 +449,19 @@ BPPP_HD void u64p_phase3_one(const WS &w, size_t i) {
 }
 
 // WNLA round j (wnla.rs:162-175): transcript -> y_j; fold l, n, c; scalars of the next round's X, R
-BPPP_HD void u64p_round_one(const WS &w, size_t i, int j) {
-    Merlin m; ws_ld_merlin(m, w, i, PL::MERLIN);
+BPPP_HD void u64p_round_one(const WS &w, size_t i, int j, const uint8_t *ext = nullptr) {
+    Tx m; tx_load(m, w, i, PL::MERLIN, ext);      // ext: y_j
     bool id;
     PtA a;
-    a = u64p_affine(w, i, PP_COM, -1, id);           merlin_append_point(m, BPPP_LBL("wnla_com"), a, id);
-    a = u64p_affine(w, i, PP_X + j, PO_X + (3 - j), id); merlin_append_point(m, BPPP_LBL("wnla_x"), a, id);
-    a = u64p_affine(w, i, PP_R + j, PO_R + (3 - j), id); merlin_append_point(m, BPPP_LBL("wnla_r"), a, id);
+    a = u64p_affine(w, i, PP_COM, -1, id);           tx_point(m, BPPP_LBL("wnla_com"), a, id);
+    a = u64p_affine(w, i, PP_X + j, PO_X + (3 - j), id); tx_point(m, BPPP_LBL("wnla_x"), a, id);
+    a = u64p_affine(w, i, PP_R + j, PO_R + (3 - j), id); tx_point(m, BPPP_LBL("wnla_r"), a, id);
     const int Lh = 32 >> j, Lg = 16 >> j;
-    merlin_append_u64(m, BPPP_LBL("l.sz"), (uint64_t)Lh);    // l.len() (wnla.rs:165)
-    merlin_append_u64(m, BPPP_LBL("n.sz"), (uint64_t)Lg);
+    tx_u64(m, BPPP_LBL("l.sz"), (uint64_t)Lh);    // l.len() (wnla.rs:165)
+    tx_u64(m, BPPP_LBL("n.sz"), (uint64_t)Lg);
     Sc y;
-    if (!merlin_challenge_scalar(m, BPPP_LBL("wnla_challenge"), y)) pset_status(w, i, ST_PANIC_CHALLENGE_RANGE);
-    ws_st_merlin(w, i, PL::MERLIN, m);
+    if (!tx_challenge(m, BPPP_LBL("wnla_challenge"), y)) pset_status(w, i, ST_PANIC_CHALLENGE_RANGE);
+    tx_store(m, w, i, PL::MERLIN);
     ws_st_sc(w, i, PL::Y + 8 * j, y);
     Sc rho_inv_j = ws_ld_sc(w, i, PL::RHOINV);
 #pragma unroll 1

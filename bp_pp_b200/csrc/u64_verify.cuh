@@ -143,33 +143,33 @@ BPPP_HD PtA ws_affine(const WS &w, size_t i, int pt_off, int zinv_off, bool &is_
 
 // Phase 1: transcript up to tau, all challenge-derived scalars for the circuit part.
 // reciprocal.rs:99-100; circuit.rs:155-239 (closed forms, see header).
-BPPP_HD void u64v_phase1_one(const WS &w, size_t i, const Merlin &init) {
-    Merlin m = init;
+BPPP_HD void u64v_phase1_one(const WS &w, size_t i, const Merlin &init, const uint8_t *ext = nullptr) {
+    Tx m; tx_init(m, init, ext);      // ext: e, rho, lambda, beta, delta, tau from a caller-owned transcript
     uint32_t idmask = ws_ld(w, i, VL::IDMASK);
     bool bad = false, zero_inv = false;
     // reciprocal.rs:99-100
     PtA V = ws_ld_pta(w, i, VL::PT + 16 * VP_V);
-    merlin_append_point(m, BPPP_LBL("reciprocal_commitment"), V, idmask & (1u << VP_V));
-    Sc e; bad |= !merlin_challenge_scalar(m, BPPP_LBL("reciprocal_challenge"), e);
+    tx_point(m, BPPP_LBL("reciprocal_commitment"), V, idmask & (1u << VP_V));
+    Sc e; bad |= !tx_challenge(m, BPPP_LBL("reciprocal_challenge"), e);
     // circuit.rs:155-164
     bool vp_id;
     PtA vpa = ws_affine(w, i, VL::VP, VL::ZINV, vp_id);
     ws_st_pta(w, i, VL::VPA, vpa);
     if (vp_id) idmask |= 1u << 14;
     ws_st(w, i, VL::IDMASK, idmask);
-    merlin_append_point(m, BPPP_LBL("commitment_cl"), ws_ld_pta(w, i, VL::PT + 16 * VP_CL), idmask & (1u << VP_CL));
-    merlin_append_point(m, BPPP_LBL("commitment_cr"), ws_ld_pta(w, i, VL::PT + 16 * VP_CR), idmask & (1u << VP_CR));
-    merlin_append_point(m, BPPP_LBL("commitment_co"), ws_ld_pta(w, i, VL::PT + 16 * VP_CO), idmask & (1u << VP_CO));
-    merlin_append_point(m, BPPP_LBL("commitment_v"), vpa, vp_id);
+    tx_point(m, BPPP_LBL("commitment_cl"), ws_ld_pta(w, i, VL::PT + 16 * VP_CL), idmask & (1u << VP_CL));
+    tx_point(m, BPPP_LBL("commitment_cr"), ws_ld_pta(w, i, VL::PT + 16 * VP_CR), idmask & (1u << VP_CR));
+    tx_point(m, BPPP_LBL("commitment_co"), ws_ld_pta(w, i, VL::PT + 16 * VP_CO), idmask & (1u << VP_CO));
+    tx_point(m, BPPP_LBL("commitment_v"), vpa, vp_id);
     Sc rho, lambda, beta, delta, tau;
-    bad |= !merlin_challenge_scalar(m, BPPP_LBL("circuit_rho"), rho);
-    bad |= !merlin_challenge_scalar(m, BPPP_LBL("circuit_lambda"), lambda);
-    bad |= !merlin_challenge_scalar(m, BPPP_LBL("circuit_beta"), beta);
-    bad |= !merlin_challenge_scalar(m, BPPP_LBL("circuit_delta"), delta);
+    bad |= !tx_challenge(m, BPPP_LBL("circuit_rho"), rho);
+    bad |= !tx_challenge(m, BPPP_LBL("circuit_lambda"), lambda);
+    bad |= !tx_challenge(m, BPPP_LBL("circuit_beta"), beta);
+    bad |= !tx_challenge(m, BPPP_LBL("circuit_delta"), delta);
     // circuit.rs:189-191
-    merlin_append_point(m, BPPP_LBL("commitment_cs"), ws_ld_pta(w, i, VL::PT + 16 * VP_CS), idmask & (1u << VP_CS));
-    bad |= !merlin_challenge_scalar(m, BPPP_LBL("circuit_tau"), tau);
-    ws_st_merlin(w, i, VL::MERLIN, m);
+    tx_point(m, BPPP_LBL("commitment_cs"), ws_ld_pta(w, i, VL::PT + 16 * VP_CS), idmask & (1u << VP_CS));
+    bad |= !tx_challenge(m, BPPP_LBL("circuit_tau"), tau);
+    tx_store(m, w, i, VL::MERLIN);
 
     Sc mu = sc_sqr(rho);
     // One inversion for {mu, tau, e+0 .. e+15} (Montgomery's trick); delta only has to be non-zero
@@ -360,20 +360,20 @@ BPPP_HD Pt u64v_var5_partial(const WS &w, size_t i, int lane, int nlanes) {
 }
 
 // WNLA round j = 0..3 (wnla.rs:84-102): transcript -> y_j, fold c, scalars for com' = com + y X + (y^2-1) R
-BPPP_HD void u64v_round_one(const WS &w, size_t i, int j) {
-    Merlin m; ws_ld_merlin(m, w, i, VL::MERLIN);
+BPPP_HD void u64v_round_one(const WS &w, size_t i, int j, const uint8_t *ext = nullptr) {
+    Tx m; tx_load(m, w, i, VL::MERLIN, ext);      // ext: y_j
     uint32_t idmask = ws_ld(w, i, VL::IDMASK);
     bool com_id;
     PtA com = ws_affine(w, i, VL::COM, VL::ZINV, com_id);
     const int xs = VP_X + (3 - j), rs = VP_R + (3 - j);     // proof.x.last(), proof.r.last() (wnla.rs:89-90)
-    merlin_append_point(m, BPPP_LBL("wnla_com"), com, com_id);
-    merlin_append_point(m, BPPP_LBL("wnla_x"), ws_ld_pta(w, i, VL::PT + 16 * xs), idmask & (1u << xs));
-    merlin_append_point(m, BPPP_LBL("wnla_r"), ws_ld_pta(w, i, VL::PT + 16 * rs), idmask & (1u << rs));
-    merlin_append_u64(m, BPPP_LBL("l.sz"), (uint64_t)(32 >> j));    // |h_vec| (wnla.rs:91)
-    merlin_append_u64(m, BPPP_LBL("n.sz"), (uint64_t)(16 >> j));    // |g_vec| (wnla.rs:92)
+    tx_point(m, BPPP_LBL("wnla_com"), com, com_id);
+    tx_point(m, BPPP_LBL("wnla_x"), ws_ld_pta(w, i, VL::PT + 16 * xs), idmask & (1u << xs));
+    tx_point(m, BPPP_LBL("wnla_r"), ws_ld_pta(w, i, VL::PT + 16 * rs), idmask & (1u << rs));
+    tx_u64(m, BPPP_LBL("l.sz"), (uint64_t)(32 >> j));    // |h_vec| (wnla.rs:91)
+    tx_u64(m, BPPP_LBL("n.sz"), (uint64_t)(16 >> j));    // |g_vec| (wnla.rs:92)
     Sc y;
-    if (!merlin_challenge_scalar(m, BPPP_LBL("wnla_challenge"), y)) set_status(w, i, ST_PANIC_CHALLENGE_RANGE);
-    ws_st_merlin(w, i, VL::MERLIN, m);
+    if (!tx_challenge(m, BPPP_LBL("wnla_challenge"), y)) set_status(w, i, ST_PANIC_CHALLENGE_RANGE);
+    tx_store(m, w, i, VL::MERLIN);
     ws_st_sc(w, i, VL::Y + 8 * j, y);
     const int half = (32 >> j) / 2;
 #pragma unroll 1

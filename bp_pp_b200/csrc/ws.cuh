@@ -72,6 +72,29 @@ BPPP_HD bool merlin_challenge_scalar(Merlin &m, const char *label, uint32_t labe
     return sc_from_be32(out, b);
 }
 
+// Transcript endpoint of one proof within one phase.
+//  * internal (ext == nullptr): the device-side Merlin of the batch entry points, which own a fresh Transcript::new(label);
+//  * external: the CALLER owns the merlin::Transcript (the reference's single-instance signatures take `t: &mut Transcript`
+//    with arbitrary prior state, and merlin keeps its STROBE state private).  The host was handed the bytes of the points
+//    this phase appends by the previous step and did the appends itself, so appends are no-ops here and the phase's
+//    challenges are read, in order, from `ext` (32 bytes big-endian each).
+struct Tx {
+    Merlin m;
+    const uint8_t *ext;
+    int k;
+};
+BPPP_HD void tx_init(Tx &t, const Merlin &init, const uint8_t *ext) { t.ext = ext; t.k = 0; if (!ext) t.m = init; }
+BPPP_HD void tx_load(Tx &t, const WS &w, size_t i, int off, const uint8_t *ext) { t.ext = ext; t.k = 0; if (!ext) ws_ld_merlin(t.m, w, i, off); }
+BPPP_HD void tx_store(const Tx &t, const WS &w, size_t i, int off) { if (!t.ext) ws_st_merlin(w, i, off, t.m); }
+BPPP_HD void tx_point(Tx &t, const char *label, uint32_t label_len, const PtA &a_canonical, bool is_identity) {
+    if (!t.ext) merlin_append_point(t.m, label, label_len, a_canonical, is_identity);
+}
+BPPP_HD void tx_u64(Tx &t, const char *label, uint32_t label_len, uint64_t v) { if (!t.ext) merlin_append_u64(t.m, label, label_len, v); }
+BPPP_HD bool tx_challenge(Tx &t, const char *label, uint32_t label_len, Sc &out) {
+    if (t.ext) return sc_from_be32(out, t.ext + 32 * t.k++);
+    return merlin_challenge_scalar(t.m, label, label_len, out);
+}
+
 // status codes shared by the device code and the C ABI (include/bppp.h)
 enum : int32_t {
     ST_FALSE = 0, ST_TRUE = 1,

@@ -79,6 +79,9 @@ int bppp_ctx_create(bppp_ctx **out, int device, const uint8_t *gens64, int windo
  * side by side, which keeps the GPU full when each batch is small (a rank's 1/8 share of a 65,536 batch).  The parent
  * must outlive every context that shares its tables. */
 int bppp_ctx_create_shared(bppp_ctx **out, const bppp_ctx *parent, size_t max_batch);
+/* Hint: the caller keeps `batches` independent batches in flight on this GPU (sibling contexts).  Only affects how many
+ * lanes per proof the kernels use for small batches (results are identical for every choice). */
+int bppp_ctx_set_inflight(bppp_ctx *ctx, int batches);
 void bppp_ctx_destroy(bppp_ctx *ctx);
 const char *bppp_last_error(void);
 /* bytes of device memory held by the context (tables + workspace), build time of the tables in ms */
@@ -101,8 +104,51 @@ int bppp_u64_prove_batch(bppp_ctx *ctx, size_t n, const uint64_t *x, const uint8
 int bppp_u64_prove_batch_dev(bppp_ctx *ctx, size_t n, const void *d_x, const void *d_blinds32, const void *d_rng,
                              const uint8_t *label, size_t label_len, void *d_proofs_out, void *d_status, void *stream);
 
+/* ---- phase-stepped variants for a CALLER-OWNED transcript -------------------------------------------------------------
+ * The reference's single-instance signatures take `t: &mut merlin::Transcript` in whatever state the caller left it
+ * (src/range_proof/u64_proof.rs:42,57; src/range_proof/reciprocal.rs:98,110; src/circuit.rs:154,260; src/wnla.rs:75,125)
+ * and merlin keeps its STROBE state private, so a shim cannot hand the transcript to the device.  These entry points cut
+ * the same kernel sequences at the transcript's challenge points: every step RETURNS the
+ * 33-byte compressed points the host must `app_point` next (those it does not already hold) and TAKES the challenges
+ * it then drew with `get_challenge` (32 bytes big-endian each).  n independent instances advance together (n = 1 for
+ * the reference's signatures); all per-step arrays are proof-major.  One stepped session per context at a time, calls
+ * in the order listed, synchronous; bppp_u64_step_abort drops a half-finished session.
+ *
+ * verify: host appends reciprocal_commitment V -> e; commitment_cl/cr/co from the proof and commitment_v = V' (returned by
+ *   _begin) -> rho, lambda, beta, delta; commitment_cs -> tau; then per WNLA round j: wnla_com (returned), wnla_x, wnla_r
+ *   from the proof (x[3-j], r[3-j]), l.sz = 32 >> j, n.sz = 16 >> j -> y_j. */
+int bppp_u64_verify_begin(bppp_ctx *ctx, size_t n, const uint8_t *commits, const uint8_t *proofs, int fmt, uint8_t *vprime33_out);
+int bppp_u64_verify_circuit(bppp_ctx *ctx, const uint8_t *chal /* n x 6 x 32: e rho lambda beta delta tau */, uint8_t *com33_out /* n x 33: wnla_com of round 0 */);
+int bppp_u64_verify_round(bppp_ctx *ctx, int j, const uint8_t *y32 /* n x 32 */, uint8_t *com33_out /* j < 3: wnla_com of round j + 1; j == 3: unused */);
+int bppp_u64_verify_finish(bppp_ctx *ctx, int32_t *status);
+/* prove: _begin returns V (reciprocal_commitment) -> e; _reciprocal returns commitment_cl, cr, co, v -> rho, lambda, beta,
+ *   delta; _circuit returns commitment_cs -> tau; _tau returns wnla_com, wnla_x, wnla_r of round 0 -> y_0; _round(j) returns
+ *   those of round j + 1 (nothing for j == 3); _finish writes the 525-byte records.  rng as in bppp_u64_prove_batch. */
+int bppp_u64_prove_begin(bppp_ctx *ctx, size_t n, const uint64_t *x, const uint8_t *blinds32, const uint8_t *rng, uint8_t *v33_out);
+int bppp_u64_prove_reciprocal(bppp_ctx *ctx, const uint8_t *e32 /* n x 32 */, uint8_t *pts33_out /* n x 4 x 33 */);
+int bppp_u64_prove_circuit(bppp_ctx *ctx, const uint8_t *chal /* n x 4 x 32: rho lambda beta delta */, uint8_t *cs33_out /* n x 33 */);
+int bppp_u64_prove_tau(bppp_ctx *ctx, const uint8_t *tau32 /* n x 32 */, uint8_t *pts33_out /* n x 3 x 33: com X_0 R_0 */);
+int bppp_u64_prove_round(bppp_ctx *ctx, int j, const uint8_t *y32 /* n x 32 */, uint8_t *pts33_out /* j < 3: n x 3 x 33: com X_{j+1} R_{j+1} */);
+int bppp_u64_prove_finish(bppp_ctx *ctx, uint8_t *proofs_out, int32_t *status);
+void bppp_u64_step_abort(bppp_ctx *ctx);
+
 /* number of kernels launched by this context since creation (for the bench's gpu_launches claim) */
 uint64_t bppp_launch_count(const bppp_ctx *ctx);
+
+/* ---- one process, several GPUs ---------------------------------------------------------------------------------------
+ * A bppp_multi_ctx owns one context per listed CUDA device (generators and tables replicated); each batch call
+ * cuts [0, n) into contiguous per-device ranges, one host thread per device, no data-path collective.  The result for
+ * proof i is independent of the device list.  Arguments as for the single-device entry points (host buffers). */
+typedef struct bppp_multi_ctx bppp_multi_ctx;
+int bppp_multi_ctx_create(bppp_multi_ctx **out, const int *devices, int ndev, const uint8_t *gens64, int window_bits, size_t max_batch_per_device);
+void bppp_multi_ctx_destroy(bppp_multi_ctx *m);
+int bppp_multi_device_count(const bppp_multi_ctx *m);
+bppp_ctx *bppp_multi_ctx_get(const bppp_multi_ctx *m, int k);      /* the k-th device's context (owned by m) */
+int bppp_multi_u64_commit_batch(bppp_multi_ctx *m, size_t n, const uint64_t *x, const uint8_t *blinds32, int fmt, uint8_t *out);
+int bppp_multi_u64_verify_batch(bppp_multi_ctx *m, size_t n, const uint8_t *commits, const uint8_t *proofs, int fmt,
+                                const uint8_t *label, size_t label_len, int32_t *status);
+int bppp_multi_u64_prove_batch(bppp_multi_ctx *m, size_t n, const uint64_t *x, const uint8_t *blinds32, const uint8_t *rng,
+                               const uint8_t *label, size_t label_len, uint8_t *proofs_out, int32_t *status);
 
 /* ---- generic (arbitrary-size, single-instance) entry points ------------------------------------------------ */
 

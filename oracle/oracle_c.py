@@ -298,3 +298,9 @@ def bench_point_mul(p64, k32, iters):
     out = _out(64)
     lib().oracle_bench_point_mul(_buf(p64), _buf(k32), C.c_int(iters), out)
     return bytes(out)
+
+
+def bench_sc_inv(a32, iters):
+    out = _out(32)
+    lib().oracle_bench_sc_inv(_buf(a32), C.c_int(iters), out)
+    return bytes(out)

@@ -329,3 +329,54 @@ def test_shared_table_contexts_run_side_by_side(ctx, batch):
         assert proofs == batch["proofs"] and st == [1] * n and verdicts == [1] * n
     for c in others:
         c.close()
+
+
+def test_full_batch_matches_the_oracle_block_hashes(gens64):
+    """BASELINE configs 2/3 at FULL size against the C oracle: all 65,536 commitments and proofs (sha256 per 4,096-proof
+    block) and the complete verdict vector of the 8-rule tampered batch, from tests/golden/u64_batch_golden.json
+    (generated by tests/golden/make_batch_golden.py with the oracle on all host cores)."""
+    import json
+    import hashlib
+    import bp_pp_b200 as B
+    from bp_pp_b200 import synth
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "u64_batch_golden.json")))
+    n = gold["n"]
+    assert hashlib.sha256(gens64).hexdigest() == gold["generators_sha256"]
+    assert synth.synth_generators64(0) == gens64             # the product-side generator synthesis is the oracle's
+    ctx = B.Context(gens64, 0, 16, n)
+    xs, blinds, rng = synth.synth_batch(n)
+    commits = ctx.commit_batch(xs.tolist(), blinds.tobytes())
+    assert synth.block_hashes(commits, 33) == gold["commit_block_sha256"]
+    proofs, st = ctx.prove_batch(xs.tolist(), blinds.tobytes(), rng.tobytes(), LABEL)
+    assert st == [1] * n
+    assert synth.block_hashes(proofs, 525) == gold["proof_block_sha256"]
+    bad, bcom, idx = synth.tamper_batch(proofs, commits, synth.engine_add_g(0))
+    assert synth.block_hashes(bad, 525) == gold["tampered_proof_block_sha256"]
+    assert synth.block_hashes(bcom, 33) == gold["tampered_commit_block_sha256"]
+    verdicts = ctx.verify_batch(bcom, bad, LABEL)
+    expect = [1] * n
+    for i, v in zip(idx, gold["tampered_verdicts"]):
+        expect[i] = v
+    assert verdicts == expect
+    ctx.close()
+
+
+def test_multi_context_in_one_process(gens64, batch):
+    """bppp_multi_ctx: one process, a list of devices (here the visible GPUs, or GPU 0 three times when there is only
+    one -- three contexts, three host threads, same splitting logic): results must not depend on the device list."""
+    import torch
+    import bp_pp_b200 as B
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0, 0]
+    m = B.MultiContext(gens64, devices, 8, 64)          # max_batch 64 per device: 384 proofs also exercise slicing
+    n = batch["n"]
+    assert m.commit_batch(batch["xs"], batch["blinds"]) == batch["commits"]
+    proofs, st = m.prove_batch(batch["xs"], batch["blinds"], batch["rngs"], LABEL)
+    assert proofs == batch["proofs"] and st == [1] * n
+    bad = bytearray(proofs)
+    for i in range(0, n, 5):
+        bad[525 * i + 430] ^= 2
+    exp = [0 if i % 5 == 0 else 1 for i in range(n)]
+    assert m.verify_batch(batch["commits"], bytes(bad), LABEL) == exp
+    assert m.verify_batch(batch["commits"][:33 * 2], proofs[:525 * 2], LABEL) == [1, 1]      # fewer proofs than devices
+    m.close()

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--window-bits", type=int, default=20)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--lane-sweep", action="store_true", help="time every (ladder lanes, fixed-base lanes) override at every size")
     ap.add_argument("--inflight", default="1,2,4,8", help="independent batches in flight (one shared-table context and stream each)")
     args = ap.parse_args()
     sizes = [int(s) for s in args.sizes.split(",")]
@@ -83,6 +84,28 @@ def main():
             rec["kernels_verify_ms"] = {k: [round(ms, 3), c] for k, (ms, c) in sorted(pv.items(), key=lambda kv: -kv[1][0])}
             rec["kernels_prove_ms"] = {k: [round(ms, 3), c] for k, (ms, c) in sorted(pp.items(), key=lambda kv: -kv[1][0])}
         out["sizes"][str(n)] = rec
+    if args.lane_sweep:
+        out["lane_sweep"] = {}
+        for vl, ml in [(1, 4), (2, 4), (4, 4), (1, 8), (1, 16), (2, 8), (4, 8), (4, 16)]:
+            os.environ["BPPP_VAR_LANES_RT"], os.environ["BPPP_MSM_LANES_RT"] = str(vl), str(ml)
+            c2 = ctx.shared(nmax)
+            for n in sizes:
+                def t(step):
+                    for _ in range(2):
+                        step()
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    for _ in range(args.steps):
+                        step()
+                    e1.record(stream); e1.synchronize()
+                    return e0.elapsed_time(e1) / args.steps
+                v = t(lambda: c2.verify_batch_dev(n, d_commits.data_ptr(), d_proofs.data_ptr(), LABEL, d_status.data_ptr(), stream=stream.cuda_stream))
+                p = t(lambda: c2.prove_batch_dev(n, d_x.data_ptr(), d_blinds.data_ptr(), d_rng.data_ptr(), LABEL, d_out.data_ptr(), d_pst.data_ptr(),
+                                                 stream=stream.cuda_stream))
+                out["lane_sweep"][f"var{vl}_msm{ml}_n{n}"] = [round(v, 3), round(p, 3)]
+            c2.close()
+        del os.environ["BPPP_VAR_LANES_RT"], os.environ["BPPP_MSM_LANES_RT"]
     # ---- throughput with S independent batches in flight: S contexts sharing the tables, one stream each ----
     S_list = [int(v) for v in args.inflight.split(",") if int(v) > 1]
     smax = max(S_list) if S_list else 1
