@@ -22,6 +22,8 @@ EXPORTS = [
     "bppp_launch_count", "bppp_microbench", "bppp_ctx_profile_begin", "bppp_ctx_profile_end",
     "bppp_msm", "bppp_points_upload", "bppp_scalars_upload", "bppp_device_free", "bppp_msm_uploaded", "bppp_points_sum", "bppp_points_generate", "bppp_points_convert",
     "bppp_wnla_commit", "bppp_wnla_prove", "bppp_wnla_verify",
+    "bppp_wnla_shard_create", "bppp_wnla_shard_destroy", "bppp_wnla_shard_state", "bppp_wnla_shard_commit_partial", "bppp_wnla_shard_xr_partial",
+    "bppp_wnla_shard_fold", "bppp_wnla_shard_export",
     "bppp_circuit_commit", "bppp_circuit_prove", "bppp_circuit_verify",
     "bppp_reciprocal_commit_value", "bppp_reciprocal_prove", "bppp_reciprocal_verify",
 ]
@@ -49,6 +51,8 @@ def lib():
         L.bppp_multi_ctx_destroy.restype = None
         L.bppp_multi_ctx_get.restype = C.c_void_p
         L.bppp_multi_ctx_get.argtypes = [C.c_void_p, C.c_int]
+        L.bppp_wnla_shard_destroy.argtypes = [C.c_void_p]
+        L.bppp_wnla_shard_destroy.restype = None
         L.bppp_device_free.restype = None
         L.bppp_device_free.argtypes = [C.c_int, C.c_void_p]
         _lib = L

@@ -88,13 +88,14 @@ __global__ void k_wnla_xr_scalars(const uint32_t *l, const uint32_t *n, size_t L
 // per-block partial sums of
 //   out[0]: sum_i n[2i] n[2i+1] mu2^(i+1)   out[1]: sum_i c[2i] l[2i+1] + c[2i+1] l[2i]
 //   out[2]: sum_i n[2i+1]^2 mu2^(i+1)       out[3]: sum_i c[2i+1] l[2i+1]
-__global__ void __launch_bounds__(128) k_wnla_dots(const uint32_t *c, const uint32_t *l, const uint32_t *n, size_t Lh, size_t Lg, ScParam mu2_p, uint32_t *partials) {
+// goff: global index of this block's first (halved) n pair -- 0 for a whole instance, the block offset for a shard
+__global__ void __launch_bounds__(128) k_wnla_dots(const uint32_t *c, const uint32_t *l, const uint32_t *n, size_t Lh, size_t Lg, ScParam mu2_p, uint32_t *partials, size_t goff) {
     __shared__ uint32_t sh[4][128][8];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     Sc a0 = sc_zero(), a1 = sc_zero(), a2 = sc_zero(), a3 = sc_zero();
     if (2 * i + 1 < Lg) {
         Sc n0 = ld_sc8(n + 8 * (2 * i)), n1 = ld_sc8(n + 8 * (2 * i + 1));
-        Sc w = sc_pow_u64_dev(from_param(mu2_p), (uint64_t)i + 1);
+        Sc w = sc_pow_u64_dev(from_param(mu2_p), (uint64_t)(goff + i) + 1);
         Sc n1w = sc_mul(n1, w);
         a0 = sc_mul(n0, n1w); a2 = sc_mul(n1, n1w);
     }
@@ -114,12 +115,12 @@ __global__ void __launch_bounds__(128) k_wnla_dots(const uint32_t *c, const uint
     if (threadIdx.x < 4) st_sc8(partials + 8 * (4 * (size_t)blockIdx.x + threadIdx.x), ld_sc8(sh[threadIdx.x][0]));
 }
 // generic: per-block partial sums of  sum_i a[i] b[i]  and  sum_i n[i]^2 w^(i+1)   (wnla.commit's v)
-__global__ void __launch_bounds__(128) k_commit_dots(const uint32_t *c, const uint32_t *l, size_t Lcl, const uint32_t *n, size_t Ln, ScParam mu_p, uint32_t *partials) {
+__global__ void __launch_bounds__(128) k_commit_dots(const uint32_t *c, const uint32_t *l, size_t Lcl, const uint32_t *n, size_t Ln, ScParam mu_p, uint32_t *partials, size_t goff) {
     __shared__ uint32_t sh[2][128][8];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     Sc a0 = sc_zero(), a1 = sc_zero();
     if (i < Lcl) a0 = sc_mul(ld_sc8(c + 8 * i), ld_sc8(l + 8 * i));
-    if (i < Ln) { Sc v = ld_sc8(n + 8 * i); a1 = sc_mul(sc_sqr(v), sc_pow_u64_dev(from_param(mu_p), (uint64_t)i + 1)); }
+    if (i < Ln) { Sc v = ld_sc8(n + 8 * i); a1 = sc_mul(sc_sqr(v), sc_pow_u64_dev(from_param(mu_p), (uint64_t)(goff + i) + 1)); }
     st_sc8(sh[0][threadIdx.x], a0); st_sc8(sh[1][threadIdx.x], a1);
     __syncthreads();
     for (int s = 64; s >= 1; s >>= 1) {
@@ -267,7 +268,7 @@ int wnla_commit_dev(cudaStream_t st, const WnlaDev &w, const uint32_t *d_l, cons
     uint32_t *d_part = nullptr, *d_sc = nullptr;
     CUDA_OK(cudaMalloc(&d_part, 64 * (nblk ? nblk : 1)));
     CUDA_OK(cudaMalloc(&d_sc, 32 * (w.Lh + w.Lg + 1)));
-    if (nblk) WL(k_commit_dots, (unsigned)nblk, 128, w.c, d_l, w.Lh, d_n, w.Lg, to_param(w.mu), d_part);
+    if (nblk) WL(k_commit_dots, (unsigned)nblk, 128, w.c, d_l, w.Lh, d_n, w.Lg, to_param(w.mu), d_part, (size_t)0);
     Sc sums[2];
     int rc = sum_partials_to_host(st, d_part, nblk, 2, sums);
     if (rc != BPPP_OK) return rc;
@@ -298,7 +299,7 @@ int wnla_prove_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, ui
         size_t half = (std::max(Lh, Lg) + 1) / 2, nblk = (half + 127) / 128;
         CUDA_OK(cudaMalloc(&d_part, 128 * (nblk ? nblk : 1)));
         WL(k_wnla_xr_scalars, nblocks(Lh + Lg, 128), 128, d_l, d_n, Lh, Lg, to_param(w.rho), to_param(rho_inv), d_sx, d_sr);
-        if (nblk) WL(k_wnla_dots, (unsigned)nblk, 128, w.c, d_l, d_n, Lh, Lg, to_param(mu2), d_part);
+        if (nblk) WL(k_wnla_dots, (unsigned)nblk, 128, w.c, d_l, d_n, Lh, Lg, to_param(mu2), d_part, (size_t)0);
         Sc sums[4];
         rc = sum_partials_to_host(st, d_part, nblk, 4, sums);
         if (rc != BPPP_OK) break;
@@ -522,5 +523,191 @@ extern "C" int bppp_wnla_verify(int device, const uint8_t *g64, const uint8_t *g
     Merlin t; merlin_init(t, label, (uint32_t)label_len);
     rc = wnla_verify_dev(st, w, t, d_com30, r33, rn, x33, xn, l32, ln, n32, nn, verdict);
     cudaFree(d_com16); cudaFree(d_com30); w.release();
+    return rc;
+}
+
+
+// ---- a block of a standalone WNLA instance resident on one GPU (BASELINE config 5) ----------------------------
+// The generator index range is cut into contiguous blocks with even offsets, one per GPU.  Folding maps the pair
+// (2i, 2i + 1) to i (util.rs:7-22), so a block with an even offset and an even length folds locally; each round a block
+// contributes ONE partial point to X and one to R (its share of vx / vr rides on g inside the partial), the partials
+// of all blocks are added (the only exchange: 2 x 64 bytes per block per round) and every holder runs the identical
+// transcript.  A shard created with whole = 1 is the entire instance (odd lengths fold with the reference's zero
+// extension): that is also the stepped single-GPU prover for a caller-owned transcript.
+struct bppp_wnla_shard {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    size_t nh = 0, ng = 0, h_off = 0, g_off = 0;
+    int whole = 0;
+    uint32_t *pts[2] = {nullptr, nullptr};      // [H (nh) | G (ng) | g], 16 words each; ping-pong across folds
+    uint32_t *c[2] = {nullptr, nullptr}, *l[2] = {nullptr, nullptr}, *n[2] = {nullptr, nullptr};
+    uint32_t *sx = nullptr, *sr = nullptr, *part = nullptr, *out30 = nullptr;
+    int cur = 0;
+    Sc rho, mu;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+extern "C" void bppp_wnla_shard_destroy(bppp_wnla_shard *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    for (int k = 0; k < 2; k++) { cudaFree(s->pts[k]); cudaFree(s->c[k]); cudaFree(s->l[k]); cudaFree(s->n[k]); }
+    cudaFree(s->sx); cudaFree(s->sr); cudaFree(s->part); cudaFree(s->out30);
+    if (s->e0) cudaEventDestroy(s->e0);
+    if (s->e1) cudaEventDestroy(s->e1);
+    if (s->st) cudaStreamDestroy(s->st);
+    delete s;
+}
+
+extern "C" int bppp_wnla_shard_create(bppp_wnla_shard **out, int device, const uint8_t *g64, const uint8_t *hvec64, const uint8_t *c32, const uint8_t *l32,
+                                      size_t nh, size_t h_off, const uint8_t *gvec64, const uint8_t *n32, size_t ng, size_t g_off, const uint8_t *rho32,
+                                      const uint8_t *mu32, int whole) {
+    if (!out || !g64 || !rho32 || !mu32 || (nh && (!hvec64 || !c32 || !l32)) || (ng && (!gvec64 || !n32))) return fail(BPPP_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (!whole && ((h_off | g_off) & 1)) return fail(BPPP_ERR_ARG, "a block must start at an even index");
+    int rc = pick_device(device); if (rc != BPPP_OK) return rc;
+    bppp_wnla_shard *s = new bppp_wnla_shard();
+    struct Guard { bppp_wnla_shard *s; ~Guard() { if (s) bppp_wnla_shard_destroy(s); } } guard{s};
+    s->device = device; s->nh = nh; s->ng = ng; s->h_off = h_off; s->g_off = g_off; s->whole = whole;
+    if (!sc_from_be32(s->rho, rho32) || !sc_from_be32(s->mu, mu32)) return fail(BPPP_ERR_ARG, "rho/mu not canonical");
+    CUDA_OK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreate(&s->e0)); CUDA_OK(cudaEventCreate(&s->e1));
+    cudaStream_t st = s->st;
+    std::vector<uint8_t> pb(64 * (nh + ng + 1));
+    if (nh) memcpy(pb.data(), hvec64, 64 * nh);
+    if (ng) memcpy(pb.data() + 64 * nh, gvec64, 64 * ng);
+    memcpy(pb.data() + 64 * (nh + ng), g64, 64);
+    rc = decode_points_to_device(st, pb.data(), FMT_AFFINE64, nh + ng + 1, &s->pts[0]); if (rc != BPPP_OK) return rc;
+    rc = decode_scalars_to_device(st, c32, nh, &s->c[0]); if (rc != BPPP_OK) return rc;
+    rc = decode_scalars_to_device(st, l32, nh, &s->l[0]); if (rc != BPPP_OK) return rc;
+    rc = decode_scalars_to_device(st, n32, ng, &s->n[0]); if (rc != BPPP_OK) return rc;
+    const size_t nh2 = (nh + 1) / 2, ng2 = (ng + 1) / 2, half = std::max(nh, ng) + 1;
+    CUDA_OK(cudaMalloc(&s->pts[1], 64 * (nh2 + ng2 + 1)));
+    CUDA_OK(cudaMalloc(&s->c[1], 32 * (nh2 ? nh2 : 1))); CUDA_OK(cudaMalloc(&s->l[1], 32 * (nh2 ? nh2 : 1))); CUDA_OK(cudaMalloc(&s->n[1], 32 * (ng2 ? ng2 : 1)));
+    CUDA_OK(cudaMalloc(&s->sx, 32 * (nh + ng + 1))); CUDA_OK(cudaMalloc(&s->sr, 32 * (nh + ng + 1)));
+    CUDA_OK(cudaMalloc(&s->part, 128 * ((half + 127) / 128)));
+    CUDA_OK(cudaMalloc(&s->out30, 2 * PT_BYTES));
+    guard.s = nullptr;
+    *out = s;
+    return BPPP_OK;
+}
+
+extern "C" int bppp_wnla_shard_state(const bppp_wnla_shard *s, size_t *nh, size_t *ng, size_t *h_off, size_t *g_off, uint8_t *rho32, uint8_t *mu32) {
+    if (!s) return fail(BPPP_ERR_ARG, "null argument");
+    if (nh) *nh = s->nh;
+    if (ng) *ng = s->ng;
+    if (h_off) *h_off = s->h_off;
+    if (g_off) *g_off = s->g_off;
+    if (rho32) sc_to_be32(rho32, s->rho);
+    if (mu32) sc_to_be32(mu32, s->mu);
+    return BPPP_OK;
+}
+
+// this block's share of wnla.commit(l, n) (wnla.rs:66-72): (<c, l> + |n|^2_mu restricted to the block) g + <h, l> + <g_vec, n>
+extern "C" int bppp_wnla_shard_commit_partial(bppp_wnla_shard *s, uint8_t *out64) {
+    if (!s || !out64) return fail(BPPP_ERR_ARG, "null argument");
+    CUDA_OK(cudaSetDevice(s->device));
+    cudaStream_t st = s->st;
+    const int k = s->cur;
+    const size_t L = std::max(s->nh, s->ng), nblk = (L + 127) / 128, Lt = s->nh + s->ng + 1;
+    if (nblk) WL(k_commit_dots, (unsigned)nblk, 128, s->c[k], s->l[k], s->nh, s->n[k], s->ng, to_param(s->mu), s->part, s->g_off);
+    Sc sums[2];
+    int rc = sum_partials_to_host(st, s->part, nblk, 2, sums); if (rc != BPPP_OK) return rc;
+    Sc v = sc_add(sums[0], sums[1]);
+    if (s->nh) CUDA_OK(cudaMemcpyAsync(s->sx, s->l[k], 32 * s->nh, cudaMemcpyDeviceToDevice, st));
+    if (s->ng) CUDA_OK(cudaMemcpyAsync(s->sx + 8 * s->nh, s->n[k], 32 * s->ng, cudaMemcpyDeviceToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(s->sx + 8 * (s->nh + s->ng), v.v, 32, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaStreamSynchronize(st));       // v is a stack variable
+    rc = msm_device(st, s->pts[k], s->sx, Lt, nullptr, s->out30); if (rc != BPPP_OK) return rc;
+    return encode_points_from_device(st, s->out30, 1, FMT_AFFINE64, out64);
+}
+
+// this block's shares of X and R (wnla.rs:143-160), 64-byte affine each; *device_ms: device time of the kernels
+extern "C" int bppp_wnla_shard_xr_partial(bppp_wnla_shard *s, uint8_t *out128, float *device_ms) {
+    if (!s || !out128) return fail(BPPP_ERR_ARG, "null argument");
+    if (sc_is_zero(s->rho)) return fail(BPPP_ERR_ARG, "rho is zero: the reference panics (rho.invert_vartime().unwrap(), wnla.rs:135)");
+    CUDA_OK(cudaSetDevice(s->device));
+    cudaStream_t st = s->st;
+    const int k = s->cur;
+    const size_t Lh = s->nh, Lg = s->ng, Lt = Lh + Lg + 1;
+    Sc rho_inv = sc_inv(s->rho), mu2 = sc_sqr(s->mu);
+    const size_t half = (std::max(Lh, Lg) + 1) / 2, nblk = (half + 127) / 128;
+    CUDA_OK(cudaEventRecord(s->e0, st));
+    if (Lh + Lg) WL(k_wnla_xr_scalars, nblocks(Lh + Lg, 128), 128, s->l[k], s->n[k], Lh, Lg, to_param(s->rho), to_param(rho_inv), s->sx, s->sr);
+    if (nblk) WL(k_wnla_dots, (unsigned)nblk, 128, s->c[k], s->l[k], s->n[k], Lh, Lg, to_param(mu2), s->part, s->g_off / 2);
+    Sc sums[4];
+    int rc = sum_partials_to_host(st, s->part, nblk, 4, sums); if (rc != BPPP_OK) return rc;
+    Sc vx = sc_add(sc_mul(sums[0], sc_dbl(rho_inv)), sums[1]);       // wnla.rs:145-148, this block's terms
+    Sc vr = sc_add(sums[2], sums[3]);                                // wnla.rs:150
+    CUDA_OK(cudaMemcpyAsync(s->sx + 8 * (Lh + Lg), vx.v, 32, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(s->sr + 8 * (Lh + Lg), vr.v, 32, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    rc = msm_device(st, s->pts[k], s->sx, Lt, nullptr, s->out30); if (rc != BPPP_OK) return rc;
+    rc = msm_device(st, s->pts[k], s->sr, Lt, nullptr, s->out30 + PT_W); if (rc != BPPP_OK) return rc;
+    CUDA_OK(cudaEventRecord(s->e1, st));
+    rc = encode_points_from_device(st, s->out30, 2, FMT_AFFINE64, out128); if (rc != BPPP_OK) return rc;
+    if (device_ms) CUDA_OK(cudaEventElapsedTime(device_ms, s->e0, s->e1));
+    return BPPP_OK;
+}
+
+// fold the block with the round's challenge (wnla.rs:170-175, 177-184): h' = h0 + y h1, g' = rho g0 + y g1, c' = c0 + y c1,
+// l' = l0 + y l1, n' = rho^-1 n0 + y n1; rho <- mu, mu <- mu^2; offsets and lengths halve
+extern "C" int bppp_wnla_shard_fold(bppp_wnla_shard *s, const uint8_t *y32, float *device_ms) {
+    if (!s || !y32) return fail(BPPP_ERR_ARG, "null argument");
+    if (!s->whole && ((s->nh | s->ng | s->h_off | s->g_off) & 1))
+        return fail(BPPP_ERR_ARG, "this block no longer folds locally (odd length or offset): gather the blocks into a whole instance");
+    Sc y;
+    if (!sc_from_be32(y, y32)) return fail(BPPP_ERR_ARG, "challenge is not a canonical scalar");
+    if (sc_is_zero(s->rho)) return fail(BPPP_ERR_ARG, "rho is zero: the reference panics (wnla.rs:135)");
+    CUDA_OK(cudaSetDevice(s->device));
+    cudaStream_t st = s->st;
+    const int k = s->cur, o = k ^ 1;
+    const size_t Lh = s->nh, Lg = s->ng, Lh2 = (Lh + 1) / 2, Lg2 = (Lg + 1) / 2;
+    Sc rho_inv = sc_inv(s->rho);
+    CUDA_OK(cudaEventRecord(s->e0, st));
+    if (Lh2) WL(k_wnla_fold_points, nblocks(Lh2, 64), 64, s->pts[k], Lh, to_param(y), to_param(s->rho), 0, s->pts[o]);
+    if (Lg2) WL(k_wnla_fold_points, nblocks(Lg2, 64), 64, s->pts[k] + 16 * Lh, Lg, to_param(y), to_param(s->rho), 1, s->pts[o] + 16 * Lh2);
+    CUDA_OK(cudaMemcpyAsync(s->pts[o] + 16 * (Lh2 + Lg2), s->pts[k] + 16 * (Lh + Lg), 64, cudaMemcpyDeviceToDevice, st));
+    if (Lh2 + Lg2) WL(k_wnla_fold_scalars, nblocks(std::max(Lh2, Lg2), 128), 128, s->c[k], s->l[k], s->n[k], Lh, Lg, to_param(y), to_param(rho_inv), s->c[o], s->l[o], s->n[o], 1);
+    CUDA_OK(cudaEventRecord(s->e1, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaGetLastError());
+    if (device_ms) CUDA_OK(cudaEventElapsedTime(device_ms, s->e0, s->e1));
+    s->cur = o; s->nh = Lh2; s->ng = Lg2; s->h_off /= 2; s->g_off /= 2;
+    Sc mu2 = sc_sqr(s->mu);
+    s->rho = s->mu; s->mu = mu2;
+    return BPPP_OK;
+}
+
+__global__ void k_words_to_be(const uint32_t *w, size_t n, int words, uint8_t *out) {      // 8 LE words per 32-byte big-endian field
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * (size_t)(words / 8)) return;
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = w[8 * t + k];
+    words_to_be32(out + 32 * t, v);
+}
+// the block's current contents (64-byte affine points, 32-byte scalars): what the holders exchange once the blocks are too
+// short to fold locally, and how a proof's final l, n leave the device
+extern "C" int bppp_wnla_shard_export(bppp_wnla_shard *s, uint8_t *hvec64, uint8_t *c32, uint8_t *l32, uint8_t *gvec64, uint8_t *n32) {
+    if (!s) return fail(BPPP_ERR_ARG, "null argument");
+    CUDA_OK(cudaSetDevice(s->device));
+    cudaStream_t st = s->st;
+    const int k = s->cur;
+    uint8_t *d_tmp = nullptr;
+    const size_t cap = 64 * std::max(s->nh, s->ng) + 64;
+    CUDA_OK(cudaMalloc(&d_tmp, cap));
+    auto dump = [&](const uint32_t *src, size_t n, int words, uint8_t *dst) -> int {
+        if (!dst || !n) return BPPP_OK;
+        WL(k_words_to_be, nblocks(n * (size_t)(words / 8), 128), 128, src, n, words, d_tmp);
+        CUDA_OK(cudaMemcpyAsync(dst, d_tmp, 4 * (size_t)words * n, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        return BPPP_OK;
+    };
+    int rc = dump(s->pts[k], s->nh, 16, hvec64);
+    if (rc == BPPP_OK) rc = dump(s->c[k], s->nh, 8, c32);
+    if (rc == BPPP_OK) rc = dump(s->l[k], s->nh, 8, l32);
+    if (rc == BPPP_OK) rc = dump(s->pts[k] + 16 * s->nh, s->ng, 16, gvec64);
+    if (rc == BPPP_OK) rc = dump(s->n[k], s->ng, 8, n32);
+    cudaFree(d_tmp);
     return rc;
 }

@@ -59,3 +59,198 @@ def msm_sharded(points: bytes, scalars32: bytes, device: int, points_fmt: int = 
     dist.all_gather(gathered, mine)
     allparts = b"".join(bytes(t.cpu().numpy().tobytes()) for t in gathered)
     return api.points_sum(allparts, api.FMT_COMPRESSED, api.FMT_COMPRESSED, device)
+
+
+# ---- a standalone WNLA instance over several GPUs (BASELINE config 5) -------------------------------------
+class WnlaShard:
+    """One contiguous block of a WeightNormLinearArgument instance resident on one GPU (bppp_wnla_shard, include/bppp.h)."""
+
+    def __init__(self, device: int, g64: bytes, hvec64: bytes, c32: bytes, l32: bytes, h_off: int, gvec64: bytes, n32: bytes, g_off: int,
+                 rho32: bytes, mu32: bytes, whole: bool = False):
+        import ctypes as C
+        from ._lib import check, lib
+        from .api import _in
+        nh, ng = len(hvec64) // 64, len(gvec64) // 64
+        if len(c32) != 32 * nh or len(l32) != 32 * nh or len(n32) != 32 * ng:
+            raise ValueError("a block holds equally long h_vec / c / l and equally long g_vec / n")
+        self._h, self.device = C.c_void_p(), device
+        check(lib().bppp_wnla_shard_create(C.byref(self._h), C.c_int(device), _in(g64), _in(hvec64), _in(c32), _in(l32), C.c_size_t(nh), C.c_size_t(h_off),
+                                           _in(gvec64), _in(n32), C.c_size_t(ng), C.c_size_t(g_off), _in(rho32), _in(mu32), C.c_int(int(whole))),
+              "bppp_wnla_shard_create")
+
+    def state(self):
+        import ctypes as C
+        from ._lib import check, lib
+        nh, ng, ho, go = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        rho, mu = (C.c_uint8 * 32)(), (C.c_uint8 * 32)()
+        check(lib().bppp_wnla_shard_state(self._h, C.byref(nh), C.byref(ng), C.byref(ho), C.byref(go), rho, mu), "bppp_wnla_shard_state")
+        return {"nh": nh.value, "ng": ng.value, "h_off": ho.value, "g_off": go.value, "rho": bytes(rho), "mu": bytes(mu)}
+
+    def commit_partial(self) -> bytes:
+        import ctypes as C
+        from ._lib import check, lib
+        out = (C.c_uint8 * 64)()
+        check(lib().bppp_wnla_shard_commit_partial(self._h, out), "bppp_wnla_shard_commit_partial")
+        return bytes(out)
+
+    def xr_partial(self):
+        import ctypes as C
+        from ._lib import check, lib
+        out, ms = (C.c_uint8 * 128)(), C.c_float()
+        check(lib().bppp_wnla_shard_xr_partial(self._h, out, C.byref(ms)), "bppp_wnla_shard_xr_partial")
+        return bytes(out), ms.value
+
+    def fold(self, y32: bytes) -> float:
+        import ctypes as C
+        from ._lib import check, lib
+        from .api import _in
+        ms = C.c_float()
+        check(lib().bppp_wnla_shard_fold(self._h, _in(y32), C.byref(ms)), "bppp_wnla_shard_fold")
+        return ms.value
+
+    def export(self):
+        import ctypes as C
+        from ._lib import check, lib
+        st = self.state()
+        nh, ng = st["nh"], st["ng"]
+        h, c, l = (C.c_uint8 * max(64 * nh, 1))(), (C.c_uint8 * max(32 * nh, 1))(), (C.c_uint8 * max(32 * nh, 1))()
+        g, n = (C.c_uint8 * max(64 * ng, 1))(), (C.c_uint8 * max(32 * ng, 1))()
+        check(lib().bppp_wnla_shard_export(self._h, h, c, l, g, n), "bppp_wnla_shard_export")
+        return {"hvec64": bytes(h)[:64 * nh], "c32": bytes(c)[:32 * nh], "l32": bytes(l)[:32 * nh], "gvec64": bytes(g)[:64 * ng], "n32": bytes(n)[:32 * ng]}
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            from ._lib import lib
+            import ctypes as C
+            lib().bppp_wnla_shard_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_N = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+
+
+def _gather_bytes(mine: bytes, device: int) -> List[bytes]:
+    """All-gather of one equal-length byte string per process (NCCL on the GPU under an nccl group, gloo on the CPU);
+    a single-process call returns [mine]."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [mine]
+    dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+    outs = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, t)
+    return [bytes(o.cpu().numpy().tobytes()) for o in outs]
+
+
+def wnla_prove_sharded(g64: bytes, blocks: Sequence[dict], rho32: bytes, mu32: bytes, commitment33: bytes, t, devices: Sequence[int], stats: dict = None):
+    """`WeightNormLinearArgument::prove(&self, commitment, t, l, n)` (src/wnla.rs:125-190) for an instance cut into equal,
+    contiguous blocks: this process holds `blocks` (dicts with hvec64, c32, l32, gvec64, n32), block j resident on
+    devices[j]; under torch.distributed the processes' blocks follow each other in rank order.  `t` is the caller's
+    transcript (bp_pp_b200.transcript.Transcript or compatible); commitment33 = None computes `commit(l, n)` first (returned
+    in stats["commitment33"]).  Every process returns the same (r, x, l, n) byte
+    strings, r / x innermost round first (wnla.rs:186-188), byte-identical to the single-GPU bppp_wnla_prove.
+
+    Per round: each block's shares of X and R on its own GPU (host threads within a process), ONE all-gather of
+    128 bytes per block, identical transcript everywhere, local fold.  Once the blocks are too short to fold locally
+    (2^17 -> 1 element after 17 rounds for 2^20 generators on 8 GPUs) their contents are all-gathered and every process
+    finishes the last rounds on one GPU."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    import torch.distributed as dist
+    from . import api
+    from .transcript import app_point, get_challenge
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    world, rank = (dist.get_world_size(), dist.get_rank()) if multi else (1, 0)
+    nb = len(blocks)
+    if nb < 1 or len(devices) < nb:
+        raise ValueError("one device per local block")
+    nh, ng = len(blocks[0]["hvec64"]) // 64, len(blocks[0]["gvec64"]) // 64
+    if any(len(b["hvec64"]) != 64 * nh or len(b["gvec64"]) != 64 * ng for b in blocks):
+        raise ValueError("blocks must be equally long")
+    total_blocks = world * nb
+    whole = total_blocks == 1
+    dev0 = devices[0]
+    t0 = time.perf_counter()
+    shards = [WnlaShard(devices[j], g64, b["hvec64"], b["c32"], b["l32"], (rank * nb + j) * nh, b["gvec64"], b["n32"], (rank * nb + j) * ng, rho32, mu32, whole)
+              for j, b in enumerate(blocks)]
+    len_l, len_n = total_blocks * nh, total_blocks * ng
+    st = {"rounds_sharded": 0, "rounds_whole": 0, "device_ms": 0.0, "upload_s": time.perf_counter() - t0, "exchange_bytes": 0}
+    pool = ThreadPoolExecutor(max_workers=nb) if nb > 1 else None
+    pmap = (lambda f, xs: list(pool.map(f, xs))) if pool else (lambda f, xs: [f(x) for x in xs])
+
+    def total(parts64):          # sum of 64-byte affine points -> (affine64, compressed33)
+        allp = b"".join(parts64)
+        return (api.points_sum(allp, api.FMT_AFFINE64, api.FMT_AFFINE64, dev0), api.points_sum(allp, api.FMT_AFFINE64, api.FMT_COMPRESSED, dev0))
+
+    if commitment33 is None:
+        # WeightNormLinearArgument::commit(l, n) (wnla.rs:66-72) block by block: what a caller computes before proving
+        cp = b"".join(pmap(lambda sh: sh.commit_partial(), shards))
+        cp = cp if whole else b"".join(_gather_bytes(cp, dev0))
+        com64, com33 = total([cp[o:o + 64] for o in range(0, len(cp), 64)])
+        st["commitment33"] = com33
+    else:
+        com64, com33 = api.points_convert(commitment33, api.FMT_COMPRESSED, api.FMT_AFFINE64, dev0), commitment33
+    rs, xs = [], []
+    first = True
+    t1 = time.perf_counter()
+    try:
+        while len_l + len_n >= 6:                                    # wnla.rs:126
+            s0 = shards[0].state()
+            if not whole and ((s0["nh"] | s0["ng"]) & 1 or s0["nh"] < 2 or s0["ng"] < 2 or (s0["h_off"] | s0["g_off"]) & 1):
+                # the blocks no longer fold locally: gather their contents, finish as one instance on one GPU per process
+                ex = [sh.export() for sh in shards]
+                keys = ("hvec64", "c32", "l32", "gvec64", "n32")
+                mine = {k: b"".join(e[k] for e in ex) for k in keys}
+                full = {k: b"".join(_gather_bytes(mine[k], dev0)) for k in keys}
+                st["exchange_bytes"] += sum(len(v) for v in full.values())
+                for sh in shards:
+                    sh.close()
+                shards = [WnlaShard(dev0, g64, full["hvec64"], full["c32"], full["l32"], 0, full["gvec64"], full["n32"], 0, s0["rho"], s0["mu"], True)]
+                whole, pmap = True, (lambda f, xs: [f(x) for x in xs])
+            parts = pmap(lambda sh: sh.xr_partial(), shards)
+            st["device_ms"] += max(ms for _, ms in parts)
+            mine = b"".join(p for p, _ in parts)
+            allparts = mine if whole else b"".join(_gather_bytes(mine, dev0))
+            if not whole:
+                st["exchange_bytes"] += len(allparts)
+            X64, X33 = total([allparts[o:o + 64] for o in range(0, len(allparts), 128)])
+            R64, R33 = total([allparts[o + 64:o + 128] for o in range(0, len(allparts), 128)])
+            app_point(b"wnla_com", com33, t); app_point(b"wnla_x", X33, t); app_point(b"wnla_r", R33, t)        # wnla.rs:162-164
+            t.append_u64(b"l.sz", len_l); t.append_u64(b"n.sz", len_n)                                        # :165-166
+            y32 = get_challenge(b"wnla_challenge", t)
+            st["device_ms"] += max(pmap(lambda sh: sh.fold(y32), shards))
+            if first:
+                # the reference recomputes wnla'.commit(l', n') (wnla.rs:186); it equals C + y X + (y^2 - 1) R only when the
+                # caller's commitment matched (l, n), so the first re-commit is evaluated literally, block by block
+                cp = b"".join(pmap(lambda sh: sh.commit_partial(), shards))
+                cp = cp if whole else b"".join(_gather_bytes(cp, dev0))
+                com64, com33 = total([cp[o:o + 64] for o in range(0, len(cp), 64)])
+                first = False
+            else:
+                y = int.from_bytes(y32, "big")
+                sc = (1).to_bytes(32, "big") + y32 + ((y * y - 1) % _N).to_bytes(32, "big")
+                com64 = api.msm(com64 + X64 + R64, sc, api.FMT_AFFINE64, api.FMT_AFFINE64, dev0)                 # wnla.rs:100-102
+                com33 = api.points_convert(com64, api.FMT_AFFINE64, api.FMT_COMPRESSED, dev0)
+            rs.append(R33); xs.append(X33)
+            len_l, len_n = (len_l + 1) // 2, (len_n + 1) // 2
+            st["rounds_whole" if whole else "rounds_sharded"] += 1
+        ex = [sh.export() for sh in shards]
+        l_out, n_out = b"".join(e["l32"] for e in ex), b"".join(e["n32"] for e in ex)
+        if not whole:
+            l_out, n_out = b"".join(_gather_bytes(l_out, dev0)), b"".join(_gather_bytes(n_out, dev0))
+    finally:
+        for sh in shards:
+            sh.close()
+        if pool:
+            pool.shutdown()
+    st["prove_s"] = time.perf_counter() - t1
+    if stats is not None:
+        stats.update(st)
+    return b"".join(reversed(rs)), b"".join(reversed(xs)), l_out, n_out

@@ -189,6 +189,26 @@ int bppp_wnla_verify(int device, const uint8_t *g64, const uint8_t *gvec64, size
                      const uint8_t *r33, size_t rn, const uint8_t *x33, size_t xn, const uint8_t *l32, size_t ln,
                      const uint8_t *n32, size_t nn, const uint8_t *label, size_t label_len, int32_t *verdict);
 
+/* ---- a standalone WNLA instance cut into blocks, one per GPU (BASELINE config 5) ---------------------------
+ * A shard holds one contiguous block of the instance resident on one GPU: h_vec / c / l indices [h_off, h_off + nh) and
+ * g_vec / n indices [g_off, g_off + ng), offsets even.  Folding maps the pair (2i, 2i+1) to i (src/util.rs:7-22), so an
+ * even-offset, even-length block folds locally.  Per round every block yields its shares of X and R (src/wnla.rs:143-160;
+ * the block's part of vx / vr rides on g), the holders add the shares -- the only exchange, 2 x 64 bytes per block --
+ * run the identical transcript and fold with the challenge.  When the blocks become too short to fold locally their
+ * contents are gathered (_export) into one shard created with whole = 1, which finishes the recursion; a whole shard is
+ * also the stepped single-GPU prover for a caller-owned transcript.  Drivers: bp_pp_b200/shard.py (torch.distributed /
+ * NCCL all-gather between processes, host threads between the GPUs of one process). */
+typedef struct bppp_wnla_shard bppp_wnla_shard;
+int bppp_wnla_shard_create(bppp_wnla_shard **out, int device, const uint8_t *g64, const uint8_t *hvec64, const uint8_t *c32, const uint8_t *l32,
+                           size_t nh, size_t h_off, const uint8_t *gvec64, const uint8_t *n32, size_t ng, size_t g_off, const uint8_t *rho32,
+                           const uint8_t *mu32, int whole);
+void bppp_wnla_shard_destroy(bppp_wnla_shard *s);
+int bppp_wnla_shard_state(const bppp_wnla_shard *s, size_t *nh, size_t *ng, size_t *h_off, size_t *g_off, uint8_t *rho32, uint8_t *mu32);
+int bppp_wnla_shard_commit_partial(bppp_wnla_shard *s, uint8_t *out64);                 /* share of wnla.commit(l, n), src/wnla.rs:66-72 */
+int bppp_wnla_shard_xr_partial(bppp_wnla_shard *s, uint8_t *out128, float *device_ms);  /* shares of X and R, 64-byte affine each */
+int bppp_wnla_shard_fold(bppp_wnla_shard *s, const uint8_t *y32, float *device_ms);     /* src/wnla.rs:170-184 on the block */
+int bppp_wnla_shard_export(bppp_wnla_shard *s, uint8_t *hvec64, uint8_t *c32, uint8_t *l32, uint8_t *gvec64, uint8_t *n32);
+
 /* ArithmeticCircuit<P> (src/circuit.rs:95-139) with dense row-major W_m (dim_nm x dim_nw) and W_l (dim_nl x dim_nw),
  * dim_nl = dim_nv * k, dim_nw = 2 dim_nm + dim_no, and the partition closure tabulated: part_xx[j] = index or -1 for
  * j < part_n (PartitionType LO / LL / LR / NO, src/circuit.rs:15-20).  Generators 64-byte affine. */

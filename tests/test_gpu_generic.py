@@ -272,26 +272,86 @@ def test_config4_wide_reciprocal_dim_1024(oracle, ref):
     assert proto.verify(com, bytes(bad), rounds, rounds, ll, nl, b"wide") in (0, -3)
 
 
-@pytest.mark.parametrize("logn", [12, 16])
-def test_config5_standalone_wnla_large(oracle, ref, logn):
-    """BASELINE config 5 shape: |g_vec| = |h_vec| = |c| = |l| = |n| = 2^logn.  2^12 is checked against the oracle; larger sizes
-    through size-independent properties (prove -> verify true, any tampering -> false, first-round X/R linearity)."""
+def _big_wnla(ref, logn):
     import bp_pp_b200 as B
+    import numpy as np
     n = 1 << logn
-    rnd = random.Random(logn)
     base, step = xy(ref.pt_mul(ref.G, 11)), xy(ref.pt_mul(ref.G, 29))
     pts = B.points_generate(base, step, 2 * n + 1)
-    assert pts[:64] == base and pts[64:128] == oracle.point_add(base, step)
-    g, gvec, hvec = pts[:64], pts[64:64 * (n + 1)], pts[64 * (n + 1):]
-    c = rnd.randbytes(32 * n); c = b"".join(bytes([c[32 * i] & 0x7F]) + c[32 * i + 1:32 * i + 32] for i in range(n))
-    l = rnd.randbytes(32 * n); l = b"".join(bytes([l[32 * i] & 0x7F]) + l[32 * i + 1:32 * i + 32] for i in range(n))
-    nn = rnd.randbytes(32 * n); nn = b"".join(bytes([nn[32 * i] & 0x7F]) + nn[32 * i + 1:32 * i + 32] for i in range(n))
-    rho = rnd.randrange(1, ref.N); mu = rho * rho % ref.N
+    rnd = np.random.default_rng(logn)
+
+    def scalars():
+        a = np.frombuffer(rnd.bytes(32 * n), dtype=np.uint8).reshape(n, 32).copy()
+        a[:, 0] &= 0x7F
+        return a.tobytes()
+    rho = random.Random(logn).randrange(1, ref.N)
+    return pts[:64], pts[64:64 * (n + 1)], pts[64 * (n + 1):], scalars(), _be(rho), _be(rho * rho % ref.N), scalars(), scalars()
+
+
+@pytest.mark.parametrize("blocks", [1, 2, 8])
+def test_wnla_sharded_blocks_equal_the_single_gpu_prover(oracle, ref, blocks):
+    """bppp_wnla_shard_* + bp_pp_b200.shard.wnla_prove_sharded: the instance cut into `blocks` equal blocks (all resident on
+    GPU 0 here; one per GPU under torchrun / a device list), shares of X and R added per round, local folds, final
+    gather.  Must equal the single-GPU prover and the C oracle byte for byte (n = 2^10)."""
+    import bp_pp_b200 as B
+    from bp_pp_b200.shard import wnla_prove_sharded
+    from bp_pp_b200.transcript import Transcript
+    g, gvec, hvec, c, rho, mu, l, n = _wnla_instance(oracle, ref, 1024, 1024, 1024, 1024, seed=4242)
+    label = b"wnla sharded"
+    com = oracle.wnla_commit(g, gvec, hvec, c, rho, mu, l, n)
+    want = oracle.wnla_prove(g, gvec, hvec, c, rho, mu, com, l, n, label)
+    per = 1024 // blocks
+    blks = [dict(hvec64=hvec[64 * per * j:64 * per * (j + 1)], c32=c[32 * per * j:32 * per * (j + 1)], l32=l[32 * per * j:32 * per * (j + 1)],
+                 gvec64=gvec[64 * per * j:64 * per * (j + 1)], n32=n[32 * per * j:32 * per * (j + 1)]) for j in range(blocks)]
+    stats = {}
+    got = wnla_prove_sharded(g, blks, rho, mu, com, Transcript(label), [0] * blocks, stats)
+    assert got == want
+    assert got == B.WeightNormLinearArgument(g, gvec, hvec, c, rho, mu).prove(com, label, l, n)
+    assert stats["rounds_sharded"] + stats["rounds_whole"] == 9 and (blocks == 1 or stats["rounds_sharded"] >= 6)
+
+
+def test_wnla_sharded_with_an_inconsistent_commitment_and_a_foreign_transcript(ref):
+    """The reference's prove takes any commitment and a caller-owned transcript (wnla.rs:125): a commitment that does NOT
+    match (l, n) changes only the first wnla_com append (the re-commit is literal, wnla.rs:186), and prior transcript
+    state flows into every challenge.  Checked against the Python oracle on n = 16."""
+    from bp_pp_b200.shard import wnla_prove_sharded
+    from bp_pp_b200.transcript import Transcript
+    rnd = random.Random(31)
+    N = ref.N
+    pts = [ref.pt_mul(ref.G, rnd.randrange(1, N)) for _ in range(33)]
+    g, gv, hv = pts[0], pts[1:17], pts[17:33]
+    c = [rnd.randrange(N) for _ in range(16)]
+    rho = rnd.randrange(1, N); mu = rho * rho % N
+    l = [rnd.randrange(N) for _ in range(16)]; n = [rnd.randrange(N) for _ in range(16)]
+    w = ref.WeightNormLinearArgument(g, gv, hv, c, rho, mu)
+    wrong_com = ref.pt_add(w.commit(l, n), ref.G)
+    t_o = ref.Transcript(b"outer"); t_o.append_message(b"prior", b"state")
+    proof = w.prove(wrong_com, t_o, list(l), list(n))
+    t_p = Transcript(b"outer"); t_p.append_message(b"prior", b"state")
+    be = lambda v: v.to_bytes(32, "big")  # noqa: E731
+    blks = [dict(hvec64=b"".join(xy(p) for p in hv[8 * j:8 * j + 8]), c32=b"".join(be(v) for v in c[8 * j:8 * j + 8]), l32=b"".join(be(v) for v in l[8 * j:8 * j + 8]),
+                 gvec64=b"".join(xy(p) for p in gv[8 * j:8 * j + 8]), n32=b"".join(be(v) for v in n[8 * j:8 * j + 8])) for j in range(2)]
+    r, x, lo, no = wnla_prove_sharded(xy(g), blks, be(rho), be(mu), ref.pt_to_bytes(wrong_com), t_p, [0, 0])
+    assert r == b"".join(ref.pt_to_bytes(p) for p in proof.r) and x == b"".join(ref.pt_to_bytes(p) for p in proof.x)
+    assert lo == b"".join(be(v) for v in proof.l) and no == b"".join(be(v) for v in proof.n)
+    assert t_p.challenge_bytes(b"after", 16) == t_o.challenge_bytes(b"after", 16)
+
+
+@pytest.mark.parametrize("logn", [12, 16, 20])
+def test_config5_standalone_wnla_large(oracle, ref, logn):
+    """BASELINE config 5 shape: |g_vec| = |h_vec| = |c| = |l| = |n| = 2^logn.  2^12 and 2^16 are checked against the C oracle
+    (2^16: about a minute of host time); 2^20 -- the configuration's full size -- through size-independent properties
+    (prove -> verify true, any tampering -> false, MSM linearity) and sharded == single-GPU bytes."""
+    import bp_pp_b200 as B
+    n = 1 << logn
+    g, gvec, hvec, c, rho_b, mu_b, l, nn = _big_wnla(ref, logn)
+    assert g == xy(ref.pt_mul(ref.G, 11)) and gvec[:64] == oracle.point_add(g, xy(ref.pt_mul(ref.G, 29)))
+    rho, mu = int.from_bytes(rho_b, "big"), int.from_bytes(mu_b, "big")
     w = B.WeightNormLinearArgument(g, gvec, hvec, c, _be(rho), _be(mu))
     com = w.commit(l, nn)
     r, x, lo, no = w.prove(com, b"wnla big", l, nn)
     assert len(r) == len(x) == 33 * (logn - 1) and len(lo) == 64 and len(no) == 64
-    if logn <= 12:
+    if logn <= 16:
         oracle.use_native()
         assert com == oracle.wnla_commit(g, gvec, hvec, c, _be(rho), _be(mu), l, nn)
         assert (r, x, lo, no) == oracle.wnla_prove(g, gvec, hvec, c, _be(rho), _be(mu), com, l, nn, b"wnla big")
@@ -303,3 +363,10 @@ def test_config5_standalone_wnla_large(oracle, ref, logn):
     half = n // 2
     a = B.msm(hvec[:64 * half], l[:32 * half]); b = B.msm(hvec[64 * half:], l[32 * half:])
     assert B.points_sum(a + b) == B.msm(hvec, l)
+    if logn >= 16:
+        from bp_pp_b200.shard import wnla_prove_sharded
+        from bp_pp_b200.transcript import Transcript
+        per = n // 8
+        blks = [dict(hvec64=hvec[64 * per * j:64 * per * (j + 1)], c32=c[32 * per * j:32 * per * (j + 1)], l32=l[32 * per * j:32 * per * (j + 1)],
+                     gvec64=gvec[64 * per * j:64 * per * (j + 1)], n32=nn[32 * per * j:32 * per * (j + 1)]) for j in range(8)]
+        assert wnla_prove_sharded(g, blks, _be(rho), _be(mu), com, Transcript(b"wnla big"), [0] * 8) == (r, x, lo, no)
