@@ -196,8 +196,8 @@ int bppp_wnla_verify(int device, const uint8_t *g64, const uint8_t *gvec64, size
  * the block's part of vx / vr rides on g), the holders add the shares -- the only exchange, 2 x 64 bytes per block --
  * run the identical transcript and fold with the challenge.  When the blocks become too short to fold locally their
  * contents are gathered (_export) into one shard created with whole = 1, which finishes the recursion; a whole shard is
- * also the stepped single-GPU prover for a caller-owned transcript.  Drivers: bp_pp_b200/shard.py (torch.distributed /
- * NCCL all-gather between processes, host threads between the GPUs of one process). */
+ * also the stepped single-GPU prover for a caller-owned transcript.  Drivers: bp_pp_b200/shard.py (an
+ * NCCL all-gather between one-GPU processes, host threads between the GPUs of one process). */
 typedef struct bppp_wnla_shard bppp_wnla_shard;
 int bppp_wnla_shard_create(bppp_wnla_shard **out, int device, const uint8_t *g64, const uint8_t *hvec64, const uint8_t *c32, const uint8_t *l32,
                            size_t nh, size_t h_off, const uint8_t *gvec64, const uint8_t *n32, size_t ng, size_t g_off, const uint8_t *rho32,

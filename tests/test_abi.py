@@ -81,3 +81,21 @@ def test_serde_identity_point_is_the_one_byte_sec1_encoding(golden):
     import pytest
     with pytest.raises(ValueError):
         serde.reciprocal_obj_to_record({**obj, "r": "0000"})
+
+
+def test_rust_ffi_declarations_match_the_header():
+    """rust/bp-pp-gpu/src/ffi.rs (authored without a toolchain) must bind only symbols the library exports, with the
+    argument COUNT the C header declares -- the cheapest check that the crate would at least link."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "bppp.h")).read(), flags=re.S)
+    c_args = {}
+    for m in re.finditer(r"\b(bppp_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        c_args[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    rs = open(os.path.join(ROOT, "rust", "bp-pp-gpu", "src", "ffi.rs")).read()
+    rs = re.sub(r"//.*", "", rs)
+    found = re.findall(r"pub fn (bppp_[a-z0-9_]+)\s*\(([^)]*)\)", rs, flags=re.S)
+    assert len(found) >= 35
+    for name, args in found:
+        assert name in c_args, f"ffi.rs declares {name}, which include/bppp.h does not"
+        n = 0 if not args.strip() else args.count(":")
+        assert n == c_args[name], f"{name}: {n} arguments in ffi.rs, {c_args[name]} in bppp.h"
