@@ -24,7 +24,7 @@ EXPORTS = [
     "bppp_wnla_commit", "bppp_wnla_prove", "bppp_wnla_verify",
     "bppp_wnla_shard_create", "bppp_wnla_shard_destroy", "bppp_wnla_shard_state", "bppp_wnla_shard_commit_partial", "bppp_wnla_shard_xr_partial",
     "bppp_wnla_shard_fold", "bppp_wnla_shard_export",
-    "bppp_circuit_commit", "bppp_circuit_prove", "bppp_circuit_verify",
+    "bppp_circuit_commit", "bppp_circuit_prove", "bppp_circuit_verify", "bppp_circuit_commit_sparse", "bppp_circuit_prove_sparse", "bppp_circuit_verify_sparse",
     "bppp_reciprocal_commit_value", "bppp_reciprocal_prove", "bppp_reciprocal_verify",
 ]
 

@@ -529,14 +529,57 @@ class CircuitDesc(C.Structure):
     ]
 
 
-class ArithmeticCircuit:
-    """Mirror of `bp_pp::circuit::ArithmeticCircuit` (circuit.rs:95-139): dense row-major W_m / W_l (32-byte scalars) and the
-    partition function tabulated as four index lists (-1 = None)."""
+class SparseMatrix(C.Structure):
+    """`bppp_sparse_matrix` of include/bppp.h (CSR, values direct or through a dictionary)."""
+    _fields_ = [("rows", C.c_size_t), ("cols", C.c_size_t), ("nnz", C.c_size_t), ("row_ptr", C.POINTER(C.c_uint64)), ("col_idx", C.POINTER(C.c_uint32)),
+                ("value_idx", C.POINTER(C.c_uint32)), ("values32", C.POINTER(C.c_uint8)), ("n_values", C.c_size_t)]
 
-    def __init__(self, dim_nm, dim_no, k, dim_nv, g, g_vec, h_vec, W_m, W_l, a_m, a_l, f_l, f_m, g_vec_, h_vec_, part_lo, part_ll, part_lr, part_no, device=0):
+
+class CircuitDescSparse(C.Structure):
+    """`bppp_circuit_desc_sparse` of include/bppp.h."""
+    _u8p = C.POINTER(C.c_uint8)
+    _fields_ = [
+        ("dim_nm", C.c_size_t), ("dim_no", C.c_size_t), ("k", C.c_size_t), ("dim_nv", C.c_size_t), ("f_l", C.c_int), ("f_m", C.c_int),
+        ("g64", _u8p), ("gvec64", _u8p), ("hvec64", _u8p), ("gvec2_64", _u8p), ("hvec2_64", _u8p),
+        ("gn", C.c_size_t), ("hn", C.c_size_t), ("gn2", C.c_size_t), ("hn2", C.c_size_t),
+        ("W_m", SparseMatrix), ("W_l", SparseMatrix), ("a_m32", _u8p), ("a_l32", _u8p),
+        ("part_lo", C.POINTER(C.c_int32)), ("part_ll", C.POINTER(C.c_int32)), ("part_lr", C.POINTER(C.c_int32)), ("part_no", C.POINTER(C.c_int32)),
+        ("part_n", C.c_size_t),
+    ]
+
+
+def dense_to_csr(W32: bytes, rows: int, cols: int, dictionary: bool = True):
+    """Row-major dense matrix of 32-byte scalars -> (row_ptr, col_idx, value_idx or None, values32): the CSR form of
+    bppp_sparse_matrix, with the distinct values collected into a dictionary when `dictionary`."""
+    zero = bytes(32)
+    row_ptr, col_idx, val_idx, values, table = [0], [], [], [], {}
+    for i in range(rows):
+        for j in range(cols):
+            e = W32[32 * (i * cols + j):32 * (i * cols + j) + 32]
+            if e == zero:
+                continue
+            col_idx.append(j)
+            if dictionary:
+                val_idx.append(table.setdefault(e, len(table)))
+            else:
+                values.append(e)
+        row_ptr.append(len(col_idx))
+    if dictionary:
+        values = sorted(table, key=table.get)
+    return row_ptr, col_idx, (val_idx if dictionary else None), b"".join(values)
+
+
+class ArithmeticCircuit:
+    """Mirror of `bp_pp::circuit::ArithmeticCircuit` (circuit.rs:95-139): row-major W_m / W_l (32-byte scalars) and the
+    partition function tabulated as four index lists (-1 = None).  sparse = None passes the dense descriptor; "csr" /
+    "csr-dict" pass the same matrices through bppp_circuit_desc_sparse (values per non-zero / through a dictionary)."""
+
+    def __init__(self, dim_nm, dim_no, k, dim_nv, g, g_vec, h_vec, W_m, W_l, a_m, a_l, f_l, f_m, g_vec_, h_vec_, part_lo, part_ll, part_lr, part_no, device=0,
+                 sparse=None):
         self.device = device
         self._keep = []
-        d = CircuitDesc()
+        self._sfx = "_sparse" if sparse else ""
+        d = CircuitDescSparse() if sparse else CircuitDesc()
 
         def pb(b):
             a = _in(b); self._keep.append(a); return C.cast(a, CircuitDesc._u8p)
@@ -547,7 +590,24 @@ class ArithmeticCircuit:
         d.dim_nm, d.dim_no, d.k, d.dim_nv, d.f_l, d.f_m = dim_nm, dim_no, k, dim_nv, int(f_l), int(f_m)
         d.g64, d.gvec64, d.hvec64, d.gvec2_64, d.hvec2_64 = pb(g), pb(g_vec), pb(h_vec), pb(g_vec_), pb(h_vec_)
         d.gn, d.hn, d.gn2, d.hn2 = len(g_vec) // 64, len(h_vec) // 64, len(g_vec_) // 64, len(h_vec_) // 64
-        d.W_m32, d.W_l32, d.a_m32, d.a_l32 = pb(W_m), pb(W_l), pb(a_m), pb(a_l)
+        if sparse:
+            dim_nw = 2 * dim_nm + dim_no
+            for name, W, rows in (("W_m", W_m, dim_nm), ("W_l", W_l, dim_nv * k)):
+                rp, ci, vi, vals = dense_to_csr(W, rows, dim_nw, dictionary=(sparse == "csr-dict"))
+                m = SparseMatrix()
+                m.rows, m.cols, m.nnz = rows, dim_nw, len(ci)
+                a_rp, a_ci = (C.c_uint64 * len(rp))(*rp), (C.c_uint32 * max(len(ci), 1))(*ci)
+                self._keep += [a_rp, a_ci]
+                m.row_ptr, m.col_idx = C.cast(a_rp, C.POINTER(C.c_uint64)), C.cast(a_ci, C.POINTER(C.c_uint32))
+                if vi is not None:
+                    a_vi = (C.c_uint32 * max(len(vi), 1))(*vi)
+                    self._keep.append(a_vi)
+                    m.value_idx = C.cast(a_vi, C.POINTER(C.c_uint32))
+                m.values32, m.n_values = pb(vals), len(vals) // 32
+                setattr(d, name, m)
+            d.a_m32, d.a_l32 = pb(a_m), pb(a_l)
+        else:
+            d.W_m32, d.W_l32, d.a_m32, d.a_l32 = pb(W_m), pb(W_l), pb(a_m), pb(a_l)
         d.part_lo, d.part_ll, d.part_lr, d.part_no = pi(part_lo), pi(part_ll), pi(part_lr), pi(part_no)
         d.part_n = len(part_lo)
         self.desc = d
@@ -555,7 +615,7 @@ class ArithmeticCircuit:
     # circuit.rs:146-151
     def commit(self, v32: bytes, s32: bytes) -> bytes:
         out = (C.c_uint8 * 33)()
-        check(lib().bppp_circuit_commit(C.c_int(self.device), C.byref(self.desc), _in(v32), _in(s32), out), "bppp_circuit_commit")
+        check(getattr(lib(), "bppp_circuit_commit" + self._sfx)(C.c_int(self.device), C.byref(self.desc), _in(v32), _in(s32), out), "bppp_circuit_commit")
         return bytes(out)
 
     # circuit.rs:260-556 -> (record, rounds, l_len, n_len)
@@ -563,7 +623,7 @@ class ArithmeticCircuit:
         cap = 33 * (4 + 2 * 64) + 32 * 16
         out = (C.c_uint8 * cap)()
         ro, lo, no, st = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_int32()
-        check(lib().bppp_circuit_prove(C.c_int(self.device), C.byref(self.desc), _in(commits33), _in(v32), _in(sv32), _in(wl32), _in(wr32), _in(wo32), _in(rng),
+        check(getattr(lib(), "bppp_circuit_prove" + self._sfx)(C.c_int(self.device), C.byref(self.desc), _in(commits33), _in(v32), _in(sv32), _in(wl32), _in(wr32), _in(wo32), _in(rng),
                                        C.c_size_t(len(rng)), _in(label), C.c_size_t(len(label)), out, C.c_size_t(cap), C.byref(ro), C.byref(lo), C.byref(no),
                                        C.byref(st)), "bppp_circuit_prove")
         if st.value != ST_TRUE:
@@ -574,7 +634,7 @@ class ArithmeticCircuit:
     # circuit.rs:154-256
     def verify(self, commits33: bytes, rec: bytes, rounds_r: int, rounds_x: int, l_len: int, n_len: int, label: bytes) -> int:
         verdict = C.c_int32()
-        check(lib().bppp_circuit_verify(C.c_int(self.device), C.byref(self.desc), _in(commits33), _in(rec), C.c_size_t(rounds_r), C.c_size_t(rounds_x),
+        check(getattr(lib(), "bppp_circuit_verify" + self._sfx)(C.c_int(self.device), C.byref(self.desc), _in(commits33), _in(rec), C.c_size_t(rounds_r), C.c_size_t(rounds_x),
                                         C.c_size_t(l_len), C.c_size_t(n_len), _in(label), C.c_size_t(len(label)), C.byref(verdict)), "bppp_circuit_verify")
         return verdict.value
 

@@ -1,15 +1,18 @@
 // libbppp.so, generic arithmetic-circuit / reciprocal translation unit: ArithmeticCircuit::{commit, prove, verify}
-// (reference src/circuit.rs:146-653) for arbitrary dimensions, dense W_m / W_l and a tabulated partition function,
+// (reference src/circuit.rs:146-653) for arbitrary dimensions, W_m / W_l dense or sparse (CSR) and a tabulated partition function,
 // and ReciprocalRangeProofProtocol::{commit_value, commit_poles, prove, verify, make_circuit}
 // (src/range_proof/reciprocal.rs:88-214) for arbitrary (dim_nd, dim_np) on top of it.
 //
-// Division of labour (north_star): the host drives the Merlin transcript and the scalar-field (mod n) algebra of
-// the coefficient vectors -- the same sc.cuh code the kernels run -- while every elliptic-curve operation
-// (all commitments, the verifier's recombination, the whole WNLA) runs on the GPU through engine_msm.cu /
-// engine_wnla.cu.  The batched u64 fast path (engine_prove.cu / engine_verify.cu) is the specialisation of this
+// Division of labour: W_m / W_l live on the device in compressed-sparse-column form with a dictionary of distinct values
+// (circuits are mostly 0 / +-1 / a few constants), and the only super-linear step of the protocol -- the products
+// lambda_vec x W_l and mu_vec x W_m behind collect_c (circuit.rs:584-653, util.rs:134-142) -- is a kernel (k_spmv_cols);
+// every elliptic-curve operation (all commitments, the verifier's recombination, the whole WNLA) runs on the GPU through
+// engine_msm.cu / engine_wnla.cu.  What remains on the host is the Merlin transcript and O(dim) vector algebra over F_n
+// (the same sc.cuh code the kernels run).  The batched u64 fast path (engine_prove.cu / engine_verify.cu) is the specialisation of this
 // file with closed-form coefficients and on-device transcripts.
 #define BPPP_FE_NOINLINE 1
 #include <algorithm>
+#include <map>
 #include "engine_generic.cuh"
 
 using namespace bppp;
@@ -42,38 +45,95 @@ SV slice(const SV &a, size_t from, size_t to) { return SV(a.begin() + (long)std:
 SV tensor(const SV &a, const SV &b) { SV r; for (auto &x : b) { SV t = vscale(a, x); r.insert(r.end(), t.begin(), t.end()); } return r; }     // util.rs:111-116
 Sc sc_minus(const Sc &v) { return sc_neg(v); }                                                        // minus, util.rs:153-155
 
-struct Mat { size_t rows = 0, cols = 0; SV v; Sc at(size_t i, size_t j) const { return v[i * cols + j]; } };
-// vector_mul_on_matrix (util.rs:134-142): out[j] = sum_i a[i] m[i][j] with zero-extension; 0 / 1 entries short-cut
-SV vmat(const SV &a, const Mat &m) {
-    SV r(m.cols, sc_zero());
-    const Sc one = sc_one();
-    size_t rows = std::min(a.size(), m.rows);
-    for (size_t i = 0; i < rows; i++) {
-        if (sc_is_zero(a[i])) continue;
-        for (size_t j = 0; j < m.cols; j++) {
-            const Sc &e = m.v[i * m.cols + j];
-            if (sc_is_zero(e)) continue;
-            r[j] = sc_add(r[j], sc_eq(e, one) ? a[i] : sc_mul(a[i], e));
-        }
+// W_m / W_l: compressed sparse columns, values through a dictionary (id 0 is reserved for the scalar one: no multiplication).
+struct Sparse {
+    size_t rows = 0, cols = 0;
+    std::vector<uint32_t> colptr, rowidx, validx;
+    SV table;                                   // distinct values, table[0] = 1
+    uint32_t *d_colptr = nullptr, *d_rowidx = nullptr, *d_validx = nullptr, *d_table = nullptr;
+    size_t nnz() const { return rowidx.size(); }
+    void release() { cudaFree(d_colptr); cudaFree(d_rowidx); cudaFree(d_validx); cudaFree(d_table); d_colptr = d_rowidx = d_validx = d_table = nullptr; }
+};
+struct ScKey { uint32_t v[8]; bool operator<(const ScKey &o) const { return memcmp(v, o.v, 32) < 0; } };
+struct ValueDict {
+    Sparse &m; std::map<ScKey, uint32_t> ids;
+    explicit ValueDict(Sparse &mm) : m(mm) { m.table.assign(1, sc_one()); ScKey k; memcpy(k.v, m.table[0].v, 32); ids[k] = 0; }
+    uint32_t id(const Sc &s) {
+        ScKey k; memcpy(k.v, s.v, 32);
+        auto it = ids.find(k);
+        if (it != ids.end()) return it->second;
+        uint32_t n = (uint32_t)m.table.size(); m.table.push_back(s); ids[k] = n; return n;
     }
-    return r;
+};
+// entries as (row, col, value id) triples -> CSC by a counting sort over the columns
+void sparse_from_triples(Sparse &m, size_t rows, size_t cols, const std::vector<uint32_t> &tr, const std::vector<uint32_t> &tc, const std::vector<uint32_t> &tv) {
+    m.rows = rows; m.cols = cols;
+    m.colptr.assign(cols + 1, 0);
+    for (uint32_t c : tc) m.colptr[c + 1]++;
+    for (size_t j = 0; j < cols; j++) m.colptr[j + 1] += m.colptr[j];
+    m.rowidx.resize(tr.size()); m.validx.resize(tr.size());
+    std::vector<uint32_t> cur(m.colptr.begin(), m.colptr.end() - 1);
+    for (size_t k = 0; k < tr.size(); k++) { uint32_t p = cur[tc[k]]++; m.rowidx[p] = tr[k]; m.validx[p] = tv[k]; }
+}
+int sparse_upload(Sparse &m) {
+    auto up = [](const void *h, size_t bytes, uint32_t **d) -> int {
+        CUDA_OK(cudaMalloc(d, bytes ? bytes : 4));
+        if (bytes) CUDA_OK(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+        return BPPP_OK;
+    };
+    int rc = up(m.colptr.data(), 4 * m.colptr.size(), &m.d_colptr);
+    if (rc == BPPP_OK) rc = up(m.rowidx.data(), 4 * m.rowidx.size(), &m.d_rowidx);
+    if (rc == BPPP_OK) rc = up(m.validx.data(), 4 * m.validx.size(), &m.d_validx);
+    if (rc == BPPP_OK) rc = up(m.table.data(), 32 * m.table.size(), &m.d_table);
+    return rc;
+}
+}  // namespace
+
+// vector_mul_on_matrix (util.rs:134-142) for a sparse matrix: out[j] = sum_i a[i] m[i][j], rows beyond |a| contribute nothing
+// (the reference zero-extends).  One warp per column: lanes stride over the column's entries, shuffle tree at the end.
+__global__ void __launch_bounds__(128) k_spmv_cols(const uint32_t *colptr, const uint32_t *rowidx, const uint32_t *validx, const uint32_t *table, const uint32_t *a, uint32_t na,
+                                                   uint32_t cols, uint32_t *out) {
+    const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
+    if (j >= cols) return;
+    Sc acc = sc_zero();
+    for (uint32_t k = colptr[j] + lane; k < colptr[j + 1]; k += 32) {
+        const uint32_t r = rowidx[k], vi = validx[k];
+        if (r >= na) continue;
+        Sc av, tv;
+#pragma unroll
+        for (int q = 0; q < 8; q++) av.v[q] = a[8 * (size_t)r + q];
+        if (vi) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) tv.v[q] = table[8 * (size_t)vi + q];
+            av = sc_mul(av, tv);
+        }
+        acc = sc_add(acc, av);
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        Sc o;
+#pragma unroll
+        for (int q = 0; q < 8; q++) o.v[q] = __shfl_xor_sync(0xFFFFFFFFu, acc.v[q], off);
+        acc = sc_add(acc, o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) out[8 * (size_t)j + q] = acc.v[q];
+    }
 }
 
-// the same over the column block [from, to) of the first `rows` rows of m, without materialising the block
-SV vmat_cols(const SV &a, const Mat &m, size_t rows_m, size_t from, size_t to) {
-    SV r(to - from, sc_zero());
-    const Sc one = sc_one();
-    size_t rows = std::min(a.size(), rows_m);
-    for (size_t i = 0; i < rows; i++) {
-        if (sc_is_zero(a[i])) continue;
-        const Sc *row = &m.v[i * m.cols];
-        for (size_t j = from; j < to; j++) {
-            const Sc &e = row[j];
-            if (sc_is_zero(e)) continue;
-            r[j - from] = sc_add(r[j - from], sc_eq(e, one) ? a[i] : sc_mul(a[i], e));
-        }
-    }
-    return r;
+namespace {
+// a x m on the device
+int spmv(const SV &a, const Sparse &m, SV &out) {
+    out.assign(m.cols, sc_zero());
+    if (!m.cols) return BPPP_OK;
+    uint32_t *d_a = nullptr, *d_o = nullptr;
+    CUDA_OK(cudaMalloc(&d_a, 32 * std::max<size_t>(a.size(), 1))); CUDA_OK(cudaMalloc(&d_o, 32 * m.cols));
+    if (!a.empty()) CUDA_OK(cudaMemcpy(d_a, a.data(), 32 * a.size(), cudaMemcpyHostToDevice));
+    k_spmv_cols<<<(unsigned)((m.cols * 32 + 127) / 128), 128>>>(m.d_colptr, m.d_rowidx, m.d_validx, m.d_table, d_a, (uint32_t)a.size(), (uint32_t)m.cols, d_o);
+    CUDA_OK(cudaMemcpy(out.data(), d_o, 32 * m.cols, cudaMemcpyDeviceToHost));
+    cudaFree(d_a); cudaFree(d_o);
+    CUDA_OK(cudaGetLastError());
+    return BPPP_OK;
 }
 
 struct Panic { int32_t code; };
@@ -82,13 +142,13 @@ Sc inv_or_panic(const Sc &a) { if (sc_is_zero(a)) throw Panic{ST_PANIC_INVERT_ZE
 struct Circuit {
     size_t dim_nm = 0, dim_no = 0, k = 0, dim_nl = 0, dim_nv = 0, dim_nw = 0;
     bool f_l = false, f_m = false;
-    Mat W_m, W_l; SV a_m, a_l;
+    Sparse W_m, W_l; SV a_m, a_l;
     std::vector<int32_t> part[4]; // LO, LL, LR, NO
     std::vector<uint8_t> g64, gvec64, hvec64, gvec2_64, hvec2_64;
     // device: [h_vec | g_vec | g]
     uint32_t *d_pts = nullptr; size_t hn = 0, gn = 0;
     int part_get(int typ, size_t j) const { return j < part[typ].size() ? part[typ][j] : -1; }
-    void release() { cudaFree(d_pts); d_pts = nullptr; }
+    void release() { cudaFree(d_pts); d_pts = nullptr; W_m.release(); W_l.release(); }
 };
 enum { P_LO = 0, P_LL = 1, P_LR = 2, P_NO = 3 };
 
@@ -136,46 +196,30 @@ SV collect_lambda(const Circuit &c, const Sc &lambda, const Sc &mu) {
                            tensor(e_pow(mu, c.dim_nv), e_pow(pow_u64(lambda, c.dim_nv), c.k))));
     return lv;
 }
-Mat sub_cols(const Mat &W, size_t rows, size_t from, size_t to) {
-    Mat m; m.rows = rows; m.cols = to - from; m.v.resize(m.rows * m.cols);
-    for (size_t i = 0; i < rows; i++) for (size_t j = from; j < to; j++) m.v[i * m.cols + (j - from)] = W.v[i * W.cols + j];
-    return m;
-}
-// vector_mul_on_matrix(a, map_f(..)) of circuit.rs:627-653 without building map_f's isz x jsz matrix (dim_nl x dim_nv scalars,
-// almost all zero): out[j] = sum_i a[i] Wx[i][partition(typ, j)] for the j the partition maps, zero elsewhere
-SV vmat_mapped(const SV &a, const Circuit &c, size_t isz, size_t jsz, int typ, const Mat &Wx) {
-    SV r(jsz, sc_zero());
-    const Sc one = sc_one();
-    size_t rows = std::min(a.size(), isz);
-    for (size_t j = 0; j < jsz; j++) {
-        int j_ = c.part_get(typ, j);
-        if (j_ < 0 || (size_t)j_ >= Wx.cols) continue;
-        Sc acc = sc_zero();
-        for (size_t i = 0; i < rows; i++) {
-            const Sc &e = Wx.v[i * Wx.cols + (size_t)j_];
-            if (sc_is_zero(e) || sc_is_zero(a[i])) continue;
-            acc = sc_add(acc, sc_eq(e, one) ? a[i] : sc_mul(a[i], e));
-        }
-        r[j] = acc;
-    }
-    return r;
-}
 struct Coefs { SV nL, nR, nO, lL, lR, lO; };
+// circuit.rs:584-653.  u = lambda_vec x W_l and v = mu_vec x W_m over ALL dim_nw columns (two sparse products on the device);
+// the twelve blocks the reference slices out of W (W_lL, W_lR, W_lO, W_mL, W_mR, W_mO and the partition-mapped copies of the
+// O blocks, circuit.rs:627-653) are then index ranges / gathers of u and v.
 Coefs collect_c(const Circuit &c, const SV &lambda_vec, const SV &mu_vec, const Sc &mu) {
     size_t nm = c.dim_nm;
-    Mat W_lO = sub_cols(c.W_l, c.dim_nl, 2 * nm, c.W_l.cols), W_mO = sub_cols(c.W_m, c.dim_nm, 2 * nm, c.W_m.cols);
+    SV u, v;
+    if (spmv(lambda_vec, c.W_l, u) != BPPP_OK || spmv(mu_vec, c.W_m, v) != BPPP_OK) throw Panic{ST_BAD_ARG};
+    SV d = vsub(u, v);                                     // (lambda_vec W_l - mu_vec W_m), dim_nw entries
     // diag_inv(mu, nm) (util.rs:118-132) applied as a diagonal scaling
     Sc mu_inv = inv_or_panic(mu);
     SV dinv(nm); Sc val = sc_one();
     for (size_t i = 0; i < nm; i++) { val = sc_mul(val, mu_inv); dinv[i] = val; }
-    auto scale_diag = [&](SV v) { v.resize(nm, sc_zero()); for (size_t j = 0; j < nm; j++) v[j] = sc_mul(v[j], dinv[j]); return v; };
+    auto mapped = [&](int typ, size_t jsz) {               // column j of the mapped O block is column partition(typ, j) of W_xO
+        SV r(jsz, sc_zero());
+        for (size_t j = 0; j < jsz; j++) { int j_ = c.part_get(typ, j); if (j_ >= 0) r[j] = d[2 * nm + (size_t)j_]; }
+        return r;
+    };
     Coefs r;
-    r.nL = scale_diag(vsub(vmat_cols(lambda_vec, c.W_l, c.dim_nl, 0, nm), vmat_cols(mu_vec, c.W_m, c.dim_nm, 0, nm)));
-    r.nR = scale_diag(vsub(vmat_cols(lambda_vec, c.W_l, c.dim_nl, nm, 2 * nm), vmat_cols(mu_vec, c.W_m, c.dim_nm, nm, 2 * nm)));
-    r.nO = scale_diag(vsub(vmat_mapped(lambda_vec, c, c.dim_nl, c.dim_nm, P_NO, W_lO), vmat_mapped(mu_vec, c, c.dim_nm, c.dim_nm, P_NO, W_mO)));
-    r.lL = vsub(vmat_mapped(lambda_vec, c, c.dim_nl, c.dim_nv, P_LL, W_lO), vmat_mapped(mu_vec, c, c.dim_nm, c.dim_nv, P_LL, W_mO));
-    r.lR = vsub(vmat_mapped(lambda_vec, c, c.dim_nl, c.dim_nv, P_LR, W_lO), vmat_mapped(mu_vec, c, c.dim_nm, c.dim_nv, P_LR, W_mO));
-    r.lO = vsub(vmat_mapped(lambda_vec, c, c.dim_nl, c.dim_nv, P_LO, W_lO), vmat_mapped(mu_vec, c, c.dim_nm, c.dim_nv, P_LO, W_mO));
+    r.nL.resize(nm); r.nR.resize(nm);
+    for (size_t j = 0; j < nm; j++) { r.nL[j] = sc_mul(d[j], dinv[j]); r.nR[j] = sc_mul(d[nm + j], dinv[j]); }
+    r.nO = mapped(P_NO, nm);
+    for (size_t j = 0; j < nm; j++) r.nO[j] = sc_mul(r.nO[j], dinv[j]);
+    r.lL = mapped(P_LL, c.dim_nv); r.lR = mapped(P_LR, c.dim_nv); r.lO = mapped(P_LO, c.dim_nv);
     return r;
 }
 SV make_cr_tau(const Sc &tau, const Sc &tau_inv, const Sc &tau2, const Sc &tau3, const Sc &beta) {
@@ -352,7 +396,7 @@ int circuit_verify(const Circuit &c, const std::vector<std::vector<uint8_t>> &v3
         }
         uint32_t *d_p = nullptr, *d_s = nullptr;
         rc = decode_points_to_device(nullptr, pb.data(), FMT_COMPRESSED, np, &d_p);
-        if (rc != BPPP_OK) { *verdict = ST_BAD_POINT; cudaFree(d_pt30); cudaFree(d_com30); return BPPP_OK; }
+        if (rc != BPPP_OK) { cudaFree(d_pt30); cudaFree(d_com30); if (rc != BPPP_ERR_ENCODING) return rc; *verdict = ST_BAD_POINT; return BPPP_OK; }
         rc = decode_scalars_to_device(nullptr, sb.data(), np, &d_s);
         if (rc == BPPP_OK) rc = msm_device(nullptr, d_p, d_s, np, d_pt30, d_com30);
         cudaFree(d_p); cudaFree(d_s);
@@ -366,7 +410,7 @@ int circuit_verify(const Circuit &c, const std::vector<std::vector<uint8_t>> &v3
     return rc;
 }
 
-int load_scalars(SV &out, const uint8_t *b, size_t n) { out.resize(n); for (size_t i = 0; i < n; i++) if (!sc_from_be32(out[i], b + 32 * i)) return fail(BPPP_ERR_ARG, "a scalar is not canonical (>= n)"); return BPPP_OK; }
+int load_scalars(SV &out, const uint8_t *b, size_t n) { out.resize(n); for (size_t i = 0; i < n; i++) if (!sc_from_be32(out[i], b + 32 * i)) return fail(BPPP_ERR_ENCODING, "a scalar is not canonical (>= n)"); return BPPP_OK; }
 
 int pick_device(int device) {
     int ndev = 0;
@@ -376,20 +420,89 @@ int pick_device(int device) {
     return BPPP_OK;
 }
 
+// the descriptor checks the reference enforces by panicking (index out of bounds): reject instead of reading past a buffer
+int circuit_check_shape(size_t dim_nm, size_t dim_no, size_t k, size_t dim_nv, size_t gn, size_t hn, const int32_t *const parts[4], size_t part_n) {
+    if (dim_nv < 1 || k < 1) return fail(BPPP_ERR_ARG, "circuit: dim_nv and k must be at least 1");
+    if (gn < dim_nm) return fail(BPPP_ERR_ARG, "circuit: g_vec needs dim_nm points (circuit.rs:148-150 indexes it)");
+    if (hn < dim_nv + 9) return fail(BPPP_ERR_ARG, "circuit: h_vec needs dim_nv + 9 points (circuit.rs:148-150)");
+    (void)dim_nm;      // indices at or beyond part_n read as None (documented in bppp.h): a short table is a sparse partition, not an error
+    for (int t = 0; t < 4; t++) {
+        if (part_n && !parts[t]) return fail(BPPP_ERR_ARG, "circuit: null partition table");
+        for (size_t j = 0; j < part_n; j++)
+            if (parts[t][j] < -1 || (parts[t][j] >= 0 && (size_t)parts[t][j] >= dim_no)) return fail(BPPP_ERR_ARG, "circuit: partition entry outside [-1, dim_no) (the reference would index w_o out of bounds)");
+    }
+    return BPPP_OK;
+}
+int circuit_common(Circuit &c, size_t dim_nm, size_t dim_no, size_t k, size_t dim_nv, int f_l, int f_m, const uint8_t *g64, const uint8_t *gvec64, size_t gn, const uint8_t *hvec64,
+                   size_t hn, const uint8_t *gvec2_64, size_t gn2, const uint8_t *hvec2_64, size_t hn2, const uint8_t *a_m32, const uint8_t *a_l32,
+                   const int32_t *const parts[4], size_t part_n) {
+    if (!g64 || (gn && !gvec64) || (hn && !hvec64) || (gn2 && !gvec2_64) || (hn2 && !hvec2_64) || !a_m32 || !a_l32) return fail(BPPP_ERR_ARG, "circuit: null pointer with a non-zero size");
+    int rc = circuit_check_shape(dim_nm, dim_no, k, dim_nv, gn, hn, parts, part_n);
+    if (rc != BPPP_OK) return rc;
+    c.dim_nm = dim_nm; c.dim_no = dim_no; c.k = k; c.dim_nv = dim_nv; c.dim_nl = dim_nv * k; c.dim_nw = 2 * dim_nm + dim_no;
+    c.f_l = f_l != 0; c.f_m = f_m != 0;
+    c.g64.assign(g64, g64 + 64);
+    c.gvec64.assign(gvec64, gvec64 + 64 * gn); c.hvec64.assign(hvec64, hvec64 + 64 * hn);
+    c.gvec2_64.assign(gvec2_64, gvec2_64 + 64 * gn2); c.hvec2_64.assign(hvec2_64, hvec2_64 + 64 * hn2);
+    if ((rc = load_scalars(c.a_m, a_m32, c.dim_nm)) != BPPP_OK) return rc;
+    if ((rc = load_scalars(c.a_l, a_l32, c.dim_nl)) != BPPP_OK) return rc;
+    for (int t = 0; t < 4; t++) c.part[t].assign(parts[t], parts[t] + part_n);
+    return BPPP_OK;
+}
+int sparse_from_dense(Sparse &m, const uint8_t *W32, size_t rows, size_t cols) {
+    if (rows * cols && !W32) return fail(BPPP_ERR_ARG, "circuit: null matrix");
+    ValueDict dict(m);
+    std::vector<uint32_t> tr, tc, tv;
+    for (size_t i = 0; i < rows; i++)
+        for (size_t j = 0; j < cols; j++) {
+            Sc e;
+            if (!sc_from_be32(e, W32 + 32 * (i * cols + j))) return fail(BPPP_ERR_ENCODING, "a scalar is not canonical (>= n)");
+            if (sc_is_zero(e)) continue;
+            tr.push_back((uint32_t)i); tc.push_back((uint32_t)j); tv.push_back(dict.id(e));
+        }
+    sparse_from_triples(m, rows, cols, tr, tc, tv);
+    return sparse_upload(m);
+}
+int sparse_from_csr(Sparse &m, const bppp_sparse_matrix *d, size_t rows, size_t cols) {
+    if (!d || d->rows != rows || d->cols != cols || !d->row_ptr || (d->nnz && (!d->col_idx || !d->values32))) return fail(BPPP_ERR_ARG, "circuit: sparse matrix shape / pointers");
+    if (d->row_ptr[0] != 0 || d->row_ptr[rows] != d->nnz || d->nnz >= 0xFFFFFFFFull) return fail(BPPP_ERR_ARG, "circuit: sparse matrix row_ptr does not span nnz");
+    const size_t nvals = d->value_idx ? d->n_values : d->nnz;
+    SV vals(nvals);
+    for (size_t k = 0; k < nvals; k++) if (!sc_from_be32(vals[k], d->values32 + 32 * k)) return fail(BPPP_ERR_ENCODING, "a scalar is not canonical (>= n)");
+    ValueDict dict(m);
+    std::vector<uint32_t> ids(nvals);
+    for (size_t k = 0; k < nvals; k++) ids[k] = dict.id(vals[k]);
+    std::vector<uint32_t> tr, tc, tv;
+    tr.reserve(d->nnz); tc.reserve(d->nnz); tv.reserve(d->nnz);
+    for (size_t i = 0; i < rows; i++) {
+        if (d->row_ptr[i + 1] < d->row_ptr[i] || d->row_ptr[i + 1] > d->nnz) return fail(BPPP_ERR_ARG, "circuit: sparse matrix row_ptr not monotone");
+        for (uint64_t k = d->row_ptr[i]; k < d->row_ptr[i + 1]; k++) {
+            if (d->col_idx[k] >= cols) return fail(BPPP_ERR_ARG, "circuit: sparse matrix column index out of range");
+            size_t vi = d->value_idx ? d->value_idx[k] : (size_t)k;
+            if (vi >= nvals) return fail(BPPP_ERR_ARG, "circuit: sparse matrix value index out of range");
+            if (sc_is_zero(vals[vi])) continue;
+            tr.push_back((uint32_t)i); tc.push_back(d->col_idx[k]); tv.push_back(ids[vi]);
+        }
+    }
+    sparse_from_triples(m, rows, cols, tr, tc, tv);
+    return sparse_upload(m);
+}
 int circuit_from_desc(Circuit &c, const bppp_circuit_desc *d) {
-    c.dim_nm = d->dim_nm; c.dim_no = d->dim_no; c.k = d->k; c.dim_nv = d->dim_nv; c.dim_nl = d->dim_nv * d->k; c.dim_nw = 2 * d->dim_nm + d->dim_no;
-    c.f_l = d->f_l != 0; c.f_m = d->f_m != 0;
-    c.g64.assign(d->g64, d->g64 + 64);
-    c.gvec64.assign(d->gvec64, d->gvec64 + 64 * d->gn); c.hvec64.assign(d->hvec64, d->hvec64 + 64 * d->hn);
-    c.gvec2_64.assign(d->gvec2_64, d->gvec2_64 + 64 * d->gn2); c.hvec2_64.assign(d->hvec2_64, d->hvec2_64 + 64 * d->hn2);
-    c.W_m.rows = c.dim_nm; c.W_m.cols = c.dim_nw; c.W_l.rows = c.dim_nl; c.W_l.cols = c.dim_nw;
-    int rc;
-    if ((rc = load_scalars(c.W_m.v, d->W_m32, c.dim_nm * c.dim_nw)) != BPPP_OK) return rc;
-    if ((rc = load_scalars(c.W_l.v, d->W_l32, c.dim_nl * c.dim_nw)) != BPPP_OK) return rc;
-    if ((rc = load_scalars(c.a_m, d->a_m32, c.dim_nm)) != BPPP_OK) return rc;
-    if ((rc = load_scalars(c.a_l, d->a_l32, c.dim_nl)) != BPPP_OK) return rc;
     const int32_t *parts[4] = {d->part_lo, d->part_ll, d->part_lr, d->part_no};
-    for (int t = 0; t < 4; t++) c.part[t].assign(parts[t], parts[t] + d->part_n);
+    int rc = circuit_common(c, d->dim_nm, d->dim_no, d->k, d->dim_nv, d->f_l, d->f_m, d->g64, d->gvec64, d->gn, d->hvec64, d->hn, d->gvec2_64, d->gn2, d->hvec2_64, d->hn2,
+                            d->a_m32, d->a_l32, parts, d->part_n);
+    if (rc != BPPP_OK) return rc;
+    if ((rc = sparse_from_dense(c.W_m, d->W_m32, c.dim_nm, c.dim_nw)) != BPPP_OK) return rc;
+    if ((rc = sparse_from_dense(c.W_l, d->W_l32, c.dim_nl, c.dim_nw)) != BPPP_OK) return rc;
+    return circuit_upload(c);
+}
+int circuit_from_sparse_desc(Circuit &c, const bppp_circuit_desc_sparse *d) {
+    const int32_t *parts[4] = {d->part_lo, d->part_ll, d->part_lr, d->part_no};
+    int rc = circuit_common(c, d->dim_nm, d->dim_no, d->k, d->dim_nv, d->f_l, d->f_m, d->g64, d->gvec64, d->gn, d->hvec64, d->hn, d->gvec2_64, d->gn2, d->hvec2_64, d->hn2,
+                            d->a_m32, d->a_l32, parts, d->part_n);
+    if (rc != BPPP_OK) return rc;
+    if ((rc = sparse_from_csr(c.W_m, &d->W_m, c.dim_nm, c.dim_nw)) != BPPP_OK) return rc;
+    if ((rc = sparse_from_csr(c.W_l, &d->W_l, c.dim_nl, c.dim_nw)) != BPPP_OK) return rc;
     return circuit_upload(c);
 }
 
@@ -403,36 +516,54 @@ size_t write_circuit_record(uint8_t *out, const CircuitProofHost &p) {
     return (size_t)(o - out);
 }
 
-// reciprocal.rs:150-214 with the np distinct inverses computed once (the reference recomputes them per row)
-void make_reciprocal_circuit(Circuit &c, size_t nd, size_t np, const Sc &e) {
+// reciprocal.rs:150-214 built directly in sparse form (the reference materialises dense (nd + 1) x (2 nd + np) matrices and
+// recomputes the np distinct inverses per row): W_m has nd entries, W_l nd + nd (nd - 1) ones + nd np inverses
+int make_reciprocal_circuit(Circuit &c, size_t nd, size_t np, const Sc &e) {
     c.dim_nm = nd; c.dim_no = np; c.k = 1; c.dim_nv = nd + 1; c.dim_nl = nd + 1; c.dim_nw = 2 * nd + np;
     c.f_l = true; c.f_m = false;
     c.a_m.assign(nd, sc_one()); c.a_l.assign(nd + 1, sc_zero());
-    c.W_m.rows = nd; c.W_m.cols = c.dim_nw; c.W_m.v.assign(nd * c.dim_nw, sc_zero());
-    Sc me = sc_neg(e);
-    for (size_t i = 0; i < nd; i++) c.W_m.v[i * c.dim_nw + i + nd] = me;
-    c.W_l.rows = nd + 1; c.W_l.cols = c.dim_nw; c.W_l.v.assign((nd + 1) * c.dim_nw, sc_zero());
-    Sc base = sc_from_u64((uint64_t)(uint32_t)np), pw = sc_one();
-    for (size_t i = 0; i < nd; i++) { c.W_l.v[i] = sc_neg(pw); pw = sc_mul(pw, base); }
-    SV inv(np);
-    for (size_t j = 0; j < np; j++) inv[j] = sc_neg(inv_or_panic(sc_add(e, sc_from_u64((uint64_t)(uint32_t)j))));
-    for (size_t i = 0; i < nd; i++) {
-        Sc *row = &c.W_l.v[(i + 1) * c.dim_nw];
-        for (size_t j = 0; j < nd; j++) row[j + nd] = j == i ? sc_zero() : sc_one();
-        for (size_t j = 0; j < np; j++) row[j + 2 * nd] = inv[j];
+    c.W_m.release(); c.W_l.release();
+    c.W_m = Sparse(); c.W_l = Sparse();
+    std::vector<uint32_t> tr, tc, tv;
+    {
+        ValueDict dict(c.W_m);
+        uint32_t me = dict.id(sc_neg(e));
+        for (size_t i = 0; i < nd; i++) { tr.push_back((uint32_t)i); tc.push_back((uint32_t)(i + nd)); tv.push_back(me); }       // -e on w_R (reciprocal.rs:166-169)
+        sparse_from_triples(c.W_m, nd, c.dim_nw, tr, tc, tv);
+    }
+    tr.clear(); tc.clear(); tv.clear();
+    {
+        ValueDict dict(c.W_l);
+        Sc base = sc_from_u64((uint64_t)(uint32_t)np), pw = sc_one();
+        for (size_t i = 0; i < nd; i++) { tr.push_back(0); tc.push_back((uint32_t)i); tv.push_back(dict.id(sc_neg(pw))); pw = sc_mul(pw, base); }    // :172-176
+        std::vector<uint32_t> inv(np);
+        for (size_t j = 0; j < np; j++) inv[j] = dict.id(sc_neg(inv_or_panic(sc_add(e, sc_from_u64((uint64_t)(uint32_t)j)))));
+        tr.reserve(nd * (nd + np)); tc.reserve(nd * (nd + np)); tv.reserve(nd * (nd + np));
+        for (size_t i = 0; i < nd; i++) {
+            for (size_t j = 0; j < nd; j++) if (j != i) { tr.push_back((uint32_t)(i + 1)); tc.push_back((uint32_t)(j + nd)); tv.push_back(0); }       // ones, :178-180
+            for (size_t j = 0; j < np; j++) { tr.push_back((uint32_t)(i + 1)); tc.push_back((uint32_t)(j + 2 * nd)); tv.push_back(inv[j]); }           // :181-183
+        }
+        sparse_from_triples(c.W_l, nd + 1, c.dim_nw, tr, tc, tv);
     }
     size_t pn = nd + 1;
     for (int t = 0; t < 4; t++) { c.part[t].assign(pn, -1); }
     for (size_t j = 0; j < pn && j < np; j++) c.part[P_LL][j] = (int32_t)j;
+    int rc = sparse_upload(c.W_m);
+    if (rc == BPPP_OK) rc = sparse_upload(c.W_l);
+    return rc;
 }
 
 }  // namespace
 
+static int load_desc(Circuit &c, const bppp_circuit_desc *d) { return circuit_from_desc(c, d); }
+static int load_desc(Circuit &c, const bppp_circuit_desc_sparse *d) { return circuit_from_sparse_desc(c, d); }
+
 // ArithmeticCircuit::commit (src/circuit.rs:146-151)
-extern "C" int bppp_circuit_commit(int device, const bppp_circuit_desc *d, const uint8_t *v32, const uint8_t *s32, uint8_t *out33) {
+template <class Desc>
+static int circuit_commit_any(int device, const Desc *d, const uint8_t *v32, const uint8_t *s32, uint8_t *out33) {
     if (!d || !v32 || !s32 || !out33) return fail(BPPP_ERR_ARG, "null argument");
     int rc = pick_device(device); if (rc != BPPP_OK) return rc;
-    Circuit c; if ((rc = circuit_from_desc(c, d)) != BPPP_OK) return rc;
+    Circuit c; if ((rc = load_desc(c, d)) != BPPP_OK) { c.release(); return rc; }
     SV v, s;
     if ((rc = load_scalars(v, v32, d->dim_nv)) == BPPP_OK && (rc = load_scalars(s, s32, 1)) == BPPP_OK) {
         SV hs(c.hn, sc_zero());
@@ -444,13 +575,17 @@ extern "C" int bppp_circuit_commit(int device, const bppp_circuit_desc *d, const
     return rc;
 }
 
+extern "C" int bppp_circuit_commit(int device, const bppp_circuit_desc *d, const uint8_t *v32, const uint8_t *s32, uint8_t *out33) { return circuit_commit_any(device, d, v32, s32, out33); }
+extern "C" int bppp_circuit_commit_sparse(int device, const bppp_circuit_desc_sparse *d, const uint8_t *v32, const uint8_t *s32, uint8_t *out33) { return circuit_commit_any(device, d, v32, s32, out33); }
+
 // ArithmeticCircuit::prove (src/circuit.rs:260-556), fresh Transcript::new(label).  out: c_l c_r c_o c_s | r | x | l | n
-extern "C" int bppp_circuit_prove(int device, const bppp_circuit_desc *d, const uint8_t *commits33, const uint8_t *v32, const uint8_t *sv32, const uint8_t *wl32,
+template <class Desc>
+static int circuit_prove_any(int device, const Desc *d, const uint8_t *commits33, const uint8_t *v32, const uint8_t *sv32, const uint8_t *wl32,
                                   const uint8_t *wr32, const uint8_t *wo32, const uint8_t *rng_bytes, size_t rng_len, const uint8_t *label, size_t label_len,
                                   uint8_t *out, size_t out_cap, size_t *rounds_out, size_t *l_len_out, size_t *n_len_out, int32_t *status) {
     if (!d || !out || !rounds_out || !l_len_out || !n_len_out || !status) return fail(BPPP_ERR_ARG, "null argument");
     int rc = pick_device(device); if (rc != BPPP_OK) return rc;
-    Circuit c; if ((rc = circuit_from_desc(c, d)) != BPPP_OK) return rc;
+    Circuit c; if ((rc = load_desc(c, d)) != BPPP_OK) { c.release(); return rc; }
     std::vector<std::vector<uint8_t>> v33(d->k);
     std::vector<SV> wv(d->k);
     SV s_v, w_l, w_r, w_o;
@@ -475,12 +610,20 @@ extern "C" int bppp_circuit_prove(int device, const bppp_circuit_desc *d, const 
     return rc;
 }
 
+#define BPPP_PROVE_ARGS const uint8_t *commits33, const uint8_t *v32, const uint8_t *sv32, const uint8_t *wl32, const uint8_t *wr32, const uint8_t *wo32, \
+                        const uint8_t *rng_bytes, size_t rng_len, const uint8_t *label, size_t label_len, uint8_t *out, size_t out_cap, size_t *rounds_out,   \
+                        size_t *l_len_out, size_t *n_len_out, int32_t *status
+#define BPPP_PROVE_PASS commits33, v32, sv32, wl32, wr32, wo32, rng_bytes, rng_len, label, label_len, out, out_cap, rounds_out, l_len_out, n_len_out, status
+extern "C" int bppp_circuit_prove(int device, const bppp_circuit_desc *d, BPPP_PROVE_ARGS) { return circuit_prove_any(device, d, BPPP_PROVE_PASS); }
+extern "C" int bppp_circuit_prove_sparse(int device, const bppp_circuit_desc_sparse *d, BPPP_PROVE_ARGS) { return circuit_prove_any(device, d, BPPP_PROVE_PASS); }
+
 // ArithmeticCircuit::verify (src/circuit.rs:154-256)
-extern "C" int bppp_circuit_verify(int device, const bppp_circuit_desc *d, const uint8_t *commits33, const uint8_t *rec, size_t rounds_r, size_t rounds_x, size_t l_len,
-                                   size_t n_len, const uint8_t *label, size_t label_len, int32_t *verdict) {
+template <class Desc>
+static int circuit_verify_any(int device, const Desc *d, const uint8_t *commits33, const uint8_t *rec, size_t rounds_r, size_t rounds_x, size_t l_len,
+                              size_t n_len, const uint8_t *label, size_t label_len, int32_t *verdict) {
     if (!d || !rec || !verdict) return fail(BPPP_ERR_ARG, "null argument");
     int rc = pick_device(device); if (rc != BPPP_OK) return rc;
-    Circuit c; if ((rc = circuit_from_desc(c, d)) != BPPP_OK) return rc;
+    Circuit c; if ((rc = load_desc(c, d)) != BPPP_OK) { c.release(); return rc; }
     std::vector<std::vector<uint8_t>> v33(d->k);
     for (size_t i = 0; i < d->k; i++) v33[i].assign(commits33 + 33 * i, commits33 + 33 * (i + 1));
     Merlin t; merlin_init(t, label, (uint32_t)label_len);
@@ -489,6 +632,14 @@ extern "C" int bppp_circuit_verify(int device, const bppp_circuit_desc *d, const
     catch (const Panic &p) { *verdict = p.code; }
     c.release();
     return rc;
+}
+extern "C" int bppp_circuit_verify(int device, const bppp_circuit_desc *d, const uint8_t *commits33, const uint8_t *rec, size_t rounds_r, size_t rounds_x, size_t l_len,
+                                   size_t n_len, const uint8_t *label, size_t label_len, int32_t *verdict) {
+    return circuit_verify_any(device, d, commits33, rec, rounds_r, rounds_x, l_len, n_len, label, label_len, verdict);
+}
+extern "C" int bppp_circuit_verify_sparse(int device, const bppp_circuit_desc_sparse *d, const uint8_t *commits33, const uint8_t *rec, size_t rounds_r, size_t rounds_x,
+                                          size_t l_len, size_t n_len, const uint8_t *label, size_t label_len, int32_t *verdict) {
+    return circuit_verify_any(device, d, commits33, rec, rounds_r, rounds_x, l_len, n_len, label, label_len, verdict);
 }
 
 namespace {
@@ -544,7 +695,7 @@ extern "C" int bppp_reciprocal_prove(int device, size_t dim_nd, size_t dim_np, c
         for (size_t i = 0; i < dim_nd; i++) hs[9 + i] = r[i];
         uint8_t rcom33[33], ccom33[33];
         if (rc == BPPP_OK) rc = commit_hg(c, hs, SV(), sc_zero(), rcom33);             // commit_poles, reciprocal.rs:93-95
-        make_reciprocal_circuit(c, dim_nd, dim_np, e);
+        if (rc == BPPP_OK) rc = make_reciprocal_circuit(c, dim_nd, dim_np, e);
         SV v = concat(SV{xs[0]}, r);
         Sc s_tot = sc_add(ss[0], r_blind);
         SV hs2(c.hn, sc_zero()); hs2[0] = s_tot;
@@ -580,13 +731,15 @@ extern "C" int bppp_reciprocal_verify(int device, size_t dim_nd, size_t dim_np, 
         Merlin t; merlin_init(t, label, (uint32_t)label_len);
         merlin_append(t, BPPP_LBL("reciprocal_commitment"), commit33, 33);
         Sc e; challenge(t, BPPP_LBL("reciprocal_challenge"), e);
-        make_reciprocal_circuit(c, dim_nd, dim_np, e);
+        rc = make_reciprocal_circuit(c, dim_nd, dim_np, e);
+        if (rc != BPPP_OK) { c.release(); return rc; }
         const uint8_t *r33 = rec + 132, *x33 = r33 + 33 * rounds_r, *l32 = x33 + 33 * rounds_x, *n32 = l32 + 32 * l_len, *pr = n32 + 32 * n_len;
         // circuit_commitment = commitment + proof.r  (reciprocal.rs:104)
         uint8_t two_pts[66], vp33[33];
         memcpy(two_pts, commit33, 33); memcpy(two_pts + 33, pr, 33);
         rc = bppp_points_sum(device, two_pts, FMT_COMPRESSED, 2, FMT_COMPRESSED, vp33);
-        if (rc != BPPP_OK) { *verdict = ST_BAD_POINT; rc = BPPP_OK; }
+        if (rc == BPPP_ERR_ENCODING) { *verdict = ST_BAD_POINT; rc = BPPP_OK; }
+        else if (rc != BPPP_OK) { c.release(); return rc; }
         else {
             std::vector<std::vector<uint8_t>> v33{std::vector<uint8_t>(vp33, vp33 + 33)};
             rc = circuit_verify(c, v33, t, rec, rec + 33, rec + 66, rec + 99, r33, rounds_r, x33, rounds_x, l32, l_len, n32, n_len, verdict);

@@ -47,6 +47,7 @@ struct bppp_ctx {
     // so that tail waves and low-parallelism kernels of one sub-batch overlap with work of the others
     static constexpr int MAX_SUB = 8;
     int nsub = 2;
+    int nsub_host = 4;              // host-buffer entry points: more, smaller sub-batches so that the first upload (3.3 KB of RNG bytes per proof for prove) is short
     cudaStream_t sub_stream[MAX_SUB] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
     uint64_t launches = 0;
@@ -105,7 +106,7 @@ static inline TermMap identity_map() { TermMap tm; for (int t = 0; t < NUM_GENS;
 // sub-batch plan for a slice of n proofs: part k covers [lo[k], lo[k+1]) and owns workspace words starting at
 // d_ws + words_per_proof * lo[k] with row stride (lo[k+1] - lo[k])
 struct SubPlan { int parts; size_t lo[bppp_ctx::MAX_SUB + 1]; };
-SubPlan plan_sub(bppp_ctx *c, size_t n);     // also records the number of concurrent parts in c->active_parts
+SubPlan plan_sub(bppp_ctx *c, size_t n, bool host_buffers = false);     // also records the number of concurrent parts in c->active_parts
 int fork_streams(bppp_ctx *c, cudaStream_t caller, const SubPlan &sp);
 int join_streams(bppp_ctx *c, cudaStream_t caller, const SubPlan &sp);
 static inline WS sub_ws(const bppp_ctx *c, const SubPlan &sp, int k) {

@@ -128,9 +128,9 @@ __global__ void __launch_bounds__(128) k_tab_write(WS tmp, uint4 *dst) {
 static constexpr int MSM_LANES = BPPP_MSM_LANES;
 
 namespace bppp {
-SubPlan plan_sub(bppp_ctx *c, size_t n) {
+SubPlan plan_sub(bppp_ctx *c, size_t n, bool host_buffers) {
     SubPlan sp;
-    int parts = c->profiling ? 1 : c->nsub;          // per-kernel timing wants kernels back to back on one stream
+    int parts = c->profiling ? 1 : (host_buffers ? c->nsub_host : c->nsub);          // per-kernel timing wants kernels back to back on one stream
     const size_t min_part = 2048;                    // below this a sub-batch cannot fill the GPU anyway
     while (parts > 1 && n / parts < min_part) parts--;
     sp.parts = parts;
@@ -229,6 +229,7 @@ static int alloc_work(bppp_ctx *c, size_t max_batch) {
     c->sm_count = prop.multiProcessorCount;
     CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     if (const char *e = getenv("BPPP_NSUB")) { int v = atoi(e); if (v >= 1 && v <= bppp_ctx::MAX_SUB) c->nsub = v; }
+    if (const char *e = getenv("BPPP_NSUB_HOST")) { int v = atoi(e); if (v >= 1 && v <= bppp_ctx::MAX_SUB) c->nsub_host = v; }
     if (const char *e = getenv("BPPP_MSM_LANES_RT")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16) c->msm_lanes_override = v; }
     if (const char *e = getenv("BPPP_VAR_LANES_RT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->var_lanes_override = v; }
     for (int k = 0; k < bppp_ctx::MAX_SUB; k++) {

@@ -3,13 +3,13 @@
 // scalar multiplication per term) for large n -- WNLA X/R commitments (src/wnla.rs:152-160), wnla.commit
 // (src/wnla.rs:66-72) and the circuit commitments (src/circuit.rs:335-345,469-470,522-524).
 //
-// Pippenger with signed c-bit windows:
-//   k_msm_digits      signed digits of every scalar -> (bucket key, point index | sign) pairs, window-major
-//   cub radix sort    pairs by bucket key (the only library call; it moves 8-byte pairs, no curve arithmetic)
-//   k_msm_bounds      first / one-past-last sorted position of every bucket
-//   k_msm_buckets     one thread per bucket: mixed-adds its points; buckets above the heavy threshold (skewed scalars, the
-//                     partially filled top window) are deferred to k_msm_heavy: one 128-thread block per segment of at
-//                     most MSM_SEG entries, shared-memory tree reduction; k_msm_heavy_sum adds the segments of a bucket
+// Pippenger with signed c-bit windows, every kernel in this file (no library call):
+//   k_msm_digits      signed 16-bit digits of every scalar, window-major
+//   k_msm_hist / k_scan_* / k_msm_scatter   counting sort of the point indices by (window, bucket): shared-memory histograms per
+//                     (chunk, window) block, one exclusive scan, scatter through shared-memory cursors -- no global atomics
+//   k_msm_slices      one thread per 64 consecutive sorted entries (XYZZ mixed additions, next point prefetched): perfectly
+//                     balanced warps; whole buckets are written directly, runs cut by a slice boundary as head / tail pieces
+//   k_msm_fixup(_wide) adds the pieces of cut buckets (a bucket of skewed scalars spanning > 32 slices gets a block)
 //   k_msm_chunks      per window: chunked running-sum reduction  sum_b (b+1) B_b  (two adds per bucket)
 //   k_pt_sum_groups   tree sums;  k_msm_horner: sum_w 2^(c w) W_w
 // Small inputs (n <= 1024) use one GLV scalar multiplication per point and the same tree sum.
@@ -17,7 +17,6 @@
 #define BPPP_PTX_ADD_NOINLINE 1   // ec.cuh: the bucket accumulation's XYZZ addition as one call with inlined products
 #include "engine_generic.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
 #include <mutex>
 
 using namespace bppp;
@@ -82,7 +81,9 @@ __global__ void k_encode_points(const uint32_t *pts30, int fmt, uint8_t *out, si
 }
 
 // ---- Pippenger ----
-__global__ void k_msm_digits(const uint32_t *sc, size_t n, int c, int nwin, uint32_t *keys, uint32_t *vals) {
+// signed c-bit digits of every scalar, window-major, 16 bits each: low 15 bits magnitude - 1 (0x7FFF when the digit is zero
+// ... the magnitude is at most 2^(c-1) <= 2^15, so mag - 1 fits 15 bits), bit 15 = sign.  Zero digits are stored as 0xFFFF.
+__global__ void k_msm_digits(const uint32_t *sc, size_t n, int c, int nwin, uint16_t *digits) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t k[9];
@@ -99,101 +100,195 @@ __global__ void k_msm_digits(const uint32_t *sc, size_t n, int c, int nwin, uint
         uint32_t neg = 0, mag = raw;
         carry = 0;
         if (raw > half) { mag = (1u << c) - raw; neg = 1; carry = 1; }
-        keys[(size_t)w * n + i] = mag == 0 ? (uint32_t)nwin * half : (uint32_t)w * half + (mag - 1);     // zero digits: key nb, sorts last
-        vals[(size_t)w * n + i] = (uint32_t)i | (neg << 31);
+        digits[(size_t)w * n + i] = mag == 0 ? (uint16_t)0xFFFFu : (uint16_t)((mag - 1) | (neg << 15));
     }
 }
-
-// Buckets holding more than `heavy_thr` entries go to the block-per-bucket kernel.  The threshold follows the mean bucket
-// size (max(32, 2 n / 2^(c-1))): skewed scalars, and the partially filled top window of every MSM (its few buckets share
-// all n points), would otherwise serialise the launch behind a handful of threads.
-
-__global__ void k_msm_bounds(const uint32_t *keys, size_t total, uint32_t nb, uint32_t *start, uint32_t *end) {
-    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= total) return;
-    uint32_t k = keys[p];
-    if (k >= nb) return;
-    if (p == 0 || keys[p - 1] != k) start[k] = (uint32_t)p;
-    if (p + 1 == total || keys[p + 1] != k) end[k] = (uint32_t)(p + 1);
-}
-__device__ __forceinline__ Pt msm_accumulate_range(const uint32_t *pts, const uint32_t *vals, uint32_t p0, uint32_t p1, uint32_t stride) {
-    PtX acc = ptx_identity();             // XYZZ accumulator: 8 M + 2 S per point, exceptional cases handled exactly
-#pragma unroll 1
-    for (uint32_t p = p0; p < p1; p += stride) {
-        uint32_t v = vals[p];
-        PtA q;
-        if (load_dev_point(q, pts, v & 0x7FFFFFFFu)) {
-            if (v >> 31) q.y = fe_normalize_weak(fe_negate(q.y, 1));
-            acc = ptx_add_mixed_hot(acc, q);
+// Counting sort of the (window, bucket) keys without a library and without global atomics.  Pass 1: block (j, w) histograms
+// chunk j of window w's digits in shared memory (2^(c-1) counters, 128 KB at c = 16) and writes the counts to
+// counts[(w * half + b) * NCH + j]; an exclusive scan of that array gives every bucket's start (entry b * NCH).
+// The order inside a bucket depends on thread timing; bucket SUMS do not (exact group arithmetic).
+__global__ void __launch_bounds__(1024) k_msm_hist(const uint16_t *digits, size_t n, uint32_t half, uint32_t nch, uint32_t *counts) {
+    extern __shared__ uint32_t sh[];
+    const uint32_t j = blockIdx.x, w = blockIdx.y;
+    for (uint32_t b = threadIdx.x; b < half; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    size_t per = (n + nch - 1) / nch; per = (per + 7) & ~(size_t)7;           // chunk starts stay 16-byte aligned
+    const size_t lo = (size_t)j * per < n ? (size_t)j * per : n, hi = lo + per < n ? lo + per : n;
+    const uint16_t *d16 = digits + (size_t)w * n + lo;
+    const size_t m = hi - lo, m8 = (reinterpret_cast<uintptr_t>(d16) & 15) == 0 ? m / 8 : 0;
+    for (size_t i = threadIdx.x; i < m8; i += blockDim.x) {
+        uint4 q = __ldg(reinterpret_cast<const uint4 *>(d16) + i);
+        const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t a = wd[k] & 0xFFFFu, b = wd[k] >> 16;
+            if (a != 0xFFFFu) atomicAdd(&sh[a & 0x7FFFu], 1u);
+            if (b != 0xFFFFu) atomicAdd(&sh[b & 0x7FFFu], 1u);
         }
     }
-    return ptx_to_pt(acc);
-}
-// bucket sums are stored AoS, PT_W words per point
-static constexpr uint32_t MSM_SEG = 2048;     // entries per heavy-bucket work item (16 per thread of a 128-thread block)
-// Heavy work items: region M (slots [0, capM)) holds buckets of thr < size <= MSM_SEG, one slot each; region L (slots
-// [capM, capM + capL)) holds the segments of larger buckets.  capL = 2 total / MSM_SEG can never overflow (every such bucket
-// needs at most size / MSM_SEG + 1 <= 2 size / MSM_SEG slots); a bucket that finds region M full is summed in place.
-struct HeavyQueue {
-    uint32_t *count;      // [0] region M, [1] region L
-    uint32_t *bucket;     // per slot: bucket id
-    uint32_t *seg;        // per slot: segment index within its bucket
-    uint32_t *seg_out;    // per slot of region L: partial sum (PT_W words)
-    uint32_t capM, capL;
-};
-__global__ void __launch_bounds__(64, 7) k_msm_buckets(const uint32_t *pts, const uint32_t *vals, const uint32_t *start, const uint32_t *end, uint32_t nb,
-                                                        uint32_t *buckets, HeavyQueue hq, uint32_t heavy_thr) {
-    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    uint32_t p0 = start[b], p1 = end[b], size = p1 - p0;
-    if (size > MSM_SEG) {
-        uint32_t nseg = (size + MSM_SEG - 1) / MSM_SEG;
-        uint32_t slot = hq.capM + atomicAdd(hq.count + 1, nseg);
-        for (uint32_t k = 0; k < nseg; k++) { hq.bucket[slot + k] = (uint32_t)b; hq.seg[slot + k] = k; }
-        return;                                            // k_msm_heavy_sum writes the bucket
-    }
-    if (size > heavy_thr) {
-        uint32_t slot = atomicAdd(hq.count, 1u);
-        if (slot < hq.capM) { hq.bucket[slot] = (uint32_t)b; hq.seg[slot] = 0; return; }      // k_msm_heavy writes the bucket
-    }
-    st_pt30(buckets + PT_W * b, msm_accumulate_range(pts, vals, p0, p1, 1));
-}
-__global__ void __launch_bounds__(128) k_msm_heavy(const uint32_t *pts, const uint32_t *vals, const uint32_t *start, const uint32_t *end, HeavyQueue hq,
-                                                    uint32_t *buckets) {
-    __shared__ uint32_t sh[128 * PT_W];
-    const uint32_t slot = blockIdx.x;
-    const bool large = slot >= hq.capM;
-    uint32_t cnt = large ? hq.count[1] : hq.count[0];
-    if (!large && cnt > hq.capM) cnt = hq.capM;
-    if ((large ? slot - hq.capM : slot) >= cnt) return;
-    uint32_t b = hq.bucket[slot], k = hq.seg[slot];
-    uint32_t p0 = start[b] + k * MSM_SEG, p1 = end[b];
-    if (p1 - p0 > MSM_SEG && large) p1 = p0 + MSM_SEG;
-    Pt acc = msm_accumulate_range(pts, vals, p0 + threadIdx.x, p1, 128);
-    st_pt30(sh + PT_W * threadIdx.x, acc);
+    for (size_t i = m8 * 8 + threadIdx.x; i < m; i += blockDim.x) { uint16_t d = d16[i]; if (d != 0xFFFFu) atomicAdd(&sh[d & 0x7FFFu], 1u); }
     __syncthreads();
-    for (int s = 64; s >= 1; s >>= 1) {
-        if ((int)threadIdx.x < s) st_pt30(sh + PT_W * threadIdx.x, pt_add(ld_pt30(sh + PT_W * threadIdx.x), ld_pt30(sh + PT_W * (threadIdx.x + s))));
+    for (uint32_t b = threadIdx.x; b < half; b += blockDim.x) counts[((size_t)w * half + b) * nch + j] = sh[b];
+}
+// Pass 2: block (r, w) owns the bucket RANGE [r * span, (r + 1) * span) of window w, streams all n digits of the window
+// (coalesced 16-bit reads) and scatters the entries of its buckets through shared-memory cursors.  The block's writes land
+// in one contiguous region of `vals` (its buckets are adjacent), so they combine in L2 instead of dirtying a 32-byte sector
+// per 4-byte entry all over the array (a chunk-of-scalars scatter measured 0.75 ms at 2^21 points against 0.14 ms for pass 1).
+__global__ void __launch_bounds__(1024) k_msm_scatter(const uint16_t *digits, size_t n, uint32_t half, uint32_t span, uint32_t nch, const uint32_t *scan, uint32_t *vals) {
+    extern __shared__ uint32_t sh[];
+    const uint32_t w = blockIdx.y, base = blockIdx.x * span, top = base + span < half ? base + span : half;
+    for (uint32_t b = base + threadIdx.x; b < top; b += blockDim.x) sh[b - base] = scan[((size_t)w * half + b) * nch];
+    __syncthreads();
+    const uint16_t *d16 = digits + (size_t)w * n;
+    auto place = [&](uint32_t d, size_t i) {
+        uint32_t b = d & 0x7FFFu;
+        if (d != 0xFFFFu && b >= base && b < top) vals[atomicAdd(&sh[b - base], 1u)] = (uint32_t)i | ((d >> 15) << 31);
+    };
+    // eight digits per 16-byte load: one load in flight per warp made this pass latency-bound (1.1 ms at 2^21 points)
+    const size_t n8 = (reinterpret_cast<uintptr_t>(d16) & 15) == 0 ? n / 8 : 0;
+    for (size_t i = threadIdx.x; i < n8; i += blockDim.x) {
+        uint4 q = __ldg(reinterpret_cast<const uint4 *>(d16) + i);
+        const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) { place(wd[k] & 0xFFFFu, 8 * i + 2 * k); place(wd[k] >> 16, 8 * i + 2 * k + 1); }
+    }
+    for (size_t i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) place(d16[i], i);
+}
+// exclusive prefix sum of `count` 32-bit values (+ the total at out[count]) in three launches: 2048 values per block,
+// one block over the block totals, offsets added back
+__global__ void __launch_bounds__(256) k_scan_blocks(const uint32_t *in, size_t count, uint32_t *out, uint32_t *block_sums) {
+    __shared__ uint32_t sh[256];
+    const size_t base = (size_t)blockIdx.x * 2048 + (size_t)threadIdx.x * 8;
+    uint32_t v[8], run = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { v[k] = base + k < count ? in[base + k] : 0u; run += v[k]; }
+    sh[threadIdx.x] = run;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {
+        uint32_t t = (int)threadIdx.x >= off ? sh[threadIdx.x - off] : 0u;
+        __syncthreads();
+        sh[threadIdx.x] += t;
         __syncthreads();
     }
-    if (threadIdx.x == 0) st_pt30(large ? hq.seg_out + PT_W * (size_t)(slot - hq.capM) : buckets + PT_W * (size_t)b, ld_pt30(sh));
+    uint32_t excl = sh[threadIdx.x] - run;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { if (base + k < count) out[base + k] = excl; excl += v[k]; }
+    if (threadIdx.x == 255) block_sums[blockIdx.x] = sh[255];
 }
-// region L: the block of a bucket's first segment adds the partial sums of all its segments (they occupy adjacent slots)
-__global__ void __launch_bounds__(128) k_msm_heavy_sum(const uint32_t *start, const uint32_t *end, HeavyQueue hq, uint32_t *buckets) {
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t *block_sums, size_t nblk, uint32_t *total_out) {
+    __shared__ uint32_t sh[1024];
+    uint32_t carry = 0;
+    for (size_t base = 0; base < nblk; base += 1024) {
+        size_t i = base + threadIdx.x;
+        uint32_t v = i < nblk ? block_sums[i] : 0u;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            uint32_t t = (int)threadIdx.x >= off ? sh[threadIdx.x - off] : 0u;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nblk) block_sums[i] = carry + sh[threadIdx.x] - v;
+        carry += sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+__global__ void __launch_bounds__(256) k_scan_add(uint32_t *out, size_t count, const uint32_t *block_sums) {
+    const size_t base = (size_t)blockIdx.x * 2048 + (size_t)threadIdx.x * 8;
+    const uint32_t add = block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (base + k < count) out[base + k] += add;
+}
+
+// ---- bucket accumulation over equal SLICES of the sorted index array ----
+// Thread t adds the points of entries [t * SL, (t + 1) * SL) whatever buckets they fall in: every thread of a warp does the
+// same number of additions (one thread per bucket wasted ~25 % of every warp on the largest of its 32 Poisson-sized buckets).
+// A run of entries of one bucket that covers the whole bucket is written to the bucket; a run cut by a slice boundary goes
+// to the slice's head slot (first run) or tail slot (last run) as an XYZZ point, and k_msm_fixup adds the pieces.
+static constexpr uint32_t MSM_SL = 64;
+struct SortedView { const uint32_t *scan; uint32_t nch, nb; };       // start of bucket b = scan[b * nch]; scan[nb * nch] = entries
+__device__ __forceinline__ uint32_t sv_start(const SortedView &v, uint32_t b) { return v.scan[(size_t)b * v.nch]; }
+__device__ __forceinline__ void st_ptx32(uint32_t *p, const PtX &a) {
+#pragma unroll
+    for (int k = 0; k < FE_W; k++) { p[k] = a.inf ? 0u : a.x.v[k]; p[FE_W + k] = a.inf ? 0u : a.y.v[k]; p[2 * FE_W + k] = a.inf ? 0u : a.zz.v[k]; p[3 * FE_W + k] = a.inf ? 0u : a.zzz.v[k]; }
+}
+__device__ __forceinline__ Pt ld_ptx32_as_pt(const uint32_t *p) {
+    PtX a;
+#pragma unroll
+    for (int k = 0; k < FE_W; k++) { a.x.v[k] = p[k]; a.y.v[k] = p[FE_W + k]; a.zz.v[k] = p[2 * FE_W + k]; a.zzz.v[k] = p[3 * FE_W + k]; }
+    a.inf = fe_normalizes_to_zero(a.zz);
+    return ptx_to_pt(a);
+}
+__global__ void __launch_bounds__(64, 7) k_msm_slices(const uint32_t *pts, const uint32_t *vals, SortedView sv, uint32_t *buckets, uint32_t *head, uint32_t *tail) {
+    const uint32_t total = sv_start(sv, sv.nb);
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t * MSM_SL >= total) return;
+    const uint32_t s = (uint32_t)(t * MSM_SL), e = s + MSM_SL < total ? s + MSM_SL : total;
+    // bucket of entry s: the last b with start[b] <= s (empty buckets share a start with their successor: take the last)
+    uint32_t lo = 0, hi = sv.nb;           // invariant: start[lo] <= s < start[hi]
+    while (hi - lo > 1) { uint32_t mid = lo + (hi - lo) / 2; if (sv_start(sv, mid) <= s) lo = mid; else hi = mid; }
+    uint32_t b = lo, bend = sv_start(sv, b + 1);
+    uint32_t run_begin = s;
+    bool first_run = true;
+    PtX acc = ptx_identity();
+    uint32_t v = vals[s];
+    PtA q; bool ok = load_dev_point(q, pts, v & 0x7FFFFFFFu);
+#pragma unroll 1
+    for (uint32_t p = s; p < e; p++) {
+        if (p == bend) {                   // bucket b ends here: the run is complete unless it began at a slice boundary inside b
+            if (run_begin == sv_start(sv, b)) st_pt30(buckets + PT_W * (size_t)b, ptx_to_pt(acc));
+            else st_ptx32(head + 32 * t, acc);                      // only the first run can have begun inside its bucket
+            acc = ptx_identity(); first_run = false; run_begin = p;
+            do { b++; bend = sv_start(sv, b + 1); } while (bend <= p);
+        }
+        const uint32_t vc = v; const PtA qc = q; const bool okc = ok;
+        if (p + 1 < e) { v = vals[p + 1]; ok = load_dev_point(q, pts, v & 0x7FFFFFFFu); }       // next point in flight during this addition
+        if (okc) {
+            PtA qa = qc;
+            if (vc >> 31) qa.y = fe_normalize_weak(fe_negate(qa.y, 1));
+            acc = ptx_add_mixed_hot(acc, qa);
+        }
+    }
+    if (run_begin == sv_start(sv, b) && e == bend) st_pt30(buckets + PT_W * (size_t)b, ptx_to_pt(acc));
+    else if (first_run) st_ptx32(head + 32 * t, acc);
+    else st_ptx32(tail + 32 * t, acc);
+}
+// buckets cut by slice boundaries: sum of their pieces (slot of bucket B in slice t: head when B began at or before the slice's
+// first entry, else tail); empty buckets become the identity; buckets spanning more than 32 slices go to the block kernel
+struct SpanQueue { uint32_t *count; uint32_t *bucket; uint32_t cap; };
+__device__ __forceinline__ const uint32_t *slice_piece(const uint32_t *head, const uint32_t *tail, uint32_t S, uint32_t t) {
+    return (S <= t * MSM_SL ? head : tail) + 32 * (size_t)t;
+}
+__global__ void __launch_bounds__(64) k_msm_fixup(SortedView sv, const uint32_t *head, const uint32_t *tail, uint32_t *buckets, SpanQueue sq) {
+    const size_t B = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (B >= sv.nb) return;
+    const uint32_t S = sv_start(sv, (uint32_t)B), E = sv_start(sv, (uint32_t)B + 1);
+    if (S == E) { st_pt30(buckets + PT_W * B, pt_identity()); return; }
+    const uint32_t t0 = S / MSM_SL, t1 = (E - 1) / MSM_SL;
+    if (t0 == t1) return;                                   // whole bucket inside one slice: k_msm_slices wrote it
+    if (t1 - t0 >= 32) { uint32_t slot = atomicAdd(sq.count, 1u); if (slot < sq.cap) { sq.bucket[slot] = (uint32_t)B; return; } }
+    Pt acc = ld_ptx32_as_pt(slice_piece(head, tail, S, t0));
+#pragma unroll 1
+    for (uint32_t t = t0 + 1; t <= t1; t++) acc = pt_add(acc, ld_ptx32_as_pt(slice_piece(head, tail, S, t)));
+    st_pt30(buckets + PT_W * B, acc);
+}
+__global__ void __launch_bounds__(128) k_msm_fixup_wide(SortedView sv, const uint32_t *head, const uint32_t *tail, uint32_t *buckets, SpanQueue sq) {
     __shared__ uint32_t sh[128 * PT_W];
-    const uint32_t i = blockIdx.x;                          // index within region L
-    if (i >= hq.count[1] || hq.seg[hq.capM + i] != 0) return;
-    uint32_t b = hq.bucket[hq.capM + i];
-    uint32_t nseg = (end[b] - start[b] + MSM_SEG - 1) / MSM_SEG;
+    uint32_t cnt = *sq.count; if (cnt > sq.cap) cnt = sq.cap;
+    if (blockIdx.x >= cnt) return;
+    const uint32_t B = sq.bucket[blockIdx.x];
+    const uint32_t S = sv_start(sv, B), E = sv_start(sv, B + 1), t0 = S / MSM_SL, t1 = (E - 1) / MSM_SL;
     Pt acc = pt_identity();
-    for (uint32_t k = threadIdx.x; k < nseg; k += 128) acc = pt_add(acc, ld_pt30(hq.seg_out + PT_W * (size_t)(i + k)));
+    for (uint32_t t = t0 + threadIdx.x; t <= t1; t += 128) acc = pt_add(acc, ld_ptx32_as_pt(slice_piece(head, tail, S, t)));
     st_pt30(sh + PT_W * threadIdx.x, acc);
     __syncthreads();
     for (int s = 64; s >= 1; s >>= 1) {
         if ((int)threadIdx.x < s) st_pt30(sh + PT_W * threadIdx.x, pt_add(ld_pt30(sh + PT_W * threadIdx.x), ld_pt30(sh + PT_W * (threadIdx.x + s))));
         __syncthreads();
     }
-    if (threadIdx.x == 0) st_pt30(buckets + PT_W * (size_t)b, ld_pt30(sh));
+    if (threadIdx.x == 0) st_pt30(buckets + PT_W * (size_t)B, ld_pt30(sh));
 }
 __global__ void k_pt_fill_identity(uint32_t *pts30, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -336,43 +431,53 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     const int nwin = (256 + c) / c;            // 257 bits of signed digits
     const uint32_t half = 1u << (c - 1);
     const uint32_t nb = (uint32_t)nwin * half;
-    const size_t total = (size_t)nwin * n;
+    const size_t total = (size_t)nwin * n;     // upper bound of the sorted entries (zero digits drop out)
+    if (total >= 0x7FFFFFFFull || n >= 0x80000000ull) return fail(BPPP_ERR_ARG, "MSM too large for 31-bit point indices");
     uint32_t CH = 16; if (CH > half) CH = half;        // 2 CH sequential additions per thread: short chains, many threads
     const uint32_t nchunks = (half + CH - 1) / CH;
-    HeavyQueue hq;
-    hq.capM = 8192; hq.capL = (uint32_t)(2 * total / MSM_SEG + 2);
-    const size_t hslots = (size_t)hq.capM + hq.capL;
-    uint32_t heavy_thr = (uint32_t)(2 * ((n + half - 1) / half)); if (heavy_thr < 32) heavy_thr = 32;
-    int key_bits = 1; while (((uint64_t)1 << key_bits) <= (uint64_t)nb) key_bits++;      // keys are 0 .. nb
-    size_t cub_bytes = 0;
-    CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, total, 0, key_bits, st));
+    int dev_for_lock = 0, sms = 148;
+    CUDA_OK(cudaGetDevice(&dev_for_lock));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_for_lock);
+    uint32_t nch = (uint32_t)(sms / nwin); if (nch < 1) nch = 1;      // sort blocks: nch chunks x nwin windows ~ one per SM
+    while (nch > 1 && n / nch < 4096) nch /= 2;
+    const size_t ncount = (size_t)nb * nch, nscanblk = (ncount + 2047) / 2048;
+    const size_t nslices = (total + MSM_SL - 1) / MSM_SL;
+    SpanQueue sq; sq.cap = (uint32_t)(total / (32 * MSM_SL) + 2);
     // one cached slab per device, carved into the working arrays (cudaMalloc per call cost more than the kernels)
     Carver cv;
-    size_t o_keys = cv.take(4 * total), o_vals = cv.take(4 * total), o_keys2 = cv.take(4 * total), o_vals2 = cv.take(4 * total);
-    size_t o_start = cv.take(4 * (size_t)nb), o_end = cv.take(4 * (size_t)nb), o_buckets = cv.take((size_t)PT_BYTES * nb);
-    size_t o_heavy = cv.take(256 + 8 * hslots), o_segout = cv.take((size_t)PT_BYTES * hq.capL), o_chunks = cv.take((size_t)PT_BYTES * nwin * nchunks);
-    size_t o_tmp = cv.take((size_t)PT_BYTES * ((size_t)nwin * nchunks / 16 + 2)), o_cub = cv.take(cub_bytes);
-    int dev_for_lock = 0;
-    CUDA_OK(cudaGetDevice(&dev_for_lock));
+    size_t o_digits = cv.take(2 * total), o_vals = cv.take(4 * total), o_counts = cv.take(4 * ncount), o_scan = cv.take(4 * (ncount + 1));
+    size_t o_bsum = cv.take(4 * (nscanblk + 1)), o_buckets = cv.take((size_t)PT_BYTES * nb), o_head = cv.take(128 * nslices), o_tail = cv.take(128 * nslices);
+    size_t o_sq = cv.take(256 + 4 * (size_t)sq.cap), o_chunks = cv.take((size_t)PT_BYTES * nwin * nchunks);
+    size_t o_tmp = cv.take((size_t)PT_BYTES * ((size_t)nwin * nchunks / 16 + 2));
     std::lock_guard<std::mutex> slab_lock(g_slab_mu[dev_for_lock & 15]);     // released after the final synchronise below
     uint8_t *slab = nullptr;
     int rc = scratch_reserve(cv.total, &slab);
     if (rc != BPPP_OK) return rc;
-    uint32_t *keys = (uint32_t *)(slab + o_keys), *vals = (uint32_t *)(slab + o_vals), *keys2 = (uint32_t *)(slab + o_keys2), *vals2 = (uint32_t *)(slab + o_vals2);
-    uint32_t *start = (uint32_t *)(slab + o_start), *end = (uint32_t *)(slab + o_end), *buckets = (uint32_t *)(slab + o_buckets);
+    uint16_t *digits = (uint16_t *)(slab + o_digits);
+    uint32_t *vals = (uint32_t *)(slab + o_vals), *counts = (uint32_t *)(slab + o_counts), *scan = (uint32_t *)(slab + o_scan), *bsum = (uint32_t *)(slab + o_bsum);
+    uint32_t *buckets = (uint32_t *)(slab + o_buckets), *head = (uint32_t *)(slab + o_head), *tail = (uint32_t *)(slab + o_tail);
     uint32_t *chunks = (uint32_t *)(slab + o_chunks), *tmp = (uint32_t *)(slab + o_tmp);
-    hq.count = (uint32_t *)(slab + o_heavy); hq.bucket = hq.count + 64; hq.seg = hq.bucket + hslots; hq.seg_out = (uint32_t *)(slab + o_segout);
-    void *cub_tmp = slab + o_cub;
-    CUDA_OK(cudaMemsetAsync(start, 0, 4 * (size_t)nb, st));          // empty buckets keep start == end == 0
-    CUDA_OK(cudaMemsetAsync(end, 0, 4 * (size_t)nb, st));
-    CUDA_OK(cudaMemsetAsync(hq.count, 0, 8, st));
-    GL(k_msm_digits, nblocks(n, 128), 128, d_sc, n, c, nwin, keys, vals);
-    CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys2, vals, vals2, total, 0, key_bits, st));   // only the bits a key can have
-    g_generic_launches += 4;
-    GL(k_msm_bounds, nblocks(total, 256), 256, keys2, total, nb, start, end);
-    GL(k_msm_buckets, nblocks(nb, 64), 64, d_pts, vals2, start, end, nb, buckets, hq, heavy_thr);
-    GL(k_msm_heavy, (unsigned)hslots, 128, d_pts, vals2, start, end, hq, buckets);
-    GL(k_msm_heavy_sum, hq.capL, 128, start, end, hq, buckets);
+    sq.count = (uint32_t *)(slab + o_sq); sq.bucket = sq.count + 64;
+    static bool smem_set[16] = {};
+    if (!smem_set[dev_for_lock & 15]) {
+        CUDA_OK(cudaFuncSetAttribute(k_msm_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << 15));
+        CUDA_OK(cudaFuncSetAttribute(k_msm_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << 15));
+        smem_set[dev_for_lock & 15] = true;
+    }
+    CUDA_OK(cudaMemsetAsync(sq.count, 0, 4, st));
+    GL(k_msm_digits, nblocks(n, 128), 128, d_sc, n, c, nwin, digits);
+    k_msm_hist<<<dim3(nch, (unsigned)nwin), 1024, 4 * (size_t)half, st>>>(digits, n, half, nch, counts); g_generic_launches++;
+    GL(k_scan_blocks, (unsigned)nscanblk, 256, counts, ncount, scan, bsum);
+    GL(k_scan_sums, 1, 1024, bsum, nscanblk, scan + ncount);
+    GL(k_scan_add, (unsigned)nscanblk, 256, scan, ncount, bsum);
+    uint32_t nrange = (uint32_t)(sms / nwin); if (nrange < 1) nrange = 1;
+    if (nrange > half) nrange = half;
+    const uint32_t span = (half + nrange - 1) / nrange;
+    k_msm_scatter<<<dim3((half + span - 1) / span, (unsigned)nwin), 1024, 4 * (size_t)span, st>>>(digits, n, half, span, nch, scan, vals); g_generic_launches++;
+    SortedView sv; sv.scan = scan; sv.nch = nch; sv.nb = nb;
+    GL(k_msm_slices, nblocks(nslices, 64), 64, d_pts, vals, sv, buckets, head, tail);
+    GL(k_msm_fixup, nblocks(nb, 64), 64, sv, head, tail, buckets, sq);
+    GL(k_msm_fixup_wide, sq.cap, 128, sv, head, tail, buckets, sq);
     GL(k_msm_chunks, nblocks((size_t)nwin * nchunks, 64), 64, buckets, nwin, half, CH, nchunks, chunks);
     // per-window sum of chunk results: groups of 16 until nwin points remain
     uint32_t *in = chunks, *out = tmp;
@@ -400,7 +505,7 @@ int decode_points_to_device(cudaStream_t st, const uint8_t *h_pts, int fmt, size
     CUDA_OK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
     cudaFree(d_raw); cudaFree(d_bad);
-    if (bad) { cudaFree(d_w); return fail(BPPP_ERR_ARG, "a point is not on the curve"); }
+    if (bad) { cudaFree(d_w); return fail(BPPP_ERR_ENCODING, "a point is not on the curve"); }
     *d_words = d_w;
     return BPPP_OK;
 }
@@ -414,7 +519,7 @@ int decode_scalars_to_device(cudaStream_t st, const uint8_t *h_sc, size_t n, uin
     CUDA_OK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
     cudaFree(d_raw); cudaFree(d_bad);
-    if (bad) { cudaFree(d_w); return fail(BPPP_ERR_ARG, "a scalar is not canonical (>= n)"); }
+    if (bad) { cudaFree(d_w); return fail(BPPP_ERR_ENCODING, "a scalar is not canonical (>= n)"); }
     *d_words = d_w;
     return BPPP_OK;
 }

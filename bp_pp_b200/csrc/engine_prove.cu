@@ -131,7 +131,7 @@ extern "C" int bppp_u64_prove_batch(bppp_ctx *c, size_t n, const uint64_t *x, co
     Merlin init; merlin_init(init, label, (uint32_t)label_len);
     for (size_t off = 0; off < n; off += c->max_batch) {
         size_t m = n - off < c->max_batch ? n - off : c->max_batch;
-        SubPlan sp = plan_sub(c, m);
+        SubPlan sp = plan_sub(c, m, true);
         for (int k = 0; k < sp.parts; k++) {
             cudaStream_t st = sp.parts == 1 ? c->stream : c->sub_stream[k];
             size_t lo = sp.lo[k], cnt = sp.lo[k + 1] - sp.lo[k];

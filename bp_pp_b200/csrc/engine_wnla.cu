@@ -17,6 +17,7 @@
 // (rho_0 = rho, rho_{k+1} = mu_k, mu_{k+1} = mu_k^2), bit-identical to the round-by-round evaluation.
 #define BPPP_FE_NOINLINE 1
 #include <algorithm>
+#include <functional>
 #include "engine_generic.cuh"
 
 using namespace bppp;
@@ -283,23 +284,54 @@ int wnla_commit_dev(cudaStream_t st, const WnlaDev &w, const uint32_t *d_l, cons
 
 
 // wnla.rs:125-190.  d_com30: commitment (projective, device).  d_l / d_n: padded witness arrays (consumed).
+// All scratch is allocated once: the scalar / partial-sum buffers at their first-round size and one half-size "B" set the
+// folds ping-pong with (round k reads the set round k-1 wrote).  The next commitment C + y X + (y^2 - 1) R (two 128-doubling
+// ladders, ~1.4 ms on two threads) runs on a side stream under the round's fold kernels and the next round's MSMs: only the
+// next transcript append needs it.
 int wnla_prove_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, uint32_t *d_l, uint32_t *d_n, size_t len_l, size_t len_n, WnlaProofHost &proof,
                    int32_t *status) {
     std::vector<std::vector<uint8_t>> rs, xs;
-    uint32_t *d_x30 = nullptr, *d_r30 = nullptr, *d_three = nullptr;
-    CUDA_OK(cudaMalloc(&d_x30, PT_BYTES)); CUDA_OK(cudaMalloc(&d_r30, PT_BYTES)); CUDA_OK(cudaMalloc(&d_three, 3 * PT_BYTES));
+    const size_t Lh0 = w.Lh, Lg0 = w.Lg, Lt0 = Lh0 + Lg0 + 1;
+    const size_t LhB = (Lh0 + 1) / 2, LgB = (Lg0 + 1) / 2;
+    uint32_t *d_xr30 = nullptr, *d_three = nullptr, *d_sx = nullptr, *d_sr = nullptr, *d_part = nullptr, *d_com_next = nullptr;
+    uint32_t *ptsB = nullptr, *cB = nullptr, *lB = nullptr, *nB = nullptr;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_xr = nullptr, ev_com = nullptr;
+    struct Cleanup {
+        std::function<void()> f; ~Cleanup() { f(); }
+    } cleanup{[&] {
+        cudaFree(d_xr30); cudaFree(d_three); cudaFree(d_sx); cudaFree(d_sr); cudaFree(d_part); cudaFree(d_com_next);
+        cudaFree(ptsB); cudaFree(cB); cudaFree(lB); cudaFree(nB);
+        if (side) cudaStreamDestroy(side);
+        if (ev_xr) cudaEventDestroy(ev_xr);
+        if (ev_com) cudaEventDestroy(ev_com);
+    }};
+    // the caller's buffers are set A; d_l / d_n are consumed (freed on every path, like the earlier implementation)
+    uint32_t *ptsA = w.pts, *cA = w.c, *lA = d_l, *nA = d_n;
+    struct FreeLN { uint32_t *&l, *&n; ~FreeLN() { cudaFree(l); cudaFree(n); } } free_ln{lA, nA};
+    CUDA_OK(cudaMalloc(&d_xr30, 2 * PT_BYTES)); CUDA_OK(cudaMalloc(&d_three, 3 * PT_BYTES)); CUDA_OK(cudaMalloc(&d_com_next, PT_BYTES));
+    CUDA_OK(cudaMalloc(&d_sx, 32 * Lt0)); CUDA_OK(cudaMalloc(&d_sr, 32 * Lt0));
+    {
+        size_t half0 = (std::max(Lh0, Lg0) + 1) / 2, nblk0 = (half0 + 127) / 128;
+        size_t Lc = std::max(LhB, LgB), nblkc = (Lc + 127) / 128;                 // wnla_commit_dev's partial sums after the first fold
+        CUDA_OK(cudaMalloc(&d_part, 128 * std::max<size_t>(std::max(nblk0, nblkc), 1)));
+    }
+    CUDA_OK(cudaMalloc(&ptsB, 64 * (LhB + LgB + 1))); CUDA_OK(cudaMalloc(&cB, 32 * std::max<size_t>(LhB, 1)));
+    CUDA_OK(cudaMalloc(&lB, 32 * std::max<size_t>(LhB, 1))); CUDA_OK(cudaMalloc(&nB, 32 * std::max<size_t>(LgB, 1)));
+    CUDA_OK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&ev_xr, cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&ev_com, cudaEventDisableTiming));
+    uint32_t *pts = ptsA, *cc = cA, *ll = lA, *nn = nA;                  // current set
+    uint32_t *pts2 = ptsB, *c2 = cB, *l2 = lB, *n2 = nB;                 // the set the next fold writes
+    uint32_t *d_x30 = d_xr30, *d_r30 = d_xr30 + PT_W;
     int rc = BPPP_OK;
-    bool first_round = true;
+    bool first_round = true, com_pending = false;
     while (len_l + len_n >= 6) {     // wnla.rs:126
         size_t Lh = w.Lh, Lg = w.Lg, Lt = Lh + Lg + 1;
         if (sc_is_zero(w.rho)) { *status = ST_PANIC_INVERT_ZERO; break; }     // rho.invert_vartime().unwrap(), wnla.rs:135
         Sc rho_inv = sc_inv(w.rho), mu2 = sc_sqr(w.mu);
-        uint32_t *d_sx = nullptr, *d_sr = nullptr, *d_part = nullptr;
-        CUDA_OK(cudaMalloc(&d_sx, 32 * Lt)); CUDA_OK(cudaMalloc(&d_sr, 32 * Lt));
         size_t half = (std::max(Lh, Lg) + 1) / 2, nblk = (half + 127) / 128;
-        CUDA_OK(cudaMalloc(&d_part, 128 * (nblk ? nblk : 1)));
-        WL(k_wnla_xr_scalars, nblocks(Lh + Lg, 128), 128, d_l, d_n, Lh, Lg, to_param(w.rho), to_param(rho_inv), d_sx, d_sr);
-        if (nblk) WL(k_wnla_dots, (unsigned)nblk, 128, w.c, d_l, d_n, Lh, Lg, to_param(mu2), d_part, (size_t)0);
+        WL(k_wnla_xr_scalars, nblocks(Lh + Lg, 128), 128, ll, nn, Lh, Lg, to_param(w.rho), to_param(rho_inv), d_sx, d_sr);
+        if (nblk) WL(k_wnla_dots, (unsigned)nblk, 128, cc, ll, nn, Lh, Lg, to_param(mu2), d_part, (size_t)0);
         Sc sums[4];
         rc = sum_partials_to_host(st, d_part, nblk, 4, sums);
         if (rc != BPPP_OK) break;
@@ -307,13 +339,13 @@ int wnla_prove_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, ui
         Sc vr = sc_add(sums[2], sums[3]);                                // wnla.rs:150
         CUDA_OK(cudaMemcpyAsync(d_sx + 8 * (Lh + Lg), vx.v, 32, cudaMemcpyHostToDevice, st));
         CUDA_OK(cudaMemcpyAsync(d_sr + 8 * (Lh + Lg), vr.v, 32, cudaMemcpyHostToDevice, st));
-        rc = msm_device(st, w.pts, d_sx, Lt, nullptr, d_x30); if (rc != BPPP_OK) break;
-        rc = msm_device(st, w.pts, d_sr, Lt, nullptr, d_r30); if (rc != BPPP_OK) break;
-        cudaFree(d_sx); cudaFree(d_sr); cudaFree(d_part);
+        CUDA_OK(cudaStreamSynchronize(st));                              // vx / vr live on this stack frame
+        rc = msm_device(st, pts, d_sx, Lt, nullptr, d_x30); if (rc != BPPP_OK) break;
+        rc = msm_device(st, pts, d_sr, Lt, nullptr, d_r30); if (rc != BPPP_OK) break;
         // transcript (wnla.rs:162-168)
+        if (com_pending) { CUDA_OK(cudaStreamWaitEvent(st, ev_com, 0)); CUDA_OK(cudaMemcpyAsync(d_com30, d_com_next, PT_BYTES, cudaMemcpyDeviceToDevice, st)); com_pending = false; }
         CUDA_OK(cudaMemcpyAsync(d_three, d_com30, PT_BYTES, cudaMemcpyDeviceToDevice, st));
-        CUDA_OK(cudaMemcpyAsync(d_three + PT_W, d_x30, PT_BYTES, cudaMemcpyDeviceToDevice, st));
-        CUDA_OK(cudaMemcpyAsync(d_three + 2 * PT_W, d_r30, PT_BYTES, cudaMemcpyDeviceToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(d_three + PT_W, d_xr30, 2 * PT_BYTES, cudaMemcpyDeviceToDevice, st));
         uint8_t b[99];
         rc = encode_points_from_device(st, d_three, 3, FMT_COMPRESSED, b); if (rc != BPPP_OK) break;
         host_append_point33(t, BPPP_LBL("wnla_com"), b);
@@ -324,19 +356,21 @@ int wnla_prove_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, ui
         Sc y;
         if (!host_challenge(t, BPPP_LBL("wnla_challenge"), y)) { *status = ST_PANIC_CHALLENGE_RANGE; break; }
         xs.emplace_back(b + 33, b + 66); rs.emplace_back(b + 66, b + 99);
+        if (!first_round) {
+            // com' = com + y X + (y^2 - 1) R on the side stream (reads d_three: this round's com, X, R stay untouched until the next encode)
+            CUDA_OK(cudaEventRecord(ev_xr, st));
+            CUDA_OK(cudaStreamWaitEvent(side, ev_xr, 0));
+            k_wnla_next_commitment<<<1, 2, 0, side>>>(d_three, d_three + PT_W, d_three + 2 * PT_W, to_param(y), d_com_next); g_wnla_launches++;
+            CUDA_OK(cudaEventRecord(ev_com, side));
+            com_pending = true;
+        }
         // fold generators and scalars (wnla.rs:170-175)
         size_t Lh2 = (Lh + 1) / 2, Lg2 = (Lg + 1) / 2;
-        uint32_t *pts2 = nullptr, *c2 = nullptr, *l2 = nullptr, *n2 = nullptr;
-        CUDA_OK(cudaMalloc(&pts2, 64 * (Lh2 + Lg2 + 1))); CUDA_OK(cudaMalloc(&c2, 32 * (Lh2 ? Lh2 : 1)));
-        CUDA_OK(cudaMalloc(&l2, 32 * (Lh2 ? Lh2 : 1))); CUDA_OK(cudaMalloc(&n2, 32 * (Lg2 ? Lg2 : 1)));
-        if (Lh2) WL(k_wnla_fold_points, nblocks(Lh2, 64), 64, w.pts, Lh, to_param(y), to_param(w.rho), 0, pts2);
-        if (Lg2) WL(k_wnla_fold_points, nblocks(Lg2, 64), 64, w.pts + 16 * Lh, Lg, to_param(y), to_param(w.rho), 1, pts2 + 16 * Lh2);
-        CUDA_OK(cudaMemcpyAsync(pts2 + 16 * (Lh2 + Lg2), w.pts + 16 * (Lh + Lg), 64, cudaMemcpyDeviceToDevice, st));
-        WL(k_wnla_fold_scalars, nblocks(std::max(Lh2, Lg2), 128), 128, w.c, d_l, d_n, Lh, Lg, to_param(y), to_param(rho_inv), c2, l2, n2, 1);
-        WL(k_wnla_next_commitment, 1, 2, d_com30, d_x30, d_r30, to_param(y), d_com30);
-        CUDA_OK(cudaStreamSynchronize(st));
-        cudaFree(w.pts); cudaFree(w.c); cudaFree(d_l); cudaFree(d_n);
-        w.pts = pts2; w.c = c2; d_l = l2; d_n = n2;
+        if (Lh2) WL(k_wnla_fold_points, nblocks(Lh2, 64), 64, pts, Lh, to_param(y), to_param(w.rho), 0, pts2);
+        if (Lg2) WL(k_wnla_fold_points, nblocks(Lg2, 64), 64, pts + 16 * Lh, Lg, to_param(y), to_param(w.rho), 1, pts2 + 16 * Lh2);
+        CUDA_OK(cudaMemcpyAsync(pts2 + 16 * (Lh2 + Lg2), pts + 16 * (Lh + Lg), 64, cudaMemcpyDeviceToDevice, st));
+        WL(k_wnla_fold_scalars, nblocks(std::max(Lh2, Lg2), 128), 128, cc, ll, nn, Lh, Lg, to_param(y), to_param(rho_inv), c2, l2, n2, 1);
+        std::swap(pts, pts2); std::swap(cc, c2); std::swap(ll, l2); std::swap(nn, n2);
         w.Lh = Lh2; w.Lg = Lg2;
         len_l = (len_l + 1) / 2; len_n = (len_n + 1) / 2;
         w.len_h = (w.len_h + 1) / 2; w.len_g = (w.len_g + 1) / 2;
@@ -344,22 +378,28 @@ int wnla_prove_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, ui
         if (first_round) {
             // the reference recomputes wnla'.commit(l', n') (wnla.rs:186); C + yX + (y^2-1)R equals it only when the caller's
             // commitment was consistent with (l, n), so the first re-commit is evaluated literally, later ones by the identity
-            rc = wnla_commit_dev(st, w, d_l, d_n, d_com30); if (rc != BPPP_OK) break;
+            WnlaDev cur = w; cur.pts = pts; cur.c = cc;
+            rc = wnla_commit_dev(st, cur, ll, nn, d_com30); if (rc != BPPP_OK) break;
             first_round = false;
         }
     }
+    if (rc == BPPP_OK && com_pending) { CUDA_OK(cudaStreamSynchronize(side)); }
     if (rc == BPPP_OK) {
+        CUDA_OK(cudaStreamSynchronize(st));
         // proof.r / proof.x are pushed after the recursion returns: innermost round first (wnla.rs:186-188)
         proof.r33.clear(); proof.x33.clear();
         for (size_t k = rs.size(); k-- > 0;) { proof.r33.insert(proof.r33.end(), rs[k].begin(), rs[k].end()); proof.x33.insert(proof.x33.end(), xs[k].begin(), xs[k].end()); }
         std::vector<uint32_t> hl(8 * (len_l ? len_l : 1)), hn(8 * (len_n ? len_n : 1));
-        if (len_l) CUDA_OK(cudaMemcpy(hl.data(), d_l, 32 * len_l, cudaMemcpyDeviceToHost));
-        if (len_n) CUDA_OK(cudaMemcpy(hn.data(), d_n, 32 * len_n, cudaMemcpyDeviceToHost));
+        if (len_l) CUDA_OK(cudaMemcpy(hl.data(), ll, 32 * len_l, cudaMemcpyDeviceToHost));
+        if (len_n) CUDA_OK(cudaMemcpy(hn.data(), nn, 32 * len_n, cudaMemcpyDeviceToHost));
         proof.l32.resize(32 * len_l); proof.n32.resize(32 * len_n);
         for (size_t i = 0; i < len_l; i++) { Sc s; memcpy(s.v, &hl[8 * i], 32); sc_to_be32(&proof.l32[32 * i], s); }
         for (size_t i = 0; i < len_n; i++) { Sc s; memcpy(s.v, &hn[8 * i], 32); sc_to_be32(&proof.n32[32 * i], s); }
     }
-    cudaFree(d_l); cudaFree(d_n); cudaFree(d_x30); cudaFree(d_r30); cudaFree(d_three);
+    cudaStreamSynchronize(side);
+    cudaStreamSynchronize(st);
+    // the caller releases w.pts / w.c (set A); they may currently be the "other" set, which is fine: both stay allocated until here
+    w.pts = ptsA; w.c = cA;
     return rc;
 }
 
@@ -374,10 +414,12 @@ int wnla_verify_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, c
     std::vector<uint8_t> both(33 * 2 * (size_t)(R ? R : 1));
     memcpy(both.data(), x33, 33 * (size_t)R); memcpy(both.data() + 33 * (size_t)R, r33, 33 * (size_t)R);
     rc = decode_points_to_device(st, both.data(), FMT_COMPRESSED, 2 * (size_t)R, &d_xr);
-    if (rc != BPPP_OK) { *verdict = ST_BAD_POINT; return BPPP_OK; }
+    // only a bad ENCODING is a verdict (the reference fails to deserialise); out-of-memory / CUDA errors stay errors
+    if (rc == BPPP_ERR_ENCODING) { *verdict = ST_BAD_POINT; return BPPP_OK; }
+    if (rc != BPPP_OK) return rc;
     rc = decode_scalars_to_device(st, l32, ln, &d_l);
     if (rc == BPPP_OK) rc = decode_scalars_to_device(st, n32, nn, &d_n);
-    if (rc != BPPP_OK) { cudaFree(d_xr); cudaFree(d_l); *verdict = ST_BAD_SCALAR; return BPPP_OK; }
+    if (rc != BPPP_OK) { cudaFree(d_xr); cudaFree(d_l); if (rc != BPPP_ERR_ENCODING) return rc; *verdict = ST_BAD_SCALAR; return BPPP_OK; }
     CUDA_OK(cudaMalloc(&d_x30, PT_BYTES)); CUDA_OK(cudaMalloc(&d_r30, PT_BYTES));
     std::vector<Sc> ys(R), rhos(R);
     Sc rho = w.rho, mu = w.mu;
@@ -517,7 +559,7 @@ extern "C" int bppp_wnla_verify(int device, const uint8_t *g64, const uint8_t *g
     rc = wnla_load(st, w, g64, gvec64, gn, hvec64, hn, c32, cn, rho32, mu32, 0, 0); if (rc != BPPP_OK) return rc;
     uint32_t *d_com16 = nullptr, *d_com30 = nullptr;
     rc = decode_points_to_device(st, commit33, FMT_COMPRESSED, 1, &d_com16);
-    if (rc != BPPP_OK) { w.release(); *verdict = ST_BAD_POINT; return BPPP_OK; }
+    if (rc != BPPP_OK) { w.release(); if (rc != BPPP_ERR_ENCODING) return rc; *verdict = ST_BAD_POINT; return BPPP_OK; }
     CUDA_OK(cudaMalloc(&d_com30, PT_BYTES));
     k_decode_one_point30<<<1, 1, 0, st>>>(d_com16, d_com30);
     Merlin t; merlin_init(t, label, (uint32_t)label_len);

@@ -182,8 +182,9 @@ def wnla_prove_sharded(g64: bytes, blocks: Sequence[dict], rho32: bytes, mu32: b
               for j, b in enumerate(blocks)]
     len_l, len_n = total_blocks * nh, total_blocks * ng
     st = {"rounds_sharded": 0, "rounds_whole": 0, "device_ms": 0.0, "upload_s": time.perf_counter() - t0, "exchange_bytes": 0}
-    pool = ThreadPoolExecutor(max_workers=nb) if nb > 1 else None
-    pmap = (lambda f, xs: list(pool.map(f, xs))) if pool else (lambda f, xs: [f(x) for x in xs])
+    pool = ThreadPoolExecutor(max_workers=nb + 1)        # one worker per local block + one for the running commitment
+    pmap = (lambda f, xs: list(pool.map(f, xs))) if nb > 1 else (lambda f, xs: [f(x) for x in xs])
+    com_future = None
 
     def total(parts64):          # sum of 64-byte affine points -> (affine64, compressed33)
         allp = b"".join(parts64)
@@ -214,8 +215,12 @@ def wnla_prove_sharded(g64: bytes, blocks: Sequence[dict], rho32: bytes, mu32: b
                     sh.close()
                 shards = [WnlaShard(dev0, g64, full["hvec64"], full["c32"], full["l32"], 0, full["gvec64"], full["n32"], 0, s0["rho"], s0["mu"], True)]
                 whole, pmap = True, (lambda f, xs: [f(x) for x in xs])
+                nb = 1
             parts = pmap(lambda sh: sh.xr_partial(), shards)
             st["device_ms"] += max(ms for _, ms in parts)
+            if com_future is not None:                               # C + y X + (y^2 - 1) R of the previous round, computed under this round's MSMs
+                com64, com33 = com_future.result()
+                com_future = None
             mine = b"".join(p for p, _ in parts)
             allparts = mine if whole else b"".join(_gather_bytes(mine, dev0))
             if not whole:
@@ -234,13 +239,17 @@ def wnla_prove_sharded(g64: bytes, blocks: Sequence[dict], rho32: bytes, mu32: b
                 com64, com33 = total([cp[o:o + 64] for o in range(0, len(cp), 64)])
                 first = False
             else:
-                y = int.from_bytes(y32, "big")
-                sc = (1).to_bytes(32, "big") + y32 + ((y * y - 1) % _N).to_bytes(32, "big")
-                com64 = api.msm(com64 + X64 + R64, sc, api.FMT_AFFINE64, api.FMT_AFFINE64, dev0)                 # wnla.rs:100-102
-                com33 = api.points_convert(com64, api.FMT_AFFINE64, api.FMT_COMPRESSED, dev0)
+                def next_commitment(c64=com64, x64=X64, r64=R64, yb=y32):                                         # wnla.rs:100-102
+                    y = int.from_bytes(yb, "big")
+                    sc = (1).to_bytes(32, "big") + yb + ((y * y - 1) % _N).to_bytes(32, "big")
+                    n64 = api.msm(c64 + x64 + r64, sc, api.FMT_AFFINE64, api.FMT_AFFINE64, dev0)
+                    return n64, api.points_convert(n64, api.FMT_AFFINE64, api.FMT_COMPRESSED, dev0)
+                com_future = pool.submit(next_commitment)
             rs.append(R33); xs.append(X33)
             len_l, len_n = (len_l + 1) // 2, (len_n + 1) // 2
             st["rounds_whole" if whole else "rounds_sharded"] += 1
+        if com_future is not None:
+            com_future.result()
         ex = [sh.export() for sh in shards]
         l_out, n_out = b"".join(e["l32"] for e in ex), b"".join(e["n32"] for e in ex)
         if not whole:
@@ -248,8 +257,7 @@ def wnla_prove_sharded(g64: bytes, blocks: Sequence[dict], rho32: bytes, mu32: b
     finally:
         for sh in shards:
             sh.close()
-        if pool:
-            pool.shutdown()
+        pool.shutdown()
     st["prove_s"] = time.perf_counter() - t1
     if stats is not None:
         stats.update(st)

@@ -59,7 +59,9 @@ enum {
     BPPP_ERR_NO_DEVICE = -11,  /* no CUDA device: there is deliberately no CPU fallback */
     BPPP_ERR_CUDA = -12,
     BPPP_ERR_GENERATOR = -13,  /* a generator is not a curve point */
-    BPPP_ERR_NOMEM = -14
+    BPPP_ERR_NOMEM = -14,
+    BPPP_ERR_ENCODING = -15    /* an input point is not on the curve / a scalar is >= n (verify entry points turn this into a
+                                  BPPP_ST_BAD_* verdict; infrastructure failures -- NOMEM, CUDA -- are returned as such) */
 };
 
 #define BPPP_U64_NUM_GENS 49        /* g, g_vec[16], h_vec[32]: src/range_proof/u64_proof.rs:12-14,19-28 */
@@ -211,7 +213,7 @@ int bppp_wnla_shard_export(bppp_wnla_shard *s, uint8_t *hvec64, uint8_t *c32, ui
 
 /* ArithmeticCircuit<P> (src/circuit.rs:95-139) with dense row-major W_m (dim_nm x dim_nw) and W_l (dim_nl x dim_nw),
  * dim_nl = dim_nv * k, dim_nw = 2 dim_nm + dim_no, and the partition closure tabulated: part_xx[j] = index or -1 for
- * j < part_n (PartitionType LO / LL / LR / NO, src/circuit.rs:15-20).  Generators 64-byte affine. */
+ * j < part_n, None beyond (PartitionType LO / LL / LR / NO, src/circuit.rs:15-20); entries must lie in [-1, dim_no).  Generators 64-byte affine. */
 typedef struct bppp_circuit_desc {
     size_t dim_nm, dim_no, k, dim_nv;
     int f_l, f_m;
@@ -223,8 +225,8 @@ typedef struct bppp_circuit_desc {
 } bppp_circuit_desc;
 /* ArithmeticCircuit::commit / prove / verify (src/circuit.rs:146-151, 260-556, 154-256); fresh Transcript::new(label).
  * prove: witness v (k x dim_nv), s_v (k), w_l, w_r (dim_nm), w_o (dim_no); rng = (18 + dim_nv + dim_nm) x 64 bytes in draw
- * order; out record = c_l c_r c_o c_s | r[rounds] | x[rounds] | l | n.  The host evaluates the coefficient vectors
- * (scalar field), the GPU every commitment and the WNLA. */
+ * order; out record = c_l c_r c_o c_s | r[rounds] | x[rounds] | l | n.  A descriptor the reference would panic on (index out
+ * of bounds: too few generators, partition entries outside [-1, dim_no)) is rejected with BPPP_ERR_ARG. */
 int bppp_circuit_commit(int device, const bppp_circuit_desc *desc, const uint8_t *v32, const uint8_t *s32, uint8_t *out33);
 int bppp_circuit_prove(int device, const bppp_circuit_desc *desc, const uint8_t *commits33, const uint8_t *v32, const uint8_t *sv32,
                        const uint8_t *wl32, const uint8_t *wr32, const uint8_t *wo32, const uint8_t *rng, size_t rng_len,
@@ -232,6 +234,37 @@ int bppp_circuit_prove(int device, const bppp_circuit_desc *desc, const uint8_t 
                        size_t *l_len_out, size_t *n_len_out, int32_t *status);
 int bppp_circuit_verify(int device, const bppp_circuit_desc *desc, const uint8_t *commits33, const uint8_t *rec, size_t rounds_r,
                         size_t rounds_x, size_t l_len, size_t n_len, const uint8_t *label, size_t label_len, int32_t *verdict);
+
+/* The same circuit with W_m and W_l in compressed-sparse-row form (what a circuit compiler emits; the dense descriptor needs
+ * O(dim^2) memory).  Values either one per non-zero (value_idx NULL, values32 = nnz x 32 bytes) or through a dictionary of
+ * n_values distinct scalars (values32 = n_values x 32 bytes, value_idx[k] selects the k-th non-zero's value).  The engine
+ * keeps the matrices on the device (compressed sparse columns) and evaluates lambda_vec x W_l, mu_vec x W_m -- the only
+ * super-linear step of circuit.rs:584-653 -- in a kernel. */
+typedef struct bppp_sparse_matrix {
+    size_t rows, cols, nnz;
+    const uint64_t *row_ptr;      /* rows + 1 entries, row_ptr[rows] = nnz */
+    const uint32_t *col_idx;      /* nnz */
+    const uint32_t *value_idx;    /* nnz, or NULL */
+    const uint8_t *values32;
+    size_t n_values;
+} bppp_sparse_matrix;
+typedef struct bppp_circuit_desc_sparse {
+    size_t dim_nm, dim_no, k, dim_nv;
+    int f_l, f_m;
+    const uint8_t *g64, *gvec64, *hvec64, *gvec2_64, *hvec2_64;
+    size_t gn, hn, gn2, hn2;
+    bppp_sparse_matrix W_m, W_l;   /* dim_nm x dim_nw, dim_nl x dim_nw */
+    const uint8_t *a_m32, *a_l32;
+    const int32_t *part_lo, *part_ll, *part_lr, *part_no;
+    size_t part_n;
+} bppp_circuit_desc_sparse;
+int bppp_circuit_commit_sparse(int device, const bppp_circuit_desc_sparse *desc, const uint8_t *v32, const uint8_t *s32, uint8_t *out33);
+int bppp_circuit_prove_sparse(int device, const bppp_circuit_desc_sparse *desc, const uint8_t *commits33, const uint8_t *v32, const uint8_t *sv32,
+                              const uint8_t *wl32, const uint8_t *wr32, const uint8_t *wo32, const uint8_t *rng, size_t rng_len,
+                              const uint8_t *label, size_t label_len, uint8_t *out, size_t out_cap, size_t *rounds_out,
+                              size_t *l_len_out, size_t *n_len_out, int32_t *status);
+int bppp_circuit_verify_sparse(int device, const bppp_circuit_desc_sparse *desc, const uint8_t *commits33, const uint8_t *rec, size_t rounds_r,
+                               size_t rounds_x, size_t l_len, size_t n_len, const uint8_t *label, size_t label_len, int32_t *verdict);
 
 /* ReciprocalRangeProofProtocol { dim_nd, dim_np, g, g_vec, h_vec, g_vec_, h_vec_ } (src/range_proof/reciprocal.rs:64-84)
  * for arbitrary dimensions: commit_value (:88-90), prove (:110-146), verify (:98-107); make_circuit (:150-214) is built

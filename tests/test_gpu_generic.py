@@ -256,6 +256,80 @@ def test_circuit_k_and_f_m_branches_on_gpu(oracle, ref, k, f_l, f_m):
     assert circ.verify(coms, bytes(bad), rounds, rounds, ll, nl, b"c2") == oracle.circuit_verify(desc, coms, bytes(bad), rounds, rounds, ll, nl, b"c2")
 
 
+@pytest.mark.parametrize("mode", ["csr", "csr-dict"])
+def test_sparse_circuit_descriptor_equals_the_dense_one(oracle, ref, mode):
+    """bppp_circuit_desc_sparse (CSR W_m / W_l, values per non-zero or through a dictionary) against the dense descriptor and
+    the C oracle: commit, prove and verify bytes for a random circuit with k = 2 and for one with f_m."""
+    import bp_pp_b200 as B
+    from conftest import circuit_bytes, synth_circuit
+    for k, f_l, f_m in ((2, True, False), (1, True, True)):
+        nv = 3
+        c = synth_circuit(ref, k, nv, k * nv if f_m else 4, 3, f_l, f_m, seed=70 + k)
+        b = circuit_bytes(ref, c)
+        args = (c["nm"], c["no"], k, nv, b["g"], b["g_vec"], b["h_vec"], b["W_m"], b["W_l"], b["a_m"], b["a_l"], f_l, f_m, b"", b["h_vec_"],
+                b["part_lo"], b["part_ll"], b["part_lr"], b["part_no"])
+        dense, sparse = B.ArithmeticCircuit(*args), B.ArithmeticCircuit(*args, sparse=mode)
+        desc = oracle.make_circuit_desc(c["nm"], c["no"], k, nv, f_l, f_m, b["g"], b["g_vec"], b["h_vec"], b"", b["h_vec_"], b["W_m"], b["W_l"], b["a_m"], b["a_l"],
+                                        b["part_lo"], b["part_ll"], b["part_lr"], b["part_no"])
+        coms = b"".join(sparse.commit(b["v"][32 * nv * i:32 * nv * (i + 1)], b["s_v"][32 * i:32 * i + 32]) for i in range(k))
+        assert coms == b"".join(oracle.circuit_commit(desc, b["v"][32 * nv * i:32 * nv * (i + 1)], b["s_v"][32 * i:32 * i + 32]) for i in range(k))
+        rng = random.Random(19).randbytes(64 * 64)
+        out = sparse.prove(coms, b["v"], b["s_v"], b["wl"], b["wr"], b["wo"], rng, b"sp")
+        assert out == dense.prove(coms, b["v"], b["s_v"], b["wl"], b["wr"], b["wo"], rng, b"sp")
+        assert out == oracle.circuit_prove(desc, coms, b["v"], b["s_v"], b["wl"], b["wr"], b["wo"], rng, b"sp")
+        rec, rounds, ll, nl = out
+        assert sparse.verify(coms, rec, rounds, rounds, ll, nl, b"sp") == oracle.circuit_verify(desc, coms, rec, rounds, rounds, ll, nl, b"sp")
+
+
+def test_circuit_descriptor_is_validated(ref):
+    """What the reference answers with an index-out-of-bounds panic must be an error here, not a read past a buffer
+    (ADVICE r1): partition entries outside [-1, dim_no), too few generators, a partition table that is too short."""
+    import bp_pp_b200 as B
+    from conftest import circuit_bytes, synth_circuit
+    c = synth_circuit(ref, 1, 2, 2, 2, True, False, seed=5)
+    b = circuit_bytes(ref, c)
+
+    def make(**over):
+        a = dict(part_lo=b["part_lo"], part_ll=b["part_ll"], part_lr=b["part_lr"], part_no=b["part_no"], g_vec=b["g_vec"], h_vec=b["h_vec"])
+        a.update(over)
+        return B.ArithmeticCircuit(c["nm"], c["no"], 1, 2, b["g"], a["g_vec"], a["h_vec"], b["W_m"], b["W_l"], b["a_m"], b["a_l"], True, False, b"", b["h_vec_"],
+                                   a["part_lo"], a["part_ll"], a["part_lr"], a["part_no"])
+    v, s = b["v"][:64], b["s_v"][:32]
+    assert len(make().commit(v, s)) == 33
+    for bad in (dict(part_ll=[0, 7]), dict(part_no=[-2, -1]), dict(g_vec=b["g_vec"][:64]), dict(h_vec=b["h_vec"][:64 * 10])):
+        with pytest.raises(B.BpppError):
+            make(**bad).commit(v, s)
+
+
+def test_reciprocal_dim_4096(oracle, ref):
+    """A reciprocal range proof over 4096 digits (BASELINE config 4 scaled 4x): the circuit's W_l holds 16.8 M non-zeros -- 1 GB as
+    the dense matrix the reference builds -- kept on the device as sparse columns with a value dictionary.  Checked through
+    size-independent properties; dim 1024 (below) is compared with the oracle byte for byte."""
+    import bp_pp_b200 as B
+    nd, np_ = 4096, 16
+    rnd = random.Random(4096)
+    be = lambda v: (v % ref.N).to_bytes(32, "big")  # noqa: E731
+    base, step = xy(ref.pt_mul(ref.G, 13)), xy(ref.pt_mul(ref.G, 31))
+    pts = B.points_generate(base, step, 1 + nd + 8192)
+    g, gvec, hvec, hvec2 = pts[:64], pts[64:64 * (1 + nd)], pts[64 * (1 + nd):64 * (1 + nd + nd + 10)], pts[64 * (1 + nd + nd + 10):]
+    assert len(hvec) // 64 == nd + 10 and len(hvec2) // 64 == 8192 - (nd + 10)
+    digits = [rnd.randrange(np_) for _ in range(nd)]
+    x32 = be(sum(d * pow(np_, i, ref.N) for i, d in enumerate(digits)))
+    s32 = be(rnd.randrange(ref.N))
+    rng = rnd.randbytes((1 + 18 + (nd + 1) + nd) * 64)
+    proto = B.ReciprocalRangeProofProtocol(nd, np_, g, gvec, hvec, b"", hvec2)
+    rec, rounds, ll, nl, com = proto.prove(x32, s32, digits, rng, b"dim 4096")
+    assert (rounds, ll, nl) == (12, 2, 1) and com == proto.commit_value(x32, s32)
+    assert proto.verify(com, rec, rounds, rounds, ll, nl, b"dim 4096") == 1
+    assert proto.prove(x32, s32, digits, rng, b"dim 4096")[0] == rec                                  # deterministic
+    bad = bytearray(rec); bad[-40] ^= 1                                                              # the final n scalar
+    assert proto.verify(com, bytes(bad), rounds, rounds, ll, nl, b"dim 4096") == 0
+    assert proto.verify(com, rec, rounds, rounds, ll, nl, b"dim 4097") == 0
+    wrong = list(digits); wrong[7] = (wrong[7] + 1) % np_                                            # digits that do not add up to x: the proof must not verify
+    rec2, *_ = proto.prove(x32, s32, wrong, rng, b"dim 4096")
+    assert proto.verify(com, rec2, rounds, rounds, ll, nl, b"dim 4096") == 0
+
+
 def test_config4_wide_reciprocal_dim_1024(oracle, ref):
     """BASELINE config 4: dim_nd = 1024 digits, dim_np = 16, WNLA over 2^11 + 2^11 generators (10 rounds), vs the oracle."""
     import bp_pp_b200 as B

@@ -1,12 +1,26 @@
 """Repeated wall-clock timing of the generic WNLA entry points at n = 2^20 (first call vs warm calls) and of an MSM upload."""
 import os, sys, time, random
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import bp_pp_b200 as B, bppp_ref as R
-from tools.bench_generic import xy, rand_scalars
+sys.path.insert(0, ROOT)
+import numpy as np
+import bp_pp_b200 as B
+from bp_pp_b200 import synth
+
+
+class R:
+    N = synth.N
+
+
+def rand_scalars(rnd, n):
+    a = np.frombuffer(np.random.default_rng(rnd.randrange(1 << 30)).bytes(32 * n), dtype=np.uint8).reshape(n, 32).copy()
+    a[:, 0] &= 0x7F
+    return a.tobytes()
+
+
 rnd = random.Random(1)
-base, step = xy(R.pt_mul(R.G, 11)), xy(R.pt_mul(R.G, 29))
-n = 1 << 20
+be = lambda v: (v % synth.N).to_bytes(32, "big")  # noqa: E731
+base, step = B.msm(synth.G64, be(11), B.FMT_AFFINE64, B.FMT_AFFINE64), B.msm(synth.G64, be(29), B.FMT_AFFINE64, B.FMT_AFFINE64)
+n = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 20)
 pts = B.points_generate(base, step, 2 * n + 1)
 g, gvec, hvec = pts[:64], pts[64:64 * (n + 1)], pts[64 * (n + 1):]
 c, l, nn = rand_scalars(rnd, n), rand_scalars(rnd, n), rand_scalars(rnd, n)
