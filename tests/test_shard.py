@@ -101,3 +101,31 @@ def test_msm_split_by_point_range_two_ranks_gloo(ref, oracle):
     for pr in procs:
         pr.join(60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _gather_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from bp_pp_b200.shard import _gather_bytes
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    mine = bytes([rank + 1]) * 128                       # one block's shares of X and R
+    got = _gather_bytes(mine, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, got == [bytes([r + 1]) * 128 for r in range(world)]))
+
+
+def test_wnla_exchange_step_two_ranks_gloo():
+    """The sharded WNLA's only data-path exchange: an all-gather of one equal-length byte string per rank, in rank order
+    (world_size 2, gloo on the CPU; NCCL on the GPU box -- tests/test_gpu_multirank.py runs the whole protocol)."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, True), (1, True)]
