@@ -3,8 +3,9 @@
 // scalar multiplication per term) for large n -- WNLA X/R commitments (src/wnla.rs:152-160), wnla.commit
 // (src/wnla.rs:66-72) and the circuit commitments (src/circuit.rs:335-345,469-470,522-524).
 //
-// Pippenger with signed c-bit windows, every kernel in this file (no library call):
-//   k_msm_digits      signed 16-bit digits of every scalar, window-major
+// Pippenger over the GLV halves of the scalars (128-bit magnitudes, the lambda half on (beta x, y)) with signed c-bit
+// windows, every kernel in this file (no library call):
+//   k_msm_digits      GLV split + signed 16-bit digits of both halves of every scalar, window-major;  k_msm_endo_x: beta x
 //   k_msm_hist / k_scan_* / k_msm_scatter   counting sort of the point indices by (window, bucket): shared-memory histograms per
 //                     (chunk, window) block, one exclusive scan, scatter through shared-memory cursors -- no global atomics
 //   k_msm_slices      one thread per 64 consecutive sorted entries (XYZZ mixed additions, next point prefetched): perfectly
@@ -81,27 +82,59 @@ __global__ void k_encode_points(const uint32_t *pts30, int fmt, uint8_t *out, si
 }
 
 // ---- Pippenger ----
-// signed c-bit digits of every scalar, window-major, 16 bits each: low 15 bits magnitude - 1 (0x7FFF when the digit is zero
-// ... the magnitude is at most 2^(c-1) <= 2^15, so mag - 1 fits 15 bits), bit 15 = sign.  Zero digits are stored as 0xFFFF.
+// GLV: k = k1 + k2 lambda with |k1|, |k2| < 2^128 (ec.cuh:glv_split), so scalar i becomes two ENTRIES -- 2i for (k1, P_i) and
+// 2i + 1 for (k2, lambda P_i = (beta x_i, y_i)) -- of 128-bit magnitudes: half the windows, half the buckets to reduce and half
+// the doublings of the Horner tail for the same number of bucket additions.
+// Signed c-bit digits of every entry, window-major (row w holds the 2n entries of window w), 16 bits each: low 15 bits
+// magnitude - 1 (the magnitude is at most 2^(c-1) <= 2^15), bit 15 = sign (the half-scalar's sign folded in).  Zero digits are
+// stored as 0xFFFF.  nwin = floor(128 / c) + 1 windows absorb the last carry (the top window holds < c - 1 real bits).
 __global__ void k_msm_digits(const uint32_t *sc, size_t n, int c, int nwin, uint16_t *digits) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t k[9];
+    Sc k;
 #pragma unroll
-    for (int j = 0; j < 8; j++) k[j] = sc[8 * i + j];
-    k[8] = 0;
+    for (int j = 0; j < 8; j++) k.v[j] = sc[8 * i + j];
+    const GlvSplit g = glv_split(k);
     const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1u;
-    uint32_t carry = 0;
-    for (int w = 0; w < nwin; w++) {
-        int bit = w * c, word = bit >> 5, sh = bit & 31;
-        uint64_t v = word < 8 ? k[word] : 0;
-        if (word + 1 < 9) v |= (uint64_t)k[word + 1] << 32;
-        uint32_t raw = ((uint32_t)(v >> sh) & mask) + carry;
-        uint32_t neg = 0, mag = raw;
-        carry = 0;
-        if (raw > half) { mag = (1u << c) - raw; neg = 1; carry = 1; }
-        digits[(size_t)w * n + i] = mag == 0 ? (uint16_t)0xFFFFu : (uint16_t)((mag - 1) | (neg << 15));
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+        uint32_t m[6];
+#pragma unroll
+        for (int j = 0; j < 4; j++) m[j] = h ? g.k2[j] : g.k1[j];
+        m[4] = 0; m[5] = 0;
+        const uint32_t sneg = (h ? g.neg2 : g.neg1) ? 1u : 0u;
+        uint32_t carry = 0;
+        for (int w = 0; w < nwin; w++) {
+            int bit = w * c, word = bit >> 5, sh = bit & 31;
+            uint64_t v = word < 5 ? ((uint64_t)m[word] | ((uint64_t)m[word + 1] << 32)) : 0;
+            uint32_t raw = ((uint32_t)(v >> sh) & mask) + carry;
+            uint32_t neg = 0, mag = raw;
+            carry = 0;
+            // raw == half may be written +half or -half + carry: at c = 16 the code (magnitude 2^15, final sign 1) is the zero
+            // marker 0xFFFF, so the tie takes whichever sign leaves the FINAL sign clear (never needed in the top window)
+            if (raw > half || (raw == half && sneg && w + 1 < nwin)) { mag = (1u << c) - raw; neg = 1; carry = 1; }
+            digits[(size_t)w * 2 * n + 2 * i + h] = mag == 0 ? (uint16_t)0xFFFFu : (uint16_t)((mag - 1) | ((neg ^ sneg) << 15));
+        }
     }
+}
+// beta * x of every point (canonical words): the x coordinate of the lambda-half entries; (0, 0) stays the identity sentinel
+__global__ void k_msm_endo_x(const uint32_t *pts, size_t n, uint32_t *bx) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) x[j] = pts[16 * i + j];
+    fe_to_words(x, fe_normalize(fe_mul(fe_from_words(x), fe_beta())));
+#pragma unroll
+    for (int j = 0; j < 8; j++) bx[8 * i + j] = x[j];
+}
+// point of sorted entry e: P_(e >> 1), its x taken from the beta * x array for the lambda half
+__device__ __forceinline__ bool load_entry_point(PtA &q, const uint32_t *pts, const uint32_t *bx, uint32_t e) {
+    const size_t idx = e >> 1;
+    const uint4 *px = (e & 1u) ? reinterpret_cast<const uint4 *>(bx + 8 * idx) : reinterpret_cast<const uint4 *>(pts + 16 * idx);
+    const uint4 *py = reinterpret_cast<const uint4 *>(pts + 16 * idx + 8);
+    TableEntryRaw r; r.a = __ldg(px); r.b = __ldg(px + 1); r.c = __ldg(py); r.e = __ldg(py + 1);
+    return table_decode(q, r);
 }
 // Counting sort of the (window, bucket) keys without a library and without global atomics.  Pass 1: block (j, w) histograms
 // chunk j of window w's digits in shared memory (2^(c-1) counters, 128 KB at c = 16) and writes the counts to
@@ -221,7 +254,7 @@ __device__ __forceinline__ Pt ld_ptx32_as_pt(const uint32_t *p) {
     a.inf = fe_normalizes_to_zero(a.zz);
     return ptx_to_pt(a);
 }
-__global__ void __launch_bounds__(64, 7) k_msm_slices(const uint32_t *pts, const uint32_t *vals, SortedView sv, uint32_t *buckets, uint32_t *head, uint32_t *tail) {
+__global__ void __launch_bounds__(64, 7) k_msm_slices(const uint32_t *pts, const uint32_t *bx, const uint32_t *vals, SortedView sv, uint32_t *buckets, uint32_t *head, uint32_t *tail) {
     const uint32_t total = sv_start(sv, sv.nb);
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t * MSM_SL >= total) return;
@@ -234,7 +267,7 @@ __global__ void __launch_bounds__(64, 7) k_msm_slices(const uint32_t *pts, const
     bool first_run = true;
     PtX acc = ptx_identity();
     uint32_t v = vals[s];
-    PtA q; bool ok = load_dev_point(q, pts, v & 0x7FFFFFFFu);
+    PtA q; bool ok = load_entry_point(q, pts, bx, v & 0x7FFFFFFFu);
 #pragma unroll 1
     for (uint32_t p = s; p < e; p++) {
         if (p == bend) {                   // bucket b ends here: the run is complete unless it began at a slice boundary inside b
@@ -244,7 +277,7 @@ __global__ void __launch_bounds__(64, 7) k_msm_slices(const uint32_t *pts, const
             do { b++; bend = sv_start(sv, b + 1); } while (bend <= p);
         }
         const uint32_t vc = v; const PtA qc = q; const bool okc = ok;
-        if (p + 1 < e) { v = vals[p + 1]; ok = load_dev_point(q, pts, v & 0x7FFFFFFFu); }       // next point in flight during this addition
+        if (p + 1 < e) { v = vals[p + 1]; ok = load_entry_point(q, pts, bx, v & 0x7FFFFFFFu); }       // next point in flight during this addition
         if (okc) {
             PtA qa = qc;
             if (vc >> 31) qa.y = fe_normalize_weak(fe_negate(qa.y, 1));
@@ -427,19 +460,20 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
         CUDA_OK(cudaGetLastError());
         return BPPP_OK;
     }
-    const int c = msm_choose_window(n);
-    const int nwin = (256 + c) / c;            // 257 bits of signed digits
+    const size_t n2 = 2 * n;                   // sorted entries per window: the two GLV halves of every scalar
+    const int c = msm_choose_window(n2);
+    const int nwin = 128 / c + 1;              // 129 bits of signed digits per half
     const uint32_t half = 1u << (c - 1);
     const uint32_t nb = (uint32_t)nwin * half;
-    const size_t total = (size_t)nwin * n;     // upper bound of the sorted entries (zero digits drop out)
-    if (total >= 0x7FFFFFFFull || n >= 0x80000000ull) return fail(BPPP_ERR_ARG, "MSM too large for 31-bit point indices");
+    const size_t total = (size_t)nwin * n2;    // upper bound of the sorted entries (zero digits drop out)
+    if (total >= 0x7FFFFFFFull || n2 >= 0x80000000ull) return fail(BPPP_ERR_ARG, "MSM too large for 31-bit point indices");
     uint32_t CH = 16; if (CH > half) CH = half;        // 2 CH sequential additions per thread: short chains, many threads
     const uint32_t nchunks = (half + CH - 1) / CH;
     int dev_for_lock = 0, sms = 148;
     CUDA_OK(cudaGetDevice(&dev_for_lock));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_for_lock);
     uint32_t nch = (uint32_t)(sms / nwin); if (nch < 1) nch = 1;      // sort blocks: nch chunks x nwin windows ~ one per SM
-    while (nch > 1 && n / nch < 4096) nch /= 2;
+    while (nch > 1 && n2 / nch < 4096) nch /= 2;
     const size_t ncount = (size_t)nb * nch, nscanblk = (ncount + 2047) / 2048;
     const size_t nslices = (total + MSM_SL - 1) / MSM_SL;
     SpanQueue sq; sq.cap = (uint32_t)(total / (32 * MSM_SL) + 2);
@@ -448,7 +482,7 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     size_t o_digits = cv.take(2 * total), o_vals = cv.take(4 * total), o_counts = cv.take(4 * ncount), o_scan = cv.take(4 * (ncount + 1));
     size_t o_bsum = cv.take(4 * (nscanblk + 1)), o_buckets = cv.take((size_t)PT_BYTES * nb), o_head = cv.take(128 * nslices), o_tail = cv.take(128 * nslices);
     size_t o_sq = cv.take(256 + 4 * (size_t)sq.cap), o_chunks = cv.take((size_t)PT_BYTES * nwin * nchunks);
-    size_t o_tmp = cv.take((size_t)PT_BYTES * ((size_t)nwin * nchunks / 16 + 2));
+    size_t o_tmp = cv.take((size_t)PT_BYTES * ((size_t)nwin * nchunks / 16 + 2)), o_bx = cv.take(32 * n);
     std::lock_guard<std::mutex> slab_lock(g_slab_mu[dev_for_lock & 15]);     // released after the final synchronise below
     uint8_t *slab = nullptr;
     int rc = scratch_reserve(cv.total, &slab);
@@ -456,7 +490,7 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     uint16_t *digits = (uint16_t *)(slab + o_digits);
     uint32_t *vals = (uint32_t *)(slab + o_vals), *counts = (uint32_t *)(slab + o_counts), *scan = (uint32_t *)(slab + o_scan), *bsum = (uint32_t *)(slab + o_bsum);
     uint32_t *buckets = (uint32_t *)(slab + o_buckets), *head = (uint32_t *)(slab + o_head), *tail = (uint32_t *)(slab + o_tail);
-    uint32_t *chunks = (uint32_t *)(slab + o_chunks), *tmp = (uint32_t *)(slab + o_tmp);
+    uint32_t *chunks = (uint32_t *)(slab + o_chunks), *tmp = (uint32_t *)(slab + o_tmp), *bx = (uint32_t *)(slab + o_bx);
     sq.count = (uint32_t *)(slab + o_sq); sq.bucket = sq.count + 64;
     static bool smem_set[16] = {};
     if (!smem_set[dev_for_lock & 15]) {
@@ -466,16 +500,17 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     }
     CUDA_OK(cudaMemsetAsync(sq.count, 0, 4, st));
     GL(k_msm_digits, nblocks(n, 128), 128, d_sc, n, c, nwin, digits);
-    k_msm_hist<<<dim3(nch, (unsigned)nwin), 1024, 4 * (size_t)half, st>>>(digits, n, half, nch, counts); g_generic_launches++;
+    GL(k_msm_endo_x, nblocks(n, 128), 128, d_pts, n, bx);
+    k_msm_hist<<<dim3(nch, (unsigned)nwin), 1024, 4 * (size_t)half, st>>>(digits, n2, half, nch, counts); g_generic_launches++;
     GL(k_scan_blocks, (unsigned)nscanblk, 256, counts, ncount, scan, bsum);
     GL(k_scan_sums, 1, 1024, bsum, nscanblk, scan + ncount);
     GL(k_scan_add, (unsigned)nscanblk, 256, scan, ncount, bsum);
     uint32_t nrange = (uint32_t)(sms / nwin); if (nrange < 1) nrange = 1;
     if (nrange > half) nrange = half;
     const uint32_t span = (half + nrange - 1) / nrange;
-    k_msm_scatter<<<dim3((half + span - 1) / span, (unsigned)nwin), 1024, 4 * (size_t)span, st>>>(digits, n, half, span, nch, scan, vals); g_generic_launches++;
+    k_msm_scatter<<<dim3((half + span - 1) / span, (unsigned)nwin), 1024, 4 * (size_t)span, st>>>(digits, n2, half, span, nch, scan, vals); g_generic_launches++;
     SortedView sv; sv.scan = scan; sv.nch = nch; sv.nb = nb;
-    GL(k_msm_slices, nblocks(nslices, 64), 64, d_pts, vals, sv, buckets, head, tail);
+    GL(k_msm_slices, nblocks(nslices, 64), 64, d_pts, bx, vals, sv, buckets, head, tail);
     GL(k_msm_fixup, nblocks(nb, 64), 64, sv, head, tail, buckets, sq);
     GL(k_msm_fixup_wide, sq.cap, 128, sv, head, tail, buckets, sq);
     GL(k_msm_chunks, nblocks((size_t)nwin * nchunks, 64), 64, buckets, nwin, half, CH, nchunks, chunks);

@@ -41,6 +41,26 @@ def test_msm_matches_naive_vector_mul(oracle, ref, n):
     assert B.msm(P, S) == oracle.msm(P, S) if n else B.msm(P, S) == b"\0" * 33
 
 
+def test_msm_sixteen_bit_windows_tie_digits(oracle, ref):
+    """n = 2^18 is the smallest size that selects 16-bit windows over the 2^19 GLV halves.  A half-scalar window equal to
+    2^15 exactly (about 30 of the 4 M digits here, half of them on a negated half) is the one digit whose code collides with the
+    zero marker unless the tie takes the other sign; the sum is checked against the oracle's naive vector_mul and against the
+    same MSM cut into quarters (15-bit windows, another digit layout)."""
+    import bp_pp_b200 as B
+    n = 1 << 18
+    rnd = random.Random(2018)
+    g = xy(ref.pt_mul(ref.G, 11))
+    pts = B.points_generate(g, xy(ref.pt_mul(ref.G, 29)), n)
+    sc = [rnd.randrange(ref.N) for _ in range(n)]
+    S = b"".join(_be(s) for s in sc)
+    whole = B.msm(pts, S)
+    q = n // 4
+    parts = b"".join(B.msm(pts[64 * q * j:64 * q * (j + 1)], S[32 * q * j:32 * q * (j + 1)]) for j in range(4))
+    assert B.points_sum(parts) == whole
+    oracle.use_native()
+    assert whole == oracle.msm(pts, S)
+
+
 def test_msm_zero_extension_and_degenerate_buckets(oracle, ref):
     import bp_pp_b200 as B
     n = 3000
