@@ -24,6 +24,7 @@ EXPORTS = [
     "bppp_wnla_commit", "bppp_wnla_prove", "bppp_wnla_verify",
     "bppp_wnla_shard_create", "bppp_wnla_shard_destroy", "bppp_wnla_shard_state", "bppp_wnla_shard_commit_partial", "bppp_wnla_shard_xr_partial",
     "bppp_wnla_shard_fold", "bppp_wnla_shard_export",
+    "bppp_peer_create", "bppp_peer_connect", "bppp_peer_destroy", "bppp_peer_world", "bppp_peer_rank", "bppp_peer_msm_allsum", "bppp_peer_allgather",
     "bppp_circuit_commit", "bppp_circuit_prove", "bppp_circuit_verify", "bppp_circuit_commit_sparse", "bppp_circuit_prove_sparse", "bppp_circuit_verify_sparse",
     "bppp_reciprocal_commit_value", "bppp_reciprocal_prove", "bppp_reciprocal_verify",
 ]
@@ -53,6 +54,8 @@ def lib():
         L.bppp_multi_ctx_get.argtypes = [C.c_void_p, C.c_int]
         L.bppp_wnla_shard_destroy.argtypes = [C.c_void_p]
         L.bppp_wnla_shard_destroy.restype = None
+        L.bppp_peer_destroy.argtypes = [C.c_void_p]
+        L.bppp_peer_destroy.restype = None
         L.bppp_device_free.restype = None
         L.bppp_device_free.argtypes = [C.c_int, C.c_void_p]
         _lib = L

@@ -11,6 +11,7 @@
 // (the same sc.cuh code the kernels run).  The batched u64 fast path (engine_prove.cu / engine_verify.cu) is the specialisation of this
 // file with closed-form coefficients and on-device transcripts.
 #define BPPP_FE_NOINLINE 1
+#define BPPP_GENERIC_ALLOC 1   // engine_generic.cuh: cudaMalloc / cudaFree of this file go through the caching allocator
 #include <algorithm>
 #include <map>
 #include "engine_generic.cuh"

@@ -38,4 +38,18 @@ int wnla_verify_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, c
 int point_bytes_to_pt30(cudaStream_t st, const uint8_t *p, int fmt, uint32_t *d_out30);
 uint64_t wnla_launch_count();
 
+// Caching device allocator of the generic paths (implemented in engine_multi.cu, which keeps the real calls).  One WNLA prove makes dozens of short-lived device buffers;
+// cudaMalloc / cudaFree each cost a device-wide map / unmap (far worse once peer access is enabled: every allocation is mapped
+// into the peers), which dominated the wall time next to ~0.15 s of kernels.  dev_free keeps cudaFree's contract -- it waits
+// for the device before the block can be handed out again -- but parks the block in a per-device size-class list.
+cudaError_t dev_malloc(void **p, size_t bytes);
+cudaError_t dev_free(void *p);
+void dev_trim(int device);            // return every parked block of the device to CUDA
+
 }  // namespace bppp
+
+// the generic translation units allocate through the cache
+#if defined(BPPP_GENERIC_ALLOC)
+#define cudaMalloc(p, n) bppp::dev_malloc((void **)(p), (n))
+#define cudaFree(p) bppp::dev_free((void *)(p))
+#endif

@@ -15,6 +15,7 @@
 //   k_pt_sum_groups   tree sums;  k_msm_horner: sum_w 2^(c w) W_w
 // Small inputs (n <= 1024) use one GLV scalar multiplication per point and the same tree sum.
 #define BPPP_FE_NOINLINE 1
+#define BPPP_GENERIC_ALLOC 1   // engine_generic.cuh: cudaMalloc / cudaFree of this file go through the caching allocator
 #define BPPP_PTX_ADD_NOINLINE 1   // ec.cuh: the bucket accumulation's XYZZ addition as one call with inlined products
 #include "engine_generic.cuh"
 
@@ -689,12 +690,31 @@ extern "C" int bppp_points_generate(int device, const uint8_t *base64, const uin
     return BPPP_OK;
 }
 
-// sum of n points (e.g. the partial sums gathered from the ranks of a split MSM)
+// sum of n points (e.g. the partial sums gathered from the ranks of a split MSM, the shares of X and R of a sharded WNLA round)
+__global__ void k_points_sum_small(const uint32_t *pts, size_t n, uint32_t *out30) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Pt acc = pt_identity();
+    for (size_t i = 0; i < n; i++) {
+        PtA q;
+        if (load_dev_point(q, pts, i)) acc = pt_add_mixed(acc, q);
+    }
+    st_pt30(out30, acc);
+}
 extern "C" int bppp_points_sum(int device, const uint8_t *points, int points_fmt, size_t n, int out_fmt, uint8_t *out) {
     if (!out || (n && !points)) return fail(BPPP_ERR_ARG, "null argument");
     int rc = pick_device(device);
     if (rc != BPPP_OK) return rc;
-    std::vector<uint8_t> ones(32 * (n ? n : 1), 0);
+    if (n <= 256) {                        // a handful of points: n - 1 additions by one thread instead of n scalar multiplications by one
+        uint32_t *d_pts = nullptr, *d_out = nullptr;
+        rc = decode_points_to_device(nullptr, points, points_fmt, n, &d_pts);
+        if (rc != BPPP_OK) return rc;
+        CUDA_OK(cudaMalloc(&d_out, PT_BYTES));
+        k_points_sum_small<<<1, 1>>>(d_pts, n, d_out);
+        rc = encode_points_from_device(nullptr, d_out, 1, out_fmt, out);
+        cudaFree(d_pts); cudaFree(d_out);
+        return rc;
+    }
+    std::vector<uint8_t> ones(32 * n, 0);
     for (size_t i = 0; i < n; i++) ones[32 * i + 31] = 1;
     return bppp_msm(device, points, points_fmt, n, ones.data(), n, out_fmt, out);
 }

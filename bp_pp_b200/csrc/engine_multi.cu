@@ -8,9 +8,77 @@
 #include <functional>
 #include <thread>
 
-#include "engine_common.cuh"
+#include <map>
+
+#include "engine_generic.cuh"
 
 using namespace bppp;
+
+// ---- caching device allocator (declared in engine_generic.cuh; this file calls the real cudaMalloc / cudaFree) ----
+namespace {
+struct DevCache {
+    std::mutex mu;
+    std::multimap<size_t, void *> parked;          // size class -> block
+    std::map<void *, size_t> live;                 // block -> size class
+    size_t parked_bytes = 0;
+};
+DevCache g_cache[16];
+constexpr size_t CACHE_CAP = (size_t)24 << 30;     // parked bytes per device before blocks go back to CUDA
+// size classes: eight per octave (at most 12.5 % slack), 512-byte granularity at the bottom
+size_t size_class(size_t n) {
+    if (n < 512) return 512;
+    size_t p = 512;
+    while (p * 2 <= n) p *= 2;                     // p <= n < 2p
+    size_t step = p / 8;
+    return (n + step - 1) / step * step;
+}
+}  // namespace
+namespace bppp {
+cudaError_t dev_malloc(void **out, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    DevCache &c = g_cache[dev & 15];
+    const size_t cls = size_class(bytes);
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.parked.find(cls);
+        if (it != c.parked.end()) {
+            *out = it->second; c.live[*out] = cls; c.parked_bytes -= cls; c.parked.erase(it);
+            return cudaSuccess;
+        }
+    }
+    e = cudaMalloc(out, cls);
+    if (e == cudaErrorMemoryAllocation) { (void)cudaGetLastError(); dev_trim(dev); e = cudaMalloc(out, cls); }
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> lk(c.mu); c.live[*out] = cls; }
+    return e;
+}
+cudaError_t dev_free(void *p) {
+    if (!p) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    DevCache &c = g_cache[dev & 15];
+    size_t cls = 0;
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.live.find(p);
+        if (it == c.live.end()) return cudaFree(p);          // not ours (allocated before the cache existed / by another unit)
+        cls = it->second; c.live.erase(it);
+    }
+    e = cudaDeviceSynchronize();                             // cudaFree's contract: nothing in flight still uses the block
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.parked_bytes + cls > CACHE_CAP) return cudaFree(p);
+    c.parked.emplace(cls, p); c.parked_bytes += cls;
+    return e;
+}
+void dev_trim(int device) {
+    DevCache &c = g_cache[device & 15];
+    std::lock_guard<std::mutex> lk(c.mu);
+    for (auto &kv : c.parked) cudaFree(kv.second);
+    c.parked.clear(); c.parked_bytes = 0;
+}
+}  // namespace bppp
 
 struct bppp_multi_ctx {
     std::vector<bppp_ctx *> ctx;

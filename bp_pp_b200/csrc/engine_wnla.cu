@@ -16,6 +16,7 @@
 //   H_i : l[i >> R] * prod_k y_k^bit_k(i)        G_i : n[i >> R] * prod_k (bit_k(i) ? y_k : rho_k)
 // (rho_0 = rho, rho_{k+1} = mu_k, mu_{k+1} = mu_k^2), bit-identical to the round-by-round evaluation.
 #define BPPP_FE_NOINLINE 1
+#define BPPP_GENERIC_ALLOC 1   // engine_generic.cuh: cudaMalloc / cudaFree of this file go through the caching allocator
 #include <algorithm>
 #include <functional>
 #include "engine_generic.cuh"

@@ -39,6 +39,68 @@ def gather_status(local: Sequence[int], n: int) -> List[int]:
     return full
 
 
+class PeerGroup:
+    """The ranks' mailboxes for the library's own exchange kernels (bppp_peer, include/bppp.h): remote stores over NVLink /
+    NVSwitch into every peer's HBM plus an epoch flag, instead of a collective-library call per exchange.  One per process;
+    the 64-byte CUDA IPC handles are all-gathered once here through torch.distributed (set-up, not data path)."""
+
+    def __init__(self, device: int):
+        import ctypes as C
+        import torch.distributed as dist
+        from ._lib import check, lib
+        from .api import _in
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.world, self.rank = (dist.get_world_size(), dist.get_rank()) if multi else (1, 0)
+        self.device = device
+        self._h = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        check(lib().bppp_peer_create(C.byref(self._h), C.c_int(device), C.c_int(self.world), C.c_int(self.rank), handle), "bppp_peer_create")
+        if multi:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle))
+            check(lib().bppp_peer_connect(self._h, _in(b"".join(handles))), "bppp_peer_connect")
+            dist.barrier()                      # every mailbox is mapped everywhere before the first remote store
+
+    def msm_allsum(self, up, out_fmt: int = 0):
+        """Sum over all ranks of each rank's resident block MSM (api.UploadedMsm): (encoded point, device ms from the first
+        MSM kernel to the reduced sum).  Every rank must call it."""
+        import ctypes as C
+        from ._lib import check, lib
+        from .api import _psz
+        out, ms = (C.c_uint8 * _psz(out_fmt))(), C.c_float()
+        check(lib().bppp_peer_msm_allsum(self._h, up._p, up._s, C.c_size_t(up.n), C.c_int(out_fmt), out, C.byref(ms)), "bppp_peer_msm_allsum")
+        return bytes(out), ms.value
+
+    def allgather(self, mine: bytes) -> List[bytes]:
+        """One short byte string per rank (4..240 bytes, a multiple of 4), returned in rank order on every rank."""
+        import ctypes as C
+        from ._lib import check, lib
+        from .api import _in
+        out = (C.c_uint8 * (len(mine) * self.world))()
+        check(lib().bppp_peer_allgather(self._h, _in(mine), C.c_size_t(len(mine)), out), "bppp_peer_allgather")
+        raw = bytes(out)
+        return [raw[len(mine) * r:len(mine) * (r + 1)] for r in range(self.world)]
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            import ctypes as C
+            from ._lib import lib
+            lib().bppp_peer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def msm_sharded_resident(up, peer: "PeerGroup", out_fmt: int = 0):
+    """`util::vector_mul` over a point vector cut into one resident block per rank (src/util.rs:46-60): block Pippenger, remote
+    stores of the partial sums and their reduction fused on each GPU's stream (PeerGroup.msm_allsum) -> (point, device ms)."""
+    return peer.msm_allsum(up, out_fmt)
+
+
 def msm_sharded(points: bytes, scalars32: bytes, device: int, points_fmt: int = 1) -> bytes:
     """One large MSM split by point range over the ranks of the process group (one GPU each): every rank computes the
     partial sum of its contiguous block on its own GPU, the 33-byte partial points are all-gathered (NCCL when the group
@@ -135,13 +197,24 @@ class WnlaShard:
 _N = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
 
 
-def _gather_bytes(mine: bytes, device: int) -> List[bytes]:
-    """All-gather of one equal-length byte string per process (NCCL on the GPU under an nccl group, gloo on the CPU);
-    a single-process call returns [mine]."""
+def compress64(p64: bytes) -> bytes:
+    """64-byte affine (x || y, all-zero = identity) -> the engine's 33-byte form (SEC1 tag from y's parity; identity = 33 zero
+    bytes): a re-encoding of canonical coordinates, no curve arithmetic."""
+    if p64 == b"\0" * 64:
+        return b"\0" * 33
+    return bytes([2 + (p64[63] & 1)]) + p64[:32]
+
+
+def _gather_bytes(mine: bytes, device: int, peer: "PeerGroup" = None) -> List[bytes]:
+    """All-gather of one equal-length byte string per process: through the peer mailboxes when a PeerGroup is given and the
+    string fits a slot, else torch.distributed (NCCL on the GPU under an nccl group, gloo on the CPU); a single-process
+    call returns [mine]."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return [mine]
+    if peer is not None and 4 <= len(mine) <= 240 and len(mine) % 4 == 0:
+        return peer.allgather(mine)
     dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
     t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
     outs = [torch.empty_like(t) for _ in range(dist.get_world_size())]
@@ -149,7 +222,8 @@ def _gather_bytes(mine: bytes, device: int) -> List[bytes]:
     return [bytes(o.cpu().numpy().tobytes()) for o in outs]
 
 
-def wnla_prove_sharded(g64: bytes, blocks: Sequence[dict], rho32: bytes, mu32: bytes, commitment33: bytes, t, devices: Sequence[int], stats: dict = None):
+def wnla_prove_sharded(g64: bytes, blocks: Sequence[dict], rho32: bytes, mu32: bytes, commitment33: bytes, t, devices: Sequence[int], stats: dict = None,
+                       peer: "PeerGroup" = None):
     """`WeightNormLinearArgument::prove(&self, commitment, t, l, n)` (src/wnla.rs:125-190) for an instance cut into equal,
     contiguous blocks: this process holds `blocks` (dicts with hvec64, c32, l32, gvec64, n32), block j resident on
     devices[j]; under torch.distributed the processes' blocks follow each other in rank order.  `t` is the caller's
@@ -158,7 +232,8 @@ def wnla_prove_sharded(g64: bytes, blocks: Sequence[dict], rho32: bytes, mu32: b
     strings, r / x innermost round first (wnla.rs:186-188), byte-identical to the single-GPU bppp_wnla_prove.
 
     Per round: each block's shares of X and R on its own GPU (host threads within a process), ONE all-gather of
-    128 bytes per block, identical transcript everywhere, local fold.  Once the blocks are too short to fold locally
+    128 bytes per block (through `peer`'s mailboxes when given: remote stores by the library's own kernels; else
+    torch.distributed), identical transcript everywhere, local fold.  Once the blocks are too short to fold locally
     (2^17 -> 1 element after 17 rounds for 2^20 generators on 8 GPUs) their contents are all-gathered and every process
     finishes the last rounds on one GPU."""
     import time
@@ -187,13 +262,13 @@ def wnla_prove_sharded(g64: bytes, blocks: Sequence[dict], rho32: bytes, mu32: b
     com_future = None
 
     def total(parts64):          # sum of 64-byte affine points -> (affine64, compressed33)
-        allp = b"".join(parts64)
-        return (api.points_sum(allp, api.FMT_AFFINE64, api.FMT_AFFINE64, dev0), api.points_sum(allp, api.FMT_AFFINE64, api.FMT_COMPRESSED, dev0))
+        p64 = api.points_sum(b"".join(parts64), api.FMT_AFFINE64, api.FMT_AFFINE64, dev0)
+        return p64, compress64(p64)
 
     if commitment33 is None:
         # WeightNormLinearArgument::commit(l, n) (wnla.rs:66-72) block by block: what a caller computes before proving
         cp = b"".join(pmap(lambda sh: sh.commit_partial(), shards))
-        cp = cp if whole else b"".join(_gather_bytes(cp, dev0))
+        cp = cp if whole else b"".join(_gather_bytes(cp, dev0, peer))
         com64, com33 = total([cp[o:o + 64] for o in range(0, len(cp), 64)])
         st["commitment33"] = com33
     else:
@@ -222,7 +297,7 @@ def wnla_prove_sharded(g64: bytes, blocks: Sequence[dict], rho32: bytes, mu32: b
                 com64, com33 = com_future.result()
                 com_future = None
             mine = b"".join(p for p, _ in parts)
-            allparts = mine if whole else b"".join(_gather_bytes(mine, dev0))
+            allparts = mine if whole else b"".join(_gather_bytes(mine, dev0, peer))
             if not whole:
                 st["exchange_bytes"] += len(allparts)
             X64, X33 = total([allparts[o:o + 64] for o in range(0, len(allparts), 128)])
@@ -235,7 +310,7 @@ def wnla_prove_sharded(g64: bytes, blocks: Sequence[dict], rho32: bytes, mu32: b
                 # the reference recomputes wnla'.commit(l', n') (wnla.rs:186); it equals C + y X + (y^2 - 1) R only when the
                 # caller's commitment matched (l, n), so the first re-commit is evaluated literally, block by block
                 cp = b"".join(pmap(lambda sh: sh.commit_partial(), shards))
-                cp = cp if whole else b"".join(_gather_bytes(cp, dev0))
+                cp = cp if whole else b"".join(_gather_bytes(cp, dev0, peer))
                 com64, com33 = total([cp[o:o + 64] for o in range(0, len(cp), 64)])
                 first = False
             else:
@@ -243,7 +318,7 @@ def wnla_prove_sharded(g64: bytes, blocks: Sequence[dict], rho32: bytes, mu32: b
                     y = int.from_bytes(yb, "big")
                     sc = (1).to_bytes(32, "big") + yb + ((y * y - 1) % _N).to_bytes(32, "big")
                     n64 = api.msm(c64 + x64 + r64, sc, api.FMT_AFFINE64, api.FMT_AFFINE64, dev0)
-                    return n64, api.points_convert(n64, api.FMT_AFFINE64, api.FMT_COMPRESSED, dev0)
+                    return n64, compress64(n64)
                 com_future = pool.submit(next_commitment)
             rs.append(R33); xs.append(X33)
             len_l, len_n = (len_l + 1) // 2, (len_n + 1) // 2

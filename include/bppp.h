@@ -211,6 +211,28 @@ int bppp_wnla_shard_xr_partial(bppp_wnla_shard *s, uint8_t *out128, float *devic
 int bppp_wnla_shard_fold(bppp_wnla_shard *s, const uint8_t *y32, float *device_ms);     /* src/wnla.rs:170-184 on the block */
 int bppp_wnla_shard_export(bppp_wnla_shard *s, uint8_t *hvec64, uint8_t *c32, uint8_t *l32, uint8_t *gvec64, uint8_t *n32);
 
+/* ---- peer exchange over NVLink / NVSwitch (one process per GPU) ------------------------------------------------------
+ * The two exchange steps of the path -- the partial sums of a point-range-split util::vector_mul (src/util.rs:46-60) and
+ * the per-round shares of X and R of a block-sharded WeightNormLinearArgument::prove (src/wnla.rs:152-160) -- done by the
+ * library's own kernels: every rank owns a mailbox in its HBM, a producer stores its payload straight into its slot of every
+ * peer's mailbox (remote stores), fences and publishes an epoch flag; a consumer kernel spins on its local flags and
+ * reduces / copies the slots.  _create returns the mailbox's 64-byte CUDA IPC handle; the caller gathers the handles of
+ * all ranks once (any transport) and passes them, in rank order, to _connect.  The collective calls (_msm_allsum,
+ * _allgather) must be made by every rank in the same order.  world <= 16.  A rank that never arrives ends the wait with
+ * BPPP_ERR_CUDA after 20 s. */
+typedef struct bppp_peer bppp_peer;
+int bppp_peer_create(bppp_peer **out, int device, int world, int rank, uint8_t *ipc_handle64_out);
+int bppp_peer_connect(bppp_peer *p, const uint8_t *handles /* world x 64 bytes */);
+void bppp_peer_destroy(bppp_peer *p);
+int bppp_peer_world(const bppp_peer *p);
+int bppp_peer_rank(const bppp_peer *p);
+/* sum over all ranks of each rank's block MSM (handles from bppp_points_upload / bppp_scalars_upload): Pippenger, the remote
+ * stores of the partial sum and the reduction of the world's partial sums back to back on one stream; every rank receives
+ * the same point.  *elapsed_ms (optional): device time from the first MSM kernel to the reduced sum. */
+int bppp_peer_msm_allsum(bppp_peer *p, const void *points_handle, const void *scalars_handle, size_t n, int out_fmt, uint8_t *out, float *elapsed_ms);
+/* all-gather of one short byte string per rank (4..240 bytes, a multiple of 4): out = world x bytes in rank order */
+int bppp_peer_allgather(bppp_peer *p, const uint8_t *in, size_t bytes, uint8_t *out);
+
 /* ArithmeticCircuit<P> (src/circuit.rs:95-139) with dense row-major W_m (dim_nm x dim_nw) and W_l (dim_nl x dim_nw),
  * dim_nl = dim_nv * k, dim_nw = 2 dim_nm + dim_no, and the partition closure tabulated: part_xx[j] = index or -1 for
  * j < part_n, None beyond (PartitionType LO / LL / LR / NO, src/circuit.rs:15-20); entries must lie in [-1, dim_no).  Generators 64-byte affine. */

@@ -4,6 +4,7 @@ use std::os::raw::{c_char, c_int, c_void};
 #[repr(C)] pub struct bppp_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct bppp_multi_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct bppp_wnla_shard { _p: [u8; 0] }
+#[repr(C)] pub struct bppp_peer { _p: [u8; 0] }
 
 pub const BPPP_OK: c_int = 0;
 pub const BPPP_FMT_COMPRESSED: c_int = 0;
@@ -58,6 +59,11 @@ extern "C" {
     pub fn bppp_wnla_shard_xr_partial(s: *mut bppp_wnla_shard, out128: *mut u8, device_ms: *mut f32) -> c_int;
     pub fn bppp_wnla_shard_fold(s: *mut bppp_wnla_shard, y32: *const u8, device_ms: *mut f32) -> c_int;
     pub fn bppp_wnla_shard_export(s: *mut bppp_wnla_shard, hvec64: *mut u8, c32: *mut u8, l32: *mut u8, gvec64: *mut u8, n32: *mut u8) -> c_int;
+    pub fn bppp_peer_create(out: *mut *mut bppp_peer, device: c_int, world: c_int, rank: c_int, ipc_handle64_out: *mut u8) -> c_int;
+    pub fn bppp_peer_connect(p: *mut bppp_peer, handles: *const u8) -> c_int;
+    pub fn bppp_peer_destroy(p: *mut bppp_peer);
+    pub fn bppp_peer_msm_allsum(p: *mut bppp_peer, points_handle: *const c_void, scalars_handle: *const c_void, n: usize, out_fmt: c_int, out: *mut u8, elapsed_ms: *mut f32) -> c_int;
+    pub fn bppp_peer_allgather(p: *mut bppp_peer, input: *const u8, bytes: usize, out: *mut u8) -> c_int;
     pub fn bppp_reciprocal_prove(device: c_int, dim_nd: usize, dim_np: usize, g64: *const u8, gvec64: *const u8, gn: usize, hvec64: *const u8, hn: usize,
                                  gvec2_64: *const u8, gn2: usize, hvec2_64: *const u8, hn2: usize, x32: *const u8, s32: *const u8, digits: *const u32,
                                  rng: *const u8, rng_len: usize, label: *const u8, label_len: usize, out: *mut u8, out_cap: usize, rounds_out: *mut usize,

@@ -24,7 +24,7 @@ def _worker(rank, world, port, q):
         import torch.distributed as dist
         import bp_pp_b200 as B
         from bp_pp_b200 import synth
-        from bp_pp_b200.shard import wnla_prove_sharded
+        from bp_pp_b200.shard import PeerGroup, wnla_prove_sharded
         from bp_pp_b200.transcript import Transcript
         dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
         dev = rank % torch.cuda.device_count()
@@ -61,11 +61,19 @@ def _worker(rank, world, port, q):
         per = n // world
         sl = lambda b, item: b[item * per * rank:item * per * (rank + 1)]      # noqa: E731
         stats = {}
+        peer = PeerGroup(dev)            # mailboxes in both ranks' HBM (CUDA IPC between the two processes): the library's own exchange kernels
         got = wnla_prove_sharded(g, [dict(hvec64=sl(hvec, 64), c32=sl(c, 32), l32=sl(l, 32), gvec64=sl(gvec, 64), n32=sl(nn, 32))], rho, mu, None,
-                                 Transcript(b"two ranks"), [dev], stats)
+                                 Transcript(b"two ranks"), [dev], stats, peer)
         w = B.WeightNormLinearArgument(g, gvec, hvec, c, rho, mu, device=dev)
         com = w.commit(l, nn)
         ok = ok and stats["commitment33"] == com and got == w.prove(com, b"two ranks", l, nn) and stats["rounds_sharded"] >= 10
+        # ---- the split MSM: block Pippenger + remote stores of the partial sums + their reduction, fused on each GPU's stream ----
+        up = B.UploadedMsm(sl(hvec, 64), sl(l, 32), device=dev)
+        for _ in range(3):               # the epoch counter and both slot parities
+            total, ms = peer.msm_allsum(up)
+            ok = ok and total == B.msm(hvec, l, device=dev) and ms > 0
+        ok = ok and peer.allgather(bytes([rank + 1]) * 240) == [bytes([r + 1]) * 240 for r in range(world)]
+        up.close(); peer.close()
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, bool(ok), ""))
