@@ -1,7 +1,20 @@
 // libbppp.so, variable-base translation unit: the joint Straus ladders over per-proof points
 // (one thread per proof, tables of 1P..8P per point in thread-local memory).
+//
+// engine_var_lat.cu compiles this file a second time with BPPP_VAR_LAT: only the 4-lane kernels, with the call boundary at the
+// point operation (ec.cuh: BPPP_PTJ_*_NOINLINE -- a doubling / mixed addition is one function with its products inlined, so
+// ptxas overlaps the independent products of one formula).  That shortens the dependent chain of a proof: 4-lane ladders
+// 1.84 -> 1.53 ms at 2,048 proofs, 2.37 -> 2.17 ms at 8,192 (profiles/r2_kernel_experiments.txt); with the GPU full it loses
+// (instruction-cache footprint), so the throughput kernels keep the field-level calls.
 #ifndef BPPP_VAR_INLINE
 #define BPPP_FE_NOINLINE 1   // see fe.cuh: keeps the ladder loop inside the instruction cache
+#endif
+#if defined(BPPP_VAR_LAT)
+#define BPPP_PTJ_DBL_NOINLINE 1
+#define BPPP_PTJ_ADD_NOINLINE 1
+#define LATNAME(x) x##_lat
+#else
+#define LATNAME(x) x
 #endif
 #include "engine_common.cuh"
 
@@ -13,6 +26,7 @@ using namespace bppp;
 #ifndef BPPP_VAR_MINBLOCKS
 #define BPPP_VAR_MINBLOCKS 7
 #endif
+#if !defined(BPPP_VAR_LAT)
 __global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_v_var5(WS w) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < w.n) u64v_var5_one(w, i);
@@ -25,11 +39,12 @@ __global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_p_var2(W
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < w.n) u64p_var2_one(w, i, j);
 }
+#endif
 // The same ladders with LANES adjacent threads per proof (straus_tables_partial): the GLV halves are shared out, every lane
 // repeats the doublings, the partial sums meet through warp shuffles.  More total work, a shorter dependent chain and
 // LANES times the warps: selected when the (sub-)batch alone leaves most of the GPU idle.
 template <int LANES>
-__global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_v_var5_lanes(WS w) {
+__global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) LATNAME(k_v_var5_lanes)(WS w) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t i = t / LANES; const int lane = (int)(t % LANES);
     const bool live = i < w.n;
@@ -38,7 +53,7 @@ __global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_v_var5_l
     if (live && lane == 0) ws_st_pt(w, i, VL::COM, pt_add(part, ws_ld_pt(w, i, VL::ACC)));
 }
 template <int LANES>
-__global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_v_var2_lanes(WS w, int j) {
+__global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) LATNAME(k_v_var2_lanes)(WS w, int j) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t i = t / LANES; const int lane = (int)(t % LANES);
     const bool live = i < w.n;
@@ -47,7 +62,7 @@ __global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_v_var2_l
     if (live && lane == 0) ws_st_pt(w, i, VL::COM, pt_add(part, ws_ld_pt(w, i, VL::COM)));
 }
 template <int LANES>
-__global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_p_var2_lanes(WS w, int j) {
+__global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) LATNAME(k_p_var2_lanes)(WS w, int j) {
     (void)j;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t i = t / LANES; const int lane = (int)(t % LANES);
@@ -56,6 +71,13 @@ __global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_p_var2_l
     Pt part = lanes_reduce<LANES>(u64p_var2_partial(w, i, lane, LANES));
     if (live && lane == 0) ws_st_pt(w, i, PL::COM, pt_add(part, ws_ld_pt(w, i, PL::COM)));
 }
+#if defined(BPPP_VAR_LAT)
+namespace bppp {
+void launch_v_var5_lat(bppp_ctx *c, cudaStream_t st, WS w) { LAUNCH(c, k_v_var5_lanes_lat<4>, nblocks(w.n * 4, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w); }
+void launch_v_var2_lat(bppp_ctx *c, cudaStream_t st, WS w, int j) { LAUNCH(c, k_v_var2_lanes_lat<4>, nblocks(w.n * 4, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j); }
+void launch_p_var2_lat(bppp_ctx *c, cudaStream_t st, WS w, int j) { LAUNCH(c, k_p_var2_lanes_lat<4>, nblocks(w.n * 4, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j); }
+}  // namespace bppp
+#else
 __global__ void __launch_bounds__(64) k_p_tables_build(WS w, int j) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int p = (int)(t / w.n); size_t i = t - (size_t)p * w.n;
@@ -66,6 +88,10 @@ __global__ void __launch_bounds__(128) k_p_tables_normalize(WS w, size_t nthread
     if (t < nthreads) tables_normalize_strided(w, ptab_region(), t, nthreads);
 }
 namespace bppp {
+// engine_var_lat.cu: the 4-lane kernels built for latency
+void launch_v_var5_lat(bppp_ctx *c, cudaStream_t st, WS w);
+void launch_v_var2_lat(bppp_ctx *c, cudaStream_t st, WS w, int j);
+void launch_p_var2_lat(bppp_ctx *c, cudaStream_t st, WS w, int j);
 // lanes per proof for the ladders, by the number of proofs in flight on the GPU
 static int var_lanes_for(const bppp_ctx *c, size_t n) {
     if (c->var_lanes_override) return c->var_lanes_override;
@@ -80,13 +106,13 @@ void launch_v_var5(bppp_ctx *c, cudaStream_t st, WS w) {
     const int lanes = var_lanes_for(c, w.n);
     if (lanes == 1) LAUNCH(c, k_v_var5, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w);
     else if (lanes == 2) LAUNCH(c, k_v_var5_lanes<2>, nblocks(w.n * 2, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w);
-    else LAUNCH(c, k_v_var5_lanes<4>, nblocks(w.n * 4, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w);
+    else launch_v_var5_lat(c, st, w);
 }
 void launch_v_var2(bppp_ctx *c, cudaStream_t st, WS w, int j) {
     const int lanes = var_lanes_for(c, w.n);
     if (lanes == 1) LAUNCH(c, k_v_var2, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
     else if (lanes == 2) LAUNCH(c, k_v_var2_lanes<2>, nblocks(w.n * 2, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
-    else LAUNCH(c, k_v_var2_lanes<4>, nblocks(w.n * 4, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
+    else launch_v_var2_lat(c, st, w, j);
 }
 void launch_p_var2(bppp_ctx *c, cudaStream_t st, WS w, int j) {
     // tables of X_j, R_j (point-major), one cross-proof inversion for their 16 entries, then the ladder
@@ -98,6 +124,7 @@ void launch_p_var2(bppp_ctx *c, cudaStream_t st, WS w, int j) {
     const int lanes = var_lanes_for(c, w.n);
     if (lanes == 1) LAUNCH(c, k_p_var2, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
     else if (lanes == 2) LAUNCH(c, k_p_var2_lanes<2>, nblocks(w.n * 2, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
-    else LAUNCH(c, k_p_var2_lanes<4>, nblocks(w.n * 4, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
+    else launch_p_var2_lat(c, st, w, j);
 }
 }  // namespace bppp
+#endif

@@ -17,7 +17,7 @@ fn main() {
     }
     let csrc = env::var("BPPP_CSRC").map(PathBuf::from).unwrap_or_else(|_| manifest.join("../../bp_pp_b200/csrc"));
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
-    let units = ["engine_core", "engine_verify", "engine_prove", "engine_var", "engine_bench", "engine_msm", "engine_wnla", "engine_circuit", "engine_multi", "engine_peer"];
+    let units = ["engine_core", "engine_verify", "engine_prove", "engine_var", "engine_var_lat", "engine_bench", "engine_msm", "engine_wnla", "engine_circuit", "engine_multi", "engine_peer"];
     let mut objects = Vec::new();
     for u in units {
         let src = csrc.join(format!("{u}.cu"));

@@ -6,7 +6,7 @@ name=$1; flags=$2
 cd "$(dirname "$0")/../bp_pp_b200/csrc"
 NV="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -diag-suppress 550 $flags"
 mkdir -p _obj/var/$name ../variants
-for f in engine_core engine_verify engine_prove engine_var engine_bench engine_msm engine_wnla engine_circuit engine_multi engine_peer; do
+for f in engine_core engine_verify engine_prove engine_var engine_var_lat engine_bench engine_msm engine_wnla engine_circuit engine_multi engine_peer; do
   ( $NV -Xptxas -v -c -o _obj/var/$name/$f.o $f.cu 2> _obj/var/$name/$f.log || (cat _obj/var/$name/$f.log; false) ) &
 done
 wait
