@@ -50,10 +50,6 @@ struct bppp_ctx {
     int nsub_host = 4;              // host-buffer entry points: more, smaller sub-batches so that the first upload (3.3 KB of RNG bytes per proof for prove) is short
     cudaStream_t sub_stream[MAX_SUB] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
-    // one side stream per sub-batch: work of a phase that does not depend on the transcript (the verifier's ladder tables) runs beside the
-    // transcript / scalar kernels, which use the ALU pipe and leave the multiplier pipe idle
-    cudaStream_t aux_stream[MAX_SUB] = {};
-    cudaEvent_t ev_aux_fork[MAX_SUB] = {}, ev_aux_join[MAX_SUB] = {};
     uint64_t launches = 0;
     int sm_count = 148;
     // phase-stepped session (bppp_u64_{verify,prove}_begin .. _finish): one at a time per context, lives in the workspace

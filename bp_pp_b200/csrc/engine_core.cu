@@ -235,9 +235,6 @@ static int alloc_work(bppp_ctx *c, size_t max_batch) {
     for (int k = 0; k < bppp_ctx::MAX_SUB; k++) {
         CUDA_OK(cudaStreamCreateWithFlags(&c->sub_stream[k], cudaStreamNonBlocking));
         CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
-        CUDA_OK(cudaStreamCreateWithFlags(&c->aux_stream[k], cudaStreamNonBlocking));
-        CUDA_OK(cudaEventCreateWithFlags(&c->ev_aux_fork[k], cudaEventDisableTiming));
-        CUDA_OK(cudaEventCreateWithFlags(&c->ev_aux_join[k], cudaEventDisableTiming));
     }
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     c->max_batch = max_batch;
@@ -323,9 +320,6 @@ extern "C" void bppp_ctx_destroy(bppp_ctx *c) {
     for (int k = 0; k < bppp_ctx::MAX_SUB; k++) {
         if (c->sub_stream[k]) cudaStreamDestroy(c->sub_stream[k]);
         if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
-        if (c->aux_stream[k]) cudaStreamDestroy(c->aux_stream[k]);
-        if (c->ev_aux_fork[k]) cudaEventDestroy(c->ev_aux_fork[k]);
-        if (c->ev_aux_join[k]) cudaEventDestroy(c->ev_aux_join[k]);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     delete c;

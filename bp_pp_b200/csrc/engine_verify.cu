@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(64) k_v_verdict(WS w, int32_t *status) {
 }
 
 // ---- verify ----
-static int verify_part(bppp_ctx *c, cudaStream_t st, int part, WS w, const uint8_t *d_commits, const uint8_t *d_proofs, int fmt,
+static int verify_part(bppp_ctx *c, cudaStream_t st, WS w, const uint8_t *d_commits, const uint8_t *d_proofs, int fmt,
                        const Merlin &init, int32_t *d_status) {
     const size_t n = w.n;
     const unsigned g64 = nblocks(n, 64);
@@ -68,24 +68,14 @@ static int verify_part(bppp_ctx *c, cudaStream_t st, int part, WS w, const uint8
     LAUNCH(c, k_v_decode, nblocks(n * VP_COUNT, 128), 128, w, d_commits, d_proofs, fmt, flags);
     LAUNCH(c, k_v_load_finish, g64, 64, w, d_proofs, fmt, flags);
     launch_batch_inv(c, st, w, VL::VP + 2 * FE_W, VL::ZINV);
-    // The ladder tables depend on the decoded points only, the transcript phase and the first fixed-base sum on nothing the tables
-    // write: the tables go to this part's side stream and meet the main stream again before the first ladder.
-    CUDA_OK(cudaEventRecord(c->ev_aux_fork[part], st));
-    {
-        cudaStream_t main_st = st;
-        cudaStream_t st = c->aux_stream[part];
-        (void)main_st;
-        CUDA_OK(cudaStreamWaitEvent(st, c->ev_aux_fork[part], 0));
-        // affine 1P..8P tables of the 13 per-proof points: one batch inversion serves all 104 entries of every proof
+    LAUNCH(c, k_v_phase1, g64, 64, w, init, (const uint8_t *)nullptr, 0);
+    {   // affine 1P..8P tables of the 13 per-proof points: one batch inversion serves all 104 entries of every proof
         LAUNCH(c, k_v_tables_build, nblocks(n * VL::TAB_POINTS, 64), 64, w);
         size_t items = n * VL::TAB_ENTRIES, nthreads = (items + 63) / 64;
         LAUNCH(c, k_v_tables_normalize, nblocks(nthreads, 128), 128, w, nthreads);
-        CUDA_OK(cudaEventRecord(c->ev_aux_join[part], st));
     }
-    LAUNCH(c, k_v_phase1, g64, 64, w, init, (const uint8_t *)nullptr, 0);
     TermMap tm = identity_map();
     launch_msm_fixed(c, st, w, VL::FS, tm, 17, VL::ACC);      // pt = ps_tau g + <g_vec, pn_tau>  (circuit.rs:206)
-    CUDA_OK(cudaStreamWaitEvent(st, c->ev_aux_join[part], 0));
     launch_v_var5(c, st, w);
     for (int j = 0; j < 4; j++) {
         launch_batch_inv(c, st, w, VL::COM + 2 * FE_W, VL::ZINV);
@@ -107,7 +97,7 @@ static int verify_slice(bppp_ctx *c, cudaStream_t st, size_t n, const uint8_t *d
     if (rc != BPPP_OK) return rc;
     for (int k = 0; k < sp.parts; k++) {
         cudaStream_t s = sp.parts == 1 ? st : c->sub_stream[k];
-        rc = verify_part(c, s, k, sub_ws(c, sp, k), d_commits + csz * sp.lo[k], d_proofs + psz * sp.lo[k], fmt, init, d_status + sp.lo[k]);
+        rc = verify_part(c, s, sub_ws(c, sp, k), d_commits + csz * sp.lo[k], d_proofs + psz * sp.lo[k], fmt, init, d_status + sp.lo[k]);
         if (rc != BPPP_OK) return rc;
     }
     return join_streams(c, st, sp);
@@ -149,7 +139,7 @@ extern "C" int bppp_u64_verify_batch(bppp_ctx *c, size_t n, const uint8_t *commi
             size_t lo = sp.lo[k], cnt = sp.lo[k + 1] - sp.lo[k];
             CUDA_OK(cudaMemcpyAsync(c->d_in_a + csz * lo, commits + csz * (off + lo), csz * cnt, cudaMemcpyHostToDevice, st));
             CUDA_OK(cudaMemcpyAsync(c->d_in_b + psz * lo, proofs + psz * (off + lo), psz * cnt, cudaMemcpyHostToDevice, st));
-            int rc = verify_part(c, st, k, sub_ws(c, sp, k), c->d_in_a + csz * lo, c->d_in_b + psz * lo, fmt, init, c->d_status + lo);
+            int rc = verify_part(c, st, sub_ws(c, sp, k), c->d_in_a + csz * lo, c->d_in_b + psz * lo, fmt, init, c->d_status + lo);
             if (rc != BPPP_OK) return rc;
             CUDA_OK(cudaMemcpyAsync(status + off + lo, c->d_status + lo, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
         }

@@ -254,7 +254,7 @@ BPPP_HD Pt straus_var(const PtA *pts, const bool *ident, const Sc *ks, const Pt 
 BPPP_HD void u64v_table_build_one(const WS &w, size_t i, int t) {
     uint32_t idmask = ws_ld(w, i, VL::IDMASK);
     PtA a; bool id;
-    if (t == VTAB_VP) a = ws_affine(w, i, VL::VP, VL::ZINV, id);      // V' = V + r from its batch-inverted Z (not phase 1's copy: this kernel runs beside phase 1)
+    if (t == VTAB_VP) { a = ws_ld_pta(w, i, VL::VPA); id = idmask & (1u << 14); }
     else { a = ws_ld_pta(w, i, VL::PT + 16 * (t + 1)); id = idmask & (1u << (t + 1)); }
     PtTable8 tab;
     pt_table8_build(tab, pt_from_affine(a, id));
