@@ -6,6 +6,8 @@
 //   bp_pp::range_proof::u64_proof::U64RangeProofProtocol   src/range_proof/u64_proof.rs:19-102
 //   bp_pp::wnla::WeightNormLinearArgument                   src/wnla.rs:12-190
 //   bp_pp::range_proof::reciprocal::Proof (525-byte record) src/range_proof/reciprocal.rs:30-41
+//   bp_pp::range_proof::reciprocal::ReciprocalRangeProofProtocol   src/range_proof/reciprocal.rs:64-214 (any dim_nd, dim_np)
+//   bp_pp::circuit::ArithmeticCircuit                              src/circuit.rs:95-556 (dense W_m / W_l, tabulated partition)
 #pragma once
 #include <array>
 #include <cstdint>
@@ -120,6 +122,117 @@ private:
 };
 }  // namespace u64_proof
 }  // namespace range_proof
+
+// ---- generic records: c_l c_r c_o c_s | r[rounds] | x[rounds] | l | n (| r for the reciprocal protocol) ----
+struct GenericProof {
+    std::vector<uint8_t> record;
+    size_t rounds = 0, l_len = 0, n_len = 0;
+};
+inline const uint8_t *pts_ptr(const std::vector<Point> &v) { return v.empty() ? nullptr : v[0].data(); }
+inline const uint8_t *sc_ptr(const std::vector<Scalar> &v) { return v.empty() ? nullptr : v[0].data(); }
+inline bool verdict_to_bool(int32_t verdict, const char *what) {
+    if (verdict == BPPP_ST_PANIC_INVERT_ZERO || verdict == BPPP_ST_PANIC_CHALLENGE_RANGE) throw Panic(verdict, std::string(what) + ": the reference would panic");
+    if (verdict < 0) throw Malformed(verdict, std::string(what) + ": the proof does not deserialise");
+    return verdict == BPPP_ST_TRUE;
+}
+
+namespace range_proof {
+namespace reciprocal {
+// reciprocal.rs:22-28: the committed value, its blinding and the digits (base dim_np, dim_nd of them)
+struct Witness { Scalar x, s; std::vector<uint32_t> digits; };
+
+// reciprocal.rs:64-84, for arbitrary (dim_nd, dim_np); make_circuit (:150-214) is built inside the engine from the challenge
+struct ReciprocalRangeProofProtocol {
+    size_t dim_nd = 0, dim_np = 0;
+    Point g; std::vector<Point> g_vec, h_vec, g_vec_, h_vec_;
+    int device = 0;
+
+    // reciprocal.rs:88-90
+    CompressedPoint commit_value(const Scalar &x, const Scalar &s) const {
+        if (h_vec.empty()) throw Panic(BPPP_ST_BAD_ARG, "index out of bounds: h_vec is empty");
+        CompressedPoint out;
+        check(bppp_reciprocal_commit_value(device, g.data(), h_vec[0].data(), x.data(), s.data(), out.data()), "bppp_reciprocal_commit_value");
+        return out;
+    }
+    // reciprocal.rs:110-146 with a fresh Transcript::new(label); rng = (1 + 18 + (dim_nd + 1) + dim_nd) x 64 bytes in draw order
+    GenericProof prove(const Witness &w, const std::string &label, const std::vector<uint8_t> &rng, CompressedPoint *commitment_out = nullptr) const {
+        GenericProof pr;
+        pr.record.resize(33 * (4 + 2 * 64) + 32 * (2 * (dim_nd + dim_np) + 64));
+        CompressedPoint com; int32_t st = 0;
+        check(bppp_reciprocal_prove(device, dim_nd, dim_np, g.data(), pts_ptr(g_vec), g_vec.size(), pts_ptr(h_vec), h_vec.size(), pts_ptr(g_vec_), g_vec_.size(),
+                                    pts_ptr(h_vec_), h_vec_.size(), w.x.data(), w.s.data(), w.digits.data(), rng.data(), rng.size(),
+                                    (const uint8_t *)label.data(), label.size(), pr.record.data(), pr.record.size(), &pr.rounds, &pr.l_len, &pr.n_len, com.data(), &st),
+              "bppp_reciprocal_prove");
+        if (st != BPPP_ST_TRUE) throw Panic(st, "reciprocal prove: the reference would panic");
+        pr.record.resize(33 * (4 + 2 * pr.rounds) + 32 * (pr.l_len + pr.n_len) + 33);      // ... | l | n | r (the pole commitment, a point)
+        if (commitment_out) *commitment_out = com;
+        return pr;
+    }
+    // reciprocal.rs:98-107
+    bool verify(const CompressedPoint &commitment, const GenericProof &pr, const std::string &label) const {
+        int32_t verdict = 0;
+        check(bppp_reciprocal_verify(device, dim_nd, dim_np, g.data(), pts_ptr(g_vec), g_vec.size(), pts_ptr(h_vec), h_vec.size(), pts_ptr(g_vec_), g_vec_.size(),
+                                     pts_ptr(h_vec_), h_vec_.size(), commitment.data(), pr.record.data(), pr.rounds, pr.rounds, pr.l_len, pr.n_len,
+                                     (const uint8_t *)label.data(), label.size(), &verdict), "bppp_reciprocal_verify");
+        return verdict_to_bool(verdict, "reciprocal verify");
+    }
+};
+}  // namespace reciprocal
+}  // namespace range_proof
+
+namespace circuit {
+// circuit.rs:15-20: the partition closure tabulated (index into w_o, or -1 for None)
+struct Partition { std::vector<int32_t> lo, ll, lr, no; };
+// circuit.rs:78-93
+struct Witness { std::vector<Scalar> v, s_v, w_l, w_r, w_o; };     // v: k x dim_nv row-major
+
+// circuit.rs:95-139 with dense row-major W_m (dim_nm x dim_nw) and W_l (dim_nl x dim_nw), dim_nl = dim_nv k, dim_nw = 2 dim_nm + dim_no
+struct ArithmeticCircuit {
+    size_t dim_nm = 0, dim_no = 0, k = 0, dim_nv = 0;
+    bool f_l = false, f_m = false;
+    Point g; std::vector<Point> g_vec, h_vec, g_vec_, h_vec_;
+    std::vector<Scalar> W_m, W_l, a_m, a_l;
+    Partition partition;
+    int device = 0;
+
+    bppp_circuit_desc desc() const {
+        bppp_circuit_desc d{};
+        d.dim_nm = dim_nm; d.dim_no = dim_no; d.k = k; d.dim_nv = dim_nv; d.f_l = f_l; d.f_m = f_m;
+        d.g64 = g.data(); d.gvec64 = pts_ptr(g_vec); d.hvec64 = pts_ptr(h_vec); d.gvec2_64 = pts_ptr(g_vec_); d.hvec2_64 = pts_ptr(h_vec_);
+        d.gn = g_vec.size(); d.hn = h_vec.size(); d.gn2 = g_vec_.size(); d.hn2 = h_vec_.size();
+        d.W_m32 = sc_ptr(W_m); d.W_l32 = sc_ptr(W_l); d.a_m32 = sc_ptr(a_m); d.a_l32 = sc_ptr(a_l);
+        d.part_lo = partition.lo.data(); d.part_ll = partition.ll.data(); d.part_lr = partition.lr.data(); d.part_no = partition.no.data();
+        d.part_n = partition.lo.size();
+        return d;
+    }
+    // circuit.rs:146-151
+    CompressedPoint commit(const std::vector<Scalar> &v, const Scalar &s) const {
+        bppp_circuit_desc d = desc(); CompressedPoint out;
+        check(bppp_circuit_commit(device, &d, sc_ptr(v), s.data(), out.data()), "bppp_circuit_commit");
+        return out;
+    }
+    // circuit.rs:260-556 with a fresh Transcript::new(label); rng = (18 + dim_nv + dim_nm) x 64 bytes in draw order
+    GenericProof prove(const std::vector<CompressedPoint> &v_commitments, const Witness &w, const std::string &label, const std::vector<uint8_t> &rng) const {
+        bppp_circuit_desc d = desc();
+        GenericProof pr;
+        pr.record.resize(33 * (4 + 2 * 64) + 32 * (2 * (dim_nm + dim_nv + 9) + 64));
+        int32_t st = 0;
+        check(bppp_circuit_prove(device, &d, v_commitments.empty() ? nullptr : v_commitments[0].data(), sc_ptr(w.v), sc_ptr(w.s_v), sc_ptr(w.w_l), sc_ptr(w.w_r),
+                                 sc_ptr(w.w_o), rng.data(), rng.size(), (const uint8_t *)label.data(), label.size(), pr.record.data(), pr.record.size(), &pr.rounds,
+                                 &pr.l_len, &pr.n_len, &st), "bppp_circuit_prove");
+        if (st != BPPP_ST_TRUE) throw Panic(st, "circuit prove: the reference would panic");
+        pr.record.resize(33 * (4 + 2 * pr.rounds) + 32 * (pr.l_len + pr.n_len));
+        return pr;
+    }
+    // circuit.rs:154-256
+    bool verify(const std::vector<CompressedPoint> &v_commitments, const GenericProof &pr, const std::string &label) const {
+        bppp_circuit_desc d = desc(); int32_t verdict = 0;
+        check(bppp_circuit_verify(device, &d, v_commitments.empty() ? nullptr : v_commitments[0].data(), pr.record.data(), pr.rounds, pr.rounds, pr.l_len, pr.n_len,
+                                  (const uint8_t *)label.data(), label.size(), &verdict), "bppp_circuit_verify");
+        return verdict_to_bool(verdict, "circuit verify");
+    }
+};
+}  // namespace circuit
 
 namespace wnla {
 // wnla::Proof { r, x, l, n } with r / x in push order (innermost round first, wnla.rs:186-188)

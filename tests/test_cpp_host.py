@@ -52,3 +52,18 @@ def test_cpp_layer_matches_the_oracle(exe, ref, oracle, gens64):
     com = oracle.wnla_commit(gens64[:64], gens64[64:64 + 4 * 64], gens64[17 * 64:21 * 64], b"".join(map(sc, [1, 2, 4, 2])), sc(2), sc(4),
                              b"".join(map(sc, [2, 1, 4, 1])), b"".join(map(sc, [1, 4, 2, 2])))
     assert kv["wnla_commit"] == com.hex()
+    # ReciprocalRangeProofProtocol mirror at the u64 dimensions: the fast path's record (and so the oracle's) plus the blinded pole commitment r
+    assert kv["reciprocal_proof"] == proofs.hex() and kv["reciprocal_commit"] == kv["commit"] == kv["reciprocal_commit_value"]
+    assert kv["reciprocal_shape"] == "4,2,1" and kv["reciprocal_verify"] == "1"
+    # ArithmeticCircuit mirror: the reference's ac_works instance against the C oracle
+    N = ref.N
+    be = lambda v: (v % N).to_bytes(32, "big")  # noqa: E731
+    P = lambda k: gens64[64 * k:64 * (k + 1)]  # noqa: E731
+    g, g_vec, h_vec = P(0), [P(1 + k) for k in range(16)], [P(17 + k) for k in range(32)]
+    desc = oracle.make_circuit_desc(1, 2, 1, 2, True, False, g, g_vec[0], b"".join(h_vec[:11]), b"", b"".join(h_vec[11:16]),
+                                    b"".join(map(be, [0, 0, 1, 0])), b"".join(map(be, [0, 1, 0, 0, 0, N - 1, 1, 0])), be(0), be(-8) + be(-15),
+                                    [-1, -1], [0, 1], [-1, -1], [-1, -1])
+    ccom = oracle.circuit_commit(desc, be(3) + be(5), blind)
+    rec, rounds, ll, nl = oracle.circuit_prove(desc, ccom, be(3) + be(5), blind, be(3), be(5), be(15) + be(8), rng[:(18 + 2 + 1) * 64], b"circuit test")
+    assert kv["circuit_commit"] == ccom.hex() and kv["circuit_proof"] == rec.hex() and kv["circuit_shape"] == f"{rounds},{ll},{nl}"
+    assert kv["circuit_verify"] == "1" and kv["circuit_verify_tampered"] == "0"
