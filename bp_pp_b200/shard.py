@@ -56,10 +56,21 @@ class PeerGroup:
         handle = (C.c_uint8 * 64)()
         check(lib().bppp_peer_create(C.byref(self._h), C.c_int(device), C.c_int(self.world), C.c_int(self.rank), handle), "bppp_peer_create")
         if multi:
+            import torch
+            from ._lib import BpppError
             handles = [None] * self.world
             dist.all_gather_object(handles, bytes(handle))
-            check(lib().bppp_peer_connect(self._h, _in(b"".join(handles))), "bppp_peer_connect")
-            dist.barrier()                      # every mailbox is mapped everywhere before the first remote store
+            err = None
+            try:
+                check(lib().bppp_peer_connect(self._h, _in(b"".join(handles))), "bppp_peer_connect")
+            except BpppError as e:              # e.g. CUDA IPC not permitted between the ranks' containers
+                err = e
+            # every mailbox is mapped everywhere before the first remote store -- or every rank gives up together
+            ok = torch.tensor([0 if err else 1], device=torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu"))
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                self.close()
+                raise err or BpppError("bppp_peer_connect failed on another rank of the group")
 
     def msm_allsum(self, up, out_fmt: int = 0):
         """Sum over all ranks of each rank's resident block MSM (api.UploadedMsm): (encoded point, device ms from the first
