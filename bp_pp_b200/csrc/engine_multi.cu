@@ -17,12 +17,13 @@ using namespace bppp;
 // ---- caching device allocator (declared in engine_generic.cuh; this file calls the real cudaMalloc / cudaFree) ----
 namespace {
 struct DevCache {
-    std::mutex mu;
     std::multimap<size_t, void *> parked;          // size class -> block
-    std::map<void *, size_t> live;                 // block -> size class
     size_t parked_bytes = 0;
 };
+struct Live { int dev; size_t cls; };
+std::mutex g_cache_mu;                             // one lock: the calls are rare next to the kernels they feed
 DevCache g_cache[16];
+std::map<void *, Live> g_live;                     // block -> (device it was allocated on, size class)
 constexpr size_t CACHE_CAP = (size_t)24 << 30;     // parked bytes per device before blocks go back to CUDA
 // size classes: eight per octave (at most 12.5 % slack), 512-byte granularity at the bottom
 size_t size_class(size_t n) {
@@ -38,45 +39,59 @@ cudaError_t dev_malloc(void **out, size_t bytes) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    DevCache &c = g_cache[dev & 15];
     const size_t cls = size_class(bytes);
     {
-        std::lock_guard<std::mutex> lk(c.mu);
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        DevCache &c = g_cache[dev & 15];
         auto it = c.parked.find(cls);
         if (it != c.parked.end()) {
-            *out = it->second; c.live[*out] = cls; c.parked_bytes -= cls; c.parked.erase(it);
+            *out = it->second; g_live[*out] = Live{dev, cls}; c.parked_bytes -= cls; c.parked.erase(it);
             return cudaSuccess;
         }
     }
     e = cudaMalloc(out, cls);
     if (e == cudaErrorMemoryAllocation) { (void)cudaGetLastError(); dev_trim(dev); e = cudaMalloc(out, cls); }
-    if (e == cudaSuccess) { std::lock_guard<std::mutex> lk(c.mu); c.live[*out] = cls; }
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> lk(g_cache_mu); g_live[*out] = Live{dev, cls}; }
     return e;
 }
 cudaError_t dev_free(void *p) {
     if (!p) return cudaSuccess;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    DevCache &c = g_cache[dev & 15];
-    size_t cls = 0;
+    Live l{};
     {
-        std::lock_guard<std::mutex> lk(c.mu);
-        auto it = c.live.find(p);
-        if (it == c.live.end()) return cudaFree(p);          // not ours (allocated before the cache existed / by another unit)
-        cls = it->second; c.live.erase(it);
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto it = g_live.find(p);
+        if (it == g_live.end()) return cudaFree(p);          // not ours (allocated by a unit that calls CUDA directly)
+        l = it->second; g_live.erase(it);
     }
-    e = cudaDeviceSynchronize();                             // cudaFree's contract: nothing in flight still uses the block
-    std::lock_guard<std::mutex> lk(c.mu);
-    if (c.parked_bytes + cls > CACHE_CAP) return cudaFree(p);
-    c.parked.emplace(cls, p); c.parked_bytes += cls;
+    // cudaFree's contract: nothing in flight still uses the block.  The block belongs to the device it was allocated on,
+    // whatever device is current in the calling thread.
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != l.dev) cudaSetDevice(l.dev);
+    cudaError_t e = cudaDeviceSynchronize();
+    bool park;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        DevCache &c = g_cache[l.dev & 15];
+        park = c.parked_bytes + l.cls <= CACHE_CAP;
+        if (park) { c.parked.emplace(l.cls, p); c.parked_bytes += l.cls; }
+    }
+    if (!park) e = cudaFree(p);
+    if (cur != l.dev) cudaSetDevice(cur);
     return e;
 }
 void dev_trim(int device) {
-    DevCache &c = g_cache[device & 15];
-    std::lock_guard<std::mutex> lk(c.mu);
-    for (auto &kv : c.parked) cudaFree(kv.second);
-    c.parked.clear(); c.parked_bytes = 0;
+    std::multimap<size_t, void *> blocks;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        DevCache &c = g_cache[device & 15];
+        blocks.swap(c.parked); c.parked_bytes = 0;
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != device) cudaSetDevice(device);
+    for (auto &kv : blocks) cudaFree(kv.second);
+    if (cur != device) cudaSetDevice(cur);
 }
 }  // namespace bppp
 

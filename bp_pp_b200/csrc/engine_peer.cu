@@ -100,6 +100,7 @@ __global__ void k_peer_gather(const uint32_t *mine, int world, uint32_t epoch, i
     }
 }
 
+extern "C" void bppp_peer_destroy(bppp_peer *p);
 extern "C" int bppp_peer_create(bppp_peer **out, int device, int world, int rank, uint8_t *ipc_handle64_out) {
     if (!out || !ipc_handle64_out || world < 1 || world > PEER_MAX || rank < 0 || rank >= world) return fail(BPPP_ERR_ARG, "bad peer group arguments");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
@@ -111,7 +112,7 @@ extern "C" int bppp_peer_create(bppp_peer **out, int device, int world, int rank
     bppp_peer *p = new bppp_peer();
     p->device = device; p->world = world; p->rank = rank;
     const size_t bytes = (size_t)2 * world * SLOT_WORDS * sizeof(uint32_t);
-    auto bail = [&](int rc) { cudaFree(p->mine); cudaFree(p->d_part); cudaFree(p->d_out); cudaFree(p->d_err); delete p; return rc; };
+    auto bail = [&](int rc) { bppp_peer_destroy(p); return rc; };        // frees whatever was created so far
 #define PEER_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { (void)cudaGetLastError(); \
         return bail(fail(_e == cudaErrorMemoryAllocation ? BPPP_ERR_NOMEM : BPPP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e))); } } while (0)
     PEER_OK(cudaMalloc(&p->mine, bytes));
