@@ -368,6 +368,21 @@ __global__ void __launch_bounds__(64) k_pt_sum_groups(const uint32_t *in, size_t
     }
     st_pt30(out + PT_W * g, acc);
 }
+// out[w] = sum of the per-chunk results of window w (in[w * per + j], j < per): one block per window, a strided partial sum per
+// thread and a shared-memory tree -- one launch instead of log16(per) rounds of k_pt_sum_groups (three launches of latency at c = 16)
+__global__ void __launch_bounds__(256) k_msm_window_sums(const uint32_t *in, uint32_t per, uint32_t *out) {
+    __shared__ uint32_t sh[256 * PT_W];
+    const uint32_t w = blockIdx.x;
+    Pt acc = pt_identity();
+    for (uint32_t j = threadIdx.x; j < per; j += 256) acc = pt_add(acc, ld_pt30(in + PT_W * ((size_t)w * per + j)));
+    st_pt30(sh + PT_W * threadIdx.x, acc);
+    __syncthreads();
+    for (int s = 128; s >= 1; s >>= 1) {
+        if ((int)threadIdx.x < s) st_pt30(sh + PT_W * threadIdx.x, pt_add(ld_pt30(sh + PT_W * threadIdx.x), ld_pt30(sh + PT_W * (threadIdx.x + s))));
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_pt30(out + PT_W * (size_t)w, ld_pt30(sh));
+}
 // result = sum_w 2^(c w) W_w, optionally + *addend
 __global__ void k_msm_horner(const uint32_t *win, int c, int nwin, const uint32_t *addend, uint32_t *out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -487,7 +502,7 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     size_t o_digits = cv.take(2 * total), o_vals = cv.take(4 * total), o_counts = cv.take(4 * ncount), o_scan = cv.take(4 * (ncount + 1));
     size_t o_bsum = cv.take(4 * (nscanblk + 1)), o_buckets = cv.take((size_t)PT_BYTES * nb), o_head = cv.take(128 * nslices), o_tail = cv.take(128 * nslices);
     size_t o_sq = cv.take(256 + 4 * (size_t)sq.cap), o_chunks = cv.take((size_t)PT_BYTES * nwin * nchunks);
-    size_t o_tmp = cv.take((size_t)PT_BYTES * ((size_t)nwin * nchunks / 16 + 2)), o_bx = cv.take(32 * n);
+    size_t o_tmp = cv.take((size_t)PT_BYTES * ((size_t)nwin + 2)), o_bx = cv.take(32 * n);       // tmp: one point per window
     std::lock_guard<std::mutex> slab_lock(g_slab_mu[dev_for_lock & 15]);     // released after the final synchronise below
     uint8_t *slab = nullptr;
     int rc = scratch_reserve(cv.total, &slab);
@@ -519,15 +534,9 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     GL(k_msm_fixup, nblocks(nb, 64), 64, sv, head, tail, buckets, sq);
     GL(k_msm_fixup_wide, std::min<uint32_t>(sq.cap, (uint32_t)sms * 4), 128, sv, head, tail, buckets, sq);
     GL(k_msm_chunks, nblocks((size_t)nwin * nchunks, 64), 64, buckets, nwin, half, CH, nchunks, chunks);
-    // per-window sum of chunk results: groups of 16 until nwin points remain
-    uint32_t *in = chunks, *out = tmp;
-    size_t per = nchunks;
-    while (per > 1) {
-        uint32_t group = per >= 16 ? 16u : (uint32_t)per;
-        size_t nout = (size_t)nwin * (per / group);
-        GL(k_pt_sum_groups, nblocks(nout, 64), 64, in, (size_t)nwin * per, group, out, nout);
-        std::swap(in, out); per /= group;
-    }
+    // per-window sum of the chunk results
+    uint32_t *in = chunks;
+    if (nchunks > 1) { GL(k_msm_window_sums, (unsigned)nwin, 256, chunks, nchunks, tmp); in = tmp; }
     GL(k_msm_horner, 1, 1, in, c, nwin, d_addend30, d_out30);
     CUDA_OK(cudaStreamSynchronize(st));
     CUDA_OK(cudaGetLastError());
