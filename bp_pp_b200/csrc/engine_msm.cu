@@ -241,8 +241,9 @@ __global__ void __launch_bounds__(256) k_scan_add(uint32_t *out, size_t count, c
 // same number of additions (one thread per bucket wasted ~25 % of every warp on the largest of its 32 Poisson-sized buckets).
 // A run of entries of one bucket that covers the whole bucket is written to the bucket; a run cut by a slice boundary goes
 // to the slice's head slot (first run) or tail slot (last run) as an XYZZ point, and k_msm_fixup adds the pieces.
-static constexpr uint32_t MSM_SL = 64;
-struct SortedView { const uint32_t *scan; uint32_t nch, nb; };       // start of bucket b = scan[b * nch]; scan[nb * nch] = entries
+// Slice length: 64 when the input alone gives every SM enough slices; shorter for small inputs, which would otherwise be a few
+// thousand threads each walking 64 dependent additions (2^16 points: 407 us of pure latency).
+struct SortedView { const uint32_t *scan; uint32_t nch, nb, sl; };   // start of bucket b = scan[b * nch]; scan[nb * nch] = entries; sl = slice length
 __device__ __forceinline__ uint32_t sv_start(const SortedView &v, uint32_t b) { return v.scan[(size_t)b * v.nch]; }
 __device__ __forceinline__ void st_ptx32(uint32_t *p, const PtX &a) {
 #pragma unroll
@@ -258,6 +259,7 @@ __device__ __forceinline__ Pt ld_ptx32_as_pt(const uint32_t *p) {
 __global__ void __launch_bounds__(64, 7) k_msm_slices(const uint32_t *pts, const uint32_t *bx, const uint32_t *vals, SortedView sv, uint32_t *buckets, uint32_t *head, uint32_t *tail) {
     const uint32_t total = sv_start(sv, sv.nb);
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t MSM_SL = sv.sl;
     if (t * MSM_SL >= total) return;
     const uint32_t s = (uint32_t)(t * MSM_SL), e = s + MSM_SL < total ? s + MSM_SL : total;
     // bucket of entry s: the last b with start[b] <= s (empty buckets share a start with their successor: take the last)
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(64, 7) k_msm_slices(const uint32_t *pts, const
 // buckets cut by slice boundaries: sum of their pieces (slot of bucket B in slice t: head when B began at or before the slice's
 // first entry, else tail); empty buckets become the identity; buckets spanning more than 32 slices go to the block kernel
 struct SpanQueue { uint32_t *count; uint32_t *bucket; uint32_t cap; };
-__device__ __forceinline__ const uint32_t *slice_piece(const uint32_t *head, const uint32_t *tail, uint32_t S, uint32_t t) {
+__device__ __forceinline__ const uint32_t *slice_piece(const uint32_t *head, const uint32_t *tail, uint32_t S, uint32_t t, uint32_t MSM_SL) {
     return (S <= t * MSM_SL ? head : tail) + 32 * (size_t)t;
 }
 __global__ void __launch_bounds__(64) k_msm_fixup(SortedView sv, const uint32_t *head, const uint32_t *tail, uint32_t *buckets, SpanQueue sq) {
@@ -300,12 +302,13 @@ __global__ void __launch_bounds__(64) k_msm_fixup(SortedView sv, const uint32_t 
     if (B >= sv.nb) return;
     const uint32_t S = sv_start(sv, (uint32_t)B), E = sv_start(sv, (uint32_t)B + 1);
     if (S == E) { st_pt30(buckets + PT_W * B, pt_identity()); return; }
+    const uint32_t MSM_SL = sv.sl;
     const uint32_t t0 = S / MSM_SL, t1 = (E - 1) / MSM_SL;
     if (t0 == t1) return;                                   // whole bucket inside one slice: k_msm_slices wrote it
     if (t1 - t0 >= 32) { uint32_t slot = atomicAdd(sq.count, 1u); if (slot < sq.cap) { sq.bucket[slot] = (uint32_t)B; return; } }
-    Pt acc = ld_ptx32_as_pt(slice_piece(head, tail, S, t0));
+    Pt acc = ld_ptx32_as_pt(slice_piece(head, tail, S, t0, MSM_SL));
 #pragma unroll 1
-    for (uint32_t t = t0 + 1; t <= t1; t++) acc = pt_add(acc, ld_ptx32_as_pt(slice_piece(head, tail, S, t)));
+    for (uint32_t t = t0 + 1; t <= t1; t++) acc = pt_add(acc, ld_ptx32_as_pt(slice_piece(head, tail, S, t, MSM_SL)));
     st_pt30(buckets + PT_W * B, acc);
 }
 __global__ void __launch_bounds__(128) k_msm_fixup_wide(SortedView sv, const uint32_t *head, const uint32_t *tail, uint32_t *buckets, SpanQueue sq) {
@@ -315,9 +318,10 @@ __global__ void __launch_bounds__(128) k_msm_fixup_wide(SortedView sv, const uin
     // possible entry cost 0.23 ms of empty launches at 2^21 points
     for (uint32_t q = blockIdx.x; q < cnt; q += gridDim.x) {
         const uint32_t B = sq.bucket[q];
+        const uint32_t MSM_SL = sv.sl;
         const uint32_t S = sv_start(sv, B), E = sv_start(sv, B + 1), t0 = S / MSM_SL, t1 = (E - 1) / MSM_SL;
         Pt acc = pt_identity();
-        for (uint32_t t = t0 + threadIdx.x; t <= t1; t += 128) acc = pt_add(acc, ld_ptx32_as_pt(slice_piece(head, tail, S, t)));
+        for (uint32_t t = t0 + threadIdx.x; t <= t1; t += 128) acc = pt_add(acc, ld_ptx32_as_pt(slice_piece(head, tail, S, t, MSM_SL)));
         st_pt30(sh + PT_W * threadIdx.x, acc);
         __syncthreads();
         for (int s = 64; s >= 1; s >>= 1) {
@@ -495,6 +499,8 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     uint32_t nch = (uint32_t)(sms / nwin); if (nch < 1) nch = 1;      // sort blocks: nch chunks x nwin windows ~ one per SM
     while (nch > 1 && n2 / nch < 4096) nch /= 2;
     const size_t ncount = (size_t)nb * nch, nscanblk = (ncount + 2047) / 2048;
+    // measured on a B200 (2^12 .. 2^20 points): 16-entry slices win below ~0.5 M sorted entries, 32 up to ~8 M, 64 beyond
+    const uint32_t MSM_SL = total < (512u << 10) ? 16u : (total < (8u << 20) ? 32u : 64u);
     const size_t nslices = (total + MSM_SL - 1) / MSM_SL;
     SpanQueue sq; sq.cap = (uint32_t)(total / (32 * MSM_SL) + 2);
     // one cached slab per device, carved into the working arrays (cudaMalloc per call cost more than the kernels)
@@ -529,10 +535,10 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     if (nrange > half) nrange = half;
     const uint32_t span = (half + nrange - 1) / nrange;
     k_msm_scatter<<<dim3((half + span - 1) / span, (unsigned)nwin), 1024, 4 * (size_t)span, st>>>(digits, n2, half, span, nch, scan, vals); g_generic_launches++;
-    SortedView sv; sv.scan = scan; sv.nch = nch; sv.nb = nb;
+    SortedView sv; sv.scan = scan; sv.nch = nch; sv.nb = nb; sv.sl = MSM_SL;
     GL(k_msm_slices, nblocks(nslices, 64), 64, d_pts, bx, vals, sv, buckets, head, tail);
     GL(k_msm_fixup, nblocks(nb, 64), 64, sv, head, tail, buckets, sq);
-    GL(k_msm_fixup_wide, std::min<uint32_t>(sq.cap, (uint32_t)sms * 4), 128, sv, head, tail, buckets, sq);
+    GL(k_msm_fixup_wide, std::min<uint32_t>(sq.cap, 32u), 128, sv, head, tail, buckets, sq);      // the queue is almost always empty
     GL(k_msm_chunks, nblocks((size_t)nwin * nchunks, 64), 64, buckets, nwin, half, CH, nchunks, chunks);
     // per-window sum of the chunk results
     uint32_t *in = chunks;
