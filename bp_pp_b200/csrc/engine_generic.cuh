@@ -50,6 +50,12 @@ uint64_t wnla_launch_count();
 cudaError_t dev_malloc(void **p, size_t bytes);
 cudaError_t dev_free(void *p);
 void dev_trim(int device);            // return every parked block of the device to CUDA
+// frees the registered device pointers when the scope ends, whatever path leaves it (CUDA_OK returns early on errors)
+struct DevScope {
+    std::vector<void **> slots;
+    template <typename T> void own(T **p) { slots.push_back(reinterpret_cast<void **>(p)); }
+    ~DevScope() { for (void **p : slots) { if (*p) dev_free(*p); *p = nullptr; } }
+};
 
 }  // namespace bppp
 

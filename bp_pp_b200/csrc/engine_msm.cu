@@ -472,6 +472,7 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     }
     if (n <= 1024) {
         uint32_t *a = nullptr, *b = nullptr, *res = nullptr;
+        DevScope scope; scope.own(&a); scope.own(&b);
         CUDA_OK(cudaMalloc(&a, PT_BYTES * (n + 1)));
         CUDA_OK(cudaMalloc(&b, PT_BYTES * (n / 16 + 2)));
         GL(k_msm_small, nblocks(n, 64), 64, d_pts, d_sc, n, a);
@@ -480,7 +481,6 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
         tree_sum(st, a, b, count, &res);
         CUDA_OK(cudaMemcpyAsync(d_out30, res, PT_BYTES, cudaMemcpyDeviceToDevice, st));
         CUDA_OK(cudaStreamSynchronize(st));
-        cudaFree(a); cudaFree(b);
         CUDA_OK(cudaGetLastError());
         return BPPP_OK;
     }

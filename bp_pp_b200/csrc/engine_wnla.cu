@@ -276,6 +276,7 @@ int wnla_load(cudaStream_t st, WnlaDev &w, const uint8_t *g64, const uint8_t *gv
 int wnla_commit_dev(cudaStream_t st, const WnlaDev &w, const uint32_t *d_l, const uint32_t *d_n, uint32_t *d_out30) {
     size_t L = std::max(w.Lh, w.Lg), nblk = (L + 127) / 128;
     uint32_t *d_part = nullptr, *d_sc = nullptr;
+    DevScope scope; scope.own(&d_part); scope.own(&d_sc);
     CUDA_OK(cudaMalloc(&d_part, 64 * (nblk ? nblk : 1)));
     CUDA_OK(cudaMalloc(&d_sc, 32 * (w.Lh + w.Lg + 1)));
     if (nblk) WL(k_commit_dots, (unsigned)nblk, 128, w.c, d_l, w.Lh, d_n, w.Lg, to_param(w.mu), d_part, (size_t)0);
@@ -287,9 +288,7 @@ int wnla_commit_dev(cudaStream_t st, const WnlaDev &w, const uint32_t *d_l, cons
     CUDA_OK(cudaMemcpyAsync(d_sc + 8 * w.Lh, d_n, 32 * w.Lg, cudaMemcpyDeviceToDevice, st));
     if (w.scaled && w.Lg) WL(k_sc_scale, nblocks(w.Lg, 128), 128, d_sc + 8 * w.Lh, w.Lg, to_param(w.sigma));
     CUDA_OK(cudaMemcpyAsync(d_sc + 8 * (w.Lh + w.Lg), v.v, 32, cudaMemcpyHostToDevice, st));
-    rc = msm_device(st, w.pts, d_sc, w.Lh + w.Lg + 1, nullptr, d_out30);
-    cudaFree(d_part); cudaFree(d_sc);
-    return rc;
+    return msm_device(st, w.pts, d_sc, w.Lh + w.Lg + 1, nullptr, d_out30);
 }
 
 
@@ -422,6 +421,10 @@ int wnla_verify_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, c
     const int R = (int)xn;
     int rc = BPPP_OK;
     uint32_t *d_xr = nullptr, *d_x30 = nullptr, *d_r30 = nullptr, *d_l = nullptr, *d_n = nullptr, *d_ys = nullptr, *d_rhos = nullptr;
+    uint32_t *d_sc = nullptr, *d_cl = nullptr, *d_part = nullptr, *d_f30 = nullptr;
+    DevScope scope;                                             // every return path below releases what was allocated so far
+    scope.own(&d_xr); scope.own(&d_x30); scope.own(&d_r30); scope.own(&d_l); scope.own(&d_n); scope.own(&d_ys); scope.own(&d_rhos);
+    scope.own(&d_sc); scope.own(&d_cl); scope.own(&d_part); scope.own(&d_f30);
     // decode proof points (a malformed encoding is a deserialisation failure in the reference)
     std::vector<uint8_t> both(33 * 2 * (size_t)(R ? R : 1));
     memcpy(both.data(), x33, 33 * (size_t)R); memcpy(both.data() + 33 * (size_t)R, r33, 33 * (size_t)R);
@@ -431,7 +434,7 @@ int wnla_verify_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, c
     if (rc != BPPP_OK) return rc;
     rc = decode_scalars_to_device(st, l32, ln, &d_l);
     if (rc == BPPP_OK) rc = decode_scalars_to_device(st, n32, nn, &d_n);
-    if (rc != BPPP_OK) { cudaFree(d_xr); cudaFree(d_l); if (rc != BPPP_ERR_ENCODING) return rc; *verdict = ST_BAD_SCALAR; return BPPP_OK; }
+    if (rc != BPPP_OK) { if (rc != BPPP_ERR_ENCODING) return rc; *verdict = ST_BAD_SCALAR; return BPPP_OK; }
     CUDA_OK(cudaMalloc(&d_x30, PT_BYTES)); CUDA_OK(cudaMalloc(&d_r30, PT_BYTES));
     std::vector<Sc> ys(R), rhos(R);
     Sc rho = w.rho, mu = w.mu;
@@ -458,7 +461,6 @@ int wnla_verify_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, c
     if (rc == BPPP_OK && *verdict == ST_TRUE) {
         // base case: commitment == commit(l, n) over the folded generators == one MSM over the original ones
         size_t Lh = w.Lh, Lg = w.Lg, Lt = Lh + Lg + 1;
-        uint32_t *d_sc = nullptr, *d_cl = nullptr, *d_part = nullptr, *d_f30 = nullptr;
         CUDA_OK(cudaMalloc(&d_sc, 32 * Lt)); CUDA_OK(cudaMalloc(&d_cl, 32 * (Lh ? Lh : 1)));
         CUDA_OK(cudaMalloc(&d_ys, 32 * (size_t)(R ? R : 1))); CUDA_OK(cudaMalloc(&d_rhos, 32 * (size_t)(R ? R : 1)));
         CUDA_OK(cudaMalloc(&d_f30, PT_BYTES));
@@ -484,9 +486,7 @@ int wnla_verify_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, c
             if (rc == BPPP_OK) rc = encode_points_from_device(st, d_f30, 1, FMT_COMPRESSED, b);
             if (rc == BPPP_OK) *verdict = memcmp(a, b, 33) == 0 ? ST_TRUE : ST_FALSE;     // ProjectivePoint::eq (wnla.rs:81)
         }
-        cudaFree(d_sc); cudaFree(d_cl); cudaFree(d_part); cudaFree(d_f30);
     }
-    cudaFree(d_xr); cudaFree(d_x30); cudaFree(d_r30); cudaFree(d_l); cudaFree(d_n); cudaFree(d_ys); cudaFree(d_rhos);
     return rc;
 }
 
