@@ -459,6 +459,12 @@ int msm_choose_window(size_t n) {
     int c = lg - 3;
     if (c < 4) c = 4;
     if (c > 16) c = 16;
+    // Measured on a B200 (2^12 .. 2^21 points, widths 10..16): 16 wins from 2^19 points up, 13 below (down to 2^12 points).  The top window of the
+    // 129-bit signed GLV halves decides: at c = 16 it holds only the carry, at c = 13 twelve real bits (thousands of buckets), while
+    // c = 14 / 15 leave it 2 / 8 bits -- a whole window's entries in a handful of buckets, which serialises the shared-memory
+    // cursors of the counting sort.
+    if (c >= 10) c = n >= ((size_t)1 << 20) ? 16 : 13;      // n counts the GLV halves: 2^19 points and up take 16
+    if (const char *e = getenv("BPPP_MSM_C")) { int v = atoi(e); if (v >= 4 && v <= 16) c = v; }       // experiments
     return c;
 }
 
