@@ -311,25 +311,38 @@ __global__ void __launch_bounds__(64) k_msm_fixup(SortedView sv, const uint32_t 
     for (uint32_t t = t0 + 1; t <= t1; t++) acc = pt_add(acc, ld_ptx32_as_pt(slice_piece(head, tail, S, t, MSM_SL)));
     st_pt30(buckets + PT_W * B, acc);
 }
-__global__ void __launch_bounds__(128) k_msm_fixup_wide(SortedView sv, const uint32_t *head, const uint32_t *tail, uint32_t *buckets, SpanQueue sq) {
+// A bucket spanning 32 slices or more (skewed scalars -- and, at 16-bit windows, the carry bucket of the top window, which
+// holds half of all entries): WIDE_SPLIT blocks each sum an interleaved share of its pieces into `part`, k_msm_fixup_wide_sum
+// adds the shares.  A fixed, small grid strides over the queue (it is short: one block per possible entry cost 0.23 ms of
+// empty launches at 2^21 points).
+static constexpr uint32_t WIDE_SPLIT = 8;
+__global__ void __launch_bounds__(128) k_msm_fixup_wide(SortedView sv, const uint32_t *head, const uint32_t *tail, uint32_t *part, SpanQueue sq) {
     __shared__ uint32_t sh[128 * PT_W];
     uint32_t cnt = *sq.count; if (cnt > sq.cap) cnt = sq.cap;
-    // a fixed, small grid strides over the queue: it is almost always empty (only skewed scalars fill it), and one block per
-    // possible entry cost 0.23 ms of empty launches at 2^21 points
+    const uint32_t split = blockIdx.y;
     for (uint32_t q = blockIdx.x; q < cnt; q += gridDim.x) {
         const uint32_t B = sq.bucket[q];
         const uint32_t MSM_SL = sv.sl;
         const uint32_t S = sv_start(sv, B), E = sv_start(sv, B + 1), t0 = S / MSM_SL, t1 = (E - 1) / MSM_SL;
         Pt acc = pt_identity();
-        for (uint32_t t = t0 + threadIdx.x; t <= t1; t += 128) acc = pt_add(acc, ld_ptx32_as_pt(slice_piece(head, tail, S, t, MSM_SL)));
+        for (uint32_t t = t0 + split * 128 + threadIdx.x; t <= t1; t += 128 * WIDE_SPLIT) acc = pt_add(acc, ld_ptx32_as_pt(slice_piece(head, tail, S, t, MSM_SL)));
         st_pt30(sh + PT_W * threadIdx.x, acc);
         __syncthreads();
         for (int s = 64; s >= 1; s >>= 1) {
             if ((int)threadIdx.x < s) st_pt30(sh + PT_W * threadIdx.x, pt_add(ld_pt30(sh + PT_W * threadIdx.x), ld_pt30(sh + PT_W * (threadIdx.x + s))));
             __syncthreads();
         }
-        if (threadIdx.x == 0) st_pt30(buckets + PT_W * (size_t)B, ld_pt30(sh));
+        if (threadIdx.x == 0) st_pt30(part + PT_W * ((size_t)q * WIDE_SPLIT + split), ld_pt30(sh));
         __syncthreads();
+    }
+}
+__global__ void k_msm_fixup_wide_sum(const uint32_t *part, uint32_t *buckets, SpanQueue sq) {
+    uint32_t cnt = *sq.count; if (cnt > sq.cap) cnt = sq.cap;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) {
+        Pt acc = ld_pt30(part + PT_W * (size_t)q * WIDE_SPLIT);
+#pragma unroll 1
+        for (uint32_t s = 1; s < WIDE_SPLIT; s++) acc = pt_add(acc, ld_pt30(part + PT_W * ((size_t)q * WIDE_SPLIT + s)));
+        st_pt30(buckets + PT_W * (size_t)sq.bucket[q], acc);
     }
 }
 __global__ void k_pt_fill_identity(uint32_t *pts30, size_t n) {
@@ -515,6 +528,7 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     size_t o_bsum = cv.take(4 * (nscanblk + 1)), o_buckets = cv.take((size_t)PT_BYTES * nb), o_head = cv.take(128 * nslices), o_tail = cv.take(128 * nslices);
     size_t o_sq = cv.take(256 + 4 * (size_t)sq.cap), o_chunks = cv.take((size_t)PT_BYTES * nwin * nchunks);
     size_t o_tmp = cv.take((size_t)PT_BYTES * ((size_t)nwin + 2)), o_bx = cv.take(32 * n);       // tmp: one point per window
+    size_t o_wide = cv.take((size_t)PT_BYTES * WIDE_SPLIT * sq.cap);
     std::lock_guard<std::mutex> slab_lock(g_slab_mu[dev_for_lock & 15]);     // released after the final synchronise below
     uint8_t *slab = nullptr;
     int rc = scratch_reserve(cv.total, &slab);
@@ -522,7 +536,7 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     uint16_t *digits = (uint16_t *)(slab + o_digits);
     uint32_t *vals = (uint32_t *)(slab + o_vals), *counts = (uint32_t *)(slab + o_counts), *scan = (uint32_t *)(slab + o_scan), *bsum = (uint32_t *)(slab + o_bsum);
     uint32_t *buckets = (uint32_t *)(slab + o_buckets), *head = (uint32_t *)(slab + o_head), *tail = (uint32_t *)(slab + o_tail);
-    uint32_t *chunks = (uint32_t *)(slab + o_chunks), *tmp = (uint32_t *)(slab + o_tmp), *bx = (uint32_t *)(slab + o_bx);
+    uint32_t *chunks = (uint32_t *)(slab + o_chunks), *tmp = (uint32_t *)(slab + o_tmp), *bx = (uint32_t *)(slab + o_bx), *wide = (uint32_t *)(slab + o_wide);
     sq.count = (uint32_t *)(slab + o_sq); sq.bucket = sq.count + 64;
     static bool smem_set[16] = {};
     if (!smem_set[dev_for_lock & 15]) {
@@ -544,7 +558,8 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     SortedView sv; sv.scan = scan; sv.nch = nch; sv.nb = nb; sv.sl = MSM_SL;
     GL(k_msm_slices, nblocks(nslices, 64), 64, d_pts, bx, vals, sv, buckets, head, tail);
     GL(k_msm_fixup, nblocks(nb, 64), 64, sv, head, tail, buckets, sq);
-    GL(k_msm_fixup_wide, std::min<uint32_t>(sq.cap, 32u), 128, sv, head, tail, buckets, sq);      // the queue is almost always empty
+    GL(k_msm_fixup_wide, dim3(std::min<uint32_t>(sq.cap, 32u), WIDE_SPLIT), 128, sv, head, tail, wide, sq);
+    GL(k_msm_fixup_wide_sum, 8, 32, wide, buckets, sq);
     GL(k_msm_chunks, nblocks((size_t)nwin * nchunks, 64), 64, buckets, nwin, half, CH, nchunks, chunks);
     // per-window sum of the chunk results
     uint32_t *in = chunks;
