@@ -13,8 +13,6 @@ namespace bppp {
 int msm_choose_window(size_t n);
 static constexpr size_t PT_BYTES = PT_W * sizeof(uint32_t);
 int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, size_t n, const uint32_t *d_addend30, uint32_t *d_out30);
-// K <= 2 sums over the same points in one Pippenger pass (a WNLA round's X and R): out[k] = sum_i sc[k][i] * P_i
-int msm_device_multi(cudaStream_t st, const uint32_t *d_pts, const uint32_t *const *d_scs, int K, size_t n, const uint32_t *d_addend30, uint32_t *const *d_outs);
 int decode_points_to_device(cudaStream_t st, const uint8_t *h_pts, int fmt, size_t n, uint32_t **d_words);
 int decode_scalars_to_device(cudaStream_t st, const uint8_t *h_sc, size_t n, uint32_t **d_words);
 int encode_points_from_device(cudaStream_t st, const uint32_t *d_pts30, size_t n, int fmt, uint8_t *h_out);

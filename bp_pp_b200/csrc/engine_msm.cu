@@ -481,20 +481,6 @@ int msm_choose_window(size_t n) {
     return c;
 }
 
-// K sums over the SAME points in one Pippenger pass: out[k] = sum_i sc[k][i] * P_i (+ *d_addend30 for k = 0 when given).  The K
-// scalar vectors share the sort, the bucket accumulation launch and the reduction -- window k * nwin + w belongs to sum k -- so a
-// WNLA round's X and R (src/wnla.rs:152-160) cost one chain of kernel launches instead of two (the rounds after the first few
-// are pure launch latency).  d_out30[k]: projective result (PT_W words, device).  Synchronises before returning.
-static constexpr int MSM_MAX_K = 2;
-static int msm_device_pippenger(cudaStream_t st, const uint32_t *d_pts, const uint32_t *const *d_scs, int K, size_t n, const uint32_t *d_addend30, uint32_t *const *d_outs);
-int msm_device_multi(cudaStream_t st, const uint32_t *d_pts, const uint32_t *const *d_scs, int K, size_t n, const uint32_t *d_addend30, uint32_t *const *d_outs) {
-    if (K < 1 || K > MSM_MAX_K) return fail(BPPP_ERR_ARG, "msm_device_multi: 1 or 2 scalar vectors");
-    if (n <= 1024) {                           // identity, a single ladder per point: nothing to share
-        for (int k = 0; k < K; k++) { int rc = msm_device(st, d_pts, d_scs[k], n, k == 0 ? d_addend30 : nullptr, d_outs[k]); if (rc != BPPP_OK) return rc; }
-        return BPPP_OK;
-    }
-    return msm_device_pippenger(st, d_pts, d_scs, K, n, d_addend30, d_outs);
-}
 // d_out30: projective result (PT_W words, device).  d_addend30 may be null.  Synchronises before returning.
 int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, size_t n, const uint32_t *d_addend30, uint32_t *d_out30) {
     if (n == 0) {
@@ -517,16 +503,9 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
         CUDA_OK(cudaGetLastError());
         return BPPP_OK;
     }
-    const uint32_t *scs[1] = {d_sc}; uint32_t *outs[1] = {d_out30};
-    return msm_device_pippenger(st, d_pts, scs, 1, n, d_addend30, outs);
-}
-
-// Pippenger proper (n > 1024): K scalar vectors over the same points
-static int msm_device_pippenger(cudaStream_t st, const uint32_t *d_pts, const uint32_t *const *d_scs, int K, size_t n, const uint32_t *d_addend30, uint32_t *const *d_outs) {
     const size_t n2 = 2 * n;                   // sorted entries per window: the two GLV halves of every scalar
     const int c = msm_choose_window(n2);
-    const int nwin1 = 128 / c + 1;             // 129 bits of signed digits per half
-    const int nwin = K * nwin1;                // windows of all K sums: window k * nwin1 + w belongs to sum k
+    const int nwin = 128 / c + 1;              // 129 bits of signed digits per half
     const uint32_t half = 1u << (c - 1);
     const uint32_t nb = (uint32_t)nwin * half;
     const size_t total = (size_t)nwin * n2;    // upper bound of the sorted entries (zero digits drop out)
@@ -566,7 +545,7 @@ static int msm_device_pippenger(cudaStream_t st, const uint32_t *d_pts, const ui
         smem_set[dev_for_lock & 15] = true;
     }
     CUDA_OK(cudaMemsetAsync(sq.count, 0, 4, st));
-    for (int k = 0; k < K; k++) GL(k_msm_digits, nblocks(n, 128), 128, d_scs[k], n, c, nwin1, digits + (size_t)k * nwin1 * n2);
+    GL(k_msm_digits, nblocks(n, 128), 128, d_sc, n, c, nwin, digits);
     GL(k_msm_endo_x, nblocks(n, 128), 128, d_pts, n, bx);
     k_msm_hist<<<dim3(nch, (unsigned)nwin), 1024, 4 * (size_t)half, st>>>(digits, n2, half, nch, counts); g_generic_launches++;
     GL(k_scan_blocks, (unsigned)nscanblk, 256, counts, ncount, scan, bsum);
@@ -585,7 +564,7 @@ static int msm_device_pippenger(cudaStream_t st, const uint32_t *d_pts, const ui
     // per-window sum of the chunk results
     uint32_t *in = chunks;
     if (nchunks > 1) { GL(k_msm_window_sums, (unsigned)nwin, 256, chunks, nchunks, tmp); in = tmp; }
-    for (int k = 0; k < K; k++) GL(k_msm_horner, 1, 1, in + (size_t)PT_W * k * nwin1, c, nwin1, k == 0 ? d_addend30 : nullptr, d_outs[k]);
+    GL(k_msm_horner, 1, 1, in, c, nwin, d_addend30, d_out30);
     CUDA_OK(cudaStreamSynchronize(st));
     CUDA_OK(cudaGetLastError());
     return BPPP_OK;

@@ -350,10 +350,8 @@ int wnla_prove_dev(cudaStream_t st, WnlaDev &w, Merlin &t, uint32_t *d_com30, ui
         CUDA_OK(cudaMemcpyAsync(d_sx + 8 * (Lh + Lg), vx.v, 32, cudaMemcpyHostToDevice, st));
         CUDA_OK(cudaMemcpyAsync(d_sr + 8 * (Lh + Lg), vr.v, 32, cudaMemcpyHostToDevice, st));
         CUDA_OK(cudaStreamSynchronize(st));                              // vx / vr live on this stack frame
-        {   // X and R over the same generators: one Pippenger pass (engine_msm.cu:msm_device_multi)
-            const uint32_t *scs[2] = {d_sx, d_sr}; uint32_t *outs[2] = {d_x30, d_r30};
-            rc = msm_device_multi(st, pts, scs, 2, Lt, nullptr, outs); if (rc != BPPP_OK) break;
-        }
+        rc = msm_device(st, pts, d_sx, Lt, nullptr, d_x30); if (rc != BPPP_OK) break;
+        rc = msm_device(st, pts, d_sr, Lt, nullptr, d_r30); if (rc != BPPP_OK) break;
         // transcript (wnla.rs:162-168)
         if (com_pending) { CUDA_OK(cudaStreamWaitEvent(st, ev_com, 0)); CUDA_OK(cudaMemcpyAsync(d_com30, d_com_next, PT_BYTES, cudaMemcpyDeviceToDevice, st)); com_pending = false; }
         CUDA_OK(cudaMemcpyAsync(d_three, d_com30, PT_BYTES, cudaMemcpyDeviceToDevice, st));
@@ -701,10 +699,8 @@ extern "C" int bppp_wnla_shard_xr_partial(bppp_wnla_shard *s, uint8_t *out128, f
     CUDA_OK(cudaMemcpyAsync(s->sx + 8 * (Lh + Lg), vx.v, 32, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(s->sr + 8 * (Lh + Lg), vr.v, 32, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaStreamSynchronize(st));
-    {
-        const uint32_t *scs[2] = {s->sx, s->sr}; uint32_t *outs[2] = {s->out30, s->out30 + PT_W};
-        rc = msm_device_multi(st, s->pts[k], scs, 2, Lt, nullptr, outs); if (rc != BPPP_OK) return rc;
-    }
+    rc = msm_device(st, s->pts[k], s->sx, Lt, nullptr, s->out30); if (rc != BPPP_OK) return rc;
+    rc = msm_device(st, s->pts[k], s->sr, Lt, nullptr, s->out30 + PT_W); if (rc != BPPP_OK) return rc;
     CUDA_OK(cudaEventRecord(s->e1, st));
     rc = encode_points_from_device(st, s->out30, 2, FMT_AFFINE64, out128); if (rc != BPPP_OK) return rc;
     if (device_ms) CUDA_OK(cudaEventElapsedTime(device_ms, s->e0, s->e1));
