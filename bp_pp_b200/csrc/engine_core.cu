@@ -230,6 +230,11 @@ static int alloc_work(bppp_ctx *c, size_t max_batch) {
     CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     if (const char *e = getenv("BPPP_NSUB")) { int v = atoi(e); if (v >= 1 && v <= bppp_ctx::MAX_SUB) c->nsub = v; }
     if (const char *e = getenv("BPPP_NSUB_HOST")) { int v = atoi(e); if (v >= 1 && v <= bppp_ctx::MAX_SUB) c->nsub_host = v; }
+    if (const char *e = getenv("BPPP_TAB_AFFINE")) c->tab_affine = atoi(e) != 0;
+    if (const char *e = getenv("BPPP_TAB_K")) {     // "k1,k2,k3": items per thread (= per inversion) of the three levels
+        int a = 0, b = 0, d = 0;
+        if (sscanf(e, "%d,%d,%d", &a, &b, &d) == 3 && a >= 1 && b >= 1 && d >= 1) { c->tab_k[0] = a; c->tab_k[1] = b; c->tab_k[2] = d; }
+    }
     if (const char *e = getenv("BPPP_MSM_LANES_RT")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16) c->msm_lanes_override = v; }
     if (const char *e = getenv("BPPP_VAR_LANES_RT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->var_lanes_override = v; }
     for (int k = 0; k < bppp_ctx::MAX_SUB; k++) {

@@ -57,6 +57,28 @@ __global__ void __launch_bounds__(64) k_v_verdict(WS w, int32_t *status) {
     status[i] = (int32_t)ws_ld(w, i, VL::STATUS);
 }
 
+// the same tables in affine coordinates, one launch per dependent level (u64_verify.cuh:tables_affine_level)
+__global__ void __launch_bounds__(128) k_v_tables_affine(WS w, int level, size_t nthreads) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nthreads) u64v_tables_affine_level(w, level, t, nthreads);
+}
+// Ladder tables of the 13 per-proof points: three affine levels (~60 M per point against 148 M for the projective build +
+// normalisation pass, kept behind BPPP_TAB_AFFINE=0), each level one cross-proof inversion per thread.
+static int launch_v_tables(bppp_ctx *c, cudaStream_t st, WS w) {
+    const size_t n = w.n;
+    if (c->tab_affine) {
+        for (int level = 1; level <= 3; level++) {
+            const size_t nthreads = tab_level_threads(c, n * VL::TAB_POINTS * (size_t)aff_level_nops(level), level);
+            LAUNCH(c, k_v_tables_affine, nblocks(nthreads, 128), 128, w, level, nthreads);
+        }
+    } else {
+        LAUNCH(c, k_v_tables_build, nblocks(n * VL::TAB_POINTS, 64), 64, w);
+        size_t items = n * VL::TAB_ENTRIES, nthreads = (items + 63) / 64;
+        LAUNCH(c, k_v_tables_normalize, nblocks(nthreads, 128), 128, w, nthreads);
+    }
+    return BPPP_OK;
+}
+
 // ---- verify ----
 static int verify_part(bppp_ctx *c, cudaStream_t st, WS w, const uint8_t *d_commits, const uint8_t *d_proofs, int fmt,
                        const Merlin &init, int32_t *d_status) {
@@ -69,11 +91,7 @@ static int verify_part(bppp_ctx *c, cudaStream_t st, WS w, const uint8_t *d_comm
     LAUNCH(c, k_v_load_finish, g64, 64, w, d_proofs, fmt, flags);
     launch_batch_inv(c, st, w, VL::VP + 2 * FE_W, VL::ZINV);
     LAUNCH(c, k_v_phase1, g64, 64, w, init, (const uint8_t *)nullptr, 0);
-    {   // affine 1P..8P tables of the 13 per-proof points: one batch inversion serves all 104 entries of every proof
-        LAUNCH(c, k_v_tables_build, nblocks(n * VL::TAB_POINTS, 64), 64, w);
-        size_t items = n * VL::TAB_ENTRIES, nthreads = (items + 63) / 64;
-        LAUNCH(c, k_v_tables_normalize, nblocks(nthreads, 128), 128, w, nthreads);
-    }
+    launch_v_tables(c, st, w);      // affine 1P..8P tables of the 13 per-proof points
     TermMap tm = identity_map();
     launch_msm_fixed(c, st, w, VL::FS, tm, 17, VL::ACC);      // pt = ps_tau g + <g_vec, pn_tau>  (circuit.rs:206)
     launch_v_var5(c, st, w);
@@ -194,9 +212,7 @@ extern "C" int bppp_u64_verify_circuit(bppp_ctx *c, const uint8_t *chal, uint8_t
     Merlin unused{};
     CUDA_OK(cudaMemcpyAsync(c->d_in_c, chal, 192 * n, cudaMemcpyHostToDevice, st));
     LAUNCH(c, k_v_phase1, nblocks(n, 64), 64, w, unused, (const uint8_t *)c->d_in_c, 192);
-    LAUNCH(c, k_v_tables_build, nblocks(n * VL::TAB_POINTS, 64), 64, w);
-    size_t items = n * VL::TAB_ENTRIES, nthreads = (items + 63) / 64;
-    LAUNCH(c, k_v_tables_normalize, nblocks(nthreads, 128), 128, w, nthreads);
+    launch_v_tables(c, st, w);
     TermMap tm = identity_map();
     launch_msm_fixed(c, st, w, VL::FS, tm, 17, VL::ACC);
     launch_v_var5(c, st, w);

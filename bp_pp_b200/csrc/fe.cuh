@@ -19,6 +19,7 @@
 // The internal representation is unobservable; only canonical bytes leave the device.
 #pragma once
 #include <stdint.h>
+#include "modinv.cuh"
 
 #if defined(__CUDACC__)
 #define BPPP_HD __host__ __device__ __forceinline__
@@ -596,8 +597,8 @@ BPPP_HD Fe fe_sqr_n(Fe a, int n) {
 #endif
 }
 
-// a^(p-2): 255 squarings + 15 multiplications.  fe_inv(0) = 0.
-BPPP_HD Fe fe_inv(const Fe &a) {
+// a^(p-2): 255 squarings + 15 multiplications.  fe_inv_fermat(0) = 0.  Kept as the cross-check of fe_inv (tests/hostemu).
+BPPP_HD Fe fe_inv_fermat(const Fe &a) {
     Fe x2 = fe_mul(fe_sqr(a), a);
     Fe x3 = fe_mul(fe_sqr(x2), a);
     Fe x6 = fe_mul(fe_sqr_n(x3, 3), x3);
@@ -614,6 +615,26 @@ BPPP_HD Fe fe_inv(const Fe &a) {
     t = fe_mul(fe_sqr_n(t, 3), x2);
     t = fe_mul(fe_sqr_n(t, 2), a);
     return t;
+}
+
+// a^-1 by safegcd division steps (modinv.cuh): ~14 k instructions against ~36 k for the power.  fe_inv(0) = 0.
+#if defined(__CUDACC__)
+static __device__ __noinline__ Fe fe_inv_gcd_call(Fe a) {
+    Fe c = fe_normalize(a), r;
+    mi_modinv_words<MIModP>(r.v, c.v);
+    return r;
+}
+#endif
+BPPP_HD Fe fe_inv(const Fe &a) {
+#if defined(BPPP_INV_FERMAT)
+    return fe_inv_fermat(a);
+#elif defined(__CUDA_ARCH__)
+    return fe_inv_gcd_call(a);          // one copy per translation unit: every caller is a cold, once-per-thread site
+#else
+    Fe c = fe_normalize(a), r;
+    mi_modinv_words<MIModP>(r.v, c.v);
+    return r;
+#endif
 }
 
 // candidate square root a^((p+1)/4); caller checks r^2 == a

@@ -296,6 +296,108 @@ BPPP_HD void tables_normalize_strided(const WS &w, const TabRegion &R, size_t t,
     }
 }
 BPPP_HD void u64v_tables_normalize_strided(const WS &w, size_t t, size_t T) { tables_normalize_strided(w, vtab_region(), t, T); }
+
+// ---- the same tables built directly in AFFINE coordinates, level by level ----
+// kP for k = 2..8 by affine additions / doublings whose denominators are inverted together ACROSS proofs (Montgomery's
+// trick over a thread's strided share of the (operation, point, proof) items of one level).  Per entry: 2 M + 1 S for the
+// chord formula (+ 1 S for a tangent), 3 M for its share of the inversion, 1 M for beta x -- against 8-12 M for the
+// complete projective formula plus 9 M to normalise the entry afterwards (T1 + T2/T3 above: 148 M per point, here ~60 M).
+// Three dependent levels: {2P}, {3P = 2P + P, 4P = 2 (2P)}, {5P = 4P + P, 6P = 2 (3P), 7P = 4P + 3P, 8P = 2 (4P)}.
+// The group has prime order, so for an on-curve P != O no denominator vanishes (x_a = x_b needs (a -+ b) P = O, y = 0 a
+// point of order two).  A vanishing denominator can therefore only come from bytes a failed decode left behind: it is kept
+// out of the thread's shared product (other proofs are unaffected) and yields the identity sentinel.
+struct AffOp { int a, b, out; };                                  // out P = a P + b P;  b == 0: out P = 2 (a P)
+BPPP_HD int aff_level_nops(int level) { return level == 1 ? 1 : level == 2 ? 2 : 4; }
+BPPP_HD AffOp aff_level_op(int level, int k) {
+    AffOp r;
+    if (level == 1) { r.a = 1; r.b = 0; r.out = 2; }
+    else if (level == 2) { r.a = 2; r.b = k == 0 ? 1 : 0; r.out = k == 0 ? 3 : 4; }
+    else if (k == 0) { r.a = 4; r.b = 1; r.out = 5; }
+    else if (k == 1) { r.a = 3; r.b = 0; r.out = 6; }
+    else if (k == 2) { r.a = 4; r.b = 3; r.out = 7; }
+    else { r.a = 4; r.b = 0; r.out = 8; }
+    return r;
+}
+BPPP_HD bool pta_is_sentinel(const PtA &a) { return fe_is_zero_canonical(a.x) && fe_is_zero_canonical(a.y); }
+BPPP_HD PtA vtab_ld_pta(const uint32_t *ent) { PtA a; a.x = vtab_ld_fe(ent); a.y = vtab_ld_fe(ent + FE_W); return a; }
+BPPP_HD void vtab_st_entry(uint32_t *dst, const PtA &a_canonical, const Fe &beta) {
+    vtab_st_fe(dst, a_canonical.x); vtab_st_fe(dst + FE_W, a_canonical.y);
+    vtab_st_fe(dst + 2 * FE_W, fe_normalize(fe_mul(a_canonical.x, beta)));
+}
+// operands of item (op, point p, proof i); false when the result is the identity (P = O).  Level 1 reads P from the
+// record through SRC (the table does not hold it yet), the other levels read finished entries of earlier levels.
+template <class SRC>
+BPPP_HD bool aff_operands(const WS &w, const TabRegion &R, int level, size_t i, int p, const AffOp &op, const SRC &src, PtA &A, PtA &B) {
+    if (level == 1) {
+        if (src(w, i, p, A)) return false;
+        B = A;
+        return !pta_is_sentinel(A);
+    }
+    A = vtab_ld_pta(tab_entry(w, R, i, p * 8 + op.a - 1));
+    B = op.b ? vtab_ld_pta(tab_entry(w, R, i, p * 8 + op.b - 1)) : A;
+    return !(pta_is_sentinel(A) || pta_is_sentinel(B));
+}
+BPPP_HD Fe aff_denominator(const AffOp &op, const PtA &A, const PtA &B) { return op.b ? fe_sub(B.x, A.x) : fe_mul_int(A.y, 2); }
+template <class SRC>
+BPPP_HD void tables_affine_level(const WS &w, const TabRegion &R, int level, size_t t, size_t T, const SRC &src) {
+    const int points = R.entries / 8, nops = aff_level_nops(level);
+    const size_t per_op = (size_t)points * w.n, total = per_op * (size_t)nops;
+    const Fe beta = fe_beta();
+    Fe run = fe_one();
+#pragma unroll 1
+    for (size_t idx = t; idx < total; idx += T) {
+        const int k = (int)(idx / per_op); const size_t rem = idx - (size_t)k * per_op;
+        const int p = (int)(rem / w.n); const size_t i = rem - (size_t)p * w.n;
+        const AffOp op = aff_level_op(level, k);
+        PtA A, B;
+        const bool live = aff_operands(w, R, level, i, p, op, src, A, B);
+        if (level == 1) {                                         // entry 0 is P itself
+            if (!live) { A.x = fe_zero(); A.y = fe_zero(); }
+            vtab_st_entry(tab_entry(w, R, i, p * 8), A, beta);
+        }
+        if (!live) continue;
+        const Fe d = aff_denominator(op, A, B);
+        if (fe_normalizes_to_zero(d)) continue;
+        ws_st_fe(w, i, R.tab + (p * 8 + op.out - 1) * TAB_STRIDE_W + PT_W, run);      // prefix product before this item
+        run = fe_mul(run, d);
+    }
+    Fe rinv = fe_inv(run);
+    const size_t cnt = total > t ? (total - t + T - 1) / T : 0;
+#pragma unroll 1
+    for (size_t c = cnt; c-- > 0;) {
+        const size_t idx = t + c * T;
+        const int k = (int)(idx / per_op); const size_t rem = idx - (size_t)k * per_op;
+        const int p = (int)(rem / w.n); const size_t i = rem - (size_t)p * w.n;
+        const AffOp op = aff_level_op(level, k);
+        uint32_t *dst = tab_entry(w, R, i, p * 8 + op.out - 1);
+        PtA A, B, r;
+        const bool live = aff_operands(w, R, level, i, p, op, src, A, B);
+        Fe d = fe_zero();
+        if (live) d = aff_denominator(op, A, B);
+        if (!live || fe_normalizes_to_zero(d)) {
+            r.x = fe_zero(); r.y = fe_zero();
+            vtab_st_entry(dst, r, beta);
+            continue;
+        }
+        const Fe inv = fe_mul(rinv, ws_ld_fe(w, i, R.tab + (p * 8 + op.out - 1) * TAB_STRIDE_W + PT_W));
+        rinv = fe_mul(rinv, d);
+        const Fe lam = fe_mul(op.b ? fe_sub(B.y, A.y) : fe_mul_int(fe_sqr(A.x), 3), inv);
+        r.x = fe_sub(fe_sub(fe_sqr(lam), A.x), B.x);               // B = A for a doubling
+        r.y = fe_sub(fe_mul(lam, fe_sub(A.x, r.x)), A.y);
+        r.x = fe_normalize(r.x); r.y = fe_normalize(r.y);
+        vtab_st_entry(dst, r, beta);
+    }
+}
+// the verifier's 13 table points: input slots 1..12 and V' (u64v_table_build_one reads the same)
+struct VTabSource {
+    BPPP_HD bool operator()(const WS &w, size_t i, int t, PtA &a) const {
+        const uint32_t idmask = ws_ld(w, i, VL::IDMASK);
+        if (t == VTAB_VP) { a = ws_ld_pta(w, i, VL::VPA); return (idmask & (1u << 14)) != 0; }
+        a = ws_ld_pta(w, i, VL::PT + 16 * (t + 1));
+        return (idmask & (1u << (t + 1))) != 0;
+    }
+};
+BPPP_HD void u64v_tables_affine_level(const WS &w, int level, size_t t, size_t T) { tables_affine_level(w, vtab_region(), level, t, T, VTabSource()); }
 // One lane's share of sum_k ks[k] * P_{tids[k]} from the affine tables: the 2 NP GLV halves are dealt round-robin to
 // `nlanes` lanes (half h belongs to lane h % nlanes); every lane runs the full 128-doubling chain over its own halves.
 // nlanes = 1 is the whole sum.  More lanes shorten the dependent chain of one proof (fewer additions per lane) at the

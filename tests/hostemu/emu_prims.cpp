@@ -13,6 +13,15 @@ extern "C" {
 void emu_fe_mul(const uint8_t *a, const uint8_t *b, uint8_t *r) { fe_to_be(r, fe_mul(fe_from_be(a), fe_from_be(b))); }
 void emu_fe_sqr(const uint8_t *a, uint8_t *r) { fe_to_be(r, fe_sqr(fe_from_be(a))); }
 void emu_fe_inv(const uint8_t *a, uint8_t *r) { fe_to_be(r, fe_inv(fe_from_be(a))); }
+void emu_fe_inv_fermat(const uint8_t *a, uint8_t *r) { fe_to_be(r, fe_inv_fermat(fe_from_be(a))); }
+void emu_sc_inv_fermat(const uint8_t *a, uint8_t *r) { Sc x; sc_from_be32(x, a); sc_to_be32(r, sc_inv_fermat(x)); }
+// n inversions in one call (32 bytes big-endian each): field = 0 base field (any 256-bit input), 1 scalar field (canonical input)
+void emu_inv_many(int field, size_t n, const uint8_t *a, uint8_t *r) {
+    for (size_t i = 0; i < n; i++) {
+        if (field == 0) fe_to_be(r + 32 * i, fe_inv(fe_from_be(a + 32 * i)));
+        else { Sc x; sc_from_be32(x, a + 32 * i); sc_to_be32(r + 32 * i, sc_inv(x)); }
+    }
+}
 void emu_fe_norm(const uint8_t *a, uint8_t *r) { fe_to_be(r, fe_from_be(a)); }
 // (a*k1 + b*k2 - c) * d with lazy adds: exercises magnitude handling
 void emu_fe_expr(const uint8_t *a, const uint8_t *b, const uint8_t *c, const uint8_t *d, uint32_t k1, uint32_t k2, uint8_t *r) {

@@ -16,7 +16,10 @@ struct EmuCtx {
     PtA gens[NUM_GENS]; bool gen_id[NUM_GENS];
 };
 
+static int g_tab_affine = 1;      // ladder tables: 1 = affine levels (tables_affine_level), 0 = projective build + normalise
+
 extern "C" {
+void emu_set_tab_affine(int on) { g_tab_affine = on; }
 void *emu_ctx_create(const uint8_t *gens64, int W) {
     EmuCtx *c = new EmuCtx();
     bool sgn = W < 0;                          // negative: signed windows of |W| bits (ws.cuh:FixedTable)
@@ -73,8 +76,16 @@ int emu_u64_verify_batch(void *ctx, size_t n, const uint8_t *commits, const uint
     for (size_t i = 0; i < n; i++) u64v_load_one(w, i, commits + csz * i, proofs + psz * i, fmt);
     emu_batch_inv(w, n, VL::VP + 2 * FE_W, VL::ZINV);
     for (size_t i = 0; i < n; i++) u64v_phase1_one(w, i, init);
-    for (size_t i = 0; i < n; i++) for (int t = 0; t < VL::TAB_POINTS; t++) u64v_table_build_one(w, i, t);
-    { size_t T = (n * VL::TAB_ENTRIES + 6) / 7; for (size_t t = 0; t < T; t++) u64v_tables_normalize_strided(w, t, T); }
+    if (g_tab_affine) {
+        for (int level = 1; level <= 3; level++) {
+            size_t items = n * VL::TAB_POINTS * aff_level_nops(level), T = (items + 4) / 5;      // 5 items per emulated thread
+            for (size_t t = 0; t < T; t++) u64v_tables_affine_level(w, level, t, T);
+        }
+    } else {
+        for (size_t i = 0; i < n; i++) for (int t = 0; t < VL::TAB_POINTS; t++) u64v_table_build_one(w, i, t);
+        size_t T = (n * VL::TAB_ENTRIES + 6) / 7;
+        for (size_t t = 0; t < T; t++) u64v_tables_normalize_strided(w, t, T);
+    }
     int tg17[17]; for (int t = 0; t < 17; t++) tg17[t] = t;
     emu_msm_fixed(c, w, n, VL::FS, tg17, 17, VL::ACC, 8);
     for (size_t i = 0; i < n; i++) u64v_var5_one(w, i);
@@ -87,6 +98,29 @@ int emu_u64_verify_batch(void *ctx, size_t n, const uint8_t *commits, const uint
     int tg49[49]; for (int t = 0; t < 49; t++) tg49[t] = t;
     emu_msm_fixed(c, w, n, VL::FS, tg49, 49, VL::ACC, 8);
     for (size_t i = 0; i < n; i++) { u64v_verdict_one(w, i); status[i] = (int32_t)ws_ld(w, i, VL::STATUS); }
+    return 0;
+}
+// the finished ladder tables (array-of-structures region, 104 entries x 24 words per proof) of a batch after phase 1,
+// built the way `affine` says: the two constructions must agree word for word
+int emu_u64_verify_tables(size_t n, const uint8_t *commits, const uint8_t *proofs, int fmt, int affine, uint32_t *out) {
+    std::vector<uint32_t> buf((size_t)VL::WORDS * n, 0);
+    WS w{buf.data(), n};
+    Merlin init; merlin_init(init, (const uint8_t *)"t", 1);
+    size_t csz = fmt == FMT_COMPRESSED ? 33 : 64, psz = fmt == FMT_COMPRESSED ? U64_PROOF_BYTES_COMPRESSED : U64_PROOF_BYTES_AFFINE;
+    for (size_t i = 0; i < n; i++) u64v_load_one(w, i, commits + csz * i, proofs + psz * i, fmt);
+    emu_batch_inv(w, n, VL::VP + 2 * FE_W, VL::ZINV);
+    for (size_t i = 0; i < n; i++) u64v_phase1_one(w, i, init);
+    if (affine) {
+        for (int level = 1; level <= 3; level++) {
+            size_t items = n * VL::TAB_POINTS * aff_level_nops(level), T = (items + 2) / 3;
+            for (size_t t = 0; t < T; t++) u64v_tables_affine_level(w, level, t, T);
+        }
+    } else {
+        for (size_t i = 0; i < n; i++) for (int t = 0; t < VL::TAB_POINTS; t++) u64v_table_build_one(w, i, t);
+        size_t T = (n * VL::TAB_ENTRIES + 6) / 7;
+        for (size_t t = 0; t < T; t++) u64v_tables_normalize_strided(w, t, T);
+    }
+    memcpy(out, tab_entry(w, vtab_region(), 0, 0), sizeof(uint32_t) * n * VL::TAB_ENTRIES * VL::TABA_STRIDE);
     return 0;
 }
 // commit_value (engine_core.cu:bppp_u64_commit_batch): x g + s h_0 through the fixed-base lane code, 3 lanes
@@ -148,8 +182,16 @@ extern "C" int emu_u64_prove_batch(void *ctx, size_t n, const uint64_t *xs, cons
         emu_batch_inv(w, n, PL::PTS + PT_W * (PP_R + j) + 2 * FE_W, PL::ZINV + FE_W * (PP_R + j));
         for (size_t i = 0; i < n; i++) u64p_round_one(w, i, j);
         if (j < 3) {
-            for (int t = 0; t < 2; t++) for (size_t i = 0; i < n; i++) u64p_table_build_one(w, i, j, t);
-            { size_t T = (n * PL::TAB_ENTRIES + 4) / 5; for (size_t t = 0; t < T; t++) tables_normalize_strided(w, ptab_region(), t, T); }
+            if (g_tab_affine) {
+                for (int level = 1; level <= 3; level++) {
+                    size_t items = n * 2 * aff_level_nops(level), T = (items + 2) / 3;
+                    for (size_t t = 0; t < T; t++) u64p_tables_affine_level(w, j, level, t, T);
+                }
+            } else {
+                for (int t = 0; t < 2; t++) for (size_t i = 0; i < n; i++) u64p_table_build_one(w, i, j, t);
+                size_t T = (n * PL::TAB_ENTRIES + 4) / 5;
+                for (size_t t = 0; t < T; t++) tables_normalize_strided(w, ptab_region(), t, T);
+            }
             for (size_t i = 0; i < n; i++) u64p_var2_one(w, i, j);
         }
     }

@@ -42,6 +42,34 @@ def test_field_ops(emu_prims, ref):
         assert ok == 1 and r * r % P == sq
 
 
+def test_safegcd_inversion_both_moduli(emu_prims, ref):
+    """modinv.cuh (600 division steps in 20 batches of 30) against Python's modular inverse and against the Fermat powers it
+    replaced: 0 -> 0, 1, -1, +-2, powers of two around the limb boundaries of both the 32-bit words and the 30-bit limbs,
+    non-canonical field representatives in [p, 2^256), and 4,000 random values per modulus."""
+    L = emu_prims
+    rnd = random.Random(11)
+    for field, M in ((0, ref.P), (1, ref.N)):
+        edge = [0, 1, 2, 3, M - 1, M - 2, M - 3, (M + 1) // 2, (M - 1) // 2, 2**255, 2**255 - 1, 2**128, 2**128 - 1, M >> 1, M >> 128]
+        edge += [2**k for k in (29, 30, 31, 32, 59, 60, 61, 64, 90, 120, 150, 180, 210, 239, 240, 241, 254)]
+        edge += [(2**k - 1) for k in (30, 60, 90, 240, 250)]
+        if field == 0:
+            edge += [M, M + 1, M + 5, 2**256 - 1, 2**256 - 2, M + 2**32]          # representatives fe_inv must normalise first
+        vals = edge + [rnd.randrange(M) for _ in range(4000)] + [rnd.randrange(1, 2**k) for k in range(1, 256, 3)]
+        vals = [v % 2**256 if field == 0 else v % M for v in vals]
+        buf = b"".join(be(v) for v in vals)
+        out = O(32 * len(vals))
+        L.emu_inv_many(field, C.c_size_t(len(vals)), B(buf), out)
+        out = bytes(out)
+        for k, v in enumerate(vals):
+            got = int.from_bytes(out[32 * k:32 * k + 32], "big")
+            want = pow(v % M, -1, M) if v % M else 0
+            assert got == want, (field, hex(v))
+        for v in edge[:12] + vals[-20:]:
+            o = O(32)
+            (L.emu_fe_inv_fermat if field == 0 else L.emu_sc_inv_fermat)(B(be(v)), o)
+            assert int.from_bytes(o, "big") == (pow(v % M, -1, M) if v % M else 0)
+
+
 def test_field_ops_on_non_canonical_representatives(emu_prims, ref):
     """every pair of edge values, including the representatives in [p, 2^256) that trigger the rare double wrap
     of fe_add / double borrow of fe_sub / second fold of the product reduction"""
@@ -269,6 +297,59 @@ def test_device_verify_logic_matches_oracle(emu_u64, ref, oracle, gens64):
     emu_u64.emu_ctx_destroy(ctx)
 
 
+def test_affine_ladder_tables_equal_the_projective_construction(emu_u64, ref, oracle, gens64):
+    """u64_verify.cuh:tables_affine_level (affine chords / tangents with cross-proof Montgomery inversions) against
+    u64v_table_build_one + tables_normalize_strided (complete projective formulas, then normalisation): the 104 finished
+    entries (x, y, beta x) of every proof must agree word for word -- honest proofs, identity points (33 zero bytes) in
+    several slots, undecodable points, and X_j == R_j."""
+    n = 7
+    xs, blinds, rngs = synth_batch(ref, n)
+    proofs, st = oracle.u64_prove_batch(gens64, xs, blinds, rngs, LABEL, 4)
+    commits = bytearray(b"".join(oracle.u64_commit(gens64, xs[i], blinds[32 * i:32 * i + 32]) for i in range(n)))
+    rec = bytearray(proofs)
+    rec[525 * 1 + 33 * 2:525 * 1 + 33 * 3] = bytes(33)                    # c_o = identity
+    rec[525 * 2 + 33 * 4:525 * 2 + 33 * 5] = bytes(33)                    # r[0] = identity
+    rec[525 * 2 + 33 * 11:525 * 2 + 33 * 12] = bytes(33)                  # x[3] = identity
+    rec[525 * 3 + 33 * 8:525 * 3 + 33 * 9] = rec[525 * 3 + 33 * 4:525 * 3 + 33 * 5]      # x[0] = r[0]
+    rec[525 * 4 + 1:525 * 4 + 33] = (5).to_bytes(32, "big")               # c_l: x = 5 is not on the curve
+    commits[33 * 5:33 * 6] = bytes(33)                                    # V = identity
+    rec[525 * 6 + 492:525 * 6 + 525] = commits[33 * 6:33 * 6 + 1].replace(b"\x02", b"\x13").replace(b"\x03", b"\x02").replace(b"\x13", b"\x03") + commits[33 * 6 + 1:33 * 7]   # r = -V: V' = identity
+    words = n * 104 * 24
+    out = [(C.c_uint32 * words)(), (C.c_uint32 * words)()]
+    for mode in (0, 1):
+        emu_u64.emu_u64_verify_tables(C.c_size_t(n), B(bytes(commits)), B(bytes(rec)), 0, mode, out[mode])
+    a, b = list(out[0]), list(out[1])
+    for i in range(n):
+        for e in range(104):
+            lo = (i * 104 + e) * 24
+            assert a[lo:lo + 24] == b[lo:lo + 24], (i, e)
+    assert any(a), "tables are empty"
+    # V' = identity really is the sentinel in both (slot 12 of proof 6), and the honest proof 0 has none
+    assert a[(6 * 104 + 12 * 8) * 24:(6 * 104 + 13 * 8) * 24] == [0] * (8 * 24)
+    assert all(any(a[(0 * 104 + e) * 24:(0 * 104 + e) * 24 + 16]) for e in range(104))
+
+
+@pytest.mark.parametrize("tab_affine", [0, 1])
+def test_device_verify_logic_with_either_table_construction(emu_u64, ref, oracle, gens64, tab_affine):
+    n = 4
+    xs, blinds, rngs = synth_batch(ref, n, start=9)
+    proofs, st = oracle.u64_prove_batch(gens64, xs, blinds, rngs, LABEL, 4)
+    commits = b"".join(oracle.u64_commit(gens64, xs[i], blinds[32 * i:32 * i + 32]) for i in range(n))
+    bad = bytearray(proofs)
+    bad[525 * 1 + 33 * 5:525 * 1 + 33 * 6] = bytes(33)      # r[1] = identity
+    bad[525 * 2 + 33 * 8 + 7] ^= 4                            # x[0] tampered (most likely undecodable or another point)
+    ctx = _emu_ctx(emu_u64, gens64)
+    status = (C.c_int32 * n)()
+    emu_u64.emu_set_tab_affine(tab_affine)
+    try:
+        emu_u64.emu_u64_verify_batch(ctx, C.c_size_t(n), B(commits), B(bytes(bad)), 0, B(LABEL), len(LABEL), status)
+    finally:
+        emu_u64.emu_set_tab_affine(1)
+    assert list(status) == oracle.u64_verify_batch(gens64, commits, bytes(bad), LABEL, 4)
+    assert status[0] == 1 and status[3] == 1 and status[1] <= 0
+    emu_u64.emu_ctx_destroy(ctx)
+
+
 @pytest.mark.parametrize("W", [5, -5, -7])     # 5: a width that does not divide 32; negative: signed windows (ws.cuh:FixedTable)
 def test_device_prove_logic_matches_oracle(emu_u64, ref, oracle, gens64, W):
     n = 5
@@ -280,6 +361,23 @@ def test_device_prove_logic_matches_oracle(emu_u64, ref, oracle, gens64, W):
     emu_u64.emu_u64_prove_batch(ctx, C.c_size_t(n), xa, B(blinds), B(rngs), B(LABEL), len(LABEL), out, status)
     assert list(status) == [1] * n
     assert bytes(out) == proofs
+    emu_u64.emu_ctx_destroy(ctx)
+
+
+def test_device_prove_logic_with_the_projective_table_construction(emu_u64, ref, oracle, gens64):
+    """the prover's re-commit ladders over tables built the round-1 way (BPPP_TAB_AFFINE=0 in the library)"""
+    n = 3
+    xs, blinds, rngs = synth_batch(ref, n, start=20)
+    proofs, st = oracle.u64_prove_batch(gens64, xs, blinds, rngs, LABEL, 4)
+    ctx = _emu_ctx(emu_u64, gens64)
+    out = (C.c_uint8 * (525 * n))(); status = (C.c_int32 * n)()
+    xa = (C.c_uint64 * n)(*xs)
+    emu_u64.emu_set_tab_affine(0)
+    try:
+        emu_u64.emu_u64_prove_batch(ctx, C.c_size_t(n), xa, B(blinds), B(rngs), B(LABEL), len(LABEL), out, status)
+    finally:
+        emu_u64.emu_set_tab_affine(1)
+    assert list(status) == [1] * n and bytes(out) == proofs
     emu_u64.emu_ctx_destroy(ctx)
 
 
