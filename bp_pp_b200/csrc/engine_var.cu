@@ -87,10 +87,6 @@ __global__ void __launch_bounds__(128) k_p_tables_normalize(WS w, size_t nthread
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nthreads) tables_normalize_strided(w, ptab_region(), t, nthreads);
 }
-__global__ void __launch_bounds__(128) k_p_tables_affine(WS w, int j, int level, size_t nthreads) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < nthreads) u64p_tables_affine_level(w, j, level, t, nthreads);
-}
 namespace bppp {
 // engine_var_lat.cu: the 4-lane kernels built for latency
 void launch_v_var5_lat(bppp_ctx *c, cudaStream_t st, WS w);
@@ -119,19 +115,13 @@ void launch_v_var2(bppp_ctx *c, cudaStream_t st, WS w, int j) {
     else launch_v_var2_lat(c, st, w, j);
 }
 void launch_p_var2(bppp_ctx *c, cudaStream_t st, WS w, int j) {
-    // tables of X_j, R_j: three affine levels (or the projective build + one normalisation pass), then the ladder
-    if (c->tab_affine) {
-        for (int level = 1; level <= 3; level++) {
-            const size_t nthreads = tab_level_threads(c, w.n * 2 * (size_t)aff_level_nops(level), level);
-            LAUNCH(c, k_p_tables_affine, nblocks(nthreads, 128), 128, w, j, level, nthreads);
-        }
-    } else {
-        LAUNCH(c, k_p_tables_build, nblocks(w.n * 2, 64), 64, w, j);
-        size_t items = w.n * PL::TAB_ENTRIES, nthreads = (items + 15) / 16;
-        size_t min_threads = (size_t)c->sm_count * 128;
-        if (nthreads < min_threads) nthreads = items < min_threads ? items : min_threads;
-        LAUNCH(c, k_p_tables_normalize, nblocks(nthreads, 128), 128, w, nthreads);
-    }
+    // tables of X_j, R_j (point-major), one cross-proof inversion for their 16 entries, then the ladder.  (Two points per
+    // proof are too few items for the verifier's affine levels to pay: three latency-bound launches, 1.12 against 1.13 ms.)
+    LAUNCH(c, k_p_tables_build, nblocks(w.n * 2, 64), 64, w, j);
+    size_t items = w.n * PL::TAB_ENTRIES, nthreads = (items + 15) / 16;
+    size_t min_threads = (size_t)c->sm_count * 128;
+    if (nthreads < min_threads) nthreads = items < min_threads ? items : min_threads;
+    LAUNCH(c, k_p_tables_normalize, nblocks(nthreads, 128), 128, w, nthreads);
     const int lanes = var_lanes_for(c, w.n);
     if (lanes == 1) LAUNCH(c, k_p_var2, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
     else if (lanes == 2) LAUNCH(c, k_p_var2_lanes<2>, nblocks(w.n * 2, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);

@@ -494,20 +494,6 @@ BPPP_HD void u64p_table_build_one(const WS &w, size_t i, int j, int t) {
 #pragma unroll 1
     for (int e = 0; e < 8; e++) ws_st_pt(w, i, PL::TAB + (t * 8 + e) * TAB_STRIDE_W, tab.m[e]);
 }
-// the same two tables by affine levels (u64_verify.cuh:tables_affine_level)
-struct PTabSource {
-    int j;
-    BPPP_HD bool operator()(const WS &w, size_t i, int t, PtA &a) const {
-        bool id;
-        const int slot = (t ? PP_R : PP_X) + j;
-        a = ws_affine(w, i, PL::PTS + PT_W * slot, PL::ZINV + FE_W * slot, id);
-        return id;
-    }
-};
-BPPP_HD void u64p_tables_affine_level(const WS &w, int j, int level, size_t t, size_t T) {
-    PTabSource src; src.j = j;
-    tables_affine_level(w, ptab_region(), level, t, T, src);
-}
 // com_{j+1} = com_j + y X_j + (y^2 - 1) R_j from the normalised tables (same ladder as the verifier's rounds)
 BPPP_HD void u64p_var2_one(const WS &w, size_t i, int j) {
     (void)j;

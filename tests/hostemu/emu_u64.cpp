@@ -182,16 +182,8 @@ extern "C" int emu_u64_prove_batch(void *ctx, size_t n, const uint64_t *xs, cons
         emu_batch_inv(w, n, PL::PTS + PT_W * (PP_R + j) + 2 * FE_W, PL::ZINV + FE_W * (PP_R + j));
         for (size_t i = 0; i < n; i++) u64p_round_one(w, i, j);
         if (j < 3) {
-            if (g_tab_affine) {
-                for (int level = 1; level <= 3; level++) {
-                    size_t items = n * 2 * aff_level_nops(level), T = (items + 2) / 3;
-                    for (size_t t = 0; t < T; t++) u64p_tables_affine_level(w, j, level, t, T);
-                }
-            } else {
-                for (int t = 0; t < 2; t++) for (size_t i = 0; i < n; i++) u64p_table_build_one(w, i, j, t);
-                size_t T = (n * PL::TAB_ENTRIES + 4) / 5;
-                for (size_t t = 0; t < T; t++) tables_normalize_strided(w, ptab_region(), t, T);
-            }
+            for (int t = 0; t < 2; t++) for (size_t i = 0; i < n; i++) u64p_table_build_one(w, i, j, t);
+            { size_t T = (n * PL::TAB_ENTRIES + 4) / 5; for (size_t t = 0; t < T; t++) tables_normalize_strided(w, ptab_region(), t, T); }
             for (size_t i = 0; i < n; i++) u64p_var2_one(w, i, j);
         }
     }

@@ -364,23 +364,6 @@ def test_device_prove_logic_matches_oracle(emu_u64, ref, oracle, gens64, W):
     emu_u64.emu_ctx_destroy(ctx)
 
 
-def test_device_prove_logic_with_the_projective_table_construction(emu_u64, ref, oracle, gens64):
-    """the prover's re-commit ladders over tables built the round-1 way (BPPP_TAB_AFFINE=0 in the library)"""
-    n = 3
-    xs, blinds, rngs = synth_batch(ref, n, start=20)
-    proofs, st = oracle.u64_prove_batch(gens64, xs, blinds, rngs, LABEL, 4)
-    ctx = _emu_ctx(emu_u64, gens64)
-    out = (C.c_uint8 * (525 * n))(); status = (C.c_int32 * n)()
-    xa = (C.c_uint64 * n)(*xs)
-    emu_u64.emu_set_tab_affine(0)
-    try:
-        emu_u64.emu_u64_prove_batch(ctx, C.c_size_t(n), xa, B(blinds), B(rngs), B(LABEL), len(LABEL), out, status)
-    finally:
-        emu_u64.emu_set_tab_affine(1)
-    assert list(status) == [1] * n and bytes(out) == proofs
-    emu_u64.emu_ctx_destroy(ctx)
-
-
 def test_device_prove_matches_golden(emu_u64, ref, golden, gens64):
     c = golden["cases"][0]
     ctx = _emu_ctx(emu_u64, gens64)
