@@ -5,18 +5,11 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 out=gpurun_out/tab_sweep.jsonl; : > $out
 run() { n=$1; shift; echo "# n=$n $*" >> $out; env "$@" BPPP_PROFILE=1 python tools/variant_bench.py $n >> $out 2>> gpurun_out/tab_sweep.err; }
-run 65536 BPPP_TAB_AFFINE=0
 run 65536 BPPP_TAB_AFFINE=1
 run 65536 BPPP_TAB_K=8,16,32
 run 65536 BPPP_TAB_K=4,8,16
-run 65536 BPPP_TAB_K=8,8,16
 run 65536 BPPP_TAB_K=16,16,32
-run 16384 BPPP_TAB_AFFINE=0
-run 16384 BPPP_TAB_AFFINE_MIN=1 BPPP_TAB_K=4,8,16
-run 16384 BPPP_TAB_AFFINE_MIN=1 BPPP_TAB_K=2,4,8
-run 8192 BPPP_TAB_AFFINE=0
-run 8192 BPPP_TAB_AFFINE_MIN=1 BPPP_TAB_K=4,8,16
-run 8192 BPPP_TAB_AFFINE_MIN=1 BPPP_TAB_K=2,4,8
-run 2048 BPPP_TAB_AFFINE=0
-run 2048 BPPP_TAB_AFFINE_MIN=1 BPPP_TAB_K=1,2,4
+run 65536 BPPP_TAB_K=32,64,64
+run 8192 BPPP_TAB_AFFINE=1
+run 2048 BPPP_TAB_AFFINE=1
 cat $out
