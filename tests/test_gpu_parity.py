@@ -124,6 +124,32 @@ def test_verify_verdicts_match_oracle_on_tampered_batch(ctx, batch, oracle, gens
     assert expect.count(1) >= n // 2 and expect.count(0) > 0 and any(v < 0 for v in expect)
 
 
+def test_projective_table_construction_gives_the_same_verdicts(gens64, batch, oracle, monkeypatch):
+    """BPPP_TAB_AFFINE=0 (read at context creation) switches the verifier's ladder tables back to the projective build +
+    normalisation pass; the 8-rule tampered batch must come out exactly as with the affine levels and as the oracle says.
+    Identity points, swapped X / R and undecodable bytes all pass through the tables."""
+    import bp_pp_b200 as B
+    rnd = random.Random(7)
+    n = 192
+    recs, coms = [], []
+    for i in range(n):
+        rec, com = batch["proofs"][525 * i:525 * i + 525], batch["commits"][33 * i:33 * i + 33]
+        if i % 3:
+            rec, com = _tamper(rec, com, i % 8, rnd, oracle)
+        recs.append(rec); coms.append(com)
+    recs, coms = b"".join(recs), b"".join(coms)
+    expect = oracle.u64_verify_batch(gens64, coms, recs, LABEL, THREADS)
+    got = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("BPPP_TAB_AFFINE", mode)
+        c = B.Context(gens64, 0, 8, 256)
+        try:
+            got[mode] = c.verify_batch(coms, recs, LABEL)
+        finally:
+            c.close()
+    assert got["0"] == expect and got["1"] == expect
+
+
 def test_affine64_input_format(ctx, batch, oracle):
     import bp_pp_b200 as B
     n = 64
