@@ -400,54 +400,24 @@ __global__ void __launch_bounds__(256) k_msm_window_sums(const uint32_t *in, uin
     }
     if (threadIdx.x == 0) st_pt30(out + PT_W * (size_t)w, ld_pt30(sh));
 }
-// One Jacobian doubling (dbl-2009-l, 2 M + 5 S) spread over the lanes of a warp that all hold the same point: the products
-// that do not depend on each other run side by side on lanes 0, 1, 2 and are broadcast back, so a doubling is three
-// products deep (X^2 | Y^2 | Y Z, then B^2 | (X + B)^2 | E^2, then E (D - X3)) instead of seven.
-__device__ __forceinline__ Fe fe_bcast(const Fe &v, int src) {
-    Fe r;
-#pragma unroll
-    for (int k = 0; k < FE_W; k++) r.v[k] = __shfl_sync(0xFFFFFFFFu, v.v[k], src);
-    return r;
-}
-__device__ __forceinline__ Fe fe_pick3(const Fe &a, const Fe &b, const Fe &c, int lane) {
-    Fe r;
-#pragma unroll
-    for (int k = 0; k < FE_W; k++) r.v[k] = lane == 0 ? a.v[k] : (lane == 1 ? b.v[k] : c.v[k]);
-    return r;
-}
-__device__ __forceinline__ PtJ ptj_double_warp(const PtJ &p, int lane) {
-    PtJ r;
-    const Fe r1 = fe_mul_inl_t<false>(fe_pick3(p.x, p.y, p.y, lane), fe_pick3(p.x, p.y, p.z, lane));
-    const Fe A = fe_bcast(r1, 0), B = fe_bcast(r1, 1), YZ = fe_bcast(r1, 2);
-    const Fe E = fe_mul_int_t<false>(A, 3);
-    const Fe r2 = fe_sqr_inl_t<false>(fe_pick3(B, fe_add_t<false>(p.x, B), E, lane));
-    const Fe C = fe_bcast(r2, 0), t = fe_bcast(r2, 1), F = fe_bcast(r2, 2);
-    const Fe D = fe_mul_int_t<false>(fe_sub_t<false>(t, fe_add_t<false>(A, C)), 2);       // 2 ((X+B)^2 - A - C)
-    r.x = fe_sub_t<false>(F, fe_mul_int_t<false>(D, 2));
-    r.y = fe_sub_t<false>(fe_mul_inl_t<false>(E, fe_sub_t<false>(D, r.x)), fe_mul_int_t<false>(C, 8));
-    r.z = fe_mul_int_t<false>(YZ, 2);
-    r.inf = p.inf;
-    return r;
-}
 // result = sum_w 2^(c w) W_w, optionally + *addend
-__global__ void __launch_bounds__(32) k_msm_horner(const uint32_t *win, int c, int nwin, const uint32_t *addend, uint32_t *out) {
-    if (blockIdx.x != 0) return;
-    // One warp, c (nwin - 1) dependent doublings: latency is what counts.  Every lane carries the same accumulator; the
-    // doublings run on the Jacobian formula with inlined field arithmetic, three products at a time (ptj_double_warp).
-    const int lane = threadIdx.x & 31;
+__global__ void k_msm_horner(const uint32_t *win, int c, int nwin, const uint32_t *addend, uint32_t *out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    // One thread, 256 dependent doublings: latency is what counts, so the doublings run on the Jacobian formula with the
+    // field arithmetic inlined (ptxas overlaps the independent squarings of one doubling).
     Pt acc = ld_pt30(win + PT_W * (nwin - 1));
     for (int w = nwin - 2; w >= 0; w--) {
         if (!fe_normalizes_to_zero(acc.z)) {
             PtJ j;
             j.x = fe_mul(acc.x, acc.z); j.y = fe_mul(acc.y, fe_sqr(acc.z)); j.z = acc.z; j.inf = false;      // (X/Z, Y/Z) = (Xj/Z^2, Yj/Z^3)
 #pragma unroll 1
-            for (int k = 0; k < c; k++) j = ptj_double_warp(j, lane);
+            for (int k = 0; k < c; k++) j = ptj_double_t<true>(j);
             acc = ptj_to_pt(j);
         }
         acc = pt_add(acc, ld_pt30(win + PT_W * w));
     }
     if (addend) acc = pt_add(acc, ld_pt30(addend));
-    if (lane == 0) st_pt30(out, acc);
+    st_pt30(out, acc);
 }
 // small n: one GLV scalar multiplication per point
 __global__ void __launch_bounds__(64) k_msm_small(const uint32_t *pts, const uint32_t *sc, size_t n, uint32_t *out) {
@@ -594,7 +564,7 @@ int msm_device(cudaStream_t st, const uint32_t *d_pts, const uint32_t *d_sc, siz
     // per-window sum of the chunk results
     uint32_t *in = chunks;
     if (nchunks > 1) { GL(k_msm_window_sums, (unsigned)nwin, 256, chunks, nchunks, tmp); in = tmp; }
-    GL(k_msm_horner, 1, 32, in, c, nwin, d_addend30, d_out30);
+    GL(k_msm_horner, 1, 1, in, c, nwin, d_addend30, d_out30);
     CUDA_OK(cudaStreamSynchronize(st));
     CUDA_OK(cudaGetLastError());
     return BPPP_OK;
