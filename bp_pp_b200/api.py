@@ -378,10 +378,11 @@ class U64RangeProofProtocol:
 
 
 def microbench(device: int = 0) -> dict:
-    out = (C.c_double * 10)()
-    check(lib().bppp_microbench(C.c_int(device), out, C.c_int(10)), "bppp_microbench")
+    out = (C.c_double * 14)()
+    check(lib().bppp_microbench(C.c_int(device), out, C.c_int(14)), "bppp_microbench")
     keys = ["imad_wide_per_s", "fe_mul_per_s", "fe_sqr_per_s", "sc_mul_per_s", "pt_add_mixed_per_s",
-            "pt_double_per_s", "pt_add_per_s", "sm_clock_mhz", "imad_per_s", "iadd_per_s"]
+            "pt_double_per_s", "pt_add_per_s", "sm_clock_mhz", "imad_per_s", "iadd_per_s",
+            "fe_inv_per_s", "fe_inv_fermat_per_s", "sc_inv_per_s", "sc_inv_fermat_per_s"]
     return dict(zip(keys, list(out)))
 
 

@@ -50,6 +50,10 @@ __global__ void __launch_bounds__(64) k_mb_op(uint32_t *out, uint32_t seed, int 
         if (OP == 4) p = pt_add_mixed(p, q);
         if (OP == 5) p = pt_double(p);
         if (OP == 6) p = pt_add(p, p);
+        if (OP == 7) a = fe_add(fe_inv(a), b);             // safegcd (modinv.cuh)
+        if (OP == 8) a = fe_add(fe_inv_fermat(a), b);      // a^(p-2)
+        if (OP == 9) s = sc_add(sc_inv(s), u);
+        if (OP == 10) s = sc_add(sc_inv_fermat(s), u);
     }
     uint32_t r = 0;
 #pragma unroll
@@ -102,12 +106,17 @@ extern "C" int bppp_microbench(int device, double *out, int n_out) {
             case 3: ms = time_ms([&] { k_mb_op<3><<<opblocks, 64>>>(d32, 777u, iters); }); break;
             case 4: ms = time_ms([&] { k_mb_op<4><<<opblocks, 64>>>(d32, 777u, iters); }); break;
             case 5: ms = time_ms([&] { k_mb_op<5><<<opblocks, 64>>>(d32, 777u, iters); }); break;
-            default: ms = time_ms([&] { k_mb_op<6><<<opblocks, 64>>>(d32, 777u, iters); }); break;
+            case 6: ms = time_ms([&] { k_mb_op<6><<<opblocks, 64>>>(d32, 777u, iters); }); break;
+            case 7: ms = time_ms([&] { k_mb_op<7><<<opblocks, 64>>>(d32, 777u, iters); }); break;
+            case 8: ms = time_ms([&] { k_mb_op<8><<<opblocks, 64>>>(d32, 777u, iters); }); break;
+            case 9: ms = time_ms([&] { k_mb_op<9><<<opblocks, 64>>>(d32, 777u, iters); }); break;
+            default: ms = time_ms([&] { k_mb_op<10><<<opblocks, 64>>>(d32, 777u, iters); }); break;
         }
         return (double)opblocks * 64 * iters / (ms * 1e-3);
     };
     out[1] = run_op(1, 4000); out[2] = run_op(2, 4000); out[3] = run_op(3, 2000);
     out[4] = run_op(4, 400); out[5] = run_op(5, 400); out[6] = run_op(6, 400);
+    if (n_out >= 14) { out[10] = run_op(7, 20); out[11] = run_op(8, 20); out[12] = run_op(9, 20); out[13] = run_op(10, 20); }
     int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, device);
     out[7] = clk / 1000.0;
     cudaEventDestroy(e0); cudaEventDestroy(e1);

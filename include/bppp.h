@@ -312,7 +312,7 @@ int bppp_ctx_profile_end(bppp_ctx *ctx, char *names48, double *total_ms, uint32_
  *   [0] IMAD.WIDE.U32 multiply-accumulates/s   [1] fe_mul/s   [2] fe_sqr/s   [3] sc_mul/s
  *   [4] mixed point additions/s   [5] point doublings/s   [6] full point additions/s   [7] SM clock MHz seen
  * Used to state the integer roofline the path is bound by. */
-int bppp_microbench(int device, double *out, int n_out);   /* n_out >= 10 also fills [8] IMAD/s, [9] IADD/s */
+int bppp_microbench(int device, double *out, int n_out);   /* n_out >= 10 also fills [8] IMAD/s, [9] IADD/s; n_out >= 14: [10] fe_inv/s (safegcd), [11] fe_inv/s by a^(p-2), [12] sc_inv/s (safegcd), [13] sc_inv/s by a^(n-2) */
 
 #ifdef __cplusplus
 }
