@@ -50,6 +50,9 @@ struct bppp_ctx {
     int nsub_host = 4;              // host-buffer entry points: more, smaller sub-batches so that the first upload (3.3 KB of RNG bytes per proof for prove) is short
     cudaStream_t sub_stream[MAX_SUB] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
+    // host-buffer prove: the uploads run on their own stream in the order the phases need them (engine_prove.cu), one event per part and stage
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_up[2 * MAX_SUB] = {};
     uint64_t launches = 0;
     int sm_count = 148;
     // phase-stepped session (bppp_u64_{verify,prove}_begin .. _finish): one at a time per context, lives in the workspace

@@ -242,6 +242,8 @@ static int alloc_work(bppp_ctx *c, size_t max_batch) {
         CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
     }
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2 * bppp_ctx::MAX_SUB; k++) CUDA_OK(cudaEventCreateWithFlags(&c->ev_up[k], cudaEventDisableTiming));
     c->max_batch = max_batch;
     c->ws_words_per_proof = VL::WORDS > PL::WORDS ? VL::WORDS : PL::WORDS;
     c->ws_words_per_proof = (c->ws_words_per_proof + 3) & ~(size_t)3;      // sub-batch bases stay 16-byte aligned (vtab_entry)
@@ -327,6 +329,8 @@ extern "C" void bppp_ctx_destroy(bppp_ctx *c) {
         if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int k = 0; k < 2 * bppp_ctx::MAX_SUB; k++) if (c->ev_up[k]) cudaEventDestroy(c->ev_up[k]);
     delete c;
 }
 

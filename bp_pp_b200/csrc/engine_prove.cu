@@ -41,8 +41,10 @@ __global__ void __launch_bounds__(64) k_p_vprime(WS w) {
 }
 
 // ---- prove ----
+// rng_late: when set, the event after which the RNG bytes of the second transcript phase (scalars 19..51 of each record) are
+// in place -- the host-buffer entry point uploads them while the first-stage sums run
 static int prove_part(bppp_ctx *c, cudaStream_t st, WS w, const uint64_t *d_x, const uint8_t *d_blinds, const uint8_t *d_rng,
-                      const Merlin &init, uint8_t *d_proofs, int32_t *d_status) {
+                      const Merlin &init, uint8_t *d_proofs, int32_t *d_status, cudaEvent_t rng_late = nullptr) {
     const size_t n = w.n;
     const unsigned g64 = nblocks(n, 64);
     TermMap tm;
@@ -63,6 +65,7 @@ static int prove_part(bppp_ctx *c, cudaStream_t st, WS w, const uint64_t *d_x, c
         for (int k = 0; k < 5; k++) { int p = u64p_stage1_norm_point(k); L.in[k] = PL::PTS + PT_W * p + 2 * FE_W; L.out[k] = PL::ZINV + FE_W * p; }
         launch_batch_inv_list(c, st, w, L);
     }
+    if (rng_late) CUDA_OK(cudaStreamWaitEvent(st, rng_late, 0));
     LAUNCH(c, k_p_phase2, g64, 64, w, d_rng, (const uint8_t *)nullptr, 0);
     u64p_termmap_cs(tm.gen);
     launch_msm_fixed(c, st, w, PL::FS, tm, 42, PL::PTS + PT_W * PP_CS);
@@ -132,20 +135,37 @@ extern "C" int bppp_u64_prove_batch(bppp_ctx *c, size_t n, const uint64_t *x, co
     for (size_t off = 0; off < n; off += c->max_batch) {
         size_t m = n - off < c->max_batch ? n - off : c->max_batch;
         SubPlan sp = plan_sub(c, m, true);
+        // Uploads on their own stream, in the order the phases need them: x, blindings and the 19 scalars (1,216 bytes) of the first
+        // transcript phase for every part, then the 33 scalars (2,112 bytes) of the second phase, which arrive while the
+        // first-stage sums run.  A part starts after a third of its RNG bytes instead of all 3,328 per proof.
+        const size_t early = (size_t)U64_RNG_EARLY * 64, late = (size_t)U64_RNG_BYTES - early;
+        cudaStream_t cs = c->copy_stream;
+        for (int k = 0; k < sp.parts; k++) {
+            size_t lo = sp.lo[k], cnt = sp.lo[k + 1] - sp.lo[k];
+            CUDA_OK(cudaMemcpyAsync(c->d_in_a + 8 * lo, x + off + lo, 8 * cnt, cudaMemcpyHostToDevice, cs));
+            CUDA_OK(cudaMemcpyAsync(c->d_in_b + 32 * lo, blinds32 + 32 * (off + lo), 32 * cnt, cudaMemcpyHostToDevice, cs));
+            CUDA_OK(cudaMemcpy2DAsync(c->d_in_c + (size_t)U64_RNG_BYTES * lo, U64_RNG_BYTES, rng + (size_t)U64_RNG_BYTES * (off + lo), U64_RNG_BYTES,
+                                      early, cnt, cudaMemcpyHostToDevice, cs));
+            CUDA_OK(cudaEventRecord(c->ev_up[2 * k], cs));
+        }
+        for (int k = 0; k < sp.parts; k++) {
+            size_t lo = sp.lo[k], cnt = sp.lo[k + 1] - sp.lo[k];
+            CUDA_OK(cudaMemcpy2DAsync(c->d_in_c + (size_t)U64_RNG_BYTES * lo + early, U64_RNG_BYTES, rng + (size_t)U64_RNG_BYTES * (off + lo) + early,
+                                      U64_RNG_BYTES, late, cnt, cudaMemcpyHostToDevice, cs));
+            CUDA_OK(cudaEventRecord(c->ev_up[2 * k + 1], cs));
+        }
         for (int k = 0; k < sp.parts; k++) {
             cudaStream_t st = sp.parts == 1 ? c->stream : c->sub_stream[k];
             size_t lo = sp.lo[k], cnt = sp.lo[k + 1] - sp.lo[k];
-            CUDA_OK(cudaMemcpyAsync(c->d_in_a + 8 * lo, x + off + lo, 8 * cnt, cudaMemcpyHostToDevice, st));
-            CUDA_OK(cudaMemcpyAsync(c->d_in_b + 32 * lo, blinds32 + 32 * (off + lo), 32 * cnt, cudaMemcpyHostToDevice, st));
-            CUDA_OK(cudaMemcpyAsync(c->d_in_c + (size_t)U64_RNG_BYTES * lo, rng + (size_t)U64_RNG_BYTES * (off + lo), (size_t)U64_RNG_BYTES * cnt,
-                                    cudaMemcpyHostToDevice, st));
+            CUDA_OK(cudaStreamWaitEvent(st, c->ev_up[2 * k], 0));
             int rc = prove_part(c, st, sub_ws(c, sp, k), (const uint64_t *)c->d_in_a + lo, c->d_in_b + 32 * lo, c->d_in_c + (size_t)U64_RNG_BYTES * lo,
-                                init, c->d_out + (size_t)U64_PROOF_BYTES_COMPRESSED * lo, c->d_status + lo);
-            if (rc != BPPP_OK) return rc;
+                                init, c->d_out + (size_t)U64_PROOF_BYTES_COMPRESSED * lo, c->d_status + lo, c->ev_up[2 * k + 1]);
+            if (rc != BPPP_OK) { cudaStreamSynchronize(cs); return rc; }
             CUDA_OK(cudaMemcpyAsync(proofs_out + (size_t)U64_PROOF_BYTES_COMPRESSED * (off + lo), c->d_out + (size_t)U64_PROOF_BYTES_COMPRESSED * lo,
                                     (size_t)U64_PROOF_BYTES_COMPRESSED * cnt, cudaMemcpyDeviceToHost, st));
             CUDA_OK(cudaMemcpyAsync(status + off + lo, c->d_status + lo, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, st));
         }
+        CUDA_OK(cudaStreamSynchronize(cs));
         for (int k = 0; k < sp.parts; k++) CUDA_OK(cudaStreamSynchronize(sp.parts == 1 ? c->stream : c->sub_stream[k]));
     }
     return BPPP_OK;

@@ -17,6 +17,7 @@
 namespace bppp {
 
 static constexpr int U64_RNG_BYTES = 52 * 64;
+static constexpr int U64_RNG_EARLY = 19;     // scalars drawn by the first transcript phase (u64p_phase1_one); the other 33 by the second
 
 // prover point slots (projective in PL::PTS, 1/Z in PL::ZINV)
 enum { PP_V = 0, PP_RCOM = 1, PP_CO = 2, PP_CL = 3, PP_CR = 4, PP_VP = 5, PP_CS = 6, PP_X = 7 /*X_0..X_3*/, PP_R = 11 /*R_0..R_3*/, PP_COM = 15, PP_COUNT = 16 };
@@ -163,7 +164,7 @@ BPPP_HD void u64p_phase1_one(const WS &w, size_t i, const Merlin &init, const ui
     for (int j = 15; j >= 0; j--) { Sc t = sc_mul(rinv, pre[j]); rinv = sc_mul(rinv, inv[j]); inv[j] = t; ws_st_sc(w, i, PL::INVE + 8 * j, t); }
     // draws 1..19 (reciprocal.rs:121; circuit.rs:264-298)
 #pragma unroll 1
-    for (int k = 0; k < 19; k++) ws_st_sc(w, i, PL::RND + 8 * k, sc_from_wide_be64(rng + 64 * k));
+    for (int k = 0; k < U64_RNG_EARLY; k++) ws_st_sc(w, i, PL::RND + 8 * k, sc_from_wide_be64(rng + 64 * k));
     uint64_t x = u64p_ld_x(w, i);
     // r_com scalars: [r_blind, r_0..r_15]
     int o = PL::FS;
@@ -231,7 +232,7 @@ BPPP_HD void u64p_phase2_one(const WS &w, size_t i, const uint8_t *rng, const ui
     tx_store(m, w, i, PL::MERLIN);
     // draws 20..52: ls (17), ns (16)   (circuit.rs:371-372)
 #pragma unroll 1
-    for (int k = 19; k < 52; k++) ws_st_sc(w, i, PL::RND + 8 * k, sc_from_wide_be64(rng + 64 * k));
+    for (int k = U64_RNG_EARLY; k < 52; k++) ws_st_sc(w, i, PL::RND + 8 * k, sc_from_wide_be64(rng + 64 * k));
     // inverses of rho and beta with one inversion; mu^-1 = rho^-2 (util.rs:119 inverts mu; circuit.rs:403,455 delta, beta)
     Sc mu = sc_sqr(rho);
     zero_inv |= sc_is_zero(rho) | sc_is_zero(beta) | sc_is_zero(delta);
