@@ -47,7 +47,8 @@ struct bppp_ctx {
     // so that tail waves and low-parallelism kernels of one sub-batch overlap with work of the others
     static constexpr int MAX_SUB = 8;
     int nsub = 2;
-    int nsub_host = 4;              // host-buffer entry points: more, smaller sub-batches so that the first upload (3.3 KB of RNG bytes per proof for prove) is short
+    int nsub_host = 4;              // host-buffer entry points: more, smaller sub-batches so that the first upload is short
+    int nsub_host_prove = 2;        // host-buffer prove: its uploads are staged by phase (engine_prove.cu), two parts keep the kernels efficient
     cudaStream_t sub_stream[MAX_SUB] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
     // host-buffer prove: the uploads run on their own stream in the order the phases need them (engine_prove.cu), one event per part and stage
@@ -122,7 +123,8 @@ static inline TermMap identity_map() { TermMap tm; for (int t = 0; t < NUM_GENS;
 // sub-batch plan for a slice of n proofs: part k covers [lo[k], lo[k+1]) and owns workspace words starting at
 // d_ws + words_per_proof * lo[k] with row stride (lo[k+1] - lo[k])
 struct SubPlan { int parts; size_t lo[bppp_ctx::MAX_SUB + 1]; };
-SubPlan plan_sub(bppp_ctx *c, size_t n, bool host_buffers = false);     // also records the number of concurrent parts in c->active_parts
+enum { SUB_DEVICE = 0, SUB_HOST = 1, SUB_HOST_PROVE = 2 };
+SubPlan plan_sub(bppp_ctx *c, size_t n, int kind = SUB_DEVICE);     // also records the number of concurrent parts in c->active_parts
 int fork_streams(bppp_ctx *c, cudaStream_t caller, const SubPlan &sp);
 int join_streams(bppp_ctx *c, cudaStream_t caller, const SubPlan &sp);
 static inline WS sub_ws(const bppp_ctx *c, const SubPlan &sp, int k) {

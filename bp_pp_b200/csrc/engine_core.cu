@@ -128,9 +128,9 @@ __global__ void __launch_bounds__(128) k_tab_write(WS tmp, uint4 *dst) {
 static constexpr int MSM_LANES = BPPP_MSM_LANES;
 
 namespace bppp {
-SubPlan plan_sub(bppp_ctx *c, size_t n, bool host_buffers) {
+SubPlan plan_sub(bppp_ctx *c, size_t n, int kind) {
     SubPlan sp;
-    int parts = c->profiling ? 1 : (host_buffers ? c->nsub_host : c->nsub);          // per-kernel timing wants kernels back to back on one stream
+    int parts = c->profiling ? 1 : (kind == SUB_HOST ? c->nsub_host : kind == SUB_HOST_PROVE ? c->nsub_host_prove : c->nsub);          // per-kernel timing wants kernels back to back on one stream
     const size_t min_part = 2048;                    // below this a sub-batch cannot fill the GPU anyway
     while (parts > 1 && n / parts < min_part) parts--;
     sp.parts = parts;
@@ -230,6 +230,7 @@ static int alloc_work(bppp_ctx *c, size_t max_batch) {
     CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     if (const char *e = getenv("BPPP_NSUB")) { int v = atoi(e); if (v >= 1 && v <= bppp_ctx::MAX_SUB) c->nsub = v; }
     if (const char *e = getenv("BPPP_NSUB_HOST")) { int v = atoi(e); if (v >= 1 && v <= bppp_ctx::MAX_SUB) c->nsub_host = v; }
+    if (const char *e = getenv("BPPP_NSUB_HOST_PROVE")) { int v = atoi(e); if (v >= 1 && v <= bppp_ctx::MAX_SUB) c->nsub_host_prove = v; }
     if (const char *e = getenv("BPPP_TAB_AFFINE")) c->tab_affine = atoi(e) != 0;
     if (const char *e = getenv("BPPP_TAB_K")) {     // "k1,k2,k3": items per thread (= per inversion) of the three levels
         int a = 0, b = 0, d = 0;

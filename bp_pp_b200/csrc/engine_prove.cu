@@ -134,7 +134,7 @@ extern "C" int bppp_u64_prove_batch(bppp_ctx *c, size_t n, const uint64_t *x, co
     Merlin init; merlin_init(init, label, (uint32_t)label_len);
     for (size_t off = 0; off < n; off += c->max_batch) {
         size_t m = n - off < c->max_batch ? n - off : c->max_batch;
-        SubPlan sp = plan_sub(c, m, true);
+        SubPlan sp = plan_sub(c, m, SUB_HOST_PROVE);
         // Uploads on their own stream, in the order the phases need them: x, blindings and the 19 scalars (1,216 bytes) of the first
         // transcript phase for every part, then the 33 scalars (2,112 bytes) of the second phase, which arrive while the
         // first-stage sums run.  A part starts after a third of its RNG bytes instead of all 3,328 per proof.

@@ -151,7 +151,7 @@ extern "C" int bppp_u64_verify_batch(bppp_ctx *c, size_t n, const uint8_t *commi
     // sub-batch overlap with the kernels of the others (pinned host buffers make the copies truly asynchronous)
     for (size_t off = 0; off < n; off += c->max_batch) {
         size_t m = n - off < c->max_batch ? n - off : c->max_batch;
-        SubPlan sp = plan_sub(c, m, true);
+        SubPlan sp = plan_sub(c, m, SUB_HOST);
         for (int k = 0; k < sp.parts; k++) {
             cudaStream_t st = sp.parts == 1 ? c->stream : c->sub_stream[k];
             size_t lo = sp.lo[k], cnt = sp.lo[k + 1] - sp.lo[k];
