@@ -62,6 +62,9 @@ struct bppp_ctx {
     int inflight_hint = 1;          // bppp_ctx_set_inflight: independent batches the caller keeps in flight on sibling contexts           // sub-batches of the slice in flight (they run concurrently: lane choices look at their sum)
     // ladder tables (u64_verify.cuh:tables_affine_level): affine levels; items per thread (= per inversion) by level when forced (BPPP_TAB_K)
     int tab_affine = 1, tab_k[3] = {0, 0, 0};
+    int var_seg = 16;               // segments the verifier's one-thread ladders are cut into (engine_var.cu:k_v_var_seg); 1 = whole ladders
+    int var_seg_one_item = 1;       // one block per work item (0: persistent warps -- measured slower, kept for experiments)
+    int var_seg_warps = 0;          // > 0: warps per segmented launch (experiments); default = the launch's share of the warp slots
     int msm_lanes_override = 0, var_lanes_override = 0;   // BPPP_MSM_LANES_RT / BPPP_VAR_LANES_RT (experiments)
     // optional per-launch timing (bppp_ctx_profile_begin/end): CUDA events on the launching stream
     bool profiling = false;
@@ -106,15 +109,21 @@ __device__ __forceinline__ Pt lanes_reduce(Pt acc) {
 }
 #endif
 
-// threads of one affine table level over `items` (operation, point, proof) items: about 180 per SM and concurrent sub-batch
+// threads of one affine table level over `items` (operation, point, proof) items: about 360 per SM over the concurrent sub-batches
 // (B200 sweep, profiles/r2_kernel_experiments.txt #13: 16 / 32 / 64 items per inversion at 32,768 proofs per sub-batch,
 // 4 / 8 / 16 at 8,192, 1 / 2 / 4 at 1,024), never more than 64 items per thread
 static inline size_t tab_level_threads(const bppp_ctx *c, size_t items, int level) {
     if (c->tab_k[level - 1] > 0) return (items + c->tab_k[level - 1] - 1) / c->tab_k[level - 1];
-    const int parts = c->active_parts > 2 ? c->active_parts : 2;
+    const int parts = c->active_parts > 1 ? c->active_parts : 1;
     size_t t = (size_t)c->sm_count * 360 / (size_t)parts, lo = (items + 63) / 64;
     if (t < lo) t = lo;
     return t < items ? t : (items ? items : 1);
+}
+
+// A verification batch this large runs as ONE part with segmented ladders (engine_var.cu:k_v_var_seg) instead of two
+// sub-batches with whole ladders: 21.4 against 22.4 ms at 65,536 proofs (profiles/r2_kernel_experiments.txt #22).
+static inline bool verify_one_part(const bppp_ctx *c, size_t n) {
+    return c->var_seg > 1 && c->inflight_hint == 1 && !c->var_lanes_override && n >= 24576;
 }
 
 static inline TermMap identity_map() { TermMap tm; for (int t = 0; t < NUM_GENS; t++) tm.gen[t] = t; return tm; }

@@ -236,6 +236,9 @@ static int alloc_work(bppp_ctx *c, size_t max_batch) {
         int a = 0, b = 0, d = 0;
         if (sscanf(e, "%d,%d,%d", &a, &b, &d) == 3 && a >= 1 && b >= 1 && d >= 1) { c->tab_k[0] = a; c->tab_k[1] = b; c->tab_k[2] = d; }
     }
+    if (const char *e = getenv("BPPP_VAR_SEG")) { int v = atoi(e); if (v >= 1 && v <= 33) c->var_seg = v; }
+    if (const char *e = getenv("BPPP_VAR_SEG_ONE")) c->var_seg_one_item = atoi(e) != 0;
+    if (const char *e = getenv("BPPP_VAR_SEG_WARPS")) { int v = atoi(e); if (v >= 1) c->var_seg_warps = v; }
     if (const char *e = getenv("BPPP_MSM_LANES_RT")) { int v = atoi(e); if (v == 4 || v == 8 || v == 16) c->msm_lanes_override = v; }
     if (const char *e = getenv("BPPP_VAR_LANES_RT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->var_lanes_override = v; }
     for (int k = 0; k < bppp_ctx::MAX_SUB; k++) {

@@ -40,6 +40,48 @@ __global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_p_var2(W
     if (i < w.n) u64p_var2_one(w, i, j);
 }
 #endif
+// The verifier's ladders in segments (u64_verify.cuh:straus_tables_seg), persistent warps.  Work items are (segment, 32-proof
+// chain) pairs in segment-major order; a warp draws a ticket, waits until the chain's previous segment has been published,
+// continues the chain from the scratch rows, publishes its own segment and draws again.  The ticket order makes the wait
+// safe: the previous segment's ticket was drawn earlier by a warp that is running (or done).  The grid is this launch's share
+// of the GPU's warp slots, a little more than it has chains, so a chain continues on whichever warp frees first instead of
+// staying on the scheduler it started on, and concurrent sub-batches do not crowd each other out with waiting blocks.
+// sync: [0] ticket counter, [1] set if a wait ever timed out (~1 s; never in a correct run), [32 + g] segments done of chain g.
+template <int KIND>     // 0: five-point group (COM = ACC + ...), 1: two-point group of round j
+__global__ void __launch_bounds__(32, 16) k_v_var_seg(WS w, int j, int nseg, uint32_t *sync, int one_item) {
+    const unsigned lane = threadIdx.x;
+    const unsigned nchains = (unsigned)((w.n + 31) / 32), total = nchains * (unsigned)nseg;
+#pragma unroll 1
+    for (;;) {
+        unsigned ticket = 0;
+        if (lane == 0) ticket = atomicAdd(sync, 1u);
+        ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+        if (ticket >= total) return;
+        const unsigned seg = ticket / nchains, g = ticket - seg * nchains;
+        volatile uint32_t *done = sync + 32 + g;
+        const size_t i = (size_t)g * 32 + lane;
+        if (seg) {
+            unsigned spins = 0;
+            while (*done < seg) {
+                __nanosleep(100);
+                if (++spins > (1u << 23)) {                       // fail loudly instead of hanging the GPU
+                    sync[1] = 1u;
+                    if (i < w.n) ws_st(w, i, VL::STATUS, (uint32_t)ST_BAD_ARG);
+                    return;
+                }
+            }
+            __threadfence();
+        }
+        if (i < w.n) {
+            if (KIND == 0) u64v_var5_seg(w, i, (int)seg, nseg);
+            else u64v_var2_seg(w, i, j, (int)seg, nseg);
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) *done = seg + 1;
+        if (one_item) return;
+    }
+}
 // The same ladders with LANES adjacent threads per proof (straus_tables_partial): the GLV halves are shared out, every lane
 // repeats the doublings, the partial sums meet through warp shuffles.  More total work, a shorter dependent chain and
 // LANES times the warps: selected when the (sub-)batch alone leaves most of the GPU idle.
@@ -102,15 +144,35 @@ static int var_lanes_for(const bppp_ctx *c, size_t n) {
     if (n * 4 <= full) return 2;
     return 1;
 }
+// segmented ladders: where one thread per proof is chosen, the launch has the GPU to itself (a single part, no sibling batches
+// in flight: two such launches side by side crowd each other out with waiting blocks) and is large enough to matter
+static bool var_segments(const bppp_ctx *c, size_t n) { return verify_one_part(c, n) && c->active_parts == 1; }
+// warps of one segmented launch: its share of the 16 warp slots per SM (the sub-batches of a call and the caller's batches in
+// flight run side by side), never more than it has work items
+static unsigned var_seg_grid(const bppp_ctx *c, size_t n) {
+    const size_t items = ((n + 31) / 32) * (size_t)c->var_seg;
+    size_t share = (size_t)c->sm_count * 16 / ((size_t)c->active_parts * (size_t)c->inflight_hint);
+    if (c->var_seg_warps > 0) share = (size_t)c->var_seg_warps;
+    if (c->var_seg_one_item) return (unsigned)items;
+    if (share < 64) share = 64;
+    return (unsigned)(items < share ? items : share);
+}
+static uint32_t *var_seg_sync(cudaStream_t st, WS w) {
+    uint32_t *sync = w.p + (size_t)(VL::TAB + LS_SYNC) * w.n;
+    cudaMemsetAsync(sync, 0, sizeof(uint32_t) * (32 + (w.n + 31) / 32), st);
+    return sync;
+}
 void launch_v_var5(bppp_ctx *c, cudaStream_t st, WS w) {
     const int lanes = var_lanes_for(c, w.n);
-    if (lanes == 1) LAUNCH(c, k_v_var5, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w);
+    if (lanes == 1 && var_segments(c, w.n)) LAUNCH(c, k_v_var_seg<0>, var_seg_grid(c, w.n), 32, w, 0, c->var_seg, var_seg_sync(st, w), c->var_seg_one_item);
+    else if (lanes == 1) LAUNCH(c, k_v_var5, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w);
     else if (lanes == 2) LAUNCH(c, k_v_var5_lanes<2>, nblocks(w.n * 2, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w);
     else launch_v_var5_lat(c, st, w);
 }
 void launch_v_var2(bppp_ctx *c, cudaStream_t st, WS w, int j) {
     const int lanes = var_lanes_for(c, w.n);
-    if (lanes == 1) LAUNCH(c, k_v_var2, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
+    if (lanes == 1 && var_segments(c, w.n)) LAUNCH(c, k_v_var_seg<1>, var_seg_grid(c, w.n), 32, w, j, c->var_seg, var_seg_sync(st, w), c->var_seg_one_item);
+    else if (lanes == 1) LAUNCH(c, k_v_var2, nblocks(w.n, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
     else if (lanes == 2) LAUNCH(c, k_v_var2_lanes<2>, nblocks(w.n * 2, BPPP_VAR_BLOCK), BPPP_VAR_BLOCK, w, j);
     else launch_v_var2_lat(c, st, w, j);
 }

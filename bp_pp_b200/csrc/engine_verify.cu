@@ -111,6 +111,7 @@ static int verify_slice(bppp_ctx *c, cudaStream_t st, size_t n, const uint8_t *d
                         const Merlin &init, int32_t *d_status) {
     const size_t csz = fmt == FMT_COMPRESSED ? 33 : 64, psz = fmt == FMT_COMPRESSED ? U64_PROOF_BYTES_COMPRESSED : U64_PROOF_BYTES_AFFINE;
     SubPlan sp = plan_sub(c, n);
+    if (verify_one_part(c, n)) { sp.parts = 1; sp.lo[0] = 0; sp.lo[1] = n; c->active_parts = 1; }
     int rc = fork_streams(c, st, sp);
     if (rc != BPPP_OK) return rc;
     for (int k = 0; k < sp.parts; k++) {
@@ -152,6 +153,7 @@ extern "C" int bppp_u64_verify_batch(bppp_ctx *c, size_t n, const uint8_t *commi
     for (size_t off = 0; off < n; off += c->max_batch) {
         size_t m = n - off < c->max_batch ? n - off : c->max_batch;
         SubPlan sp = plan_sub(c, m, SUB_HOST);
+        if (verify_one_part(c, m)) { sp.parts = 1; sp.lo[0] = 0; sp.lo[1] = m; c->active_parts = 1; }
         for (int k = 0; k < sp.parts; k++) {
             cudaStream_t st = sp.parts == 1 ? c->stream : c->sub_stream[k];
             size_t lo = sp.lo[k], cnt = sp.lo[k + 1] - sp.lo[k];

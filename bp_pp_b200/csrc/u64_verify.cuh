@@ -500,6 +500,112 @@ BPPP_HD Pt u64v_var2_partial(const WS &w, size_t i, int j, int lane, int nlanes)
     return ptj_to_pt(straus_tables_partial<2>(w, vtab_region(), i, tids, ks, lane, nlanes));
 }
 
+// ---- the same ladders cut into SEGMENTS of consecutive windows (engine_var.cu:k_v_var_seg) ----
+// A 65,536-proof batch is 2,048 one-warp ladders on 2,368 warp slots: the schedulers that received four of them finish a fifth
+// later than those with three, which then idle.  Cut into segments that any warp may continue (state handed over through the
+// free build rows of the table region), the ladders are re-dealt to whichever slot frees first and the SMs finish together.
+// Scratch rows (word-major, relative to the region's build area): accumulator X Y Z + infinity flag, the GLV halves of the
+// group's scalars (so that the split runs once), one row of synchronisation words.
+static constexpr int LS_ACC = 0, LS_INF = 24, LS_NEG = 25, LS_GLV = 32, LS_SYNC = 80;
+BPPP_HD uint32_t ls_ld(const WS &w, size_t i, int row) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(w.p + (size_t)row * w.n + i);         // written by another SM a moment ago: read past the L1
+#else
+    return w.p[(size_t)row * w.n + i];
+#endif
+}
+BPPP_HD void ls_st(const WS &w, size_t i, int row, uint32_t v) { w.p[(size_t)row * w.n + i] = v; }
+// windows d_hi .. d_lo (inclusive, descending) of the joint ladder over 2 NP half-scalars; same steps as straus_tables_partial
+template <int NP>
+BPPP_HD PtJ straus_tables_windows(const WS &w, const TabRegion &R, size_t i, const int *tids, const Digits4h *dg, const bool *neg, PtJ acc, int d_hi, int d_lo) {
+#pragma unroll 1
+    for (int d = d_hi; d >= d_lo; d--) {
+        if (d != 32) {
+#pragma unroll 1
+            for (int r = 0; r < 4; r++) acc = ptj_double_hot(acc);
+        }
+#pragma unroll 1
+        for (int h = 0; h < 2 * NP; h++) {
+            int sd = digits4h_get(dg[h], d);
+            if (neg[h]) sd = -sd;
+            if (sd == 0) continue;
+            int a = sd < 0 ? -sd : sd;
+            const uint32_t *ent = tab_entry(w, R, i, tids[h >> 1] * 8 + (a - 1));
+            PtA q;
+            q.x = vtab_ld_fe(ent + ((h & 1) ? 2 * FE_W : 0));
+            q.y = vtab_ld_fe(ent + FE_W);
+            if (fe_is_zero_canonical(q.x) && fe_is_zero_canonical(q.y)) continue;
+            if (sd < 0) q.y = fe_normalize_weak(fe_negate(q.y, 1));
+            acc = ptj_add_mixed_hot(acc, q);
+        }
+    }
+    return acc;
+}
+// segment `seg` of `nseg`: the 33 windows are dealt top-down in runs of 33 / nseg (+1).  Returns true when acc is the finished
+// sum (last segment); otherwise acc has been parked in the scratch rows.  ks is read by segment 0 only.
+template <int NP>
+BPPP_HD bool straus_tables_seg(const WS &w, const TabRegion &R, size_t i, const int *tids, const Sc *ks, int seg, int nseg, PtJ &acc) {
+    Digits4h dg[2 * NP];
+    bool neg[2 * NP];
+    const int sb = R.tab;
+    if (seg == 0) {
+        uint32_t negmask = 0;
+#pragma unroll 1
+        for (int k = 0; k < NP; k++) {
+            GlvSplit g = glv_split(ks[k]);
+            dg[2 * k] = half_signed_digits4(g.k1); neg[2 * k] = g.neg1;
+            dg[2 * k + 1] = half_signed_digits4(g.k2); neg[2 * k + 1] = g.neg2;
+            negmask |= (g.neg1 ? 1u : 0u) << (2 * k) | (g.neg2 ? 1u : 0u) << (2 * k + 1);
+            if (nseg > 1) {
+#pragma unroll
+                for (int t = 0; t < 4; t++) { ls_st(w, i, sb + LS_GLV + 8 * k + t, g.k1[t]); ls_st(w, i, sb + LS_GLV + 8 * k + 4 + t, g.k2[t]); }
+            }
+        }
+        if (nseg > 1) ls_st(w, i, sb + LS_NEG, negmask);
+        acc = ptj_identity();
+    } else {
+        const uint32_t negmask = ls_ld(w, i, sb + LS_NEG);
+#pragma unroll 1
+        for (int h = 0; h < 2 * NP; h++) {
+            uint32_t m[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) m[t] = ls_ld(w, i, sb + LS_GLV + 4 * h + t);
+            dg[h] = half_signed_digits4(m); neg[h] = (negmask >> h) & 1u;
+        }
+#pragma unroll
+        for (int t = 0; t < FE_W; t++) {
+            acc.x.v[t] = ls_ld(w, i, sb + LS_ACC + t); acc.y.v[t] = ls_ld(w, i, sb + LS_ACC + FE_W + t); acc.z.v[t] = ls_ld(w, i, sb + LS_ACC + 2 * FE_W + t);
+        }
+        acc.inf = ls_ld(w, i, sb + LS_INF) != 0;
+    }
+    const int hi = 32 - (33 * seg) / nseg, lo = 32 - (33 * (seg + 1)) / nseg + 1;
+    acc = straus_tables_windows<NP>(w, R, i, tids, dg, neg, acc, hi, lo);
+    if (seg + 1 == nseg) return true;
+#pragma unroll
+    for (int t = 0; t < FE_W; t++) {
+        ls_st(w, i, sb + LS_ACC + t, acc.x.v[t]); ls_st(w, i, sb + LS_ACC + FE_W + t, acc.y.v[t]); ls_st(w, i, sb + LS_ACC + 2 * FE_W + t, acc.z.v[t]);
+    }
+    ls_st(w, i, sb + LS_INF, acc.inf ? 1u : 0u);
+    return false;
+}
+BPPP_HD void u64v_var5_seg(const WS &w, size_t i, int seg, int nseg) {
+    const int tids[5] = {vtab_of_slot(VP_CS), vtab_of_slot(VP_CO), vtab_of_slot(VP_CL), vtab_of_slot(VP_CR), VTAB_VP};
+    Sc ks[5];
+    if (seg == 0) {
+#pragma unroll 1
+        for (int k = 0; k < 5; k++) ks[k] = ws_ld_sc(w, i, VL::VS + 8 * k);
+    }
+    PtJ acc;
+    if (straus_tables_seg<5>(w, vtab_region(), i, tids, ks, seg, nseg, acc)) ws_st_pt(w, i, VL::COM, pt_add(ptj_to_pt(acc), ws_ld_pt(w, i, VL::ACC)));
+}
+BPPP_HD void u64v_var2_seg(const WS &w, size_t i, int j, int seg, int nseg) {
+    const int tids[2] = {vtab_of_slot(VP_X + (3 - j)), vtab_of_slot(VP_R + (3 - j))};
+    Sc ks[2];
+    if (seg == 0) { ks[0] = ws_ld_sc(w, i, VL::VS); ks[1] = ws_ld_sc(w, i, VL::VS + 8); }
+    PtJ acc;
+    if (straus_tables_seg<2>(w, vtab_region(), i, tids, ks, seg, nseg, acc)) ws_st_pt(w, i, VL::COM, pt_add(ptj_to_pt(acc), ws_ld_pt(w, i, VL::COM)));
+}
+
 // Base case (wnla.rs:80-82): scalars of commit(l, n) over the ORIGINAL generators.  After 4 folds
 //   h^(4)_s = sum_t (prod_k y_k^bit_k(t)) h_{16 s + t},  g^(4)_0 = sum_t (prod_k (bit_k(t) ? y_k : rho_k)) g_t
 // with rho_0 = rho, rho_{k+1} = mu_k, mu_{k+1} = mu_k^2 (wnla.rs:96-97,108-109).

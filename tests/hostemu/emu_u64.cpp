@@ -18,8 +18,11 @@ struct EmuCtx {
 
 static int g_tab_affine = 1;      // ladder tables: 1 = affine levels (tables_affine_level), 0 = projective build + normalise
 
+static int g_var_seg = 0;         // > 0: the verifier's ladders run as that many segments through the scratch rows (u64v_var*_seg)
+
 extern "C" {
 void emu_set_tab_affine(int on) { g_tab_affine = on; }
+void emu_set_var_segments(int nseg) { g_var_seg = nseg; }
 void *emu_ctx_create(const uint8_t *gens64, int W) {
     EmuCtx *c = new EmuCtx();
     bool sgn = W < 0;                          // negative: signed windows of |W| bits (ws.cuh:FixedTable)
@@ -88,11 +91,13 @@ int emu_u64_verify_batch(void *ctx, size_t n, const uint8_t *commits, const uint
     }
     int tg17[17]; for (int t = 0; t < 17; t++) tg17[t] = t;
     emu_msm_fixed(c, w, n, VL::FS, tg17, 17, VL::ACC, 8);
-    for (size_t i = 0; i < n; i++) u64v_var5_one(w, i);
+    if (g_var_seg > 0) { for (int sg = 0; sg < g_var_seg; sg++) for (size_t i = 0; i < n; i++) u64v_var5_seg(w, i, sg, g_var_seg); }
+    else for (size_t i = 0; i < n; i++) u64v_var5_one(w, i);
     for (int j = 0; j < 4; j++) {
         emu_batch_inv(w, n, VL::COM + 2 * FE_W, VL::ZINV);
         for (size_t i = 0; i < n; i++) u64v_round_one(w, i, j);
-        for (size_t i = 0; i < n; i++) u64v_var2_one(w, i, j);
+        if (g_var_seg > 0) { for (int sg = 0; sg < g_var_seg; sg++) for (size_t i = 0; i < n; i++) u64v_var2_seg(w, i, j, sg, g_var_seg); }
+        else for (size_t i = 0; i < n; i++) u64v_var2_one(w, i, j);
     }
     for (size_t i = 0; i < n; i++) u64v_final_scalars_one(w, i);
     int tg49[49]; for (int t = 0; t < 49; t++) tg49[t] = t;

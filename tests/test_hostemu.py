@@ -329,6 +329,30 @@ def test_affine_ladder_tables_equal_the_projective_construction(emu_u64, ref, or
     assert all(any(a[(0 * 104 + e) * 24:(0 * 104 + e) * 24 + 16]) for e in range(104))
 
 
+@pytest.mark.parametrize("nseg", [1, 3, 4, 7, 33])
+def test_segmented_ladders_match_the_oracle(emu_u64, ref, oracle, gens64, nseg):
+    """u64v_var5_seg / u64v_var2_seg: the ladders cut into nseg runs of windows with the accumulator and the GLV halves parked
+    in the scratch rows between runs (what k_v_var_seg does on the GPU) -- verdicts on honest and tampered records as the oracle's."""
+    n = 5
+    xs, blinds, rngs = synth_batch(ref, n, start=30)
+    proofs, st = oracle.u64_prove_batch(gens64, xs, blinds, rngs, LABEL, 4)
+    commits = b"".join(oracle.u64_commit(gens64, xs[i], blinds[32 * i:32 * i + 32]) for i in range(n))
+    bad = bytearray(proofs)
+    bad[525 * 1 + 33 * 6:525 * 1 + 33 * 7] = bytes(33)                                   # r[2] = identity
+    bad[525 * 2 + 33 * 8:525 * 2 + 33 * 9] = bad[525 * 2 + 33 * 4:525 * 2 + 33 * 5]      # x[0] = r[0]
+    bad[525 * 3 + 430] ^= 2                                                               # l[1] tampered
+    ctx = _emu_ctx(emu_u64, gens64)
+    status = (C.c_int32 * n)()
+    emu_u64.emu_set_var_segments(nseg)
+    try:
+        emu_u64.emu_u64_verify_batch(ctx, C.c_size_t(n), B(commits), B(bytes(bad)), 0, B(LABEL), len(LABEL), status)
+    finally:
+        emu_u64.emu_set_var_segments(0)
+    assert list(status) == oracle.u64_verify_batch(gens64, commits, bytes(bad), LABEL, 4)
+    assert status[0] == 1 and status[4] == 1 and status[3] == 0
+    emu_u64.emu_ctx_destroy(ctx)
+
+
 @pytest.mark.parametrize("tab_affine", [0, 1])
 def test_device_verify_logic_with_either_table_construction(emu_u64, ref, oracle, gens64, tab_affine):
     n = 4
