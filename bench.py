@@ -447,9 +447,9 @@ def make_roofline(metric, prof, n, W, peak, peaks, step_ms):
         wmac = n * msm_fixed_wmac(terms, W)               # all launches of the step together (k_msm_fixed<4> only when lanes differ)
         if metric == "prove":
             wmac *= dom_ms / sum(ms for k, (ms, _) in prof.items() if k.startswith("k_msm_fixed"))
-    elif name.startswith("k_v_var2") or name.startswith("k_p_var2"):
-        wmac = n * dom_cnt * straus_wmac(2)
-    elif name.startswith("k_v_var5"):
+    elif name.startswith("k_v_var2") or name.startswith("k_p_var2") or name.startswith("k_v_var_seg<1>"):
+        wmac = n * dom_cnt * straus_wmac(2)               # k_v_var_seg<1>: the same two-point ladder, run in segments
+    elif name.startswith("k_v_var5") or name.startswith("k_v_var_seg<0>"):
         wmac = n * straus_wmac(5)
     else:
         wmac = 0.0
