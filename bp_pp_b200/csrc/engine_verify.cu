@@ -8,9 +8,10 @@ static int fail(int code, const std::string &msg) { return engine_fail(code, msg
 
 // phase 0a: one thread per (point, proof), point-major.
 // flags[i]: bits 0..13 identity mask, bit 31 = a point failed to decode (merged with atomicOr)
-__global__ void __launch_bounds__(128) k_v_decode(WS w, const uint8_t *commits, const uint8_t *proofs, int fmt, uint32_t *flags) {
+__global__ void __launch_bounds__(128) k_v_decode(WS w, const uint8_t *commits, const uint8_t *proofs, int fmt, uint32_t *flags, size_t lo, size_t cnt) {
+    // proofs lo .. lo + cnt of the part (the host-buffer entry point decodes a part chunk by chunk while the next chunk uploads)
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int k = (int)(t / w.n); size_t i = t - (size_t)k * w.n;       // point-major: coalesced stores of the decoded words
+    int k = (int)(t / cnt); size_t i = lo + (t - (size_t)k * cnt);       // point-major: coalesced stores of the decoded words
     if (k >= VP_COUNT) return;
     size_t csz = fmt == FMT_COMPRESSED ? 33 : 64, psz = fmt == FMT_COMPRESSED ? U64_PROOF_BYTES_COMPRESSED : U64_PROOF_BYTES_AFFINE;
     uint32_t bit; bool bad;
@@ -80,14 +81,17 @@ static int launch_v_tables(bppp_ctx *c, cudaStream_t st, WS w) {
 }
 
 // ---- verify ----
+// decoded: the caller has already run k_v_decode over the whole part (chunk by chunk, bppp_u64_verify_batch)
 static int verify_part(bppp_ctx *c, cudaStream_t st, WS w, const uint8_t *d_commits, const uint8_t *d_proofs, int fmt,
-                       const Merlin &init, int32_t *d_status) {
+                       const Merlin &init, int32_t *d_status, bool decoded = false) {
     const size_t n = w.n;
     const unsigned g64 = nblocks(n, 64);
     // decode flags live in the workspace's IDMASK row until k_v_load_finish rewrites it
     uint32_t *flags = w.p + (size_t)VL::IDMASK * w.n;
-    CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n, st));
-    LAUNCH(c, k_v_decode, nblocks(n * VP_COUNT, 128), 128, w, d_commits, d_proofs, fmt, flags);
+    if (!decoded) {
+        CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n, st));
+        LAUNCH(c, k_v_decode, nblocks(n * VP_COUNT, 128), 128, w, d_commits, d_proofs, fmt, flags, (size_t)0, n);
+    }
     LAUNCH(c, k_v_load_finish, g64, 64, w, d_proofs, fmt, flags);
     launch_batch_inv(c, st, w, VL::VP + 2 * FE_W, VL::ZINV);
     LAUNCH(c, k_v_phase1, g64, 64, w, init, (const uint8_t *)nullptr, 0);
@@ -153,7 +157,31 @@ extern "C" int bppp_u64_verify_batch(bppp_ctx *c, size_t n, const uint8_t *commi
     for (size_t off = 0; off < n; off += c->max_batch) {
         size_t m = n - off < c->max_batch ? n - off : c->max_batch;
         SubPlan sp = plan_sub(c, m, SUB_HOST);
-        if (verify_one_part(c, m)) { sp.parts = 1; sp.lo[0] = 0; sp.lo[1] = m; c->active_parts = 1; }
+        if (verify_one_part(c, m)) {
+            // One part (segmented ladders want the GPU to themselves).  The records upload in four chunks on the copy stream and
+            // each chunk is decoded as it lands (the square roots of a chunk take longer than the next chunk's transfer), so only
+            // the first chunk's upload is exposed; everything after the decode runs over the whole part.
+            sp.parts = 1; sp.lo[0] = 0; sp.lo[1] = m; c->active_parts = 1;
+            cudaStream_t st = c->stream, cs = c->copy_stream;
+            WS w = sub_ws(c, sp, 0);
+            uint32_t *flags = w.p + (size_t)VL::IDMASK * w.n;
+            CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * m, st));
+            const int chunks = 4;
+            for (int q = 0; q < chunks; q++) {
+                size_t lo = m * q / chunks, cnt = m * (q + 1) / chunks - lo;
+                CUDA_OK(cudaMemcpyAsync(c->d_in_a + csz * lo, commits + csz * (off + lo), csz * cnt, cudaMemcpyHostToDevice, cs));
+                CUDA_OK(cudaMemcpyAsync(c->d_in_b + psz * lo, proofs + psz * (off + lo), psz * cnt, cudaMemcpyHostToDevice, cs));
+                CUDA_OK(cudaEventRecord(c->ev_up[q], cs));
+                CUDA_OK(cudaStreamWaitEvent(st, c->ev_up[q], 0));
+                LAUNCH(c, k_v_decode, nblocks(cnt * VP_COUNT, 128), 128, w, c->d_in_a, c->d_in_b, fmt, flags, lo, cnt);
+            }
+            int rc = verify_part(c, st, w, c->d_in_a, c->d_in_b, fmt, init, c->d_status, true);
+            if (rc != BPPP_OK) { cudaStreamSynchronize(cs); return rc; }
+            CUDA_OK(cudaMemcpyAsync(status + off, c->d_status, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, st));
+            CUDA_OK(cudaStreamSynchronize(cs));
+            CUDA_OK(cudaStreamSynchronize(st));
+            continue;
+        }
         for (int k = 0; k < sp.parts; k++) {
             cudaStream_t st = sp.parts == 1 ? c->stream : c->sub_stream[k];
             size_t lo = sp.lo[k], cnt = sp.lo[k + 1] - sp.lo[k];
@@ -191,7 +219,7 @@ extern "C" int bppp_u64_verify_begin(bppp_ctx *c, size_t n, const uint8_t *commi
     CUDA_OK(cudaMemcpyAsync(c->d_in_a, commits, csz * n, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(c->d_in_b, proofs, psz * n, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n, st));
-    LAUNCH(c, k_v_decode, nblocks(n * VP_COUNT, 128), 128, w, c->d_in_a, c->d_in_b, fmt, flags);
+    LAUNCH(c, k_v_decode, nblocks(n * VP_COUNT, 128), 128, w, c->d_in_a, c->d_in_b, fmt, flags, (size_t)0, n);
     LAUNCH(c, k_v_load_finish, nblocks(n, 64), 64, w, c->d_in_b, fmt, flags);
     launch_batch_inv(c, st, w, VL::VP + 2 * FE_W, VL::ZINV);
     EmitList L; L.n = 1; L.pt[0] = VL::VP; L.zinv[0] = VL::ZINV;     // V' = V + r: "commitment_v" (circuit.rs:159)
