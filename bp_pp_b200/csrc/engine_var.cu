@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(BPPP_VAR_BLOCK, BPPP_VAR_MINBLOCKS) k_p_var2(W
 // safe: the previous segment's ticket was drawn earlier by a warp that is running (or done).  The grid is this launch's share
 // of the GPU's warp slots, a little more than it has chains, so a chain continues on whichever warp frees first instead of
 // staying on the scheduler it started on, and concurrent sub-batches do not crowd each other out with waiting blocks.
-// sync: [0] ticket counter, [1] set if a wait ever timed out (~1 s; never in a correct run), [32 + g] segments done of chain g.
+// sync: [0] ticket counter, [1] set if a wait ever timed out (seconds; never in a correct run), [32 + g] segments done of chain g.
 template <int KIND>     // 0: five-point group (COM = ACC + ...), 1: two-point group of round j
 __global__ void __launch_bounds__(32, 16) k_v_var_seg(WS w, int j, int nseg, uint32_t *sync, int one_item) {
     const unsigned lane = threadIdx.x;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(32, 16) k_v_var_seg(WS w, int j, int nseg, uin
             unsigned spins = 0;
             while (*done < seg) {
                 __nanosleep(100);
-                if (++spins > (1u << 23)) {                       // fail loudly instead of hanging the GPU
+                if (++spins > (1u << 26)) {                       // several seconds: fail loudly instead of hanging the GPU
                     sync[1] = 1u;
                     if (i < w.n) ws_st(w, i, VL::STATUS, (uint32_t)ST_BAD_ARG);
                     return;
