@@ -123,7 +123,7 @@ static inline size_t tab_level_threads(const bppp_ctx *c, size_t items, int leve
 // A verification batch this large runs as ONE part with segmented ladders (engine_var.cu:k_v_var_seg) instead of two
 // sub-batches with whole ladders: 21.4 against 22.4 ms at 65,536 proofs (profiles/r2_kernel_experiments.txt #22).
 static inline bool verify_one_part(const bppp_ctx *c, size_t n) {
-    return c->var_seg > 1 && c->inflight_hint == 1 && !c->var_lanes_override && n >= 24576;
+    return c->var_seg > 1 && c->inflight_hint == 1 && !c->var_lanes_override && n >= 49152;     // measured at 65,536 only: smaller batches keep the two-part path
 }
 
 static inline TermMap identity_map() { TermMap tm; for (int t = 0; t < NUM_GENS; t++) tm.gen[t] = t; return tm; }
